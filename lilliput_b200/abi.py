@@ -1,0 +1,238 @@
+"""ctypes binding of the C ABI in include/lilliput_b200.h + include/lp_opencv.h.
+
+The same `Lib` class binds either library:
+
+* ``lilliput_b200/liblilliput_b200.so`` -- the product: sm_100a CUDA kernels
+  behind lilliput's cgo surface.  `load_cuda()` fails loudly if it is missing
+  or no CUDA device can be initialised; there is no CPU fallback.
+* ``oracle/_ref/libref_oracle.so`` -- the reference's own shims (test
+  infrastructure; see oracle/Makefile).  Only tests/, __graft_entry__.smoke()
+  and bench.py's CPU-baseline legs may load it.
+
+Function names mirror the reference API they stand for (ref ops.go / opencv.go).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_LIB = os.path.join(ROOT, "lilliput_b200", "liblilliput_b200.so")
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
+
+# ImageOpsSizeMethod, ref ops.go:17-22
+ImageOpsNoResize, ImageOpsFit, ImageOpsResize = 0, 1, 2
+# encoder option keys, ref opencv.hpp:33-36 / opencv.go:62-70
+JpegQuality, JpegProgressive, PngCompression, WebpQuality = 1, 2, 16, 64
+# OpenCV pixel types
+CV_8UC1, CV_8UC3, CV_8UC4 = 0, 16, 24
+INTER_LINEAR, INTER_CUBIC, INTER_AREA = 1, 2, 3
+
+LP_ERRORS = {
+    0: "ok", -1: "ErrInvalidImage", -2: "ErrDecodingFailed", -3: "ErrBufTooSmall",
+    -4: "ErrFrameBufNoPixels", -5: "ErrSkipNotSupported", -6: "ErrEncodeTimeout", -7: "EOF",
+    -8: "unsupported", -9: "cuda", -10: "bad argument",
+}
+
+
+class LilliputError(RuntimeError):
+    def __init__(self, code: int):
+        self.code = code
+        super().__init__(LP_ERRORS.get(code, f"lp_status {code}"))
+
+
+class _ImageOptions(C.Structure):
+    _fields_ = [
+        ("file_type", C.c_char_p), ("width", C.c_int), ("height", C.c_int),
+        ("resize_method", C.c_int), ("normalize_orientation", C.c_int),
+        ("encode_options", C.POINTER(C.c_int)), ("encode_options_len", C.c_size_t),
+        ("max_encode_frames", C.c_int), ("max_encode_duration_ns", C.c_int64),
+        ("encode_timeout_ns", C.c_int64), ("disable_animated_output", C.c_int),
+        ("force_sdr", C.c_int),
+    ]
+
+
+class _BatchConfig(C.Structure):
+    _fields_ = [
+        ("device", C.c_int), ("max_images", C.c_int), ("src_width", C.c_int),
+        ("src_height", C.c_int), ("dst_width", C.c_int), ("dst_height", C.c_int),
+        ("resize_method", C.c_int), ("jpeg_quality", C.c_int), ("max_in_bytes", C.c_size_t),
+        ("out_cap", C.c_size_t), ("chunk", C.c_int),
+    ]
+
+
+@dataclass
+class ImageOptions:
+    """Mirror of lilliput.ImageOptions (ref ops.go:26-65)."""
+    FileType: str = ".jpeg"
+    Width: int = 0
+    Height: int = 0
+    ResizeMethod: int = ImageOpsNoResize
+    NormalizeOrientation: bool = False
+    EncodeOptions: dict = field(default_factory=dict)
+    MaxEncodeFrames: int = 0
+    MaxEncodeDuration_ns: int = 0
+    EncodeTimeout_ns: int = 0
+    DisableAnimatedOutput: bool = False
+    ForceSdr: bool = False
+
+    def _c(self):
+        flat = []
+        for k, v in self.EncodeOptions.items():
+            flat += [int(k), int(v)]
+        arr = (C.c_int * max(1, len(flat)))(*flat)
+        o = _ImageOptions(self.FileType.encode(), self.Width, self.Height, self.ResizeMethod,
+                          int(self.NormalizeOrientation), arr, len(flat), self.MaxEncodeFrames,
+                          self.MaxEncodeDuration_ns, self.EncodeTimeout_ns,
+                          int(self.DisableAnimatedOutput), int(self.ForceSdr))
+        o._keep = arr
+        return o
+
+
+def _u8p(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+class Lib:
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        self.path = path
+        self.l = C.CDLL(path, mode=getattr(os, "RTLD_LOCAL", 0) | getattr(os, "RTLD_NOW", 2))
+        l = self.l
+        l.lp_backend_name.restype = C.c_char_p
+        l.lp_transform.restype = C.c_int
+        l.lp_transform.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(_ImageOptions), C.c_void_p,
+                                   C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
+        l.lp_decode_host.restype = C.c_int
+        l.lp_decode_host.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t] + \
+            [C.POINTER(C.c_int)] * 4
+        l.lp_fit_host.restype = C.c_int
+        l.lp_fit_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                  C.c_int]
+        l.lp_resize_host.restype = C.c_int
+        l.lp_resize_host.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p] + [C.c_int] * 3
+        l.lp_encode_host.restype = C.c_int
+        l.lp_encode_host.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_int), C.c_size_t, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_size_t)]
+        l.lp_orient_host.restype = C.c_int
+        l.lp_orient_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self.backend = l.lp_backend_name().decode()
+
+    # --- whole path: NewDecoder + ImageOps.Transform (ref ops.go:352) -------------------
+    def transform(self, data: bytes, opt: ImageOptions, dst_cap: int = 8 << 20,
+                  max_size: int = 8192) -> bytes:
+        src = np.frombuffer(data, dtype=np.uint8)
+        dst = np.empty(dst_cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        o = opt._c()
+        rc = self.l.lp_transform(src.ctypes.data, src.size, C.byref(o), dst.ctypes.data, dst.size,
+                                 C.byref(n), max_size)
+        if rc != 0:
+            raise LilliputError(rc)
+        return dst[: n.value].tobytes()
+
+    # --- stages ---------------------------------------------------------------------
+    def header(self, data: bytes):
+        src = np.frombuffer(data, dtype=np.uint8)
+        w, h, t, o = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rc = self.l.lp_decode_host(src.ctypes.data, src.size, None, 0, C.byref(w), C.byref(h),
+                                   C.byref(t), C.byref(o))
+        if rc != 0:
+            raise LilliputError(rc)
+        return w.value, h.value, t.value, o.value
+
+    def decode(self, data: bytes) -> np.ndarray:
+        """openCVDecoder.DecodeTo (ref opencv.go:816): packed BGR/BGRA/Gray u8."""
+        w0, h0, t0, _ = self.header(data)
+        src = np.frombuffer(data, dtype=np.uint8)
+        ch = ((t0 >> 3) & 63) + 1
+        px = np.empty(h0 * w0 * ch, dtype=np.uint8)
+        w, h, t, o = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rc = self.l.lp_decode_host(src.ctypes.data, src.size, px.ctypes.data, px.size, C.byref(w),
+                                   C.byref(h), C.byref(t), C.byref(o))
+        if rc != 0:
+            raise LilliputError(rc)
+        return px.reshape(h.value, w.value, ch) if ch > 1 else px.reshape(h.value, w.value)
+
+    @staticmethod
+    def _type_of(img: np.ndarray) -> int:
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        return (ch - 1) << 3
+
+    def fit(self, img: np.ndarray, w: int, h: int) -> np.ndarray:
+        """Framebuffer.Fit (ref opencv.go:326)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        dst = np.empty((h, w, ch) if ch > 1 else (h, w), dtype=np.uint8)
+        rc = self.l.lp_fit_host(img.ctypes.data, img.shape[1], img.shape[0], self._type_of(img),
+                                dst.ctypes.data, w, h)
+        if rc != 0:
+            raise LilliputError(rc)
+        return dst
+
+    def resize(self, img: np.ndarray, w: int, h: int, crop=None, interpolation=INTER_AREA):
+        """opencv_mat_resize on an opencv_mat_crop view (ref opencv.cpp:196-215)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        cx, cy, cw, chh = crop if crop else (0, 0, img.shape[1], img.shape[0])
+        dst = np.empty((h, w, ch) if ch > 1 else (h, w), dtype=np.uint8)
+        rc = self.l.lp_resize_host(img.ctypes.data, img.shape[1], img.shape[0], self._type_of(img),
+                                   cx, cy, cw, chh, dst.ctypes.data, w, h, interpolation)
+        if rc != 0:
+            raise LilliputError(rc)
+        return dst
+
+    def encode(self, ext: str, img: np.ndarray, opts: dict | None = None,
+               dst_cap: int = 0) -> bytes:
+        """openCVEncoder.Encode (ref opencv.go:872)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        flat = []
+        for k, v in (opts or {}).items():
+            flat += [int(k), int(v)]
+        arr = (C.c_int * max(1, len(flat)))(*flat)
+        cap = dst_cap or (img.size * 2 + (1 << 16))
+        dst = np.empty(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        rc = self.l.lp_encode_host(ext.encode(), img.ctypes.data, img.shape[1], img.shape[0],
+                                   self._type_of(img), arr, len(flat), dst.ctypes.data, dst.size,
+                                   C.byref(n))
+        if rc != 0:
+            raise LilliputError(rc)
+        return dst[: n.value].tobytes()
+
+    def orient(self, img: np.ndarray, orientation: int) -> np.ndarray:
+        """Framebuffer.OrientationTransform (ref opencv.go:271)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        dst = np.empty(img.size, dtype=np.uint8)
+        ow, oh = C.c_int(), C.c_int()
+        rc = self.l.lp_orient_host(img.ctypes.data, img.shape[1], img.shape[0],
+                                   self._type_of(img), orientation, dst.ctypes.data,
+                                   C.byref(ow), C.byref(oh))
+        if rc != 0:
+            raise LilliputError(rc)
+        return dst.reshape(oh.value, ow.value, ch) if ch > 1 else dst.reshape(oh.value, ow.value)
+
+
+_cache: dict[str, Lib] = {}
+
+
+def load_cuda() -> Lib:
+    """The product library.  Raises if it was not built -- never falls back."""
+    if "cuda" not in _cache:
+        _cache["cuda"] = Lib(CUDA_LIB)
+    return _cache["cuda"]
+
+
+def load_reference() -> Lib:
+    """oracle/_ref (reference shims).  Test/baseline infrastructure only."""
+    if "ref" not in _cache:
+        _cache["ref"] = Lib(REF_LIB)
+    return _cache["ref"]

@@ -1,0 +1,711 @@
+// lilliput_host.cpp -- C++ mirror of lilliput's Go policy layer (see header).
+// Every function cites the Go it follows.  No pixel arithmetic happens here:
+// all of it is behind the per-image C ABI (lp_opencv.h).
+#include "lilliput_host.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+namespace lilliput {
+
+// ---------------------------------------------------------------- Framebuffer
+
+Framebuffer::Framebuffer(int w, int h) : buf((size_t)w * (size_t)h * 4) {}
+
+Framebuffer::~Framebuffer() { Close(); }
+
+void Framebuffer::Close() {
+    if (mat) {
+        opencv_mat_release(mat);
+        mat = nullptr;
+    }
+}
+
+// ref opencv.go:223-228: memset the Go slice, then reset the mat.
+void Framebuffer::Clear() {
+    if (!buf.empty()) memset(buf.data(), 0, buf.size());
+    if (mat) opencv_mat_reset(mat);
+}
+
+Error Framebuffer::Create3Channel(int w, int h) {
+    Error e = resizeMat(w, h, PixelType{CV_8UC3});
+    if (e) return e;
+    Clear();
+    return LP_OK;
+}
+
+Error Framebuffer::Create4Channel(int w, int h) {
+    Error e = resizeMat(w, h, PixelType{CV_8UC4});
+    if (e) return e;
+    Clear();
+    return LP_OK;
+}
+
+// ref opencv.go:250-267: release the old mat, coerce depth > 8 to 8U keeping
+// the channel count, wrap buf; NULL from the C side means ErrBufTooSmall.
+Error Framebuffer::resizeMat(int w, int h, PixelType t) {
+    if (mat) {
+        opencv_mat_release(mat);
+        mat = nullptr;
+    }
+    if (t.Depth() > 8) t.v = opencv_type_convert_depth(t.v, CV_8U);
+    opencv_mat m = opencv_mat_create_from_data(w, h, t.v, buf.data(), buf.size());
+    if (!m) return LP_ERR_BUF_TOO_SMALL;
+    mat = m;
+    width = w;
+    height = h;
+    pixelType = t;
+    return LP_OK;
+}
+
+// ref opencv.go:271-279: dims are re-read from the mat afterwards (SURVEY
+// Appendix C quirk 7 depends on this refresh).
+void Framebuffer::OrientationTransform(int orientation) {
+    if (!mat) return;
+    opencv_mat_orientation_transform((CVImageOrientation)orientation, mat);
+    width = opencv_mat_get_width(mat);
+    height = opencv_mat_get_height(mat);
+}
+
+// ref opencv.go:294-309
+Error Framebuffer::ResizeTo(int w, int h, Framebuffer* dst) {
+    if (w < 1) w = 1;
+    if (h < 1) h = 1;
+    Error e = dst->resizeMat(w, h, pixelType);
+    if (e) return e;
+    opencv_mat_resize(mat, dst->mat, w, h, CV_INTER_AREA);
+    return LP_OK;
+}
+
+static Error handleOpenCVError(int rc) {  // ref opencv.go:399-426
+    return rc == OPENCV_SUCCESS ? LP_OK : (LP_ERR_OPENCV - rc);
+}
+
+// ref opencv.go:312-319
+Error Framebuffer::ClearToTransparent(int x, int y, int w, int h) {
+    if (!mat) return LP_ERR_FRAMEBUF_NO_PIXELS;
+    return handleOpenCVError(opencv_mat_clear_to_transparent(mat, x, y, w, h));
+}
+
+// ref opencv.go:331-363.  float64 arithmetic, int() truncation as in Go.
+void fitCropRect(int srcW, int srcH, int dstW, int dstH, int* left, int* top, int* wc, int* hc) {
+    double aspectIn = (double)srcW / (double)srcH;
+    double aspectOut = (double)dstW / (double)dstH;
+    int widthPostCrop, heightPostCrop;
+    if (aspectIn > aspectOut) {
+        widthPostCrop = (int)((aspectOut * (double)srcH) + 0.5);
+        heightPostCrop = srcH;
+    } else {
+        heightPostCrop = (int)(((double)srcW / aspectOut) + 0.5);
+        widthPostCrop = srcW;
+    }
+    if (widthPostCrop < 1) widthPostCrop = 1;
+    if (heightPostCrop < 1) heightPostCrop = 1;
+    int l = (int)((double)(srcW - widthPostCrop) * 0.5);
+    if (l < 0) l = 0;
+    int t = (int)((double)(srcH - heightPostCrop) * 0.5);
+    if (t < 0) t = 0;
+    *left = l;
+    *top = t;
+    *wc = widthPostCrop;
+    *hc = heightPostCrop;
+}
+
+// ref opencv.go:326-374
+Error Framebuffer::Fit(int w, int h, Framebuffer* dst) {
+    if (!mat) return LP_ERR_FRAMEBUF_NO_PIXELS;
+    int left, top, wc, hc;
+    fitCropRect(width, height, w, h, &left, &top, &wc, &hc);
+    opencv_mat view = opencv_mat_crop(mat, left, top, wc, hc);
+    Error e = dst->resizeMat(w, h, pixelType);
+    if (e) {
+        opencv_mat_release(view);
+        return e;
+    }
+    opencv_mat_resize(view, dst->mat, w, h, CV_INTER_AREA);
+    opencv_mat_release(view);
+    return LP_OK;
+}
+
+Error Framebuffer::CopyToOffsetWithAlphaBlending(Framebuffer* src, int x, int y, int w, int h) {
+    return handleOpenCVError(opencv_copy_to_region_with_alpha(src->mat, mat, x, y, w, h));
+}
+
+Error Framebuffer::CopyToOffsetNoBlend(Framebuffer* src, int x, int y, int w, int h) {
+    return handleOpenCVError(opencv_copy_to_region(src->mat, mat, x, y, w, h));
+}
+
+// ------------------------------------------------ container sniffers (host)
+
+static inline uint32_t be32(const uint8_t* p) {
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+}
+static const uint8_t kPngMagic[8] = {0x89, 0x50, 0x4e, 0x47, 0x0d, 0x0a, 0x1a, 0x0a};
+
+// Walks PNG chunks the way pngChunkIter does (ref opencv.go:467-511): a chunk
+// is visited when its 12 framing bytes fit, even if its body is truncated.
+template <class F>
+static void walkPngChunks(const uint8_t* png, size_t len, F&& visit) {
+    if (len < 8 || memcmp(png, kPngMagic, 8) != 0) return;
+    size_t off = 8;
+    while (off + 12 <= len) {
+        size_t next = off + (size_t)be32(png + off) + 12;
+        if (!visit(png + off + 4, next)) return;
+        off = next;
+    }
+}
+
+bool detectAPNG(const uint8_t* img, size_t len) {  // ref opencv.go:623-637
+    bool found = false;
+    walkPngChunks(img, len, [&](const uint8_t* type, size_t) {
+        if (!memcmp(type, "acTL", 4) || !memcmp(type, "fcTL", 4) || !memcmp(type, "fdAT", 4)) {
+            found = true;
+            return false;
+        }
+        return true;
+    });
+    return found;
+}
+
+static int detectContentLengthPNG(const uint8_t* png, size_t len) {  // ref opencv.go:513-531
+    int result = (int)len;
+    walkPngChunks(png, len, [&](const uint8_t* type, size_t next) {
+        if (!memcmp(type, "IEND", 4)) {
+            result = (int)std::min(next, len);
+            return false;
+        }
+        return true;
+    });
+    return result;
+}
+
+// ref opencv.go:533-609: walk marker segments; inside entropy-coded data skip
+// to the first 0xFF that is followed by neither 0x00, 0xFF nor RSTn.
+static int detectContentLengthJPEG(const uint8_t* j, size_t len) {
+    if (len < 3 || j[0] != 0xFF || j[1] != 0xD8 || j[2] != 0xFF) return (int)len;
+    size_t idx = 0;
+    while (idx + 1 < len && j[idx] == 0xFF) {
+        uint8_t seg = j[idx + 1];
+        size_t next = idx + 2;
+        if (seg == 0xD9) return (int)next;
+        if (seg == 0xFF) {
+            idx++;
+            continue;
+        }
+        bool unsized = seg == 0x01 || seg == 0xD8 || (seg >= 0xD0 && seg <= 0xD7);
+        if (unsized) {
+            idx = next;
+            continue;
+        }
+        if (idx + 3 >= len) break;
+        next += ((size_t)j[idx + 2] << 8) | j[idx + 3];
+        if (seg == 0xDA) {
+            for (; next < len; next++) {
+                if (j[next] != 0xFF) continue;
+                if (next + 1 >= len) {
+                    next = len;
+                    break;
+                }
+                uint8_t peek = j[next + 1];
+                if (peek == 0xFF) continue;
+                if (peek != 0 && (peek < 0xD0 || peek > 0xD7)) break;
+            }
+        }
+        idx = next;
+    }
+    return (int)len;
+}
+
+int detectContentLength(const uint8_t* img, size_t len) {  // ref opencv.go:611-620
+    return std::min(detectContentLengthJPEG(img, len), detectContentLengthPNG(img, len));
+}
+
+// ------------------------------------------------------------ OpenCV adapter
+
+class OpenCVDecoder : public Decoder {  // ref opencv.go:131-137, 442-463
+  public:
+    static Error Create(const uint8_t* buf, size_t len, std::unique_ptr<Decoder>* out) {
+        opencv_mat m = opencv_mat_create_from_data((int)len, 1, CV_8U, (void*)buf, len);
+        if (!m) return LP_ERR_BUF_TOO_SMALL;
+        opencv_decoder d = opencv_decoder_create(m);
+        if (!d) {
+            opencv_mat_release(m);
+            return LP_ERR_INVALID_IMAGE;
+        }
+        auto* self = new OpenCVDecoder;
+        self->mat = m;
+        self->decoder = d;
+        self->buf = buf;
+        self->len = len;
+        out->reset(self);
+        return LP_OK;
+    }
+    ~OpenCVDecoder() override {
+        opencv_decoder_release(decoder);
+        opencv_mat_release(mat);
+    }
+    Error Header(ImageHeader* h) override {  // ref opencv.go:639-661
+        if (!hasReadHeader && !opencv_decoder_read_header(decoder)) return LP_ERR_INVALID_IMAGE;
+        hasReadHeader = true;
+        h->width = opencv_decoder_get_width(decoder);
+        h->height = opencv_decoder_get_height(decoder);
+        h->pixelType.v = opencv_decoder_get_pixel_type(decoder);
+        h->orientation = opencv_decoder_get_orientation(decoder);
+        h->numFrames = detectAPNG(buf, len) ? 2 : 1;
+        h->contentLength = detectContentLength(buf, len);
+        return LP_OK;
+    }
+    std::string Description() override {
+        const char* s = opencv_decoder_get_description(decoder);
+        return s ? s : "";
+    }
+    Error DecodeTo(Framebuffer* f) override {  // ref opencv.go:816-839
+        if (hasDecoded) return LP_ERR_EOF;
+        ImageHeader h;
+        Error e = Header(&h);
+        if (e) return e;
+        e = f->resizeMat(h.width, h.height, h.pixelType);
+        if (e) return e;
+        if (!opencv_decoder_read_data(decoder, f->mat)) return LP_ERR_DECODING_FAILED;
+        hasDecoded = true;
+        f->blend = NoBlend;
+        f->dispose = DisposeToBackgroundColor;
+        f->xOffset = 0;
+        f->yOffset = 0;
+        f->duration_ns = 0;
+        return LP_OK;
+    }
+    Error SkipFrame() override { return LP_ERR_SKIP_NOT_SUPPORTED; }  // ref opencv.go:841-843
+    std::vector<uint8_t> ICC() override {  // ref opencv.go:691-728
+        std::vector<uint8_t> icc(32768);  // ICCProfileBufferSize, ref lilliput.go:15
+        std::string d = Description();
+        int n = 0;
+        if (d == "JPEG")
+            n = opencv_decoder_get_jpeg_icc((void*)buf, len, icc.data(), icc.size());
+        else if (d == "PNG")
+            n = opencv_decoder_get_png_icc((void*)buf, len, icc.data(), icc.size());
+        icc.resize(n > 0 ? n : 0);
+        return icc;
+    }
+
+  private:
+    opencv_mat mat = nullptr;
+    opencv_decoder decoder = nullptr;
+    const uint8_t* buf = nullptr;
+    size_t len = 0;
+    bool hasReadHeader = false, hasDecoded = false;
+};
+
+class OpenCVEncoder : public Encoder {  // ref opencv.go:139-144, 847-905
+  public:
+    static Error Create(const std::string& ext, uint8_t* dst, size_t cap,
+                        std::unique_ptr<Encoder>* out) {
+        if (cap < 1) return LP_ERR_BUF_TOO_SMALL;
+        opencv_mat m = opencv_mat_create_empty_from_data((int)cap, dst);
+        if (!m) return LP_ERR_BUF_TOO_SMALL;
+        opencv_encoder e = opencv_encoder_create(ext.c_str(), m);
+        if (!e) {
+            opencv_mat_release(m);
+            return LP_ERR_INVALID_IMAGE;
+        }
+        auto* self = new OpenCVEncoder;
+        self->encoder = e;
+        self->dst = m;
+        self->dstBuf = dst;
+        out->reset(self);
+        return LP_OK;
+    }
+    ~OpenCVEncoder() override {
+        opencv_encoder_release(encoder);
+        opencv_mat_release(dst);
+    }
+    Error Encode(Framebuffer* f, const std::map<int, int>& opt, bool* content,
+                 size_t* out_len) override {  // ref opencv.go:872-900
+        *content = false;
+        if (!f) return LP_ERR_EOF;
+        std::vector<int> optList;
+        for (auto& kv : opt) {
+            optList.push_back(kv.first);
+            optList.push_back(kv.second);
+        }
+        if (!opencv_encoder_write(encoder, f->mat, optList.empty() ? nullptr : optList.data(),
+                                  optList.size()))
+            return LP_ERR_INVALID_IMAGE;
+        // overflow is signalled by the destination mat having moved off dstBuf
+        if (opencv_mat_get_data(dst) != (void*)dstBuf) return LP_ERR_BUF_TOO_SMALL;
+        *out_len = (size_t)opencv_mat_get_height(dst);  // rows == encoded length
+        *content = true;
+        return LP_OK;
+    }
+
+  private:
+    opencv_encoder encoder = nullptr;
+    opencv_mat dst = nullptr;
+    uint8_t* dstBuf = nullptr;
+};
+
+static std::string lower(std::string s) {
+    for (auto& c : s) c = (char)tolower((unsigned char)c);
+    return s;
+}
+
+// ref lilliput.go:129-164.  GIF / WebP / AVIF / video are routed away BEFORE the
+// OpenCV adapter is tried; until those adapters exist on the device they are
+// reported as LP_ERR_UNSUPPORTED rather than silently mis-decoded.
+Error NewDecoder(const uint8_t* buf, size_t len, std::unique_ptr<Decoder>* out) {
+    if (len == 0) return LP_ERR_INVALID_IMAGE;
+    if (len >= 6 && (!memcmp(buf, "GIF87a", 6) || !memcmp(buf, "GIF89a", 6)))
+        return LP_ERR_UNSUPPORTED;
+    if (len >= 12 && !memcmp(buf, "RIFF", 4) && !memcmp(buf + 8, "WEBP", 4))
+        return LP_ERR_UNSUPPORTED;
+    if (len >= 12 && !memcmp(buf + 4, "ftyp", 4) &&
+        (!memcmp(buf + 8, "avif", 4) || !memcmp(buf + 8, "avis", 4)))
+        return LP_ERR_UNSUPPORTED;
+    return OpenCVDecoder::Create(buf, len, out);
+}
+
+// ref lilliput.go:180-202
+Error NewEncoder(const std::string& ext_, Decoder*, uint8_t* dst, size_t cap,
+                 std::unique_ptr<Encoder>* out) {
+    std::string ext = lower(ext_);
+    if (ext == ".gif" || ext == ".webp" || ext == ".avif" || ext == ".thumbhash")
+        return LP_ERR_UNSUPPORTED;
+    if (ext == ".mp4" || ext == ".webm") return LP_ERR_INVALID_IMAGE;
+    return OpenCVEncoder::Create(ext_, dst, cap, out);
+}
+
+// ------------------------------------------------------------------ ImageOps
+
+void calculateExpectedSize(int ow, int oh, int rw, int rh, int* w, int* h) {  // ref ops.go:243-255
+    int m = std::min(ow, oh);
+    if (rw == rh && rw > m) {
+        *w = m;
+        *h = m;
+    } else if (rw > ow && rh > oh && rw != rh) {
+        *w = ow;
+        *h = oh;
+    } else {
+        *w = rw;
+        *h = rh;
+    }
+}
+
+ImageOps::ImageOps(int maxSize_) : maxSize(maxSize_) {
+    frames[0].reset(new Framebuffer(maxSize, maxSize));
+    frames[1].reset(new Framebuffer(maxSize, maxSize));
+}
+
+void ImageOps::Clear() {
+    frames[0]->Clear();
+    frames[1]->Clear();
+    if (animatedCompositeBuffer) animatedCompositeBuffer->Clear();
+}
+
+Error ImageOps::decode(Decoder* d) { return d->DecodeTo(active()); }  // ref ops.go:154-165
+
+// ref ops.go:132-150
+Error ImageOps::setupAnimatedFrameBuffers(Decoder*, int icw, int ich, bool alpha) {
+    if (animatedCompositeBuffer) return LP_OK;
+    animatedCompositeBuffer.reset(new Framebuffer(icw, ich));
+    Error e = alpha ? animatedCompositeBuffer->Create4Channel(icw, ich)
+                    : animatedCompositeBuffer->Create3Channel(icw, ich);
+    if (e) return e;
+    return animatedCompositeBuffer->ClearToTransparent(0, 0, icw, ich);
+}
+
+Error ImageOps::applyDisposeMethod() {  // ref ops.go:552-562
+    Framebuffer* a = active();
+    if (a->dispose == DisposeToBackgroundColor)
+        return animatedCompositeBuffer->ClearToTransparent(a->xOffset, a->yOffset, a->Width(),
+                                                           a->Height());
+    return LP_OK;
+}
+
+Error ImageOps::applyBlendMethod() {  // ref ops.go:566-582
+    Framebuffer* a = active();
+    if (a->blend == UseAlphaBlending)
+        return animatedCompositeBuffer->CopyToOffsetWithAlphaBlending(a, a->xOffset, a->yOffset,
+                                                                      a->Width(), a->Height());
+    return animatedCompositeBuffer->CopyToOffsetNoBlend(a, a->xOffset, a->yOffset, a->Width(),
+                                                        a->Height());
+}
+
+void ImageOps::copyFramePropertiesAndSwap() {  // ref ops.go:586-591
+    secondary()->duration_ns = active()->duration_ns;
+    secondary()->dispose = active()->dispose;
+    secondary()->blend = active()->blend;
+    swap();
+}
+
+// ref ops.go:170-204
+Error ImageOps::fit(Decoder* d, int icw, int ich, int ocw, int och, bool animated, bool alpha) {
+    int nw, nh;
+    calculateExpectedSize(icw, ich, ocw, och, &nw, &nh);
+    Error e;
+    if (animated) {
+        if ((e = setupAnimatedFrameBuffers(d, icw, ich, alpha))) return e;
+        if ((e = applyBlendMethod())) return e;
+        if ((e = animatedCompositeBuffer->Fit(nw, nh, secondary()))) return e;
+        if ((e = applyDisposeMethod())) return e;
+        copyFramePropertiesAndSwap();
+        return LP_OK;
+    }
+    if ((e = active()->Fit(nw, nh, secondary()))) return e;
+    copyFramePropertiesAndSwap();
+    return LP_OK;
+}
+
+// ref ops.go:208-238
+Error ImageOps::resize(Decoder* d, int icw, int ich, int ocw, int och, bool animated, bool alpha) {
+    Error e;
+    if (animated) {
+        if ((e = setupAnimatedFrameBuffers(d, icw, ich, alpha))) return e;
+        if ((e = applyBlendMethod())) return e;
+        if ((e = animatedCompositeBuffer->ResizeTo(ocw, och, secondary()))) return e;
+        if ((e = applyDisposeMethod())) return e;
+        copyFramePropertiesAndSwap();
+        return LP_OK;
+    }
+    if ((e = active()->ResizeTo(ocw, och, secondary()))) return e;
+    copyFramePropertiesAndSwap();
+    return LP_OK;
+}
+
+// ref ops.go:449-470 (+ inputCanvasSize :474-479)
+Error ImageOps::transformCurrentFrame(Decoder* d, const ImageOptions& opt, const ImageHeader& h,
+                                      int, bool* swapped) {
+    *swapped = false;
+    if (opt.ResizeMethod == LP_OPS_NO_RESIZE && !h.IsAnimated()) return LP_OK;
+    int iw = h.width, ih = h.height;
+    if (opt.NormalizeOrientation && ImageHeader::SwapsAxes(h.orientation)) std::swap(iw, ih);
+    int ow = opt.Width, oh = opt.Height;
+    if (opt.ResizeMethod == LP_OPS_NO_RESIZE) {
+        ow = iw;
+        oh = ih;
+    }
+    Error e;
+    switch (opt.ResizeMethod) {
+        case LP_OPS_FIT:
+        case LP_OPS_NO_RESIZE:
+            e = fit(d, iw, ih, ow, oh, h.IsAnimated(), h.HasAlpha());
+            break;
+        case LP_OPS_RESIZE:
+            e = resize(d, iw, ih, ow, oh, h.IsAnimated(), h.HasAlpha());
+            break;
+        default:
+            return LP_ERR_BAD_ARGUMENT;
+    }
+    if (!e) *swapped = true;
+    return e;
+}
+
+Error ImageOps::skipToEnd(Decoder* d) {  // ref ops.go:336-344
+    for (;;) {
+        Error e = d->SkipFrame();
+        if (e) return e;
+    }
+}
+
+// ref ops.go:352-444.  Differences from the Go are only the ones the scope
+// table excludes: no HDR tone-map / cICP policy.
+Error ImageOps::Transform(Decoder* d, const ImageOptions& opt, uint8_t* dst, size_t dst_cap,
+                          size_t* out_len) {
+    struct CompositeGuard {  // the deferred close at ops.go:353-358
+        std::unique_ptr<Framebuffer>& p;
+        ~CompositeGuard() { p.reset(); }
+    } guard{animatedCompositeBuffer};
+
+    *out_len = 0;
+    ImageHeader h;
+    Error e = d->Header(&h);
+    if (e) return e;
+    std::unique_ptr<Encoder> enc;
+    if ((e = NewEncoder(opt.FileType, d, dst, dst_cap, &enc))) return e;
+
+    int frameCount = 0;
+    int64_t duration = 0;
+    auto deadline =
+        std::chrono::steady_clock::now() + std::chrono::nanoseconds(opt.EncodeTimeout_ns);
+    auto encodeEmpty = [&](size_t* n) -> Error {
+        bool content = false;
+        Error ee = enc->Encode(nullptr, opt.EncodeOptions, &content, n);
+        if (ee == LP_OK && !content) *n = 0;
+        return ee;
+    };
+
+    for (;;) {
+        e = decode(d);
+        bool emptyFrame = false;
+        if (e) {
+            if (e != LP_ERR_EOF) return e;
+            emptyFrame = true;
+        }
+        duration += active()->duration_ns;
+        if (opt.MaxEncodeDuration_ns != 0 && duration > opt.MaxEncodeDuration_ns) {
+            e = skipToEnd(d);
+            if (e != LP_ERR_EOF) return e;
+            return encodeEmpty(out_len);
+        }
+        // applied on EVERY iteration, regardless of NormalizeOrientation (ops.go:392)
+        active()->OrientationTransform(h.orientation);
+
+        bool swapped = false;
+        if (!emptyFrame) {
+            if ((e = transformCurrentFrame(d, opt, h, frameCount, &swapped))) return e;
+        }
+        bool content = false;
+        size_t n = 0;
+        if (emptyFrame)
+            e = enc->Encode(nullptr, opt.EncodeOptions, &content, &n);
+        else
+            e = enc->Encode(active(), opt.EncodeOptions, &content, &n);
+        if (e) return e;
+        if (content) {
+            *out_len = n;
+            return LP_OK;
+        }
+        frameCount++;
+        if (opt.DisableAnimatedOutput) return encodeEmpty(out_len);
+        if (opt.MaxEncodeFrames != 0 && frameCount == opt.MaxEncodeFrames) {
+            e = skipToEnd(d);
+            if (e != LP_ERR_EOF) return e;
+            return encodeEmpty(out_len);
+        }
+        if (std::chrono::steady_clock::now() > deadline) return LP_ERR_ENCODE_TIMEOUT;
+        if (swapped) swap();
+    }
+}
+
+}  // namespace lilliput
+
+// ------------------------------------------------------------------- C entry
+
+using namespace lilliput;
+
+static ImageOptions fromC(const lp_image_options* o) {
+    ImageOptions r;
+    r.FileType = o->file_type ? o->file_type : "";
+    r.Width = o->width;
+    r.Height = o->height;
+    r.ResizeMethod = o->resize_method;
+    r.NormalizeOrientation = o->normalize_orientation != 0;
+    for (size_t i = 0; i + 1 < o->encode_options_len; i += 2)
+        r.EncodeOptions[o->encode_options[i]] = o->encode_options[i + 1];
+    r.MaxEncodeFrames = o->max_encode_frames;
+    r.MaxEncodeDuration_ns = o->max_encode_duration_ns;
+    r.EncodeTimeout_ns = o->encode_timeout_ns;
+    r.DisableAnimatedOutput = o->disable_animated_output != 0;
+    r.ForceSdr = o->force_sdr != 0;
+    return r;
+}
+
+extern "C" int lp_transform(const uint8_t* in, size_t in_len, const lp_image_options* opt,
+                            uint8_t* dst, size_t dst_cap, size_t* out_len, int max_size) {
+    if (!in || !opt || !dst || !out_len) return LP_ERR_BAD_ARGUMENT;
+    std::unique_ptr<Decoder> d;
+    Error e = NewDecoder(in, in_len, &d);
+    if (e) return e;
+    // One ImageOps per calling thread, reused across calls like a long-lived
+    // Go ImageOps (ref ops.go:83-91); re-created if max_size changes.
+    thread_local std::unique_ptr<ImageOps> ops;
+    thread_local int ops_size = 0;
+    if (!ops || ops_size != max_size) {
+        ops.reset(new ImageOps(max_size));
+        ops_size = max_size;
+    }
+    return ops->Transform(d.get(), fromC(opt), dst, dst_cap, out_len);
+}
+
+extern "C" int lp_decode_host(const uint8_t* in, size_t in_len, uint8_t* pixels,
+                              size_t pixels_cap, int* width, int* height, int* type,
+                              int* orientation) {
+    std::unique_ptr<Decoder> d;
+    Error e = NewDecoder(in, in_len, &d);
+    if (e) return e;
+    ImageHeader h;
+    if ((e = d->Header(&h))) return e;
+    if (width) *width = h.width;
+    if (height) *height = h.height;
+    if (type) *type = h.pixelType.v;
+    if (orientation) *orientation = h.orientation;
+    if (!pixels) return LP_OK;
+    PixelType t = h.pixelType;
+    if (t.Depth() > 8) t.v = opencv_type_convert_depth(t.v, CV_8U);
+    if (type) *type = t.v;
+    size_t need = (size_t)h.width * h.height * t.Channels();
+    if (need > pixels_cap) return LP_ERR_BUF_TOO_SMALL;
+    int side = std::max(h.width, h.height);
+    Framebuffer f(side, side);
+    if ((e = d->DecodeTo(&f))) return e;
+    if (lp_mat_sync_host(f.mat)) return LP_ERR_CUDA;
+    memcpy(pixels, opencv_mat_get_data(f.mat), need);
+    return LP_OK;
+}
+
+static Error wrapPixels(Framebuffer& f, const uint8_t* src, int w, int h, int type) {
+    Error e = f.resizeMat(w, h, PixelType{type});
+    if (e) return e;
+    memcpy(f.buf.data(), src, (size_t)w * h * opencv_type_channels(type));
+    lp_mat_mark_host_dirty(f.mat);
+    return LP_OK;
+}
+
+extern "C" int lp_fit_host(const uint8_t* src, int sw, int sh, int type, uint8_t* dst, int dw,
+                           int dh) {
+    int side = std::max(std::max(sw, sh), std::max(dw, dh));
+    Framebuffer a(side, side), b(side, side);
+    Error e = wrapPixels(a, src, sw, sh, type);
+    if (e) return e;
+    if ((e = a.Fit(dw, dh, &b))) return e;
+    if (lp_mat_sync_host(b.mat)) return LP_ERR_CUDA;
+    memcpy(dst, opencv_mat_get_data(b.mat), (size_t)dw * dh * opencv_type_channels(type));
+    return LP_OK;
+}
+
+extern "C" int lp_resize_host(const uint8_t* src, int sw, int sh, int type, int cx, int cy, int cw,
+                              int ch, uint8_t* dst, int dw, int dh, int interpolation) {
+    int side = std::max(std::max(sw, sh), std::max(dw, dh));
+    Framebuffer a(side, side), b(side, side);
+    Error e = wrapPixels(a, src, sw, sh, type);
+    if (e) return e;
+    if (cx < 0 || cy < 0 || cw < 1 || ch < 1 || cx + cw > sw || cy + ch > sh)
+        return LP_ERR_BAD_ARGUMENT;
+    opencv_mat view = opencv_mat_crop(a.mat, cx, cy, cw, ch);
+    e = b.resizeMat(dw, dh, PixelType{type});
+    if (!e) opencv_mat_resize(view, b.mat, dw, dh, interpolation);
+    opencv_mat_release(view);
+    if (e) return e;
+    if (lp_mat_sync_host(b.mat)) return LP_ERR_CUDA;
+    memcpy(dst, opencv_mat_get_data(b.mat), (size_t)dw * dh * opencv_type_channels(type));
+    return LP_OK;
+}
+
+extern "C" int lp_encode_host(const char* ext, const uint8_t* pixels, int w, int h, int type,
+                              const int* opt, size_t opt_len, uint8_t* dst, size_t dst_cap,
+                              size_t* out_len) {
+    int side = std::max(w, h);
+    Framebuffer a(side, side);
+    Error e = wrapPixels(a, pixels, w, h, type);
+    if (e) return e;
+    std::unique_ptr<Encoder> enc;
+    if ((e = NewEncoder(ext, nullptr, dst, dst_cap, &enc))) return e;
+    std::map<int, int> o;
+    for (size_t i = 0; i + 1 < opt_len; i += 2) o[opt[i]] = opt[i + 1];
+    bool content = false;
+    return enc->Encode(&a, o, &content, out_len);
+}
+
+extern "C" int lp_orient_host(const uint8_t* src, int w, int h, int type, int orientation,
+                              uint8_t* dst, int* ow, int* oh) {
+    int side = std::max(w, h);
+    Framebuffer a(side, side);
+    Error e = wrapPixels(a, src, w, h, type);
+    if (e) return e;
+    a.OrientationTransform(orientation);
+    if (lp_mat_sync_host(a.mat)) return LP_ERR_CUDA;
+    *ow = a.Width();
+    *oh = a.Height();
+    memcpy(dst, opencv_mat_get_data(a.mat), (size_t)w * h * opencv_type_channels(type));
+    return LP_OK;
+}

@@ -1,0 +1,432 @@
+// batch.cu -- the additive batch entry points (include/lilliput_b200.h): N independent baseline
+// JPEGs -> Fit / area resize -> JPEG, every stage one grid launch over a chunk of the batch.
+//
+// Per-item semantics are those of ImageOps.Transform (ref ops.go:352-444) for a still JPEG with
+// ImageOpsFit/ImageOpsResize and ".jpeg" output: decode (ref opencv.cpp:166), orientation TL,
+// Framebuffer.Fit crop + INTER_AREA (ref opencv.go:326-374), encode (ref opencv.cpp:185).
+// Images are independent; nothing is exchanged between them or between GPUs.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "lilliput_host.hpp"
+
+using namespace lp;
+
+struct lp_batch {
+    lp_batch_config cfg;
+    cudaStream_t st = nullptr;
+    int chunk = 0, max_chunks = 0;
+    // geometry (fixed by cfg)
+    int W = 0, H = 0, out_w = 0, out_h = 0;
+    int crop_x = 0, crop_y = 0, crop_w = 0, crop_h = 0;
+    // per-image layout, filled from the first staged header
+    bool layout_known = false;
+    JpegDecodeItem proto;
+    uint32_t blocks = 0, plane_bytes = 0;
+    size_t frame_bytes = 0, resized_bytes = 0;
+    // device
+    uint8_t* d_scan = nullptr;
+    JpegDecodeItem* d_items = nullptr;
+    JpegHuffSet* d_tables = nullptr;
+    int16_t* d_coef = nullptr;
+    uint8_t* d_planes = nullptr;
+    uint8_t* d_frames = nullptr;
+    uint8_t* d_resized = nullptr;
+    uint8_t* d_enc_scratch = nullptr;
+    uint8_t* d_out = nullptr;
+    uint32_t* d_out_len = nullptr;
+    // host
+    std::vector<JpegDecodeItem> items;
+    std::vector<JpegHuffSet> tables;
+    std::map<std::string, int> table_index;
+    std::vector<int> parse_status;
+    uint8_t* h_out = nullptr;       // pinned
+    uint32_t* h_out_len = nullptr;  // pinned
+    JpegDecodeItem* h_items_back = nullptr;
+    int n = 0;
+    int last_launches = 0;
+    std::vector<cudaEvent_t> ev;  // 6 per chunk
+    static constexpr int kMaxTables = 64;
+};
+
+static void batch_free(lp_batch* b) {
+    if (!b) return;
+    cudaFree(b->d_scan); cudaFree(b->d_items); cudaFree(b->d_tables); cudaFree(b->d_coef);
+    cudaFree(b->d_planes); cudaFree(b->d_frames); cudaFree(b->d_resized); cudaFree(b->d_enc_scratch);
+    cudaFree(b->d_out); cudaFree(b->d_out_len);
+    if (b->h_out) cudaFreeHost(b->h_out);
+    if (b->h_out_len) cudaFreeHost(b->h_out_len);
+    if (b->h_items_back) cudaFreeHost(b->h_items_back);
+    for (auto e : b->ev) cudaEventDestroy(e);
+    if (b->st) cudaStreamDestroy(b->st);
+    delete b;
+}
+
+extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
+    if (!cfg || cfg->max_images < 1 || cfg->src_width < 1 || cfg->src_height < 1) return nullptr;
+    if (ensure_device()) return nullptr;
+    LP_CUDA_OK_NULL(cudaSetDevice(cfg->device));
+    lp_batch* b = new lp_batch;
+    b->cfg = *cfg;
+    b->W = cfg->src_width;
+    b->H = cfg->src_height;
+    if (cfg->resize_method == LP_OPS_FIT) {
+        // ref ops.go:170-171 + opencv.go:331-363
+        lilliput::calculateExpectedSize(b->W, b->H, cfg->dst_width, cfg->dst_height, &b->out_w, &b->out_h);
+        lilliput::fitCropRect(b->W, b->H, b->out_w, b->out_h, &b->crop_x, &b->crop_y, &b->crop_w, &b->crop_h);
+    } else if (cfg->resize_method == LP_OPS_RESIZE) {
+        b->out_w = std::max(cfg->dst_width, 1);
+        b->out_h = std::max(cfg->dst_height, 1);
+        b->crop_w = b->W;
+        b->crop_h = b->H;
+    } else {
+        delete b;
+        return nullptr;
+    }
+    b->chunk = cfg->chunk > 0 ? cfg->chunk : 512;
+    b->chunk = std::min(b->chunk, cfg->max_images);
+    b->max_chunks = ceil_div(cfg->max_images, b->chunk);
+    // worst-case per-image layout: 4:4:4 needs the most blocks; size for h,v <= 2 colour
+    const size_t mcus = (size_t)ceil_div(b->W, 8) * ceil_div(b->H, 8);
+    const size_t max_blocks = mcus * 3 + 4 * ((size_t)ceil_div(b->W, 8) + ceil_div(b->H, 8)) + 16;
+    b->frame_bytes = (size_t)b->W * b->H * 3;
+    b->resized_bytes = (size_t)b->out_w * b->out_h * 3;
+    const size_t N = cfg->max_images;
+    auto fail = [&]() -> lp_batch* { batch_free(b); return nullptr; };
+#define BALLOC(ptr, bytes)                                                                      \
+    if (cudaMalloc(&(ptr), (bytes)) != cudaSuccess) {                                           \
+        fprintf(stderr, "[lilliput_b200] lp_batch_create: cudaMalloc(%zu) failed\n", (size_t)(bytes)); \
+        return fail();                                                                          \
+    }
+    if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess) return fail();
+    BALLOC(b->d_scan, cfg->max_in_bytes + 4096);
+    BALLOC(b->d_items, N * sizeof(JpegDecodeItem));
+    BALLOC(b->d_tables, lp_batch::kMaxTables * sizeof(JpegHuffSet));
+    BALLOC(b->d_coef, (size_t)b->chunk * max_blocks * 64 * sizeof(int16_t));
+    BALLOC(b->d_planes, (size_t)b->chunk * max_blocks * 64);
+    BALLOC(b->d_frames, (size_t)b->chunk * b->frame_bytes + 256);
+    BALLOC(b->d_resized, N * b->resized_bytes + 256);
+    BALLOC(b->d_enc_scratch, jpeg_encode_scratch_bytes(b->out_w, b->out_h, 3, b->chunk, cfg->out_cap));
+    BALLOC(b->d_out, N * cfg->out_cap);
+    BALLOC(b->d_out_len, N * sizeof(uint32_t));
+#undef BALLOC
+    if (cudaMallocHost(&b->h_out, N * cfg->out_cap) != cudaSuccess) return fail();
+    if (cudaMallocHost(&b->h_out_len, N * sizeof(uint32_t)) != cudaSuccess) return fail();
+    if (cudaMallocHost(&b->h_items_back, N * sizeof(JpegDecodeItem)) != cudaSuccess) return fail();
+    b->ev.resize((size_t)b->max_chunks * 6);
+    for (auto& e : b->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return fail();
+    b->items.resize(N);
+    b->parse_status.resize(N);
+    return b;
+}
+
+extern "C" void lp_batch_destroy(lp_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->cfg.device);
+    cudaDeviceSynchronize();
+    batch_free(b);
+}
+
+static int table_set_for(lp_batch* b, const JpegHeader& h) {
+    std::string key;
+    for (int tc = 0; tc < 2; tc++)
+        for (int th = 0; th < 4; th++) {
+            key.push_back((char)h.huff_present[tc][th]);
+            if (h.huff_present[tc][th]) {
+                key.append((const char*)h.huff_bits[tc][th], 17);
+                key.append((const char*)h.huff_vals[tc][th], 256);
+            }
+        }
+    auto it = b->table_index.find(key);
+    if (it != b->table_index.end()) return it->second;
+    if ((int)b->tables.size() >= lp_batch::kMaxTables) return -1;
+    JpegHuffSet hs;
+    jpeg_build_huff_set(h, &hs);
+    b->tables.push_back(hs);
+    int idx = (int)b->tables.size() - 1;
+    b->table_index[key] = idx;
+    return idx;
+}
+
+extern "C" int lp_batch_stage(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int n,
+                              int* status) {
+    if (!b || !in || !in_len || n < 0 || n > b->cfg.max_images) return LP_ERR_BAD_ARGUMENT;
+    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+    b->n = n;
+    b->tables.clear();
+    b->table_index.clear();
+    size_t dev_off = 0;
+    // 1) host: parse headers, fill device items
+    std::vector<size_t> file_dev_off(n, 0);
+    for (int i = 0; i < n; i++) {
+        JpegHeader h;
+        int rc = jpeg_parse_header(in[i], in_len[i], &h);
+        if (!rc && !h.supported) rc = LP_ERR_UNSUPPORTED;
+        if (!rc && (h.width != b->W || h.height != b->H)) rc = LP_ERR_BAD_ARGUMENT;
+        if (!rc && h.orientation != 1) rc = LP_ERR_UNSUPPORTED;  // batch path: TL only
+        if (!rc && h.ncomp != 3) rc = LP_ERR_UNSUPPORTED;
+        int ts = rc ? 0 : table_set_for(b, h);
+        if (!rc && ts < 0) rc = LP_ERR_UNSUPPORTED;
+        b->parse_status[i] = rc;
+        JpegDecodeItem& it = b->items[i];
+        memset(&it, 0, sizeof(it));
+        it.status = rc ? -1 : 0;
+        if (rc) continue;
+        it.scan_len = (uint32_t)h.scan_length;
+        it.table_set = (uint32_t)ts;
+        it.width = h.width; it.height = h.height; it.ncomp = h.ncomp;
+        it.mcus_x = h.mcus_x; it.mcus_y = h.mcus_y; it.restart_interval = h.restart_interval;
+        uint32_t blocks = 0, plane_bytes = 0;
+        for (int c = 0; c < h.ncomp; c++) {
+            it.h[c] = h.comp[c].h; it.v[c] = h.comp[c].v;
+            it.bw[c] = h.mcus_x * h.comp[c].h; it.bh[c] = h.mcus_y * h.comp[c].v;
+            it.dw[c] = (h.width * h.comp[c].h + h.maxh - 1) / h.maxh;
+            it.dh[c] = (h.height * h.comp[c].v + h.maxv - 1) / h.maxv;
+            it.block_off[c] = blocks; it.plane_rel[c] = plane_bytes;
+            blocks += (uint32_t)it.bw[c] * it.bh[c];
+            plane_bytes += (uint32_t)it.bw[c] * it.bh[c] * 64;
+            memcpy(it.qt[c], h.qt[h.comp[c].tq], sizeof(it.qt[c]));
+            it.td[c] = h.comp[c].td; it.ta[c] = h.comp[c].ta;
+        }
+        it.frame_channels = 3;
+        if (!b->layout_known) {
+            b->blocks = blocks;
+            b->plane_bytes = plane_bytes;
+            b->layout_known = true;
+        } else if (blocks > b->blocks) {
+            // per-chunk slots are sized by the first image's layout; a mixed-sampling batch keeps
+            // the largest.  (Homogeneous corpora never take this branch.)
+            b->blocks = blocks;
+            b->plane_bytes = plane_bytes;
+        }
+        it.scan_off = h.scan_offset;  // file-relative for now
+    }
+    // 2) copy files to HBM: contiguous runs of input pointers go as one transfer
+    int i = 0;
+    while (i < n) {
+        int j = i;
+        size_t run = in_len[i];
+        while (j + 1 < n && in[j + 1] == in[j] + in_len[j]) { j++; run += in_len[j]; }
+        if (dev_off + run > b->cfg.max_in_bytes) return LP_ERR_BUF_TOO_SMALL;
+        LP_CUDA_OK(cudaMemcpyAsync(b->d_scan + dev_off, in[i], run, cudaMemcpyHostToDevice, b->st));
+        size_t o = dev_off;
+        for (int k = i; k <= j; k++) { file_dev_off[k] = o; o += in_len[k]; }
+        dev_off = round_up(dev_off + run, (size_t)16);
+        i = j + 1;
+    }
+    const size_t max_blocks_alloc = ((size_t)ceil_div(b->W, 8) * ceil_div(b->H, 8)) * 3 +
+                                    4 * ((size_t)ceil_div(b->W, 8) + ceil_div(b->H, 8)) + 16;
+    for (int k = 0; k < n; k++) {
+        JpegDecodeItem& it = b->items[k];
+        if (b->parse_status[k]) continue;
+        const uint32_t nb = it.block_off[2] + (uint32_t)it.bw[2] * it.bh[2];
+        if (nb > max_blocks_alloc) { b->parse_status[k] = LP_ERR_UNSUPPORTED; it.status = -1; continue; }
+        const int slot = k % b->chunk;
+        it.scan_off += file_dev_off[k];
+        it.coef_off = (uint64_t)slot * b->blocks * 64;
+        it.plane_off = (uint64_t)slot * b->plane_bytes;
+        it.frame_off = (uint64_t)slot * b->frame_bytes;
+    }
+    LP_CUDA_OK(cudaMemcpyAsync(b->d_items, b->items.data(), (size_t)n * sizeof(JpegDecodeItem),
+                               cudaMemcpyHostToDevice, b->st));
+    if (!b->tables.empty())
+        LP_CUDA_OK(cudaMemcpyAsync(b->d_tables, b->tables.data(), b->tables.size() * sizeof(JpegHuffSet),
+                                   cudaMemcpyHostToDevice, b->st));
+    LP_CUDA_OK(cudaStreamSynchronize(b->st));
+    if (status)
+        for (int k = 0; k < n; k++) status[k] = b->parse_status[k];
+    return LP_OK;
+}
+
+extern "C" int lp_batch_run(lp_batch* b, float* stage_ms) {
+    if (!b) return LP_ERR_BAD_ARGUMENT;
+    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+    const long launches0 = g_launches;
+    const int nchunks = ceil_div(b->n, b->chunk);
+    for (int c = 0; c < nchunks; c++) {
+        const int i0 = c * b->chunk, cnt = std::min(b->chunk, b->n - i0);
+        cudaEvent_t* ev = &b->ev[(size_t)c * 6];
+        LP_CUDA_OK(cudaEventRecord(ev[0], b->st));
+        JpegDecodeBatch d;
+        d.items = b->d_items + i0;
+        d.tables = b->d_tables;
+        d.scan = b->d_scan;
+        d.coef = b->d_coef;
+        d.planes = b->d_planes;
+        d.frames = b->d_frames;
+        d.n = cnt;
+        d.coef_elems_total = (size_t)cnt * b->blocks * 64;
+        d.max_blocks_per_image = (int)b->blocks;
+        d.max_width = b->W;
+        d.max_height = b->H;
+        int rc = jpeg_decode_launch(d, b->st, ev[1]);
+        if (rc) return rc;
+        LP_CUDA_OK(cudaEventRecord(ev[2], b->st));
+        ResizeArgs r;
+        r.src = b->d_frames;
+        r.src_img_stride = b->frame_bytes;
+        r.src_row_stride = (size_t)b->W * 3;
+        r.channels = 3;
+        r.crop_x = b->crop_x; r.crop_y = b->crop_y; r.crop_w = b->crop_w; r.crop_h = b->crop_h;
+        r.dst = b->d_resized + (size_t)i0 * b->resized_bytes;
+        r.dst_img_stride = b->resized_bytes;
+        r.dst_row_stride = (size_t)b->out_w * 3;
+        r.dst_w = b->out_w; r.dst_h = b->out_h;
+        r.n = cnt;
+        r.interpolation = 3;
+        rc = resize_launch(r, b->st);
+        if (rc) return rc;
+        LP_CUDA_OK(cudaEventRecord(ev[3], b->st));
+        JpegEncodeBatch e;
+        e.frames = r.dst;
+        e.frame_img_stride = b->resized_bytes;
+        e.frame_row_stride = (size_t)b->out_w * 3;
+        e.width = b->out_w; e.height = b->out_h; e.channels = 3;
+        e.quality = b->cfg.jpeg_quality;
+        e.n = cnt;
+        e.out = b->d_out + (size_t)i0 * b->cfg.out_cap;
+        e.out_cap = b->cfg.out_cap;
+        e.out_len = b->d_out_len + i0;
+        e.scratch = b->d_enc_scratch;
+        rc = jpeg_encode_launch(e, b->st, ev[4]);
+        if (rc) return rc;
+        LP_CUDA_OK(cudaEventRecord(ev[5], b->st));
+    }
+    LP_CUDA_OK(cudaStreamSynchronize(b->st));
+    b->last_launches = (int)(g_launches - launches0);
+    if (stage_ms) {
+        for (int s = 0; s < LP_STAGE_COUNT; s++) stage_ms[s] = 0.f;
+        for (int c = 0; c < nchunks; c++) {
+            cudaEvent_t* ev = &b->ev[(size_t)c * 6];
+            float t;
+            LP_CUDA_OK(cudaEventElapsedTime(&t, ev[0], ev[1])); stage_ms[LP_STAGE_HUFF_DECODE] += t;
+            LP_CUDA_OK(cudaEventElapsedTime(&t, ev[1], ev[2])); stage_ms[LP_STAGE_IDCT_COLOR] += t;
+            LP_CUDA_OK(cudaEventElapsedTime(&t, ev[2], ev[3])); stage_ms[LP_STAGE_RESIZE] += t;
+            LP_CUDA_OK(cudaEventElapsedTime(&t, ev[3], ev[4])); stage_ms[LP_STAGE_ENC_TRANSFORM] += t;
+            LP_CUDA_OK(cudaEventElapsedTime(&t, ev[4], ev[5])); stage_ms[LP_STAGE_ENC_ENTROPY] += t;
+            LP_CUDA_OK(cudaEventElapsedTime(&t, ev[0], ev[5])); stage_ms[LP_STAGE_TOTAL] += t;
+        }
+    }
+    return LP_OK;
+}
+
+extern "C" int lp_batch_fetch(lp_batch* b, uint8_t* const* out, size_t* out_len, int* status) {
+    if (!b || !out || !out_len) return LP_ERR_BAD_ARGUMENT;
+    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+    const size_t cap = b->cfg.out_cap;
+    LP_CUDA_OK(cudaMemcpyAsync(b->h_out_len, b->d_out_len, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->st));
+    LP_CUDA_OK(cudaMemcpyAsync(b->h_items_back, b->d_items, (size_t)b->n * sizeof(JpegDecodeItem),
+                               cudaMemcpyDeviceToHost, b->st));
+    LP_CUDA_OK(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)b->n * cap, cudaMemcpyDeviceToHost, b->st));
+    LP_CUDA_OK(cudaStreamSynchronize(b->st));
+    for (int i = 0; i < b->n; i++) {
+        int st = b->parse_status[i];
+        if (!st && b->h_items_back[i].status != 0) st = LP_ERR_DECODING_FAILED;
+        if (!st && b->h_out_len[i] == 0) st = LP_ERR_BUF_TOO_SMALL;
+        if (status) status[i] = st;
+        out_len[i] = 0;
+        if (st) continue;
+        memcpy(out[i], b->h_out + (size_t)i * cap, b->h_out_len[i]);
+        out_len[i] = b->h_out_len[i];
+    }
+    return LP_OK;
+}
+
+extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int n,
+                                  uint8_t* const* out, size_t* out_len, int* status) {
+    int rc = lp_batch_stage(b, in, in_len, n, nullptr);
+    if (rc) return rc;
+    rc = lp_batch_run(b, nullptr);
+    if (rc) return rc;
+    return lp_batch_fetch(b, out, out_len, status);
+}
+
+extern "C" int lp_batch_last_launches(const lp_batch* b) { return b ? b->last_launches : 0; }
+extern "C" const uint8_t* lp_batch_decoded_dev(const lp_batch* b, size_t* image_stride) {
+    if (image_stride) *image_stride = b->frame_bytes;
+    return b->d_frames;
+}
+extern "C" const uint8_t* lp_batch_resized_dev(const lp_batch* b, size_t* image_stride) {
+    if (image_stride) *image_stride = b->resized_bytes;
+    return b->d_resized;
+}
+
+// ---- device helpers + single stages ---------------------------------------------------------
+
+extern "C" void* lp_dev_alloc(size_t bytes) {
+    if (ensure_device()) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes + 256) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void lp_dev_free(void* p) { cudaFree(p); }
+extern "C" void* lp_host_alloc_pinned(size_t bytes) {
+    if (ensure_device()) return nullptr;
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void lp_host_free_pinned(void* p) { cudaFreeHost(p); }
+extern "C" int lp_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+    LP_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return LP_OK;
+}
+extern "C" int lp_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+    LP_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return LP_OK;
+}
+extern "C" int lp_dev_synchronize(void) {
+    LP_CUDA_OK(cudaDeviceSynchronize());
+    return LP_OK;
+}
+extern "C" int lp_set_device(int device) {
+    if (ensure_device()) return LP_ERR_CUDA;
+    LP_CUDA_OK(cudaSetDevice(device));
+    return LP_OK;
+}
+
+extern "C" int lp_resize_area_dev(const uint8_t* src, size_t src_image_stride, size_t src_row_stride,
+                                  int channels, int crop_x, int crop_y, int crop_w, int crop_h,
+                                  uint8_t* dst, size_t dst_image_stride, size_t dst_row_stride,
+                                  int dst_w, int dst_h, int n, void* stream) {
+    if (ensure_device()) return LP_ERR_CUDA;
+    ResizeArgs a{src, src_image_stride, src_row_stride, channels, crop_x, crop_y, crop_w, crop_h,
+                 dst, dst_image_stride, dst_row_stride, dst_w, dst_h, n, 3};
+    return resize_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lp_resize_area_time_dev(const uint8_t* src, size_t src_image_stride,
+                                       size_t src_row_stride, int channels, int crop_x, int crop_y,
+                                       int crop_w, int crop_h, uint8_t* dst, size_t dst_image_stride,
+                                       size_t dst_row_stride, int dst_w, int dst_h, int n, int iters,
+                                       float* ms_per_iter) {
+    if (ensure_device()) return LP_ERR_CUDA;
+    cudaStream_t st = thread_stream();
+    cudaEvent_t e0, e1;
+    LP_CUDA_OK(cudaEventCreate(&e0));
+    LP_CUDA_OK(cudaEventCreate(&e1));
+    ResizeArgs a{src, src_image_stride, src_row_stride, channels, crop_x, crop_y, crop_w, crop_h,
+                 dst, dst_image_stride, dst_row_stride, dst_w, dst_h, n, 3};
+    int rc = resize_launch(a, st);  // warm-up (also builds the tap tables)
+    if (rc) return rc;
+    LP_CUDA_OK(cudaStreamSynchronize(st));
+    LP_CUDA_OK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; i++) {
+        rc = resize_launch(a, st);
+        if (rc) return rc;
+    }
+    LP_CUDA_OK(cudaEventRecord(e1, st));
+    LP_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    LP_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_per_iter) *ms_per_iter = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return LP_OK;
+}

@@ -1,0 +1,53 @@
+// common.cuh -- shared host/device helpers for liblilliput_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#include "lilliput_b200.h"
+
+#define LP_CUDA_OK(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            fprintf(stderr, "[lilliput_b200] CUDA error %s at %s:%d: %s\n",                \
+                    cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e));     \
+            return LP_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define LP_CUDA_OK_NULL(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            fprintf(stderr, "[lilliput_b200] CUDA error %s at %s:%d: %s\n",                \
+                    cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e));     \
+            return nullptr;                                                                \
+        }                                                                                  \
+    } while (0)
+
+namespace lp {
+
+constexpr int kNumSMs = 148;  // B200
+
+// Process-wide lazy context: verifies a CUDA device exists (no CPU fallback).
+// Returns LP_OK or LP_ERR_CUDA (logged once).
+int ensure_device();
+// Per-host-thread stream used by the synchronous per-image ABI.
+cudaStream_t thread_stream();
+// Count of kernel launches issued by this library on the calling thread
+// (bench.py reports it as gpu_launches).
+extern thread_local long g_launches;
+
+template <class T>
+static inline T ceil_div(T a, T b) {
+    return (a + b - 1) / b;
+}
+template <class T>
+static inline T round_up(T a, T b) {
+    return ceil_div(a, b) * b;
+}
+
+}  // namespace lp

@@ -1,0 +1,362 @@
+// jpeg_decode.cu -- baseline JPEG decode on sm_100a: Huffman scan -> dequant + 8x8 IDCT ->
+// fancy chroma upsampling + YCbCr->BGR into a packed device frame.
+//
+// Replaces: opencv_decoder_read_data (ref opencv.cpp:166-171), i.e. what
+// cv::ImageDecoder::readData asks of libjpeg-turbo 3.1.0 with its defaults (ISLOW IDCT,
+// fancy upsampling, JCS_EXT_BGR).  Arithmetic contract: SURVEY.md Appendix E.2; results are
+// bit-identical to the reference on baseline streams (tests/test_jpeg_decode_gpu.py).
+//
+// Kernels (each one grid launch over the whole batch):
+//   jpeg_huff_decode_kernel   entropy-coded segment -> quantised coefficients (int16, natural
+//                             order, zero-initialised buffer).  Bit-serial by nature; this
+//                             first version runs one stream per thread.
+//   jpeg_idct_kernel          one thread per 8x8 block: dequantise, two 1-D passes in
+//                             registers, 8-byte row stores into the component plane.
+//   jpeg_upsample_color_kernel  triangle upsampling + fixed-point colour conversion, packed BGR.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace lp {
+
+__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                                     12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                                     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                                     58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// ------------------------------------------------------------------ entropy decode (serial)
+
+struct BitReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    uint64_t acc;
+    int nbits;
+    bool marker;
+};
+
+__device__ __forceinline__ void br_fill(BitReader& b) {
+    while (b.nbits <= 56) {
+        uint32_t byte = 0;
+        if (!b.marker && b.p < b.end) {
+            byte = *b.p;
+            if (byte == 0xFF) {
+                const uint8_t* q = b.p + 1;
+                while (q < b.end && *q == 0xFF) q++;
+                if (q < b.end && *q == 0x00) {
+                    b.p = q + 1;  // stuffed FF
+                } else {
+                    b.marker = true;  // real marker: feed zeros from here on
+                    byte = 0;
+                }
+            } else {
+                b.p++;
+            }
+        }
+        b.acc |= (uint64_t)byte << (56 - b.nbits);
+        b.nbits += 8;
+    }
+}
+
+__device__ __forceinline__ int huff_symbol(BitReader& b, const JpegHuffSet* hs, int t) {
+    if (b.nbits < 32) br_fill(b);
+    const uint32_t peek = (uint32_t)(b.acc >> 48);
+    const uint32_t e = hs->look[t][peek >> 7];
+    if (e) {
+        const int l = e >> 8;
+        b.acc <<= l;
+        b.nbits -= l;
+        return e & 0xFF;
+    }
+    int l = 10;
+    int code = (int)(peek >> 6);
+    while (l <= 16 && code > hs->maxcode[t][l]) {
+        l++;
+        code = (int)(peek >> (16 - l));
+    }
+    if (l > 16) return -1;
+    b.acc <<= l;
+    b.nbits -= l;
+    return hs->vals[t][(code + hs->valoffset[t][l]) & 0xFF];
+}
+
+__device__ __forceinline__ int receive_extend(BitReader& b, int n) {
+    if (b.nbits < 32) br_fill(b);
+    const int v = (int)(b.acc >> (64 - n));
+    b.acc <<= n;
+    b.nbits -= n;
+    return v < (1 << (n - 1)) ? v - (1 << n) + 1 : v;
+}
+
+__global__ void jpeg_huff_decode_kernel(JpegDecodeItem* items, const JpegHuffSet* tables,
+                                        const uint8_t* scan, int16_t* coef, int n) {
+    __shared__ uint8_t zz[64];
+    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    JpegDecodeItem& it = items[i];
+    const JpegHuffSet* hs = tables + it.table_set;
+    BitReader b{scan + it.scan_off, scan + it.scan_off + it.scan_len, 0, 0, false};
+    int16_t* cbase = coef + it.coef_off;
+    int pred[3] = {0, 0, 0};
+    int todo = it.restart_interval;
+    int status = 0;
+    const int nc = it.ncomp;
+    for (int my = 0; my < it.mcus_y && status == 0; my++) {
+        for (int mx = 0; mx < it.mcus_x && status == 0; mx++) {
+            if (it.restart_interval && todo == 0) {
+                // byte-align, skip to just past the next RSTn, reset predictors
+                b.acc = 0;
+                b.nbits = 0;
+                const uint8_t* q = b.p;
+                while (q + 1 < b.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
+                if (q + 1 >= b.end) {
+                    status = -3;
+                    break;
+                }
+                b.p = q + 2;
+                b.marker = false;
+                pred[0] = pred[1] = pred[2] = 0;
+                todo = it.restart_interval;
+            }
+            for (int c = 0; c < nc && status == 0; c++) {
+                const int td = it.td[c], ta = 4 + it.ta[c];
+                for (int by = 0; by < it.v[c] && status == 0; by++) {
+                    for (int bx = 0; bx < it.h[c]; bx++) {
+                        const int X = mx * it.h[c] + bx, Y = my * it.v[c] + by;
+                        int16_t* blk = cbase + ((size_t)it.block_off[c] + (size_t)Y * it.bw[c] + X) * 64;
+                        int s = huff_symbol(b, hs, td);
+                        if (s < 0 || s > 15) { status = -3; break; }
+                        if (s) pred[c] += receive_extend(b, s);
+                        blk[0] = (int16_t)pred[c];
+                        for (int k = 1; k < 64;) {
+                            const int rs = huff_symbol(b, hs, ta);
+                            if (rs < 0) { status = -3; break; }
+                            const int r = rs >> 4, sz = rs & 15;
+                            if (sz == 0) {
+                                if (r != 15) break;
+                                k += 16;
+                                continue;
+                            }
+                            k += r;
+                            if (k > 63) { status = -3; break; }
+                            blk[zz[k]] = (int16_t)receive_extend(b, sz);
+                            k++;
+                        }
+                        if (status) break;
+                    }
+                }
+            }
+            if (it.restart_interval) todo--;
+        }
+    }
+    it.status = status;
+}
+
+// ------------------------------------------------------------------ dequant + ISLOW IDCT
+
+#define LP_FIX_0_298631336 2446
+#define LP_FIX_0_390180644 3196
+#define LP_FIX_0_541196100 4433
+#define LP_FIX_0_765366865 6270
+#define LP_FIX_0_899976223 7373
+#define LP_FIX_1_175875602 9633
+#define LP_FIX_1_501321110 12299
+#define LP_FIX_1_847759065 15137
+#define LP_FIX_1_961570560 16069
+#define LP_FIX_2_053119869 16819
+#define LP_FIX_2_562915447 20995
+#define LP_FIX_3_072711026 25172
+
+template <int SHIFT, bool SAT16>
+__device__ __forceinline__ void idct8(int& v0, int& v1, int& v2, int& v3, int& v4, int& v5, int& v6,
+                                      int& v7) {
+    // even part
+    int z1 = (v2 + v6) * LP_FIX_0_541196100;
+    const int tmp2 = z1 - v6 * LP_FIX_1_847759065;
+    const int tmp3 = z1 + v2 * LP_FIX_0_765366865;
+    const int tmp0 = (v0 + v4) << 13;
+    const int tmp1 = (v0 - v4) << 13;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    // odd part
+    int t0 = v7, t1 = v5, t2 = v3, t3 = v1;
+    z1 = t0 + t3;
+    int z2 = t1 + t2, z3 = t0 + t2, z4 = t1 + t3;
+    const int z5 = (z3 + z4) * LP_FIX_1_175875602;
+    t0 *= LP_FIX_0_298631336;
+    t1 *= LP_FIX_2_053119869;
+    t2 *= LP_FIX_3_072711026;
+    t3 *= LP_FIX_1_501321110;
+    z1 *= -LP_FIX_0_899976223;
+    z2 *= -LP_FIX_2_562915447;
+    z3 = z3 * -LP_FIX_1_961570560 + z5;
+    z4 = z4 * -LP_FIX_0_390180644 + z5;
+    t0 += z1 + z3;
+    t1 += z2 + z4;
+    t2 += z2 + z3;
+    t3 += z1 + z4;
+    constexpr int R = 1 << (SHIFT - 1);
+    v0 = (tmp10 + t3 + R) >> SHIFT;
+    v7 = (tmp10 - t3 + R) >> SHIFT;
+    v1 = (tmp11 + t2 + R) >> SHIFT;
+    v6 = (tmp11 - t2 + R) >> SHIFT;
+    v2 = (tmp12 + t1 + R) >> SHIFT;
+    v5 = (tmp12 - t1 + R) >> SHIFT;
+    v3 = (tmp13 + t0 + R) >> SHIFT;
+    v4 = (tmp13 - t0 + R) >> SHIFT;
+    if (SAT16) {
+        v0 = min(max(v0, -32768), 32767); v1 = min(max(v1, -32768), 32767);
+        v2 = min(max(v2, -32768), 32767); v3 = min(max(v3, -32768), 32767);
+        v4 = min(max(v4, -32768), 32767); v5 = min(max(v5, -32768), 32767);
+        v6 = min(max(v6, -32768), 32767); v7 = min(max(v7, -32768), 32767);
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_px(int a, int b, int c, int d) {
+    a = min(max(a, -128), 127) + 128;
+    b = min(max(b, -128), 127) + 128;
+    c = min(max(c, -128), 127) + 128;
+    d = min(max(d, -128), 127) + 128;
+    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+}
+
+__global__ void __launch_bounds__(128)
+    jpeg_idct_kernel(const JpegDecodeItem* items, const int16_t* coef, uint8_t* planes) {
+    const JpegDecodeItem& it = items[blockIdx.y];
+    if (it.status != 0) return;
+    const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0;
+    if (it.ncomp == 3) c = blk >= (int)it.block_off[2] ? 2 : (blk >= (int)it.block_off[1] ? 1 : 0);
+    const int nblk = (int)it.block_off[it.ncomp - 1] + it.bw[it.ncomp - 1] * it.bh[it.ncomp - 1];
+    if (blk >= nblk) return;
+    const int rel = blk - (int)it.block_off[c];
+    const int X = rel % it.bw[c], Y = rel / it.bw[c];
+    const uint4* src = reinterpret_cast<const uint4*>(coef + it.coef_off + (size_t)blk * 64);
+    const uint16_t* q = it.qt[c];
+    int v[64];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint4 u = __ldg(src + r);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // 16-bit wrapping multiply (pmullw), as libjpeg-turbo's SIMD dequantisation does
+            const int lo = (int16_t)(w[k] & 0xffff), hi = (int16_t)(w[k] >> 16);
+            v[r * 8 + 2 * k] = (int16_t)(lo * (int)q[r * 8 + 2 * k]);
+            v[r * 8 + 2 * k + 1] = (int16_t)(hi * (int)q[r * 8 + 2 * k + 1]);
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < 8; x++)
+        idct8<11, true>(v[x], v[8 + x], v[16 + x], v[24 + x], v[32 + x], v[40 + x], v[48 + x], v[56 + x]);
+    const int stride = it.bw[c] * 8;
+    uint8_t* dst = planes + it.plane_off + it.plane_rel[c] + (size_t)Y * 8 * stride + X * 8;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        idct8<18, false>(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5],
+                         v[r * 8 + 6], v[r * 8 + 7]);
+        uint2 o;
+        o.x = pack_px(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
+        o.y = pack_px(v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+        *reinterpret_cast<uint2*>(dst + (size_t)r * stride) = o;
+    }
+}
+
+// ------------------------------------------------------------------ upsample + colour
+
+// Value of component c at full-resolution pixel (x, y): libjpeg-turbo jdsample.c.
+__device__ __forceinline__ int upsampled(const JpegDecodeItem& it, const uint8_t* planes, int c, int maxh,
+                                         int maxv, int x, int y) {
+    const uint8_t* pl = planes + it.plane_off + it.plane_rel[c];
+    const int stride = it.bw[c] * 8;
+    const int hr = maxh / it.h[c], vr = maxv / it.v[c];
+    const int cw = it.dw[c], ch = it.dh[c];
+    if (hr == 1 && vr == 1) return pl[(size_t)y * stride + x];
+    if (hr == 2 && vr == 2) {
+        const int cy = y >> 1, i = x >> 1;
+        const int fy = min(max((y & 1) ? cy + 1 : cy - 1, 0), ch - 1);
+        const uint8_t* s0 = pl + (size_t)cy * stride;
+        const uint8_t* s1 = pl + (size_t)fy * stride;
+        const int cs = 3 * s0[i] + s1[i];
+        if (x & 1) {
+            if (i == cw - 1) return (cs * 4 + 7) >> 4;
+            return (cs * 3 + 3 * s0[i + 1] + s1[i + 1] + 7) >> 4;
+        }
+        if (i == 0) return (cs * 4 + 8) >> 4;
+        return (cs * 3 + 3 * s0[i - 1] + s1[i - 1] + 8) >> 4;
+    }
+    if (hr == 2 && vr == 1) {
+        const uint8_t* s = pl + (size_t)y * stride;
+        const int i = x >> 1;
+        if (x & 1) return (i == cw - 1) ? s[i] : (3 * s[i] + s[i + 1] + 2) >> 2;
+        return (i == 0) ? s[0] : (3 * s[i] + s[i - 1] + 1) >> 2;
+    }
+    if (hr == 1 && vr == 2) {
+        const int cy = y >> 1;
+        const int fy = min(max((y & 1) ? cy + 1 : cy - 1, 0), ch - 1);
+        return (3 * pl[(size_t)cy * stride + x] + pl[(size_t)fy * stride + x] + ((y & 1) ? 2 : 1)) >> 2;
+    }
+    return pl[(size_t)(y / vr) * stride + x / hr];  // int_upsample (replication)
+}
+
+__global__ void jpeg_upsample_color_kernel(const JpegDecodeItem* items, const uint8_t* planes,
+                                           uint8_t* frames) {
+    const JpegDecodeItem& it = items[blockIdx.z];
+    if (it.status != 0) return;
+    const int xp = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const int y = blockIdx.y;
+    if (xp >= it.width || y >= it.height) return;
+    uint8_t* out = frames + it.frame_off;
+    if (it.ncomp == 1) {
+        const uint8_t* pl = planes + it.plane_off + it.plane_rel[0];
+        const int stride = it.bw[0] * 8;
+        out[(size_t)y * it.width + xp] = pl[(size_t)y * stride + xp];
+        if (xp + 1 < it.width) out[(size_t)y * it.width + xp + 1] = pl[(size_t)y * stride + xp + 1];
+        return;
+    }
+    int maxh = max(it.h[0], max(it.h[1], it.h[2])), maxv = max(it.v[0], max(it.v[1], it.v[2]));
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int x = xp + k;
+        if (x >= it.width) break;
+        const int Y = upsampled(it, planes, 0, maxh, maxv, x, y);
+        const int cb = upsampled(it, planes, 1, maxh, maxv, x, y) - 128;
+        const int cr = upsampled(it, planes, 2, maxh, maxv, x, y) - 128;
+        const int r = Y + ((91881 * cr + 32768) >> 16);
+        const int g = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+        const int b = Y + ((116130 * cb + 32768) >> 16);
+        uint8_t* o = out + ((size_t)y * it.width + x) * 3;
+        o[0] = (uint8_t)min(max(b, 0), 255);
+        o[1] = (uint8_t)min(max(g, 0), 255);
+        o[2] = (uint8_t)min(max(r, 0), 255);
+    }
+}
+
+// ------------------------------------------------------------------ launcher
+
+int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_huff) {
+    if (b.n <= 0) return LP_OK;
+    LP_CUDA_OK(cudaMemsetAsync(b.coef, 0, b.coef_elems_total * sizeof(int16_t), st));
+    {
+        const int threads = 32;
+        jpeg_huff_decode_kernel<<<ceil_div(b.n, threads), threads, 0, st>>>(b.items, b.tables, b.scan,
+                                                                           b.coef, b.n);
+        g_launches++;
+        LP_CUDA_OK(cudaGetLastError());
+    }
+    if (ev_after_huff) LP_CUDA_OK(cudaEventRecord(ev_after_huff, st));
+    {
+        dim3 grid(ceil_div(b.max_blocks_per_image, 128), b.n);
+        jpeg_idct_kernel<<<grid, 128, 0, st>>>(b.items, b.coef, b.planes);
+        g_launches++;
+        LP_CUDA_OK(cudaGetLastError());
+    }
+    {
+        dim3 grid(ceil_div(ceil_div(b.max_width, 2), 128), b.max_height, b.n);
+        jpeg_upsample_color_kernel<<<grid, 128, 0, st>>>(b.items, b.planes, b.frames);
+        g_launches++;
+        LP_CUDA_OK(cudaGetLastError());
+    }
+    return LP_OK;
+}
+
+}  // namespace lp

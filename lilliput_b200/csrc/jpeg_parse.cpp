@@ -1,0 +1,185 @@
+// jpeg_parse.cpp -- host-side JPEG marker parsing (ITU-T T.81 Annex B) and Huffman
+// table preparation for the device decoder.  No pixel arithmetic here.
+//
+// Stands where cv::ImageDecoder::readHeader does for the reference
+// (ref opencv.cpp:126-164): width / height / channel count / EXIF orientation.
+#include <cstring>
+
+#include "kernels.cuh"
+#include "lilliput_b200.h"
+
+namespace lp {
+
+static const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                                    12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                                    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                                    58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// EXIF IFD0 tag 0x0112 from an APP1 payload; 0 when absent/invalid.
+static int exif_orientation(const uint8_t* p, size_t n) {
+    if (n < 14 || memcmp(p, "Exif\0\0", 6) != 0) return 0;
+    const uint8_t* t = p + 6;
+    size_t tn = n - 6;
+    bool le;
+    if (t[0] == 'I' && t[1] == 'I') le = true;
+    else if (t[0] == 'M' && t[1] == 'M') le = false;
+    else return 0;
+    auto rd16 = [&](size_t o) -> unsigned { return le ? (t[o] | (t[o + 1] << 8)) : ((t[o] << 8) | t[o + 1]); };
+    auto rd32 = [&](size_t o) -> uint32_t {
+        return le ? ((uint32_t)t[o] | ((uint32_t)t[o + 1] << 8) | ((uint32_t)t[o + 2] << 16) | ((uint32_t)t[o + 3] << 24))
+                  : (((uint32_t)t[o] << 24) | ((uint32_t)t[o + 1] << 16) | ((uint32_t)t[o + 2] << 8) | t[o + 3]);
+    };
+    if (rd16(2) != 42) return 0;
+    size_t ifd = rd32(4);
+    if (ifd + 2 > tn) return 0;
+    unsigned cnt = rd16(ifd);
+    for (unsigned i = 0; i < cnt; i++) {
+        size_t e = ifd + 2 + (size_t)i * 12;
+        if (e + 12 > tn) return 0;
+        if (rd16(e) == 0x0112) {
+            unsigned v = rd16(e + 8);
+            return (v >= 1 && v <= 8) ? (int)v : 0;
+        }
+    }
+    return 0;
+}
+
+int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
+    JpegHeader& h = *out;
+    h = JpegHeader();
+    if (len < 4 || in[0] != 0xFF || in[1] != 0xD8) return LP_ERR_INVALID_IMAGE;
+    size_t pos = 2;
+    bool have_sof = false;
+    while (pos + 4 <= len) {
+        if (in[pos] != 0xFF) { pos++; continue; }
+        uint8_t m = in[pos + 1];
+        if (m == 0xFF) { pos++; continue; }
+        if (m == 0xD9) break;
+        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { pos += 2; continue; }
+        size_t seg = ((size_t)in[pos + 2] << 8) | in[pos + 3];
+        if (seg < 2 || pos + 2 + seg > len) return LP_ERR_INVALID_IMAGE;
+        const uint8_t* p = in + pos + 4;
+        size_t n = seg - 2;
+        if (m == 0xDB) {
+            while (n >= 65) {
+                int pq = p[0] >> 4, tq = p[0] & 15;
+                size_t need = pq ? 129 : 65;
+                if (tq > 3 || n < need) return LP_ERR_INVALID_IMAGE;
+                for (int i = 0; i < 64; i++)
+                    h.qt[tq][kZigzag[i]] = pq ? (uint16_t)((p[1 + 2 * i] << 8) | p[2 + 2 * i]) : p[1 + i];
+                h.qt_present[tq] = true;
+                p += need;
+                n -= need;
+            }
+        } else if (m == 0xC4) {
+            while (n >= 17) {
+                int tc = p[0] >> 4, th = p[0] & 15;
+                if (tc > 1 || th > 3) return LP_ERR_INVALID_IMAGE;
+                int total = 0;
+                h.huff_bits[tc][th][0] = 0;
+                for (int i = 1; i <= 16; i++) { h.huff_bits[tc][th][i] = p[i]; total += p[i]; }
+                if (total > 256 || n < (size_t)(17 + total)) return LP_ERR_INVALID_IMAGE;
+                memset(h.huff_vals[tc][th], 0, 256);
+                memcpy(h.huff_vals[tc][th], p + 17, total);
+                h.huff_present[tc][th] = true;
+                p += 17 + total;
+                n -= 17 + total;
+            }
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+            if (n < 6) return LP_ERR_INVALID_IMAGE;
+            h.progressive = (m == 0xC2);
+            int prec = p[0];
+            h.height = (p[1] << 8) | p[2];
+            h.width = (p[3] << 8) | p[4];
+            h.ncomp = p[5];
+            if (h.width < 1 || h.height < 1) return LP_ERR_INVALID_IMAGE;
+            if (prec != 8 || (h.ncomp != 1 && h.ncomp != 3) || n < (size_t)(6 + 3 * h.ncomp)) {
+                have_sof = true;  // dimensions known, but not decodable here
+                h.ncomp = h.ncomp == 1 ? 1 : 3;
+                h.supported = false;
+                pos += 2 + seg;
+                continue;
+            }
+            for (int i = 0; i < h.ncomp; i++) {
+                h.comp[i].id = p[6 + 3 * i];
+                h.comp[i].h = p[7 + 3 * i] >> 4;
+                h.comp[i].v = p[7 + 3 * i] & 15;
+                h.comp[i].tq = p[8 + 3 * i];
+                if (h.comp[i].h < 1 || h.comp[i].h > 4 || h.comp[i].v < 1 || h.comp[i].v > 4 || h.comp[i].tq > 3)
+                    return LP_ERR_INVALID_IMAGE;
+                h.maxh = h.comp[i].h > h.maxh ? h.comp[i].h : h.maxh;
+                h.maxv = h.comp[i].v > h.maxv ? h.comp[i].v : h.maxv;
+            }
+            if (h.ncomp == 1) { h.comp[0].h = h.comp[0].v = 1; h.maxh = h.maxv = 1; }
+            have_sof = true;
+            h.supported = !h.progressive;
+            for (int i = 0; i < h.ncomp; i++)
+                if (h.maxh % h.comp[i].h || h.maxv % h.comp[i].v) h.supported = false;
+            h.mcus_x = (h.width + 8 * h.maxh - 1) / (8 * h.maxh);
+            h.mcus_y = (h.height + 8 * h.maxv - 1) / (8 * h.maxv);
+        } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return LP_ERR_UNSUPPORTED;  // lossless / differential / arithmetic
+        } else if (m == 0xDD) {
+            if (n >= 2) h.restart_interval = (p[0] << 8) | p[1];
+        } else if (m == 0xE1) {
+            int o = exif_orientation(p, n);
+            if (o) h.orientation = o;
+        } else if (m == 0xDA) {
+            if (!have_sof || n < 1) return LP_ERR_INVALID_IMAGE;
+            int ns = p[0];
+            if (ns < 1 || ns > 3 || n < (size_t)(1 + 2 * ns + 3)) return LP_ERR_INVALID_IMAGE;
+            if (ns != h.ncomp) h.supported = false;  // multi-scan sequential: not on the device path
+            for (int i = 0; i < ns && h.supported; i++) {
+                int ci = -1;
+                for (int j = 0; j < h.ncomp; j++)
+                    if (h.comp[j].id == p[1 + 2 * i]) ci = j;
+                if (ci != i) { h.supported = false; break; }
+                h.comp[ci].td = p[2 + 2 * i] >> 4;
+                h.comp[ci].ta = p[2 + 2 * i] & 15;
+                if (h.comp[ci].td > 3 || h.comp[ci].ta > 3 || !h.huff_present[0][h.comp[ci].td] ||
+                    !h.huff_present[1][h.comp[ci].ta] || !h.qt_present[h.comp[ci].tq])
+                    return LP_ERR_INVALID_IMAGE;
+            }
+            h.scan_offset = pos + 2 + seg;
+            // upper bound of the entropy-coded segment: up to the last EOI if there is one
+            size_t end = len;
+            for (size_t k = len; k >= h.scan_offset + 2 && k + 64 > len; k--)
+                if (in[k - 2] == 0xFF && in[k - 1] == 0xD9) { end = k - 2; break; }
+            h.scan_length = end - h.scan_offset;
+            return LP_OK;
+        }
+        pos += 2 + seg;
+    }
+    return have_sof ? LP_ERR_INVALID_IMAGE : LP_ERR_INVALID_IMAGE;
+}
+
+// Canonical Huffman decode tables (T.81 Annex C / F.2.2.3) in the device layout.
+void jpeg_build_huff_set(const JpegHeader& h, JpegHuffSet* out) {
+    memset(out, 0, sizeof(*out));
+    for (int tc = 0; tc < 2; tc++)
+        for (int th = 0; th < 4; th++) {
+            int t = tc * 4 + th;
+            for (int l = 0; l < 18; l++) out->maxcode[t][l] = -1;
+            out->maxcode[t][17] = 0x7fffffff;
+            if (!h.huff_present[tc][th]) continue;
+            const uint8_t* bits = h.huff_bits[tc][th];
+            memcpy(out->vals[t], h.huff_vals[tc][th], 256);
+            unsigned code = 0;
+            int k = 0;
+            for (int len = 1; len <= 16; len++) {
+                out->valoffset[t][len] = k - (int)code;
+                for (int i = 0; i < bits[len]; i++, k++) {
+                    if (len <= 9) {
+                        unsigned first = code << (9 - len), cnt = 1u << (9 - len);
+                        for (unsigned j = 0; j < cnt && first + j < 512; j++)
+                            out->look[t][first + j] = (uint16_t)((len << 8) | h.huff_vals[tc][th][k]);
+                    }
+                    code++;
+                }
+                out->maxcode[t][len] = bits[len] ? (int)code - 1 : -1;
+                code <<= 1;
+            }
+        }
+}
+
+}  // namespace lp

@@ -1,0 +1,120 @@
+// kernels.cuh -- internal launch interfaces between the translation units of
+// liblilliput_b200.  Everything here takes DEVICE pointers and a stream.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace lp {
+
+// ---- resize.cu ---------------------------------------------------------------------------
+struct ResizeArgs {
+    const uint8_t* src;
+    size_t src_img_stride, src_row_stride;
+    int channels;
+    int crop_x, crop_y, crop_w, crop_h;
+    uint8_t* dst;
+    size_t dst_img_stride, dst_row_stride;
+    int dst_w, dst_h;
+    int n;
+    int interpolation;  // 1 = INTER_LINEAR, 3 = INTER_AREA
+};
+int resize_launch(const ResizeArgs& a, cudaStream_t st);
+
+// ---- jpeg_parse.cpp (host) -----------------------------------------------------------------
+struct JpegComp {
+    int id, h, v, tq, td, ta;
+};
+struct JpegHeader {
+    int width = 0, height = 0, ncomp = 0;
+    JpegComp comp[3];
+    int maxh = 1, maxv = 1;
+    uint16_t qt[4][64];  // natural order
+    bool qt_present[4] = {false, false, false, false};
+    uint8_t huff_bits[2][4][17];  // [class][id][len]
+    uint8_t huff_vals[2][4][256];
+    bool huff_present[2][4] = {{false, false, false, false}, {false, false, false, false}};
+    int restart_interval = 0;
+    int orientation = 1;
+    size_t scan_offset = 0;  // first entropy-coded byte
+    size_t scan_length = 0;  // bytes available from scan_offset (upper bound)
+    bool progressive = false;
+    bool supported = false;  // baseline/extended sequential Huffman, 8-bit, 1 or 3 comps, one scan
+    int mcus_x = 0, mcus_y = 0;
+};
+// Parses markers up to and including the first SOS.  Returns 0, or a negative lp_status.
+int jpeg_parse_header(const uint8_t* data, size_t len, JpegHeader* out);
+
+// ---- jpeg_decode.cu ------------------------------------------------------------------------
+// Device-side description of one image to decode (array of these lives in HBM).
+struct JpegDecodeItem {
+    uint64_t scan_off;    // offset of the entropy-coded segment in the batch scan buffer
+    uint32_t scan_len;    // bytes
+    uint32_t table_set;   // index into the Huffman table-set array
+    uint64_t coef_off;    // int16 offset of this image's coefficient blocks
+    uint64_t plane_off;   // byte offset of this image's component planes
+    uint64_t frame_off;   // byte offset of this image's packed output frame
+    int32_t width, height, ncomp;
+    int32_t mcus_x, mcus_y, restart_interval;
+    int32_t h[3], v[3];   // sampling factors
+    int32_t bw[3], bh[3]; // blocks per component plane (padded to the MCU grid)
+    int32_t dw[3], dh[3]; // true downsampled component size in samples
+    uint32_t block_off[3];  // first block of component c inside the image's coef area
+    uint32_t plane_rel[3];  // byte offset of component c's plane inside the image's plane area
+    uint16_t qt[3][64];     // per-component quantisation table, natural order
+    int32_t td[3], ta[3];
+    int32_t status;         // written by the decode kernel: 0 ok, <0 corrupt
+    int32_t frame_channels; // 1 or 3
+};
+
+// Huffman decode tables for one image (or many images sharing them), device format.
+struct JpegHuffSet {
+    // [class*4+id]: 9-bit lookahead: (len<<8)|symbol, 0 when the code is longer than 9 bits
+    uint16_t look[8][512];
+    int32_t maxcode[8][18];  // canonical decode for long codes; maxcode[17] = sentinel
+    int32_t valoffset[8][17];
+    uint8_t vals[8][256];
+};
+void jpeg_build_huff_set(const JpegHeader& h, JpegHuffSet* out);
+
+struct JpegDecodeBatch {
+    JpegDecodeItem* items;      // device
+    const JpegHuffSet* tables;  // device
+    const uint8_t* scan;        // device, concatenated entropy-coded segments
+    int16_t* coef;              // device, zeroed by the launcher
+    uint8_t* planes;            // device
+    uint8_t* frames;            // device, packed BGR / gray frames
+    int n;
+    size_t coef_elems_total;    // for the memset
+    int max_blocks_per_image;
+    int max_width, max_height;
+};
+// Launches: memset(coef) -> huffman decode -> idct -> upsample+colour.
+int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_huff);
+
+// ---- jpeg_encode.cu ------------------------------------------------------------------------
+struct JpegEncodeBatch {
+    const uint8_t* frames;  // device packed frames
+    size_t frame_img_stride, frame_row_stride;
+    int width, height, channels;  // shared by the batch
+    int quality;
+    int n;
+    uint8_t* out;            // device, n * out_cap
+    size_t out_cap;
+    uint32_t* out_len;       // device, n (0 on overflow)
+    // scratch (device), sized by jpeg_encode_scratch_bytes
+    void* scratch;
+};
+size_t jpeg_encode_scratch_bytes(int width, int height, int channels, int n, size_t out_cap);
+int jpeg_encode_launch(const JpegEncodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_transform);
+
+// ---- pixel_ops.cu --------------------------------------------------------------------------
+int orient_launch(const uint8_t* src, int w, int h, int channels, int orientation, uint8_t* dst,
+                  cudaStream_t st);
+int copy_region_launch(const uint8_t* src, size_t src_step, int src_ch, uint8_t* dst,
+                       size_t dst_step, int dst_ch, int w, int h, cudaStream_t st);
+int blend_region_launch(const uint8_t* src, size_t src_step, int src_ch, uint8_t* dst,
+                        size_t dst_step, int dst_ch, int w, int h, cudaStream_t st);
+
+}  // namespace lp

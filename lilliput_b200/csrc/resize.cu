@@ -1,0 +1,579 @@
+// resize.cu -- crop + cv::resize for packed u8 frames on sm_100a.
+//
+// Replaces: opencv_mat_resize on an opencv_mat_crop view (ref opencv.cpp:196-215),
+// i.e. Framebuffer.Fit / ResizeTo (ref opencv.go:294-374) and the INTER_LINEAR
+// resize inside opencv_copy_to_region* (ref opencv.cpp:585, 710).
+//
+// Arithmetic contract (bit-exact to the OpenCV 4.11 the reference links;
+// SURVEY.md Appendix E.1 / E.5):
+//   both scales integer -> box sum; 2x2: (s+2)>>2, else RNE(float(s) * (1.f/area))
+//   both scales >= 1    -> per source row a sequential fp32 FMA chain over the x taps,
+//                          then per output row `beta*buf` followed by FMA over the y taps,
+//                          RNE + clamp.  One thread owns each chain, so no reassociation.
+//   otherwise / LINEAR  -> 11-bit fixed-point bilinear.
+//
+// The general area kernel is the HBM-bound one (BASELINE config 2 reads 3.5 MB and writes
+// 0.2 MB per image).  Source row segments are staged into a shared-memory ring by a producer
+// warp with 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA engine) signalled through
+// mbarriers; eight consumer warps turn each staged row into one fp32 partial per output sample
+// and keep the vertical sums in registers.  No data is exchanged between CTAs.
+#include <cmath>
+#include <cfloat>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace lp {
+
+// ------------------------------------------------------------------ tap tables (host)
+
+// OpenCV computeResizeAreaTab for one axis, grouped per destination index.
+struct AreaTabHost {
+    int maxt = 0;
+    std::vector<int> first, count;
+    std::vector<float> w;  // [dsize][maxt], zero padded
+};
+
+static AreaTabHost make_area_tab(int ssize, int dsize) {
+    double scale = (double)ssize / dsize;
+    std::vector<std::vector<float>> rows(dsize);
+    AreaTabHost t;
+    t.first.resize(dsize);
+    t.count.resize(dsize);
+    for (int d = 0; d < dsize; d++) {
+        double f1 = d * scale, f2 = f1 + scale;
+        double cell = std::min(scale, (double)ssize - f1);
+        int s1 = (int)std::ceil(f1), s2 = std::min((int)std::floor(f2), ssize - 1);
+        s1 = std::min(s1, s2);
+        int start = -1;
+        auto push = [&](int s, double wv) {
+            if (start < 0) start = s;
+            rows[d].push_back((float)wv);
+        };
+        if (s1 - f1 > 1e-3) push(s1 - 1, (s1 - f1) / cell);
+        for (int s = s1; s < s2; s++) push(s, 1.0 / cell);
+        if (f2 - s2 > 1e-3) push(s2, std::min(std::min(f2 - s2, 1.0), cell) / cell);
+        t.first[d] = start < 0 ? 0 : start;
+        t.count[d] = (int)rows[d].size();
+        t.maxt = std::max(t.maxt, t.count[d]);
+    }
+    t.w.assign((size_t)dsize * t.maxt, 0.f);
+    for (int d = 0; d < dsize; d++)
+        for (size_t k = 0; k < rows[d].size(); k++) t.w[(size_t)d * t.maxt + k] = rows[d][k];
+    return t;
+}
+
+struct AreaTabDev {
+    int maxt = 0, padt = 0;  // padt = weights per entry as laid out on the device
+    int* first = nullptr;
+    int* count = nullptr;
+    float* w = nullptr;
+    std::vector<int> h_first, h_count;
+};
+
+static std::mutex g_tab_mu;
+static std::map<std::tuple<int, int, int, int>, AreaTabDev> g_tabs;  // (device, ssize, dsize, padt)
+
+static int pad_taps(int maxt) {
+    const int opts[] = {2, 3, 4, 6, 8, 12, 16};
+    for (int o : opts)
+        if (maxt <= o) return o;
+    return maxt;
+}
+
+// Device-resident tap table, cached per (device, ssize, dsize).
+static int get_area_tab(int ssize, int dsize, AreaTabDev* out) {
+    int dev = 0;
+    LP_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    AreaTabHost h = make_area_tab(ssize, dsize);
+    int padt = pad_taps(h.maxt);
+    auto key = std::make_tuple(dev, ssize, dsize, padt);
+    auto it = g_tabs.find(key);
+    if (it != g_tabs.end()) {
+        *out = it->second;
+        return LP_OK;
+    }
+    AreaTabDev d;
+    d.maxt = h.maxt;
+    d.padt = padt;
+    std::vector<float> w((size_t)dsize * padt, 0.f);
+    for (int i = 0; i < dsize; i++)
+        memcpy(&w[(size_t)i * padt], &h.w[(size_t)i * h.maxt], sizeof(float) * h.maxt);
+    LP_CUDA_OK(cudaMalloc(&d.first, sizeof(int) * dsize));
+    LP_CUDA_OK(cudaMalloc(&d.count, sizeof(int) * dsize));
+    LP_CUDA_OK(cudaMalloc(&d.w, sizeof(float) * w.size()));
+    LP_CUDA_OK(cudaMemcpy(d.first, h.first.data(), sizeof(int) * dsize, cudaMemcpyHostToDevice));
+    LP_CUDA_OK(cudaMemcpy(d.count, h.count.data(), sizeof(int) * dsize, cudaMemcpyHostToDevice));
+    LP_CUDA_OK(cudaMemcpy(d.w, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+    d.h_first = h.first;
+    d.h_count = h.count;
+    g_tabs[key] = d;
+    *out = d;
+    return LP_OK;
+}
+
+// ------------------------------------------------------------------ device helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LP_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LP_DONE;\n"
+        "bra LP_WAIT;\n"
+        "LP_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, no tensor map): 16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ uint8_t sat_rne_u8(float v) {
+    int i = __float2int_rn(v);
+    return (uint8_t)min(max(i, 0), 255);
+}
+
+// ------------------------------------------------------------------ general INTER_AREA kernel
+
+struct AreaParams {
+    const uint8_t* src;
+    size_t src_img_stride, src_row_stride;
+    uint8_t* dst;
+    size_t dst_img_stride, dst_row_stride;
+    int crop_x, crop_y;
+    int dw, dh;
+    const int* xfirst;
+    const int* xcount;
+    const float* xw;  // [dw][MAXT]
+    const int* yfirst;
+    const int* ycount;
+    const float* yw;  // [dh][ypad]
+    int ypad;
+    int rows_per_band;
+    int slot_bytes;
+    int slots;
+};
+
+constexpr int kAreaTile = 256;  // destination pixels per CTA (= consumer threads)
+
+template <int C, int MAXT>
+__global__ void __launch_bounds__(kAreaTile + 32)
+    resize_area_kernel(const AreaParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int S = p.slots;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + S;
+    uint8_t* ring = smem + 128;  // S <= 8 -> 16 barriers = 128 bytes
+
+    const int tid = threadIdx.x;
+    const int img = blockIdx.z;
+    const int dx0 = blockIdx.x * kAreaTile;
+    const int dx1 = min(dx0 + kAreaTile, p.dw);
+    const int dy0 = blockIdx.y * p.rows_per_band;
+    const int dy1 = min(dy0 + p.rows_per_band, p.dh);
+
+    const int x_begin = __ldg(p.xfirst + dx0);
+    const int x_end = __ldg(p.xfirst + dx1 - 1) + __ldg(p.xcount + dx1 - 1);
+    const int sy_begin = __ldg(p.yfirst + dy0);
+    const int sy_end = __ldg(p.yfirst + dy1 - 1) + __ldg(p.ycount + dy1 - 1);  // exclusive
+    const int nrows = sy_end - sy_begin;
+    const uint32_t span = (uint32_t)(x_end - x_begin) * C;
+
+    const uint8_t* seg0 = p.src + (size_t)img * p.src_img_stride +
+                          (size_t)(p.crop_y + sy_begin) * p.src_row_stride +
+                          (size_t)(p.crop_x + x_begin) * C;
+
+    constexpr int kConsumerWarps = kAreaTile / 32;
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= kAreaTile) {
+        // ---------------- producer warp: one elected lane feeds the ring ----------------
+        if (tid == kAreaTile) {
+            for (int r = 0; r < nrows; r++) {
+                const int s = r % S;
+                if (r >= S) mbar_wait(&empty[s], ((r / S) - 1) & 1);
+                const uint8_t* g = seg0 + (size_t)r * p.src_row_stride;
+                const uint32_t delta = (uint32_t)((uintptr_t)g & 15);
+                const uint32_t bytes = (delta + span + 15u) & ~15u;
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(ring + (size_t)s * p.slot_bytes, g - delta, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: thread = one destination pixel (C chains) ----------------
+    const int dx = dx0 + tid;
+    const bool active = dx < dx1;
+    const int lane = tid & 31;
+    float wx[MAXT];
+    int rel = 0;
+    if (active) {
+        rel = (__ldg(p.xfirst + dx) - x_begin) * C;
+#pragma unroll
+        for (int t = 0; t < MAXT; t++) wx[t] = __ldg(p.xw + (size_t)dx * MAXT + t);
+    } else {
+#pragma unroll
+        for (int t = 0; t < MAXT; t++) wx[t] = 0.f;
+    }
+    const uint32_t seg_lo = (uint32_t)((uintptr_t)seg0 & 15);
+    const uint32_t stride_lo = (uint32_t)(p.src_row_stride & 15);
+
+    constexpr int NA = (C * MAXT + 3) / 4;  // aligned words holding this pixel's taps
+    float buf[C];
+    float sum[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) buf[c] = sum[c] = 0.f;
+
+    int loaded = -1;
+    for (int dy = dy0; dy < dy1; dy++) {
+        const int yf = __ldg(p.yfirst + dy) - sy_begin;
+        const int yc = __ldg(p.ycount + dy);
+        for (int j = 0; j < yc; j++) {
+            const int r = yf + j;
+            while (loaded < r) {
+                loaded++;
+                const int s = loaded % S;
+                mbar_wait(&full[s], (loaded / S) & 1);
+                if (loaded == r && active) {
+                    const uint32_t delta = (seg_lo + (uint32_t)loaded * stride_lo) & 15u;
+                    const uint32_t o = delta + (uint32_t)rel;
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(
+                        ring + (size_t)s * p.slot_bytes + (o & ~3u));
+                    const uint32_t sh = (o & 3u) * 8u;
+                    uint32_t w[NA + 1];
+#pragma unroll
+                    for (int i = 0; i <= NA; i++) w[i] = wp[i];
+                    uint32_t a[NA];
+#pragma unroll
+                    for (int i = 0; i < NA; i++) a[i] = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+                    for (int c = 0; c < C; c++) buf[c] = 0.f;
+#pragma unroll
+                    for (int t = 0; t < MAXT; t++) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            const int i = t * C + c;
+                            const float v = (float)((a[i >> 2] >> (8 * (i & 3))) & 0xffu);
+                            buf[c] = __fmaf_rn(v, wx[t], buf[c]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+            const float beta = __ldg(p.yw + (size_t)dy * p.ypad + j);
+#pragma unroll
+            for (int c = 0; c < C; c++)
+                sum[c] = (j == 0) ? __fmul_rn(beta, buf[c]) : __fmaf_rn(beta, buf[c], sum[c]);
+        }
+        if (active) {
+            uint8_t* d = p.dst + (size_t)img * p.dst_img_stride + (size_t)dy * p.dst_row_stride +
+                         (size_t)dx * C;
+#pragma unroll
+            for (int c = 0; c < C; c++) d[c] = sat_rne_u8(sum[c]);
+        }
+    }
+    // drain ring entries this band never needed (cannot happen for contiguous taps; keeps
+    // the producer from being left waiting if a table ever had gaps)
+    while (loaded < nrows - 1) {
+        loaded++;
+        const int s = loaded % S;
+        mbar_wait(&full[s], (loaded / S) & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+}
+
+// Fallback for tap counts beyond the unrolled variants (scale > 16): same arithmetic,
+// runtime loops, direct global loads.  One thread per destination sample.
+__global__ void resize_area_generic_kernel(const AreaParams p, int C, int xpad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = blockIdx.z;
+    if (i >= p.dw * C) return;
+    const int dx = i / C, c = i % C;
+    const int dy = blockIdx.y;
+    const int xf = p.xfirst[dx], xc = p.xcount[dx];
+    const int yf = p.yfirst[dy], yc = p.ycount[dy];
+    float sum = 0.f;
+    for (int j = 0; j < yc; j++) {
+        const uint8_t* row = p.src + (size_t)img * p.src_img_stride +
+                             (size_t)(p.crop_y + yf + j) * p.src_row_stride +
+                             (size_t)(p.crop_x + xf) * C + c;
+        float b = 0.f;
+        for (int k = 0; k < xc; k++) b = __fmaf_rn((float)row[(size_t)k * C], p.xw[(size_t)dx * xpad + k], b);
+        const float beta = p.yw[(size_t)dy * p.ypad + j];
+        sum = (j == 0) ? __fmul_rn(beta, b) : __fmaf_rn(beta, b, sum);
+    }
+    p.dst[(size_t)img * p.dst_img_stride + (size_t)dy * p.dst_row_stride + i] = sat_rne_u8(sum);
+}
+
+// ------------------------------------------------------------------ integer-scale box kernel
+
+struct BoxParams {
+    const uint8_t* src;
+    size_t src_img_stride, src_row_stride;
+    uint8_t* dst;
+    size_t dst_img_stride, dst_row_stride;
+    int crop_x, crop_y, dw, dh, kx, ky, C;
+};
+
+__global__ void resize_box_kernel(const BoxParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // sample index within the dst row
+    if (i >= p.dw * p.C) return;
+    const int dy = blockIdx.y, img = blockIdx.z;
+    const int dx = i / p.C, c = i % p.C;
+    const uint8_t* s = p.src + (size_t)img * p.src_img_stride +
+                       (size_t)(p.crop_y + dy * p.ky) * p.src_row_stride +
+                       (size_t)(p.crop_x + dx * p.kx) * p.C + c;
+    int acc = 0;
+    for (int y = 0; y < p.ky; y++)
+        for (int x = 0; x < p.kx; x++) acc += s[(size_t)y * p.src_row_stride + (size_t)x * p.C];
+    uint8_t v;
+    if (p.kx == 2 && p.ky == 2)
+        v = (uint8_t)((acc + 2) >> 2);
+    else
+        v = sat_rne_u8(__fmul_rn((float)acc, 1.f / (float)(p.kx * p.ky)));
+    p.dst[(size_t)img * p.dst_img_stride + (size_t)dy * p.dst_row_stride + i] = v;
+}
+
+// ------------------------------------------------------------------ fixed-point bilinear kernel
+
+struct LinearParams {
+    const uint8_t* src;
+    size_t src_img_stride, src_row_stride;
+    uint8_t* dst;
+    size_t dst_img_stride, dst_row_stride;
+    int crop_x, crop_y, sw, sh, dw, dh, C;
+    const int* xofs;
+    const short* xa;  // [dw][2]
+    const int* yofs;
+    const short* yb;  // [dh][2]
+};
+
+__global__ void resize_linear_kernel(const LinearParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.dw * p.C) return;
+    const int dy = blockIdx.y, img = blockIdx.z;
+    const int dx = i / p.C, c = i % p.C;
+    const int sx = p.xofs[dx], a0 = p.xa[2 * dx], a1 = p.xa[2 * dx + 1];
+    const int sx1 = min(sx + 1, p.sw - 1);
+    const int sy = p.yofs[dy], b0 = p.yb[2 * dy], b1 = p.yb[2 * dy + 1];
+    const int r0 = min(max(sy, 0), p.sh - 1), r1 = min(max(sy + 1, 0), p.sh - 1);
+    const uint8_t* base = p.src + (size_t)img * p.src_img_stride + (size_t)p.crop_x * p.C + c;
+    const uint8_t* S0 = base + (size_t)(p.crop_y + r0) * p.src_row_stride;
+    const uint8_t* S1 = base + (size_t)(p.crop_y + r1) * p.src_row_stride;
+    const int t0 = S0[(size_t)sx * p.C] * a0 + S0[(size_t)sx1 * p.C] * a1;
+    const int t1 = S1[(size_t)sx * p.C] * a0 + S1[(size_t)sx1 * p.C] * a1;
+    const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+    p.dst[(size_t)img * p.dst_img_stride + (size_t)dy * p.dst_row_stride + i] =
+        (uint8_t)min(max(v, 0), 255);
+}
+
+// Bilinear coefficient tables (OpenCV resize(): plain or INTER_AREA "area mode"), host side.
+static void linear_tab(int ssize, int dsize, bool area_mode, bool clamp_ofs, std::vector<int>* ofs,
+                       std::vector<short>* coef) {
+    double inv = (double)dsize / ssize, scale = 1.0 / inv;
+    ofs->resize(dsize);
+    coef->resize(2 * (size_t)dsize);
+    for (int d = 0; d < dsize; d++) {
+        int s;
+        float f;
+        if (!area_mode) {
+            f = (float)((d + 0.5) * scale - 0.5);
+            s = (int)std::floor(f);
+            f -= s;
+        } else {
+            s = (int)std::floor(d * scale);
+            f = (float)((d + 1) - (s + 1) * inv);
+            f = f <= 0 ? 0.f : f - std::floor(f);
+        }
+        if (clamp_ofs) {  // horizontal only; vertically the two rows are clamped instead
+            if (s < 0) { f = 0; s = 0; }
+            if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+        }
+        (*ofs)[d] = s;
+        (*coef)[2 * d] = (short)lrintf((1.f - f) * 2048.f);
+        (*coef)[2 * d + 1] = (short)lrintf(f * 2048.f);
+    }
+}
+
+// ------------------------------------------------------------------ launcher
+
+template <int C, int MAXT>
+static int launch_area(const AreaParams& p, int n, cudaStream_t st) {
+    auto kern = resize_area_kernel<C, MAXT>;
+    size_t smem = 128 + (size_t)p.slots * p.slot_bytes;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        LP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(ceil_div(p.dw, kAreaTile), ceil_div(p.dh, p.rows_per_band), n);
+    kern<<<grid, kAreaTile + 32, smem, st>>>(p);
+    g_launches++;
+    LP_CUDA_OK(cudaGetLastError());
+    return LP_OK;
+}
+
+template <int C>
+static int dispatch_area(int padt, const AreaParams& p, int n, cudaStream_t st) {
+    switch (padt) {
+        case 2: return launch_area<C, 2>(p, n, st);
+        case 3: return launch_area<C, 3>(p, n, st);
+        case 4: return launch_area<C, 4>(p, n, st);
+        case 6: return launch_area<C, 6>(p, n, st);
+        case 8: return launch_area<C, 8>(p, n, st);
+        case 12: return launch_area<C, 12>(p, n, st);
+        case 16: return launch_area<C, 16>(p, n, st);
+    }
+    return LP_ERR_BAD_ARGUMENT;
+}
+
+int resize_launch(const ResizeArgs& a, cudaStream_t st) {
+    if (a.n <= 0) return LP_OK;
+    if (a.crop_w < 1 || a.crop_h < 1 || a.dst_w < 1 || a.dst_h < 1) return LP_ERR_BAD_ARGUMENT;
+    if (a.channels != 1 && a.channels != 3 && a.channels != 4) return LP_ERR_BAD_ARGUMENT;
+    if (a.interpolation != 1 && a.interpolation != 3) return LP_ERR_UNSUPPORTED;
+    const int C = a.channels;
+    if (a.crop_w == a.dst_w && a.crop_h == a.dst_h) {  // cv::resize: same size is a copy
+        LP_CUDA_OK(cudaMemcpy2DAsync(a.dst, a.dst_row_stride,
+                                     a.src + (size_t)a.crop_y * a.src_row_stride + (size_t)a.crop_x * C,
+                                     a.src_row_stride, (size_t)a.dst_w * C, a.dst_h,
+                                     cudaMemcpyDeviceToDevice, st));
+        for (int i = 1; i < a.n; i++)
+            LP_CUDA_OK(cudaMemcpy2DAsync(
+                a.dst + (size_t)i * a.dst_img_stride, a.dst_row_stride,
+                a.src + (size_t)i * a.src_img_stride + (size_t)a.crop_y * a.src_row_stride + (size_t)a.crop_x * C,
+                a.src_row_stride, (size_t)a.dst_w * C, a.dst_h, cudaMemcpyDeviceToDevice, st));
+        return LP_OK;
+    }
+    double scale_x = 1.0 / ((double)a.dst_w / a.crop_w), scale_y = 1.0 / ((double)a.dst_h / a.crop_h);
+    int ix = (int)lrint(scale_x), iy = (int)lrint(scale_y);
+    bool is_area_fast = std::fabs(scale_x - ix) < DBL_EPSILON && std::fabs(scale_y - iy) < DBL_EPSILON;
+    int interp = a.interpolation;
+    if (interp == 1 && is_area_fast && ix == 2 && iy == 2) interp = 3;
+
+    if (interp == 3 && scale_x >= 1 && scale_y >= 1) {
+        if (is_area_fast) {
+            BoxParams p{a.src, a.src_img_stride, a.src_row_stride, a.dst, a.dst_img_stride,
+                        a.dst_row_stride, a.crop_x, a.crop_y, a.dst_w, a.dst_h, ix, iy, C};
+            dim3 grid(ceil_div(a.dst_w * C, 256), a.dst_h, a.n);
+            resize_box_kernel<<<grid, 256, 0, st>>>(p);
+            g_launches++;
+            LP_CUDA_OK(cudaGetLastError());
+            return LP_OK;
+        }
+        AreaTabDev tx, ty;
+        int rc = get_area_tab(a.crop_w, a.dst_w, &tx);
+        if (rc) return rc;
+        rc = get_area_tab(a.crop_h, a.dst_h, &ty);
+        if (rc) return rc;
+        AreaParams p;
+        p.src = a.src; p.src_img_stride = a.src_img_stride; p.src_row_stride = a.src_row_stride;
+        p.dst = a.dst; p.dst_img_stride = a.dst_img_stride; p.dst_row_stride = a.dst_row_stride;
+        p.crop_x = a.crop_x; p.crop_y = a.crop_y; p.dw = a.dst_w; p.dh = a.dst_h;
+        p.xfirst = tx.first; p.xcount = tx.count; p.xw = tx.w;
+        p.yfirst = ty.first; p.ycount = ty.count; p.yw = ty.w; p.ypad = ty.padt;
+        if (tx.padt > 16) {
+            dim3 grid(ceil_div(a.dst_w * C, 128), a.dst_h, a.n);
+            resize_area_generic_kernel<<<grid, 128, 0, st>>>(p, C, tx.padt);
+            g_launches++;
+            LP_CUDA_OK(cudaGetLastError());
+            return LP_OK;
+        }
+        // widest source span of any x tile (+ alignment slack + unrolled over-read slack)
+        int span = 0;
+        for (int x0 = 0; x0 < a.dst_w; x0 += kAreaTile) {
+            int x1 = std::min(x0 + kAreaTile, a.dst_w) - 1;
+            span = std::max(span, tx.h_first[x1] + tx.h_count[x1] - tx.h_first[x0]);
+        }
+        p.slot_bytes = round_up(span * C + 16 + tx.padt * C + 8, 128);
+        // bands: keep >= ~4 CTAs per SM in flight when the batch is small
+        long ctas_per_row_group = (long)ceil_div(a.dst_w, kAreaTile) * a.n;
+        int rpb = 8;
+        while (rpb > 1 && ctas_per_row_group * ceil_div(a.dst_h, rpb) < 4L * kNumSMs) rpb >>= 1;
+        p.rows_per_band = rpb;
+        p.slots = p.slot_bytes <= 8 * 1024 ? 4 : (p.slot_bytes <= 24 * 1024 ? 3 : 2);
+        if ((size_t)p.slots * p.slot_bytes + 128 > 200 * 1024) {
+            dim3 grid(ceil_div(a.dst_w * C, 128), a.dst_h, a.n);
+            resize_area_generic_kernel<<<grid, 128, 0, st>>>(p, C, tx.padt);
+            g_launches++;
+            LP_CUDA_OK(cudaGetLastError());
+            return LP_OK;
+        }
+        switch (C) {
+            case 1: return dispatch_area<1>(tx.padt, p, a.n, st);
+            case 3: return dispatch_area<3>(tx.padt, p, a.n, st);
+            default: return dispatch_area<4>(tx.padt, p, a.n, st);
+        }
+    }
+
+    // fixed-point bilinear: INTER_LINEAR, or INTER_AREA when an axis is not a downscale
+    bool area_mode = interp == 3;
+    std::vector<int> xo, yo;
+    std::vector<short> xa, yb;
+    linear_tab(a.crop_w, a.dst_w, area_mode, true, &xo, &xa);
+    linear_tab(a.crop_h, a.dst_h, area_mode, false, &yo, &yb);
+    int *dxo = nullptr, *dyo = nullptr;
+    short *dxa = nullptr, *dyb = nullptr;
+    LP_CUDA_OK(cudaMallocAsync(&dxo, sizeof(int) * xo.size(), st));
+    LP_CUDA_OK(cudaMallocAsync(&dyo, sizeof(int) * yo.size(), st));
+    LP_CUDA_OK(cudaMallocAsync(&dxa, sizeof(short) * xa.size(), st));
+    LP_CUDA_OK(cudaMallocAsync(&dyb, sizeof(short) * yb.size(), st));
+    LP_CUDA_OK(cudaMemcpyAsync(dxo, xo.data(), sizeof(int) * xo.size(), cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaMemcpyAsync(dyo, yo.data(), sizeof(int) * yo.size(), cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaMemcpyAsync(dxa, xa.data(), sizeof(short) * xa.size(), cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaMemcpyAsync(dyb, yb.data(), sizeof(short) * yb.size(), cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope below
+    LinearParams p{a.src, a.src_img_stride, a.src_row_stride, a.dst, a.dst_img_stride,
+                   a.dst_row_stride, a.crop_x, a.crop_y, a.crop_w, a.crop_h, a.dst_w, a.dst_h, C,
+                   dxo, dxa, dyo, dyb};
+    dim3 grid(ceil_div(a.dst_w * C, 256), a.dst_h, a.n);
+    resize_linear_kernel<<<grid, 256, 0, st>>>(p);
+    g_launches++;
+    LP_CUDA_OK(cudaGetLastError());
+    LP_CUDA_OK(cudaFreeAsync(dxo, st));
+    LP_CUDA_OK(cudaFreeAsync(dyo, st));
+    LP_CUDA_OK(cudaFreeAsync(dxa, st));
+    LP_CUDA_OK(cudaFreeAsync(dyb, st));
+    return LP_OK;
+}
+
+}  // namespace lp

@@ -1,0 +1,7 @@
+"""Case tables shared by the golden generator and the tests."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from make_golden import BLEND_CASES, JPEG_CASES, ORIENT_SRC, RESIZE_CASES  # noqa: E402,F401

@@ -1,0 +1,96 @@
+"""Generates tests/golden/golden.npz from the REFERENCE ITSELF (oracle/_ref: lilliput's own
+opencv.cpp shims linked against its vendored OpenCV/libjpeg-turbo), so the restated oracle
+(oracle/*.c) and the CUDA path can be pinned on machines where /root/reference is absent.
+
+Run in the build container:  python tests/golden/make_golden.py
+Inputs are either regenerated from seeds (lilliput_b200.synth) or stored in the file.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from lilliput_b200 import abi  # noqa: E402
+from lilliput_b200.synth import synth_image  # noqa: E402
+
+RESIZE_CASES = [  # (seed, src_w, src_h, ch, crop(x,y,w,h) or None, dst_w, dst_h, interpolation)
+    (11, 1920, 1080, 3, (420, 0, 1080, 1080), 256, 256, 3),   # BASELINE config 2 geometry
+    (12, 800, 297, 3, (251, 0, 297, 297), 256, 256, 3),       # config 1 geometry
+    (13, 721, 1283, 3, None, 257, 255, 3),
+    (14, 300, 200, 3, None, 299, 199, 3),
+    (15, 640, 480, 4, (80, 0, 480, 480), 160, 160, 3),        # integer scale 3
+    (16, 512, 512, 3, None, 256, 256, 3),                     # 2x2 fast path
+    (17, 1024, 512, 4, None, 256, 128, 3),                    # 4x4 fast path
+    (18, 100, 100, 3, None, 250, 250, 3),                     # upscale: area-mode bilinear
+    (19, 100, 200, 4, None, 50, 300, 3),                      # mixed
+    (20, 333, 217, 3, None, 120, 97, 1),                      # INTER_LINEAR
+    (21, 64, 48, 1, None, 23, 17, 3),
+    (22, 1300, 1942, 3, (0, 321, 1300, 1300), 512, 512, 3),
+]
+JPEG_CASES = [  # (seed, w, h, ch, quality)
+    (31, 256, 256, 3, 85), (32, 800, 297, 3, 85), (33, 17, 33, 3, 90), (34, 1, 1, 3, 85),
+    (35, 9, 16, 3, 50), (36, 15, 7, 4, 100), (37, 100, 97, 1, 85), (38, 255, 257, 4, 30),
+    (39, 640, 360, 3, 90), (40, 23, 49, 3, 1),
+]
+ORIENT_SRC = np.arange(6, dtype=np.uint8).reshape(2, 3)
+BLEND_CASES = [  # (src BGRA, dst BGRA) from SURVEY Appendix D + random
+    ((10, 20, 30, 0), (0, 0, 0, 0)), ((10, 20, 30, 0), (100, 110, 120, 255)),
+    ((10, 20, 30, 255), (100, 110, 120, 255)), ((10, 20, 30, 128), (100, 110, 120, 255)),
+    ((10, 20, 30, 128), (100, 110, 120, 0)), ((200, 100, 50, 64), (20, 40, 60, 128)),
+    ((255, 255, 255, 1), (0, 0, 0, 254)),
+]
+
+
+def main():
+    ref = abi.load_reference()
+    out = {}
+    for (seed, sw, sh, ch, crop, dw, dh, interp) in RESIZE_CASES:
+        img = synth_image(seed, sw, sh, ch, noise=12.0)
+        out[f"resize_{seed}"] = ref.resize(img, dw, dh, crop=crop, interpolation=interp)
+    enc_sha = {}
+    for (seed, w, h, ch, q) in JPEG_CASES:
+        img = synth_image(seed, w, h, ch, noise=8.0)
+        data = ref.encode(".jpeg", img, {abi.JpegQuality: q})
+        enc_sha[f"{seed}"] = hashlib.sha256(data).hexdigest()
+        out[f"jpeg_{seed}"] = np.frombuffer(data, dtype=np.uint8)
+        out[f"jpegdec_{seed}"] = ref.decode(data)
+    out["jpeg_sha"] = np.array([f"{k}:{v}" for k, v in enc_sha.items()])
+    # other chroma layouts and restart intervals (made with cv2's libjpeg; decoded by the reference)
+    import cv2
+    img = synth_image(41, 203, 151, 3, noise=8.0)
+    for sf, name in [(0x111111, "444"), (0x211111, "422"), (0x121111, "440"), (0x411111, "411"),
+                     (0x221111, "420")]:
+        for rst in (0, 3):
+            ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 88,
+                                                cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf,
+                                                cv2.IMWRITE_JPEG_RST_INTERVAL, rst])
+            data = buf.tobytes()
+            out[f"jpegvar_{name}_{rst}"] = np.frombuffer(data, dtype=np.uint8)
+            out[f"jpegvardec_{name}_{rst}"] = ref.decode(data)
+    for o in range(1, 9):
+        out[f"orient_{o}"] = ref.orient(ORIENT_SRC, o)
+    img = synth_image(42, 37, 23, 3, noise=10.0)
+    for o in range(1, 9):
+        out[f"orient3_{o}"] = ref.orient(img, o)
+    # end-to-end config 1: the reference's own fixture through Transform
+    c1 = open("/root/reference/testdata/ferry_sunset.jpg", "rb").read()
+    opt = abi.ImageOptions(FileType=".jpeg", Width=256, Height=256, ResizeMethod=abi.ImageOpsFit,
+                           NormalizeOrientation=True, EncodeOptions={abi.JpegQuality: 85})
+    out["c1_input"] = np.frombuffer(c1, dtype=np.uint8)
+    out["c1_output"] = np.frombuffer(ref.transform(c1, opt), dtype=np.uint8)
+    # an EXIF-rotated fixture (orientation 6) through Transform
+    c6 = open("/root/reference/data/sunrise.jpg", "rb").read()
+    opt6 = abi.ImageOptions(FileType=".jpeg", Width=64, Height=64, ResizeMethod=abi.ImageOpsFit,
+                            NormalizeOrientation=True, EncodeOptions={abi.JpegQuality: 85})
+    out["c6_input"] = np.frombuffer(c6, dtype=np.uint8)
+    out["c6_output"] = np.frombuffer(ref.transform(c6, opt6), dtype=np.uint8)
+    out["c6_decoded"] = ref.decode(c6)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden.npz"), **out)
+    print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(ROOT, "tests/golden/golden.npz")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -163,6 +163,12 @@ int lp_resize_area_dev(const uint8_t* src, size_t src_image_stride, size_t src_r
                        size_t dst_image_stride, size_t dst_row_stride, int dst_w, int dst_h, int n,
                        void* stream);
 
+/* Batched baseline-JPEG encode of device frames into device memory (ref opencv.cpp:185-194
+ * per image).  out_len[i] = 0 when image i did not fit in out_cap. */
+int lp_jpeg_encode_dev(const uint8_t* frames, size_t frame_img_stride, size_t frame_row_stride,
+                       int width, int height, int channels, int quality, int n, uint8_t* out,
+                       size_t out_cap, uint32_t* out_len, void* stream);
+
 /* Library-owned device/pinned memory helpers so tests and bench need no torch. */
 void* lp_dev_alloc(size_t bytes);
 void lp_dev_free(void* p);

@@ -236,3 +236,105 @@ def load_reference() -> Lib:
     if "ref" not in _cache:
         _cache["ref"] = Lib(REF_LIB)
     return _cache["ref"]
+
+
+# ----------------------------------------------------------------------------------------------
+# Batch API (CUDA library only)
+# ----------------------------------------------------------------------------------------------
+STAGE_NAMES = ["huff_decode", "idct_color", "resize", "enc_transform", "enc_entropy", "total"]
+
+
+class Batch:
+    """lp_batch_*: N independent JPEGs -> Fit/area resize -> JPEG on one GPU."""
+
+    def __init__(self, lib: Lib, device: int, max_images: int, src_w: int, src_h: int, dst_w: int,
+                 dst_h: int, quality: int, max_in_bytes: int, out_cap: int = 65536,
+                 resize_method: int = ImageOpsFit, chunk: int = 0):
+        self.lib = lib
+        l = lib.l
+        l.lp_batch_create.restype = C.c_void_p
+        l.lp_batch_create.argtypes = [C.POINTER(_BatchConfig)]
+        l.lp_batch_destroy.argtypes = [C.c_void_p]
+        for name in ("lp_batch_stage",):
+            getattr(l, name).restype = C.c_int
+        l.lp_batch_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        l.lp_batch_run.restype = C.c_int
+        l.lp_batch_run.argtypes = [C.c_void_p, C.c_void_p]
+        l.lp_batch_fetch.restype = C.c_int
+        l.lp_batch_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.lp_batch_transform.restype = C.c_int
+        l.lp_batch_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+        l.lp_batch_last_launches.restype = C.c_int
+        l.lp_batch_last_launches.argtypes = [C.c_void_p]
+        cfg = _BatchConfig(device, max_images, src_w, src_h, dst_w, dst_h, resize_method, quality,
+                           max_in_bytes, out_cap, chunk)
+        self.h = l.lp_batch_create(C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("lp_batch_create failed (no CUDA device / out of memory)")
+        self.max_images = max_images
+        self.out_cap = out_cap
+
+    def close(self):
+        if self.h:
+            self.lib.l.lp_batch_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def _ptr_arrays(bufs):
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)()
+        lens = (C.c_size_t * n)()
+        keep = []
+        for i, b in enumerate(bufs):
+            if isinstance(b, tuple):  # (address, length): already-pinned memory
+                ptrs[i], lens[i] = b
+            else:
+                a = np.frombuffer(b, dtype=np.uint8)
+                keep.append(a)
+                ptrs[i], lens[i] = a.ctypes.data, a.size
+        return ptrs, lens, keep
+
+    def stage(self, bufs):
+        ptrs, lens, keep = self._ptr_arrays(bufs)
+        status = (C.c_int * len(bufs))()
+        rc = self.lib.l.lp_batch_stage(self.h, ptrs, lens, len(bufs), status)
+        if rc:
+            raise LilliputError(rc)
+        return list(status)
+
+    def run(self):
+        ms = (C.c_float * 6)()
+        rc = self.lib.l.lp_batch_run(self.h, ms)
+        if rc:
+            raise LilliputError(rc)
+        return dict(zip(STAGE_NAMES, list(ms)))
+
+    def fetch(self, n):
+        out = np.empty((n, self.out_cap), dtype=np.uint8)
+        ptrs = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
+        lens = (C.c_size_t * n)()
+        status = (C.c_int * n)()
+        rc = self.lib.l.lp_batch_fetch(self.h, ptrs, lens, status)
+        if rc:
+            raise LilliputError(rc)
+        return [out[i, : lens[i]].tobytes() for i in range(n)], list(status)
+
+    def transform_into(self, ptrs, lens, n, out_ptrs, out_lens, status):
+        """Raw call for bench.py: all arrays prebuilt (no Python work in the timed region)."""
+        return self.lib.l.lp_batch_transform(self.h, ptrs, lens, n, out_ptrs, out_lens, status)
+
+    def transform(self, bufs):
+        n = len(bufs)
+        ptrs, lens, keep = self._ptr_arrays(bufs)
+        out = np.empty((n, self.out_cap), dtype=np.uint8)
+        out_ptrs = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
+        out_lens = (C.c_size_t * n)()
+        status = (C.c_int * n)()
+        rc = self.lib.l.lp_batch_transform(self.h, ptrs, lens, n, out_ptrs, out_lens, status)
+        if rc:
+            raise LilliputError(rc)
+        return [out[i, : out_lens[i]].tobytes() for i in range(n)], list(status)
+
+    def last_launches(self):
+        return self.lib.l.lp_batch_last_launches(self.h)

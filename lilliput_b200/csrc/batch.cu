@@ -310,8 +310,10 @@ extern "C" int lp_batch_run(lp_batch* b, float* stage_ms) {
             LP_CUDA_OK(cudaEventElapsedTime(&t, ev[2], ev[3])); stage_ms[LP_STAGE_RESIZE] += t;
             LP_CUDA_OK(cudaEventElapsedTime(&t, ev[3], ev[4])); stage_ms[LP_STAGE_ENC_TRANSFORM] += t;
             LP_CUDA_OK(cudaEventElapsedTime(&t, ev[4], ev[5])); stage_ms[LP_STAGE_ENC_ENTROPY] += t;
-            LP_CUDA_OK(cudaEventElapsedTime(&t, ev[0], ev[5])); stage_ms[LP_STAGE_TOTAL] += t;
         }
+        float t;
+        LP_CUDA_OK(cudaEventElapsedTime(&t, b->ev[0], b->ev[(size_t)(nchunks - 1) * 6 + 5]));
+        stage_ms[LP_STAGE_TOTAL] = t;  // first launch of the first chunk -> end of the last chunk
     }
     return LP_OK;
 }
@@ -428,5 +430,33 @@ extern "C" int lp_resize_area_time_dev(const uint8_t* src, size_t src_image_stri
     if (ms_per_iter) *ms_per_iter = ms / iters;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    return LP_OK;
+}
+
+// Encode `n` packed device frames (shared geometry) to baseline JPEG in device memory.
+// out: n * out_cap bytes, out_len: n uint32 (0 = did not fit).  Used by bench.py to build the
+// synthetic corpus and by tests; same kernels as opencv_encoder_write.
+extern "C" int lp_jpeg_encode_dev(const uint8_t* frames, size_t frame_img_stride, size_t frame_row_stride,
+                                  int width, int height, int channels, int quality, int n, uint8_t* out,
+                                  size_t out_cap, uint32_t* out_len, void* stream) {
+    if (ensure_device()) return LP_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void* scratch = nullptr;
+    LP_CUDA_OK(cudaMallocAsync(&scratch, jpeg_encode_scratch_bytes(width, height, channels, n, out_cap), st));
+    JpegEncodeBatch e;
+    e.frames = frames;
+    e.frame_img_stride = frame_img_stride;
+    e.frame_row_stride = frame_row_stride;
+    e.width = width; e.height = height; e.channels = channels;
+    e.quality = quality;
+    e.n = n;
+    e.out = out;
+    e.out_cap = out_cap;
+    e.out_len = out_len;
+    e.scratch = scratch;
+    int rc = jpeg_encode_launch(e, st, nullptr);
+    cudaFreeAsync(scratch, st);
+    if (rc) return rc;
+    LP_CUDA_OK(cudaStreamSynchronize(st));
     return LP_OK;
 }

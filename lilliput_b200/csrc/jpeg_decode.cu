@@ -89,7 +89,7 @@ __device__ __forceinline__ int receive_extend(BitReader& b, int n) {
 __global__ void jpeg_huff_decode_kernel(JpegDecodeItem* items, const JpegHuffSet* tables,
                                         const uint8_t* scan, int16_t* coef, int n) {
     __shared__ uint8_t zz[64];
-    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) zz[k] = c_zigzag[k];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -248,11 +248,9 @@ __global__ void __launch_bounds__(128)
     jpeg_fdct_quant_kernel(const uint8_t* frames, size_t img_stride, size_t row_stride, EncGeom g,
                            const EncConst* ec, int16_t* coef, int n) {
     __shared__ uint16_t sq[2][64];
-    __shared__ uint8_t szz[64];
     if (threadIdx.x < 64) {
         sq[0][threadIdx.x] = ec->q[0][threadIdx.x];
         sq[1][threadIdx.x] = ec->q[1][threadIdx.x];
-        szz[threadIdx.x] = ec->zigzag[threadIdx.x];
     }
     __syncthreads();
     const int blocks_per_img = g.mcus_x * g.mcus_y * g.blocks_per_mcu;

@@ -66,3 +66,36 @@ extern "C" double ref_bench_transform(const uint8_t* const* in, const size_t* in
     if (first_error) *first_error = err.load();
     return (double)done.load() / el;
 }
+
+// Exactly `total` Transforms spread over `threads` workers (round-robin over the n inputs);
+// returns elapsed seconds (<0 on error).  One bench.py "step" of the reference arm.
+extern "C" double ref_transform_many(const uint8_t* const* in, const size_t* in_len, int n,
+                                     const lp_image_options* opt, int max_size, int threads,
+                                     size_t out_cap, long total, int* first_error) {
+    cv::setNumThreads(1);
+    std::atomic<long> next{0};
+    std::atomic<int> err{0};
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) {
+        pool.emplace_back([&]() {
+            std::vector<uint8_t> out(out_cap);
+            for (;;) {
+                long k = next.fetch_add(1);
+                if (k >= total || err.load()) break;
+                int i = (int)(k % n);
+                size_t len = 0;
+                int rc = lp_transform(in[i], in_len[i], opt, out.data(), out.size(), &len, max_size);
+                if (rc != 0) {
+                    int z = 0;
+                    err.compare_exchange_strong(z, rc);
+                    break;
+                }
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (first_error) *first_error = err.load();
+    return err.load() ? -1.0 : el;
+}

@@ -1,0 +1,77 @@
+"""GPU: the batch entry points against per-image Transform semantics and the oracle."""
+import numpy as np
+import pytest
+
+from lilliput_b200 import abi
+from lilliput_b200.synth import synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _corpus(oracle, n, w, h, q=90):
+    return [oracle.jpeg_encode(synth_image(1000 + i, w, h, 3), q) for i in range(n)]
+
+
+def test_batch_matches_oracle_small(cuda_lib, oracle):
+    n, w, h = 13, 320, 180
+    files = _corpus(oracle, n, w, h)
+    b = abi.Batch(cuda_lib, 0, 16, w, h, 64, 64, 85, max_in_bytes=sum(map(len, files)) + 4096,
+                  out_cap=32768, chunk=5)  # 3 chunks, last one ragged
+    try:
+        outs, status = b.transform(files)
+        assert status == [0] * n
+        for f, o in zip(files, outs):
+            dec, _ = oracle.jpeg_decode(f)
+            assert o == oracle.jpeg_encode(oracle.fit(dec, 64, 64), 85)
+        assert b.last_launches() > 0
+    finally:
+        b.close()
+
+
+def test_batch_equals_per_image_transform_1080p(cuda_lib, oracle):
+    """BASELINE config 2 geometry on a few images: batch output == lp_transform output == oracle."""
+    n, w, h = 6, 1920, 1080
+    files = _corpus(oracle, n, w, h)
+    opt = abi.ImageOptions(FileType=".jpeg", Width=256, Height=256, ResizeMethod=abi.ImageOpsFit,
+                           NormalizeOrientation=True, EncodeOptions={abi.JpegQuality: 85})
+    b = abi.Batch(cuda_lib, 0, 8, w, h, 256, 256, 85, max_in_bytes=sum(map(len, files)) + 4096)
+    try:
+        outs, status = b.transform(files)
+        assert status == [0] * n
+        for i, (f, o) in enumerate(zip(files, outs)):
+            assert o == cuda_lib.transform(f, opt)
+            if i < 2:
+                dec, _ = oracle.jpeg_decode(f)
+                assert o == oracle.jpeg_encode(oracle.fit(dec, 256, 256), 85)
+    finally:
+        b.close()
+
+
+def test_batch_per_item_errors(cuda_lib, oracle):
+    w, h = 160, 120
+    good = _corpus(oracle, 3, w, h)
+    wrong_size = oracle.jpeg_encode(synth_image(5, 96, 64, 3), 90)
+    truncated = good[1][: len(good[1]) // 3]
+    files = [good[0], wrong_size, b"\xff\xd8\xff garbage", truncated, good[2]]
+    b = abi.Batch(cuda_lib, 0, 8, w, h, 32, 32, 85, max_in_bytes=1 << 20)
+    try:
+        outs, status = b.transform(files)
+        assert status[0] == 0 and status[4] == 0
+        assert status[1] == -10 and status[2] != 0
+        assert outs[1] == b"" and outs[2] == b""
+        # a truncated entropy segment decodes like libjpeg-turbo does (zeros after the end of
+        # data), so it is reported as success with a full-size output
+        assert status[3] in (0, -2)
+        dec, _ = oracle.jpeg_decode(files[0])
+        assert outs[0] == oracle.jpeg_encode(oracle.fit(dec, 32, 32), 85)
+    finally:
+        b.close()
+
+
+def test_empty_batch(cuda_lib):
+    b = abi.Batch(cuda_lib, 0, 4, 64, 64, 8, 8, 85, max_in_bytes=4096)
+    try:
+        outs, status = b.transform([])
+        assert outs == [] and status == []
+    finally:
+        b.close()

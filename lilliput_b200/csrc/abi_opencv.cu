@@ -201,13 +201,23 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
     const size_t scan_bytes = round_up((size_t)h.scan_length + 16, (size_t)256);
     const size_t coef_bytes = round_up((size_t)blocks * 64 * sizeof(int16_t), (size_t)256);
     const size_t plane_b = round_up((size_t)plane_bytes, (size_t)256);
-    const size_t total = 1024 + round_up(sizeof(JpegHuffSet), (size_t)256) + scan_bytes + coef_bytes + plane_b;
+    const bool parallel = h.restart_interval == 0;
+    const size_t clean_b = parallel ? round_up(huff_clean_bytes(h.scan_length), (size_t)256) : 0;
+    const size_t states_b = parallel ? round_up(2 * huff_nsub(h.scan_length) * 8, (size_t)256) : 0;
+    const size_t nslots_b = parallel ? round_up(huff_nsub(h.scan_length) * 4, (size_t)256) : 0;
+    const size_t dcdiff_b = parallel ? round_up((size_t)blocks * 2, (size_t)256) : 0;
+    const size_t total = 1024 + round_up(sizeof(JpegHuffSet), (size_t)256) + scan_bytes + coef_bytes + plane_b +
+                         clean_b + states_b + nslots_b + dcdiff_b;
     LP_CUDA_OK(cudaMallocAsync(&scratch, total, st));
     JpegDecodeItem* d_item = reinterpret_cast<JpegDecodeItem*>(scratch);
     JpegHuffSet* d_hs = reinterpret_cast<JpegHuffSet*>(scratch + 1024);
     uint8_t* d_scan = scratch + 1024 + round_up(sizeof(JpegHuffSet), (size_t)256);
     int16_t* d_coef = reinterpret_cast<int16_t*>(d_scan + scan_bytes);
     uint8_t* d_planes = reinterpret_cast<uint8_t*>(d_coef) + coef_bytes;
+    uint8_t* d_clean = d_planes + plane_b;
+    uint8_t* d_states = d_clean + clean_b;
+    uint8_t* d_nslots = d_states + states_b;
+    uint8_t* d_dcdiff = d_nslots + nslots_b;
     LP_CUDA_OK(cudaMemcpyAsync(d_item, &it, sizeof(it), cudaMemcpyHostToDevice, st));
     LP_CUDA_OK(cudaMemcpyAsync(d_hs, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
     LP_CUDA_OK(cudaMemcpyAsync(d_scan, d->data + h.scan_offset, h.scan_length, cudaMemcpyHostToDevice, st));
@@ -223,6 +233,11 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
     b.max_blocks_per_image = (int)blocks;
     b.max_width = h.width;
     b.max_height = h.height;
+    b.use_parallel_huffman = parallel;
+    b.clean = d_clean;
+    b.states = d_states;
+    b.nslots = reinterpret_cast<uint32_t*>(d_nslots);
+    b.dcdiff = reinterpret_cast<int16_t*>(d_dcdiff);
     int rc = jpeg_decode_launch(b, st, nullptr);
     JpegDecodeItem back;
     if (!rc) {

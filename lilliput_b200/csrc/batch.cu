@@ -38,6 +38,11 @@ struct lp_batch {
     uint8_t* d_frames = nullptr;
     uint8_t* d_resized = nullptr;
     uint8_t* d_enc_scratch = nullptr;
+    uint8_t* d_clean = nullptr;     // parallel Huffman: unstuffed bit strings (whole batch)
+    void* d_states = nullptr;       // parallel Huffman: subsequence exit states
+    uint32_t* d_nslots = nullptr;
+    int16_t* d_dcdiff = nullptr;    // per chunk slot
+    bool parallel_huffman = true;
     uint8_t* d_out = nullptr;
     uint32_t* d_out_len = nullptr;
     // host
@@ -59,6 +64,7 @@ static void batch_free(lp_batch* b) {
     cudaFree(b->d_scan); cudaFree(b->d_items); cudaFree(b->d_tables); cudaFree(b->d_coef);
     cudaFree(b->d_planes); cudaFree(b->d_frames); cudaFree(b->d_resized); cudaFree(b->d_enc_scratch);
     cudaFree(b->d_out); cudaFree(b->d_out_len);
+    cudaFree(b->d_clean); cudaFree(b->d_states); cudaFree(b->d_nslots); cudaFree(b->d_dcdiff);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_out_len) cudaFreeHost(b->h_out_len);
     if (b->h_items_back) cudaFreeHost(b->h_items_back);
@@ -112,6 +118,10 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
     BALLOC(b->d_frames, (size_t)b->chunk * b->frame_bytes + 256);
     BALLOC(b->d_resized, N * b->resized_bytes + 256);
     BALLOC(b->d_enc_scratch, jpeg_encode_scratch_bytes(b->out_w, b->out_h, 3, b->chunk, cfg->out_cap));
+    BALLOC(b->d_clean, cfg->max_in_bytes + 64 * N + 4096);
+    BALLOC(b->d_states, (cfg->max_in_bytes / 128 + 2 * N + 16) * 2 * 8);
+    BALLOC(b->d_nslots, (cfg->max_in_bytes / 128 + 2 * N + 16) * 4);
+    BALLOC(b->d_dcdiff, (size_t)b->chunk * max_blocks * sizeof(int16_t));
     BALLOC(b->d_out, N * cfg->out_cap);
     BALLOC(b->d_out_len, N * sizeof(uint32_t));
 #undef BALLOC
@@ -222,9 +232,17 @@ extern "C" int lp_batch_stage(lp_batch* b, const uint8_t* const* in, const size_
     }
     const size_t max_blocks_alloc = ((size_t)ceil_div(b->W, 8) * ceil_div(b->H, 8)) * 3 +
                                     4 * ((size_t)ceil_div(b->W, 8) + ceil_div(b->H, 8)) + 16;
+    size_t clean_off = 0, state_off = 0;
+    b->parallel_huffman = true;
     for (int k = 0; k < n; k++) {
         JpegDecodeItem& it = b->items[k];
         if (b->parse_status[k]) continue;
+        if (it.restart_interval) b->parallel_huffman = false;  // RSTn streams take the serial kernel
+        it.clean_off = clean_off;
+        it.state_off = state_off;
+        it.dcdiff_off = (uint64_t)(k % b->chunk) * b->blocks;
+        clean_off += huff_clean_bytes(it.scan_len);
+        state_off += 2 * huff_nsub(it.scan_len);
         const uint32_t nb = it.block_off[2] + (uint32_t)it.bw[2] * it.bh[2];
         if (nb > max_blocks_alloc) { b->parse_status[k] = LP_ERR_UNSUPPORTED; it.status = -1; continue; }
         const int slot = k % b->chunk;
@@ -265,6 +283,11 @@ extern "C" int lp_batch_run(lp_batch* b, float* stage_ms) {
         d.max_blocks_per_image = (int)b->blocks;
         d.max_width = b->W;
         d.max_height = b->H;
+        d.use_parallel_huffman = b->parallel_huffman;
+        d.clean = b->d_clean;
+        d.states = b->d_states;
+        d.nslots = b->d_nslots;
+        d.dcdiff = b->d_dcdiff;
         int rc = jpeg_decode_launch(d, b->st, ev[1]);
         if (rc) return rc;
         LP_CUDA_OK(cudaEventRecord(ev[2], b->st));

@@ -336,7 +336,11 @@ __global__ void jpeg_upsample_color_kernel(const JpegDecodeItem* items, const ui
 int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_huff) {
     if (b.n <= 0) return LP_OK;
     LP_CUDA_OK(cudaMemsetAsync(b.coef, 0, b.coef_elems_total * sizeof(int16_t), st));
-    {
+    if (b.use_parallel_huffman) {
+        JpegHuffParallelArgs a{b.items, b.tables, b.scan, b.clean, b.states, b.nslots, b.coef, b.dcdiff, b.n};
+        int rc = jpeg_huff_parallel_launch(a, st);
+        if (rc) return rc;
+    } else {
         const int threads = 32;
         jpeg_huff_decode_kernel<<<ceil_div(b.n, threads), threads, 0, st>>>(b.items, b.tables, b.scan,
                                                                            b.coef, b.n);

@@ -66,6 +66,12 @@ struct JpegDecodeItem {
     int32_t td[3], ta[3];
     int32_t status;         // written by the decode kernel: 0 ok, <0 corrupt
     int32_t frame_channels; // 1 or 3
+    // parallel Huffman path (jpeg_huff_parallel.cu)
+    uint64_t clean_off;     // byte offset of this image's unstuffed bit string
+    uint64_t state_off;     // SubState offset (2 * nsub entries reserved)
+    uint64_t dcdiff_off;    // int16 offset of this image's DC-difference array (MCU order)
+    uint32_t clean_len;     // written by jpeg_unstuff_kernel
+    uint32_t pad_;
 };
 
 // Huffman decode tables for one image (or many images sharing them), device format.
@@ -89,7 +95,28 @@ struct JpegDecodeBatch {
     size_t coef_elems_total;    // for the memset
     int max_blocks_per_image;
     int max_width, max_height;
+    // parallel Huffman scratch (all device); used when use_parallel_huffman is set
+    bool use_parallel_huffman = false;
+    uint8_t* clean = nullptr;
+    void* states = nullptr;      // SubState[]
+    uint32_t* nslots = nullptr;
+    int16_t* dcdiff = nullptr;
 };
+// Scratch sizing for the parallel Huffman path, per image with `scan_len` entropy-coded bytes.
+inline size_t huff_clean_bytes(size_t scan_len) { return ((scan_len + 32 + 15) / 16) * 16; }
+inline size_t huff_nsub(size_t scan_len) { return scan_len * 8 / 1024 + 2; }
+struct JpegHuffParallelArgs {
+    JpegDecodeItem* items;
+    const JpegHuffSet* tables;
+    const uint8_t* scan;
+    uint8_t* clean;
+    void* states;
+    uint32_t* nslots;
+    int16_t* coef;
+    int16_t* dcdiff;
+    int n;
+};
+int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st);
 // Launches: memset(coef) -> huffman decode -> idct -> upsample+colour.
 int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_huff);
 

@@ -204,7 +204,7 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
     const bool parallel = h.restart_interval == 0;
     const size_t clean_b = parallel ? round_up(huff_clean_bytes(h.scan_length), (size_t)256) : 0;
     const size_t states_b = parallel ? round_up(2 * huff_nsub(h.scan_length) * 8, (size_t)256) : 0;
-    const size_t nslots_b = parallel ? round_up(huff_nsub(h.scan_length) * 4, (size_t)256) : 0;
+    const size_t nslots_b = parallel ? round_up(2 * huff_nsub(h.scan_length) * 4, (size_t)256) : 0;
     const size_t dcdiff_b = parallel ? round_up((size_t)blocks * 2, (size_t)256) : 0;
     const size_t total = 1024 + round_up(sizeof(JpegHuffSet), (size_t)256) + scan_bytes + coef_bytes + plane_b +
                          clean_b + states_b + nslots_b + dcdiff_b;

@@ -120,7 +120,7 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
     BALLOC(b->d_enc_scratch, jpeg_encode_scratch_bytes(b->out_w, b->out_h, 3, b->chunk, cfg->out_cap));
     BALLOC(b->d_clean, cfg->max_in_bytes + 64 * N + 4096);
     BALLOC(b->d_states, (cfg->max_in_bytes / 128 + 2 * N + 16) * 2 * 8);
-    BALLOC(b->d_nslots, (cfg->max_in_bytes / 128 + 2 * N + 16) * 4);
+    BALLOC(b->d_nslots, (cfg->max_in_bytes / 128 + 2 * N + 16) * 2 * 4);
     BALLOC(b->d_dcdiff, (size_t)b->chunk * max_blocks * sizeof(int16_t));
     BALLOC(b->d_out, N * cfg->out_cap);
     BALLOC(b->d_out_len, N * sizeof(uint32_t));

@@ -298,37 +298,93 @@ __device__ __forceinline__ int upsampled(const JpegDecodeItem& it, const uint8_t
     return pl[(size_t)(y / vr) * stride + x / hr];  // int_upsample (replication)
 }
 
-__global__ void jpeg_upsample_color_kernel(const JpegDecodeItem* items, const uint8_t* planes,
-                                           uint8_t* frames) {
+// Thread = 16 consecutive output pixels of one row.  4:2:0 frames whose rows are 16-byte aligned take
+// the vector path (one 16-byte Y load, four 8-byte chroma loads, three 16-byte stores); everything
+// else (other samplings, grayscale, odd widths) goes pixel by pixel through upsampled().
+__global__ void __launch_bounds__(128)
+    jpeg_upsample_color_kernel(const JpegDecodeItem* items, const uint8_t* planes, uint8_t* frames) {
     const JpegDecodeItem& it = items[blockIdx.z];
     if (it.status != 0) return;
-    const int xp = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     const int y = blockIdx.y;
-    if (xp >= it.width || y >= it.height) return;
+    if (x0 >= it.width || y >= it.height) return;
     uint8_t* out = frames + it.frame_off;
     if (it.ncomp == 1) {
-        const uint8_t* pl = planes + it.plane_off + it.plane_rel[0];
-        const int stride = it.bw[0] * 8;
-        out[(size_t)y * it.width + xp] = pl[(size_t)y * stride + xp];
-        if (xp + 1 < it.width) out[(size_t)y * it.width + xp + 1] = pl[(size_t)y * stride + xp + 1];
+        const uint8_t* pl = planes + it.plane_off + it.plane_rel[0] + (size_t)y * (it.bw[0] * 8);
+        for (int x = x0; x < min(x0 + 16, it.width); x++) out[(size_t)y * it.width + x] = pl[x];
         return;
     }
-    int maxh = max(it.h[0], max(it.h[1], it.h[2])), maxv = max(it.v[0], max(it.v[1], it.v[2]));
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int x = xp + k;
-        if (x >= it.width) break;
-        const int Y = upsampled(it, planes, 0, maxh, maxv, x, y);
-        const int cb = upsampled(it, planes, 1, maxh, maxv, x, y) - 128;
-        const int cr = upsampled(it, planes, 2, maxh, maxv, x, y) - 128;
-        const int r = Y + ((91881 * cr + 32768) >> 16);
-        const int g = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
-        const int b = Y + ((116130 * cb + 32768) >> 16);
-        uint8_t* o = out + ((size_t)y * it.width + x) * 3;
-        o[0] = (uint8_t)min(max(b, 0), 255);
-        o[1] = (uint8_t)min(max(g, 0), 255);
-        o[2] = (uint8_t)min(max(r, 0), 255);
+    const bool fast = it.h[0] == 2 && it.v[0] == 2 && it.h[1] == 1 && it.v[1] == 1 && it.h[2] == 1 &&
+                      it.v[2] == 1 && (it.width & 15) == 0 && (it.frame_off & 15) == 0;
+    if (!fast) {
+        const int maxh = max(it.h[0], max(it.h[1], it.h[2])), maxv = max(it.v[0], max(it.v[1], it.v[2]));
+        for (int x = x0; x < min(x0 + 16, it.width); x++) {
+            const int Y = upsampled(it, planes, 0, maxh, maxv, x, y);
+            const int cb = upsampled(it, planes, 1, maxh, maxv, x, y) - 128;
+            const int cr = upsampled(it, planes, 2, maxh, maxv, x, y) - 128;
+            const int r = Y + ((91881 * cr + 32768) >> 16);
+            const int g = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+            const int b = Y + ((116130 * cb + 32768) >> 16);
+            uint8_t* o = out + ((size_t)y * it.width + x) * 3;
+            o[0] = (uint8_t)min(max(b, 0), 255);
+            o[1] = (uint8_t)min(max(g, 0), 255);
+            o[2] = (uint8_t)min(max(r, 0), 255);
+        }
+        return;
     }
+    const uint8_t* base = planes + it.plane_off;
+    const int sy = it.bw[0] * 8, sc = it.bw[1] * 8;
+    const uint4 yv = *reinterpret_cast<const uint4*>(base + it.plane_rel[0] + (size_t)y * sy + x0);
+    const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+    const int cw = it.dw[1], chh = it.dh[1];
+    const int cy = y >> 1;
+    const int fy = min(max((y & 1) ? cy + 1 : cy - 1, 0), chh - 1);
+    const int i0 = x0 >> 1;
+    const int il = max(i0 - 1, 0), ir = min(i0 + 8, cw - 1);
+    int cs[2][10];  // 3*near + far for chroma columns i0-1 .. i0+8, Cb and Cr
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const uint8_t* pn = base + it.plane_rel[1 + c] + (size_t)cy * sc;
+        const uint8_t* pf = base + it.plane_rel[1 + c] + (size_t)fy * sc;
+        const uint2 n8 = *reinterpret_cast<const uint2*>(pn + i0);
+        const uint2 f8 = *reinterpret_cast<const uint2*>(pf + i0);
+        cs[c][0] = 3 * pn[il] + pf[il];
+        cs[c][9] = 3 * pn[ir] + pf[ir];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            cs[c][1 + k] = 3 * (int)((n8.x >> (8 * k)) & 0xff) + (int)((f8.x >> (8 * k)) & 0xff);
+            cs[c][5 + k] = 3 * (int)((n8.y >> (8 * k)) & 0xff) + (int)((f8.y >> (8 * k)) & 0xff);
+        }
+    }
+    uint32_t ow[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) ow[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int j = 1 + (k >> 1);  // index of this pixel's chroma column in cs[]
+        int cb, cr;
+        if (k & 1) {
+            cb = (3 * cs[0][j] + cs[0][j + 1] + 7) >> 4;
+            cr = (3 * cs[1][j] + cs[1][j + 1] + 7) >> 4;
+        } else {
+            cb = (3 * cs[0][j] + cs[0][j - 1] + 8) >> 4;
+            cr = (3 * cs[1][j] + cs[1][j - 1] + 8) >> 4;
+        }
+        cb -= 128;
+        cr -= 128;
+        const int Y = (int)((yw[k >> 2] >> (8 * (k & 3))) & 0xff);
+        const int r = min(max(Y + ((91881 * cr + 32768) >> 16), 0), 255);
+        const int g = min(max(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16), 0), 255);
+        const int b = min(max(Y + ((116130 * cb + 32768) >> 16), 0), 255);
+        const int o = k * 3;
+        ow[o >> 2] |= (uint32_t)b << (8 * (o & 3));
+        ow[(o + 1) >> 2] |= (uint32_t)g << (8 * ((o + 1) & 3));
+        ow[(o + 2) >> 2] |= (uint32_t)r << (8 * ((o + 2) & 3));
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)y * it.width + x0) * 3);
+    dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+    dst[2] = make_uint4(ow[8], ow[9], ow[10], ow[11]);
 }
 
 // ------------------------------------------------------------------ launcher
@@ -355,7 +411,7 @@ int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev
         LP_CUDA_OK(cudaGetLastError());
     }
     {
-        dim3 grid(ceil_div(ceil_div(b.max_width, 2), 128), b.max_height, b.n);
+        dim3 grid(ceil_div(ceil_div(b.max_width, 16), 128), b.max_height, b.n);
         jpeg_upsample_color_kernel<<<grid, 128, 0, st>>>(b.items, b.planes, b.frames);
         g_launches++;
         LP_CUDA_OK(cudaGetLastError());

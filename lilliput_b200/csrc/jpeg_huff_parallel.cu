@@ -137,126 +137,147 @@ struct SubState {
     uint32_t phase;  // (block-in-MCU << 6) | zig-zag index expected at p
 };
 
+constexpr int kDcBits = 9, kAcBits = 11;
+
+// Per-CTA decode tables.  DC tables are indexed by the next 9 bits, AC tables by the next 11
+// (longer codes -- well under 0.1 % of symbols with the Annex-K tables -- take the canonical walk).
 struct HuffShared {
-    uint16_t look[8][512];
+    uint16_t dc_look[4][1 << kDcBits];  // (len << 8) | symbol, 0 = longer code
+    uint16_t ac_look[4][1 << kAcBits];
     int32_t maxcode[8][18];
     int32_t valoffset[8][17];
     uint8_t vals[8][256];
     uint8_t zz[64];
-    uint8_t blk_dc[16], blk_ac[16];  // table index per block-in-MCU
+    uint8_t blk_dc[16], blk_ac[16];  // table id per block-in-MCU
+    uint8_t blk_comp[16], blk_bx[16], blk_by[16];
 };
 
-// 32 bits of the clean stream starting at bit position p.
-__device__ __forceinline__ uint32_t peek32(const uint8_t* s, uint32_t p) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(s) + (p >> 5);
-    const uint32_t a = __byte_perm(w[0], 0, 0x0123), b = __byte_perm(w[1], 0, 0x0123);
-    return __funnelshift_l(b, a, p & 31);
-}
+// MSB-first bit reader over the unstuffed string: 64-bit window, one 32-bit load per 32 bits used.
+struct BitWin {
+    const uint32_t* w;  // next word to load
+    uint64_t acc;       // next bit at bit 63
+    int avail;
+    __device__ __forceinline__ void init(const uint8_t* s, uint32_t p) {
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(s) + (p >> 5);
+        const uint64_t hi = __byte_perm(base[0], 0, 0x0123), lo = __byte_perm(base[1], 0, 0x0123);
+        acc = ((hi << 32) | lo) << (p & 31);
+        avail = 64 - (int)(p & 31);
+        w = base + 2;
+    }
+    __device__ __forceinline__ void refill() {
+        if (avail < 32) {
+            acc |= (uint64_t)__byte_perm(*w++, 0, 0x0123) << (32 - avail);
+            avail += 32;
+        }
+    }
+    __device__ __forceinline__ void skip(int n) {
+        acc <<= n;
+        avail -= n;
+    }
+};
 
 // Decode symbols that START in [p, limit).  Returns the exit state and the number of coefficient
-// slots consumed.  WRITE: store AC coefficients / DC differences at absolute slot `pos`.
+// slots consumed.  WRITE: store coefficients (DC slot receives the DC *difference*) starting at
+// absolute slot `pos`.
 template <bool WRITE>
 __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
                                             uint32_t& phase, uint32_t& nslots, int nb,
-                                            // WRITE-only state:
                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it,
-                                            int16_t* coef, int16_t* dcdiff, int* status) {
+                                            int16_t* coef, int* status) {
     uint32_t blk = phase >> 6, z = phase & 63;
     uint32_t n = 0;
-    // WRITE: current block's destination
+    BitWin bw;
+    bw.init(s, p);
+    // WRITE: running block position
     int16_t* dstblk = nullptr;
-    auto locate = [&](uint64_t slot) {
-        // absolute block counter -> (mcu, k) -> plane block
-        const uint64_t babs = slot >> 6;
-        const uint32_t mcu = (uint32_t)(babs / (uint32_t)nb), k = (uint32_t)(babs % (uint32_t)nb);
-        int c = 0, kk = (int)k;
-        while (c < it->ncomp - 1 && kk >= it->h[c] * it->v[c]) {
-            kk -= it->h[c] * it->v[c];
-            c++;
-        }
-        const int bx = kk % it->h[c], by = kk / it->h[c];
-        const int mx = (int)(mcu % (uint32_t)it->mcus_x), my = (int)(mcu / (uint32_t)it->mcus_x);
-        const int X = mx * it->h[c] + bx, Y = my * it->v[c] + by;
+    int mx = 0, my = 0;
+    uint64_t remaining = 0;
+    auto set_dst = [&]() {
+        const int c = hs.blk_comp[blk];
+        const int X = mx * it->h[c] + hs.blk_bx[blk], Y = my * it->v[c] + hs.blk_by[blk];
         dstblk = coef + it->coef_off + ((size_t)it->block_off[c] + (size_t)Y * it->bw[c] + X) * 64;
     };
-    if (WRITE && pos < total_slots) locate(pos);
+    if (WRITE) {
+        if (pos >= total_slots) {
+            nslots = 0;
+            return;
+        }
+        remaining = total_slots - pos;
+        const uint32_t mcu = (uint32_t)((pos >> 6) / (uint32_t)nb);
+        mx = (int)(mcu % (uint32_t)it->mcus_x);
+        my = (int)(mcu / (uint32_t)it->mcus_x);
+        set_dst();
+    }
+    int tdc = hs.blk_dc[blk], tac = hs.blk_ac[blk];
     while (p < limit) {
-        if (WRITE && pos + n >= total_slots) break;  // all MCUs done: the rest is padding
-        const uint32_t w = peek32(s, p);
-        const int t = z == 0 ? hs.blk_dc[blk] : hs.blk_ac[blk];
-        uint32_t e = hs.look[t][w >> 23];
+        if (WRITE && n >= remaining) break;  // every MCU produced: the rest is padding
+        bw.refill();
+        const uint32_t top = (uint32_t)(bw.acc >> 32);
+        const bool isdc = z == 0;
+        uint32_t e = isdc ? hs.dc_look[tdc][top >> (32 - kDcBits)] : hs.ac_look[tac][top >> (32 - kAcBits)];
         int len, sym;
-        if (e) {
+        if (__builtin_expect(e != 0, 1)) {
             len = e >> 8;
             sym = e & 0xFF;
         } else {
-            len = 10;
-            int code = (int)(w >> 22);
+            const int t = isdc ? tdc : 4 + tac;
+            len = (isdc ? kDcBits : kAcBits) + 1;
+            int code = (int)(top >> (32 - len));
             while (len <= 16 && code > hs.maxcode[t][len]) {
                 len++;
-                code = (int)(w >> (32 - len));
+                code = (int)(top >> (32 - len));
             }
-            if (len > 16) {  // not a codeword: only possible on a wrong guess (or a corrupt stream)
+            if (len > 16) {  // not a codeword: a wrong guess, or a corrupt stream
                 if (WRITE) {
                     *status = -3;
                     break;
                 }
+                bw.skip(1);
                 p += 1;
                 continue;
             }
             sym = hs.vals[t][(code + hs.valoffset[t][len]) & 0xFF];
         }
-        if (z == 0) {
-            const int sz = sym & 15;
-            if (WRITE) {
-                int diff = 0;
-                if (sz) {
-                    const int v = (int)((w << len) >> (32 - sz));
-                    diff = v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v;
-                }
-                dcdiff[(pos + n) >> 6] = (int16_t)diff;
-            }
-            p += len + sz;
-            z = 1;
-            n += 1;
-        } else {
-            const int r = sym >> 4, sz = sym & 15;
-            if (sz == 0) {
-                p += len;
-                if (r == 15) {  // ZRL
-                    if (z + 16 > 63) {  // runs past the block (libjpeg just ends the block here)
-                        n += 64 - z;
-                        z = 0;
-                    } else {
-                        z += 16;
-                        n += 16;
-                    }
-                } else {  // EOB
-                    n += 64 - z;
-                    z = 0;
-                }
+        const int r = sym >> 4, sz = sym & 15;
+        if (sz == 0 && !isdc) {
+            // EOB, or ZRL (16 zeros); a ZRL that would leave the block ends it, as in libjpeg
+            if (r == 15 && z + 16 <= 63) {
+                z += 16;
+                n += 16;
             } else {
-                uint32_t zn = z + r;
-                if (zn > 63) {  // wrong guess (or corrupt data): close the block
-                    if (WRITE) *status = -3;
-                    p += len + sz;
-                    n += 64 - z;
-                    z = 0;
-                } else {
-                    if (WRITE) {
-                        const int v = (int)((w << len) >> (32 - sz));
-                        dstblk[hs.zz[zn]] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
-                    }
-                    p += len + sz;
-                    n += r + 1;
-                    z = zn + 1;
-                    if (z == 64) z = 0;
+                n += 64 - z;
+                z = 0;
+            }
+            bw.skip(len);
+            p += len;
+        } else {
+            const uint32_t zn = z + r;  // DC symbols have r == 0
+            const uint32_t raw = sz ? (uint32_t)((top << len) >> (32 - sz)) : 0u;
+            const int val = sz ? ((int)raw < (1 << (sz - 1)) ? (int)raw - (1 << sz) + 1 : (int)raw) : 0;
+            bw.skip(len + sz);
+            p += len + sz;
+            if (zn > 63) {  // wrong guess (or corrupt data): close the block
+                if (WRITE) *status = -3;
+                n += 64 - z;
+                z = 0;
+            } else {
+                if (WRITE) dstblk[hs.zz[zn]] = (int16_t)val;
+                n += r + 1;
+                z = (zn + 1) & 63;
+            }
+        }
+        if (z == 0) {  // block finished
+            blk++;
+            if (blk == (uint32_t)nb) {
+                blk = 0;
+                if (WRITE && ++mx == it->mcus_x) {
+                    mx = 0;
+                    my++;
                 }
             }
-            if (z == 0) {
-                blk = blk + 1 == (uint32_t)nb ? 0 : blk + 1;
-                if (WRITE && pos + n < total_slots) locate(pos + n);
-            }
+            tdc = hs.blk_dc[blk];
+            tac = hs.blk_ac[blk];
+            if (WRITE && n < remaining) set_dst();
         }
     }
     phase = (blk << 6) | z;
@@ -265,7 +286,7 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
 
 __global__ void __launch_bounds__(kHuffThreads)
     jpeg_huff_sync_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* clean,
-                          SubState* states_all, uint32_t* nslots_all, int16_t* coef, int16_t* dcdiff_all) {
+                          SubState* states_all, uint32_t* nslots_all, int16_t* coef) {
     __shared__ HuffShared hs;
     __shared__ uint32_t warp_sums[kHuffThreads / 32];
     __shared__ uint32_t s_carry;
@@ -273,24 +294,48 @@ __global__ void __launch_bounds__(kHuffThreads)
     JpegDecodeItem& it = items[blockIdx.x];
     const int tid = threadIdx.x;
     if (it.status != 0) return;
-    // ---- tables to shared memory
+    // ---- build the per-CTA tables
     {
         const JpegHuffSet* g = tables + it.table_set;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&hs);
-        static_assert(sizeof(JpegHuffSet) % 4 == 0, "table layout");
-        for (int i = tid; i < (int)(sizeof(JpegHuffSet) / 4); i += kHuffThreads) dst[i] = src[i];
+        for (int i = tid; i < 8 * 18; i += kHuffThreads) (&hs.maxcode[0][0])[i] = (&g->maxcode[0][0])[i];
+        for (int i = tid; i < 8 * 17; i += kHuffThreads) (&hs.valoffset[0][0])[i] = (&g->valoffset[0][0])[i];
+        for (int i = tid; i < 8 * 256; i += kHuffThreads) (&hs.vals[0][0])[i] = (&g->vals[0][0])[i];
+        for (int i = tid; i < 4 * (1 << kDcBits); i += kHuffThreads) (&hs.dc_look[0][0])[i] = (&g->look[0][0])[i];
+        for (int i = tid; i < 4 * (1 << kAcBits); i += kHuffThreads) (&hs.ac_look[0][0])[i] = 0;
         if (tid < 64) hs.zz[tid] = c_zigzag_p[tid];
         if (tid == 0) {
             int k = 0;
             for (int c = 0; c < it.ncomp; c++)
                 for (int j = 0; j < it.h[c] * it.v[c]; j++, k++) {
                     hs.blk_dc[k] = (uint8_t)it.td[c];
-                    hs.blk_ac[k] = (uint8_t)(4 + it.ta[c]);
+                    hs.blk_ac[k] = (uint8_t)it.ta[c];
+                    hs.blk_comp[k] = (uint8_t)c;
+                    hs.blk_bx[k] = (uint8_t)(j % it.h[c]);
+                    hs.blk_by[k] = (uint8_t)(j / it.h[c]);
                 }
             s_changed = 0;
             s_status = 0;
             s_carry = 0;
+        }
+    }
+    __syncthreads();
+    {
+        // widen the 9-bit AC lookahead tables to 11 bits, then add the 10- and 11-bit codes
+        const JpegHuffSet* g = tables + it.table_set;
+        for (int i = tid; i < 4 * (1 << kAcBits); i += kHuffThreads) {
+            const int t = i >> kAcBits, idx = i & ((1 << kAcBits) - 1);
+            uint16_t e = g->look[4 + t][idx >> (kAcBits - 9)];
+            if (!e) {
+                // no code of <= 9 bits is a prefix of idx, so the canonical walk continues at 10
+                for (int len = 10; len <= kAcBits; len++) {
+                    const int code = idx >> (kAcBits - len);
+                    if (code <= hs.maxcode[4 + t][len]) {
+                        e = (uint16_t)((len << 8) | hs.vals[4 + t][(code + hs.valoffset[4 + t][len]) & 0xFF]);
+                        break;
+                    }
+                }
+            }
+            hs.ac_look[t][idx] = e;
         }
     }
     __syncthreads();
@@ -299,34 +344,37 @@ __global__ void __launch_bounds__(kHuffThreads)
     const uint8_t* s = clean + it.clean_off;
     const uint32_t total_bits = it.clean_len * 8u;
     const uint32_t nsub = (total_bits + kSubBits - 1) / kSubBits;
-    SubState* st = states_all + it.state_off;   // two buffers of nsub each
-    uint32_t* ns = nslots_all + it.state_off / 2;  // nsub entries
+    SubState* st = states_all + it.state_off;      // two generations of nsub entries
+    uint32_t* ns = nslots_all + it.state_off;      // [0,nsub): slots; [nsub,2nsub): last-changed iteration
+    uint32_t* last = ns + nsub;
     const uint64_t total_slots = (uint64_t)it.mcus_x * it.mcus_y * nb * 64;
-    int16_t* dcdiff = dcdiff_all + it.dcdiff_off;
 
     // ---- pass 0: every subsequence from a guessed state (exact only for subsequence 0)
     for (uint32_t i = tid; i < nsub; i += kHuffThreads) {
         uint32_t p = i * kSubBits, phase = 0, n = 0;
         const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-        decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr, nullptr);
+        decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr);
         st[i] = SubState{p, phase};
         ns[i] = n;
+        last[i] = 0;
     }
     __syncthreads();
-    // ---- synchronisation: re-decode from the left neighbour's exit state until nothing changes
+    // ---- synchronisation: subsequence i is re-decoded from its left neighbour's exit state whenever
+    //      that state changed in the previous iteration; stop when an iteration changes nothing.
     SubState* cur = st;
     SubState* nxt = st + nsub;
-    for (uint32_t iter = 0; iter < nsub; iter++) {
+    for (uint32_t iter = 1; iter <= nsub; iter++) {
         for (uint32_t i = tid; i < nsub; i += kHuffThreads) {
             SubState out = cur[i];
-            if (i > 0) {
+            if (i > 0 && last[i - 1] == iter - 1) {
                 const SubState in = cur[i - 1];
                 uint32_t p = in.p, phase = in.phase, n = 0;
                 const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-                if (p < limit) decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr, nullptr);
+                if (p < limit) decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr);
                 if (p != out.p || phase != out.phase || n != ns[i]) {
                     out = SubState{p, phase};
                     ns[i] = n;
+                    last[i] = iter;   // read by thread i+1 only in the NEXT iteration (after the barrier)
                     s_changed = 1;
                 }
             }
@@ -349,7 +397,6 @@ __global__ void __launch_bounds__(kHuffThreads)
         const uint32_t v = i < nsub ? ns[i] : 0;
         uint32_t total;
         const uint32_t ex = block_excl_scan<kHuffThreads>(v, &total, warp_sums);
-        // slot counts of one image fit 32 bits up to 64 Mpixel-components; positions kept in 64
         const uint64_t pos = (uint64_t)s_carry + ex;
         if (i < nsub) {
             uint32_t p = i == 0 ? 0u : cur[i - 1].p;
@@ -358,10 +405,11 @@ __global__ void __launch_bounds__(kHuffThreads)
             const uint32_t limit = min((i + 1) * kSubBits, total_bits);
             int status = 0;
             // the slot position implied by the prefix sum must agree with the carried phase
-            if ((uint32_t)(pos % ((uint64_t)nb * 64)) != ((phase >> 6) * 64 + (phase & 63)) && pos < total_slots)
+            if (pos < total_slots &&
+                (uint32_t)(pos % ((uint64_t)nb * 64)) != ((phase >> 6) * 64 + (phase & 63)))
                 status = -3;
             if (!status && p < limit)
-                decode_span<true>(hs, s, p, limit, phase, n, nb, pos, total_slots, &it, coef, dcdiff, &status);
+                decode_span<true>(hs, s, p, limit, phase, n, nb, pos, total_slots, &it, coef, &status);
             if (status) s_status = status;
         }
         __syncthreads();
@@ -369,14 +417,13 @@ __global__ void __launch_bounds__(kHuffThreads)
         __syncthreads();
     }
     if (tid == 0) {
-        // every MCU must have been produced
-        if ((uint64_t)s_carry < total_slots) s_status = -3;
+        if ((uint64_t)s_carry < total_slots) s_status = -3;  // the stream ended before the last MCU
         if (s_status) it.status = s_status;
     }
     __syncthreads();
     if (s_status) return;
-    // ---- 3. DC differences -> DC values: per component, prefix sum in MCU (scan) order
-    int koff = 0;
+    // ---- 3. DC differences (in slot 0 of every block) -> DC values: per component, prefix sum in
+    //         MCU (scan) order
     for (int c = 0; c < it.ncomp; c++) {
         const int bpc = it.h[c] * it.v[c];
         const uint32_t nblk = (uint32_t)it.mcus_x * it.mcus_y * bpc;
@@ -385,27 +432,22 @@ __global__ void __launch_bounds__(kHuffThreads)
         for (uint32_t base = 0; base < nblk; base += kHuffThreads) {
             const uint32_t j = base + tid;
             int d = 0;
-            uint32_t mcu = 0, kk = 0;
+            int16_t* slot0 = nullptr;
             if (j < nblk) {
-                mcu = j / bpc;
-                kk = j % bpc;
-                d = dcdiff[(size_t)mcu * nb + koff + kk];
-            }
-            // signed inclusive scan via unsigned wraparound arithmetic
-            uint32_t total;
-            const uint32_t ex = block_excl_scan<kHuffThreads>((uint32_t)d, &total, warp_sums);
-            if (j < nblk) {
-                const int dc = (int)(s_carry + ex + (uint32_t)d);
+                const uint32_t mcu = j / bpc, kk = j % bpc;
                 const int bx = kk % it.h[c], by = kk / it.h[c];
                 const int mx = (int)(mcu % (uint32_t)it.mcus_x), my = (int)(mcu / (uint32_t)it.mcus_x);
                 const int X = mx * it.h[c] + bx, Y = my * it.v[c] + by;
-                coef[it.coef_off + ((size_t)it.block_off[c] + (size_t)Y * it.bw[c] + X) * 64] = (int16_t)dc;
+                slot0 = coef + it.coef_off + ((size_t)it.block_off[c] + (size_t)Y * it.bw[c] + X) * 64;
+                d = *slot0;
             }
+            uint32_t total;  // signed prefix sum through unsigned wrap-around arithmetic
+            const uint32_t ex = block_excl_scan<kHuffThreads>((uint32_t)d, &total, warp_sums);
+            if (j < nblk) *slot0 = (int16_t)(int)(s_carry + ex + (uint32_t)d);
             __syncthreads();
             if (tid == 0) s_carry += total;
             __syncthreads();
         }
-        koff += bpc;
     }
 }
 
@@ -417,8 +459,7 @@ int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st) {
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     jpeg_huff_sync_kernel<<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean,
-                                                       reinterpret_cast<SubState*>(a.states), a.nslots, a.coef,
-                                                       a.dcdiff);
+                                                       reinterpret_cast<SubState*>(a.states), a.nslots, a.coef);
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     return LP_OK;

@@ -19,6 +19,7 @@
 // and keep the vertical sums in registers.  No data is exchanged between CTAs.
 #include <cmath>
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -180,19 +181,36 @@ struct AreaParams {
     int ypad;
     int rows_per_band;
     int slot_bytes;
-    int slots;
 };
 
-constexpr int kAreaTile = 256;  // destination pixels per CTA (= consumer threads)
+constexpr int kAreaTile = 256;    // destination pixels per CTA
+constexpr int kAreaSlots = 4;     // ring depth (power of two)
+constexpr int kAreaMaxBand = 8;   // destination rows per CTA
+constexpr int kAreaMaxYTaps = 16;
 
-template <int C, int MAXT>
-__global__ void __launch_bounds__(kAreaTile + 32)
+// u8 -> fp32, exactly.  Two routes so the work can be split across pipes: I2F.U8 runs on the XU
+// pipe (16 lanes/clk/SM, the limiter when used for every byte); PRMT + FADD builds 2^23 + b and
+// subtracts 2^23 on the ALU and FMA pipes.
+template <bool XU_PIPE>
+__device__ __forceinline__ float u8_to_f32(uint32_t word, int byte) {
+    if (XU_PIPE) return (float)((word >> (8 * byte)) & 0xffu);
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)byte)) - 8388608.0f;
+}
+
+// C channels, MAXT unrolled taps (zero-weight padded), XU = taps converted on the XU pipe,
+// PPT = destination pixels per consumer thread.
+template <int C, int MAXT, int XU, int PPT>
+__global__ void __launch_bounds__(kAreaTile / PPT + 32)
     resize_area_kernel(const AreaParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int S = p.slots;
+    constexpr int S = kAreaSlots;
+    constexpr int NT = kAreaTile / PPT;  // consumer threads
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + S;
-    uint8_t* ring = smem + 128;  // S <= 8 -> 16 barriers = 128 bytes
+    int* s_yf = reinterpret_cast<int*>(smem + 64);            // [kAreaMaxBand]
+    int* s_yc = s_yf + kAreaMaxBand;                          // [kAreaMaxBand]
+    float* s_yw = reinterpret_cast<float*>(smem + 128);       // [kAreaMaxBand][kAreaMaxYTaps]
+    uint8_t* ring = smem + 128 + kAreaMaxBand * kAreaMaxYTaps * 4;
 
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
@@ -212,21 +230,29 @@ __global__ void __launch_bounds__(kAreaTile + 32)
                           (size_t)(p.crop_y + sy_begin) * p.src_row_stride +
                           (size_t)(p.crop_x + x_begin) * C;
 
-    constexpr int kConsumerWarps = kAreaTile / 32;
     if (tid == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerWarps);
+            mbar_init(&empty[s], NT / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // the band's vertical tap table
+    for (int k = tid; k < (dy1 - dy0) * kAreaMaxYTaps; k += blockDim.x) {
+        const int row = k / kAreaMaxYTaps, j = k % kAreaMaxYTaps;
+        s_yw[k] = j < p.ypad ? __ldg(p.yw + (size_t)(dy0 + row) * p.ypad + j) : 0.f;
+        if (j == 0) {
+            s_yf[row] = __ldg(p.yfirst + dy0 + row) - sy_begin;
+            s_yc[row] = __ldg(p.ycount + dy0 + row);
+        }
+    }
     __syncthreads();
 
-    if (tid >= kAreaTile) {
+    if (tid >= NT) {
         // ---------------- producer warp: one elected lane feeds the ring ----------------
-        if (tid == kAreaTile) {
+        if (tid == NT) {
             for (int r = 0; r < nrows; r++) {
-                const int s = r % S;
+                const int s = r & (S - 1);
                 if (r >= S) mbar_wait(&empty[s], ((r / S) - 1) & 1);
                 const uint8_t* g = seg0 + (size_t)r * p.src_row_stride;
                 const uint32_t delta = (uint32_t)((uintptr_t)g & 15);
@@ -238,86 +264,103 @@ __global__ void __launch_bounds__(kAreaTile + 32)
         return;
     }
 
-    // ---------------- consumers: thread = one destination pixel (C chains) ----------------
-    const int dx = dx0 + tid;
-    const bool active = dx < dx1;
+    // ---------------- consumers: thread = PPT destination pixels (C chains each) ----------------
     const int lane = tid & 31;
-    float wx[MAXT];
-    int rel = 0;
-    if (active) {
-        rel = (__ldg(p.xfirst + dx) - x_begin) * C;
+    float wx[PPT][MAXT];
+    uint32_t rel[PPT];
 #pragma unroll
-        for (int t = 0; t < MAXT; t++) wx[t] = __ldg(p.xw + (size_t)dx * MAXT + t);
-    } else {
+    for (int q = 0; q < PPT; q++) {
+        const int dx = dx0 + tid + q * NT;
+        if (dx < dx1) {
+            rel[q] = (uint32_t)(__ldg(p.xfirst + dx) - x_begin) * C;
 #pragma unroll
-        for (int t = 0; t < MAXT; t++) wx[t] = 0.f;
+            for (int t = 0; t < MAXT; t++) wx[q][t] = __ldg(p.xw + (size_t)dx * MAXT + t);
+        } else {  // zero weights: reads valid ring bytes, contributes nothing, never stored
+            rel[q] = 0;
+#pragma unroll
+            for (int t = 0; t < MAXT; t++) wx[q][t] = 0.f;
+        }
     }
     const uint32_t seg_lo = (uint32_t)((uintptr_t)seg0 & 15);
     const uint32_t stride_lo = (uint32_t)(p.src_row_stride & 15);
+    const uint32_t ring_base = smem_u32(ring);
 
-    constexpr int NA = (C * MAXT + 3) / 4;  // aligned words holding this pixel's taps
-    float buf[C];
-    float sum[C];
+    constexpr int NA = (C * MAXT + 3) / 4;  // aligned words holding one pixel's taps
+    float buf[PPT][C];
+    float sum[PPT][C];
 #pragma unroll
-    for (int c = 0; c < C; c++) buf[c] = sum[c] = 0.f;
+    for (int q = 0; q < PPT; q++)
+#pragma unroll
+        for (int c = 0; c < C; c++) buf[q][c] = sum[q][c] = 0.f;
 
-    int loaded = -1;
+    int next_row = 0;  // next ring entry to consume
     for (int dy = dy0; dy < dy1; dy++) {
-        const int yf = __ldg(p.yfirst + dy) - sy_begin;
-        const int yc = __ldg(p.ycount + dy);
+        const int yf = s_yf[dy - dy0], yc = s_yc[dy - dy0];
+        const float* yw = s_yw + (dy - dy0) * kAreaMaxYTaps;
+#pragma unroll
+        for (int q = 0; q < PPT; q++)
+#pragma unroll
+            for (int c = 0; c < C; c++) sum[q][c] = 0.f;
         for (int j = 0; j < yc; j++) {
-            const int r = yf + j;
-            while (loaded < r) {
-                loaded++;
-                const int s = loaded % S;
-                mbar_wait(&full[s], (loaded / S) & 1);
-                if (loaded == r && active) {
-                    const uint32_t delta = (seg_lo + (uint32_t)loaded * stride_lo) & 15u;
-                    const uint32_t o = delta + (uint32_t)rel;
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(
-                        ring + (size_t)s * p.slot_bytes + (o & ~3u));
+            if (yf + j == next_row) {  // otherwise the row is the one already in buf (shared boundary row)
+                const int r = next_row++;
+                const int s = r & (S - 1);
+                mbar_wait(&full[s], (r / S) & 1);
+                const uint32_t delta = (seg_lo + (uint32_t)r * stride_lo) & 15u;
+                const uint32_t slot = ring_base + (uint32_t)s * (uint32_t)p.slot_bytes;
+#pragma unroll
+                for (int q = 0; q < PPT; q++) {
+                    const uint32_t o = delta + rel[q];
+                    const uint32_t addr = slot + (o & ~3u);
                     const uint32_t sh = (o & 3u) * 8u;
                     uint32_t w[NA + 1];
 #pragma unroll
-                    for (int i = 0; i <= NA; i++) w[i] = wp[i];
+                    for (int i = 0; i <= NA; i++)
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(addr + 4u * i));
                     uint32_t a[NA];
 #pragma unroll
                     for (int i = 0; i < NA; i++) a[i] = __funnelshift_r(w[i], w[i + 1], sh);
 #pragma unroll
-                    for (int c = 0; c < C; c++) buf[c] = 0.f;
+                    for (int c = 0; c < C; c++) buf[q][c] = 0.f;
 #pragma unroll
                     for (int t = 0; t < MAXT; t++) {
 #pragma unroll
                         for (int c = 0; c < C; c++) {
                             const int i = t * C + c;
-                            const float v = (float)((a[i >> 2] >> (8 * (i & 3))) & 0xffu);
-                            buf[c] = __fmaf_rn(v, wx[t], buf[c]);
+                            const float v = (t < XU) ? u8_to_f32<true>(a[i >> 2], i & 3)
+                                                     : u8_to_f32<false>(a[i >> 2], i & 3);
+                            buf[q][c] = __fmaf_rn(v, wx[q][t], buf[q][c]);
                         }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
             }
-            const float beta = __ldg(p.yw + (size_t)dy * p.ypad + j);
+            // first tap: fma(beta, buf, 0) == beta*buf exactly (all operands >= 0)
+            const float beta = yw[j];
 #pragma unroll
-            for (int c = 0; c < C; c++)
-                sum[c] = (j == 0) ? __fmul_rn(beta, buf[c]) : __fmaf_rn(beta, buf[c], sum[c]);
+            for (int q = 0; q < PPT; q++)
+#pragma unroll
+                for (int c = 0; c < C; c++) sum[q][c] = __fmaf_rn(beta, buf[q][c], sum[q][c]);
         }
-        if (active) {
-            uint8_t* d = p.dst + (size_t)img * p.dst_img_stride + (size_t)dy * p.dst_row_stride +
-                         (size_t)dx * C;
 #pragma unroll
-            for (int c = 0; c < C; c++) d[c] = sat_rne_u8(sum[c]);
+        for (int q = 0; q < PPT; q++) {
+            const int dx = dx0 + tid + q * NT;
+            if (dx < dx1) {
+                uint8_t* d = p.dst + (size_t)img * p.dst_img_stride + (size_t)dy * p.dst_row_stride +
+                             (size_t)dx * C;
+#pragma unroll
+                for (int c = 0; c < C; c++) d[c] = sat_rne_u8(sum[q][c]);
+            }
         }
     }
-    // drain ring entries this band never needed (cannot happen for contiguous taps; keeps
-    // the producer from being left waiting if a table ever had gaps)
-    while (loaded < nrows - 1) {
-        loaded++;
-        const int s = loaded % S;
-        mbar_wait(&full[s], (loaded / S) & 1);
+    // release ring entries the band never consumed (cannot happen with contiguous taps)
+    while (next_row < nrows) {
+        const int s = next_row & (S - 1);
+        mbar_wait(&full[s], (next_row / S) & 1);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+        next_row++;
     }
 }
 
@@ -436,32 +479,55 @@ static void linear_tab(int ssize, int dsize, bool area_mode, bool clamp_ofs, std
 
 // ------------------------------------------------------------------ launcher
 
-template <int C, int MAXT>
+static size_t area_smem_bytes(int slot_bytes) {
+    return 128 + (size_t)kAreaMaxBand * kAreaMaxYTaps * 4 + (size_t)kAreaSlots * slot_bytes;
+}
+
+template <int C, int MAXT, int XU, int PPT>
 static int launch_area(const AreaParams& p, int n, cudaStream_t st) {
-    auto kern = resize_area_kernel<C, MAXT>;
-    size_t smem = 128 + (size_t)p.slots * p.slot_bytes;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    auto kern = resize_area_kernel<C, MAXT, XU, PPT>;
+    const size_t smem = area_smem_bytes(p.slot_bytes);
+    if (smem > 48 * 1024)
         LP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     dim3 grid(ceil_div(p.dw, kAreaTile), ceil_div(p.dh, p.rows_per_band), n);
-    kern<<<grid, kAreaTile + 32, smem, st>>>(p);
+    kern<<<grid, kAreaTile / PPT + 32, smem, st>>>(p);
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     return LP_OK;
 }
 
+// LP_RESIZE_VARIANT=<xu><ppt> (e.g. "21": 2 taps on the XU pipe, 1 pixel per thread) selects a
+// tuning variant of the 3-channel 6-tap kernel for A/B timing; unset = the tuned default.
+static int area_variant() {
+    static int v = [] {
+        const char* e = getenv("LP_RESIZE_VARIANT");
+        return e ? atoi(e) : -1;
+    }();
+    return v;
+}
+
 template <int C>
 static int dispatch_area(int padt, const AreaParams& p, int n, cudaStream_t st) {
+    if (C == 3 && padt == 6) {
+        switch (area_variant()) {
+            case 1: return launch_area<3, 6, 0, 1>(p, n, st);
+            case 21: return launch_area<3, 6, 2, 1>(p, n, st);
+            case 61: return launch_area<3, 6, 6, 1>(p, n, st);
+            case 2: return launch_area<3, 6, 0, 2>(p, n, st);
+            case 22: return launch_area<3, 6, 2, 2>(p, n, st);
+            case 32: return launch_area<3, 6, 3, 2>(p, n, st);
+            case 62: return launch_area<3, 6, 6, 2>(p, n, st);
+            default: return launch_area<3, 6, 2, 2>(p, n, st);
+        }
+    }
     switch (padt) {
-        case 2: return launch_area<C, 2>(p, n, st);
-        case 3: return launch_area<C, 3>(p, n, st);
-        case 4: return launch_area<C, 4>(p, n, st);
-        case 6: return launch_area<C, 6>(p, n, st);
-        case 8: return launch_area<C, 8>(p, n, st);
-        case 12: return launch_area<C, 12>(p, n, st);
-        case 16: return launch_area<C, 16>(p, n, st);
+        case 2: return launch_area<C, 2, 1, 1>(p, n, st);
+        case 3: return launch_area<C, 3, 1, 1>(p, n, st);
+        case 4: return launch_area<C, 4, 1, 1>(p, n, st);
+        case 6: return launch_area<C, 6, 2, 1>(p, n, st);
+        case 8: return launch_area<C, 8, 2, 1>(p, n, st);
+        case 12: return launch_area<C, 12, 4, 1>(p, n, st);
+        case 16: return launch_area<C, 16, 5, 1>(p, n, st);
     }
     return LP_ERR_BAD_ARGUMENT;
 }
@@ -530,8 +596,7 @@ int resize_launch(const ResizeArgs& a, cudaStream_t st) {
         int rpb = 8;
         while (rpb > 1 && ctas_per_row_group * ceil_div(a.dst_h, rpb) < 4L * kNumSMs) rpb >>= 1;
         p.rows_per_band = rpb;
-        p.slots = p.slot_bytes <= 8 * 1024 ? 4 : (p.slot_bytes <= 24 * 1024 ? 3 : 2);
-        if ((size_t)p.slots * p.slot_bytes + 128 > 200 * 1024) {
+        if (area_smem_bytes(p.slot_bytes) > 200 * 1024 || ty.padt > kAreaMaxYTaps) {
             dim3 grid(ceil_div(a.dst_w * C, 128), a.dst_h, a.n);
             resize_area_generic_kernel<<<grid, 128, 0, st>>>(p, C, tx.padt);
             g_launches++;

@@ -188,6 +188,22 @@ def cpu_reference_run(base, offs, lens, total_images, threads):
     return el
 
 
+def usable_cpus():
+    """Host threads this container may actually use: the cgroup CPU quota if one is set."""
+    n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(np.ceil(int(quota) / int(period)))))
+    except Exception:
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -220,12 +236,14 @@ def main():
     lib = abi.load_cuda()  # no fallback: raises if the .so or the GPU is missing
     lib.l.lp_set_device.argtypes = [C.c_int]
     lib.l.lp_set_device(local_rank)
-    threads = os.cpu_count() or 1
+    cores = usable_cpus()
+    # the vendored libs gain a little from 2 threads per granted CPU; more only adds contention
+    threads = min(os.cpu_count() or 1, 2 * cores)
 
     if args.impl == "reference":
         sample_n = 256
         base, arena, offs, lens = make_corpus(lib, local_rank, sample_n, 1000)
-        per_step = max(threads * 4, 512)  # bounded sample: a few hundred ms per step on a big host
+        per_step = max(threads * 8, 512)  # bounded sample: a few hundred ms per step on a big host
         for _ in range(args.warmup):
             cpu_reference_run(base, offs, lens, per_step, threads)
         t = 0.0
@@ -239,9 +257,10 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "config2: synthetic 1920x1080 baseline JPEG q90 -> Fit 256x256 JPEG q85",
                        "images_per_step": per_step, "unique_images": sample_n},
-            "cpu_baseline": {"value": round(v, 2), "unit": "images/s", "cores": threads, "kind": "reference",
+            "cpu_baseline": {"value": round(v, 2), "unit": "images/s", "cores": cores, "kind": "reference",
                              "sample": f"{per_step} Transforms per step over {sample_n} distinct inputs, "
-                                       f"{threads} threads, cv::setNumThreads(1), {cpu_model()}"},
+                                       f"{threads} threads on {cores} usable CPUs (cgroup quota; host has "
+                                       f"{os.cpu_count()} hw threads), cv::setNumThreads(1), {cpu_model()}"},
             "e2e": {"value": round(v, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -358,11 +377,12 @@ def main():
             rate = threads * 2 / probe
             total = int(max(threads * 2, rate * args.cpu_seconds))
             el = cpu_reference_run(base, offs[:sample_n], lens[:sample_n], total, threads)
-            line["cpu_baseline"] = {"value": round(total / el, 2), "unit": "images/s", "cores": threads,
+            line["cpu_baseline"] = {"value": round(total / el, 2), "unit": "images/s", "cores": cores,
                                     "kind": "reference",
                                     "sample": f"{total} Transforms over the first {sample_n} inputs of the same "
-                                              f"corpus in {el:.1f} s, {threads} threads, cv::setNumThreads(1), "
-                                              f"{cpu_model()}"}
+                                              f"corpus in {el:.1f} s, {threads} threads on {cores} usable CPUs "
+                                              f"(cgroup quota; host has {os.cpu_count()} hw threads), "
+                                              f"cv::setNumThreads(1), {cpu_model()}"}
         print(json.dumps(line))
     b.close()
     if dist:

@@ -19,15 +19,17 @@ using namespace lp;
 
 struct lp_batch {
     lp_batch_config cfg;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;       // kernels
+    cudaStream_t st_h2d = nullptr;   // input copies (pipelined transform)
+    cudaStream_t st_d2h = nullptr;   // output copies (pipelined transform)
     int chunk = 0, max_chunks = 0;
     // geometry (fixed by cfg)
     int W = 0, H = 0, out_w = 0, out_h = 0;
     int crop_x = 0, crop_y = 0, crop_w = 0, crop_h = 0;
-    // per-image layout, filled from the first staged header
+    // per-image scratch layout, fixed by the first image staged into this context
     bool layout_known = false;
-    JpegDecodeItem proto;
     uint32_t blocks = 0, plane_bytes = 0;
+    size_t max_blocks_alloc = 0;
     size_t frame_bytes = 0, resized_bytes = 0;
     // device
     uint8_t* d_scan = nullptr;
@@ -41,21 +43,25 @@ struct lp_batch {
     uint8_t* d_clean = nullptr;     // parallel Huffman: unstuffed bit strings (whole batch)
     void* d_states = nullptr;       // parallel Huffman: subsequence exit states
     uint32_t* d_nslots = nullptr;
-    int16_t* d_dcdiff = nullptr;    // per chunk slot
-    bool parallel_huffman = true;
     uint8_t* d_out = nullptr;
     uint32_t* d_out_len = nullptr;
     // host
     std::vector<JpegDecodeItem> items;
     std::vector<JpegHuffSet> tables;
     std::map<std::string, int> table_index;
+    size_t tables_uploaded = 0;
     std::vector<int> parse_status;
+    std::vector<size_t> file_dev_off;
+    size_t dev_off = 0, clean_off = 0, state_off = 0;
+    bool parallel_huffman = true;
     uint8_t* h_out = nullptr;       // pinned
     uint32_t* h_out_len = nullptr;  // pinned
     JpegDecodeItem* h_items_back = nullptr;
     int n = 0;
     int last_launches = 0;
-    std::vector<cudaEvent_t> ev;  // 6 per chunk
+    std::vector<cudaEvent_t> ev;      // 6 per chunk (stage timing)
+    std::vector<cudaEvent_t> ev_h2d;  // per chunk
+    std::vector<cudaEvent_t> ev_d2h;  // per chunk
     static constexpr int kMaxTables = 64;
 };
 
@@ -64,12 +70,16 @@ static void batch_free(lp_batch* b) {
     cudaFree(b->d_scan); cudaFree(b->d_items); cudaFree(b->d_tables); cudaFree(b->d_coef);
     cudaFree(b->d_planes); cudaFree(b->d_frames); cudaFree(b->d_resized); cudaFree(b->d_enc_scratch);
     cudaFree(b->d_out); cudaFree(b->d_out_len);
-    cudaFree(b->d_clean); cudaFree(b->d_states); cudaFree(b->d_nslots); cudaFree(b->d_dcdiff);
+    cudaFree(b->d_clean); cudaFree(b->d_states); cudaFree(b->d_nslots);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_out_len) cudaFreeHost(b->h_out_len);
     if (b->h_items_back) cudaFreeHost(b->h_items_back);
     for (auto e : b->ev) cudaEventDestroy(e);
+    for (auto e : b->ev_h2d) cudaEventDestroy(e);
+    for (auto e : b->ev_d2h) cudaEventDestroy(e);
     if (b->st) cudaStreamDestroy(b->st);
+    if (b->st_h2d) cudaStreamDestroy(b->st_h2d);
+    if (b->st_d2h) cudaStreamDestroy(b->st_d2h);
     delete b;
 }
 
@@ -97,9 +107,10 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
     b->chunk = cfg->chunk > 0 ? cfg->chunk : 512;
     b->chunk = std::min(b->chunk, cfg->max_images);
     b->max_chunks = ceil_div(cfg->max_images, b->chunk);
-    // worst-case per-image layout: 4:4:4 needs the most blocks; size for h,v <= 2 colour
+    // worst-case per-image layout: 4:4:4 needs the most blocks
     const size_t mcus = (size_t)ceil_div(b->W, 8) * ceil_div(b->H, 8);
-    const size_t max_blocks = mcus * 3 + 4 * ((size_t)ceil_div(b->W, 8) + ceil_div(b->H, 8)) + 16;
+    b->max_blocks_alloc = mcus * 3 + 4 * ((size_t)ceil_div(b->W, 8) + ceil_div(b->H, 8)) + 16;
+    const size_t max_blocks = b->max_blocks_alloc;
     b->frame_bytes = (size_t)b->W * b->H * 3;
     b->resized_bytes = (size_t)b->out_w * b->out_h * 3;
     const size_t N = cfg->max_images;
@@ -110,7 +121,9 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
         return fail();                                                                          \
     }
     if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess) return fail();
-    BALLOC(b->d_scan, cfg->max_in_bytes + 4096);
+    if (cudaStreamCreateWithFlags(&b->st_h2d, cudaStreamNonBlocking) != cudaSuccess) return fail();
+    if (cudaStreamCreateWithFlags(&b->st_d2h, cudaStreamNonBlocking) != cudaSuccess) return fail();
+    BALLOC(b->d_scan, cfg->max_in_bytes + 16 * N + 4096);
     BALLOC(b->d_items, N * sizeof(JpegDecodeItem));
     BALLOC(b->d_tables, lp_batch::kMaxTables * sizeof(JpegHuffSet));
     BALLOC(b->d_coef, (size_t)b->chunk * max_blocks * 64 * sizeof(int16_t));
@@ -121,7 +134,6 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
     BALLOC(b->d_clean, cfg->max_in_bytes + 64 * N + 4096);
     BALLOC(b->d_states, (cfg->max_in_bytes / 128 + 2 * N + 16) * 2 * 8);
     BALLOC(b->d_nslots, (cfg->max_in_bytes / 128 + 2 * N + 16) * 2 * 4);
-    BALLOC(b->d_dcdiff, (size_t)b->chunk * max_blocks * sizeof(int16_t));
     BALLOC(b->d_out, N * cfg->out_cap);
     BALLOC(b->d_out_len, N * sizeof(uint32_t));
 #undef BALLOC
@@ -129,10 +141,17 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
     if (cudaMallocHost(&b->h_out_len, N * sizeof(uint32_t)) != cudaSuccess) return fail();
     if (cudaMallocHost(&b->h_items_back, N * sizeof(JpegDecodeItem)) != cudaSuccess) return fail();
     b->ev.resize((size_t)b->max_chunks * 6);
+    b->ev_h2d.resize(b->max_chunks);
+    b->ev_d2h.resize(b->max_chunks);
     for (auto& e : b->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return fail();
+    for (auto& e : b->ev_h2d)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail();
+    for (auto& e : b->ev_d2h)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail();
     b->items.resize(N);
     b->parse_status.resize(N);
+    b->file_dev_off.resize(N);
     return b;
 }
 
@@ -164,98 +183,194 @@ static int table_set_for(lp_batch* b, const JpegHeader& h) {
     return idx;
 }
 
-extern "C" int lp_batch_stage(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int n,
-                              int* status) {
-    if (!b || !in || !in_len || n < 0 || n > b->cfg.max_images) return LP_ERR_BAD_ARGUMENT;
-    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+static void batch_begin(lp_batch* b, int n) {
     b->n = n;
     b->tables.clear();
     b->table_index.clear();
-    size_t dev_off = 0;
-    // 1) host: parse headers, fill device items
-    std::vector<size_t> file_dev_off(n, 0);
-    for (int i = 0; i < n; i++) {
+    b->tables_uploaded = 0;
+    b->dev_off = b->clean_off = b->state_off = 0;
+    b->parallel_huffman = true;
+}
+
+// Host: parse the headers of images [i0, i0+cnt), lay out their device scratch.
+static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int i0, int cnt) {
+    // input files go to HBM as they are (contiguous runs of pointers = one transfer)
+    int i = i0;
+    while (i < i0 + cnt) {
+        int j = i;
+        size_t run = in_len[i];
+        while (j + 1 < i0 + cnt && in[j + 1] == in[j] + in_len[j]) { j++; run += in_len[j]; }
+        if (b->dev_off + run > b->cfg.max_in_bytes + 16 * (size_t)b->cfg.max_images) return LP_ERR_BUF_TOO_SMALL;
+        size_t o = b->dev_off;
+        for (int k = i; k <= j; k++) { b->file_dev_off[k] = o; o += in_len[k]; }
+        b->dev_off = round_up(b->dev_off + run, (size_t)16);
+        i = j + 1;
+    }
+    for (int k = i0; k < i0 + cnt; k++) {
         JpegHeader h;
-        int rc = jpeg_parse_header(in[i], in_len[i], &h);
+        int rc = jpeg_parse_header(in[k], in_len[k], &h);
         if (!rc && !h.supported) rc = LP_ERR_UNSUPPORTED;
         if (!rc && (h.width != b->W || h.height != b->H)) rc = LP_ERR_BAD_ARGUMENT;
-        if (!rc && h.orientation != 1) rc = LP_ERR_UNSUPPORTED;  // batch path: TL only (see DESIGN.md)
+        if (!rc && h.orientation != 1) rc = LP_ERR_UNSUPPORTED;  // batch path: TL only (DESIGN.md)
         if (!rc && h.ncomp != 3) rc = LP_ERR_UNSUPPORTED;
         int ts = rc ? 0 : table_set_for(b, h);
         if (!rc && ts < 0) rc = LP_ERR_UNSUPPORTED;
-        b->parse_status[i] = rc;
-        JpegDecodeItem& it = b->items[i];
+        JpegDecodeItem& it = b->items[k];
         memset(&it, 0, sizeof(it));
+        if (!rc) {
+            it.scan_len = (uint32_t)h.scan_length;
+            it.table_set = (uint32_t)ts;
+            it.width = h.width; it.height = h.height; it.ncomp = h.ncomp;
+            it.mcus_x = h.mcus_x; it.mcus_y = h.mcus_y; it.restart_interval = h.restart_interval;
+            uint32_t blocks = 0, plane_bytes = 0;
+            for (int c = 0; c < h.ncomp; c++) {
+                it.h[c] = h.comp[c].h; it.v[c] = h.comp[c].v;
+                it.bw[c] = h.mcus_x * h.comp[c].h; it.bh[c] = h.mcus_y * h.comp[c].v;
+                it.dw[c] = (h.width * h.comp[c].h + h.maxh - 1) / h.maxh;
+                it.dh[c] = (h.height * h.comp[c].v + h.maxv - 1) / h.maxv;
+                it.block_off[c] = blocks; it.plane_rel[c] = plane_bytes;
+                blocks += (uint32_t)it.bw[c] * it.bh[c];
+                plane_bytes += (uint32_t)it.bw[c] * it.bh[c] * 64;
+                memcpy(it.qt[c], h.qt[h.comp[c].tq], sizeof(it.qt[c]));
+                it.td[c] = h.comp[c].td; it.ta[c] = h.comp[c].ta;
+            }
+            it.frame_channels = 3;
+            if (!b->layout_known) {  // the first image fixes the per-slot scratch stride
+                b->blocks = blocks;
+                b->plane_bytes = plane_bytes;
+                b->layout_known = true;
+            }
+            if (blocks > b->blocks || blocks > b->max_blocks_alloc) rc = LP_ERR_UNSUPPORTED;  // denser sampling than the slot
+        }
+        b->parse_status[k] = rc;
         it.status = rc ? -1 : 0;
         if (rc) continue;
-        it.scan_len = (uint32_t)h.scan_length;
-        it.table_set = (uint32_t)ts;
-        it.width = h.width; it.height = h.height; it.ncomp = h.ncomp;
-        it.mcus_x = h.mcus_x; it.mcus_y = h.mcus_y; it.restart_interval = h.restart_interval;
-        uint32_t blocks = 0, plane_bytes = 0;
-        for (int c = 0; c < h.ncomp; c++) {
-            it.h[c] = h.comp[c].h; it.v[c] = h.comp[c].v;
-            it.bw[c] = h.mcus_x * h.comp[c].h; it.bh[c] = h.mcus_y * h.comp[c].v;
-            it.dw[c] = (h.width * h.comp[c].h + h.maxh - 1) / h.maxh;
-            it.dh[c] = (h.height * h.comp[c].v + h.maxv - 1) / h.maxv;
-            it.block_off[c] = blocks; it.plane_rel[c] = plane_bytes;
-            blocks += (uint32_t)it.bw[c] * it.bh[c];
-            plane_bytes += (uint32_t)it.bw[c] * it.bh[c] * 64;
-            memcpy(it.qt[c], h.qt[h.comp[c].tq], sizeof(it.qt[c]));
-            it.td[c] = h.comp[c].td; it.ta[c] = h.comp[c].ta;
-        }
-        it.frame_channels = 3;
-        if (!b->layout_known) {
-            b->blocks = blocks;
-            b->plane_bytes = plane_bytes;
-            b->layout_known = true;
-        } else if (blocks > b->blocks) {
-            // per-chunk slots are sized by the first image's layout; a mixed-sampling batch keeps
-            // the largest.  (Homogeneous corpora never take this branch.)
-            b->blocks = blocks;
-            b->plane_bytes = plane_bytes;
-        }
-        it.scan_off = h.scan_offset;  // file-relative for now
-    }
-    // 2) copy files to HBM: contiguous runs of input pointers go as one transfer
-    int i = 0;
-    while (i < n) {
-        int j = i;
-        size_t run = in_len[i];
-        while (j + 1 < n && in[j + 1] == in[j] + in_len[j]) { j++; run += in_len[j]; }
-        if (dev_off + run > b->cfg.max_in_bytes) return LP_ERR_BUF_TOO_SMALL;
-        LP_CUDA_OK(cudaMemcpyAsync(b->d_scan + dev_off, in[i], run, cudaMemcpyHostToDevice, b->st));
-        size_t o = dev_off;
-        for (int k = i; k <= j; k++) { file_dev_off[k] = o; o += in_len[k]; }
-        dev_off = round_up(dev_off + run, (size_t)16);
-        i = j + 1;
-    }
-    const size_t max_blocks_alloc = ((size_t)ceil_div(b->W, 8) * ceil_div(b->H, 8)) * 3 +
-                                    4 * ((size_t)ceil_div(b->W, 8) + ceil_div(b->H, 8)) + 16;
-    size_t clean_off = 0, state_off = 0;
-    b->parallel_huffman = true;
-    for (int k = 0; k < n; k++) {
-        JpegDecodeItem& it = b->items[k];
-        if (b->parse_status[k]) continue;
         if (it.restart_interval) b->parallel_huffman = false;  // RSTn streams take the serial kernel
-        it.clean_off = clean_off;
-        it.state_off = state_off;
-        it.dcdiff_off = (uint64_t)(k % b->chunk) * b->blocks;
-        clean_off += huff_clean_bytes(it.scan_len);
-        state_off += 2 * huff_nsub(it.scan_len);
-        const uint32_t nb = it.block_off[2] + (uint32_t)it.bw[2] * it.bh[2];
-        if (nb > max_blocks_alloc) { b->parse_status[k] = LP_ERR_UNSUPPORTED; it.status = -1; continue; }
         const int slot = k % b->chunk;
-        it.scan_off += file_dev_off[k];
+        it.scan_off = b->file_dev_off[k] + h.scan_offset;
         it.coef_off = (uint64_t)slot * b->blocks * 64;
         it.plane_off = (uint64_t)slot * b->plane_bytes;
         it.frame_off = (uint64_t)slot * b->frame_bytes;
+        it.clean_off = b->clean_off;
+        it.state_off = b->state_off;
+        b->clean_off += huff_clean_bytes(it.scan_len);
+        b->state_off += 2 * huff_nsub(it.scan_len);
     }
-    LP_CUDA_OK(cudaMemcpyAsync(b->d_items, b->items.data(), (size_t)n * sizeof(JpegDecodeItem),
-                               cudaMemcpyHostToDevice, b->st));
-    if (!b->tables.empty())
-        LP_CUDA_OK(cudaMemcpyAsync(b->d_tables, b->tables.data(), b->tables.size() * sizeof(JpegHuffSet),
-                                   cudaMemcpyHostToDevice, b->st));
+    return LP_OK;
+}
+
+// H2D: the chunk's files, its items and any Huffman table sets not yet on the device.
+static int batch_upload_chunk(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int i0, int cnt,
+                              cudaStream_t st) {
+    int i = i0;
+    while (i < i0 + cnt) {
+        int j = i;
+        size_t run = in_len[i];
+        while (j + 1 < i0 + cnt && in[j + 1] == in[j] + in_len[j]) { j++; run += in_len[j]; }
+        LP_CUDA_OK(cudaMemcpyAsync(b->d_scan + b->file_dev_off[i], in[i], run, cudaMemcpyHostToDevice, st));
+        i = j + 1;
+    }
+    LP_CUDA_OK(cudaMemcpyAsync(b->d_items + i0, b->items.data() + i0, (size_t)cnt * sizeof(JpegDecodeItem),
+                               cudaMemcpyHostToDevice, st));
+    if (b->tables.size() > b->tables_uploaded) {
+        LP_CUDA_OK(cudaMemcpyAsync(b->d_tables + b->tables_uploaded, b->tables.data() + b->tables_uploaded,
+                                   (b->tables.size() - b->tables_uploaded) * sizeof(JpegHuffSet),
+                                   cudaMemcpyHostToDevice, st));
+        b->tables_uploaded = b->tables.size();
+    }
+    return LP_OK;
+}
+
+// Every kernel of the path for images [i0, i0+cnt) on stream st; ev = 6 timing events or null.
+static int batch_launch_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st, cudaEvent_t* ev) {
+    if (ev) LP_CUDA_OK(cudaEventRecord(ev[0], st));
+    JpegDecodeBatch d;
+    d.items = b->d_items + i0;
+    d.tables = b->d_tables;
+    d.scan = b->d_scan;
+    d.coef = b->d_coef;
+    d.planes = b->d_planes;
+    d.frames = b->d_frames;
+    d.n = cnt;
+    d.coef_elems_total = (size_t)cnt * b->blocks * 64;
+    d.max_blocks_per_image = (int)b->blocks;
+    d.max_width = b->W;
+    d.max_height = b->H;
+    d.use_parallel_huffman = b->parallel_huffman;
+    d.clean = b->d_clean;
+    d.states = b->d_states;
+    d.nslots = b->d_nslots;
+    int rc = jpeg_decode_launch(d, st, ev ? ev[1] : nullptr);
+    if (rc) return rc;
+    if (ev) LP_CUDA_OK(cudaEventRecord(ev[2], st));
+    ResizeArgs r;
+    r.src = b->d_frames;
+    r.src_img_stride = b->frame_bytes;
+    r.src_row_stride = (size_t)b->W * 3;
+    r.channels = 3;
+    r.crop_x = b->crop_x; r.crop_y = b->crop_y; r.crop_w = b->crop_w; r.crop_h = b->crop_h;
+    r.dst = b->d_resized + (size_t)i0 * b->resized_bytes;
+    r.dst_img_stride = b->resized_bytes;
+    r.dst_row_stride = (size_t)b->out_w * 3;
+    r.dst_w = b->out_w; r.dst_h = b->out_h;
+    r.n = cnt;
+    r.interpolation = 3;
+    rc = resize_launch(r, st);
+    if (rc) return rc;
+    if (ev) LP_CUDA_OK(cudaEventRecord(ev[3], st));
+    JpegEncodeBatch e;
+    e.frames = r.dst;
+    e.frame_img_stride = b->resized_bytes;
+    e.frame_row_stride = (size_t)b->out_w * 3;
+    e.width = b->out_w; e.height = b->out_h; e.channels = 3;
+    e.quality = b->cfg.jpeg_quality;
+    e.n = cnt;
+    e.out = b->d_out + (size_t)i0 * b->cfg.out_cap;
+    e.out_cap = b->cfg.out_cap;
+    e.out_len = b->d_out_len + i0;
+    e.scratch = b->d_enc_scratch;
+    rc = jpeg_encode_launch(e, st, ev ? ev[4] : nullptr);
+    if (rc) return rc;
+    if (ev) LP_CUDA_OK(cudaEventRecord(ev[5], st));
+    return LP_OK;
+}
+
+static int batch_download_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st) {
+    const size_t cap = b->cfg.out_cap;
+    LP_CUDA_OK(cudaMemcpyAsync(b->h_out_len + i0, b->d_out_len + i0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+    LP_CUDA_OK(cudaMemcpyAsync(b->h_items_back + i0, b->d_items + i0, (size_t)cnt * sizeof(JpegDecodeItem),
+                               cudaMemcpyDeviceToHost, st));
+    LP_CUDA_OK(cudaMemcpyAsync(b->h_out + (size_t)i0 * cap, b->d_out + (size_t)i0 * cap, (size_t)cnt * cap,
+                               cudaMemcpyDeviceToHost, st));
+    return LP_OK;
+}
+
+static void batch_finish_chunk(lp_batch* b, int i0, int cnt, uint8_t* const* out, size_t* out_len, int* status) {
+    const size_t cap = b->cfg.out_cap;
+    for (int i = i0; i < i0 + cnt; i++) {
+        int st = b->parse_status[i];
+        if (!st && b->h_items_back[i].status != 0) st = LP_ERR_DECODING_FAILED;
+        if (!st && b->h_out_len[i] == 0) st = LP_ERR_BUF_TOO_SMALL;
+        if (status) status[i] = st;
+        out_len[i] = 0;
+        if (st) continue;
+        memcpy(out[i], b->h_out + (size_t)i * cap, b->h_out_len[i]);
+        out_len[i] = b->h_out_len[i];
+    }
+}
+
+extern "C" int lp_batch_stage(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int n,
+                              int* status) {
+    if (!b || (n > 0 && (!in || !in_len)) || n < 0 || n > b->cfg.max_images) return LP_ERR_BAD_ARGUMENT;
+    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+    batch_begin(b, n);
+    for (int i0 = 0; i0 < n; i0 += b->chunk) {
+        const int cnt = std::min(b->chunk, n - i0);
+        int rc = batch_parse_chunk(b, in, in_len, i0, cnt);
+        if (rc) return rc;
+        rc = batch_upload_chunk(b, in, in_len, i0, cnt, b->st);
+        if (rc) return rc;
+    }
     LP_CUDA_OK(cudaStreamSynchronize(b->st));
     if (status)
         for (int k = 0; k < n; k++) status[k] = b->parse_status[k];
@@ -269,62 +384,14 @@ extern "C" int lp_batch_run(lp_batch* b, float* stage_ms) {
     const int nchunks = ceil_div(b->n, b->chunk);
     for (int c = 0; c < nchunks; c++) {
         const int i0 = c * b->chunk, cnt = std::min(b->chunk, b->n - i0);
-        cudaEvent_t* ev = &b->ev[(size_t)c * 6];
-        LP_CUDA_OK(cudaEventRecord(ev[0], b->st));
-        JpegDecodeBatch d;
-        d.items = b->d_items + i0;
-        d.tables = b->d_tables;
-        d.scan = b->d_scan;
-        d.coef = b->d_coef;
-        d.planes = b->d_planes;
-        d.frames = b->d_frames;
-        d.n = cnt;
-        d.coef_elems_total = (size_t)cnt * b->blocks * 64;
-        d.max_blocks_per_image = (int)b->blocks;
-        d.max_width = b->W;
-        d.max_height = b->H;
-        d.use_parallel_huffman = b->parallel_huffman;
-        d.clean = b->d_clean;
-        d.states = b->d_states;
-        d.nslots = b->d_nslots;
-        d.dcdiff = b->d_dcdiff;
-        int rc = jpeg_decode_launch(d, b->st, ev[1]);
+        int rc = batch_launch_chunk(b, i0, cnt, b->st, &b->ev[(size_t)c * 6]);
         if (rc) return rc;
-        LP_CUDA_OK(cudaEventRecord(ev[2], b->st));
-        ResizeArgs r;
-        r.src = b->d_frames;
-        r.src_img_stride = b->frame_bytes;
-        r.src_row_stride = (size_t)b->W * 3;
-        r.channels = 3;
-        r.crop_x = b->crop_x; r.crop_y = b->crop_y; r.crop_w = b->crop_w; r.crop_h = b->crop_h;
-        r.dst = b->d_resized + (size_t)i0 * b->resized_bytes;
-        r.dst_img_stride = b->resized_bytes;
-        r.dst_row_stride = (size_t)b->out_w * 3;
-        r.dst_w = b->out_w; r.dst_h = b->out_h;
-        r.n = cnt;
-        r.interpolation = 3;
-        rc = resize_launch(r, b->st);
-        if (rc) return rc;
-        LP_CUDA_OK(cudaEventRecord(ev[3], b->st));
-        JpegEncodeBatch e;
-        e.frames = r.dst;
-        e.frame_img_stride = b->resized_bytes;
-        e.frame_row_stride = (size_t)b->out_w * 3;
-        e.width = b->out_w; e.height = b->out_h; e.channels = 3;
-        e.quality = b->cfg.jpeg_quality;
-        e.n = cnt;
-        e.out = b->d_out + (size_t)i0 * b->cfg.out_cap;
-        e.out_cap = b->cfg.out_cap;
-        e.out_len = b->d_out_len + i0;
-        e.scratch = b->d_enc_scratch;
-        rc = jpeg_encode_launch(e, b->st, ev[4]);
-        if (rc) return rc;
-        LP_CUDA_OK(cudaEventRecord(ev[5], b->st));
     }
     LP_CUDA_OK(cudaStreamSynchronize(b->st));
     b->last_launches = (int)(g_launches - launches0);
     if (stage_ms) {
         for (int s = 0; s < LP_STAGE_COUNT; s++) stage_ms[s] = 0.f;
+        if (nchunks == 0) return LP_OK;
         for (int c = 0; c < nchunks; c++) {
             cudaEvent_t* ev = &b->ev[(size_t)c * 6];
             float t;
@@ -342,34 +409,57 @@ extern "C" int lp_batch_run(lp_batch* b, float* stage_ms) {
 }
 
 extern "C" int lp_batch_fetch(lp_batch* b, uint8_t* const* out, size_t* out_len, int* status) {
-    if (!b || !out || !out_len) return LP_ERR_BAD_ARGUMENT;
+    if (!b || (b->n > 0 && (!out || !out_len))) return LP_ERR_BAD_ARGUMENT;
     LP_CUDA_OK(cudaSetDevice(b->cfg.device));
-    const size_t cap = b->cfg.out_cap;
-    LP_CUDA_OK(cudaMemcpyAsync(b->h_out_len, b->d_out_len, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->st));
-    LP_CUDA_OK(cudaMemcpyAsync(b->h_items_back, b->d_items, (size_t)b->n * sizeof(JpegDecodeItem),
-                               cudaMemcpyDeviceToHost, b->st));
-    LP_CUDA_OK(cudaMemcpyAsync(b->h_out, b->d_out, (size_t)b->n * cap, cudaMemcpyDeviceToHost, b->st));
+    if (b->n == 0) return LP_OK;
+    int rc = batch_download_chunk(b, 0, b->n, b->st);
+    if (rc) return rc;
     LP_CUDA_OK(cudaStreamSynchronize(b->st));
-    for (int i = 0; i < b->n; i++) {
-        int st = b->parse_status[i];
-        if (!st && b->h_items_back[i].status != 0) st = LP_ERR_DECODING_FAILED;
-        if (!st && b->h_out_len[i] == 0) st = LP_ERR_BUF_TOO_SMALL;
-        if (status) status[i] = st;
-        out_len[i] = 0;
-        if (st) continue;
-        memcpy(out[i], b->h_out + (size_t)i * cap, b->h_out_len[i]);
-        out_len[i] = b->h_out_len[i];
-    }
+    batch_finish_chunk(b, 0, b->n, out, out_len, status);
     return LP_OK;
 }
 
+// The reference-facing call: host buffers in, host buffers out.  Chunks are pipelined over three
+// streams: while chunk c is in the kernels, chunk c+1's headers are parsed and its bytes cross PCIe,
+// and chunk c-1's encoded bytes come back.
 extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int n,
                                   uint8_t* const* out, size_t* out_len, int* status) {
-    int rc = lp_batch_stage(b, in, in_len, n, nullptr);
-    if (rc) return rc;
-    rc = lp_batch_run(b, nullptr);
-    if (rc) return rc;
-    return lp_batch_fetch(b, out, out_len, status);
+    if (!b || n < 0 || n > b->cfg.max_images || (n > 0 && (!in || !in_len || !out || !out_len)))
+        return LP_ERR_BAD_ARGUMENT;
+    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+    batch_begin(b, n);
+    const long launches0 = g_launches;
+    const int nchunks = ceil_div(n, b->chunk);
+    int finished = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const int i0 = c * b->chunk, cnt = std::min(b->chunk, n - i0);
+        int rc = batch_parse_chunk(b, in, in_len, i0, cnt);
+        if (rc) return rc;
+        rc = batch_upload_chunk(b, in, in_len, i0, cnt, b->st_h2d);
+        if (rc) return rc;
+        LP_CUDA_OK(cudaEventRecord(b->ev_h2d[c], b->st_h2d));
+        LP_CUDA_OK(cudaStreamWaitEvent(b->st, b->ev_h2d[c], 0));
+        rc = batch_launch_chunk(b, i0, cnt, b->st, nullptr);
+        if (rc) return rc;
+        LP_CUDA_OK(cudaEventRecord(b->ev[(size_t)c * 6], b->st));
+        LP_CUDA_OK(cudaStreamWaitEvent(b->st_d2h, b->ev[(size_t)c * 6], 0));
+        rc = batch_download_chunk(b, i0, cnt, b->st_d2h);
+        if (rc) return rc;
+        LP_CUDA_OK(cudaEventRecord(b->ev_d2h[c], b->st_d2h));
+        // hand back chunks whose bytes have already landed
+        while (finished < c && cudaEventQuery(b->ev_d2h[finished]) == cudaSuccess) {
+            const int f0 = finished * b->chunk;
+            batch_finish_chunk(b, f0, std::min(b->chunk, n - f0), out, out_len, status);
+            finished++;
+        }
+    }
+    for (; finished < nchunks; finished++) {
+        LP_CUDA_OK(cudaEventSynchronize(b->ev_d2h[finished]));
+        const int f0 = finished * b->chunk;
+        batch_finish_chunk(b, f0, std::min(b->chunk, n - f0), out, out_len, status);
+    }
+    b->last_launches = (int)(g_launches - launches0);
+    return LP_OK;
 }
 
 extern "C" int lp_batch_last_launches(const lp_batch* b) { return b ? b->last_launches : 0; }

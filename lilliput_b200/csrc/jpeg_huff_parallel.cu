@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kHuffThreads)
 
 // ------------------------------------------------------------------ 2. sync + write
 
-struct SubState {
+struct alignas(8) SubState {
     uint32_t p;      // absolute bit position of the first symbol that starts after this subsequence
     uint32_t phase;  // (block-in-MCU << 6) | zig-zag index expected at p
 };
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kHuffThreads)
     __shared__ HuffShared hs;
     __shared__ uint32_t warp_sums[kHuffThreads / 32];
     __shared__ uint32_t s_carry;
-    __shared__ int s_changed, s_status;
+    __shared__ int s_status;
     JpegDecodeItem& it = items[blockIdx.x];
     const int tid = threadIdx.x;
     if (it.status != 0) return;
@@ -313,7 +313,6 @@ __global__ void __launch_bounds__(kHuffThreads)
                     hs.blk_bx[k] = (uint8_t)(j % it.h[c]);
                     hs.blk_by[k] = (uint8_t)(j / it.h[c]);
                 }
-            s_changed = 0;
             s_status = 0;
             s_carry = 0;
         }
@@ -344,9 +343,10 @@ __global__ void __launch_bounds__(kHuffThreads)
     const uint8_t* s = clean + it.clean_off;
     const uint32_t total_bits = it.clean_len * 8u;
     const uint32_t nsub = (total_bits + kSubBits - 1) / kSubBits;
-    SubState* st = states_all + it.state_off;      // two generations of nsub entries
-    uint32_t* ns = nslots_all + it.state_off;      // [0,nsub): slots; [nsub,2nsub): last-changed iteration
-    uint32_t* last = ns + nsub;
+    SubState* st = states_all + it.state_off;      // nsub entries (second half: work lists)
+    uint32_t* ns = nslots_all + it.state_off;      // [0,nsub): slots consumed per subsequence
+    uint32_t* list_a = reinterpret_cast<uint32_t*>(st + nsub);  // 2*nsub uint32 = two work lists
+    uint32_t* list_b = list_a + nsub;
     const uint64_t total_slots = (uint64_t)it.mcus_x * it.mcus_y * nb * 64;
 
     // ---- pass 0: every subsequence from a guessed state (exact only for subsequence 0)
@@ -356,41 +356,45 @@ __global__ void __launch_bounds__(kHuffThreads)
         decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr);
         st[i] = SubState{p, phase};
         ns[i] = n;
-        last[i] = 0;
     }
     __syncthreads();
-    // ---- synchronisation: subsequence i is re-decoded from its left neighbour's exit state whenever
-    //      that state changed in the previous iteration; stop when an iteration changes nothing.
-    SubState* cur = st;
-    SubState* nxt = st + nsub;
-    for (uint32_t iter = 1; iter <= nsub; iter++) {
-        for (uint32_t i = tid; i < nsub; i += kHuffThreads) {
-            SubState out = cur[i];
-            if (i > 0 && last[i - 1] == iter - 1) {
-                const SubState in = cur[i - 1];
-                uint32_t p = in.p, phase = in.phase, n = 0;
-                const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-                if (p < limit) decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr);
-                if (p != out.p || phase != out.phase || n != ns[i]) {
-                    out = SubState{p, phase};
-                    ns[i] = n;
-                    last[i] = iter;   // read by thread i+1 only in the NEXT iteration (after the barrier)
-                    s_changed = 1;
-                }
+    // ---- synchronisation.  A subsequence is re-decoded from its left neighbour's exit state whenever
+    //      that state changed; changes are collected in a work list so later (sparse) rounds keep all
+    //      lanes busy.  States are updated in place: a reader that races with a writer sees either
+    //      the old or the new 8-byte state, and in the first case the writer has queued it again.
+    //      Round 1 visits every subsequence >= 1.  The fixed point is exact by induction from 0.
+    uint32_t* cur_list = list_a;
+    uint32_t* nxt_list = list_b;
+    uint32_t cur_count = nsub > 0 ? nsub - 1 : 0;
+    bool first_round = true;
+    while (cur_count > 0) {
+        if (tid == 0) s_carry = 0;  // next list length
+        __syncthreads();
+        for (uint32_t k = tid; k < cur_count; k += kHuffThreads) {
+            const uint32_t i = first_round ? k + 1 : cur_list[k];
+            const uint64_t in64 = *reinterpret_cast<volatile uint64_t*>(&st[i - 1]);
+            const SubState in{(uint32_t)in64, (uint32_t)(in64 >> 32)};
+            const SubState old = st[i];
+            uint32_t p = in.p, phase = in.phase, n = 0;
+            const uint32_t limit = min((i + 1) * kSubBits, total_bits);
+            if (p < limit) decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr);
+            if (p != old.p || phase != old.phase || n != ns[i]) {
+                *reinterpret_cast<volatile uint64_t*>(&st[i]) = ((uint64_t)phase << 32) | p;
+                ns[i] = n;
+                if (i + 1 < nsub) nxt_list[atomicAdd(&s_carry, 1u)] = i + 1;
             }
-            nxt[i] = out;
         }
         __syncthreads();
-        const int changed = s_changed;
+        cur_count = s_carry;
         __syncthreads();
-        if (tid == 0) s_changed = 0;
-        SubState* tmp = cur;
-        cur = nxt;
-        nxt = tmp;
-        if (!changed) break;
-        __syncthreads();
+        uint32_t* t = cur_list;
+        cur_list = nxt_list;
+        nxt_list = t;
+        first_round = false;
     }
+    if (tid == 0) s_carry = 0;
     __syncthreads();
+    SubState* cur = st;
     // ---- prefix sum of slot counts, then the writing decode
     for (uint32_t base = 0; base < nsub; base += kHuffThreads) {
         const uint32_t i = base + tid;

@@ -17,6 +17,7 @@
 // warp with 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA engine) signalled through
 // mbarriers; eight consumer warps turn each staged row into one fp32 partial per output sample
 // and keep the vertical sums in registers.  No data is exchanged between CTAs.
+#include <algorithm>
 #include <cmath>
 #include <cfloat>
 #include <cstdlib>
@@ -73,6 +74,7 @@ struct AreaTabDev {
     int maxt = 0, padt = 0;  // padt = weights per entry as laid out on the device
     int* first = nullptr;
     int* count = nullptr;
+    int* perm = nullptr;  // per 256-px tile: destination indices ordered by tap count (short chains first)
     float* w = nullptr;
     std::vector<int> h_first, h_count;
 };
@@ -106,8 +108,19 @@ static int get_area_tab(int ssize, int dsize, AreaTabDev* out) {
     std::vector<float> w((size_t)dsize * padt, 0.f);
     for (int i = 0; i < dsize; i++)
         memcpy(&w[(size_t)i * padt], &h.w[(size_t)i * h.maxt], sizeof(float) * h.maxt);
+    // Within each 256-pixel tile, order destination pixels by tap count so that whole warps share a
+    // chain length and the shorter ones skip the zero-weight tail tap.
+    std::vector<int> perm(dsize);
+    for (int x0 = 0; x0 < dsize; x0 += 256) {
+        const int x1 = std::min(x0 + 256, dsize);
+        for (int i = x0; i < x1; i++) perm[i] = i;
+        std::stable_sort(perm.begin() + x0, perm.begin() + x1,
+                         [&](int a, int b) { return h.count[a] < h.count[b]; });
+    }
     LP_CUDA_OK(cudaMalloc(&d.first, sizeof(int) * dsize));
     LP_CUDA_OK(cudaMalloc(&d.count, sizeof(int) * dsize));
+    LP_CUDA_OK(cudaMalloc(&d.perm, sizeof(int) * dsize));
+    LP_CUDA_OK(cudaMemcpy(d.perm, perm.data(), sizeof(int) * dsize, cudaMemcpyHostToDevice));
     LP_CUDA_OK(cudaMalloc(&d.w, sizeof(float) * w.size()));
     LP_CUDA_OK(cudaMemcpy(d.first, h.first.data(), sizeof(int) * dsize, cudaMemcpyHostToDevice));
     LP_CUDA_OK(cudaMemcpy(d.count, h.count.data(), sizeof(int) * dsize, cudaMemcpyHostToDevice));
@@ -174,7 +187,8 @@ struct AreaParams {
     int dw, dh;
     const int* xfirst;
     const int* xcount;
-    const float* xw;  // [dw][MAXT]
+    const int* xperm;  // thread slot -> destination x (tap-count sorted within each tile)
+    const float* xw;   // [dw][MAXT]
     const int* yfirst;
     const int* ycount;
     const float* yw;  // [dh][ypad]
@@ -199,7 +213,32 @@ __device__ __forceinline__ float u8_to_f32(uint32_t word, int byte) {
 
 // C channels, MAXT unrolled taps (zero-weight padded), XU = taps converted on the XU pipe,
 // PPT = destination pixels per consumer thread.
-template <int C, int MAXT, int XU, int PPT>
+// One pixel's horizontal pass over NT taps: bytes o.. of the staged row -> C fp32 partials.
+template <int C, int NT, int XU>
+__device__ __forceinline__ void area_hpass(uint32_t slot, uint32_t o, const float* wx, float* buf) {
+    constexpr int NA = (C * NT + 3) / 4;  // aligned words holding the taps
+    const uint32_t addr = slot + (o & ~3u);
+    const uint32_t sh = (o & 3u) * 8u;
+    uint32_t w[NA + 1];
+#pragma unroll
+    for (int i = 0; i <= NA; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(addr + 4u * i));
+    uint32_t a[NA];
+#pragma unroll
+    for (int i = 0; i < NA; i++) a[i] = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+    for (int c = 0; c < C; c++) buf[c] = 0.f;
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int i = t * C + c;
+            const float v = (t < XU) ? u8_to_f32<true>(a[i >> 2], i & 3) : u8_to_f32<false>(a[i >> 2], i & 3);
+            buf[c] = __fmaf_rn(v, wx[t], buf[c]);
+        }
+    }
+}
+
+template <int C, int MAXT, int XU, int PPT, bool SORT>
 __global__ void __launch_bounds__(kAreaTile / PPT + 32)
     resize_area_kernel(const AreaParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -268,9 +307,15 @@ __global__ void __launch_bounds__(kAreaTile / PPT + 32)
     const int lane = tid & 31;
     float wx[PPT][MAXT];
     uint32_t rel[PPT];
+    int dxs[PPT];
+    bool short_chain[PPT];  // warp-uniform: every lane's pixel has < MAXT taps
 #pragma unroll
     for (int q = 0; q < PPT; q++) {
-        const int dx = dx0 + tid + q * NT;
+        const int slot = dx0 + tid + q * NT;
+        const int dx = slot < dx1 ? (SORT ? __ldg(p.xperm + slot) : slot) : p.dw;
+        dxs[q] = dx;
+        const int cnt = dx < dx1 ? __ldg(p.xcount + dx) : 0;
+        short_chain[q] = SORT && MAXT > 1 && __all_sync(0xffffffffu, cnt < MAXT);
         if (dx < dx1) {
             rel[q] = (uint32_t)(__ldg(p.xfirst + dx) - x_begin) * C;
 #pragma unroll
@@ -285,7 +330,6 @@ __global__ void __launch_bounds__(kAreaTile / PPT + 32)
     const uint32_t stride_lo = (uint32_t)(p.src_row_stride & 15);
     const uint32_t ring_base = smem_u32(ring);
 
-    constexpr int NA = (C * MAXT + 3) / 4;  // aligned words holding one pixel's taps
     float buf[PPT][C];
     float sum[PPT][C];
 #pragma unroll
@@ -311,27 +355,10 @@ __global__ void __launch_bounds__(kAreaTile / PPT + 32)
 #pragma unroll
                 for (int q = 0; q < PPT; q++) {
                     const uint32_t o = delta + rel[q];
-                    const uint32_t addr = slot + (o & ~3u);
-                    const uint32_t sh = (o & 3u) * 8u;
-                    uint32_t w[NA + 1];
-#pragma unroll
-                    for (int i = 0; i <= NA; i++)
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(addr + 4u * i));
-                    uint32_t a[NA];
-#pragma unroll
-                    for (int i = 0; i < NA; i++) a[i] = __funnelshift_r(w[i], w[i + 1], sh);
-#pragma unroll
-                    for (int c = 0; c < C; c++) buf[q][c] = 0.f;
-#pragma unroll
-                    for (int t = 0; t < MAXT; t++) {
-#pragma unroll
-                        for (int c = 0; c < C; c++) {
-                            const int i = t * C + c;
-                            const float v = (t < XU) ? u8_to_f32<true>(a[i >> 2], i & 3)
-                                                     : u8_to_f32<false>(a[i >> 2], i & 3);
-                            buf[q][c] = __fmaf_rn(v, wx[q][t], buf[q][c]);
-                        }
-                    }
+                    if (short_chain[q])
+                        area_hpass<C, (MAXT > 1 ? MAXT - 1 : 1), (XU < MAXT - 1 ? XU : (MAXT > 1 ? MAXT - 1 : 1))>(slot, o, wx[q], buf[q]);
+                    else
+                        area_hpass<C, MAXT, XU>(slot, o, wx[q], buf[q]);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
@@ -345,7 +372,7 @@ __global__ void __launch_bounds__(kAreaTile / PPT + 32)
         }
 #pragma unroll
         for (int q = 0; q < PPT; q++) {
-            const int dx = dx0 + tid + q * NT;
+            const int dx = dxs[q];
             if (dx < dx1) {
                 uint8_t* d = p.dst + (size_t)img * p.dst_img_stride + (size_t)dy * p.dst_row_stride +
                              (size_t)dx * C;
@@ -483,9 +510,9 @@ static size_t area_smem_bytes(int slot_bytes) {
     return 128 + (size_t)kAreaMaxBand * kAreaMaxYTaps * 4 + (size_t)kAreaSlots * slot_bytes;
 }
 
-template <int C, int MAXT, int XU, int PPT>
+template <int C, int MAXT, int XU, int PPT, bool SORT = false>
 static int launch_area(const AreaParams& p, int n, cudaStream_t st) {
-    auto kern = resize_area_kernel<C, MAXT, XU, PPT>;
+    auto kern = resize_area_kernel<C, MAXT, XU, PPT, SORT>;
     const size_t smem = area_smem_bytes(p.slot_bytes);
     if (smem > 48 * 1024)
         LP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -517,7 +544,13 @@ static int dispatch_area(int padt, const AreaParams& p, int n, cudaStream_t st) 
             case 22: return launch_area<3, 6, 2, 2>(p, n, st);
             case 32: return launch_area<3, 6, 3, 2>(p, n, st);
             case 62: return launch_area<3, 6, 6, 2>(p, n, st);
-            default: return launch_area<3, 6, 2, 2>(p, n, st);
+            case 24: return launch_area<3, 6, 2, 4>(p, n, st);
+            case 122: return launch_area<3, 6, 2, 2, true>(p, n, st);
+            case 112: return launch_area<3, 6, 1, 2, true>(p, n, st);
+            case 132: return launch_area<3, 6, 3, 2, true>(p, n, st);
+            case 124: return launch_area<3, 6, 2, 4, true>(p, n, st);
+            case 121: return launch_area<3, 6, 2, 1, true>(p, n, st);
+            default: return launch_area<3, 6, 2, 2, true>(p, n, st);
         }
     }
     switch (padt) {
@@ -575,7 +608,7 @@ int resize_launch(const ResizeArgs& a, cudaStream_t st) {
         p.src = a.src; p.src_img_stride = a.src_img_stride; p.src_row_stride = a.src_row_stride;
         p.dst = a.dst; p.dst_img_stride = a.dst_img_stride; p.dst_row_stride = a.dst_row_stride;
         p.crop_x = a.crop_x; p.crop_y = a.crop_y; p.dw = a.dst_w; p.dh = a.dst_h;
-        p.xfirst = tx.first; p.xcount = tx.count; p.xw = tx.w;
+        p.xfirst = tx.first; p.xcount = tx.count; p.xperm = tx.perm; p.xw = tx.w;
         p.yfirst = ty.first; p.ycount = ty.count; p.yw = ty.w; p.ypad = ty.padt;
         if (tx.padt > 16) {
             dim3 grid(ceil_div(a.dst_w * C, 128), a.dst_h, a.n);

@@ -23,7 +23,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     gb = n * (1080 * 1080 * 3 + 256 * 256 * 3) / 1e9
     print(f"variant={os.environ.get('LP_RESIZE_VARIANT','default'):>8s} rc={rc} ms={ms.value:.4f} GB/s={gb / (ms.value * 1e-3):8.1f} frac={gb / (ms.value * 1e-3) / 6583.5:.3f}")
 else:
-    for v in ["", "1", "21", "61", "2", "22", "32", "62"]:
+    for v in ["", "22", "122", "112", "132", "124", "24", "121"]:
         env = dict(os.environ)
         if v: env["LP_RESIZE_VARIANT"] = v
         subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env)

@@ -208,19 +208,22 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
         my = (int)(mcu / (uint32_t)it->mcus_x);
         set_dst();
     }
-    int tdc = hs.blk_dc[blk], tac = hs.blk_ac[blk];
+    // shared-memory byte addresses of the current block's lookahead tables
+    uint32_t dcb = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[blk]][0]);
+    uint32_t acb = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[blk]][0]);
+    // The symbol step is written with selects instead of branches: lanes of a warp sit at unrelated
+    // places of unrelated subsequences, so every branch here would be a divergent one.
     while (p < limit) {
         if (WRITE && n >= remaining) break;  // every MCU produced: the rest is padding
         bw.refill();
         const uint32_t top = (uint32_t)(bw.acc >> 32);
         const bool isdc = z == 0;
-        uint32_t e = isdc ? hs.dc_look[tdc][top >> (32 - kDcBits)] : hs.ac_look[tac][top >> (32 - kAcBits)];
-        int len, sym;
-        if (__builtin_expect(e != 0, 1)) {
-            len = e >> 8;
-            sym = e & 0xFF;
-        } else {
-            const int t = isdc ? tdc : 4 + tac;
+        const uint32_t idx = isdc ? (top >> (32 - kDcBits)) : (top >> (32 - kAcBits));
+        uint32_t e;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"((isdc ? dcb : acb) + idx * 2u));
+        int len = (int)(e >> 8), sym = (int)(e & 0xFF);
+        if (__builtin_expect(e == 0, 0)) {  // longer than the lookahead: canonical walk (rare)
+            const int t = isdc ? hs.blk_dc[blk] : 4 + hs.blk_ac[blk];
             len = (isdc ? kDcBits : kAcBits) + 1;
             int code = (int)(top >> (32 - len));
             while (len <= 16 && code > hs.maxcode[t][len]) {
@@ -238,34 +241,30 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
             }
             sym = hs.vals[t][(code + hs.valoffset[t][len]) & 0xFF];
         }
-        const int r = sym >> 4, sz = sym & 15;
-        if (sz == 0 && !isdc) {
-            // EOB, or ZRL (16 zeros); a ZRL that would leave the block ends it, as in libjpeg
-            if (r == 15 && z + 16 <= 63) {
-                z += 16;
-                n += 16;
+        const uint32_t r = (uint32_t)sym >> 4, sz = (uint32_t)sym & 15;
+        const bool ez = (sz == 0) && !isdc;                  // EOB or ZRL
+        const uint32_t zn = z + r;                           // DC symbols have r == 0
+        const bool zrl_ok = ez && r == 15 && z + 16 <= 63;   // a ZRL that leaves the block ends it
+        const bool val_ok = !ez && zn <= 63;
+        uint32_t n_add = 64 - z, z_new = 0;                  // EOB / overrun: close the block
+        n_add = zrl_ok ? 16u : n_add;
+        z_new = zrl_ok ? z + 16 : z_new;
+        n_add = val_ok ? r + 1 : n_add;
+        z_new = val_ok ? ((zn + 1) & 63u) : z_new;
+        const int used = len + (ez ? 0 : (int)sz);
+        if (WRITE && !ez) {
+            if (zn <= 63) {
+                const uint32_t raw = sz ? ((top << len) >> (32 - sz)) : 0u;
+                const int val = sz ? ((int)raw < (1 << (sz - 1)) ? (int)raw - (1 << sz) + 1 : (int)raw) : 0;
+                dstblk[hs.zz[zn]] = (int16_t)val;
             } else {
-                n += 64 - z;
-                z = 0;
-            }
-            bw.skip(len);
-            p += len;
-        } else {
-            const uint32_t zn = z + r;  // DC symbols have r == 0
-            const uint32_t raw = sz ? (uint32_t)((top << len) >> (32 - sz)) : 0u;
-            const int val = sz ? ((int)raw < (1 << (sz - 1)) ? (int)raw - (1 << sz) + 1 : (int)raw) : 0;
-            bw.skip(len + sz);
-            p += len + sz;
-            if (zn > 63) {  // wrong guess (or corrupt data): close the block
-                if (WRITE) *status = -3;
-                n += 64 - z;
-                z = 0;
-            } else {
-                if (WRITE) dstblk[hs.zz[zn]] = (int16_t)val;
-                n += r + 1;
-                z = (zn + 1) & 63;
+                *status = -3;  // coefficient index past 63: corrupt data
             }
         }
+        bw.skip(used);
+        p += (uint32_t)used;
+        n += n_add;
+        z = z_new;
         if (z == 0) {  // block finished
             blk++;
             if (blk == (uint32_t)nb) {
@@ -275,8 +274,8 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
                     my++;
                 }
             }
-            tdc = hs.blk_dc[blk];
-            tac = hs.blk_ac[blk];
+            dcb = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[blk]][0]);
+            acb = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[blk]][0]);
             if (WRITE && n < remaining) set_dst();
         }
     }

@@ -199,7 +199,7 @@ struct AreaParams {
 
 constexpr int kAreaTile = 256;    // destination pixels per CTA
 constexpr int kAreaSlots = 4;     // ring depth (power of two)
-constexpr int kAreaMaxBand = 8;   // destination rows per CTA
+constexpr int kAreaMaxBand = 16;  // destination rows per CTA
 constexpr int kAreaMaxYTaps = 16;
 
 // u8 -> fp32, exactly.  Two routes so the work can be split across pipes: I2F.U8 runs on the XU
@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(kAreaTile / PPT + 32)
     uint64_t* empty = full + S;
     int* s_yf = reinterpret_cast<int*>(smem + 64);            // [kAreaMaxBand]
     int* s_yc = s_yf + kAreaMaxBand;                          // [kAreaMaxBand]
-    float* s_yw = reinterpret_cast<float*>(smem + 128);       // [kAreaMaxBand][kAreaMaxYTaps]
-    uint8_t* ring = smem + 128 + kAreaMaxBand * kAreaMaxYTaps * 4;
+    float* s_yw = reinterpret_cast<float*>(smem + 256);       // [kAreaMaxBand][kAreaMaxYTaps]
+    uint8_t* ring = smem + 256 + kAreaMaxBand * kAreaMaxYTaps * 4;
 
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
@@ -507,7 +507,7 @@ static void linear_tab(int ssize, int dsize, bool area_mode, bool clamp_ofs, std
 // ------------------------------------------------------------------ launcher
 
 static size_t area_smem_bytes(int slot_bytes) {
-    return 128 + (size_t)kAreaMaxBand * kAreaMaxYTaps * 4 + (size_t)kAreaSlots * slot_bytes;
+    return 256 + (size_t)kAreaMaxBand * kAreaMaxYTaps * 4 + (size_t)kAreaSlots * slot_bytes;
 }
 
 template <int C, int MAXT, int XU, int PPT, bool SORT = false>
@@ -626,7 +626,8 @@ int resize_launch(const ResizeArgs& a, cudaStream_t st) {
         p.slot_bytes = round_up(span * C + 16 + tx.padt * C + 8, 128);
         // bands: keep >= ~4 CTAs per SM in flight when the batch is small
         long ctas_per_row_group = (long)ceil_div(a.dst_w, kAreaTile) * a.n;
-        int rpb = 8;
+        static const int rpb_env = getenv("LP_RESIZE_RPB") ? atoi(getenv("LP_RESIZE_RPB")) : 0;
+        int rpb = rpb_env > 0 ? std::min(rpb_env, kAreaMaxBand) : 8;
         while (rpb > 1 && ctas_per_row_group * ceil_div(a.dst_h, rpb) < 4L * kNumSMs) rpb >>= 1;
         p.rows_per_band = rpb;
         if (area_smem_bytes(p.slot_bytes) > 200 * 1024 || ty.padt > kAreaMaxYTaps) {

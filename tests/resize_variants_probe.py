@@ -23,7 +23,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     gb = n * (1080 * 1080 * 3 + 256 * 256 * 3) / 1e9
     print(f"variant={os.environ.get('LP_RESIZE_VARIANT','default'):>8s} rc={rc} ms={ms.value:.4f} GB/s={gb / (ms.value * 1e-3):8.1f} frac={gb / (ms.value * 1e-3) / 6583.5:.3f}")
 else:
-    for v in ["", "22", "122", "112", "132", "124", "24", "121"]:
+    for v, rpb in [("", ""), ("122", "16"), ("122", "4"), ("124", "16"), ("112", "16")]:
         env = dict(os.environ)
         if v: env["LP_RESIZE_VARIANT"] = v
+        if rpb: env["LP_RESIZE_RPB"] = rpb
+        print("rpb", rpb or "8", end=" ", flush=True)
         subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env)

@@ -339,8 +339,12 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
-        chunk = b.lib.l.lp_batch_last_launches(b.h)  # keep handle alive
-        nchunks = max(1, -(-n // (args.chunk or 512)))
+        lib.l.lp_batch_chunk.argtypes = [C.c_void_p]
+        chunk = lib.l.lp_batch_chunk(b.h)
+        nchunks = max(1, -(-n // chunk))
+        mean_r, max_r = C.c_double(0), C.c_int(0)
+        lib.l.lp_batch_sync_rounds.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        lib.l.lp_batch_sync_rounds(b.h, C.byref(mean_r), C.byref(max_r))
         resize_ms_per_launch = stage_sum["resize"] / (args.steps * nchunks)
         per_launch_images = n / nchunks
         achieved = per_launch_images * RESIZE_BYTES_PER_IMAGE / (resize_ms_per_launch * 1e-3) / 1e9
@@ -359,6 +363,8 @@ def main():
                        "timing": "CUDA events on the library stream (first launch -> last kernel), max over ranks",
                        "wall_ms_per_step": round(1000 * wall_max / args.steps, 3),
                        "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage_sum.items()},
+                       "chunk_images": chunk,
+                       "huffman_sync_rounds": {"mean": round(mean_r.value, 2), "max": max_r.value},
                        "setup_s": round(setup_s, 1)},
             "e2e": {"value": round(e2e_v, 1), "unit": "images/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": n * out_cap + n * 4, "encoded_bytes_per_step": out_bytes,

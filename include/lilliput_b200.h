@@ -148,6 +148,11 @@ int lp_batch_run(lp_batch* b, float* stage_ms);
 int lp_batch_fetch(lp_batch* b, uint8_t* const* out, size_t* out_len, int* status);
 /* Number of kernel launches issued by the last lp_batch_run / lp_batch_transform. */
 int lp_batch_last_launches(const lp_batch* b);
+/* Images per pipelined chunk actually used by this context. */
+int lp_batch_chunk(const lp_batch* b);
+/* Diagnostics (valid after lp_batch_fetch / lp_batch_transform): rounds the parallel Huffman
+ * synchronisation needed per image. */
+void lp_batch_sync_rounds(const lp_batch* b, double* mean, int* max);
 /* Device pointer to the decoded frames / resized frames of the last run (tests). */
 const uint8_t* lp_batch_decoded_dev(const lp_batch* b, size_t* image_stride);
 const uint8_t* lp_batch_resized_dev(const lp_batch* b, size_t* image_stride);

@@ -104,7 +104,9 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
         delete b;
         return nullptr;
     }
-    b->chunk = cfg->chunk > 0 ? cfg->chunk : 512;
+    // default chunk: two full waves of the per-image Huffman CTAs (no mostly-empty tail wave)
+    const int slots = jpeg_huff_parallel_slots();
+    b->chunk = cfg->chunk > 0 ? cfg->chunk : (slots > 0 ? 2 * slots : 512);
     b->chunk = std::min(b->chunk, cfg->max_images);
     b->max_chunks = ceil_div(cfg->max_images, b->chunk);
     // worst-case per-image layout: 4:4:4 needs the most blocks
@@ -463,6 +465,21 @@ extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const s
 }
 
 extern "C" int lp_batch_last_launches(const lp_batch* b) { return b ? b->last_launches : 0; }
+extern "C" int lp_batch_chunk(const lp_batch* b) { return b ? b->chunk : 0; }
+// Diagnostics after lp_batch_fetch / lp_batch_transform: Huffman synchronisation rounds per image.
+extern "C" void lp_batch_sync_rounds(const lp_batch* b, double* mean, int* max) {
+    double sum = 0;
+    int mx = 0, cnt = 0;
+    for (int i = 0; i < b->n; i++) {
+        if (b->parse_status[i]) continue;
+        const int r = (int)b->h_items_back[i].pad_;
+        sum += r;
+        mx = std::max(mx, r);
+        cnt++;
+    }
+    if (mean) *mean = cnt ? sum / cnt : 0;
+    if (max) *max = mx;
+}
 extern "C" const uint8_t* lp_batch_decoded_dev(const lp_batch* b, size_t* image_stride) {
     if (image_stride) *image_stride = b->frame_bytes;
     return b->d_frames;

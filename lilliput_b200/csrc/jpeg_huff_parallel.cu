@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kHuffThreads)
     }
     if (tid == 0) it.clean_len = s_carry;
     // zero padding so the 8-byte window loads past the end read defined data
-    for (uint32_t k = tid; k < 16; k += kHuffThreads) dst[s_carry + k] = 0;
+    for (uint32_t k = tid; k < 32; k += kHuffThreads) dst[s_carry + k] = 0;
 }
 
 // ------------------------------------------------------------------ 2. sync + write
@@ -154,20 +154,23 @@ struct HuffShared {
 
 // MSB-first bit reader over the unstuffed string: 64-bit window, one 32-bit load per 32 bits used.
 struct BitWin {
-    const uint32_t* w;  // next word to load
+    const uint32_t* w;  // word after `nextw`
     uint64_t acc;       // next bit at bit 63
+    uint32_t nextw;     // prefetched: its load is issued ~32 bits before it is needed
     int avail;
     __device__ __forceinline__ void init(const uint8_t* s, uint32_t p) {
         const uint32_t* base = reinterpret_cast<const uint32_t*>(s) + (p >> 5);
         const uint64_t hi = __byte_perm(base[0], 0, 0x0123), lo = __byte_perm(base[1], 0, 0x0123);
         acc = ((hi << 32) | lo) << (p & 31);
         avail = 64 - (int)(p & 31);
-        w = base + 2;
+        nextw = base[2];
+        w = base + 3;
     }
     __device__ __forceinline__ void refill() {
         if (avail < 32) {
-            acc |= (uint64_t)__byte_perm(*w++, 0, 0x0123) << (32 - avail);
+            acc |= (uint64_t)__byte_perm(nextw, 0, 0x0123) << (32 - avail);
             avail += 32;
+            nextw = *w++;
         }
     }
     __device__ __forceinline__ void skip(int n) {
@@ -283,7 +286,7 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
     nslots = n;
 }
 
-__global__ void __launch_bounds__(kHuffThreads)
+__global__ void __launch_bounds__(kHuffThreads, 4)
     jpeg_huff_sync_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* clean,
                           SubState* states_all, uint32_t* nslots_all, int16_t* coef) {
     __shared__ HuffShared hs;
@@ -366,7 +369,9 @@ __global__ void __launch_bounds__(kHuffThreads)
     uint32_t* nxt_list = list_b;
     uint32_t cur_count = nsub > 0 ? nsub - 1 : 0;
     bool first_round = true;
+    uint32_t rounds = 0;
     while (cur_count > 0) {
+        rounds++;
         if (tid == 0) s_carry = 0;  // next list length
         __syncthreads();
         for (uint32_t k = tid; k < cur_count; k += kHuffThreads) {
@@ -391,7 +396,10 @@ __global__ void __launch_bounds__(kHuffThreads)
         nxt_list = t;
         first_round = false;
     }
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) {
+        s_carry = 0;
+        it.pad_ = rounds;  // diagnostics: synchronisation rounds this image needed
+    }
     __syncthreads();
     SubState* cur = st;
     // ---- prefix sum of slot counts, then the writing decode
@@ -455,6 +463,14 @@ __global__ void __launch_bounds__(kHuffThreads)
 }
 
 // ------------------------------------------------------------------ launcher
+
+int jpeg_huff_parallel_slots() {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jpeg_huff_sync_kernel, kHuffThreads, 0);
+    return sms * per_sm;
+}
 
 int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st) {
     if (a.n <= 0) return LP_OK;

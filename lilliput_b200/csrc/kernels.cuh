@@ -103,7 +103,7 @@ struct JpegDecodeBatch {
     int16_t* dcdiff = nullptr;
 };
 // Scratch sizing for the parallel Huffman path, per image with `scan_len` entropy-coded bytes.
-inline size_t huff_clean_bytes(size_t scan_len) { return ((scan_len + 32 + 15) / 16) * 16; }
+inline size_t huff_clean_bytes(size_t scan_len) { return ((scan_len + 48 + 15) / 16) * 16; }
 inline size_t huff_nsub(size_t scan_len) { return scan_len * 8 / 1024 + 2; }
 struct JpegHuffParallelArgs {
     JpegDecodeItem* items;
@@ -117,6 +117,9 @@ struct JpegHuffParallelArgs {
     int n;
 };
 int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st);
+// Images the sync kernel can keep resident at once (SMs x CTAs per SM); chunk sizes that are a
+// multiple of this avoid a mostly-empty last wave.
+int jpeg_huff_parallel_slots();
 // Launches: memset(coef) -> huffman decode -> idct -> upsample+colour.
 int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_huff);
 

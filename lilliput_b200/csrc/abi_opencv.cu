@@ -177,22 +177,19 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
     it.mcus_x = h.mcus_x;
     it.mcus_y = h.mcus_y;
     it.restart_interval = h.restart_interval;
-    uint32_t blocks = 0, plane_bytes = 0;
+    uint32_t total_blocks = 0;
     for (int c = 0; c < h.ncomp; c++) {
         it.h[c] = h.comp[c].h;
         it.v[c] = h.comp[c].v;
-        it.bw[c] = h.mcus_x * h.comp[c].h;
-        it.bh[c] = h.mcus_y * h.comp[c].v;
         it.dw[c] = (h.width * h.comp[c].h + h.maxh - 1) / h.maxh;
         it.dh[c] = (h.height * h.comp[c].v + h.maxv - 1) / h.maxv;
-        it.block_off[c] = blocks;
-        it.plane_rel[c] = plane_bytes;
-        blocks += (uint32_t)it.bw[c] * it.bh[c];
-        plane_bytes += (uint32_t)it.bw[c] * it.bh[c] * 64;
+        total_blocks += (uint32_t)h.mcus_x * h.mcus_y * h.comp[c].h * h.comp[c].v;
         memcpy(it.qt[c], h.qt[h.comp[c].tq], sizeof(it.qt[c]));
         it.td[c] = h.comp[c].td;
         it.ta[c] = h.comp[c].ta;
     }
+    uint32_t plane_bytes = 0;
+    const uint32_t blocks = jpeg_item_set_window(&it, 0, 0, h.width, h.height, false, &plane_bytes);  // whole image
     it.frame_channels = h.ncomp == 1 ? 1 : 3;
     JpegHuffSet hs;
     jpeg_build_huff_set(h, &hs);
@@ -205,7 +202,7 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
     const size_t clean_b = parallel ? round_up(huff_clean_bytes(h.scan_length), (size_t)256) : 0;
     const size_t states_b = parallel ? round_up(2 * huff_nsub(h.scan_length) * 8, (size_t)256) : 0;
     const size_t nslots_b = parallel ? round_up(2 * huff_nsub(h.scan_length) * 4, (size_t)256) : 0;
-    const size_t dcdiff_b = parallel ? round_up((size_t)blocks * 2, (size_t)256) : 0;
+    const size_t dcdiff_b = parallel ? round_up((size_t)total_blocks * 2, (size_t)256) : 0;
     const size_t total = 1024 + round_up(sizeof(JpegHuffSet), (size_t)256) + scan_bytes + coef_bytes + plane_b +
                          clean_b + states_b + nslots_b + dcdiff_b;
     LP_CUDA_OK(cudaMallocAsync(&scratch, total, st));

@@ -43,6 +43,10 @@ struct lp_batch {
     uint8_t* d_clean = nullptr;     // parallel Huffman: unstuffed bit strings (whole batch)
     void* d_states = nullptr;       // parallel Huffman: subsequence exit states
     uint32_t* d_nslots = nullptr;
+    int16_t* d_dcdiff = nullptr;    // per chunk slot: DC differences of all blocks
+    uint32_t total_blocks = 0;      // blocks of a whole image (dcdiff slot stride)
+    int win_w = 0, win_h = 0;       // decoded pixel window (crop, x range aligned out to 16)
+    int win_x0 = 0;
     uint8_t* d_out = nullptr;
     uint32_t* d_out_len = nullptr;
     // host
@@ -70,7 +74,7 @@ static void batch_free(lp_batch* b) {
     cudaFree(b->d_scan); cudaFree(b->d_items); cudaFree(b->d_tables); cudaFree(b->d_coef);
     cudaFree(b->d_planes); cudaFree(b->d_frames); cudaFree(b->d_resized); cudaFree(b->d_enc_scratch);
     cudaFree(b->d_out); cudaFree(b->d_out_len);
-    cudaFree(b->d_clean); cudaFree(b->d_states); cudaFree(b->d_nslots);
+    cudaFree(b->d_clean); cudaFree(b->d_states); cudaFree(b->d_nslots); cudaFree(b->d_dcdiff);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_out_len) cudaFreeHost(b->h_out_len);
     if (b->h_items_back) cudaFreeHost(b->h_items_back);
@@ -136,6 +140,7 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
     BALLOC(b->d_clean, cfg->max_in_bytes + 64 * N + 4096);
     BALLOC(b->d_states, (cfg->max_in_bytes / 128 + 2 * N + 16) * 2 * 8);
     BALLOC(b->d_nslots, (cfg->max_in_bytes / 128 + 2 * N + 16) * 2 * 4);
+    BALLOC(b->d_dcdiff, (size_t)b->chunk * max_blocks * sizeof(int16_t));
     BALLOC(b->d_out, N * cfg->out_cap);
     BALLOC(b->d_out_len, N * sizeof(uint32_t));
 #undef BALLOC
@@ -224,25 +229,32 @@ static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t
             it.table_set = (uint32_t)ts;
             it.width = h.width; it.height = h.height; it.ncomp = h.ncomp;
             it.mcus_x = h.mcus_x; it.mcus_y = h.mcus_y; it.restart_interval = h.restart_interval;
-            uint32_t blocks = 0, plane_bytes = 0;
+            uint32_t total_blocks = 0;
             for (int c = 0; c < h.ncomp; c++) {
                 it.h[c] = h.comp[c].h; it.v[c] = h.comp[c].v;
-                it.bw[c] = h.mcus_x * h.comp[c].h; it.bh[c] = h.mcus_y * h.comp[c].v;
                 it.dw[c] = (h.width * h.comp[c].h + h.maxh - 1) / h.maxh;
                 it.dh[c] = (h.height * h.comp[c].v + h.maxv - 1) / h.maxv;
-                it.block_off[c] = blocks; it.plane_rel[c] = plane_bytes;
-                blocks += (uint32_t)it.bw[c] * it.bh[c];
-                plane_bytes += (uint32_t)it.bw[c] * it.bh[c] * 64;
+                total_blocks += (uint32_t)h.mcus_x * h.mcus_y * h.comp[c].h * h.comp[c].v;
                 memcpy(it.qt[c], h.qt[h.comp[c].tq], sizeof(it.qt[c]));
                 it.td[c] = h.comp[c].td; it.ta[c] = h.comp[c].ta;
             }
             it.frame_channels = 3;
-            if (!b->layout_known) {  // the first image fixes the per-slot scratch stride
+            // decode only what Fit will read: the crop window (+ the chroma-upsampling margin)
+            uint32_t plane_bytes = 0;
+            const uint32_t blocks = jpeg_item_set_window(&it, b->crop_x, b->crop_y, b->crop_x + b->crop_w,
+                                                         b->crop_y + b->crop_h, true, &plane_bytes);
+            if (!b->layout_known) {  // the first image fixes the per-slot scratch strides
                 b->blocks = blocks;
                 b->plane_bytes = plane_bytes;
+                b->total_blocks = total_blocks;
+                b->win_w = it.win_w;
+                b->win_h = it.win_h;
+                b->win_x0 = it.win_x0;
+                b->frame_bytes = (size_t)it.win_stride * it.win_h;
                 b->layout_known = true;
             }
-            if (blocks > b->blocks || blocks > b->max_blocks_alloc) rc = LP_ERR_UNSUPPORTED;  // denser sampling than the slot
+            if (blocks > b->blocks || total_blocks > b->total_blocks || total_blocks > b->max_blocks_alloc)
+                rc = LP_ERR_UNSUPPORTED;  // denser sampling than the slots were laid out for
         }
         b->parse_status[k] = rc;
         it.status = rc ? -1 : 0;
@@ -253,6 +265,7 @@ static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t
         it.coef_off = (uint64_t)slot * b->blocks * 64;
         it.plane_off = (uint64_t)slot * b->plane_bytes;
         it.frame_off = (uint64_t)slot * b->frame_bytes;
+        it.dcdiff_off = (uint64_t)slot * b->total_blocks;
         it.clean_off = b->clean_off;
         it.state_off = b->state_off;
         b->clean_off += huff_clean_bytes(it.scan_len);
@@ -296,8 +309,9 @@ static int batch_launch_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st, cud
     d.n = cnt;
     d.coef_elems_total = (size_t)cnt * b->blocks * 64;
     d.max_blocks_per_image = (int)b->blocks;
-    d.max_width = b->W;
-    d.max_height = b->H;
+    d.max_width = b->win_w;
+    d.max_height = b->win_h;
+    d.dcdiff = b->d_dcdiff;
     d.use_parallel_huffman = b->parallel_huffman;
     d.clean = b->d_clean;
     d.states = b->d_states;
@@ -308,9 +322,9 @@ static int batch_launch_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st, cud
     ResizeArgs r;
     r.src = b->d_frames;
     r.src_img_stride = b->frame_bytes;
-    r.src_row_stride = (size_t)b->W * 3;
+    r.src_row_stride = b->frame_bytes / (size_t)b->win_h;  // window rows (16-byte multiple)
     r.channels = 3;
-    r.crop_x = b->crop_x; r.crop_y = b->crop_y; r.crop_w = b->crop_w; r.crop_h = b->crop_h;
+    r.crop_x = b->crop_x - b->win_x0; r.crop_y = 0; r.crop_w = b->crop_w; r.crop_h = b->crop_h;
     r.dst = b->d_resized + (size_t)i0 * b->resized_bytes;
     r.dst_img_stride = b->resized_bytes;
     r.dst_row_stride = (size_t)b->out_w * 3;

@@ -23,6 +23,62 @@ __constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32,
                                      35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
                                      58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
+// ------------------------------------------------------------------ ROI layout (host)
+
+uint32_t jpeg_item_set_window(JpegDecodeItem* it, int x0, int y0, int x1, int y1, bool align16,
+                              uint32_t* plane_bytes_out) {
+    int maxh = 1, maxv = 1;
+    for (int c = 0; c < it->ncomp; c++) {
+        maxh = it->h[c] > maxh ? it->h[c] : maxh;
+        maxv = it->v[c] > maxv ? it->v[c] : maxv;
+    }
+    x0 = x0 < 0 ? 0 : x0;
+    y0 = y0 < 0 ? 0 : y0;
+    x1 = x1 > it->width ? it->width : x1;
+    y1 = y1 > it->height ? it->height : y1;
+    if (align16) {
+        x0 &= ~15;
+        x1 = (x1 + 15) & ~15;
+        if (x1 > it->width) x1 = it->width;
+    }
+    it->win_x0 = x0;
+    it->win_y0 = y0;
+    it->win_w = x1 - x0;
+    it->win_h = y1 - y0;
+    const int fc = it->ncomp == 1 ? 1 : 3;
+    it->win_stride = (uint32_t)(((size_t)it->win_w * fc + 15) / 16 * 16);
+    if (x0 == 0 && x1 == it->width) it->win_stride = (uint32_t)it->win_w * fc;  // whole rows: packed
+    // fancy upsampling reads one chroma sample beyond the window on every side = 2 luma pixels at 2x
+    const int mw = 8 * maxh, mh = 8 * maxv;
+    int px0 = x0 - 2 * maxh, px1 = x1 - 1 + 2 * maxh, py0 = y0 - 2 * maxv, py1 = y1 - 1 + 2 * maxv;
+    px0 = px0 < 0 ? 0 : px0;
+    py0 = py0 < 0 ? 0 : py0;
+    px1 = px1 > it->width - 1 ? it->width - 1 : px1;
+    py1 = py1 > it->height - 1 ? it->height - 1 : py1;
+    it->roi_mx0 = px0 / mw;
+    it->roi_my0 = py0 / mh;
+    it->roi_mcx = px1 / mw - it->roi_mx0 + 1;
+    it->roi_mcy = py1 / mh - it->roi_my0 + 1;
+    uint32_t blocks = 0, plane_bytes = 0;
+    for (int c = 0; c < it->ncomp; c++) {
+        it->bw[c] = it->roi_mcx * it->h[c];
+        it->bh[c] = it->roi_mcy * it->v[c];
+        it->block_off[c] = blocks;
+        it->plane_rel[c] = plane_bytes;
+        blocks += (uint32_t)it->bw[c] * it->bh[c];
+        plane_bytes += (uint32_t)it->bw[c] * it->bh[c] * 64;
+    }
+    if (plane_bytes_out) *plane_bytes_out = plane_bytes;
+    return blocks;
+}
+
+// Coefficient block of component c at full-image block position (X, Y); nullptr outside the ROI.
+__device__ __forceinline__ int16_t* roi_block(const JpegDecodeItem& it, int16_t* coef, int c, int X, int Y) {
+    const int rx = X - it.roi_mx0 * it.h[c], ry = Y - it.roi_my0 * it.v[c];
+    if (rx < 0 || ry < 0 || rx >= it.bw[c] || ry >= it.bh[c]) return nullptr;
+    return coef + it.coef_off + ((size_t)it.block_off[c] + (size_t)ry * it.bw[c] + rx) * 64;
+}
+
 // ------------------------------------------------------------------ entropy decode (serial)
 
 struct BitReader {
@@ -96,7 +152,6 @@ __global__ void jpeg_huff_decode_kernel(JpegDecodeItem* items, const JpegHuffSet
     JpegDecodeItem& it = items[i];
     const JpegHuffSet* hs = tables + it.table_set;
     BitReader b{scan + it.scan_off, scan + it.scan_off + it.scan_len, 0, 0, false};
-    int16_t* cbase = coef + it.coef_off;
     int pred[3] = {0, 0, 0};
     int todo = it.restart_interval;
     int status = 0;
@@ -123,11 +178,11 @@ __global__ void jpeg_huff_decode_kernel(JpegDecodeItem* items, const JpegHuffSet
                 for (int by = 0; by < it.v[c] && status == 0; by++) {
                     for (int bx = 0; bx < it.h[c]; bx++) {
                         const int X = mx * it.h[c] + bx, Y = my * it.v[c] + by;
-                        int16_t* blk = cbase + ((size_t)it.block_off[c] + (size_t)Y * it.bw[c] + X) * 64;
+                        int16_t* blk = roi_block(it, coef, c, X, Y);  // nullptr: decode but do not store
                         int s = huff_symbol(b, hs, td);
                         if (s < 0 || s > 15) { status = -3; break; }
                         if (s) pred[c] += receive_extend(b, s);
-                        blk[0] = (int16_t)pred[c];
+                        if (blk) blk[0] = (int16_t)pred[c];
                         for (int k = 1; k < 64;) {
                             const int rs = huff_symbol(b, hs, ta);
                             if (rs < 0) { status = -3; break; }
@@ -139,7 +194,8 @@ __global__ void jpeg_huff_decode_kernel(JpegDecodeItem* items, const JpegHuffSet
                             }
                             k += r;
                             if (k > 63) { status = -3; break; }
-                            blk[zz[k]] = (int16_t)receive_extend(b, sz);
+                            const int val = receive_extend(b, sz);
+                            if (blk) blk[zz[k]] = (int16_t)val;
                             k++;
                         }
                         if (status) break;
@@ -266,8 +322,10 @@ __global__ void __launch_bounds__(128)
 // Value of component c at full-resolution pixel (x, y): libjpeg-turbo jdsample.c.
 __device__ __forceinline__ int upsampled(const JpegDecodeItem& it, const uint8_t* planes, int c, int maxh,
                                          int maxv, int x, int y) {
-    const uint8_t* pl = planes + it.plane_off + it.plane_rel[c];
     const int stride = it.bw[c] * 8;
+    // plane origin shifted so that full-image component coordinates index it directly
+    const uint8_t* pl = planes + it.plane_off + it.plane_rel[c] -
+                        ((size_t)(it.roi_my0 * it.v[c] * 8) * stride + (size_t)(it.roi_mx0 * it.h[c] * 8));
     const int hr = maxh / it.h[c], vr = maxv / it.v[c];
     const int cw = it.dw[c], ch = it.dh[c];
     if (hr == 1 && vr == 1) return pl[(size_t)y * stride + x];
@@ -305,27 +363,31 @@ __global__ void __launch_bounds__(128)
     jpeg_upsample_color_kernel(const JpegDecodeItem* items, const uint8_t* planes, uint8_t* frames) {
     const JpegDecodeItem& it = items[blockIdx.z];
     if (it.status != 0) return;
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    const int y = blockIdx.y;
-    if (x0 >= it.width || y >= it.height) return;
-    uint8_t* out = frames + it.frame_off;
+    const int x0 = it.win_x0 + (blockIdx.x * blockDim.x + threadIdx.x) * 16;  // full-image coordinates
+    const int y = it.win_y0 + blockIdx.y;
+    const int xe = it.win_x0 + it.win_w;
+    if (x0 >= xe || y >= it.win_y0 + it.win_h) return;
+    uint8_t* out = frames + it.frame_off + (size_t)(y - it.win_y0) * it.win_stride;  // this window row
     if (it.ncomp == 1) {
-        const uint8_t* pl = planes + it.plane_off + it.plane_rel[0] + (size_t)y * (it.bw[0] * 8);
-        for (int x = x0; x < min(x0 + 16, it.width); x++) out[(size_t)y * it.width + x] = pl[x];
+        const int stride = it.bw[0] * 8;
+        const uint8_t* pl = planes + it.plane_off + it.plane_rel[0] + (size_t)(y - it.roi_my0 * 8) * stride -
+                            (size_t)(it.roi_mx0 * 8);
+        for (int x = x0; x < min(x0 + 16, xe); x++) out[x - it.win_x0] = pl[x];
         return;
     }
     const bool fast = it.h[0] == 2 && it.v[0] == 2 && it.h[1] == 1 && it.v[1] == 1 && it.h[2] == 1 &&
-                      it.v[2] == 1 && (it.width & 15) == 0 && (it.frame_off & 15) == 0;
+                      it.v[2] == 1 && (it.width & 15) == 0 && (it.win_x0 & 15) == 0 && (it.win_w & 15) == 0 &&
+                      (it.win_stride & 15) == 0 && (it.frame_off & 15) == 0;
     if (!fast) {
         const int maxh = max(it.h[0], max(it.h[1], it.h[2])), maxv = max(it.v[0], max(it.v[1], it.v[2]));
-        for (int x = x0; x < min(x0 + 16, it.width); x++) {
+        for (int x = x0; x < min(x0 + 16, xe); x++) {
             const int Y = upsampled(it, planes, 0, maxh, maxv, x, y);
             const int cb = upsampled(it, planes, 1, maxh, maxv, x, y) - 128;
             const int cr = upsampled(it, planes, 2, maxh, maxv, x, y) - 128;
             const int r = Y + ((91881 * cr + 32768) >> 16);
             const int g = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
             const int b = Y + ((116130 * cb + 32768) >> 16);
-            uint8_t* o = out + ((size_t)y * it.width + x) * 3;
+            uint8_t* o = out + (size_t)(x - it.win_x0) * 3;
             o[0] = (uint8_t)min(max(b, 0), 255);
             o[1] = (uint8_t)min(max(g, 0), 255);
             o[2] = (uint8_t)min(max(r, 0), 255);
@@ -334,7 +396,9 @@ __global__ void __launch_bounds__(128)
     }
     const uint8_t* base = planes + it.plane_off;
     const int sy = it.bw[0] * 8, sc = it.bw[1] * 8;
-    const uint4 yv = *reinterpret_cast<const uint4*>(base + it.plane_rel[0] + (size_t)y * sy + x0);
+    const int lx = it.roi_mx0 * 16, ly = it.roi_my0 * 16;  // luma / chroma plane origins (4:2:0)
+    const int cx_ = it.roi_mx0 * 8, cy_ = it.roi_my0 * 8;
+    const uint4 yv = *reinterpret_cast<const uint4*>(base + it.plane_rel[0] + (size_t)(y - ly) * sy + (x0 - lx));
     const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
     const int cw = it.dw[1], chh = it.dh[1];
     const int cy = y >> 1;
@@ -344,8 +408,8 @@ __global__ void __launch_bounds__(128)
     int cs[2][10];  // 3*near + far for chroma columns i0-1 .. i0+8, Cb and Cr
 #pragma unroll
     for (int c = 0; c < 2; c++) {
-        const uint8_t* pn = base + it.plane_rel[1 + c] + (size_t)cy * sc;
-        const uint8_t* pf = base + it.plane_rel[1 + c] + (size_t)fy * sc;
+        const uint8_t* pn = base + it.plane_rel[1 + c] + (size_t)(cy - cy_) * sc - cx_;
+        const uint8_t* pf = base + it.plane_rel[1 + c] + (size_t)(fy - cy_) * sc - cx_;
         const uint2 n8 = *reinterpret_cast<const uint2*>(pn + i0);
         const uint2 f8 = *reinterpret_cast<const uint2*>(pf + i0);
         cs[c][0] = 3 * pn[il] + pf[il];
@@ -381,7 +445,7 @@ __global__ void __launch_bounds__(128)
         ow[(o + 1) >> 2] |= (uint32_t)g << (8 * ((o + 1) & 3));
         ow[(o + 2) >> 2] |= (uint32_t)r << (8 * ((o + 2) & 3));
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)y * it.width + x0) * 3);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(x0 - it.win_x0) * 3);
     dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
     dst[2] = make_uint4(ow[8], ow[9], ow[10], ow[11]);

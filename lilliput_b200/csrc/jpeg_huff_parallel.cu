@@ -186,7 +186,7 @@ template <bool WRITE>
 __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
                                             uint32_t& phase, uint32_t& nslots, int nb,
                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it,
-                                            int16_t* coef, int* status) {
+                                            int16_t* coef, int16_t* dcdiff, int* status) {
     uint32_t blk = phase >> 6, z = phase & 63;
     uint32_t n = 0;
     BitWin bw;
@@ -195,10 +195,15 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
     int16_t* dstblk = nullptr;
     int mx = 0, my = 0;
     uint64_t remaining = 0;
-    auto set_dst = [&]() {
+    int16_t* dcp = nullptr;  // DC difference slot of the current block (all blocks, MCU order)
+    auto set_dst = [&]() {   // nullptr when the block lies outside the region of interest
         const int c = hs.blk_comp[blk];
-        const int X = mx * it->h[c] + hs.blk_bx[blk], Y = my * it->v[c] + hs.blk_by[blk];
-        dstblk = coef + it->coef_off + ((size_t)it->block_off[c] + (size_t)Y * it->bw[c] + X) * 64;
+        const int rx = (mx - it->roi_mx0) * it->h[c] + hs.blk_bx[blk];
+        const int ry = (my - it->roi_my0) * it->v[c] + hs.blk_by[blk];
+        const bool inside = (unsigned)(mx - it->roi_mx0) < (unsigned)it->roi_mcx &&
+                            (unsigned)(my - it->roi_my0) < (unsigned)it->roi_mcy;
+        dstblk = inside ? coef + it->coef_off + ((size_t)it->block_off[c] + (size_t)ry * it->bw[c] + rx) * 64
+                        : nullptr;
     };
     if (WRITE) {
         if (pos >= total_slots) {
@@ -210,6 +215,7 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
         mx = (int)(mcu % (uint32_t)it->mcus_x);
         my = (int)(mcu / (uint32_t)it->mcus_x);
         set_dst();
+        dcp = dcdiff + (pos >> 6);
     }
     // shared-memory byte addresses of the current block's lookahead tables
     uint32_t dcb = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[blk]][0]);
@@ -259,7 +265,8 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
             if (zn <= 63) {
                 const uint32_t raw = sz ? ((top << len) >> (32 - sz)) : 0u;
                 const int val = sz ? ((int)raw < (1 << (sz - 1)) ? (int)raw - (1 << sz) + 1 : (int)raw) : 0;
-                dstblk[hs.zz[zn]] = (int16_t)val;
+                if (isdc) *dcp = (int16_t)val;                          // DC difference: every block
+                else if (dstblk) dstblk[hs.zz[zn]] = (int16_t)val;      // AC: only inside the ROI
             } else {
                 *status = -3;  // coefficient index past 63: corrupt data
             }
@@ -279,7 +286,10 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
             }
             dcb = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[blk]][0]);
             acb = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[blk]][0]);
-            if (WRITE && n < remaining) set_dst();
+            if (WRITE) {
+                dcp++;
+                if (n < remaining) set_dst();
+            }
         }
     }
     phase = (blk << 6) | z;
@@ -288,7 +298,7 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
 
 __global__ void __launch_bounds__(kHuffThreads, 4)
     jpeg_huff_sync_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* clean,
-                          SubState* states_all, uint32_t* nslots_all, int16_t* coef) {
+                          SubState* states_all, uint32_t* nslots_all, int16_t* coef, int16_t* dcdiff_all) {
     __shared__ HuffShared hs;
     __shared__ uint32_t warp_sums[kHuffThreads / 32];
     __shared__ uint32_t s_carry;
@@ -350,12 +360,13 @@ __global__ void __launch_bounds__(kHuffThreads, 4)
     uint32_t* list_a = reinterpret_cast<uint32_t*>(st + nsub);  // 2*nsub uint32 = two work lists
     uint32_t* list_b = list_a + nsub;
     const uint64_t total_slots = (uint64_t)it.mcus_x * it.mcus_y * nb * 64;
+    int16_t* dcdiff = dcdiff_all + it.dcdiff_off;
 
     // ---- pass 0: every subsequence from a guessed state (exact only for subsequence 0)
     for (uint32_t i = tid; i < nsub; i += kHuffThreads) {
         uint32_t p = i * kSubBits, phase = 0, n = 0;
         const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-        decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr);
+        decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr, nullptr);
         st[i] = SubState{p, phase};
         ns[i] = n;
     }
@@ -381,10 +392,11 @@ __global__ void __launch_bounds__(kHuffThreads, 4)
             const SubState old = st[i];
             uint32_t p = in.p, phase = in.phase, n = 0;
             const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-            if (p < limit) decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr);
-            if (p != old.p || phase != old.phase || n != ns[i]) {
+            if (p < limit) decode_span<false>(hs, s, p, limit, phase, n, nb, 0, 0, nullptr, nullptr, nullptr, nullptr);
+            ns[i] = n;  // slots consumed depend on the entry state even when the exit state does not
+            if (p != old.p || phase != old.phase) {
+                // only an exit-state change can affect the right neighbour
                 *reinterpret_cast<volatile uint64_t*>(&st[i]) = ((uint64_t)phase << 32) | p;
-                ns[i] = n;
                 if (i + 1 < nsub) nxt_list[atomicAdd(&s_carry, 1u)] = i + 1;
             }
         }
@@ -420,7 +432,7 @@ __global__ void __launch_bounds__(kHuffThreads, 4)
                 (uint32_t)(pos % ((uint64_t)nb * 64)) != ((phase >> 6) * 64 + (phase & 63)))
                 status = -3;
             if (!status && p < limit)
-                decode_span<true>(hs, s, p, limit, phase, n, nb, pos, total_slots, &it, coef, &status);
+                decode_span<true>(hs, s, p, limit, phase, n, nb, pos, total_slots, &it, coef, dcdiff, &status);
             if (status) s_status = status;
         }
         __syncthreads();
@@ -433,8 +445,9 @@ __global__ void __launch_bounds__(kHuffThreads, 4)
     }
     __syncthreads();
     if (s_status) return;
-    // ---- 3. DC differences (in slot 0 of every block) -> DC values: per component, prefix sum in
-    //         MCU (scan) order
+    // ---- 3. DC differences -> DC values: per component, prefix sum over ALL blocks in MCU (scan)
+    //         order; only blocks inside the region of interest are stored
+    int koff = 0;
     for (int c = 0; c < it.ncomp; c++) {
         const int bpc = it.h[c] * it.v[c];
         const uint32_t nblk = (uint32_t)it.mcus_x * it.mcus_y * bpc;
@@ -443,22 +456,28 @@ __global__ void __launch_bounds__(kHuffThreads, 4)
         for (uint32_t base = 0; base < nblk; base += kHuffThreads) {
             const uint32_t j = base + tid;
             int d = 0;
-            int16_t* slot0 = nullptr;
+            uint32_t mcu = 0, kk = 0;
             if (j < nblk) {
-                const uint32_t mcu = j / bpc, kk = j % bpc;
-                const int bx = kk % it.h[c], by = kk / it.h[c];
-                const int mx = (int)(mcu % (uint32_t)it.mcus_x), my = (int)(mcu / (uint32_t)it.mcus_x);
-                const int X = mx * it.h[c] + bx, Y = my * it.v[c] + by;
-                slot0 = coef + it.coef_off + ((size_t)it.block_off[c] + (size_t)Y * it.bw[c] + X) * 64;
-                d = *slot0;
+                mcu = j / bpc;
+                kk = j % bpc;
+                d = dcdiff[(size_t)mcu * nb + koff + kk];
             }
             uint32_t total;  // signed prefix sum through unsigned wrap-around arithmetic
             const uint32_t ex = block_excl_scan<kHuffThreads>((uint32_t)d, &total, warp_sums);
-            if (j < nblk) *slot0 = (int16_t)(int)(s_carry + ex + (uint32_t)d);
+            if (j < nblk) {
+                const int mx = (int)(mcu % (uint32_t)it.mcus_x) - it.roi_mx0;
+                const int my = (int)(mcu / (uint32_t)it.mcus_x) - it.roi_my0;
+                if ((unsigned)mx < (unsigned)it.roi_mcx && (unsigned)my < (unsigned)it.roi_mcy) {
+                    const int rx = mx * it.h[c] + (int)(kk % it.h[c]), ry = my * it.v[c] + (int)(kk / it.h[c]);
+                    coef[it.coef_off + ((size_t)it.block_off[c] + (size_t)ry * it.bw[c] + rx) * 64] =
+                        (int16_t)(int)(s_carry + ex + (uint32_t)d);
+                }
+            }
             __syncthreads();
             if (tid == 0) s_carry += total;
             __syncthreads();
         }
+        koff += bpc;
     }
 }
 
@@ -478,7 +497,8 @@ int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st) {
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     jpeg_huff_sync_kernel<<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean,
-                                                       reinterpret_cast<SubState*>(a.states), a.nslots, a.coef);
+                                                       reinterpret_cast<SubState*>(a.states), a.nslots, a.coef,
+                                                       a.dcdiff);
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     return LP_OK;

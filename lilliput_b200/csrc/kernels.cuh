@@ -72,7 +72,21 @@ struct JpegDecodeItem {
     uint64_t dcdiff_off;    // int16 offset of this image's DC-difference array (MCU order)
     uint32_t clean_len;     // written by jpeg_unstuff_kernel
     uint32_t pad_;
+    // Region of interest.  Only MCUs [roi_mx0, roi_mx0+roi_mcx) x [roi_my0, roi_my0+roi_mcy) get
+    // coefficients / planes (bw, bh, block_off, plane_rel describe THAT grid); the packed frame holds
+    // the pixel window [win_x0, win_x0+win_w) x [win_y0, win_y0+win_h) with rows win_stride apart.
+    // A full decode has roi = every MCU and win = the whole image.
+    int32_t roi_mx0, roi_my0, roi_mcx, roi_mcy;
+    int32_t win_x0, win_y0, win_w, win_h;
+    uint32_t win_stride;
+    uint32_t pad2_;
 };
+
+// Fills the ROI / window / layout fields of `it` (whose width, height, ncomp, h, v, mcus_* are set)
+// for the pixel window [x0,x1) x [y0,y1).  align16 rounds the window's x range outwards to 16 px so
+// the vectorised colour kernel can use 16-byte stores.  Returns blocks in the ROI.
+uint32_t jpeg_item_set_window(JpegDecodeItem* it, int x0, int y0, int x1, int y1, bool align16,
+                              uint32_t* plane_bytes);
 
 // Huffman decode tables for one image (or many images sharing them), device format.
 struct JpegHuffSet {
@@ -100,7 +114,7 @@ struct JpegDecodeBatch {
     uint8_t* clean = nullptr;
     void* states = nullptr;      // SubState[]
     uint32_t* nslots = nullptr;
-    int16_t* dcdiff = nullptr;
+    int16_t* dcdiff = nullptr;   // DC differences of ALL blocks of an image, MCU order
 };
 // Scratch sizing for the parallel Huffman path, per image with `scan_len` entropy-coded bytes.
 inline size_t huff_clean_bytes(size_t scan_len) { return ((scan_len + 48 + 15) / 16) * 16; }

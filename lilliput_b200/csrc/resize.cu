@@ -634,7 +634,7 @@ int resize_launch(const ResizeArgs& a, cudaStream_t st) {
         // bands: keep >= ~4 CTAs per SM in flight when the batch is small
         long ctas_per_row_group = (long)ceil_div(a.dst_w, kAreaTile) * a.n;
         static const int rpb_env = getenv("LP_RESIZE_RPB") ? atoi(getenv("LP_RESIZE_RPB")) : 0;
-        int rpb = rpb_env > 0 ? std::min(rpb_env, kAreaMaxBand) : 8;
+        int rpb = rpb_env > 0 ? std::min(rpb_env, kAreaMaxBand) : 16;
         while (rpb > 1 && ctas_per_row_group * ceil_div(a.dst_h, rpb) < 4L * kNumSMs) rpb >>= 1;
         p.rows_per_band = rpb;
         if (area_smem_bytes(p.slot_bytes) > 200 * 1024 || ty.padt > kAreaMaxYTaps) {

@@ -75,3 +75,25 @@ def test_empty_batch(cuda_lib):
         assert outs == [] and status == []
     finally:
         b.close()
+
+
+@pytest.mark.parametrize("geom", [(333, 217, 64, 64), (640, 480, 100, 300), (96, 64, 96, 64),
+                                  (1280, 720, 256, 256), (48, 1000, 31, 17), (1000, 48, 500, 20)])
+def test_batch_roi_geometries(cuda_lib, oracle, geom):
+    """The batch path decodes only the Fit crop window (+ chroma margin): odd sizes, windows that
+    touch the image edges, tall / wide crops, and the same-size copy case must still equal the
+    full-frame oracle result."""
+    w, h, dw, dh = geom
+    n = 3
+    files = _corpus(oracle, n, w, h)
+    b = abi.Batch(cuda_lib, 0, 4, w, h, dw, dh, 85, max_in_bytes=sum(map(len, files)) + 4096,
+                  out_cap=max(65536, w * h))
+    try:
+        outs, status = b.transform(files)
+        assert status == [0] * n
+        ew, eh = oracle.expected_size(w, h, dw, dh)
+        for f, o in zip(files, outs):
+            dec, _ = oracle.jpeg_decode(f)
+            assert o == oracle.jpeg_encode(oracle.fit(dec, ew, eh), 85)
+    finally:
+        b.close()

@@ -269,7 +269,8 @@ def main():
 
     n = args.batch
     t_setup = time.time()
-    base, arena, offs, lens = make_corpus(lib, local_rank, n, 1000 + rank * n)
+    from lilliput_b200.shard import corpus_seed, max_over_ranks
+    base, arena, offs, lens = make_corpus(lib, local_rank, n, corpus_seed(1000, rank, n))
     in_bytes = int(sum(lens))
     out_cap = 65536
     b = abi.Batch(lib, local_rank, n, SRC_W, SRC_H, DST, DST, Q_OUT, max_in_bytes=in_bytes + (1 << 20),
@@ -326,10 +327,7 @@ def main():
     e2e_s = time.perf_counter() - t0
     assert all(status[i] == 0 for i in range(n))
 
-    t_dev = torch.tensor([dev_ms / 1000.0, e2e_s, wall_s], device="cuda", dtype=torch.float64)
-    if dist:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_s, e2e_max, wall_max = [float(x) for x in t_dev.tolist()]
+    dev_s, e2e_max, wall_max = max_over_ranks([dev_ms / 1000.0, e2e_s, wall_s], dist, device="cuda")
 
     if rank == 0:
         peaks = {}

@@ -18,12 +18,18 @@
 //   3. the same kernel then turns DC differences into DC values with a per-component prefix sum.
 // (Scheme after Weissenberger & Schmidt, "Accelerating JPEG Decompression on GPUs", restated from
 // the published description.)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace lp {
 
-constexpr int kSubBits = 1024;  // subsequence length in bits (128 bytes)
+constexpr uint32_t kMinSubBits = 1024;  // shortest subsequence (bits); scratch is sized for this
+// Subsequences per thread and pass.  Synchronising the position inside the MCU (not just the
+// codeword boundary) takes several hundred symbols, so short subsequences need ~10 re-decode rounds;
+// sizing them so that one pass is exactly kSubPerThread full rounds of the CTA cuts that to ~3.
+constexpr uint32_t kSubPerThread = 2;
 constexpr int kHuffThreads = 512;
 
 __constant__ uint8_t c_zigzag_p[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
@@ -298,7 +304,8 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
 
 __global__ void __launch_bounds__(kHuffThreads, 4)
     jpeg_huff_sync_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* clean,
-                          SubState* states_all, uint32_t* nslots_all, int16_t* coef, int16_t* dcdiff_all) {
+                          SubState* states_all, uint32_t* nslots_all, int16_t* coef, int16_t* dcdiff_all,
+                          uint32_t sub_per_thread) {
     __shared__ HuffShared hs;
     __shared__ uint32_t warp_sums[kHuffThreads / 32];
     __shared__ uint32_t s_carry;
@@ -354,6 +361,8 @@ __global__ void __launch_bounds__(kHuffThreads, 4)
     for (int c = 0; c < it.ncomp; c++) nb += it.h[c] * it.v[c];
     const uint8_t* s = clean + it.clean_off;
     const uint32_t total_bits = it.clean_len * 8u;
+    uint32_t kSubBits = (total_bits + kHuffThreads * sub_per_thread - 1) / (kHuffThreads * sub_per_thread);
+    kSubBits = max(kMinSubBits, (kSubBits + 31u) & ~31u);
     const uint32_t nsub = (total_bits + kSubBits - 1) / kSubBits;
     SubState* st = states_all + it.state_off;      // nsub entries (second half: work lists)
     uint32_t* ns = nslots_all + it.state_off;      // [0,nsub): slots consumed per subsequence
@@ -493,12 +502,13 @@ int jpeg_huff_parallel_slots() {
 
 int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st) {
     if (a.n <= 0) return LP_OK;
+    static const uint32_t spt = getenv("LP_HUFF_SPT") ? (uint32_t)atoi(getenv("LP_HUFF_SPT")) : kSubPerThread;
     jpeg_unstuff_kernel<<<a.n, kHuffThreads, 0, st>>>(a.items, a.scan, a.clean);
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     jpeg_huff_sync_kernel<<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean,
                                                        reinterpret_cast<SubState*>(a.states), a.nslots, a.coef,
-                                                       a.dcdiff);
+                                                       a.dcdiff, spt);
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     return LP_OK;

@@ -1,0 +1,107 @@
+"""CPU: the product library loads without a GPU and exports every symbol the headers declare
+(no compute call is made here), and the host-only container helpers behave like the reference."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "lilliput_b200", "liblilliput_b200.so")
+
+
+def _declared():
+    names = set()
+    for h in ("lp_opencv.h", "lilliput_b200.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b((?:opencv|lp)_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB), "run __graft_entry__.build() first"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB]).decode()
+    have = {l.split()[-1] for l in out.splitlines()}
+    missing = sorted(n for n in _declared() if n not in have)
+    assert missing == []
+    for g in ("CV_INTER_AREA", "CV_INTER_LINEAR", "CV_INTER_CUBIC"):  # ref opencv.hpp:53-55
+        assert g in have
+    # the 36 functions of the reference's opencv.hpp:61-132
+    assert len([n for n in _declared() if n.startswith("opencv_")]) == 36
+
+
+def test_library_loads_and_host_only_entry_points_work():
+    l = C.CDLL(LIB)
+    l.lp_backend_name.restype = C.c_char_p
+    assert l.lp_backend_name() == b"cuda-sm100a"
+    assert C.c_int.in_dll(l, "CV_INTER_AREA").value == 3
+    assert C.c_int.in_dll(l, "CV_INTER_LINEAR").value == 1
+    # type helpers (ref opencv.cpp:83-96): CV_8UC3 = 16, CV_16UC4 = 26
+    assert l.opencv_type_depth(16) == 8 and l.opencv_type_channels(16) == 3
+    assert l.opencv_type_depth(26) == 16 and l.opencv_type_channels(26) == 4
+    assert l.opencv_type_convert_depth(26, 0) == 24
+    # mat over caller memory: NULL when the buffer is too small (ref opencv.cpp:29-32)
+    l.opencv_mat_create_from_data.restype = C.c_void_p
+    l.opencv_mat_create_from_data.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    l.opencv_mat_release.argtypes = [C.c_void_p]
+    buf = np.zeros(100, dtype=np.uint8)
+    assert l.opencv_mat_create_from_data(10, 10, 16, buf.ctypes.data, buf.size) is None
+    m = l.opencv_mat_create_from_data(5, 5, 16, buf.ctypes.data, buf.size)
+    assert m
+    l.opencv_mat_get_width.argtypes = [C.c_void_p]
+    l.opencv_mat_get_data.argtypes = [C.c_void_p]
+    l.opencv_mat_get_data.restype = C.c_void_p
+    assert l.opencv_mat_get_width(m) == 5 and l.opencv_mat_get_data(m) == buf.ctypes.data
+    l.opencv_mat_release(m)
+    # decoder sniffing: unknown signature -> NULL (ErrInvalidImage), JPEG header parse is host-only
+    l.opencv_decoder_create.restype = C.c_void_p
+    l.opencv_decoder_create.argtypes = [C.c_void_p]
+    junk = np.frombuffer(b"definitely not an image", dtype=np.uint8).copy()
+    jm = l.opencv_mat_create_from_data(junk.size, 1, 0, junk.ctypes.data, junk.size)
+    assert l.opencv_decoder_create(jm) is None
+    l.opencv_mat_release(jm)
+
+
+def test_jpeg_header_and_cicp_helpers(golden):
+    l = C.CDLL(LIB)
+    data = golden["c6_input"].copy()  # EXIF orientation 6
+    l.opencv_mat_create_from_data.restype = C.c_void_p
+    l.opencv_mat_create_from_data.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    l.opencv_decoder_create.restype = C.c_void_p
+    l.opencv_decoder_create.argtypes = [C.c_void_p]
+    for f in ("opencv_decoder_read_header", "opencv_decoder_get_width", "opencv_decoder_get_height",
+              "opencv_decoder_get_orientation", "opencv_decoder_get_pixel_type", "opencv_decoder_release"):
+        getattr(l, f).argtypes = [C.c_void_p]
+    l.opencv_decoder_read_header.restype = C.c_bool
+    l.opencv_decoder_get_description.restype = C.c_char_p
+    l.opencv_decoder_get_description.argtypes = [C.c_void_p]
+    m = l.opencv_mat_create_from_data(data.size, 1, 0, data.ctypes.data, data.size)
+    d = l.opencv_decoder_create(m)
+    assert d and l.opencv_decoder_get_description(d) == b"JPEG"
+    assert l.opencv_decoder_read_header(d)
+    h, w = golden["c6_decoded"].shape[:2]
+    assert (l.opencv_decoder_get_width(d), l.opencv_decoder_get_height(d)) == (w, h)
+    assert l.opencv_decoder_get_orientation(d) == 6
+    assert l.opencv_decoder_get_pixel_type(d) == 16
+    l.opencv_decoder_release(d)
+    # cICP insert + read back (ref opencv.cpp:413-464, png_cicp_test.go)
+    png = bytearray(b"\x89PNG\r\n\x1a\n" + b"\x00\x00\x00\x0dIHDR" + bytes(13) + bytes(4) +
+                    b"\x00\x00\x00\x00IEND\xaeB`\x82")
+    cap = len(png) + 32
+    arr = (C.c_uint8 * cap)(*png)
+    l.opencv_png_insert_cicp.restype = C.c_size_t
+    l.opencv_png_insert_cicp.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t] + [C.c_uint8] * 4
+    n = l.opencv_png_insert_cicp(arr, len(png), cap, 12, 13, 0, 1)
+    assert n == len(png) + 16
+    out = bytes(arr[:n])
+    assert out[33:37] == b"\x00\x00\x00\x04" and out[37:41] == b"cICP" and out[41:45] == bytes([12, 13, 0, 1])
+    import zlib
+    assert int.from_bytes(out[45:49], "big") == zlib.crc32(out[37:45])
+    vals = [C.c_uint8() for _ in range(4)]
+    l.opencv_decoder_get_png_cicp.argtypes = [C.c_void_p, C.c_size_t] + [C.POINTER(C.c_uint8)] * 4
+    assert l.opencv_decoder_get_png_cicp(arr, n, *[C.byref(v) for v in vals]) == 1
+    assert [v.value for v in vals] == [12, 13, 0, 1]
+    assert l.opencv_png_insert_cicp(arr, n, n + 3, 1, 1, 1, 1) == n  # no room: unchanged

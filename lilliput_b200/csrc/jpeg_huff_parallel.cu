@@ -28,8 +28,9 @@ namespace lp {
 constexpr uint32_t kMinSubBits = 1024;  // shortest subsequence (bits); scratch is sized for this
 // Subsequences per thread and pass.  Synchronising the position inside the MCU (not just the
 // codeword boundary) takes several hundred symbols, so short subsequences need ~10 re-decode rounds;
-// sizing them so that one pass is exactly kSubPerThread full rounds of the CTA cuts that to ~3.
-constexpr uint32_t kSubPerThread = 2;
+// sizing them so that one pass is exactly kSubPerThread full rounds of the CTA cuts that to ~2
+// (measured: 10.9 rounds at 1024 bits, 1.9 at one subsequence per thread).
+constexpr uint32_t kSubPerThread = 1;
 constexpr int kHuffThreads = 512;
 
 __constant__ uint8_t c_zigzag_p[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
@@ -194,14 +195,16 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it,
                                             int16_t* coef, int16_t* dcdiff, int* status) {
     uint32_t blk = phase >> 6, z = phase & 63;
-    uint32_t n = 0;
+    const uint32_t z_start = z;
+    uint32_t closed = 0;                       // blocks completed in this span
+    int32_t bits_left = (int32_t)(limit - p);  // symbols that START before `limit` belong to this span
     BitWin bw;
     bw.init(s, p);
     // WRITE: running block position
     int16_t* dstblk = nullptr;
+    int16_t* dcp = nullptr;  // DC difference slot of the current block (all blocks, MCU order)
     int mx = 0, my = 0;
     uint64_t remaining = 0;
-    int16_t* dcp = nullptr;  // DC difference slot of the current block (all blocks, MCU order)
     auto set_dst = [&]() {   // nullptr when the block lies outside the region of interest
         const int c = hs.blk_comp[blk];
         const int rx = (mx - it->roi_mx0) * it->h[c] + hs.blk_bx[blk];
@@ -216,7 +219,7 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
             nslots = 0;
             return;
         }
-        remaining = total_slots - pos;
+        remaining = total_slots - pos + z_start;  // slots from the start of the current block
         const uint32_t mcu = (uint32_t)((pos >> 6) / (uint32_t)nb);
         mx = (int)(mcu % (uint32_t)it->mcus_x);
         my = (int)(mcu / (uint32_t)it->mcus_x);
@@ -226,10 +229,10 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
     // shared-memory byte addresses of the current block's lookahead tables
     uint32_t dcb = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[blk]][0]);
     uint32_t acb = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[blk]][0]);
-    // The symbol step is written with selects instead of branches: lanes of a warp sit at unrelated
-    // places of unrelated subsequences, so every branch here would be a divergent one.
-    while (p < limit) {
-        if (WRITE && n >= remaining) break;  // every MCU produced: the rest is padding
+    // The symbol step uses selects instead of branches: lanes of a warp sit at unrelated places of
+    // unrelated subsequences, so every branch here would be a divergent one.  Coefficient slots are
+    // not counted per symbol: slots = 64 * blocks closed + z_end - z_start.
+    while (bits_left > 0) {
         bw.refill();
         const uint32_t top = (uint32_t)(bw.acc >> 32);
         const bool isdc = z == 0;
@@ -251,37 +254,33 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
                     break;
                 }
                 bw.skip(1);
-                p += 1;
+                bits_left -= 1;
                 continue;
             }
             sym = hs.vals[t][(code + hs.valoffset[t][len]) & 0xFF];
         }
         const uint32_t r = (uint32_t)sym >> 4, sz = (uint32_t)sym & 15;
-        const bool ez = (sz == 0) && !isdc;                  // EOB or ZRL
-        const uint32_t zn = z + r;                           // DC symbols have r == 0
-        const bool zrl_ok = ez && r == 15 && z + 16 <= 63;   // a ZRL that leaves the block ends it
-        const bool val_ok = !ez && zn <= 63;
-        uint32_t n_add = 64 - z, z_new = 0;                  // EOB / overrun: close the block
-        n_add = zrl_ok ? 16u : n_add;
-        z_new = zrl_ok ? z + 16 : z_new;
-        n_add = val_ok ? r + 1 : n_add;
-        z_new = val_ok ? ((zn + 1) & 63u) : z_new;
+        const bool ez = (sz == 0) && !isdc;  // EOB or ZRL (DC symbols have r == 0 and are values)
+        // slots this symbol advances: value r+1, ZRL 16, EOB "to the end"; reaching or passing 64
+        // closes the block (a ZRL or run that would leave the block ends it, as libjpeg does)
+        const uint32_t adv = ez ? (r == 15 ? 16u : 64u) : r + 1;
+        const uint32_t zt = z + adv;
         const int used = len + (ez ? 0 : (int)sz);
         if (WRITE && !ez) {
-            if (zn <= 63) {
+            if (zt <= 64) {
                 const uint32_t raw = sz ? ((top << len) >> (32 - sz)) : 0u;
                 const int val = sz ? ((int)raw < (1 << (sz - 1)) ? (int)raw - (1 << sz) + 1 : (int)raw) : 0;
-                if (isdc) *dcp = (int16_t)val;                          // DC difference: every block
-                else if (dstblk) dstblk[hs.zz[zn]] = (int16_t)val;      // AC: only inside the ROI
+                if (isdc) *dcp = (int16_t)val;                            // DC difference: every block
+                else if (dstblk) dstblk[hs.zz[zt - 1]] = (int16_t)val;   // AC: only inside the ROI
             } else {
                 *status = -3;  // coefficient index past 63: corrupt data
             }
         }
         bw.skip(used);
-        p += (uint32_t)used;
-        n += n_add;
-        z = z_new;
+        bits_left -= used;
+        z = zt >= 64 ? 0u : zt;
         if (z == 0) {  // block finished
+            closed++;
             blk++;
             if (blk == (uint32_t)nb) {
                 blk = 0;
@@ -293,13 +292,15 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
             dcb = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[blk]][0]);
             acb = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[blk]][0]);
             if (WRITE) {
+                if ((uint64_t)closed * 64 >= remaining) break;  // every MCU produced: the rest is padding
                 dcp++;
-                if (n < remaining) set_dst();
+                set_dst();
             }
         }
     }
+    p = limit - (uint32_t)bits_left;  // bits_left <= 0 here unless the stream ended early
     phase = (blk << 6) | z;
-    nslots = n;
+    nslots = closed * 64 + z - z_start;
 }
 
 __global__ void __launch_bounds__(kHuffThreads, 4)

@@ -40,6 +40,9 @@ def lib():
         l.oracle_jpeg_encode.restype = C.c_size_t
         l.oracle_jpeg_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_void_p, C.c_size_t]
+        l.oracle_png_decode.restype = C.c_int
+        l.oracle_png_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t] + \
+            [C.POINTER(C.c_int)] * 4
         l.oracle_orient.restype = C.c_int
         l.oracle_orient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -103,6 +106,22 @@ def jpeg_decode(data: bytes):
         raise RuntimeError(f"oracle_jpeg_decode rc={rc}")
     shape = (h.value, w.value, c.value) if c.value > 1 else (h.value, w.value)
     return out.reshape(shape), o.value
+
+
+def png_decode(data: bytes):
+    src = np.frombuffer(data, dtype=np.uint8)
+    w, h, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rc = lib().oracle_png_decode(src.ctypes.data, src.size, None, 0, C.byref(w), C.byref(h),
+                                 C.byref(c), C.byref(d))
+    if rc != 0:
+        raise RuntimeError(f"oracle_png_decode header rc={rc}")
+    out = np.empty(h.value * w.value * c.value, dtype=np.uint8)
+    rc = lib().oracle_png_decode(src.ctypes.data, src.size, out.ctypes.data, out.size,
+                                 C.byref(w), C.byref(h), C.byref(c), C.byref(d))
+    if rc != 0:
+        raise RuntimeError(f"oracle_png_decode rc={rc}")
+    shape = (h.value, w.value, c.value) if c.value > 1 else (h.value, w.value)
+    return out.reshape(shape)
 
 
 def jpeg_encode(img: np.ndarray, quality: int = 95) -> bytes:

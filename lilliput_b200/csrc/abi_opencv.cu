@@ -143,6 +143,8 @@ struct Decoder {
     const uint8_t* data = nullptr;
     size_t len = 0;
     JpegHeader jpeg;
+    PngHeader png;
+    bool is_png = false;
     bool header_ok = false;
     std::string description;
 };
@@ -240,6 +242,69 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
     if (!rc) {
         LP_CUDA_OK(cudaMemcpyAsync(&back, d_item, sizeof(back), cudaMemcpyDeviceToHost, st));
         rc = sync_stream();
+    }
+    cudaFreeAsync(scratch, st);
+    if (rc) return rc;
+    return back.status == 0 ? LP_OK : LP_ERR_DECODING_FAILED;
+}
+
+// Decode one PNG into m (device mirror).  Used by opencv_decoder_read_data.
+static int decode_png_into(const Decoder* d, Mat* m) {
+    const PngHeader& h = d->png;
+    if (h.interlace) {
+        fprintf(stderr, "[lilliput_b200] interlaced PNG is not supported on the device path\n");
+        return LP_ERR_UNSUPPORTED;
+    }
+    if (h.idat_total < 2) return LP_ERR_DECODING_FAILED;
+    cudaStream_t st = thread_stream();
+    PngDecodeItem it;
+    memset(&it, 0, sizeof(it));
+    it.z_len = (uint32_t)h.idat_total;
+    it.width = h.width;
+    it.height = h.height;
+    it.bit_depth = h.bit_depth;
+    it.color_type = h.color_type;
+    it.src_channels = h.src_channels;
+    it.out_channels = h.out_channels;
+    it.bpp = h.bpp;
+    it.row_bytes = (uint32_t)h.row_bytes;
+    it.frame_stride = (uint32_t)m->dev_step;
+    it.npal = h.npal;
+    it.ntrns = h.ntrns;
+    it.has_trns = h.has_trns;
+    memcpy(it.trns_rgb, h.trns_rgb, sizeof(it.trns_rgb));
+    memcpy(it.palette, h.palette, sizeof(it.palette));
+    memcpy(it.trns, h.trns, sizeof(it.trns));
+    // the IDAT payloads form ONE zlib stream: gather them on the host, one H2D copy
+    std::vector<uint8_t> z(h.idat_total + 16, 0);
+    size_t o = 0;
+    for (const PngSegment& sgm : h.idat) {
+        memcpy(z.data() + o, d->data + sgm.offset, sgm.length);
+        o += sgm.length;
+    }
+    const size_t zb = round_up(z.size(), (size_t)256);
+    const size_t rawb = round_up((h.row_bytes + 1) * (size_t)h.height + 16, (size_t)256);
+    uint8_t* scratch = nullptr;
+    LP_CUDA_OK(cudaMallocAsync(&scratch, 4096 + zb + rawb, st));
+    PngDecodeItem* d_item = reinterpret_cast<PngDecodeItem*>(scratch);
+    uint8_t* d_z = scratch + 4096;
+    uint8_t* d_raw = d_z + zb;
+    static_assert(sizeof(PngDecodeItem) <= 4096, "item fits its slot");
+    LP_CUDA_OK(cudaMemcpyAsync(d_item, &it, sizeof(it), cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaMemcpyAsync(d_z, z.data(), z.size(), cudaMemcpyHostToDevice, st));
+    PngDecodeBatch b;
+    b.items = d_item;
+    b.z = d_z;
+    b.raw = d_raw;
+    b.frames = m->dptr();
+    b.n = 1;
+    b.max_width = h.width;
+    b.max_height = h.height;
+    int rc = png_decode_launch(b, st);
+    PngDecodeItem back;
+    if (!rc) {
+        LP_CUDA_OK(cudaMemcpyAsync(&back, d_item, sizeof(back), cudaMemcpyDeviceToHost, st));
+        rc = sync_stream();  // also keeps `z` alive until the copy has been consumed
     }
     cudaFreeAsync(scratch, st);
     if (rc) return rc;
@@ -566,27 +631,43 @@ bool opencv_decoder_read_header(opencv_decoder d) {
         dd->header_ok = (rc == LP_OK);
         return dd->header_ok;
     }
-    fprintf(stderr, "[lilliput_b200] %s decode is not implemented on the device path yet\n",
-            dd->description.c_str());
-    return false;
+    dd->is_png = true;
+    dd->header_ok = png_parse(dd->data, dd->len, &dd->png) == LP_OK;
+    return dd->header_ok;
 }
 
-int opencv_decoder_get_width(const opencv_decoder d) { return static_cast<Decoder*>(d)->jpeg.width; }
-int opencv_decoder_get_height(const opencv_decoder d) { return static_cast<Decoder*>(d)->jpeg.height; }
+int opencv_decoder_get_width(const opencv_decoder d) {
+    const Decoder* dd = static_cast<Decoder*>(d);
+    return dd->is_png ? dd->png.width : dd->jpeg.width;
+}
+int opencv_decoder_get_height(const opencv_decoder d) {
+    const Decoder* dd = static_cast<Decoder*>(d);
+    return dd->is_png ? dd->png.height : dd->jpeg.height;
+}
 int opencv_decoder_get_pixel_type(const opencv_decoder d) {
-    return static_cast<Decoder*>(d)->jpeg.ncomp == 1 ? CV_8UC1 : CV_8UC3;
+    const Decoder* dd = static_cast<Decoder*>(d);
+    if (dd->is_png)  // 16-bit files report CV_16UCn; the 8-bit Framebuffer strips them (opencv.go:255)
+        return (dd->png.bit_depth == 16 ? CV_16U : CV_8U) + ((dd->png.out_channels - 1) << 3);
+    return dd->jpeg.ncomp == 1 ? CV_8UC1 : CV_8UC3;
 }
 int opencv_decoder_get_orientation(const opencv_decoder d) {
-    return static_cast<Decoder*>(d)->jpeg.orientation;
+    const Decoder* dd = static_cast<Decoder*>(d);
+    return dd->is_png ? 1 : dd->jpeg.orientation;
 }
 
 bool opencv_decoder_read_data(opencv_decoder d, opencv_mat dst) {
     Decoder* dd = static_cast<Decoder*>(d);
     Mat* m = static_cast<Mat*>(dst);
     if (!dd || !m || !dd->header_ok) return false;
-    const int type = dd->jpeg.ncomp == 1 ? CV_8UC1 : CV_8UC3;
-    if (fresh_dev(m, dd->jpeg.width, dd->jpeg.height, type)) return false;
-    int rc = decode_jpeg_into(dd, m);
+    int rc;
+    if (dd->is_png) {
+        if (fresh_dev(m, dd->png.width, dd->png.height, (dd->png.out_channels - 1) << 3)) return false;
+        rc = decode_png_into(dd, m);
+    } else {
+        const int type = dd->jpeg.ncomp == 1 ? CV_8UC1 : CV_8UC3;
+        if (fresh_dev(m, dd->jpeg.width, dd->jpeg.height, type)) return false;
+        rc = decode_jpeg_into(dd, m);
+    }
     if (rc) return false;
     m->dev_valid = true;
     m->host_valid = false;
@@ -713,9 +794,8 @@ int opencv_decoder_get_jpeg_icc(void* src, size_t src_len, void* dest, size_t de
     return (int)total;
 }
 
-int opencv_decoder_get_png_icc(void*, size_t, void*, size_t) {
-    // iCCP payload is zlib-compressed; arrives with the device inflate
-    return 0;
+int opencv_decoder_get_png_icc(void* src, size_t src_len, void* dest, size_t dest_len) {
+    return png_extract_icc(static_cast<const uint8_t*>(src), src_len, static_cast<uint8_t*>(dest), dest_len);
 }
 
 int opencv_decoder_get_png_cicp(void* src, size_t src_len, uint8_t* primaries, uint8_t* transfer,

@@ -5,6 +5,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 
 namespace lp {
 
@@ -136,6 +137,51 @@ int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st);
 int jpeg_huff_parallel_slots();
 // Launches: memset(coef) -> huffman decode -> idct -> upsample+colour.
 int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_huff);
+
+// ---- png_parse.cpp (host) / png_decode.cu ------------------------------------------------------
+struct PngSegment {
+    size_t offset, length;  // an IDAT payload inside the file
+};
+struct PngHeader {
+    int width = 0, height = 0, bit_depth = 0, color_type = 0, interlace = 0;
+    int src_channels = 0, out_channels = 0, bpp = 1;
+    size_t row_bytes = 0;  // filtered scanline without the filter-type byte
+    int npal = 0, ntrns = 0;
+    bool has_trns = false;
+    uint8_t palette[256 * 3] = {0};
+    uint8_t trns[256] = {0};
+    uint16_t trns_rgb[3] = {0, 0, 0};
+    std::vector<PngSegment> idat;
+    size_t idat_total = 0;
+};
+int png_parse(const uint8_t* data, size_t len, PngHeader* out);
+int png_extract_icc(const uint8_t* data, size_t len, uint8_t* dest, size_t dest_len);
+
+// One PNG to decode (array in HBM).  zoff: the concatenated IDAT payload (one zlib stream);
+// raw: (row_bytes+1)*height bytes of filtered scanlines, defiltered in place; frame: packed output.
+struct PngDecodeItem {
+    uint64_t z_off, raw_off, frame_off;
+    uint32_t z_len;
+    int32_t width, height, bit_depth, color_type, src_channels, out_channels, bpp;
+    uint32_t row_bytes, frame_stride;
+    int32_t npal, ntrns, has_trns;
+    uint16_t trns_rgb[3];
+    uint16_t pad_;
+    uint8_t palette[256 * 3];
+    uint8_t trns[256];
+    int32_t status;  // 0 ok, <0 corrupt stream
+    uint32_t produced;
+};
+struct PngDecodeBatch {
+    PngDecodeItem* items;  // device
+    const uint8_t* z;      // device: zlib streams
+    uint8_t* raw;          // device
+    uint8_t* frames;       // device
+    int n;
+    int max_width, max_height;
+};
+// inflate -> defilter -> convert to packed Gray / BGR / BGRA u8.
+int png_decode_launch(const PngDecodeBatch& b, cudaStream_t st);
 
 // ---- jpeg_encode.cu ------------------------------------------------------------------------
 struct JpegEncodeBatch {

@@ -44,6 +44,50 @@ BLEND_CASES = [  # (src BGRA, dst BGRA) from SURVEY Appendix D + random
 ]
 
 
+PNG_NAMES = ["rgb", "rgba", "gray", "la", "pal37", "pal16", "pal2", "bit1", "gray16", "rgba16",
+             "pal_trns", "rgb_trns", "stored", "level9", "filters", "wide", "ref_enc", "ref_enc_rgba",
+             "fixture_ferry", "fixture_16bit_alpha"]
+
+
+def png_cases(ref):
+    import io
+    from PIL import Image
+    rng = np.random.default_rng(7)
+    arr = synth_image(51, 53, 37, 3, noise=10.0)[:, :, ::-1].copy()  # RGB for PIL
+
+    def enc(im, **kw):
+        bio = io.BytesIO()
+        im.save(bio, "PNG", **kw)
+        return bio.getvalue()
+    cases = {
+        "rgb": enc(Image.fromarray(arr)),
+        "rgba": enc(Image.fromarray(np.dstack([arr, arr[:, :, 0]]))),
+        "gray": enc(Image.fromarray(arr[:, :, 0])),
+        "la": enc(Image.fromarray(np.ascontiguousarray(arr[:, :, :2]), "LA")),
+        "pal37": enc(Image.fromarray(arr).quantize(37)),
+        "pal16": enc(Image.fromarray(arr).quantize(16)),
+        "pal2": enc(Image.fromarray(arr).quantize(2)),
+        "bit1": enc(Image.fromarray(arr[:, :, 0] > 128)),
+        "gray16": enc(Image.fromarray(arr[:, :, 0].astype(np.uint16) * 257 + 3)),
+        "pal_trns": enc(Image.fromarray(arr).quantize(20), transparency=3),
+        "rgb_trns": enc(Image.fromarray(arr), transparency=tuple(int(v) for v in arr[0, 0])),
+        "stored": enc(Image.fromarray(arr), compress_level=0),
+        "level9": enc(Image.fromarray(synth_image(52, 200, 120, 3, noise=2.0)), compress_level=9),
+        "wide": enc(Image.fromarray(rng.integers(0, 256, (3, 700, 4), dtype=np.uint8))),
+    }
+    import cv2
+    big = synth_image(53, 320, 200, 4, noise=4.0)
+    cases["filters"] = cv2.imencode(".png", big, [cv2.IMWRITE_PNG_COMPRESSION, 6])[1].tobytes()
+    r16 = (synth_image(54, 40, 30, 4, noise=10.0).astype(np.uint16) << 8) | 0x5A
+    cases["rgba16"] = cv2.imencode(".png", r16)[1].tobytes()
+    cases["ref_enc"] = ref.encode(".png", synth_image(55, 97, 61, 3), {abi.PngCompression: 7})
+    cases["ref_enc_rgba"] = ref.encode(".png", synth_image(56, 64, 64, 4), {abi.PngCompression: 1})
+    cases["fixture_ferry"] = open("/root/reference/testdata/ferry_sunset.png", "rb").read()
+    cases["fixture_16bit_alpha"] = open("/root/reference/data/firefox-16bit-alpha.png", "rb").read()
+    assert sorted(cases) == sorted(PNG_NAMES)
+    return [(k, cases[k]) for k in PNG_NAMES]
+
+
 def main():
     ref = abi.load_reference()
     out = {}
@@ -88,6 +132,10 @@ def main():
     out["c6_input"] = np.frombuffer(c6, dtype=np.uint8)
     out["c6_output"] = np.frombuffer(ref.transform(c6, opt6), dtype=np.uint8)
     out["c6_decoded"] = ref.decode(c6)
+    # PNG decode (lossless): files made by PIL / the reference encoder, decoded by the reference
+    for name, data in png_cases(ref):
+        out[f"png_{name}"] = np.frombuffer(data, dtype=np.uint8)
+        out[f"pngdec_{name}"] = ref.decode(data)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden.npz"), **out)
     print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(ROOT, "tests/golden/golden.npz")), "bytes")
 

@@ -1,0 +1,61 @@
+"""GPU: PNG decode (device inflate + defilter + convert) through the C ABI vs the reference-made
+golden vectors and the oracle.  Lossless path: bit-exact."""
+import io
+
+import numpy as np
+import pytest
+
+from lilliput_b200 import abi
+from lilliput_b200.synth import synth_image
+from tests.cases import PNG_NAMES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", PNG_NAMES)
+def test_png_decode_matches_reference_golden(cuda_lib, golden, name):
+    data = golden[f"png_{name}"].tobytes()
+    exp = golden[f"pngdec_{name}"]
+    w, h, t, o = cuda_lib.header(data)
+    assert (h, w) == exp.shape[:2] and o == 1
+    assert ((t >> 3) & 63) + 1 == (1 if exp.ndim == 2 else exp.shape[2])
+    assert np.array_equal(cuda_lib.decode(data), exp)
+
+
+def test_png_random_sizes_vs_oracle(cuda_lib, oracle):
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    for i in range(12):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+        ch = int(rng.choice([1, 3, 4]))
+        img = synth_image(700 + i, w, h, ch, noise=float(rng.choice([0.0, 3.0, 20.0])))
+        mode_img = Image.fromarray(img if ch != 3 else img[:, :, ::-1].copy()) if ch != 4 else \
+            Image.fromarray(img[:, :, [2, 1, 0, 3]].copy())
+        bio = io.BytesIO()
+        mode_img.save(bio, "PNG", compress_level=int(rng.integers(0, 10)))
+        data = bio.getvalue()
+        assert np.array_equal(cuda_lib.decode(data), oracle.png_decode(data)), (w, h, ch)
+
+
+def test_png_to_jpeg_transform(cuda_lib, golden, oracle):
+    """PNG -> Fit -> JPEG through lp_transform (the PNG share of BASELINE config 5)."""
+    data = golden["png_fixture_ferry"].tobytes()
+    opt = abi.ImageOptions(FileType=".jpeg", Width=256, Height=256, ResizeMethod=abi.ImageOpsFit,
+                           NormalizeOrientation=True, EncodeOptions={abi.JpegQuality: 85})
+    out = cuda_lib.transform(data, opt)
+    dec = oracle.png_decode(data)
+    assert out == oracle.jpeg_encode(oracle.fit(dec, 256, 256), 85)
+    # RGBA source: alpha is dropped by the JPEG encoder
+    data = golden["png_filters"].tobytes()
+    out = cuda_lib.transform(data, abi.ImageOptions(FileType=".jpeg", Width=100, Height=60,
+                                                    ResizeMethod=abi.ImageOpsResize,
+                                                    EncodeOptions={abi.JpegQuality: 90}))
+    dec = oracle.png_decode(data)
+    assert out == oracle.jpeg_encode(oracle.resize(dec, 100, 60), 90)
+
+
+def test_png_errors(cuda_lib, golden):
+    data = golden["png_rgb"].tobytes()
+    with pytest.raises(abi.LilliputError) as e:
+        cuda_lib.decode(data[: len(data) // 2] + b"\x00" * 40)  # truncated IDAT
+    assert e.value.code == -2  # ErrDecodingFailed

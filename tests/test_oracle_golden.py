@@ -110,3 +110,14 @@ def test_oracle_against_live_reference(oracle, ref_lib):
         enc = ref_lib.encode(".jpeg", img, {abi.JpegQuality: q})
         assert oracle.jpeg_encode(img, q) == enc
         assert np.array_equal(oracle.jpeg_decode(enc)[0], ref_lib.decode(enc))
+
+
+from tests.cases import PNG_NAMES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", PNG_NAMES)
+def test_png_decode_matches_golden(oracle, golden, name):
+    """PNG decode is lossless: every colour type / bit depth / filter / block type the fixtures
+    cover must equal what the reference decoded (Gray, BGR or BGRA u8; 16-bit -> high byte)."""
+    got = oracle.png_decode(golden[f"png_{name}"].tobytes())
+    assert np.array_equal(got, golden[f"pngdec_{name}"])

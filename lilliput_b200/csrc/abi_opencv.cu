@@ -690,6 +690,33 @@ bool opencv_encoder_write(opencv_encoder e, const opencv_mat src, const int* opt
     Encoder* enc = static_cast<Encoder*>(e);
     Mat* s = static_cast<Mat*>(src);
     if (!enc || !s) return false;
+    if (enc->ext == ".png") {
+        // OpenCV: IMWRITE_PNG_COMPRESSION given -> that zlib level with libpng's adaptive filters;
+        // absent -> Z_BEST_SPEED + FILTER_SUB (grfmt_png.cpp)
+        int level = 1;
+        bool adaptive = false;
+        for (size_t i = 0; i + 1 < opt_len; i += 2)
+            if (opt[i] == CV_IMWRITE_PNG_COMPRESSION) {
+                level = std::min(std::max(opt[i + 1], 0), 9);
+                adaptive = true;
+            }
+        if (ensure_dev(s)) return false;
+        std::vector<uint8_t> file;
+        if (png_encode_frame(s->dptr(), s->dev_step, s->cols, s->rows, s->channels(), level, adaptive, &file,
+                             thread_stream()) != LP_OK)
+            return false;
+        Mat* d = enc->dst;
+        if (file.size() > d->host_cap) {  // overflow: data moves off the caller's buffer (opencv.go:890-895)
+            d->owned_host.resize(file.size());
+            d->host = d->owned_host.data();
+            d->host_cap = file.size();
+        }
+        memcpy(d->host, file.data(), file.size());
+        d->rows = (int)file.size();
+        d->cols = 1;
+        d->host_valid = true;
+        return true;
+    }
     if (enc->ext != ".jpeg" && enc->ext != ".jpg" && enc->ext != ".jpe") {
         fprintf(stderr, "[lilliput_b200] encoder for '%s' is not implemented on the device path yet\n",
                 enc->ext.c_str());

@@ -183,6 +183,11 @@ struct PngDecodeBatch {
 // inflate -> defilter -> convert to packed Gray / BGR / BGRA u8.
 int png_decode_launch(const PngDecodeBatch& b, cudaStream_t st);
 
+// ---- png_encode.cu ---------------------------------------------------------------------------
+// One packed device frame -> a complete PNG file in host memory (filter + deflate on the device).
+int png_encode_frame(const uint8_t* frame, size_t row_stride, int width, int height, int channels, int level,
+                     bool adaptive_filters, std::vector<uint8_t>* out, cudaStream_t st);
+
 // ---- jpeg_encode.cu ------------------------------------------------------------------------
 struct JpegEncodeBatch {
     const uint8_t* frames;  // device packed frames

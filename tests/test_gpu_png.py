@@ -59,3 +59,41 @@ def test_png_errors(cuda_lib, golden):
     with pytest.raises(abi.LilliputError) as e:
         cuda_lib.decode(data[: len(data) // 2] + b"\x00" * 40)  # truncated IDAT
     assert e.value.code == -2  # ErrDecodingFailed
+
+
+@pytest.mark.parametrize("case", [(97, 61, 3, 7), (64, 64, 4, 1), (256, 256, 3, 7), (33, 17, 1, 6),
+                                  (500, 300, 4, 9), (40, 30, 3, 0), (1, 1, 3, 7), (640, 360, 3, None)])
+def test_png_encode_decodes_to_identical_pixels(cuda_lib, oracle, ref_lib, case):
+    """PNG output contract = decoded-pixel equality + IHDR policy (colour type 0/2/6, 8-bit), not
+    byte-identical files.  The file must decode with an independent decoder (oracle, PIL) to the
+    exact input pixels and stay within 1.6x of the reference encoder's size."""
+    import io
+    from PIL import Image
+    w, h, ch, level = case
+    img = synth_image(800 + w, w, h, ch, noise=4.0)
+    opts = {} if level is None else {abi.PngCompression: level}
+    data = cuda_lib.encode(".png", img, opts)
+    assert data[:8] == b"\x89PNG\r\n\x1a\n" and data[12:16] == b"IHDR"
+    assert int.from_bytes(data[16:20], "big") == w and int.from_bytes(data[20:24], "big") == h
+    assert data[24] == 8 and data[25] == {1: 0, 3: 2, 4: 6}[ch] and data[28] == 0   # depth, type, no interlace
+    assert np.array_equal(oracle.png_decode(data), img)
+    pil = np.array(Image.open(io.BytesIO(data)))
+    exp = img if ch == 1 else (img[:, :, ::-1] if ch == 3 else img[:, :, [2, 1, 0, 3]])
+    assert np.array_equal(pil, exp)
+    assert np.array_equal(cuda_lib.decode(data), img)   # and through the device decoder
+    ref_size = len(ref_lib.encode(".png", img, opts))
+    if level != 0 and w * h > 4096:
+        assert len(data) <= 1.6 * ref_size + 256, (len(data), ref_size)
+
+
+def test_png_to_png_transform(cuda_lib, oracle, golden):
+    """PNG -> Fit -> PNG (lossless path): decoded output == oracle fit of the decoded input."""
+    data = golden["png_filters"].tobytes()   # 320x200 BGRA
+    opt = abi.ImageOptions(FileType=".png", Width=64, Height=64, ResizeMethod=abi.ImageOpsFit,
+                           EncodeOptions={abi.PngCompression: 7})
+    out = cuda_lib.transform(data, opt)
+    exp = oracle.fit(oracle.png_decode(data), 64, 64)
+    assert np.array_equal(oracle.png_decode(out), exp)
+    with pytest.raises(abi.LilliputError) as e:   # too-small destination -> ErrBufTooSmall
+        cuda_lib.transform(data, opt, dst_cap=64)
+    assert e.value.code == -3

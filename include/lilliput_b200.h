@@ -97,6 +97,19 @@ int lp_encode_host(const char* ext, const uint8_t* pixels, int width, int height
 int lp_orient_host(const uint8_t* src, int width, int height, int type, int orientation,
                    uint8_t* dst, int* out_w, int* out_h);
 
+/* GIF: animation metadata as gifDecoder reports it (ref giflib.go:76-151). */
+typedef struct lp_gif_info {
+    int width, height, frame_count, loop_count, duration_ms;
+    unsigned int background_color; /* gifDecoder.BackgroundColor(): A<<24 | R<<16 | G<<8 | B */
+} lp_gif_info;
+int lp_gif_get_info(const uint8_t* in, size_t in_len, lp_gif_info* info);
+/* Decode up to max_frames frames through gifDecoder.DecodeTo (ref giflib.go:180-219): every frame
+ * is the FULL canvas, BGRA u8, written back to back into `frames`.  delays_ms / disposals (lilliput
+ * DisposeMethod values) get one entry per frame.  *n_frames = frames decoded; returns LP_OK when the
+ * stream ended with EOF, else the error that stopped it (frames decoded so far are still valid). */
+int lp_gif_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
+                              int max_frames, int* n_frames, int* delays_ms, int* disposals);
+
 #ifndef LP_REFERENCE_BACKEND
 /* ------------------------- CUDA-only entry points -------------------------- */
 

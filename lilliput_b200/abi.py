@@ -207,6 +207,35 @@ class Lib:
             raise LilliputError(rc)
         return dst[: n.value].tobytes()
 
+    # --- GIF (ref giflib.go) -------------------------------------------------------------
+    def gif_info(self, data: bytes) -> dict:
+        class _Info(C.Structure):
+            _fields_ = [("width", C.c_int), ("height", C.c_int), ("frame_count", C.c_int),
+                        ("loop_count", C.c_int), ("duration_ms", C.c_int), ("background_color", C.c_uint)]
+        src = np.frombuffer(data, dtype=np.uint8)
+        info = _Info()
+        self.l.lp_gif_get_info.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        rc = self.l.lp_gif_get_info(src.ctypes.data, src.size, C.byref(info))
+        if rc != 0:
+            raise LilliputError(rc)
+        return {k: getattr(info, k) for k, _ in _Info._fields_}
+
+    def gif_frames(self, data: bytes, max_frames: int = 1 << 16):
+        """gifDecoder.DecodeTo until EOF: (frames[n,h,w,4] BGRA full canvas, delays_ms, disposals, rc)."""
+        info = self.gif_info(data)
+        n = max(1, min(max_frames, info["frame_count"] + 1))
+        src = np.frombuffer(data, dtype=np.uint8)
+        frames = np.zeros((n, info["height"], info["width"], 4), dtype=np.uint8)
+        delays = (C.c_int * n)()
+        disp = (C.c_int * n)()
+        got = C.c_int(0)
+        self.l.lp_gif_decode_frames_host.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int,
+                                                     C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        rc = self.l.lp_gif_decode_frames_host(src.ctypes.data, src.size, frames.ctypes.data, frames.nbytes,
+                                              n, C.byref(got), delays, disp)
+        k = got.value
+        return frames[:k], list(delays[:k]), list(disp[:k]), rc
+
     def orient(self, img: np.ndarray, orientation: int) -> np.ndarray:
         """Framebuffer.OrientationTransform (ref opencv.go:271)."""
         img = np.ascontiguousarray(img, dtype=np.uint8)

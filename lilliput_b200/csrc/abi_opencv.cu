@@ -311,6 +311,28 @@ static int decode_png_into(const Decoder* d, Mat* m) {
     return back.status == 0 ? LP_OK : LP_ERR_DECODING_FAILED;
 }
 
+// Accessors for the other adapters (gif_decode.cu), which do not see the Mat layout.
+const uint8_t* mat_host_bytes(const void* mat, size_t* len) {
+    const Mat* m = static_cast<const Mat*>(mat);
+    if (!m || !m->host) return nullptr;
+    *len = (size_t)m->cols * m->rows * m->elem();
+    return m->host;
+}
+int mat_bind_device_frame(void* mat, int cols, int rows, int type, uint8_t** dev, size_t* step) {
+    Mat* m = static_cast<Mat*>(mat);
+    if (!m) return LP_ERR_BAD_ARGUMENT;
+    int rc = fresh_dev(m, cols, rows, type);
+    if (rc) return rc;
+    *dev = m->dptr();
+    *step = m->dev_step;
+    return LP_OK;
+}
+void mat_mark_device_written(void* mat) {
+    Mat* m = static_cast<Mat*>(mat);
+    m->dev_valid = true;
+    m->host_valid = false;
+}
+
 }  // namespace lp
 
 using namespace lp;

@@ -1,0 +1,588 @@
+// gif_decode.cu -- lilliput's GIF decoder surface (include/lp_giflib.h = ref giflib.hpp:33-52) on
+// sm_100a: host container walk, device LZW decode, device full-canvas compositor.
+//
+// Replaces: giflib_decoder_* (ref giflib.cpp:104-347, 570-724, 1308-1431): giflib 5.2.2's
+// DGifGetRecordType / DGifGetExtension / DGifGetImageHeader / DGifGetLine plus the reference's own
+// compositor (ref giflib.cpp:349-568): background fill on the first frame, dispose-to-background /
+// restore-previous of the previous frame's clipped rectangle, snapshot, then non-transparent,
+// in-palette pixels drawn with A=255, frames that hang off the canvas clipped.  Output is the
+// full-canvas BGRA frame lilliput's ops.go expects.  Lossless: bit-exact to the reference
+// (tests/test_gpu_gif.py against reference-made golden frames).
+//
+// LZW on a GPU: a GIF code stream is serial, so the unit of parallelism is the frame (one warp).
+// Every dictionary entry is kept as (offset, length) INTO THE OUTPUT already written -- an LZ78 string
+// is always "the previous string plus one more pixel", i.e. a span of the output -- so emitting a
+// code is a warp-wide copy instead of a pointer chase.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "lp_giflib.h"
+
+namespace lp {
+
+// ------------------------------------------------------------------ container walk (host)
+
+struct GifGcb {
+    int disposal = 0, delay = 0, transparent = -1;
+    bool user_input = false;
+};
+
+struct GifImage {
+    int left = 0, top = 0, width = 0, height = 0;
+    bool interlace = false;
+    int ncolors = 0;          // local colour table entries (0 = none)
+    const uint8_t* colors = nullptr;
+    int min_code = 0;
+};
+
+// Sequential reader over the borrowed bytes, with giflib's record semantics.
+struct GifReader {
+    const uint8_t* p = nullptr;
+    size_t n = 0, pos = 0;
+    int sw = 0, sh = 0, bg_index = 0, gct_colors = 0;
+    const uint8_t* gct = nullptr;
+
+    bool get(uint8_t* b) {
+        if (pos >= n) return false;
+        *b = p[pos++];
+        return true;
+    }
+    bool open() {  // DGifOpen: signature, logical screen descriptor, global colour table
+        if (n < 13 || (memcmp(p, "GIF87a", 6) && memcmp(p, "GIF89a", 6))) return false;
+        sw = p[6] | (p[7] << 8);
+        sh = p[8] | (p[9] << 8);
+        const uint8_t packed = p[10];
+        bg_index = p[11];
+        pos = 13;
+        if (packed & 0x80) {
+            gct_colors = 1 << ((packed & 7) + 1);
+            if (pos + (size_t)gct_colors * 3 > n) return false;
+            gct = p + pos;
+            pos += (size_t)gct_colors * 3;
+        }
+        return true;
+    }
+    // 0 = image descriptor, 1 = extension, 2 = terminator, -1 = error (incl. read past the end)
+    int record() {
+        uint8_t b;
+        if (!get(&b)) return -1;
+        return b == 0x2C ? 0 : b == 0x21 ? 1 : b == 0x3B ? 2 : -1;
+    }
+    // one data sub-block: *len = 0 at the terminator
+    bool sub_block(const uint8_t** data, int* len) {
+        uint8_t b;
+        if (!get(&b)) return false;
+        *len = b;
+        *data = p + pos;
+        if (pos + b > n) return false;
+        pos += b;
+        return true;
+    }
+    bool image_header(GifImage* im) {  // DGifGetImageHeader (+ the LZW minimum code size byte)
+        if (pos + 9 > n) return false;
+        im->left = p[pos] | (p[pos + 1] << 8);
+        im->top = p[pos + 2] | (p[pos + 3] << 8);
+        im->width = p[pos + 4] | (p[pos + 5] << 8);
+        im->height = p[pos + 6] | (p[pos + 7] << 8);
+        const uint8_t packed = p[pos + 8];
+        pos += 9;
+        im->interlace = (packed & 0x40) != 0;
+        im->ncolors = 0;
+        im->colors = nullptr;
+        if (packed & 0x80) {
+            im->ncolors = 1 << ((packed & 7) + 1);
+            if (pos + (size_t)im->ncolors * 3 > n) return false;
+            im->colors = p + pos;
+            pos += (size_t)im->ncolors * 3;
+        }
+        uint8_t cs;
+        if (!get(&cs)) return false;
+        if (cs > 8) return false;  // giflib: D_GIF_ERR_READ_FAILED
+        im->min_code = cs;
+        return true;
+    }
+};
+
+// DGifExtensionToGCB: only a 4-byte block is a valid graphic control block.
+static bool gcb_from_block(const uint8_t* b, int len, GifGcb* g) {
+    if (len != 4) return false;
+    g->disposal = (b[0] >> 2) & 7;
+    g->user_input = (b[0] >> 1) & 1;
+    g->delay = b[1] | (b[2] << 8);
+    g->transparent = (b[0] & 1) ? b[3] : -1;
+    return true;
+}
+
+// ref giflib.cpp:595-636
+static void background_color(const GifReader& r, const GifGcb& g, uint8_t* R, uint8_t* G, uint8_t* B, uint8_t* A) {
+    const bool valid = r.gct && r.bg_index >= 0 && r.bg_index < r.gct_colors;
+    if (valid) {
+        *R = r.gct[r.bg_index * 3];
+        *G = r.gct[r.bg_index * 3 + 1];
+        *B = r.gct[r.bg_index * 3 + 2];
+    } else {
+        *R = *G = *B = 255;
+    }
+    *A = g.transparent != -1 ? 0 : 255;
+}
+
+// ------------------------------------------------------------------ device kernels
+
+struct GifFrameDev {
+    const uint8_t* lzw;   // concatenated sub-block payload
+    uint32_t lzw_len;
+    int min_code;
+    uint32_t npix;
+    uint8_t* indices;     // npix bytes
+    int* status;          // 0 ok, -1 short / corrupt stream
+};
+
+struct LzwBits {
+    const uint8_t* p;
+    const uint8_t* end;
+    uint64_t acc;
+    int cnt;
+    __device__ __forceinline__ int get(int n) {
+        while (cnt < n) {
+            if (p >= end) return -1;
+            acc |= (uint64_t)(*p++) << cnt;
+            cnt += 8;
+        }
+        const int v = (int)(acc & ((1u << n) - 1));
+        acc >>= n;
+        cnt -= n;
+        return v;
+    }
+};
+
+__global__ void __launch_bounds__(32) gif_lzw_kernel(GifFrameDev f) {
+    __shared__ uint32_t t_off[4096];
+    __shared__ uint16_t t_len[4096];
+    const int lane = threadIdx.x;
+    // giflib's DGifDecompressInput/Line state machine: `running` counts codes read since the last
+    // clear (+ clear + 2); the code width grows when it passes maxcode1; a code creates entry
+    // running - 2 from the previous string.
+    const int clear = 1 << f.min_code, eof = clear + 1;
+    int bits = f.min_code + 1, maxcode1 = 1 << bits, running = clear + 2, top = clear + 2;
+    LzwBits b{f.lzw, f.lzw + f.lzw_len, 0, 0};
+    uint32_t o = 0;
+    uint32_t prev_off = 0;
+    int prev_len = 0;  // 0 = no previous string since the last clear
+    int status = 0;
+    while (o < f.npix) {
+        // lane 0 reads the next code and resolves it to a span of the output (or a literal)
+        uint32_t src = 0;
+        int len = 0, lit = -1, cmd = 0;  // cmd: 0 emit, 1 clear, 3 error
+        if (lane == 0) {
+            const int code = b.get(bits);
+            if (code >= 0 && running < 4097 && ++running > maxcode1 && bits < 12) {
+                maxcode1 <<= 1;
+                bits++;
+            }
+            if (code < 0) cmd = 3;                 // data ran out before the frame was complete
+            else if (code == eof) cmd = 3;         // giflib: EOF code before the last pixel is an error
+            else if (code == clear) cmd = 1;
+            else {
+                const int create = running - 2;    // entry this code will add (if there is a previous string)
+                if (code < clear) { lit = code; len = 1; }
+                else if (code > eof && code < top) { src = t_off[code]; len = t_len[code]; }
+                else if (prev_len && code == create && code == top) { src = prev_off; len = prev_len + 1; }  // KwKwK
+                else cmd = 3;
+                if (!cmd) {
+                    if (prev_len && create < 4096 && create == top) {
+                        t_off[create] = prev_off;
+                        t_len[create] = (uint16_t)min(prev_len + 1, 65535);
+                        top++;
+                    }
+                    prev_off = o;
+                    prev_len = len;
+                }
+            }
+            if (cmd == 1) {
+                bits = f.min_code + 1;
+                maxcode1 = 1 << bits;
+                running = clear + 2;
+                top = clear + 2;
+                prev_len = 0;
+            }
+        }
+        cmd = __shfl_sync(0xffffffffu, cmd, 0);
+        if (cmd == 1) continue;
+        if (cmd >= 2) { status = -1; break; }
+        len = __shfl_sync(0xffffffffu, len, 0);
+        src = __shfl_sync(0xffffffffu, src, 0);
+        lit = __shfl_sync(0xffffffffu, lit, 0);
+        const uint32_t take = min((uint32_t)len, f.npix - o);
+        if (lit >= 0) {
+            if (lane == 0) f.indices[o] = (uint8_t)lit;
+        } else {
+            // bytes src.. were written before o, except the KwKwK tail byte which equals byte src
+            for (uint32_t i = lane; i < take; i += 32) f.indices[o + i] = f.indices[src + i < o ? src + i : src];
+        }
+        __syncwarp();
+        o += take;
+    }
+    if (lane == 0) *f.status = status;
+}
+
+struct GifCompose {
+    uint8_t* canvas;        // BGRA, cw x ch, packed
+    uint8_t* prev;          // BGRA snapshot buffer (same size)
+    const uint8_t* indices;
+    int cw, ch;
+    int first;              // first frame: fill background
+    int prev_disposal;      // giflib DisposalMode of the previous frame (2 = background, 3 = previous)
+    int pl, pt, pw, ph;     // previous frame rectangle, already clipped to the canvas
+    int fl, ft, fw, fh;     // this frame's rectangle as declared (may hang off the canvas)
+    int interlace;
+    int transparent, ncolors;
+    uchar4 bg;              // B, G, R, A
+    uint8_t palette[256 * 3];
+};
+
+__global__ void gif_compose_kernel(const GifCompose c) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= c.cw || y >= c.ch) return;
+    const size_t at = ((size_t)y * c.cw + x) * 4;
+    uchar4 px = *reinterpret_cast<uchar4*>(c.canvas + at);
+    if (c.first) {
+        px = c.bg;
+    } else {
+        const bool in_prev = x >= c.pl && x < c.pl + c.pw && y >= c.pt && y < c.pt + c.ph;
+        if (in_prev && c.prev_disposal == 2) px = c.bg;
+        else if (in_prev && c.prev_disposal == 3) px = *reinterpret_cast<const uchar4*>(c.prev + at);
+        *reinterpret_cast<uchar4*>(c.prev + at) = px;  // snapshot after disposal, before drawing
+    }
+    const int fx = x - c.fl, fy = y - c.ft;
+    if (fx >= 0 && fx < c.fw && fy >= 0 && fy < c.fh) {
+        int row = fy;
+        if (c.interlace) {  // position of image row fy in the 4-pass raster order
+            const int h = c.fh;
+            const int n0 = (h + 7) / 8, n1 = (h + 3) / 8, n2 = (h + 1) / 4;
+            if ((fy & 7) == 0) row = fy / 8;
+            else if ((fy & 7) == 4) row = n0 + fy / 8;
+            else if ((fy & 3) == 2) row = n0 + n1 + fy / 4;
+            else row = n0 + n1 + n2 + fy / 2;
+        }
+        const int idx = c.indices[(size_t)row * c.fw + fx];
+        if (idx != c.transparent && idx < c.ncolors)
+            px = make_uchar4(c.palette[idx * 3 + 2], c.palette[idx * 3 + 1], c.palette[idx * 3], 255);
+    }
+    *reinterpret_cast<uchar4*>(c.canvas + at) = px;
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+// The mat handle is defined in abi_opencv.cu; the decoder only needs these few accessors.
+namespace lp {
+const uint8_t* mat_host_bytes(const void* mat, size_t* len);
+int mat_bind_device_frame(void* mat, int cols, int rows, int type, uint8_t** dev, size_t* step);
+void mat_mark_device_written(void* mat);
+}  // namespace lp
+
+struct giflib_decoder_struct {
+    GifReader rd;
+    GifImage image;                    // gif->Image
+    std::vector<GifGcb> pending_gcbs;  // graphic control blocks seen since the last frame
+    bool seek_clear_extensions = false;
+    bool have_read_first_frame = false;
+    int prev_disposal = 0, prev_delay = 0, prev_left = 0, prev_top = 0, prev_width = 0, prev_height = 0;
+    uint8_t bg_r = 255, bg_g = 255, bg_b = 255, bg_a = 255;
+    int image_count = 0;
+    // device state owned by the decoder: the canvas persists between frames here (the reference
+    // relies on the Go framebuffer keeping its bytes), plus the restore-previous snapshot
+    uint8_t* d_canvas = nullptr;
+    uint8_t* d_prev = nullptr;
+    uint8_t* d_indices = nullptr;
+    uint8_t* d_lzw = nullptr;
+    int* d_status = nullptr;
+    size_t indices_cap = 0, lzw_cap = 0;
+};
+
+struct giflib_encoder_struct {
+    int unused;
+};
+
+extern "C" {
+
+giflib_decoder giflib_decoder_create(const opencv_mat buf) {
+    if (!buf) return nullptr;
+    size_t len = 0;
+    const uint8_t* bytes = mat_host_bytes(buf, &len);
+    if (!bytes) return nullptr;
+    auto* d = new giflib_decoder_struct;
+    d->rd.p = bytes;
+    d->rd.n = len;
+    if (!d->rd.open() || d->rd.sw <= 0 || d->rd.sh <= 0) {
+        delete d;
+        return nullptr;
+    }
+    return d;
+}
+
+int giflib_decoder_get_width(const giflib_decoder d) { return d->rd.sw; }
+int giflib_decoder_get_height(const giflib_decoder d) { return d->rd.sh; }
+int giflib_decoder_get_num_frames(const giflib_decoder d) { return d->image_count; }
+int giflib_decoder_get_frame_width(const giflib_decoder d) { return d->image.width; }
+int giflib_decoder_get_frame_height(const giflib_decoder d) { return d->image.height; }
+int giflib_decoder_get_prev_frame_delay(const giflib_decoder d) { return d->prev_delay; }
+
+int giflib_decoder_get_prev_frame_disposal(const giflib_decoder d) {  // ref giflib.cpp:187-199
+    switch (d->prev_disposal) {
+        case 2: return GIF_DISPOSE_BACKGROUND;
+        case 3: return GIF_DISPOSE_PREVIOUS;
+        default: return GIF_DISPOSE_NONE;
+    }
+}
+
+void giflib_decoder_release(giflib_decoder d) {
+    if (!d) return;
+    cudaStream_t st = thread_stream();
+    if (d->d_canvas) cudaFreeAsync(d->d_canvas, st);
+    if (d->d_prev) cudaFreeAsync(d->d_prev, st);
+    if (d->d_indices) cudaFreeAsync(d->d_indices, st);
+    if (d->d_lzw) cudaFreeAsync(d->d_lzw, st);
+    if (d->d_status) cudaFreeAsync(d->d_status, st);
+    delete d;
+}
+
+// ref giflib.cpp:209-246: every extension's sub-blocks are walked; graphic control blocks are kept
+static bool read_extension(giflib_decoder d) {
+    uint8_t label;
+    if (!d->rd.get(&label)) return false;
+    const uint8_t* data;
+    int len;
+    if (!d->rd.sub_block(&data, &len)) return false;
+    bool first = true;
+    while (len != 0) {
+        if (first && label == 0xF9) {
+            GifGcb g;
+            if (gcb_from_block(data, len, &g)) d->pending_gcbs.push_back(g);
+            else d->pending_gcbs.push_back(GifGcb());  // a malformed block still resets to defaults
+        }
+        first = false;
+        if (!d->rd.sub_block(&data, &len)) return false;
+    }
+    return true;
+}
+
+// ref giflib.cpp:289-326
+static giflib_decoder_frame_state seek_next_frame(giflib_decoder d) {
+    if (d->seek_clear_extensions) {
+        d->pending_gcbs.clear();
+        d->seek_clear_extensions = false;
+    }
+    for (;;) {
+        const int rec = d->rd.record();
+        if (rec < 0) return giflib_decoder_error;
+        if (rec == 0) return giflib_decoder_have_next_frame;
+        if (rec == 1) {
+            if (!read_extension(d)) return giflib_decoder_error;
+        } else {
+            return giflib_decoder_eof;
+        }
+    }
+}
+
+giflib_decoder_frame_state giflib_decoder_decode_frame_header(giflib_decoder d) {  // ref giflib.cpp:331-347
+    const giflib_decoder_frame_state s = seek_next_frame(d);
+    if (s != giflib_decoder_have_next_frame) return s;
+    if (!d->rd.image_header(&d->image)) return giflib_decoder_error;
+    return giflib_decoder_have_next_frame;
+}
+
+giflib_decoder_frame_state giflib_decoder_skip_frame(giflib_decoder d) {  // ref giflib.cpp:570-590
+    const giflib_decoder_frame_state s = giflib_decoder_decode_frame_header(d);
+    if (s != giflib_decoder_have_next_frame) return s;
+    const uint8_t* data;
+    int len;
+    do {
+        if (!d->rd.sub_block(&data, &len)) return giflib_decoder_error;
+    } while (len != 0);
+    return giflib_decoder_have_next_frame;
+}
+
+bool giflib_decoder_decode_frame(giflib_decoder d, opencv_mat mat) {  // ref giflib.cpp:640-724 + 349-568
+    const GifImage& im = d->image;
+    if (im.width <= 0 || im.height <= 0) return false;
+    if (ensure_device()) return false;
+    cudaStream_t st = thread_stream();
+    // gather the LZW sub-blocks (giflib reads them through DGifGetLine)
+    std::vector<uint8_t> lzw;
+    {
+        const uint8_t* data;
+        int len;
+        for (;;) {
+            if (!d->rd.sub_block(&data, &len)) return false;
+            if (len == 0) break;
+            lzw.insert(lzw.end(), data, data + len);
+        }
+    }
+    GifGcb gcb;  // ref giflib.cpp:248-270: defaults, then the last graphic control block seen
+    if (!d->pending_gcbs.empty()) gcb = d->pending_gcbs.back();
+    if (!d->have_read_first_frame) background_color(d->rd, gcb, &d->bg_r, &d->bg_g, &d->bg_b, &d->bg_a);
+    const uint8_t* colors = im.colors ? im.colors : d->rd.gct;
+    const int ncolors = im.colors ? im.ncolors : d->rd.gct_colors;
+    if (!colors) {
+        fprintf(stderr, "encountered error, gif frame has no color map\n");
+        return false;
+    }
+    // the frame mat is the full canvas, BGRA
+    uint8_t* frame_dev = nullptr;
+    size_t frame_step = 0;
+    const int cw = d->rd.sw, chh = d->rd.sh;
+    if (mat_bind_device_frame(mat, cw, chh, CV_8UC4, &frame_dev, &frame_step)) return false;
+    const size_t canvas_bytes = (size_t)cw * chh * 4;
+    const size_t npix = (size_t)im.width * im.height;
+    if (!d->d_canvas) {
+        if (cudaMallocAsync(&d->d_canvas, canvas_bytes, st) != cudaSuccess) return false;
+        if (cudaMallocAsync(&d->d_prev, canvas_bytes, st) != cudaSuccess) return false;
+        if (cudaMallocAsync(&d->d_status, sizeof(int), st) != cudaSuccess) return false;
+        cudaMemsetAsync(d->d_prev, 0, canvas_bytes, st);  // the reference's prev_frame_bgra starts zeroed
+        cudaMemsetAsync(d->d_canvas, 0, canvas_bytes, st);
+    }
+    if (npix > d->indices_cap) {
+        if (d->d_indices) cudaFreeAsync(d->d_indices, st);
+        if (cudaMallocAsync(&d->d_indices, npix + 64, st) != cudaSuccess) return false;
+        d->indices_cap = npix;
+    }
+    if (lzw.size() + 16 > d->lzw_cap) {
+        if (d->d_lzw) cudaFreeAsync(d->d_lzw, st);
+        d->lzw_cap = lzw.size() * 2 + 4096;
+        if (cudaMallocAsync(&d->d_lzw, d->lzw_cap, st) != cudaSuccess) return false;
+    }
+    if (!lzw.empty()) cudaMemcpyAsync(d->d_lzw, lzw.data(), lzw.size(), cudaMemcpyHostToDevice, st);
+    GifFrameDev f{d->d_lzw, (uint32_t)lzw.size(), im.min_code, (uint32_t)npix, d->d_indices, d->d_status};
+    gif_lzw_kernel<<<1, 32, 0, st>>>(f);
+    g_launches++;
+    GifCompose c;
+    c.canvas = d->d_canvas;
+    c.prev = d->d_prev;
+    c.indices = d->d_indices;
+    c.cw = cw;
+    c.ch = chh;
+    c.first = d->have_read_first_frame ? 0 : 1;
+    c.prev_disposal = d->prev_disposal;
+    // previous rectangle clipped exactly as ref giflib.cpp:407-436 does
+    int pl = d->prev_left, pt = d->prev_top, pw = d->prev_width, ph = d->prev_height;
+    if (pl < 0) { pw += pl; pl = 0; }
+    if (pt < 0) { ph += pt; pt = 0; }
+    if (pl + pw > cw) pw = cw - pl;
+    if (pt + ph > chh) ph = chh - pt;
+    c.pl = pl; c.pt = pt; c.pw = pw < 0 ? 0 : pw; c.ph = ph < 0 ? 0 : ph;
+    c.fl = im.left; c.ft = im.top; c.fw = im.width; c.fh = im.height;
+    c.interlace = im.interlace;
+    c.transparent = gcb.transparent;
+    c.ncolors = ncolors;
+    c.bg = make_uchar4(d->bg_b, d->bg_g, d->bg_r, d->bg_a);
+    memset(c.palette, 0, sizeof(c.palette));
+    memcpy(c.palette, colors, (size_t)std::min(ncolors, 256) * 3);
+    dim3 grid(ceil_div(cw, 128), chh);
+    gif_compose_kernel<<<grid, 128, 0, st>>>(c);
+    g_launches++;
+    int status = 0;
+    cudaMemcpyAsync(&status, d->d_status, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaMemcpy2DAsync(frame_dev, frame_step, d->d_canvas, (size_t)cw * 4, (size_t)cw * 4, chh,
+                      cudaMemcpyDeviceToDevice, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return false;  // `lzw` and `c` stay alive until here
+    if (status != 0) {
+        fprintf(stderr, "encountered error, could not rasterize gif\n");
+        return false;
+    }
+    mat_mark_device_written(mat);
+    d->prev_disposal = gcb.disposal;
+    d->prev_delay = gcb.delay;
+    d->prev_left = im.left;
+    d->prev_top = im.top;
+    d->prev_width = im.width;
+    d->prev_height = im.height;
+    d->have_read_first_frame = true;
+    d->seek_clear_extensions = true;
+    return true;
+}
+
+// ref giflib.cpp:1308-1431: a second walk over the container
+struct GifAnimationInfo giflib_decoder_get_animation_info(const giflib_decoder d) {
+    GifAnimationInfo info = {1, 0, 255, 255, 255, 0, 0};
+    GifReader r;
+    r.p = d->rd.p;
+    r.n = d->rd.n;
+    if (!r.open()) return info;
+    bool found_loop = false, found_gcb = false;
+    GifGcb first_gcb;
+    for (;;) {
+        const int rec = r.record();
+        if (rec < 0) break;  // DGifGetRecordType != GIF_OK ends the walk
+        if (rec == 2) return info;  // terminator: straight to cleanup (no background fix-up)
+        if (rec == 1) {
+            uint8_t label;
+            if (!r.get(&label)) break;
+            const uint8_t* data;
+            int len;
+            if (!r.sub_block(&data, &len)) break;
+            if (len == 0) continue;
+            if (label == 0xF9) {
+                GifGcb g;
+                gcb_from_block(data, len, &g);
+                info.duration_ms += (info.frame_count > 0 && g.delay < 2) ? 20 : g.delay * 10;
+                if (!found_gcb) {
+                    found_gcb = true;
+                    first_gcb = g;
+                    uint8_t R, G, B, A;
+                    background_color(r, g, &R, &G, &B, &A);
+                    info.bg_red = R; info.bg_green = G; info.bg_blue = B; info.bg_alpha = A;
+                }
+            } else if (!found_loop && label == 0xFF && len >= 11 && !memcmp(data, "NETSCAPE2.0", 11)) {
+                if (r.sub_block(&data, &len) && len != 0) {
+                    if (len >= 3 && data[0] == 1) {
+                        info.loop_count = data[1] | (data[2] << 8);
+                        found_loop = true;
+                    }
+                } else {
+                    if (len == 0) continue;
+                    return info;
+                }
+            }
+            bool ok = true;
+            while (len != 0) {
+                if (!r.sub_block(&data, &len)) { ok = false; break; }
+            }
+            if (!ok) return info;
+        } else {  // image descriptor
+            info.frame_count++;
+            GifImage im;
+            if (!r.image_header(&im)) return info;
+            const uint8_t* data;
+            int len;
+            bool ok = true;
+            do {
+                if (!r.sub_block(&data, &len)) { ok = false; break; }
+            } while (len != 0);
+            if (!ok) return info;
+        }
+    }
+    if (!found_gcb) {
+        uint8_t R, G, B, A;
+        background_color(r, first_gcb, &R, &G, &B, &A);
+        info.bg_red = R; info.bg_green = G; info.bg_blue = B; info.bg_alpha = A;
+    }
+    return info;
+}
+
+// GIF encoding is a "next" row: not on the device yet, fail loudly.
+giflib_encoder giflib_encoder_create(void*, size_t) {
+    fprintf(stderr, "[lilliput_b200] GIF encoding is not implemented on the device path yet\n");
+    return nullptr;
+}
+bool giflib_encoder_init(giflib_encoder, const giflib_decoder, int, int) { return false; }
+bool giflib_encoder_encode_frame(giflib_encoder, const giflib_decoder, const opencv_mat) { return false; }
+bool giflib_encoder_flush(giflib_encoder, const giflib_decoder) { return false; }
+void giflib_encoder_release(giflib_encoder e) { delete e; }
+int giflib_encoder_get_output_length(giflib_encoder) { return 0; }
+
+}  // extern "C"

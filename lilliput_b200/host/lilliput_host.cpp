@@ -4,6 +4,7 @@
 #include "lilliput_host.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 
@@ -345,18 +346,147 @@ class OpenCVEncoder : public Encoder {  // ref opencv.go:139-144, 847-905
     uint8_t* dstBuf = nullptr;
 };
 
+// ------------------------------------------------------------------ GIF adapter
+
+static std::atomic<uint64_t> gifMaxFrameDimension{10000};  // ref giflib.go:39,49-52,305-307
+void SetGIFMaxFrameDimension(uint64_t dim) { gifMaxFrameDimension.store(dim); }
+
+class GifDecoder : public Decoder {  // ref giflib.go:14-30, 56-234
+  public:
+    static Error Create(const uint8_t* buf, size_t len, std::unique_ptr<Decoder>* out) {
+        opencv_mat m = opencv_mat_create_from_data((int)len, 1, CV_8U, (void*)buf, len);
+        if (!m) return LP_ERR_BUF_TOO_SMALL;
+        giflib_decoder d = giflib_decoder_create(m);
+        if (!d) {
+            opencv_mat_release(m);
+            return LP_ERR_INVALID_IMAGE;
+        }
+        auto* self = new GifDecoder;
+        self->mat = m;
+        self->decoder = d;
+        self->len = len;
+        out->reset(self);
+        return LP_OK;
+    }
+    ~GifDecoder() override {
+        giflib_decoder_release(decoder);
+        opencv_mat_release(mat);
+    }
+    Error Header(ImageHeader* h) override {  // ref giflib.go:76-85
+        h->width = giflib_decoder_get_width(decoder);
+        h->height = giflib_decoder_get_height(decoder);
+        h->pixelType.v = CV_8UC4;
+        h->orientation = 1;
+        readAnimationInfo();
+        h->numFrames = info.frame_count;
+        h->contentLength = (int)len;
+        return LP_OK;
+    }
+    std::string Description() override { return "GIF"; }
+    Error DecodeTo(Framebuffer* f) override {  // ref giflib.go:180-219
+        ImageHeader h;
+        Header(&h);
+        Error e = f->resizeMat(h.width, h.height, h.pixelType);
+        if (e) return e;
+        const int next = (int)giflib_decoder_decode_frame_header(decoder);
+        if (next == giflib_decoder_eof) return LP_ERR_EOF;
+        if (next == giflib_decoder_error) return LP_ERR_INVALID_IMAGE;
+        const int maxDim = (int)gifMaxFrameDimension.load();
+        if (giflib_decoder_get_frame_width(decoder) > maxDim || giflib_decoder_get_frame_height(decoder) > maxDim)
+            return LP_ERR_INVALID_IMAGE;
+        if (!giflib_decoder_decode_frame(decoder, f->mat)) return LP_ERR_DECODING_FAILED;
+        f->duration_ns = (int64_t)giflib_decoder_get_prev_frame_delay(decoder) * 10 * 1000000;
+        f->blend = NoBlend;
+        // Go stores the C value straight into DisposeMethod: 1 (GIF_DISPOSE_BACKGROUND) happens to
+        // equal DisposeToBackgroundColor; 2 (previous) matches no case in applyDisposeMethod
+        f->dispose = (DisposeMethod)giflib_decoder_get_prev_frame_disposal(decoder);
+        f->xOffset = 0;
+        f->yOffset = 0;
+        return LP_OK;
+    }
+    Error SkipFrame() override {  // ref giflib.go:223-234
+        const int next = (int)giflib_decoder_skip_frame(decoder);
+        if (next == giflib_decoder_eof) return LP_ERR_EOF;
+        if (next == giflib_decoder_error) return LP_ERR_INVALID_IMAGE;
+        return LP_OK;
+    }
+    uint32_t BackgroundColor() override {  // ref giflib.go:131-134
+        readAnimationInfo();
+        return ((uint32_t)info.bg_red << 16) | ((uint32_t)info.bg_green << 8) | (uint32_t)info.bg_blue |
+               ((uint32_t)info.bg_alpha << 24);
+    }
+    int LoopCount() override {
+        readAnimationInfo();
+        return info.loop_count;
+    }
+    int64_t Duration_ns() override {
+        readAnimationInfo();
+        return (int64_t)info.duration_ms * 1000000;
+    }
+    giflib_decoder GifHandle() override { return decoder; }
+
+  private:
+    void readAnimationInfo() {  // ref giflib.go:138-151 (lazy, cached)
+        if (!infoRead) {
+            info = giflib_decoder_get_animation_info(decoder);
+            infoRead = true;
+        }
+    }
+    opencv_mat mat = nullptr;
+    giflib_decoder decoder = nullptr;
+    size_t len = 0;
+    bool infoRead = false;
+    GifAnimationInfo info{};
+};
+
+class GifEncoder : public Encoder {  // ref giflib.go:239-300
+  public:
+    static Error Create(Decoder* decodedBy, uint8_t* dst, size_t cap, std::unique_ptr<Encoder>* out) {
+        if (!decodedBy || !decodedBy->GifHandle()) return LP_ERR_INVALID_IMAGE;  // ErrGifEncoderNeedsDecoder
+        giflib_encoder e = giflib_encoder_create(dst, cap);
+        if (!e) return LP_ERR_BUF_TOO_SMALL;
+        auto* self = new GifEncoder;
+        self->encoder = e;
+        self->decoder = decodedBy->GifHandle();
+        out->reset(self);
+        return LP_OK;
+    }
+    ~GifEncoder() override { giflib_encoder_release(encoder); }
+    Error Encode(Framebuffer* f, const std::map<int, int>&, bool* content, size_t* out_len) override {
+        *content = false;
+        if (hasFlushed) return LP_ERR_EOF;
+        if (!f) {
+            if (!giflib_encoder_flush(encoder, decoder)) return LP_ERR_INVALID_IMAGE;
+            hasFlushed = true;
+            *out_len = (size_t)giflib_encoder_get_output_length(encoder);
+            *content = true;
+            return LP_OK;
+        }
+        if (frameIndex == 0) giflib_encoder_init(encoder, decoder, f->Width(), f->Height());
+        if (!giflib_encoder_encode_frame(encoder, decoder, f->mat)) return LP_ERR_INVALID_IMAGE;
+        frameIndex++;
+        return LP_OK;  // (nil, nil): send the next frame
+    }
+
+  private:
+    giflib_encoder encoder = nullptr;
+    giflib_decoder decoder = nullptr;
+    int frameIndex = 0;
+    bool hasFlushed = false;
+};
+
 static std::string lower(std::string s) {
     for (auto& c : s) c = (char)tolower((unsigned char)c);
     return s;
 }
 
-// ref lilliput.go:129-164.  GIF / WebP / AVIF / video are routed away BEFORE the
-// OpenCV adapter is tried; until those adapters exist on the device they are
-// reported as LP_ERR_UNSUPPORTED rather than silently mis-decoded.
+// ref lilliput.go:129-164.  GIF goes to the giflib adapter; WebP / AVIF / video are routed away
+// BEFORE the OpenCV adapter is tried and, until those adapters exist on the device, are reported
+// as LP_ERR_UNSUPPORTED rather than silently mis-decoded.
 Error NewDecoder(const uint8_t* buf, size_t len, std::unique_ptr<Decoder>* out) {
     if (len == 0) return LP_ERR_INVALID_IMAGE;
     if (len >= 6 && (!memcmp(buf, "GIF87a", 6) || !memcmp(buf, "GIF89a", 6)))
-        return LP_ERR_UNSUPPORTED;
+        return GifDecoder::Create(buf, len, out);
     if (len >= 12 && !memcmp(buf, "RIFF", 4) && !memcmp(buf + 8, "WEBP", 4))
         return LP_ERR_UNSUPPORTED;
     if (len >= 12 && !memcmp(buf + 4, "ftyp", 4) &&
@@ -366,11 +496,11 @@ Error NewDecoder(const uint8_t* buf, size_t len, std::unique_ptr<Decoder>* out) 
 }
 
 // ref lilliput.go:180-202
-Error NewEncoder(const std::string& ext_, Decoder*, uint8_t* dst, size_t cap,
+Error NewEncoder(const std::string& ext_, Decoder* decodedBy, uint8_t* dst, size_t cap,
                  std::unique_ptr<Encoder>* out) {
     std::string ext = lower(ext_);
-    if (ext == ".gif" || ext == ".webp" || ext == ".avif" || ext == ".thumbhash")
-        return LP_ERR_UNSUPPORTED;
+    if (ext == ".gif") return GifEncoder::Create(decodedBy, dst, cap, out);
+    if (ext == ".webp" || ext == ".avif" || ext == ".thumbhash") return LP_ERR_UNSUPPORTED;
     if (ext == ".mp4" || ext == ".webm") return LP_ERR_INVALID_IMAGE;
     return OpenCVEncoder::Create(ext_, dst, cap, out);
 }
@@ -707,5 +837,49 @@ extern "C" int lp_orient_host(const uint8_t* src, int w, int h, int type, int or
     *ow = a.Width();
     *oh = a.Height();
     memcpy(dst, opencv_mat_get_data(a.mat), (size_t)w * h * opencv_type_channels(type));
+    return LP_OK;
+}
+
+extern "C" int lp_gif_get_info(const uint8_t* in, size_t in_len, lp_gif_info* info) {
+    if (!in || !info) return LP_ERR_BAD_ARGUMENT;
+    std::unique_ptr<Decoder> d;
+    Error e = NewDecoder(in, in_len, &d);
+    if (e) return e;
+    if (!d->GifHandle()) return LP_ERR_BAD_ARGUMENT;
+    ImageHeader h;
+    if ((e = d->Header(&h))) return e;
+    info->width = h.width;
+    info->height = h.height;
+    info->frame_count = h.numFrames;
+    info->loop_count = d->LoopCount();
+    info->duration_ms = (int)(d->Duration_ns() / 1000000);
+    info->background_color = d->BackgroundColor();
+    return LP_OK;
+}
+
+extern "C" int lp_gif_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
+                                         int max_frames, int* n_frames, int* delays_ms, int* disposals) {
+    if (!in || !frames || !n_frames) return LP_ERR_BAD_ARGUMENT;
+    *n_frames = 0;
+    std::unique_ptr<Decoder> d;
+    Error e = NewDecoder(in, in_len, &d);
+    if (e) return e;
+    if (!d->GifHandle()) return LP_ERR_BAD_ARGUMENT;
+    ImageHeader h;
+    if ((e = d->Header(&h))) return e;
+    const size_t frame_bytes = (size_t)h.width * h.height * 4;
+    // like ImageOps, ONE framebuffer receives every frame (the compositor builds on its content)
+    Framebuffer f(std::max(h.width, h.height), std::max(h.width, h.height));
+    for (int i = 0; i < max_frames; i++) {
+        e = d->DecodeTo(&f);
+        if (e == LP_ERR_EOF) return LP_OK;
+        if (e) return e;
+        if ((size_t)(i + 1) * frame_bytes > frames_cap) return LP_ERR_BUF_TOO_SMALL;
+        if (lp_mat_sync_host(f.mat)) return LP_ERR_CUDA;
+        memcpy(frames + (size_t)i * frame_bytes, opencv_mat_get_data(f.mat), frame_bytes);
+        if (delays_ms) delays_ms[i] = (int)(f.duration_ns / 1000000);
+        if (disposals) disposals[i] = (int)f.dispose;
+        *n_frames = i + 1;
+    }
     return LP_OK;
 }

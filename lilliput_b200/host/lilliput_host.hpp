@@ -7,6 +7,7 @@
 //   Decoder / Encoder    ref lilliput.go:42-98
 //   OpenCVDecoder        ref opencv.go:442-463, 639-661, 816-843
 //   OpenCVEncoder        ref opencv.go:847-905
+//   GifDecoder / GifEncoder  ref giflib.go:56-300
 //   NewDecoder           ref lilliput.go:129-164
 //   NewEncoder           ref lilliput.go:180-202
 //   ImageOps::Transform  ref ops.go:352-444 (+ helpers 154-350, 449-591)
@@ -24,6 +25,7 @@
 #include <vector>
 
 #include "lilliput_b200.h"
+#include "lp_giflib.h"
 #include "lp_opencv.h"
 
 namespace lilliput {
@@ -94,7 +96,12 @@ class Decoder {  // ref lilliput.go:42-88
     virtual std::vector<uint8_t> ICC() { return {}; }
     virtual uint32_t BackgroundColor() { return 0xFFFFFFFFu; }
     virtual int LoopCount() { return 0; }
+    virtual int64_t Duration_ns() { return 0; }
+    virtual giflib_decoder GifHandle() { return nullptr; }  // Go: type assertion to *gifDecoder
 };
+
+// SetGIFMaxFrameDimension (ref giflib.go:44-52; default 10000, giflib.go:39,305-307)
+void SetGIFMaxFrameDimension(uint64_t dim);
 
 class Encoder {  // ref lilliput.go:90-98
   public:

@@ -4,4 +4,4 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-from make_golden import BLEND_CASES, JPEG_CASES, ORIENT_SRC, PNG_NAMES, RESIZE_CASES  # noqa: E402,F401
+from make_golden import BLEND_CASES, GIF_NAMES, JPEG_CASES, ORIENT_SRC, PNG_NAMES, RESIZE_CASES  # noqa: E402,F401

@@ -88,6 +88,44 @@ def png_cases(ref):
     return [(k, cases[k]) for k in PNG_NAMES]
 
 
+GIF_NAMES = ["dispose_bgnd", "duplicate_number_of_loops", "ferry_sunset", "no-loop", "no_gce_first_frame",
+             "party-discord", "restore_previous", "syn_interlaced", "syn_offsets", "syn_local_palettes",
+             "syn_dispose3", "syn_wide"]
+
+
+def gif_cases():
+    import io
+    from PIL import Image
+    cases = {}
+    for n in GIF_NAMES[:7]:
+        cases[n] = open(f"/root/reference/testdata/{n}.gif", "rb").read()
+    rng = np.random.default_rng(3)
+
+    def frames_to_gif(frames, **kw):
+        bio = io.BytesIO()
+        frames[0].save(bio, "GIF", save_all=True, append_images=frames[1:], **kw)
+        return bio.getvalue()
+    base = [Image.fromarray(synth_image(60 + i, 90, 70, 3, noise=3.0)[:, :, ::-1].copy()).quantize(64) for i in range(4)]
+    cases["syn_interlaced"] = frames_to_gif(base, duration=70, loop=3, interlace=True, optimize=False)
+    # PIL writes minimal bounding-box sub-frames when frames differ little: offsets + transparency
+    a = np.zeros((60, 80, 3), np.uint8) + 200
+    seq = []
+    for i in range(5):
+        b = a.copy()
+        b[10 + 5 * i:25 + 5 * i, 15 + 8 * i:40 + 8 * i] = (30 * i, 255 - 40 * i, 90)
+        seq.append(Image.fromarray(b))
+    cases["syn_offsets"] = frames_to_gif(seq, duration=[50, 0, 10, 200, 30], loop=0, disposal=1, optimize=True)
+    cases["syn_local_palettes"] = frames_to_gif(
+        [Image.fromarray(synth_image(70 + i, 64, 48, 3, noise=8.0)[:, :, ::-1].copy()).quantize(256 if i % 2 else 16)
+         for i in range(3)], duration=40, loop=1, optimize=False)
+    cases["syn_dispose3"] = frames_to_gif(seq, duration=30, loop=0, disposal=[3, 2, 3, 1, 2], transparency=0,
+                                          optimize=False)
+    cases["syn_wide"] = frames_to_gif([Image.fromarray(rng.integers(0, 256, (5, 700, 3), dtype=np.uint8)).quantize(128)
+                                       for _ in range(2)], duration=20)
+    assert sorted(cases) == sorted(GIF_NAMES)
+    return [(k, cases[k]) for k in GIF_NAMES]
+
+
 def main():
     ref = abi.load_reference()
     out = {}
@@ -136,6 +174,19 @@ def main():
     for name, data in png_cases(ref):
         out[f"png_{name}"] = np.frombuffer(data, dtype=np.uint8)
         out[f"pngdec_{name}"] = ref.decode(data)
+    # GIF decode: reference fixtures + synthetic animations; frames pinned by SHA-256 (full canvas BGRA)
+    for name, data in gif_cases():
+        info = ref.gif_info(data)
+        frames, delays, disposals, rc = ref.gif_frames(data)
+        out[f"gif_{name}"] = np.frombuffer(data, dtype=np.uint8)
+        out[f"gifmeta_{name}"] = np.array([info["width"], info["height"], info["frame_count"], info["loop_count"],
+                                           info["duration_ms"], info["background_color"], rc, len(frames)],
+                                          dtype=np.int64)
+        out[f"gifdelay_{name}"] = np.array(delays, dtype=np.int64)
+        out[f"gifdisp_{name}"] = np.array(disposals, dtype=np.int64)
+        out[f"gifsha_{name}"] = np.array([hashlib.sha256(f.tobytes()).hexdigest() for f in frames])
+        if frames.nbytes <= 200000:
+            out[f"gifframes_{name}"] = frames
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden.npz"), **out)
     print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(ROOT, "tests/golden/golden.npz")), "bytes")
 

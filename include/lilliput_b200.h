@@ -109,6 +109,13 @@ int lp_gif_get_info(const uint8_t* in, size_t in_len, lp_gif_info* info);
  * stream ended with EOF, else the error that stopped it (frames decoded so far are still valid). */
 int lp_gif_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
                               int max_frames, int* n_frames, int* delays_ms, int* disposals);
+/* WebP: every frame exactly as webp_decoder_decode leaves it in the mat (ref webp.cpp:291-359:
+ * frame-sized BGR / BGRA), packed back to back.  meta[8*i..] = width, height, channels, x_offset,
+ * y_offset, delay_ms, dispose, blend.  info[0..7] = canvas width, canvas height, pixel type, frame
+ * count, total duration (ms), loop count, background colour, ICC profile length.  `frames` may be
+ * NULL to read `info` only. */
+int lp_webp_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
+                               int max_frames, int* n_frames, int* meta, unsigned int* info);
 
 #ifndef LP_REFERENCE_BACKEND
 /* ------------------------- CUDA-only entry points -------------------------- */

@@ -31,6 +31,8 @@ JpegQuality, JpegProgressive, PngCompression, WebpQuality = 1, 2, 16, 64
 CV_8UC1, CV_8UC3, CV_8UC4 = 0, 16, 24
 INTER_LINEAR, INTER_CUBIC, INTER_AREA = 1, 2, 3
 
+LP_OK, LP_ERR_INVALID_IMAGE, LP_ERR_DECODING_FAILED, LP_ERR_BUF_TOO_SMALL = 0, -1, -2, -3
+
 LP_ERRORS = {
     0: "ok", -1: "ErrInvalidImage", -2: "ErrDecodingFailed", -3: "ErrBufTooSmall",
     -4: "ErrFrameBufNoPixels", -5: "ErrSkipNotSupported", -6: "ErrEncodeTimeout", -7: "EOF",
@@ -235,6 +237,34 @@ class Lib:
                                               n, C.byref(got), delays, disp)
         k = got.value
         return frames[:k], list(delays[:k]), list(disp[:k]), rc
+
+    # --- WebP (ref webp.hpp) ---------------------------------------------------------------
+    def webp_frames(self, data: bytes, max_frames: int = 1 << 16, decode: bool = True):
+        """Raw webp_decoder_* walk: (info dict, [frame arrays], [meta dicts], rc)."""
+        src = np.frombuffer(data, dtype=np.uint8)
+        info = (C.c_uint * 8)()
+        got = C.c_int(0)
+        f = self.l.lp_webp_decode_frames_host
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.c_void_p,
+                      C.c_void_p]
+        rc = f(src.ctypes.data, src.size, None, 0, 0, C.byref(got), None, info)
+        if rc != 0:
+            return None, [], [], rc
+        keys = ("width", "height", "pixel_type", "num_frames", "total_duration", "loop_count", "bg_color", "icc_len")
+        inf = dict(zip(keys, [int(v) for v in info]))
+        if not decode:
+            return inf, [], [], 0
+        n = max(1, min(max_frames, inf["num_frames"]))
+        buf = np.zeros(n * inf["width"] * inf["height"] * 4, dtype=np.uint8)
+        meta = (C.c_int * (8 * n))()
+        rc = f(src.ctypes.data, src.size, buf.ctypes.data, buf.nbytes, n, C.byref(got), meta, info)
+        frames, metas, off = [], [], 0
+        for i in range(got.value):
+            w, h, ch, x, y, delay, dispose, blend = [int(v) for v in meta[8 * i:8 * i + 8]]
+            frames.append(buf[off:off + w * h * ch].reshape(h, w, ch).copy())
+            off += w * h * ch
+            metas.append(dict(x=x, y=y, delay=delay, dispose=dispose, blend=blend))
+        return inf, frames, metas, rc
 
     def orient(self, img: np.ndarray, orientation: int) -> np.ndarray:
         """Framebuffer.OrientationTransform (ref opencv.go:271)."""

@@ -482,13 +482,83 @@ static std::string lower(std::string s) {
 
 // ref lilliput.go:129-164.  GIF goes to the giflib adapter; WebP / AVIF / video are routed away
 // BEFORE the OpenCV adapter is tried and, until those adapters exist on the device, are reported
+
+// ------------------------------------------------------------------ WebP adapter
+
+class WebpDecoder : public Decoder {  // ref webp.go:13-18, 30-176
+  public:
+    static Error Create(const uint8_t* buf, size_t len, std::unique_ptr<Decoder>* out) {
+        opencv_mat m = opencv_mat_create_from_data((int)len, 1, CV_8U, (void*)buf, len);
+        if (!m) return LP_ERR_BUF_TOO_SMALL;
+        webp_decoder d = webp_decoder_create(m);
+        if (!d) {
+            opencv_mat_release(m);
+            return LP_ERR_INVALID_IMAGE;
+        }
+        auto* self = new WebpDecoder;
+        self->mat = m;
+        self->decoder = d;
+        self->len = len;
+        out->reset(self);
+        return LP_OK;
+    }
+    ~WebpDecoder() override {
+        webp_decoder_release(decoder);
+        opencv_mat_release(mat);
+    }
+    Error Header(ImageHeader* h) override {  // ref webp.go:50-59
+        h->width = webp_decoder_get_width(decoder);
+        h->height = webp_decoder_get_height(decoder);
+        h->pixelType.v = webp_decoder_get_pixel_type(decoder);
+        h->orientation = 1;
+        h->numFrames = webp_decoder_get_num_frames(decoder);
+        h->contentLength = (int)len;
+        return LP_OK;
+    }
+    std::string Description() override { return "WEBP"; }
+    Error DecodeTo(Framebuffer* f) override {  // ref webp.go:139-171
+        if (!f) return LP_ERR_EOF;
+        ImageHeader h;
+        Header(&h);
+        Error e = f->resizeMat(h.width, h.height, h.pixelType);
+        if (e) return e;
+        if (!webp_decoder_decode(decoder, f->mat)) {
+            if (webp_decoder_has_more_frames(decoder) == 0) return LP_ERR_EOF;
+            return LP_ERR_DECODING_FAILED;
+        }
+        // NB: the C side re-creates the mat at the frame's own size (ref webp.cpp:319-320) while the
+        // Go Framebuffer keeps the canvas width/height it was resized to; mirrored as is.
+        f->duration_ns = (int64_t)webp_decoder_get_prev_frame_delay(decoder) * 1000000;
+        f->xOffset = webp_decoder_get_prev_frame_x_offset(decoder);
+        f->yOffset = webp_decoder_get_prev_frame_y_offset(decoder);
+        f->dispose = (DisposeMethod)webp_decoder_get_prev_frame_dispose(decoder);
+        f->blend = (BlendMethod)webp_decoder_get_prev_frame_blend(decoder);
+        webp_decoder_advance_frame(decoder);
+        return LP_OK;
+    }
+    Error SkipFrame() override { return LP_ERR_SKIP_NOT_SUPPORTED; }  // ref webp.go:174-176
+    std::vector<uint8_t> ICC() override {                             // ref webp.go:103-107
+        std::vector<uint8_t> icc(32768);  // ICCProfileBufferSize, ref lilliput.go:15
+        icc.resize(webp_decoder_get_icc(decoder, icc.data(), icc.size()));
+        return icc;
+    }
+    uint32_t BackgroundColor() override { return webp_decoder_get_bg_color(decoder); }
+    int LoopCount() override { return (int)webp_decoder_get_loop_count(decoder); }
+    int64_t Duration_ns() override { return (int64_t)webp_decoder_get_total_duration(decoder) * 1000000; }
+
+  private:
+    webp_decoder decoder = nullptr;
+    opencv_mat mat = nullptr;
+    size_t len = 0;
+};
+
 // as LP_ERR_UNSUPPORTED rather than silently mis-decoded.
 Error NewDecoder(const uint8_t* buf, size_t len, std::unique_ptr<Decoder>* out) {
     if (len == 0) return LP_ERR_INVALID_IMAGE;
     if (len >= 6 && (!memcmp(buf, "GIF87a", 6) || !memcmp(buf, "GIF89a", 6)))
         return GifDecoder::Create(buf, len, out);
-    if (len >= 12 && !memcmp(buf, "RIFF", 4) && !memcmp(buf + 8, "WEBP", 4))
-        return LP_ERR_UNSUPPORTED;
+    if (len >= 12 && !memcmp(buf, "RIFF", 4) && !memcmp(buf + 8, "WEBP", 4))  // ref lilliput.go:104-109,147-150
+        return WebpDecoder::Create(buf, len, out);
     if (len >= 12 && !memcmp(buf + 4, "ftyp", 4) &&
         (!memcmp(buf + 8, "avif", 4) || !memcmp(buf + 8, "avis", 4)))
         return LP_ERR_UNSUPPORTED;
@@ -882,4 +952,74 @@ extern "C" int lp_gif_decode_frames_host(const uint8_t* in, size_t in_len, uint8
         *n_frames = i + 1;
     }
     return LP_OK;
+}
+
+// Raw webp_decoder_* walk (ref webp.hpp:35-51,74-75): every frame exactly as webp_decoder_decode
+// leaves it in the mat (frame-sized, BGR or BGRA), packed back to back into `frames`.
+// meta[8*i..] = width, height, channels, x_offset, y_offset, delay_ms, dispose, blend.
+// info[0..7] = canvas width, canvas height, pixel type, frame count, total duration, loop count,
+// background colour, ICC length.
+extern "C" int lp_webp_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
+                                          int max_frames, int* n_frames, int* meta, unsigned int* info) {
+    if (!in || !n_frames) return LP_ERR_BAD_ARGUMENT;
+    *n_frames = 0;
+    opencv_mat src = opencv_mat_create_from_data((int)in_len, 1, CV_8U, (void*)in, in_len);
+    if (!src) return LP_ERR_BUF_TOO_SMALL;
+    webp_decoder d = webp_decoder_create(src);
+    if (!d) {
+        opencv_mat_release(src);
+        return LP_ERR_INVALID_IMAGE;
+    }
+    const int cw = webp_decoder_get_width(d), ch = webp_decoder_get_height(d), type = webp_decoder_get_pixel_type(d);
+    if (info) {
+        std::vector<uint8_t> icc(32768);
+        info[0] = (unsigned)cw;
+        info[1] = (unsigned)ch;
+        info[2] = (unsigned)type;
+        info[3] = (unsigned)webp_decoder_get_num_frames(d);
+        info[4] = (unsigned)webp_decoder_get_total_duration(d);
+        info[5] = webp_decoder_get_loop_count(d);
+        info[6] = webp_decoder_get_bg_color(d);
+        info[7] = (unsigned)webp_decoder_get_icc(d, icc.data(), icc.size());
+    }
+    int rc = LP_OK;
+    size_t used = 0;
+    opencv_mat m = opencv_mat_create(cw, ch, type);
+    for (int i = 0; frames && i < max_frames; i++) {
+        if (!webp_decoder_decode(d, m)) {
+            rc = (i >= webp_decoder_get_num_frames(d)) ? LP_OK : LP_ERR_DECODING_FAILED;
+            break;
+        }
+        if (lp_mat_sync_host(m)) {
+            rc = LP_ERR_CUDA;
+            break;
+        }
+        const int w = opencv_mat_get_width(m), h = opencv_mat_get_height(m);
+        const int chn = opencv_type_channels(type);
+        const size_t row = (size_t)w * chn;  // cv::Mat::create leaves the mat continuous
+        if (used + row * h > frames_cap) {
+            rc = LP_ERR_BUF_TOO_SMALL;
+            break;
+        }
+        const uint8_t* px = (const uint8_t*)opencv_mat_get_data(m);
+        memcpy(frames + used, px, row * h);
+        used += row * h;
+        if (meta) {
+            int* q = meta + 8 * i;
+            q[0] = w;
+            q[1] = h;
+            q[2] = chn;
+            q[3] = webp_decoder_get_prev_frame_x_offset(d);
+            q[4] = webp_decoder_get_prev_frame_y_offset(d);
+            q[5] = webp_decoder_get_prev_frame_delay(d);
+            q[6] = webp_decoder_get_prev_frame_dispose(d);
+            q[7] = webp_decoder_get_prev_frame_blend(d);
+        }
+        *n_frames = i + 1;
+        webp_decoder_advance_frame(d);
+    }
+    opencv_mat_release(m);
+    webp_decoder_release(d);
+    opencv_mat_release(src);
+    return rc;
 }

@@ -8,6 +8,7 @@
 //   OpenCVDecoder        ref opencv.go:442-463, 639-661, 816-843
 //   OpenCVEncoder        ref opencv.go:847-905
 //   GifDecoder / GifEncoder  ref giflib.go:56-300
+//   WebpDecoder          ref webp.go:13-176
 //   NewDecoder           ref lilliput.go:129-164
 //   NewEncoder           ref lilliput.go:180-202
 //   ImageOps::Transform  ref ops.go:352-444 (+ helpers 154-350, 449-591)
@@ -26,6 +27,7 @@
 
 #include "lilliput_b200.h"
 #include "lp_giflib.h"
+#include "lp_webp.h"
 #include "lp_opencv.h"
 
 namespace lilliput {

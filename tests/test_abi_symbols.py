@@ -14,10 +14,10 @@ LIB = os.path.join(ROOT, "lilliput_b200", "liblilliput_b200.so")
 
 def _declared():
     names = set()
-    for h in ("lp_opencv.h", "lilliput_b200.h"):
+    for h in ("lp_opencv.h", "lilliput_b200.h", "lp_giflib.h", "lp_webp.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        names |= set(re.findall(r"\b((?:opencv|lp)_[a-z0-9_]+)\s*\(", src))
+        names |= set(re.findall(r"\b((?:opencv|lp|giflib|webp)_[a-z0-9_]+)\s*\(", src))
     return names
 
 
@@ -31,6 +31,22 @@ def test_library_exports_every_declared_symbol():
         assert g in have
     # the 36 functions of the reference's opencv.hpp:61-132
     assert len([n for n in _declared() if n.startswith("opencv_")]) == 36
+    # giflib.hpp:33-52 (19 functions) and webp.hpp:35-75 (23 functions)
+    assert len([n for n in _declared() if n.startswith("giflib_")]) == 19
+    assert len([n for n in _declared() if n.startswith("webp_")]) == 23
+
+
+def test_webp_container_is_parsed_on_the_host():
+    """webp_decoder_create / get_* need no device: header fields of a golden stream, and a refusal."""
+    from lilliput_b200 import abi
+    from tests.webp_util import webp_golden
+    g = webp_golden()
+    lib = abi.load_cuda()
+    info, _, _, rc = lib.webp_frames(g["webp_anim_lossy"].tobytes(), decode=False)
+    assert rc == 0 and [info[k] for k in ("width", "height", "pixel_type", "num_frames", "total_duration",
+                                          "loop_count", "bg_color")] == [int(v) for v in g["webpinfo_anim_lossy"][:7]]
+    info, _, _, rc = lib.webp_frames(g["webp_bad_truncated"].tobytes(), decode=False)
+    assert info is None and rc == abi.LP_ERR_INVALID_IMAGE
 
 
 def test_library_loads_and_host_only_entry_points_work():

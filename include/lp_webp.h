@@ -3,12 +3,12 @@
  * Same names, signatures and return conventions as the reference's webp.hpp (cited per symbol).
  *
  * Decode: the RIFF container (VP8 / VP8L / VP8X / ICCP / ANIM / ANMF / ALPH) is walked on the
- * host, standing where libwebpmux does for the reference (ref webp.cpp:61-139); VP8 (lossy)
- * key frames are decoded on the device -- boolean-coded modes and tokens, inverse transforms,
- * intra prediction, loop filter, libwebp's fancy upsampler and YUV->BGR -- bit-exact to
- * WebPDecodeBGRInto / WebPDecodeBGRAInto (ref webp.cpp:336-351).  Frames coded as VP8L
- * (lossless), or carrying a VP8L-compressed ALPH plane, are not decoded yet:
- * webp_decoder_decode returns false for them, which webp.go:160-167 maps to ErrDecodingFailed.
+ * host, standing where libwebpmux does for the reference (ref webp.cpp:61-139); the frames are
+ * decoded on the device, bit-exact to WebPDecodeBGRInto / WebPDecodeBGRAInto (ref webp.cpp:336-351):
+ *   VP8  (lossy key frames): boolean-coded modes and tokens, inverse transforms, intra prediction,
+ *        loop filter, libwebp's "fancy" upsampler and fixed-point YUV->BGR;
+ *   VP8L (lossless): prefix codes + meta prefix image, colour cache, LZ77, the four transforms;
+ *   ALPH (alpha plane of a lossy frame): raw or VP8L-coded, with its prediction filters.
  *
  * Encode: the entry points exist so the Go package links; WebP *encoding* is not implemented
  * (SURVEY.md 8 row R8): webp_encoder_create returns NULL, which webp.go:214-217 maps to an error.

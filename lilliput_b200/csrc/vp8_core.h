@@ -23,6 +23,9 @@
 #ifndef LP_VP8_FN
 #define LP_VP8_FN static inline
 #endif
+#ifndef LP_VP8_INL  // small primitives that must stay in registers
+#define LP_VP8_INL LP_VP8_FN
+#endif
 #ifndef LP_VP8_HD  // the two layout helpers are also called by the host launcher
 #define LP_VP8_HD LP_VP8_FN
 #endif
@@ -41,7 +44,7 @@ struct BoolDec {
     int bits;        // number of bits in `value` below the 8-bit compare window
 };
 
-LP_VP8_FN int clz32(uint32_t v) {
+LP_VP8_INL int clz32(uint32_t v) {
 #ifdef __CUDA_ARCH__
     return __clz((int)v);
 #else
@@ -49,7 +52,7 @@ LP_VP8_FN int clz32(uint32_t v) {
 #endif
 }
 
-LP_VP8_FN void bd_init(BoolDec& b, const uint8_t* p, size_t n) {
+LP_VP8_INL void bd_init(BoolDec& b, const uint8_t* p, size_t n) {
     b.p = p;
     b.end = p + n;
     b.value = 0;
@@ -57,7 +60,7 @@ LP_VP8_FN void bd_init(BoolDec& b, const uint8_t* p, size_t n) {
     b.bits = -8;
 }
 
-LP_VP8_FN void bd_fill(BoolDec& b) {
+LP_VP8_INL void bd_fill(BoolDec& b) {
     // keep at least one byte of lookahead; take up to 6 bytes per refill
     if (b.p + 6 <= b.end) {
         uint64_t w = 0;
@@ -73,7 +76,7 @@ LP_VP8_FN void bd_fill(BoolDec& b) {
     }
 }
 
-LP_VP8_FN int bd_bit(BoolDec& b, int prob) {
+LP_VP8_INL int bd_bit(BoolDec& b, int prob) {
     if (b.bits < 0) bd_fill(b);
     uint32_t range = b.range;
     const uint32_t split = (range * (uint32_t)prob) >> 8;
@@ -368,9 +371,9 @@ LP_VP8_FN void inverse_wht(const int16_t* in, int16_t* dst /* stride 16 */) {
     }
 }
 
-LP_VP8_FN uint8_t clip8(int v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
-LP_VP8_FN int mul1(int a) { return ((a * 20091) >> 16) + a; }
-LP_VP8_FN int mul2(int a) { return (a * 35468) >> 16; }
+LP_VP8_INL uint8_t clip8(int v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
+LP_VP8_INL int mul1(int a) { return ((a * 20091) >> 16) + a; }
+LP_VP8_INL int mul2(int a) { return (a * 35468) >> 16; }
 
 // dst += IDCT(in), clipped; dst is a stride-`bps` pixel block.
 LP_VP8_FN void inverse_dct_add(const int16_t* in, uint8_t* dst, int bps) {
@@ -579,176 +582,197 @@ LP_VP8_HD void work_carve(uint8_t* base, int mb_w, int mb_h, Work& w) {
     w.proba = base + off + (size_t)mb_w * mb_h * 4;
 }
 
-// ---- macroblock parse + reconstruction (RFC 6386 s.19.3, s.11-14) --------------------------
+// ---- macroblock parse (RFC 6386 s.19.3, s.11, s.13) ----------------------------------------
+struct MbInfo {
+    uint8_t is_i4x4, ymode, uvmode, segment;
+    uint8_t modes[16];   // sub-block modes when is_i4x4
+    uint32_t nz_blocks;  // bit b set: block b (0..15 Y, 16..19 U, 20..23 V) has a non-zero coefficient
+    uint32_t finfo;      // loop-filter parameters, packed as in Work::finfo
+};
+struct RowCtx {  // state carried from the macroblock on the left
+    uint8_t left_modes[4];
+    uint8_t left_nz[9];
+};
+LP_VP8_FN void row_ctx_reset(RowCtx& rc) {
+    for (int i = 0; i < 4; i++) rc.left_modes[i] = B_DC;
+    for (int i = 0; i < 9; i++) rc.left_nz[i] = 0;
+}
+
+// Mode bits of one macroblock (first partition).  `tm` = the 4 sub-block modes above it.
+// Returns the coded skip flag.
+LP_VP8_FN int parse_mb_modes(const FrameHdr& h, BoolDec& br, uint8_t* tm, RowCtx& rc, MbInfo& mb) {
+    int segment = 0;
+    if (h.update_map)
+        segment = !bd_bit(br, h.seg_proba[0]) ? bd_bit(br, h.seg_proba[1]) : bd_bit(br, h.seg_proba[2]) + 2;
+    mb.segment = (uint8_t)segment;
+    const int skip = h.use_skip ? bd_bit(br, h.skip_p) : 0;
+    mb.is_i4x4 = (uint8_t)!bd_bit(br, 145);
+    mb.ymode = DC_PRED;
+    if (!mb.is_i4x4) {
+        const int ymode = bd_bit(br, 156) ? (bd_bit(br, 128) ? TM_PRED : H_PRED) : (bd_bit(br, 163) ? V_PRED : DC_PRED);
+        mb.ymode = (uint8_t)ymode;
+        for (int i = 0; i < 4; i++) tm[i] = rc.left_modes[i] = (uint8_t)ymode;
+    } else {
+        for (int by = 0; by < 4; by++) {
+            int lm = rc.left_modes[by];
+            for (int bx = 0; bx < 4; bx++) {
+                const uint8_t* prob = kVp8BModesProba[tm[bx]][lm];
+                int i = kVp8YModesIntra4[bd_bit(br, prob[0])];
+                while (i > 0) i = kVp8YModesIntra4[2 * i + bd_bit(br, prob[i])];
+                lm = -i;
+                tm[bx] = (uint8_t)lm;
+                mb.modes[by * 4 + bx] = (uint8_t)lm;
+            }
+            rc.left_modes[by] = (uint8_t)lm;
+        }
+    }
+    mb.uvmode = (uint8_t)(!bd_bit(br, 142) ? DC_PRED : !bd_bit(br, 114) ? V_PRED : bd_bit(br, 183) ? TM_PRED : H_PRED);
+    return skip;
+}
+
+// Coefficient tokens of one macroblock (its row's token partition) into `coeffs` (25 blocks of
+// 16, zeroed by the caller; block 24 is scratch for Y2).  `tnz` = the 9 non-zero flags above.
+// Fills mb.nz_blocks and mb.finfo.
+LP_VP8_FN void parse_mb_residuals(const FrameHdr& h, BoolDec& tbr, const uint8_t* proba, uint8_t* tnz, RowCtx& rc,
+                                  int skip, MbInfo& mb, int16_t* coeffs) {
+    const QuantMat& q = h.q[mb.segment];
+    uint32_t nzb = 0;
+    if (!skip) {
+        const int has_y2 = !mb.is_i4x4;
+        // one loop over Y2?, 16 Y, 4 U, 4 V so the token reader is instantiated once
+        for (int k = has_y2 ? -1 : 0; k < 24; k++) {
+            int type, ti, li, first = 0;
+            const int* dq;
+            int16_t* out;
+            if (k < 0) {
+                type = 1; ti = 8; li = 8; dq = q.y2; out = coeffs + 24 * 16;
+            } else if (k < 16) {
+                type = has_y2 ? 0 : 3; ti = k & 3; li = k >> 2; dq = q.y1; out = coeffs + k * 16; first = has_y2;
+            } else {
+                const int c = k - 16;  // 0..3 U, 4..7 V
+                type = 2; ti = 4 + (c >> 2) * 2 + (c & 1); li = 4 + (c >> 2) * 2 + ((c >> 1) & 1); dq = q.uv; out = coeffs + k * 16;
+            }
+            const int ctx = tnz[ti] + rc.left_nz[li];
+            const int nz = get_coeffs(tbr, proba, type, ctx, dq, first, out);
+            const uint8_t flag = (uint8_t)(nz > first);
+            tnz[ti] = rc.left_nz[li] = flag;
+            if (k < 0) {
+                inverse_wht(out, coeffs);
+            } else {
+                nzb |= (uint32_t)((nz > 1) | (out[0] != 0)) << k;  // the DC may come from the Y2 transform
+            }
+        }
+        skip = nzb == 0;
+    } else {
+        for (int i = 0; i < 8; i++) tnz[i] = rc.left_nz[i] = 0;
+        if (!mb.is_i4x4) tnz[8] = rc.left_nz[8] = 0;
+    }
+    mb.nz_blocks = nzb;
+    const FilterStrength& f = h.fs[mb.segment][mb.is_i4x4];
+    const uint32_t inner = f.inner | (uint32_t)(!skip);
+    mb.finfo = f.limit | ((uint32_t)f.ilevel << 8) | ((uint32_t)f.hev << 16) | (inner << 24);
+}
+
+// ---- macroblock reconstruction, serial form (RFC 6386 s.12, s.14) --------------------------
+// Work-buffer geometry shared with the device kernel: stride 32, luma block at column 8 of row 1,
+// so the row above and the column to the left hold the prediction borders.
+enum { BPS = 32, YB_SIZE = 17 * BPS, CB_SIZE = 9 * BPS };
+
+LP_VP8_FN void reconstruct_mb(const FrameHdr& h, Work& w, int mb_x, int mb_y, const MbInfo& mb, const int16_t* coeffs,
+                              uint8_t* yb, uint8_t* ub, uint8_t* vb) {
+    const int mb_w = h.mb_w;
+    const int ys = mb_w * 16, cs = mb_w * 8;
+    uint8_t* yd = yb + BPS + 8;
+    uint8_t* ud = ub + BPS + 8;
+    uint8_t* vd = vb + BPS + 8;
+    uint8_t* py = w.y + (size_t)mb_y * 16 * ys + mb_x * 16;
+    uint8_t* pu = w.u + (size_t)mb_y * 8 * cs + mb_x * 8;
+    uint8_t* pv = w.v + (size_t)mb_y * 8 * cs + mb_x * 8;
+    // prediction borders (s.12.2): 127 above the first row, 129 left of the first column
+    if (mb_x > 0) {
+        for (int j = 0; j < 16; j++) yd[j * BPS - 1] = py[j * ys - 1];
+        for (int j = 0; j < 8; j++) {
+            ud[j * BPS - 1] = pu[j * cs - 1];
+            vd[j * BPS - 1] = pv[j * cs - 1];
+        }
+    } else {
+        for (int j = 0; j < 16; j++) yd[j * BPS - 1] = 129;
+        for (int j = 0; j < 8; j++) ud[j * BPS - 1] = vd[j * BPS - 1] = 129;
+    }
+    if (mb_y > 0) {
+        for (int i = 0; i < 16; i++) yd[i - BPS] = py[i - ys];
+        for (int i = 0; i < 8; i++) {
+            ud[i - BPS] = pu[i - cs];
+            vd[i - BPS] = pv[i - cs];
+        }
+        if (mb_x < mb_w - 1)
+            for (int i = 16; i < 20; i++) yd[i - BPS] = py[i - ys];
+        else
+            for (int i = 16; i < 20; i++) yd[i - BPS] = py[15 - ys];
+        if (mb_x > 0) {
+            yd[-1 - BPS] = py[-1 - ys];
+            ud[-1 - BPS] = pu[-1 - cs];
+            vd[-1 - BPS] = pv[-1 - cs];
+        } else {
+            yd[-1 - BPS] = ud[-1 - BPS] = vd[-1 - BPS] = 129;
+        }
+    } else {
+        for (int i = -1; i < 20; i++) yd[i - BPS] = 127;
+        for (int i = -1; i < 8; i++) ud[i - BPS] = vd[i - BPS] = 127;
+    }
+    if (mb.is_i4x4) {
+        // the above-right samples of the macroblock serve every row of sub-blocks
+        for (int r = 1; r < 4; r++)
+            for (int i = 16; i < 20; i++) yd[(4 * r - 1) * BPS + i] = yd[i - BPS];
+        for (int n = 0; n < 16; n++) {
+            uint8_t* d = yd + (n >> 2) * 4 * BPS + (n & 3) * 4;
+            pred_4x4(d, BPS, mb.modes[n]);
+            if ((mb.nz_blocks >> n) & 1) inverse_dct_add(coeffs + n * 16, d, BPS);
+        }
+    } else {
+        pred_block(yd, BPS, 16, mb.ymode, mb_y > 0, mb_x > 0);
+        for (int n = 0; n < 16; n++)
+            if ((mb.nz_blocks >> n) & 1) inverse_dct_add(coeffs + n * 16, yd + (n >> 2) * 4 * BPS + (n & 3) * 4, BPS);
+    }
+    pred_block(ud, BPS, 8, mb.uvmode, mb_y > 0, mb_x > 0);
+    pred_block(vd, BPS, 8, mb.uvmode, mb_y > 0, mb_x > 0);
+    for (int n = 0; n < 4; n++) {
+        if ((mb.nz_blocks >> (16 + n)) & 1) inverse_dct_add(coeffs + (16 + n) * 16, ud + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
+        if ((mb.nz_blocks >> (20 + n)) & 1) inverse_dct_add(coeffs + (20 + n) * 16, vd + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
+    }
+    for (int j = 0; j < 16; j++)
+        for (int i = 0; i < 16; i++) py[j * ys + i] = yd[j * BPS + i];
+    for (int j = 0; j < 8; j++)
+        for (int i = 0; i < 8; i++) {
+            pu[j * cs + i] = ud[j * BPS + i];
+            pv[j * cs + i] = vd[j * BPS + i];
+        }
+}
+
 // Decodes every macroblock of the frame in raster order into the (unfiltered) planes and
 // records the loop-filter parameters.  Serial by construction of the format: mode and token
-// contexts chain left-to-right / top-to-bottom, and so does intra prediction.
+// contexts chain left-to-right / top-to-bottom, and so does intra prediction.  (The device
+// kernel runs the same parse functions on one lane and spreads reconstruction over the warp.)
 LP_VP8_FN int decode_macroblocks(const uint8_t* data, const FrameHdr& h, BoolDec& br, Work& w) {
     const int mb_w = h.mb_w, mb_h = h.mb_h;
-    const int ys = mb_w * 16, cs = mb_w * 8;
     for (int i = 0; i < mb_w * 4; i++) w.top_modes[i] = B_DC;
     for (int i = 0; i < mb_w * 9; i++) w.top_nz[i] = 0;
-
-    enum { BPS = 32 };
-    uint8_t yb[17 * BPS], ub[9 * BPS], vb[9 * BPS];
+    uint8_t yb[YB_SIZE], ub[CB_SIZE], vb[CB_SIZE];
     int16_t coeffs[25 * 16];
-    uint8_t modes[16];
-
-    // one bool decoder per token partition, advanced row by row
+    // one bool decoder per token partition, advanced row by row (s.9.5)
     BoolDec parts[8];
     for (int p = 0; p < h.num_parts; p++) bd_init(parts[p], data + h.part_off[p], h.part_len[p]);
-
     for (int mb_y = 0; mb_y < mb_h; mb_y++) {
         BoolDec& tbr = parts[mb_y & (h.num_parts - 1)];
-        uint8_t left_modes[4] = {B_DC, B_DC, B_DC, B_DC};
-        uint8_t left_nz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        RowCtx rc;
+        row_ctx_reset(rc);
         for (int mb_x = 0; mb_x < mb_w; mb_x++) {
-            // -- modes (first partition) --
-            int segment = 0;
-            if (h.update_map)
-                segment = !bd_bit(br, h.seg_proba[0]) ? bd_bit(br, h.seg_proba[1]) : bd_bit(br, h.seg_proba[2]) + 2;
-            int skip = h.use_skip ? bd_bit(br, h.skip_p) : 0;
-            const int is_i4x4 = !bd_bit(br, 145);
-            uint8_t* tm = w.top_modes + mb_x * 4;
-            int ymode = DC_PRED;
-            if (!is_i4x4) {
-                ymode = bd_bit(br, 156) ? (bd_bit(br, 128) ? TM_PRED : H_PRED) : (bd_bit(br, 163) ? V_PRED : DC_PRED);
-                for (int i = 0; i < 4; i++) tm[i] = left_modes[i] = (uint8_t)ymode;
-            } else {
-                for (int by = 0; by < 4; by++) {
-                    int lm = left_modes[by];
-                    for (int bx = 0; bx < 4; bx++) {
-                        const uint8_t* prob = kVp8BModesProba[tm[bx]][lm];
-                        int i = kVp8YModesIntra4[bd_bit(br, prob[0])];
-                        while (i > 0) i = kVp8YModesIntra4[2 * i + bd_bit(br, prob[i])];
-                        lm = -i;
-                        tm[bx] = (uint8_t)lm;
-                        modes[by * 4 + bx] = (uint8_t)lm;
-                    }
-                    left_modes[by] = (uint8_t)lm;
-                }
-            }
-            const int uvmode = !bd_bit(br, 142) ? DC_PRED : !bd_bit(br, 114) ? V_PRED : bd_bit(br, 183) ? TM_PRED : H_PRED;
-
-            // -- residuals (token partition) --
-            uint8_t* tnz = w.top_nz + mb_x * 9;
-            const QuantMat& q = h.q[segment];
+            MbInfo mb;
+            const int skip = parse_mb_modes(h, br, w.top_modes + mb_x * 4, rc, mb);
             for (int i = 0; i < 25 * 16; i++) coeffs[i] = 0;
-            if (!skip) {
-                int first = 0, ytype = 3;
-                int any = 0;
-                if (!is_i4x4) {
-                    int16_t* dc = coeffs + 24 * 16;
-                    const int ctx = tnz[8] + left_nz[8];
-                    const int nz = get_coeffs(tbr, w.proba, 1, ctx, q.y2, 0, dc);
-                    tnz[8] = left_nz[8] = (uint8_t)(nz > 0);
-                    inverse_wht(dc, coeffs);
-                    first = 1;
-                    ytype = 0;
-                }
-                for (int by = 0; by < 4; by++) {
-                    int l = left_nz[by];
-                    for (int bx = 0; bx < 4; bx++) {
-                        const int ctx = l + tnz[bx];
-                        int16_t* blk = coeffs + (by * 4 + bx) * 16;
-                        const int nz = get_coeffs(tbr, w.proba, ytype, ctx, q.y1, first, blk);
-                        l = nz > first;
-                        tnz[bx] = (uint8_t)l;
-                        any |= (nz > 1) | (blk[0] != 0);  // the DC may come from the Y2 transform
-                    }
-                    left_nz[by] = (uint8_t)l;
-                }
-                for (int ch = 0; ch < 2; ch++) {
-                    for (int by = 0; by < 2; by++) {
-                        int l = left_nz[4 + ch * 2 + by];
-                        for (int bx = 0; bx < 2; bx++) {
-                            const int ctx = l + tnz[4 + ch * 2 + bx];
-                            int16_t* blk = coeffs + (16 + ch * 4 + by * 2 + bx) * 16;
-                            const int nz = get_coeffs(tbr, w.proba, 2, ctx, q.uv, 0, blk);
-                            l = nz > 0;
-                            tnz[4 + ch * 2 + bx] = (uint8_t)l;
-                            any |= (nz > 1) | (blk[0] != 0);
-                        }
-                        left_nz[4 + ch * 2 + by] = (uint8_t)l;
-                    }
-                }
-                skip = !any;
-            } else {
-                for (int i = 0; i < 8; i++) tnz[i] = left_nz[i] = 0;
-                if (!is_i4x4) tnz[8] = left_nz[8] = 0;
-            }
-            {
-                const FilterStrength& f = h.fs[segment][is_i4x4];
-                const uint32_t inner = f.inner | (uint32_t)(!skip);
-                w.finfo[mb_y * mb_w + mb_x] = f.limit | ((uint32_t)f.ilevel << 8) | ((uint32_t)f.hev << 16) | (inner << 24);
-            }
-
-            // -- prediction context (s.12.2 borders) --
-            uint8_t* yd = yb + BPS + 8;
-            uint8_t* ud = ub + BPS + 8;
-            uint8_t* vd = vb + BPS + 8;
-            uint8_t* py = w.y + (size_t)mb_y * 16 * ys + mb_x * 16;
-            uint8_t* pu = w.u + (size_t)mb_y * 8 * cs + mb_x * 8;
-            uint8_t* pv = w.v + (size_t)mb_y * 8 * cs + mb_x * 8;
-            if (mb_x > 0) {
-                for (int j = 0; j < 16; j++) yd[j * BPS - 1] = py[j * ys - 1];
-                for (int j = 0; j < 8; j++) {
-                    ud[j * BPS - 1] = pu[j * cs - 1];
-                    vd[j * BPS - 1] = pv[j * cs - 1];
-                }
-            } else {
-                for (int j = 0; j < 16; j++) yd[j * BPS - 1] = 129;
-                for (int j = 0; j < 8; j++) ud[j * BPS - 1] = vd[j * BPS - 1] = 129;
-            }
-            if (mb_y > 0) {
-                for (int i = 0; i < 16; i++) yd[i - BPS] = py[i - ys];
-                for (int i = 0; i < 8; i++) {
-                    ud[i - BPS] = pu[i - cs];
-                    vd[i - BPS] = pv[i - cs];
-                }
-                if (mb_x < mb_w - 1)
-                    for (int i = 16; i < 20; i++) yd[i - BPS] = py[i - ys];
-                else
-                    for (int i = 16; i < 20; i++) yd[i - BPS] = py[15 - ys];
-                if (mb_x > 0) {
-                    yd[-1 - BPS] = py[-1 - ys];
-                    ud[-1 - BPS] = pu[-1 - cs];
-                    vd[-1 - BPS] = pv[-1 - cs];
-                } else {
-                    yd[-1 - BPS] = ud[-1 - BPS] = vd[-1 - BPS] = 129;
-                }
-            } else {
-                for (int i = -1; i < 20; i++) yd[i - BPS] = 127;
-                for (int i = -1; i < 8; i++) ud[i - BPS] = vd[i - BPS] = 127;
-            }
-
-            // -- reconstruction --
-            if (is_i4x4) {
-                // the above-right samples of the macroblock serve every row of sub-blocks
-                for (int r = 1; r < 4; r++)
-                    for (int i = 16; i < 20; i++) yd[(4 * r - 1) * BPS + i] = yd[i - BPS];
-                for (int n = 0; n < 16; n++) {
-                    uint8_t* d = yd + (n >> 2) * 4 * BPS + (n & 3) * 4;
-                    pred_4x4(d, BPS, modes[n]);
-                    inverse_dct_add(coeffs + n * 16, d, BPS);
-                }
-            } else {
-                pred_block(yd, BPS, 16, ymode, mb_y > 0, mb_x > 0);
-                for (int n = 0; n < 16; n++) inverse_dct_add(coeffs + n * 16, yd + (n >> 2) * 4 * BPS + (n & 3) * 4, BPS);
-            }
-            pred_block(ud, BPS, 8, uvmode, mb_y > 0, mb_x > 0);
-            pred_block(vd, BPS, 8, uvmode, mb_y > 0, mb_x > 0);
-            for (int n = 0; n < 4; n++) {
-                inverse_dct_add(coeffs + (16 + n) * 16, ud + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
-                inverse_dct_add(coeffs + (20 + n) * 16, vd + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
-            }
-            for (int j = 0; j < 16; j++)
-                for (int i = 0; i < 16; i++) py[j * ys + i] = yd[j * BPS + i];
-            for (int j = 0; j < 8; j++)
-                for (int i = 0; i < 8; i++) {
-                    pu[j * cs + i] = ud[j * BPS + i];
-                    pv[j * cs + i] = vd[j * BPS + i];
-                }
+            parse_mb_residuals(h, tbr, w.proba, w.top_nz + mb_x * 9, rc, skip, mb, coeffs);
+            w.finfo[mb_y * mb_w + mb_x] = mb.finfo;
+            reconstruct_mb(h, w, mb_x, mb_y, mb, coeffs, yb, ub, vb);
         }
     }
     return VP8_OK;

@@ -1,5 +1,5 @@
 // webp_decode.cu -- lilliput's WebP decoder surface (include/lp_webp.h = ref webp.hpp:35-51,74-75)
-// on sm_100a: host RIFF walk, device VP8 key-frame decode, device upsample + colour conversion.
+// on sm_100a: host RIFF walk, device VP8 / VP8L / ALPH decode, device upsample + colour conversion.
 //
 // Replaces: webp_decoder_* (ref webp.cpp:61-370), i.e. libwebpmux's chunk walk
 // (WebPMuxCreate / GetFeatures / GetFrame / GetCanvasSize / GetAnimationParams / GetChunk "ICCP")
@@ -20,9 +20,11 @@
 #include "lp_webp.h"
 
 #define LP_VP8_FN static __device__
+#define LP_VP8_INL static __device__ __forceinline__
 #define LP_VP8_HD static __host__ __device__
 #define LP_VP8_TABLE static __device__ const
 #include "vp8_core.h"
+#include "vp8l_core.h"
 
 namespace lp {
 
@@ -99,28 +101,198 @@ __device__ void filter_macroblock_warp(const vp8::FrameHdr& h, vp8::Work& w, int
 
 constexpr int kVp8WarpsPerBlock = 4;
 
+// Per-warp shared state of the decode kernel.
+struct Vp8WarpSmem {
+    vp8::FrameHdr hdr;
+    vp8::MbInfo mb;
+    alignas(16) int16_t coeffs[25 * 16];
+    alignas(16) uint8_t yb[vp8::YB_SIZE];
+    alignas(16) uint8_t ub[vp8::CB_SIZE];
+    alignas(16) uint8_t vb[vp8::CB_SIZE];
+};
+
+// 16x16 / 8x8 prediction spread over lanes: `dst` block of `size`, this lane fills `n` pixels
+// starting at (row, col).  The DC sum arrives pre-reduced.
+__device__ __forceinline__ void pred_span(uint8_t* dst, int size, int mode, int row, int col, int n, int dc) {
+    uint8_t* d = dst + row * vp8::BPS + col;
+    if (mode == vp8::DC_PRED) {
+        for (int i = 0; i < n; i++) d[i] = (uint8_t)dc;
+    } else if (mode == vp8::TM_PRED) {
+        const uint8_t* top = dst - vp8::BPS;
+        const int l = dst[row * vp8::BPS - 1] - top[-1];
+        for (int i = 0; i < n; i++) d[i] = vp8::clip8(top[col + i] + l);
+    } else if (mode == vp8::V_PRED) {
+        const uint8_t* top = dst - vp8::BPS;
+        for (int i = 0; i < n; i++) d[i] = top[col + i];
+    } else {
+        const uint8_t l = dst[row * vp8::BPS - 1];
+        for (int i = 0; i < n; i++) d[i] = l;
+    }
+}
+
+// Sum over a group of `width` consecutive lanes (width = 16 or 32), result in every lane of it.
+__device__ __forceinline__ int group_sum(int v, int width) {
+    for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Reconstructs one parsed macroblock with the whole warp (same arithmetic as vp8::reconstruct_mb).
+__device__ void reconstruct_mb_warp(Vp8WarpSmem& sm, vp8::Work& w, int mb_x, int mb_y, int lane) {
+    using namespace vp8;
+    const FrameHdr& h = sm.hdr;
+    const MbInfo& mb = sm.mb;
+    const int mb_w = h.mb_w, ys = mb_w * 16, cs = mb_w * 8;
+    uint8_t* yd = sm.yb + BPS + 8;
+    uint8_t* ud = sm.ub + BPS + 8;
+    uint8_t* vd = sm.vb + BPS + 8;
+    uint8_t* py = w.y + (size_t)mb_y * 16 * ys + mb_x * 16;
+    uint8_t* pu = w.u + (size_t)mb_y * 8 * cs + mb_x * 8;
+    uint8_t* pv = w.v + (size_t)mb_y * 8 * cs + mb_x * 8;
+    const bool have_top = mb_y > 0, have_left = mb_x > 0;
+    // ---- borders (s.12.2) ----
+    if (lane < 16) {
+        yd[lane * BPS - 1] = have_left ? py[lane * ys - 1] : 129;
+    } else {
+        const int j = lane & 7;
+        uint8_t* cd = lane < 24 ? ud : vd;
+        const uint8_t* pc = lane < 24 ? pu : pv;
+        cd[j * BPS - 1] = have_left ? pc[j * cs - 1] : 129;
+    }
+    if (lane < 21) {  // luma: top-left, 16 above, 4 above-right
+        const int i = lane - 1;
+        uint8_t v = 127;
+        if (have_top) {
+            if (i < 0) v = have_left ? py[-1 - ys] : 129;
+            else if (i < 16 || mb_x < mb_w - 1) v = py[i - ys];
+            else v = py[15 - ys];
+        }
+        yd[i - BPS] = v;
+    }
+    {
+        const int i = (lane & 15) - 1;  // chroma: top-left + 8 above, U on lanes 0..8, V on 16..24
+        if (i < 8) {
+            uint8_t* cd = lane < 16 ? ud : vd;
+            const uint8_t* pc = lane < 16 ? pu : pv;
+            uint8_t v = 127;
+            if (have_top) v = i < 0 ? (have_left ? pc[-1 - cs] : 129) : pc[i - cs];
+            cd[i - BPS] = v;
+        }
+    }
+    __syncwarp();
+    // ---- luma prediction ----
+    if (!mb.is_i4x4) {
+        int dc = 0x80;
+        if (mb.ymode == DC_PRED) {
+            int v = 0;
+            if (lane < 16) v = have_top ? yd[lane - BPS] : 0;
+            else v = have_left ? yd[(lane - 16) * BPS - 1] : 0;
+            const int s = group_sum(v, 32);
+            if (have_top && have_left) dc = (s + 16) >> 5;
+            else if (have_top || have_left) dc = (s + 8) >> 4;
+        }
+        pred_span(yd, 16, mb.ymode, lane >> 1, (lane & 1) * 8, 8, dc);
+    } else if (lane == 0) {
+        for (int r = 1; r < 4; r++)
+            for (int i = 16; i < 20; i++) yd[(4 * r - 1) * BPS + i] = yd[i - BPS];
+        for (int n = 0; n < 16; n++) {
+            uint8_t* d = yd + (n >> 2) * 4 * BPS + (n & 3) * 4;
+            pred_4x4(d, BPS, mb.modes[n]);
+            if ((mb.nz_blocks >> n) & 1) inverse_dct_add(sm.coeffs + n * 16, d, BPS);
+        }
+    }
+    // ---- chroma prediction: U on lanes 0..15, V on 16..31, 4 pixels each ----
+    {
+        uint8_t* cd = lane < 16 ? ud : vd;
+        const int l = lane & 15;
+        int dc = 0x80;
+        if (mb.uvmode == DC_PRED) {
+            int v = 0;
+            if (l < 8) v = have_top ? cd[l - BPS] : 0;
+            else v = have_left ? cd[(l - 8) * BPS - 1] : 0;
+            const int s = group_sum(v, 16);
+            if (have_top && have_left) dc = (s + 8) >> 4;
+            else if (have_top || have_left) dc = (s + 4) >> 3;
+        }
+        pred_span(cd, 8, mb.uvmode, l >> 1, (l & 1) * 4, 4, dc);
+    }
+    __syncwarp();
+    // ---- residuals: one 4x4 block per lane (i4x4 luma was added in order above) ----
+    if (lane < 24 && ((mb.nz_blocks >> lane) & 1) && !(mb.is_i4x4 && lane < 16)) {
+        uint8_t* d;
+        if (lane < 16) d = yd + (lane >> 2) * 4 * BPS + (lane & 3) * 4;
+        else {
+            const int n = lane & 3;
+            d = (lane < 20 ? ud : vd) + (n >> 1) * 4 * BPS + (n & 1) * 4;
+        }
+        inverse_dct_add(sm.coeffs + lane * 16, d, BPS);
+    }
+    __syncwarp();
+    // ---- store: luma row per lane 0..15, chroma row per lane 16..31 ----
+    if (lane < 16) {
+        const uint2 a = *reinterpret_cast<const uint2*>(yd + lane * BPS);
+        const uint2 b = *reinterpret_cast<const uint2*>(yd + lane * BPS + 8);
+        *reinterpret_cast<uint4*>(py + (size_t)lane * ys) = make_uint4(a.x, a.y, b.x, b.y);
+    } else {
+        const int j = lane & 7;
+        const uint8_t* cd = lane < 24 ? ud : vd;
+        uint8_t* pc = lane < 24 ? pu : pv;
+        *reinterpret_cast<uint2*>(pc + (size_t)j * cs) = *reinterpret_cast<const uint2*>(cd + j * BPS);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kVp8WarpsPerBlock * 32) vp8_decode_kernel(const Vp8Item* items, int n) {
-    __shared__ vp8::FrameHdr s_hdr[kVp8WarpsPerBlock];
+    __shared__ Vp8WarpSmem s_warp[kVp8WarpsPerBlock];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int idx = blockIdx.x * kVp8WarpsPerBlock + wid;
     if (idx >= n) return;
     const Vp8Item it = items[idx];
-    vp8::FrameHdr& h = s_hdr[wid];
+    Vp8WarpSmem& sm = s_warp[wid];
+    vp8::FrameHdr& h = sm.hdr;
     vp8::Work w;
     vp8::work_carve(it.work, it.mb_w, it.mb_h, w);
     int st = 0;
+    vp8::BoolDec br;        // first partition (lane 0)
+    vp8::BoolDec parts[8];  // token partitions (lane 0)
     if (lane == 0) {
-        vp8::BoolDec br;
         st = vp8::parse_frame_header(it.data, it.size, h, br, w.proba);
         if (!st && (h.mb_w != it.mb_w || h.mb_h != it.mb_h)) st = vp8::VP8_BAD;
-        if (!st) st = vp8::decode_macroblocks(it.data, h, br, w);
-        *it.status = st;
+        if (!st)
+            for (int p = 0; p < h.num_parts; p++) vp8::bd_init(parts[p], it.data + h.part_off[p], h.part_len[p]);
+        if (st) *it.status = st;  // zeroed by the launcher; an ALPH error must survive
     }
     st = __shfl_sync(0xffffffffu, st, 0);
     __syncwarp();
-    if (st || h.filter_type == 0) return;
-    for (int mb_y = 0; mb_y < h.mb_h; mb_y++)
-        for (int mb_x = 0; mb_x < h.mb_w; mb_x++) filter_macroblock_warp(h, w, mb_x, mb_y, lane);
+    if (st) return;
+    const int mb_w = h.mb_w, mb_h = h.mb_h;
+    for (int i = lane; i < mb_w * 4; i += 32) w.top_modes[i] = vp8::B_DC;
+    for (int i = lane; i < mb_w * 9; i += 32) w.top_nz[i] = 0;
+    __syncwarp();
+    uint32_t* cz = reinterpret_cast<uint32_t*>(sm.coeffs);
+    for (int mb_y = 0; mb_y < mb_h; mb_y++) {
+        vp8::RowCtx rc;
+        vp8::BoolDec tbr;
+        if (lane == 0) {
+            vp8::row_ctx_reset(rc);
+            tbr = parts[mb_y & (h.num_parts - 1)];
+        }
+        for (int mb_x = 0; mb_x < mb_w; mb_x++) {
+            for (int i = lane; i < 25 * 8; i += 32) cz[i] = 0;
+            __syncwarp();
+            if (lane == 0) {
+                const int skip = vp8::parse_mb_modes(h, br, w.top_modes + mb_x * 4, rc, sm.mb);
+                vp8::parse_mb_residuals(h, tbr, w.proba, w.top_nz + mb_x * 9, rc, skip, sm.mb, sm.coeffs);
+                w.finfo[mb_y * mb_w + mb_x] = sm.mb.finfo;
+            }
+            __syncwarp();
+            reconstruct_mb_warp(sm, w, mb_x, mb_y, lane);
+        }
+        if (lane == 0) parts[mb_y & (h.num_parts - 1)] = tbr;
+    }
+    __syncwarp();
+    if (h.filter_type == 0) return;
+    for (int mb_y = 0; mb_y < mb_h; mb_y++)
+        for (int mb_x = 0; mb_x < mb_w; mb_x++) filter_macroblock_warp(h, w, mb_x, mb_y, lane);
 }
 
 struct Vp8Output {
@@ -145,6 +317,49 @@ __global__ void vp8_output_kernel(Vp8Output o) {
     d[1] = bgr[1];
     d[2] = bgr[2];
     if (o.channels == 4) d[3] = o.alpha ? o.alpha[(size_t)y * o.width + x] : 255;
+}
+
+// VP8L (lossless) frames and ALPH planes: an LZ77 + prefix-coded stream is one serial chain, so
+// one thread walks it (vp8l_core.h) inside a bump arena in HBM; the colour-order conversion to the
+// mat is a separate, parallel kernel.
+struct Vp8lItem {
+    const uint8_t* data;   // "VP8L" chunk payload, or "ALPH" chunk payload
+    uint32_t size;
+    int width, height;
+    uint8_t* arena;
+    size_t arena_cap;
+    int is_alph;
+    uint8_t* alpha_out;    // is_alph: width*height plane
+    uint32_t** px_out;     // !is_alph: where to leave the pointer to the final ARGB pixels
+    int* status;
+};
+
+__global__ void vp8l_decode_kernel(Vp8lItem it) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    vp8l::Arena a{it.arena, it.arena_cap, 0};
+    int rc;
+    if (it.is_alph) {
+        rc = vp8l::decode_alph(it.data, it.size, it.width, it.height, a, it.alpha_out);
+    } else {
+        uint32_t* px = nullptr;
+        rc = vp8l::decode_vp8l(it.data, it.size, it.width, it.height, a, &px);
+        *it.px_out = px;
+    }
+    if (rc) *it.status = rc;
+}
+
+__global__ void argb_output_kernel(uint32_t* const* px_ptr, int width, int height, uint8_t* dst, size_t dst_step,
+                                   int channels) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const uint32_t* px = *px_ptr;
+    if (x >= width || !px) return;
+    const uint32_t v = px[(size_t)y * width + x];
+    uint8_t* d = dst + (size_t)y * dst_step + (size_t)x * channels;
+    d[0] = (uint8_t)v;
+    d[1] = (uint8_t)(v >> 8);
+    d[2] = (uint8_t)(v >> 16);
+    if (channels == 4) d[3] = (uint8_t)(v >> 24);
 }
 
 // ------------------------------------------------------------------ container walk (host)
@@ -356,7 +571,11 @@ struct webp_decoder_struct {
     uint8_t* d_work = nullptr;
     Vp8Item* d_item = nullptr;
     int* d_status = nullptr;
-    size_t in_cap = 0, work_cap = 0;
+    uint8_t* d_arena = nullptr;   // VP8L / ALPH bump arena
+    uint8_t* d_alpha = nullptr;   // decoded ALPH plane
+    uint8_t* d_alph_in = nullptr; // ALPH chunk bytes
+    uint32_t** d_px = nullptr;    // where the VP8L kernel leaves its result pointer
+    size_t in_cap = 0, work_cap = 0, arena_cap = 0, alpha_cap = 0, alph_in_cap = 0;
 };
 
 struct webp_encoder_struct {
@@ -422,6 +641,10 @@ void webp_decoder_release(webp_decoder d) {
     if (d->d_work) cudaFreeAsync(d->d_work, st);
     if (d->d_item) cudaFreeAsync(d->d_item, st);
     if (d->d_status) cudaFreeAsync(d->d_status, st);
+    if (d->d_arena) cudaFreeAsync(d->d_arena, st);
+    if (d->d_alpha) cudaFreeAsync(d->d_alpha, st);
+    if (d->d_alph_in) cudaFreeAsync(d->d_alph_in, st);
+    if (d->d_px) cudaFreeAsync(d->d_px, st);
     cudaStreamSynchronize(st);
     delete d;
 }
@@ -441,37 +664,58 @@ bool webp_decoder_decode(const webp_decoder d, opencv_mat mat) {
     d->prev_dispose = f.dispose;
     d->prev_blend = f.blend;
     d->prev_has_alpha = f.has_alpha;
-    if (f.lossless) return false;                 // VP8L: not decoded on the device yet
-    if (f.has_alph && type == CV_8UC4) return false;  // ALPH plane: not decoded yet
-
     cudaStream_t st = thread_stream();
-    const int mb_w = (f.width + 15) >> 4, mb_h = (f.height + 15) >> 4;
-    const size_t need_work = vp8::work_bytes(mb_w, mb_h);
+    const int channels = type == CV_8UC4 ? 4 : 3;
+    auto grow = [&](uint8_t** p, size_t* cap, size_t need) -> bool {
+        if (need <= *cap) return true;
+        if (*p) cudaFreeAsync(*p, st);
+        *cap = need;
+        return cudaMallocAsync(p, need, st) == cudaSuccess;
+    };
     if (!d->d_item) {
         if (cudaMallocAsync(&d->d_item, sizeof(Vp8Item), st) != cudaSuccess) return false;
         if (cudaMallocAsync(&d->d_status, sizeof(int), st) != cudaSuccess) return false;
+        if (cudaMallocAsync(&d->d_px, sizeof(uint32_t*), st) != cudaSuccess) return false;
     }
-    if (f.img_len + 16 > d->in_cap) {
-        if (d->d_in) cudaFreeAsync(d->d_in, st);
-        d->in_cap = f.img_len + 4096;
-        if (cudaMallocAsync(&d->d_in, d->in_cap, st) != cudaSuccess) return false;
-    }
-    if (need_work > d->work_cap) {
-        if (d->d_work) cudaFreeAsync(d->d_work, st);
-        d->work_cap = need_work;
-        if (cudaMallocAsync(&d->d_work, d->work_cap, st) != cudaSuccess) return false;
-    }
+    cudaMemsetAsync(d->d_status, 0, sizeof(int), st);
+    cudaMemsetAsync(d->d_px, 0, sizeof(uint32_t*), st);
+    if (!grow(&d->d_in, &d->in_cap, f.img_len + 4096)) return false;
     cudaMemcpyAsync(d->d_in, d->bytes + f.img_off, f.img_len, cudaMemcpyHostToDevice, st);
-    Vp8Item item{d->d_in, (uint32_t)f.img_len, d->d_work, d->d_status, mb_w, mb_h};
-    cudaMemcpyAsync(d->d_item, &item, sizeof(item), cudaMemcpyHostToDevice, st);
-    vp8_decode_kernel<<<1, kVp8WarpsPerBlock * 32, 0, st>>>(d->d_item, 1);
-    g_launches++;
-    vp8::Work w;
-    vp8::work_carve(d->d_work, mb_w, mb_h, w);
-    Vp8Output o{w.y, w.u, w.v, nullptr, mb_w * 16, mb_w * 8, f.width, f.height, frame_dev, frame_step, type == CV_8UC4 ? 4 : 3};
-    dim3 grid(ceil_div(f.width, 128), f.height);
-    vp8_output_kernel<<<grid, 128, 0, st>>>(o);
-    g_launches++;
+    const size_t npix = (size_t)f.width * f.height;
+    const size_t arena_need = npix * 12 + (16u << 20);
+    const bool need_alph = f.has_alph && !f.lossless && channels == 4;
+    if (f.lossless || need_alph) {
+        if (!grow(&d->d_arena, &d->arena_cap, arena_need)) return false;
+    }
+    if (f.lossless) {
+        Vp8lItem li{d->d_in, (uint32_t)f.img_len, f.width, f.height, d->d_arena, d->arena_cap, 0, nullptr, d->d_px, d->d_status};
+        vp8l_decode_kernel<<<1, 32, 0, st>>>(li);
+        g_launches++;
+        dim3 grid(ceil_div(f.width, 128), f.height);
+        argb_output_kernel<<<grid, 128, 0, st>>>(d->d_px, f.width, f.height, frame_dev, frame_step, channels);
+        g_launches++;
+    } else {
+        const int mb_w = (f.width + 15) >> 4, mb_h = (f.height + 15) >> 4;
+        if (!grow(&d->d_work, &d->work_cap, vp8::work_bytes(mb_w, mb_h))) return false;
+        if (need_alph) {
+            if (!grow(&d->d_alph_in, &d->alph_in_cap, f.alph_len + 4096)) return false;
+            if (!grow(&d->d_alpha, &d->alpha_cap, npix + 256)) return false;
+            cudaMemcpyAsync(d->d_alph_in, d->bytes + f.alph_off, f.alph_len, cudaMemcpyHostToDevice, st);
+            Vp8lItem ai{d->d_alph_in, (uint32_t)f.alph_len, f.width, f.height, d->d_arena, d->arena_cap, 1, d->d_alpha, nullptr, d->d_status};
+            vp8l_decode_kernel<<<1, 32, 0, st>>>(ai);
+            g_launches++;
+        }
+        Vp8Item item{d->d_in, (uint32_t)f.img_len, d->d_work, d->d_status, mb_w, mb_h};
+        cudaMemcpyAsync(d->d_item, &item, sizeof(item), cudaMemcpyHostToDevice, st);
+        vp8_decode_kernel<<<1, kVp8WarpsPerBlock * 32, 0, st>>>(d->d_item, 1);
+        g_launches++;
+        vp8::Work w;
+        vp8::work_carve(d->d_work, mb_w, mb_h, w);
+        Vp8Output o{w.y, w.u, w.v, need_alph ? d->d_alpha : nullptr, mb_w * 16, mb_w * 8, f.width, f.height, frame_dev, frame_step, channels};
+        dim3 grid(ceil_div(f.width, 128), f.height);
+        vp8_output_kernel<<<grid, 128, 0, st>>>(o);
+        g_launches++;
+    }
     int status = 0;
     cudaMemcpyAsync(&status, d->d_status, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) return false;

@@ -39,3 +39,29 @@ extern "C" int vp8_cpu_decode_bgr(const uint8_t* d, size_t n, uint8_t* out, int 
         }
     return 0;
 }
+
+// ---- VP8L (lossless) and ALPH, same idea ---------------------------------------------------
+#include "../../lilliput_b200/csrc/vp8l_core.h"
+
+// Decodes a "VP8L" chunk payload to BGRA (channels = 4) or BGR (3).
+extern "C" int vp8l_cpu_decode(const uint8_t* d, size_t n, int w, int h, uint8_t* out, int channels) {
+    std::vector<uint8_t> mem((size_t)w * h * 16 + (32u << 20));
+    vp8l::Arena a{mem.data(), mem.size(), 0};
+    uint32_t* px = nullptr;
+    const int rc = vp8l::decode_vp8l(d, n, w, h, a, &px);
+    if (rc) return rc;
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        out[i * channels + 0] = (uint8_t)px[i];
+        out[i * channels + 1] = (uint8_t)(px[i] >> 8);
+        out[i * channels + 2] = (uint8_t)(px[i] >> 16);
+        if (channels == 4) out[i * 4 + 3] = (uint8_t)(px[i] >> 24);
+    }
+    return 0;
+}
+
+// Decodes an "ALPH" chunk payload to a w*h alpha plane.
+extern "C" int alph_cpu_decode(const uint8_t* d, size_t n, int w, int h, uint8_t* alpha) {
+    std::vector<uint8_t> mem((size_t)w * h * 16 + (32u << 20));
+    vp8l::Arena a{mem.data(), mem.size(), 0};
+    return vp8l::decode_alph(d, n, w, h, a, alpha);
+}

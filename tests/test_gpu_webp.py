@@ -1,4 +1,4 @@
-"""GPU: WebP decode (host RIFF walk + device VP8 key-frame decode + device upsample/colour) through
+"""GPU: WebP decode (host RIFF walk + device VP8 / VP8L / ALPH decode + device upsample/colour) through
 the webp_decoder_* ABI vs what the reference's webp.cpp returns for the same bytes (golden frames
 made through oracle/_ref).  Bit-exact, frame by frame, metadata included."""
 import hashlib
@@ -12,10 +12,6 @@ from tests.webp_util import webp_golden
 pytestmark = pytest.mark.gpu
 G = webp_golden()
 NAMES = [str(n) for n in G["webp_names"]]
-# Frames the device path does not decode yet (VP8L bitstreams, ALPH planes): see include/lp_webp.h
-NOT_YET = {"lossy_alpha", "lossy_alpha_raw", "lossless_rgb", "lossless_rgba", "fixture_party-discord",
-           "fixture_animated-webp-supported"}
-
 
 @pytest.mark.parametrize("name", NAMES)
 def test_webp_frames_match_reference(cuda_lib, name):
@@ -27,9 +23,6 @@ def test_webp_frames_match_reference(cuda_lib, name):
         return
     keys = ("width", "height", "pixel_type", "num_frames", "total_duration", "loop_count", "bg_color", "icc_len")
     assert [info[k] for k in keys] == [int(v) for v in G[f"webpinfo_{name}"]]
-    if name in NOT_YET:
-        assert rc == abi.LP_ERR_DECODING_FAILED and len(frames) == 0
-        return
     assert rc == rc_ref and len(frames) == n_ref
     meta = G[f"webpmeta_{name}"]
     for i, (f, m) in enumerate(zip(frames, metas)):

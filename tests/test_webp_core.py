@@ -7,7 +7,8 @@ import hashlib
 import numpy as np
 import pytest
 
-from tests.webp_util import chunks_of, vp8_cpu_decode, vp8_cpu_lib, webp_golden
+from tests.webp_util import (alph_cpu_decode, chunks_of, frames_of, vp8_cpu_decode, vp8_cpu_lib, vp8l_cpu_decode,
+                             webp_golden)
 
 G = webp_golden()
 LOSSY = [n for n in G["webp_names"] if n.startswith("lossy") and "alpha" not in n] + \
@@ -43,3 +44,31 @@ def test_vp8_core_against_reference_library_sweep(cpu, ref_lib):
         assert rc == 0
         got = vp8_cpu_decode(cpu, dict(chunks_of(data))[b"VP8 "])
         assert np.array_equal(got, frames[0])
+
+
+MIXED = ["lossless_rgb", "lossless_rgba", "lossy_alpha", "lossy_alpha_raw", "fixture_party-discord",
+         "fixture_animated-webp-supported"]
+
+
+@pytest.mark.parametrize("name", MIXED)
+def test_vp8l_and_alph_core_match_reference_frames(cpu, name):
+    """VP8L frames, and lossy frames with an ALPH plane (raw or VP8L-coded, filtered), frame by
+    frame: colour from the VP8 / VP8L core, alpha from the ALPH core, against the reference's output."""
+    data = G[f"webp_{name}"].tobytes()
+    meta = G[f"webpmeta_{name}"]
+    sha = G[f"webpsha_{name}"]
+    frames = frames_of(data)
+    assert len(frames) == len(sha)
+    for i, (tag, payload, alph) in enumerate(frames):
+        w, h, ch = [int(v) for v in meta[i][:3]]
+        if tag == b"VP8L":
+            got = vp8l_cpu_decode(cpu, payload, w, h, ch)
+        else:
+            bgr = vp8_cpu_decode(cpu, payload)
+            if ch == 4:
+                a = alph_cpu_decode(cpu, alph, w, h) if alph is not None else np.full((h, w), 255, np.uint8)
+                got = np.dstack([bgr, a])
+            else:
+                got = bgr
+        assert got.shape == (h, w, ch)
+        assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == str(sha[i]), f"frame {i}"

@@ -30,7 +30,8 @@ def vp8_cpu_lib():
     so = os.path.join(_BUILD, "libvp8cpu.so")
     srcs = [os.path.join(ROOT, "tests", "native", "vp8_cpu.cpp"),
             os.path.join(ROOT, "lilliput_b200", "csrc", "vp8_core.h"),
-            os.path.join(ROOT, "lilliput_b200", "csrc", "vp8_tables.h")]
+            os.path.join(ROOT, "lilliput_b200", "csrc", "vp8_tables.h"),
+            os.path.join(ROOT, "lilliput_b200", "csrc", "vp8l_core.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, srcs[0]])
     return ctypes.CDLL(so)
@@ -43,5 +44,40 @@ def vp8_cpu_decode(lib, payload: bytes) -> np.ndarray:
     assert lib.vp8_cpu_info(p, ctypes.c_size_t(arr.size), ctypes.byref(w), ctypes.byref(h)) == 0
     out = np.zeros((h.value, w.value, 3), np.uint8)
     rc = lib.vp8_cpu_decode_bgr(p, ctypes.c_size_t(arr.size), out.ctypes.data_as(ctypes.c_void_p), w.value * 3, 0, None)
+    assert rc == 0, rc
+    return out
+
+
+def frames_of(webp: bytes):
+    """[(image_tag, image_payload, alph_payload or None)] for every frame of a still or animated file."""
+    out = []
+    for tag, payload in chunks_of(webp):
+        if tag == b"ANMF":
+            sub = chunks_of(b"\0" * 12 + payload[16:])
+            alph = next((p for t, p in sub if t == b"ALPH"), None)
+            img = next(((t, p) for t, p in sub if t in (b"VP8 ", b"VP8L")))
+            out.append((img[0], img[1], alph))
+    if not out:
+        top = chunks_of(webp)
+        alph = next((p for t, p in top if t == b"ALPH"), None)
+        img = next(((t, p) for t, p in top if t in (b"VP8 ", b"VP8L")))
+        out.append((img[0], img[1], alph))
+    return out
+
+
+def vp8l_cpu_decode(lib, payload: bytes, w: int, h: int, channels: int) -> np.ndarray:
+    arr = np.frombuffer(payload, np.uint8)
+    out = np.zeros((h, w, channels), np.uint8)
+    rc = lib.vp8l_cpu_decode(arr.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arr.size), w, h,
+                             out.ctypes.data_as(ctypes.c_void_p), channels)
+    assert rc == 0, rc
+    return out
+
+
+def alph_cpu_decode(lib, payload: bytes, w: int, h: int) -> np.ndarray:
+    arr = np.frombuffer(payload, np.uint8)
+    out = np.zeros((h, w), np.uint8)
+    rc = lib.alph_cpu_decode(arr.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arr.size), w, h,
+                             out.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0, rc
     return out

@@ -64,3 +64,19 @@ def test_webp_with_icc_transforms_like_the_reference(cuda_lib, oracle):
 def test_webp_header_fields(cuda_lib):
     w, h, ptype, _ = cuda_lib.header(G["webp_fixture_tears_of_steel_no_icc"].tobytes())[:4]
     assert (w, h) == (1920, 800)
+
+
+@pytest.mark.parametrize("name", ["fixture_party-discord", "fixture_animated-webp-supported", "anim_lossy",
+                                  "lossy_alpha", "lossless_rgba"])
+def test_animated_and_alpha_webp_transform_matches_reference_library(cuda_lib, ref_lib, oracle, name):
+    """Whole ImageOps.Transform with a WebP source (ops.go:352-444: animated sources composite into
+    the canvas first, single-frame encoders stop after frame 1) against the reference library
+    itself: JPEG byte-identical, PNG pixel-identical."""
+    data = G[f"webp_{name}"].tobytes()
+    jopt = abi.ImageOptions(FileType=".jpeg", Width=24, Height=16, ResizeMethod=abi.ImageOpsFit,
+                            EncodeOptions={abi.JpegQuality: 90})
+    assert cuda_lib.transform(data, jopt) == ref_lib.transform(data, jopt)
+    popt = abi.ImageOptions(FileType=".png", Width=20, Height=12, ResizeMethod=abi.ImageOpsResize,
+                            EncodeOptions={abi.PngCompression: 7})
+    assert np.array_equal(oracle.png_decode(cuda_lib.transform(data, popt)),
+                          oracle.png_decode(ref_lib.transform(data, popt)))

@@ -162,10 +162,20 @@ static int sync_stream() {
 // Decode one baseline JPEG into m (device mirror).  Used by opencv_decoder_read_data.
 static int decode_jpeg_into(const Decoder* d, Mat* m) {
     const JpegHeader& h = d->jpeg;
-    if (!h.supported) {
-        fprintf(stderr, "[lilliput_b200] JPEG variant not supported on the device path (%s)\n",
-                h.progressive ? "progressive" : "sampling/scan layout");
+    if (!h.supported && !h.multiscan) {
+        fprintf(stderr, "[lilliput_b200] JPEG variant not supported on the device path (sampling layout)\n");
         return LP_ERR_UNSUPPORTED;
+    }
+    // multi-scan files (progressive, or one scan per component): the scans and the tables in force
+    std::vector<JpegScanDesc> scans;
+    std::vector<JpegHuffSet> sets;
+    int nscans = 0, nsets = 0;
+    if (h.multiscan) {
+        scans.resize(256);
+        sets.resize(64);
+        int rc = jpeg_parse_scans(d->data, d->len, h, scans.data(), (int)scans.size(), &nscans, sets.data(),
+                                  (int)sets.size(), &nsets);
+        if (rc) return rc;
     }
     cudaStream_t st = thread_stream();
     JpegDecodeItem it;
@@ -197,29 +207,39 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
     jpeg_build_huff_set(h, &hs);
 
     uint8_t* scratch = nullptr;
-    const size_t scan_bytes = round_up((size_t)h.scan_length + 16, (size_t)256);
+    const size_t upload_len = h.multiscan ? d->len : h.scan_length;  // multi-scan: the whole file
+    const size_t scan_bytes = round_up(upload_len + 16, (size_t)256);
+    const size_t sets_b = round_up(sizeof(JpegHuffSet) * (size_t)(h.multiscan ? nsets : 1), (size_t)256);
+    const size_t scans_b = round_up(sizeof(JpegScanDesc) * (size_t)nscans + 16, (size_t)256);
     const size_t coef_bytes = round_up((size_t)blocks * 64 * sizeof(int16_t), (size_t)256);
     const size_t plane_b = round_up((size_t)plane_bytes, (size_t)256);
-    const bool parallel = h.restart_interval == 0;
+    const bool parallel = h.restart_interval == 0 && !h.multiscan;
     const size_t clean_b = parallel ? round_up(huff_clean_bytes(h.scan_length), (size_t)256) : 0;
     const size_t states_b = parallel ? round_up(2 * huff_nsub(h.scan_length) * 8, (size_t)256) : 0;
     const size_t nslots_b = parallel ? round_up(2 * huff_nsub(h.scan_length) * 4, (size_t)256) : 0;
     const size_t dcdiff_b = parallel ? round_up((size_t)total_blocks * 2, (size_t)256) : 0;
-    const size_t total = 1024 + round_up(sizeof(JpegHuffSet), (size_t)256) + scan_bytes + coef_bytes + plane_b +
-                         clean_b + states_b + nslots_b + dcdiff_b;
+    const size_t total = 1024 + sets_b + scan_bytes + coef_bytes + plane_b + clean_b + states_b + nslots_b +
+                         dcdiff_b + scans_b;
     LP_CUDA_OK(cudaMallocAsync(&scratch, total, st));
     JpegDecodeItem* d_item = reinterpret_cast<JpegDecodeItem*>(scratch);
     JpegHuffSet* d_hs = reinterpret_cast<JpegHuffSet*>(scratch + 1024);
-    uint8_t* d_scan = scratch + 1024 + round_up(sizeof(JpegHuffSet), (size_t)256);
+    uint8_t* d_scan = scratch + 1024 + sets_b;
     int16_t* d_coef = reinterpret_cast<int16_t*>(d_scan + scan_bytes);
     uint8_t* d_planes = reinterpret_cast<uint8_t*>(d_coef) + coef_bytes;
     uint8_t* d_clean = d_planes + plane_b;
     uint8_t* d_states = d_clean + clean_b;
     uint8_t* d_nslots = d_states + states_b;
     uint8_t* d_dcdiff = d_nslots + nslots_b;
+    JpegScanDesc* d_scans = reinterpret_cast<JpegScanDesc*>(d_dcdiff + dcdiff_b);
     LP_CUDA_OK(cudaMemcpyAsync(d_item, &it, sizeof(it), cudaMemcpyHostToDevice, st));
-    LP_CUDA_OK(cudaMemcpyAsync(d_hs, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
-    LP_CUDA_OK(cudaMemcpyAsync(d_scan, d->data + h.scan_offset, h.scan_length, cudaMemcpyHostToDevice, st));
+    if (h.multiscan) {
+        LP_CUDA_OK(cudaMemcpyAsync(d_hs, sets.data(), sizeof(JpegHuffSet) * nsets, cudaMemcpyHostToDevice, st));
+        LP_CUDA_OK(cudaMemcpyAsync(d_scans, scans.data(), sizeof(JpegScanDesc) * nscans, cudaMemcpyHostToDevice, st));
+        LP_CUDA_OK(cudaMemcpyAsync(d_scan, d->data, d->len, cudaMemcpyHostToDevice, st));
+    } else {
+        LP_CUDA_OK(cudaMemcpyAsync(d_hs, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+        LP_CUDA_OK(cudaMemcpyAsync(d_scan, d->data + h.scan_offset, h.scan_length, cudaMemcpyHostToDevice, st));
+    }
     JpegDecodeBatch b;
     b.items = d_item;
     b.tables = d_hs;
@@ -237,6 +257,10 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
     b.states = d_states;
     b.nslots = reinterpret_cast<uint32_t*>(d_nslots);
     b.dcdiff = reinterpret_cast<int16_t*>(d_dcdiff);
+    if (h.multiscan) {
+        b.scans = d_scans;
+        b.nscans = nscans;
+    }
     int rc = jpeg_decode_launch(b, st, nullptr);
     JpegDecodeItem back;
     if (!rc) {
@@ -251,10 +275,6 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
 // Decode one PNG into m (device mirror).  Used by opencv_decoder_read_data.
 static int decode_png_into(const Decoder* d, Mat* m) {
     const PngHeader& h = d->png;
-    if (h.interlace) {
-        fprintf(stderr, "[lilliput_b200] interlaced PNG is not supported on the device path\n");
-        return LP_ERR_UNSUPPORTED;
-    }
     if (h.idat_total < 2) return LP_ERR_DECODING_FAILED;
     cudaStream_t st = thread_stream();
     PngDecodeItem it;
@@ -269,6 +289,8 @@ static int decode_png_into(const Decoder* d, Mat* m) {
     it.bpp = h.bpp;
     it.row_bytes = (uint32_t)h.row_bytes;
     it.frame_stride = (uint32_t)m->dev_step;
+    it.interlace = h.interlace ? 1 : 0;
+    png_item_set_passes(&it);
     it.npal = h.npal;
     it.ntrns = h.ntrns;
     it.has_trns = h.has_trns;
@@ -283,7 +305,7 @@ static int decode_png_into(const Decoder* d, Mat* m) {
         o += sgm.length;
     }
     const size_t zb = round_up(z.size(), (size_t)256);
-    const size_t rawb = round_up((h.row_bytes + 1) * (size_t)h.height + 16, (size_t)256);
+    const size_t rawb = round_up((size_t)it.raw_total + 16, (size_t)256);
     uint8_t* scratch = nullptr;
     LP_CUDA_OK(cudaMallocAsync(&scratch, 4096 + zb + rawb, st));
     PngDecodeItem* d_item = reinterpret_cast<PngDecodeItem*>(scratch);

@@ -208,6 +208,192 @@ __global__ void jpeg_huff_decode_kernel(JpegDecodeItem* items, const JpegHuffSet
     it.status = status;
 }
 
+// ------------------------------------------------------------------ multi-scan files (serial)
+// Progressive JPEG (T.81 Annex G; libjpeg-turbo's jdphuff.c is what the reference runs) and
+// sequential files with one scan per component.  Every scan refines the same coefficient array,
+// and inside a scan the end-of-band runs chain across blocks, so one thread walks the scans in
+// order.  Restated in oracle/oracle_jpeg_dec.c (prog_*), which is pinned on the reference.
+
+__device__ __forceinline__ int br_bits(BitReader& b, int n) {
+    if (n == 0) return 0;
+    if (b.nbits < 32) br_fill(b);
+    const int v = (int)(b.acc >> (64 - n));
+    b.acc <<= n;
+    b.nbits -= n;
+    return v;
+}
+
+struct ProgState {
+    int Ss, Se, Al;
+    unsigned eobrun;
+};
+
+__device__ int prog_ac_first(BitReader& b, const JpegHuffSet* hs, int ta, ProgState& ps, int16_t* blk, const uint8_t* zz) {
+    if (ps.eobrun > 0) {
+        ps.eobrun--;
+        return 0;
+    }
+    for (int k = ps.Ss; k <= ps.Se; k++) {
+        const int rs = huff_symbol(b, hs, ta);
+        if (rs < 0) return -3;
+        int r = rs >> 4;
+        const int n = rs & 15;
+        if (n) {
+            k += r;
+            if (k > 63) return -3;
+            blk[zz[k]] = (int16_t)((unsigned)receive_extend(b, n) << ps.Al);
+        } else if (r == 15) {
+            k += 15;
+        } else {
+            ps.eobrun = 1u << r;
+            if (r) ps.eobrun += (unsigned)br_bits(b, r);
+            ps.eobrun--;
+            break;
+        }
+    }
+    return 0;
+}
+
+__device__ int prog_ac_refine(BitReader& b, const JpegHuffSet* hs, int ta, ProgState& ps, int16_t* blk, const uint8_t* zz) {
+    const int p1 = 1 << ps.Al, m1 = -(1 << ps.Al);
+    int k = ps.Ss;
+    if (ps.eobrun == 0) {
+        for (; k <= ps.Se; k++) {
+            const int rs = huff_symbol(b, hs, ta);
+            if (rs < 0) return -3;
+            int r = rs >> 4;
+            const int n = rs & 15;
+            int val = 0;
+            if (n) {
+                if (n != 1) return -3;
+                val = br_bits(b, 1) ? p1 : m1;
+            } else if (r != 15) {
+                ps.eobrun = 1u << r;
+                if (r) ps.eobrun += (unsigned)br_bits(b, r);
+                break;
+            }
+            do {
+                int16_t* co = blk + zz[k];
+                if (*co != 0) {
+                    if (br_bits(b, 1)) {
+                        if ((*co & p1) == 0) *co = (int16_t)(*co + (*co >= 0 ? p1 : m1));
+                    }
+                } else {
+                    if (--r < 0) break;
+                }
+                k++;
+            } while (k <= ps.Se);
+            if (val) {
+                if (k > 63) return -3;
+                blk[zz[k]] = (int16_t)val;
+            }
+        }
+    }
+    if (ps.eobrun > 0) {
+        for (; k <= ps.Se; k++) {
+            int16_t* co = blk + zz[k];
+            if (*co != 0 && br_bits(b, 1)) {
+                if ((*co & p1) == 0) *co = (int16_t)(*co + (*co >= 0 ? p1 : m1));
+            }
+        }
+        ps.eobrun--;
+    }
+    return 0;
+}
+
+__global__ void jpeg_multiscan_kernel(JpegDecodeItem* item, const JpegScanDesc* scans, int nscans,
+                                      const JpegHuffSet* sets, const uint8_t* file, int16_t* coef) {
+    __shared__ uint8_t zz[64];
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) zz[k] = c_zigzag[k];
+    __syncthreads();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    JpegDecodeItem& it = *item;
+    int status = 0;
+    for (int s = 0; s < nscans && status == 0; s++) {
+        const JpegScanDesc sc = scans[s];
+        const JpegHuffSet* hs = sets + sc.table_set;
+        BitReader b{file + sc.data_off, file + sc.data_off + sc.data_len, 0, 0, false};
+        ProgState ps{sc.Ss, sc.Se, sc.Al, 0u};
+        int pred[3] = {0, 0, 0};
+        int mcux, mcuy;
+        if (sc.ns == 1) {  // non-interleaved: one block per MCU over the component's true block grid
+            mcux = (it.dw[sc.ci[0]] + 7) / 8;
+            mcuy = (it.dh[sc.ci[0]] + 7) / 8;
+        } else {
+            mcux = it.mcus_x;
+            mcuy = it.mcus_y;
+        }
+        int todo = sc.restart_interval;
+        for (int my = 0; my < mcuy && status == 0; my++) {
+            for (int mx = 0; mx < mcux && status == 0; mx++) {
+                if (sc.restart_interval && todo == 0) {
+                    b.acc = 0;
+                    b.nbits = 0;
+                    const uint8_t* q = b.p;
+                    while (q + 1 < b.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
+                    if (q + 1 >= b.end) {
+                        status = -3;
+                        break;
+                    }
+                    b.p = q + 2;
+                    b.marker = false;
+                    pred[0] = pred[1] = pred[2] = 0;
+                    ps.eobrun = 0;
+                    todo = sc.restart_interval;
+                }
+                for (int i = 0; i < sc.ns && status == 0; i++) {
+                    const int c = sc.ci[i];
+                    const int bh = sc.ns == 1 ? 1 : it.h[c], bv = sc.ns == 1 ? 1 : it.v[c];
+                    const int td = sc.td[i], ta = 4 + sc.ta[i];
+                    for (int by = 0; by < bv && status == 0; by++) {
+                        for (int bx = 0; bx < bh && status == 0; bx++) {
+                            int16_t* blk = roi_block(it, coef, c, mx * bh + bx, my * bv + by);
+                            if (!blk) {
+                                status = -3;
+                                break;
+                            }
+                            if (!sc.progressive) {  // sequential block: DC difference + AC run/size pairs
+                                const int sz = huff_symbol(b, hs, td);
+                                if (sz < 0 || sz > 15) { status = -3; break; }
+                                if (sz) pred[i] += receive_extend(b, sz);
+                                blk[0] = (int16_t)pred[i];
+                                for (int k = 1; k < 64;) {
+                                    const int rs = huff_symbol(b, hs, ta);
+                                    if (rs < 0) { status = -3; break; }
+                                    const int r = rs >> 4, n = rs & 15;
+                                    if (n == 0) {
+                                        if (r != 15) break;
+                                        k += 16;
+                                        continue;
+                                    }
+                                    k += r;
+                                    if (k > 63) { status = -3; break; }
+                                    blk[zz[k]] = (int16_t)receive_extend(b, n);
+                                    k++;
+                                }
+                            } else if (sc.Ss == 0) {
+                                if (sc.Ah == 0) {  // DC first pass
+                                    const int sz = huff_symbol(b, hs, td);
+                                    if (sz < 0 || sz > 15) { status = -3; break; }
+                                    if (sz) pred[i] += receive_extend(b, sz);
+                                    blk[0] = (int16_t)((unsigned)pred[i] << sc.Al);
+                                } else if (br_bits(b, 1)) {  // DC refinement
+                                    blk[0] |= (int16_t)(1 << sc.Al);
+                                }
+                            } else {
+                                status = sc.Ah == 0 ? prog_ac_first(b, hs, ta, ps, blk, zz)
+                                                    : prog_ac_refine(b, hs, ta, ps, blk, zz);
+                            }
+                        }
+                    }
+                }
+                if (sc.restart_interval) todo--;
+            }
+        }
+    }
+    it.status = status;
+}
+
 // ------------------------------------------------------------------ dequant + ISLOW IDCT
 
 #define LP_FIX_0_298631336 2446
@@ -456,7 +642,11 @@ __global__ void __launch_bounds__(128)
 int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_huff) {
     if (b.n <= 0) return LP_OK;
     LP_CUDA_OK(cudaMemsetAsync(b.coef, 0, b.coef_elems_total * sizeof(int16_t), st));
-    if (b.use_parallel_huffman) {
+    if (b.scans) {
+        jpeg_multiscan_kernel<<<1, 32, 0, st>>>(b.items, b.scans, b.nscans, b.tables, b.scan, b.coef);
+        g_launches++;
+        LP_CUDA_OK(cudaGetLastError());
+    } else if (b.use_parallel_huffman) {
         JpegHuffParallelArgs a{b.items, b.tables, b.scan, b.clean, b.states, b.nslots, b.coef, b.dcdiff, b.n};
         int rc = jpeg_huff_parallel_launch(a, st);
         if (rc) return rc;

@@ -128,7 +128,13 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
             if (!have_sof || n < 1) return LP_ERR_INVALID_IMAGE;
             int ns = p[0];
             if (ns < 1 || ns > 3 || n < (size_t)(1 + 2 * ns + 3)) return LP_ERR_INVALID_IMAGE;
-            if (ns != h.ncomp) h.supported = false;  // multi-scan sequential: not on the device path
+            if (ns != h.ncomp) h.supported = false;  // one scan per component: serial multi-scan path
+            if (h.progressive || ns != h.ncomp) {
+                bool ok = true;
+                for (int i = 0; i < h.ncomp; i++)
+                    if (h.maxh % h.comp[i].h || h.maxv % h.comp[i].v || !h.qt_present[h.comp[i].tq]) ok = false;
+                h.multiscan = ok;
+            }
             for (int i = 0; i < ns && h.supported; i++) {
                 int ci = -1;
                 for (int j = 0; j < h.ncomp; j++)
@@ -151,6 +157,99 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
         pos += 2 + seg;
     }
     return have_sof ? LP_ERR_INVALID_IMAGE : LP_ERR_INVALID_IMAGE;
+}
+
+// Second walk for multi-scan files: one JpegScanDesc per SOS, with the DHT / DRI state at that point.
+int jpeg_parse_scans(const uint8_t* in, size_t len, const JpegHeader& h0, JpegScanDesc* scans, int max_scans,
+                     int* nscans, JpegHuffSet* sets, int max_sets, int* nsets) {
+    JpegHeader h = h0;  // tracks DHT redefinitions between scans
+    memset(h.huff_present, 0, sizeof(h.huff_present));
+    h.restart_interval = 0;
+    *nscans = 0;
+    *nsets = 0;
+    bool dirty = true;
+    size_t pos = 2;
+    while (pos + 4 <= len) {
+        if (in[pos] != 0xFF) { pos++; continue; }
+        const uint8_t m = in[pos + 1];
+        if (m == 0xFF) { pos++; continue; }
+        if (m == 0xD9) break;
+        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { pos += 2; continue; }
+        const size_t seg = ((size_t)in[pos + 2] << 8) | in[pos + 3];
+        if (seg < 2 || pos + 2 + seg > len) break;  // truncated: decode the scans seen so far
+        const uint8_t* p = in + pos + 4;
+        size_t n = seg - 2;
+        if (m == 0xC4) {
+            while (n >= 17) {
+                const int tc = p[0] >> 4, th = p[0] & 15;
+                if (tc > 1 || th > 3) return LP_ERR_INVALID_IMAGE;
+                int total = 0;
+                h.huff_bits[tc][th][0] = 0;
+                for (int i = 1; i <= 16; i++) { h.huff_bits[tc][th][i] = p[i]; total += p[i]; }
+                if (total > 256 || n < (size_t)(17 + total)) return LP_ERR_INVALID_IMAGE;
+                memset(h.huff_vals[tc][th], 0, 256);
+                memcpy(h.huff_vals[tc][th], p + 17, total);
+                h.huff_present[tc][th] = true;
+                p += 17 + total;
+                n -= 17 + total;
+            }
+            dirty = true;
+        } else if (m == 0xDD) {
+            if (n >= 2) h.restart_interval = (p[0] << 8) | p[1];
+        } else if (m == 0xDA) {
+            if (n < 1) return LP_ERR_INVALID_IMAGE;
+            const int ns = p[0];
+            if (ns < 1 || ns > h.ncomp || n < (size_t)(1 + 2 * ns + 3)) return LP_ERR_INVALID_IMAGE;
+            if (*nscans >= max_scans) return LP_ERR_UNSUPPORTED;
+            JpegScanDesc& sc = scans[*nscans];
+            memset(&sc, 0, sizeof(sc));
+            sc.ns = ns;
+            sc.progressive = h.progressive;
+            sc.Ss = h.progressive ? p[1 + 2 * ns] : 0;
+            sc.Se = h.progressive ? p[2 + 2 * ns] : 63;
+            sc.Ah = h.progressive ? p[3 + 2 * ns] >> 4 : 0;
+            sc.Al = h.progressive ? p[3 + 2 * ns] & 15 : 0;
+            if (sc.Ss > sc.Se || sc.Se > 63 || sc.Al > 13 || (h.progressive && sc.Ss == 0 && sc.Se != 0) ||
+                (sc.Ss > 0 && ns != 1))
+                return LP_ERR_INVALID_IMAGE;
+            for (int i = 0; i < ns; i++) {
+                int ci = -1;
+                for (int j = 0; j < h.ncomp; j++)
+                    if (h.comp[j].id == p[1 + 2 * i]) ci = j;
+                if (ci < 0) return LP_ERR_INVALID_IMAGE;
+                sc.ci[i] = ci;
+                sc.td[i] = p[2 + 2 * i] >> 4;
+                sc.ta[i] = p[2 + 2 * i] & 15;
+                if (sc.td[i] > 3 || sc.ta[i] > 3) return LP_ERR_INVALID_IMAGE;
+                const bool need_dc = !h.progressive || (sc.Ss == 0 && sc.Ah == 0);
+                const bool need_ac = !h.progressive || sc.Ss > 0;
+                if ((need_dc && !h.huff_present[0][sc.td[i]]) || (need_ac && !h.huff_present[1][sc.ta[i]]))
+                    return LP_ERR_INVALID_IMAGE;
+            }
+            if (dirty) {
+                if (*nsets >= max_sets) return LP_ERR_UNSUPPORTED;
+                jpeg_build_huff_set(h, &sets[*nsets]);
+                (*nsets)++;
+                dirty = false;
+            }
+            sc.table_set = *nsets - 1;
+            sc.restart_interval = h.restart_interval;
+            // entropy-coded segment: up to the next marker that is neither a stuffed FF00 nor RSTn
+            size_t q = pos + 2 + seg;
+            const size_t start = q;
+            while (q + 1 < len && !(in[q] == 0xFF && in[q + 1] != 0x00 && in[q + 1] != 0xFF &&
+                                    !(in[q + 1] >= 0xD0 && in[q + 1] <= 0xD7)))
+                q++;
+            if (q + 1 >= len) q = len;
+            sc.data_off = (uint32_t)start;
+            sc.data_len = (uint32_t)(q - start);
+            (*nscans)++;
+            pos = q;
+            continue;
+        }
+        pos += 2 + seg;
+    }
+    return *nscans > 0 ? LP_OK : LP_ERR_INVALID_IMAGE;
 }
 
 // Canonical Huffman decode tables (T.81 Annex C / F.2.2.3) in the device layout.

@@ -42,10 +42,22 @@ struct JpegHeader {
     size_t scan_length = 0;  // bytes available from scan_offset (upper bound)
     bool progressive = false;
     bool supported = false;  // baseline/extended sequential Huffman, 8-bit, 1 or 3 comps, one scan
+    bool multiscan = false;  // progressive, or sequential with one scan per component: serial device path
     int mcus_x = 0, mcus_y = 0;
 };
 // Parses markers up to and including the first SOS.  Returns 0, or a negative lp_status.
 int jpeg_parse_header(const uint8_t* data, size_t len, JpegHeader* out);
+
+// One scan of a multi-scan file (progressive: T.81 Annex G; or non-interleaved sequential).
+struct JpegScanDesc {
+    uint32_t data_off, data_len;  // entropy-coded segment inside the uploaded FILE
+    int32_t ns;                   // components in the scan
+    int32_t ci[3], td[3], ta[3];  // frame component index, DC / AC table ids
+    int32_t Ss, Se, Ah, Al;       // spectral band and successive-approximation bit positions
+    int32_t restart_interval;
+    int32_t table_set;            // Huffman tables in force at this scan
+    int32_t progressive;
+};
 
 // ---- jpeg_decode.cu ------------------------------------------------------------------------
 // Device-side description of one image to decode (array of these lives in HBM).
@@ -98,6 +110,10 @@ struct JpegHuffSet {
     uint8_t vals[8][256];
 };
 void jpeg_build_huff_set(const JpegHeader& h, JpegHuffSet* out);
+// Walks every SOS of a multi-scan file, snapshotting the Huffman tables / restart interval in force.
+// `sets`/`scans` are caller arrays (max_sets / max_scans entries).  Returns 0 or a negative lp_status.
+int jpeg_parse_scans(const uint8_t* data, size_t len, const JpegHeader& h, JpegScanDesc* scans, int max_scans,
+                     int* nscans, JpegHuffSet* sets, int max_sets, int* nsets);
 
 struct JpegDecodeBatch {
     JpegDecodeItem* items;      // device
@@ -116,6 +132,9 @@ struct JpegDecodeBatch {
     void* states = nullptr;      // SubState[]
     uint32_t* nslots = nullptr;
     int16_t* dcdiff = nullptr;   // DC differences of ALL blocks of an image, MCU order
+    // multi-scan files (n == 1): every scan decoded in order by one thread; `scan` holds the whole file
+    const JpegScanDesc* scans = nullptr;
+    int nscans = 0;
 };
 // Scratch sizing for the parallel Huffman path, per image with `scan_len` entropy-coded bytes.
 inline size_t huff_clean_bytes(size_t scan_len) { return ((scan_len + 48 + 15) / 16) * 16; }
@@ -171,7 +190,15 @@ struct PngDecodeItem {
     uint8_t trns[256];
     int32_t status;  // 0 ok, <0 corrupt stream
     uint32_t produced;
+    // Adam7 (PNG spec s.8.2): the inflated stream is up to seven reduced images back to back, each
+    // with its own scanline length.  A non-interlaced image is one "pass" covering everything.
+    int32_t interlace, npass;
+    uint32_t raw_total;               // inflated bytes expected
+    uint32_t pass_off[7], pass_rb[7];  // byte offset / scanline bytes (without the filter byte)
+    int32_t pass_w[7], pass_h[7];
 };
+// Fills npass / raw_total / pass_* from width, height, bit depth, channels, interlace.
+void png_item_set_passes(PngDecodeItem* it);
 struct PngDecodeBatch {
     PngDecodeItem* items;  // device
     const uint8_t* z;      // device: zlib streams

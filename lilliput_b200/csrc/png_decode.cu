@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kPngWarps * 32)
     InflateShared& sh = sh_all[warp];
     const uint8_t* z = zall + it.z_off;
     uint8_t* out = rawall + it.raw_off;
-    const uint32_t cap = (it.row_bytes + 1) * (uint32_t)it.height;
+    const uint32_t cap = it.raw_total;
     uint32_t o = 0;
     int status = 0;
     LsbBits b{z + 2, z + it.z_len, 0, 0};
@@ -329,14 +329,20 @@ __global__ void __launch_bounds__(kPngWarps * 32)
     if (img >= n) return;
     PngDecodeItem& it = items[img];
     if (it.status != 0) return;
-    uint8_t* raw = rawall + it.raw_off;
-    switch (it.bpp) {
-        case 1: defilter_image<1>(raw, it.row_bytes, it.height); break;
-        case 2: defilter_image<2>(raw, it.row_bytes, it.height); break;
-        case 3: defilter_image<3>(raw, it.row_bytes, it.height); break;
-        case 4: defilter_image<4>(raw, it.row_bytes, it.height); break;
-        case 6: defilter_image<6>(raw, it.row_bytes, it.height); break;
-        default: defilter_image<8>(raw, it.row_bytes, it.height); break;
+    for (int ps = 0; ps < it.npass; ps++) {  // Adam7: every reduced image is filtered on its own
+        if (it.pass_w[ps] == 0 || it.pass_h[ps] == 0) continue;
+        uint8_t* raw = rawall + it.raw_off + it.pass_off[ps];
+        const uint32_t rb = it.pass_rb[ps];
+        const int ph = it.pass_h[ps];
+        switch (it.bpp) {
+            case 1: defilter_image<1>(raw, rb, ph); break;
+            case 2: defilter_image<2>(raw, rb, ph); break;
+            case 3: defilter_image<3>(raw, rb, ph); break;
+            case 4: defilter_image<4>(raw, rb, ph); break;
+            case 6: defilter_image<6>(raw, rb, ph); break;
+            default: defilter_image<8>(raw, rb, ph); break;
+        }
+        __syncwarp();
     }
 }
 
@@ -345,10 +351,23 @@ __global__ void __launch_bounds__(kPngWarps * 32)
 __global__ void png_convert_kernel(const PngDecodeItem* items, const uint8_t* rawall, uint8_t* frames) {
     const PngDecodeItem& it = items[blockIdx.z];
     if (it.status != 0) return;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= it.width || y >= it.height) return;
-    const uint8_t* c = rawall + it.raw_off + (size_t)y * (it.row_bytes + 1) + 1;
-    uint8_t* o = frames + it.frame_off + (size_t)y * it.frame_stride + (size_t)x * it.out_channels;
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+    if (ox >= it.width || oy >= it.height) return;
+    int x = ox, y = oy, ps = 0;
+    if (it.interlace) {  // which reduced image holds (ox, oy), and where
+        int x0, y0, sx, sy;
+        if (oy & 1) { ps = 6; x0 = 0; y0 = 1; sx = 0; sy = 1; }
+        else if (ox & 1) { ps = 5; x0 = 1; y0 = 0; sx = 1; sy = 1; }
+        else if ((oy & 3) == 2) { ps = 4; x0 = 0; y0 = 2; sx = 1; sy = 2; }
+        else if ((ox & 3) == 2) { ps = 3; x0 = 2; y0 = 0; sx = 2; sy = 2; }
+        else if ((oy & 7) == 4) { ps = 2; x0 = 0; y0 = 4; sx = 2; sy = 3; }
+        else if ((ox & 7) == 4) { ps = 1; x0 = 4; y0 = 0; sx = 3; sy = 3; }
+        else { ps = 0; x0 = 0; y0 = 0; sx = 3; sy = 3; }
+        x = (ox - x0) >> sx;
+        y = (oy - y0) >> sy;
+    }
+    const uint8_t* c = rawall + it.raw_off + it.pass_off[ps] + (size_t)y * (it.pass_rb[ps] + 1) + 1;
+    uint8_t* o = frames + it.frame_off + (size_t)oy * it.frame_stride + (size_t)ox * it.out_channels;
     const int bd = it.bit_depth, sc = it.src_channels, ct = it.color_type, och = it.out_channels;
     uint32_t s[4] = {0, 0, 0, 0};
     for (int k = 0; k < sc; k++) {
@@ -378,6 +397,26 @@ __global__ void png_convert_kernel(const PngDecodeItem* items, const uint8_t* ra
         else if (och == 4)
             o[3] = (s[0] == it.trns_rgb[0] && s[1] == it.trns_rgb[1] && s[2] == it.trns_rgb[2]) ? 0 : 255;
     }
+}
+
+void png_item_set_passes(PngDecodeItem* it) {
+    static const int X0[7] = {0, 4, 0, 2, 0, 1, 0}, Y0[7] = {0, 0, 4, 0, 2, 0, 1};
+    static const int DX[7] = {8, 8, 4, 4, 2, 2, 1}, DY[7] = {8, 8, 8, 4, 4, 2, 2};
+    const size_t bits = (size_t)it->src_channels * it->bit_depth;
+    it->npass = it->interlace ? 7 : 1;
+    uint32_t off = 0;
+    for (int ps = 0; ps < it->npass; ps++) {
+        const int x0 = it->interlace ? X0[ps] : 0, y0 = it->interlace ? Y0[ps] : 0;
+        const int dx = it->interlace ? DX[ps] : 1, dy = it->interlace ? DY[ps] : 1;
+        const int pw = it->width > x0 ? (it->width - x0 + dx - 1) / dx : 0;
+        const int ph = it->height > y0 ? (it->height - y0 + dy - 1) / dy : 0;
+        it->pass_w[ps] = pw;
+        it->pass_h[ps] = ph;
+        it->pass_off[ps] = off;
+        it->pass_rb[ps] = (uint32_t)(((size_t)pw * bits + 7) / 8);
+        if (pw && ph) off += (it->pass_rb[ps] + 1) * (uint32_t)ph;
+    }
+    it->raw_total = off;
 }
 
 int png_decode_launch(const PngDecodeBatch& b, cudaStream_t st) {

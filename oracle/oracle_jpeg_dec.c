@@ -136,6 +136,100 @@ static int decode_block(BitReader* b, const HuffTable* dc, const HuffTable* ac, 
     return 0;
 }
 
+/* ---- progressive scans (T.81 Annex G; libjpeg-turbo jdphuff.c decode_mcu_{DC,AC}_{first,refine}) ---- */
+typedef struct {
+    int Ss, Se, Ah, Al;
+    unsigned eobrun; /* blocks still covered by an end-of-band run */
+} ProgState;
+
+/* DC coefficient, first pass (G.1.2.1): difference coding as in sequential mode, value << Al. */
+static int prog_dc_first(BitReader* b, const HuffTable* dc, Comp* c, const ProgState* ps, int16_t* blk) {
+    int s = huff_decode(b, dc);
+    if (s < 0 || s > 15) return E_CORRUPT;
+    int diff = s ? extend(br_get(b, s), s) : 0;
+    c->pred += diff;
+    blk[0] = (int16_t)((unsigned)c->pred << ps->Al);
+    return 0;
+}
+/* DC refinement (G.1.2.1): one more bit of precision per block. */
+static int prog_dc_refine(BitReader* b, const ProgState* ps, int16_t* blk) {
+    if (br_get(b, 1)) blk[0] |= (int16_t)(1 << ps->Al);
+    return 0;
+}
+/* AC band, first pass (G.1.2.2): run/size pairs with EOBn runs spanning blocks. */
+static int prog_ac_first(BitReader* b, const HuffTable* ac, ProgState* ps, int16_t* blk) {
+    if (ps->eobrun > 0) {
+        ps->eobrun--;
+        return 0;
+    }
+    for (int k = ps->Ss; k <= ps->Se; k++) {
+        int rs = huff_decode(b, ac);
+        if (rs < 0) return E_CORRUPT;
+        int r = rs >> 4, n = rs & 15;
+        if (n) {
+            k += r;
+            if (k > 63) return E_CORRUPT;
+            blk[ZIGZAG[k]] = (int16_t)((unsigned)extend(br_get(b, n), n) << ps->Al);
+        } else if (r == 15) {
+            k += 15; /* ZRL */
+        } else {
+            ps->eobrun = 1u << r;
+            if (r) ps->eobrun += (unsigned)br_get(b, r);
+            ps->eobrun--; /* this block is the first of the run */
+            break;
+        }
+    }
+    return 0;
+}
+/* AC band refinement (G.1.2.3): correction bits for already-nonzero coefficients interleaved
+ * with newly-nonzero ones. */
+static int prog_ac_refine(BitReader* b, const HuffTable* ac, ProgState* ps, int16_t* blk) {
+    const int p1 = 1 << ps->Al, m1 = -(1 << ps->Al);
+    int k = ps->Ss;
+    if (ps->eobrun == 0) {
+        for (; k <= ps->Se; k++) {
+            int rs = huff_decode(b, ac);
+            if (rs < 0) return E_CORRUPT;
+            int r = rs >> 4, n = rs & 15, val = 0;
+            if (n) {
+                if (n != 1) return E_CORRUPT; /* size of a newly nonzero coefficient must be 1 */
+                val = br_get(b, 1) ? p1 : m1;
+            } else if (r != 15) {
+                ps->eobrun = 1u << r;
+                if (r) ps->eobrun += (unsigned)br_get(b, r);
+                break; /* the rest of the block is handled by the end-of-band logic below */
+            }
+            /* advance over already-nonzero coefficients and r still-zero ones */
+            do {
+                int16_t* co = blk + ZIGZAG[k];
+                if (*co != 0) {
+                    if (br_get(b, 1)) {
+                        if ((*co & p1) == 0) *co = (int16_t)(*co + (*co >= 0 ? p1 : m1));
+                    }
+                } else {
+                    if (--r < 0) break; /* reached the target zero coefficient */
+                }
+                k++;
+            } while (k <= ps->Se);
+            if (val) {
+                if (k > 63) return E_CORRUPT;
+                blk[ZIGZAG[k]] = (int16_t)val;
+            }
+        }
+    }
+    if (ps->eobrun > 0) {
+        /* in an end-of-band run: only correction bits for the nonzero coefficients that remain */
+        for (; k <= ps->Se; k++) {
+            int16_t* co = blk + ZIGZAG[k];
+            if (*co != 0 && br_get(b, 1)) {
+                if ((*co & p1) == 0) *co = (int16_t)(*co + (*co >= 0 ? p1 : m1));
+            }
+        }
+        ps->eobrun--;
+    }
+    return 0;
+}
+
 /* jpeg_idct_islow with libjpeg-turbo's SIMD range behaviour. */
 #define FIX_0_298631336 2446
 #define FIX_0_390180644 3196
@@ -303,7 +397,7 @@ int oracle_jpeg_decode(const uint8_t* in, size_t len, uint8_t* out, size_t out_c
     Comp comp[4];
     memset(comp, 0, sizeof(comp));
     int ncomp = 0, W = 0, H = 0, maxh = 1, maxv = 1, restart = 0, orient = 1, have_sof = 0;
-    int rc = 0, scans_done = 0;
+    int rc = 0, scans_done = 0, progressive = 0, prog_scans = 0;
     size_t pos = 2;
     if (len < 4 || in[0] != 0xFF || in[1] != 0xD8) return E_CORRUPT;
 
@@ -344,7 +438,8 @@ int oracle_jpeg_decode(const uint8_t* in, size_t len, uint8_t* out, size_t out_c
                 p += 17 + total;
                 n -= 17 + total;
             }
-        } else if (m == 0xC0 || m == 0xC1) { /* SOF0 / SOF1: sequential Huffman */
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) { /* SOF0 / SOF1 sequential, SOF2 progressive Huffman */
+            progressive = (m == 0xC2);
             if (n < 6 || p[0] != 8) { rc = E_UNSUPPORTED; goto done; }
             H = (p[1] << 8) | p[2];
             W = (p[3] << 8) | p[4];
@@ -381,8 +476,8 @@ int oracle_jpeg_decode(const uint8_t* in, size_t len, uint8_t* out, size_t out_c
                 c->coef = calloc((size_t)c->bw * c->bh * 64, sizeof(int16_t));
                 c->plane = malloc((size_t)c->bw * c->bh * 64);
             }
-        } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
-            rc = E_UNSUPPORTED; /* progressive / lossless / arithmetic */
+        } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            rc = E_UNSUPPORTED; /* lossless / differential / arithmetic */
             goto done;
         } else if (m == 0xDD) {
             if (n >= 2) restart = (p[0] << 8) | p[1];
@@ -401,8 +496,20 @@ int oracle_jpeg_decode(const uint8_t* in, size_t len, uint8_t* out, size_t out_c
                 if (!sc[i]) { rc = E_CORRUPT; goto done; }
                 sc[i]->td = p[2 + 2 * i] >> 4;
                 sc[i]->ta = p[2 + 2 * i] & 15;
-                if (sc[i]->td > 3 || sc[i]->ta > 3 || !ht[0][sc[i]->td].present || !ht[1][sc[i]->ta].present) { rc = E_CORRUPT; goto done; }
+                if (sc[i]->td > 3 || sc[i]->ta > 3) { rc = E_CORRUPT; goto done; }
                 sc[i]->pred = 0;
+            }
+            ProgState ps = {p[1 + 2 * ns], p[2 + 2 * ns], p[3 + 2 * ns] >> 4, p[3 + 2 * ns] & 15, 0};
+            if (!progressive) {
+                ps.Ss = 0; ps.Se = 63; ps.Ah = ps.Al = 0;
+            } else if (ps.Ss > ps.Se || ps.Se > 63 || ps.Al > 13 || (ps.Ss == 0 && ps.Se != 0) || (ps.Ss > 0 && ns != 1)) {
+                rc = E_CORRUPT; /* G.1.1.1.1: DC scans carry only DC; AC scans are single-component */
+                goto done;
+            }
+            for (int i = 0; i < ns; i++) {
+                const int need_dc = !progressive || (ps.Ss == 0 && ps.Ah == 0);
+                const int need_ac = !progressive || ps.Ss > 0;
+                if ((need_dc && !ht[0][sc[i]->td].present) || (need_ac && !ht[1][sc[i]->ta].present)) { rc = E_CORRUPT; goto done; }
             }
             BitReader b = {in + pos + 2 + seg, in + len, 0, 0, 0};
             int mcux, mcuy;
@@ -426,6 +533,7 @@ int oracle_jpeg_decode(const uint8_t* in, size_t len, uint8_t* out, size_t out_c
                         b.hit_marker = 0;
                         rstn = (rstn + 1) & 7;
                         for (int i = 0; i < ns; i++) sc[i]->pred = 0;
+                        ps.eobrun = 0;
                         todo = restart;
                     }
                     for (int i = 0; i < ns && !rc; i++) {
@@ -434,26 +542,29 @@ int oracle_jpeg_decode(const uint8_t* in, size_t len, uint8_t* out, size_t out_c
                         for (int by = 0; by < bv_ && !rc; by++)
                             for (int bx = 0; bx < bh_ && !rc; bx++) {
                                 int X = mxi * bh_ + bx, Y = my * bv_ + by;
-                                rc = decode_block(&b, &ht[0][c->td], &ht[1][c->ta], c,
-                                                  c->coef + ((size_t)Y * c->bw + X) * 64);
+                                int16_t* blk = c->coef + ((size_t)Y * c->bw + X) * 64;
+                                if (!progressive) rc = decode_block(&b, &ht[0][c->td], &ht[1][c->ta], c, blk);
+                                else if (ps.Ss == 0) rc = ps.Ah == 0 ? prog_dc_first(&b, &ht[0][c->td], c, &ps, blk) : prog_dc_refine(&b, &ps, blk);
+                                else rc = ps.Ah == 0 ? prog_ac_first(&b, &ht[1][c->ta], &ps, blk) : prog_ac_refine(&b, &ht[1][c->ta], &ps, blk);
                             }
                     }
                     if (restart) todo--;
                 }
             if (rc) goto done;
-            scans_done += ns;
+            if (progressive) prog_scans++;
+            else scans_done += ns;
             /* continue after the entropy-coded segment: find the next non-RST marker */
             const uint8_t* q = b.p;
             while (q + 1 < b.end && !(q[0] == 0xFF && q[1] != 0x00 && q[1] != 0xFF && !(q[1] >= 0xD0 && q[1] <= 0xD7))) q++;
             pos = (size_t)(q - in);
-            if (scans_done >= ncomp) break;
-            continue;
+            if (!progressive && scans_done >= ncomp) break;
+            continue; /* progressive: keep reading scans until EOI */
         }
         pos += 2 + seg;
     }
     if (!have_sof) { rc = E_CORRUPT; goto done; }
     if (!out) { if (orientation) *orientation = orient; goto done; }
-    if (scans_done < ncomp) { rc = E_TRUNC; goto done; }
+    if (progressive ? prog_scans == 0 : scans_done < ncomp) { rc = E_TRUNC; goto done; }
     if (orientation) *orientation = orient;
     {
         int och = ncomp == 1 ? 1 : 3;

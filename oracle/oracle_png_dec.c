@@ -200,16 +200,34 @@ int oracle_png_decode(const uint8_t* in, size_t len, uint8_t* out, size_t out_ca
     if (channels) *channels = och;
     if (depth) *depth = bd;
     if (!out) { free(z); return 0; }
-    if (interlace) { free(z); return -2; }
     if ((size_t)W * H * och > out_cap) { free(z); return -4; }
-    size_t bpp_bits = (size_t)src_ch * bd, stride = (W * bpp_bits + 7) / 8, bpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;
-    uint8_t* raw = malloc((stride + 1) * H + 8);
-    long got = zlib_inflate(z, zn, raw, (stride + 1) * H);
+    /* Adam7 (PNG spec s.8.2): seven reduced images, each filtered on its own; pass geometry below.
+     * A non-interlaced image is the single "pass" {0,0,1,1}. */
+    static const int PX0[7] = {0, 4, 0, 2, 0, 1, 0}, PY0[7] = {0, 0, 4, 0, 2, 0, 1};
+    static const int PDX[7] = {8, 8, 4, 4, 2, 2, 1}, PDY[7] = {8, 8, 8, 4, 4, 2, 2};
+    const int npass = interlace ? 7 : 1;
+    size_t bpp_bits = (size_t)src_ch * bd, bpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;
+    size_t total = 0;
+    for (int ps = 0; ps < npass; ps++) {
+        int x0 = interlace ? PX0[ps] : 0, y0 = interlace ? PY0[ps] : 0, dx = interlace ? PDX[ps] : 1, dy = interlace ? PDY[ps] : 1;
+        int pw = W > x0 ? (W - x0 + dx - 1) / dx : 0, ph = H > y0 ? (H - y0 + dy - 1) / dy : 0;
+        if (pw && ph) total += ((pw * bpp_bits + 7) / 8 + 1) * (size_t)ph;
+    }
+    uint8_t* raw = malloc(total + 8);
+    long got = zlib_inflate(z, zn, raw, total);
     free(z);
-    if (got < (long)((stride + 1) * H)) { free(raw); return -1; }
-    uint8_t* prev = calloc(stride, 1);
-    for (int y = 0; y < H; y++) {
-        uint8_t* r = raw + (size_t)y * (stride + 1);
+    if (got < (long)total) { free(raw); return -1; }
+    size_t full_stride = (W * bpp_bits + 7) / 8;
+    uint8_t* prev = calloc(full_stride + 1, 1);
+    size_t off = 0;
+    for (int ps = 0; ps < npass; ps++) {
+        int x0 = interlace ? PX0[ps] : 0, y0 = interlace ? PY0[ps] : 0, dx = interlace ? PDX[ps] : 1, dy = interlace ? PDY[ps] : 1;
+        int pw = W > x0 ? (W - x0 + dx - 1) / dx : 0, ph = H > y0 ? (H - y0 + dy - 1) / dy : 0;
+        if (!pw || !ph) continue;
+        size_t stride = (pw * bpp_bits + 7) / 8;
+        memset(prev, 0, stride);
+    for (int py = 0; py < ph; py++) {
+        uint8_t* r = raw + off + (size_t)py * (stride + 1);
         int f = r[0];
         uint8_t* c = r + 1;
         for (size_t x = 0; x < stride; x++) {
@@ -224,8 +242,10 @@ int oracle_png_decode(const uint8_t* in, size_t len, uint8_t* out, size_t out_ca
             c[x] = (uint8_t)v;
         }
         memcpy(prev, c, stride);
-        uint8_t* o = out + (size_t)y * W * och;
-        for (int x = 0; x < W; x++) {
+        uint8_t* orow = out + (size_t)(y0 + py * dy) * W * och;
+        for (int px = 0; px < pw; px++) {
+            uint8_t* o = orow + (size_t)(x0 + px * dx) * och - (size_t)px * och; /* o[px*och+k] lands on the pixel */
+            int x = px;
             unsigned s[4] = {0, 0, 0, 0}; /* samples at full precision */
             for (int k = 0; k < src_ch; k++) {
                 size_t bit = ((size_t)x * src_ch + k) * bd;
@@ -251,6 +271,8 @@ int oracle_png_decode(const uint8_t* in, size_t len, uint8_t* out, size_t out_ca
                 else if (och == 4) o[x * 4 + 3] = (s[0] == trns_rgb[0] && s[1] == trns_rgb[1] && s[2] == trns_rgb[2]) ? 0 : 255;
             }
         }
+    }
+    off += (stride + 1) * (size_t)ph;
     }
     free(prev);
     free(raw);

@@ -1,9 +1,9 @@
 /*
  * lp_giflib.h -- the cgo surface of lilliput's GIF adapter as exported by liblilliput_b200.so.
  * Same names, signatures and return conventions as the reference's giflib.hpp (cited per symbol).
- * Decode (LZW + full-canvas compositing) runs on the device; the encoder entry points exist so the
- * Go package links, but GIF *encoding* is not implemented on the device yet:
- * giflib_encoder_create returns NULL, which giflib.go maps to an error.
+ * Decode (LZW + full-canvas compositing) and encode (palette mapping with the reference's memo
+ * semantics + giflib's LZW) both run on the device; GIF -> GIF output is byte-identical to the
+ * reference's.
  */
 #ifndef LP_GIFLIB_H
 #define LP_GIFLIB_H

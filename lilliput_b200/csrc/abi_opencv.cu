@@ -340,6 +340,19 @@ const uint8_t* mat_host_bytes(const void* mat, size_t* len) {
     *len = (size_t)m->cols * m->rows * m->elem();
     return m->host;
 }
+// Read-only device view of a mat (uploading the host copy first when it is newer).
+int mat_device_view(void* mat, int* cols, int* rows, int* type, const uint8_t** dev, size_t* step) {
+    Mat* m = static_cast<Mat*>(mat);
+    if (!m || m->rows <= 0 || m->cols <= 0) return LP_ERR_BAD_ARGUMENT;
+    int rc = ensure_dev(m);
+    if (rc) return rc;
+    *cols = m->cols;
+    *rows = m->rows;
+    *type = m->type;
+    *dev = m->dptr();
+    *step = m->dev_step;
+    return LP_OK;
+}
 int mat_bind_device_frame(void* mat, int cols, int rows, int type, uint8_t** dev, size_t* step) {
     Mat* m = static_cast<Mat*>(mat);
     if (!m) return LP_ERR_BAD_ARGUMENT;

@@ -44,6 +44,7 @@ struct GifReader {
     size_t n = 0, pos = 0;
     int sw = 0, sh = 0, bg_index = 0, gct_colors = 0;
     const uint8_t* gct = nullptr;
+    uint8_t packed = 0, aspect = 0;  // logical screen descriptor bytes 10 and 12
 
     bool get(uint8_t* b) {
         if (pos >= n) return false;
@@ -54,8 +55,9 @@ struct GifReader {
         if (n < 13 || (memcmp(p, "GIF87a", 6) && memcmp(p, "GIF89a", 6))) return false;
         sw = p[6] | (p[7] << 8);
         sh = p[8] | (p[9] << 8);
-        const uint8_t packed = p[10];
+        packed = p[10];
         bg_index = p[11];
+        aspect = p[12];
         pos = 13;
         if (packed & 0x80) {
             gct_colors = 1 << ((packed & 7) + 1);
@@ -274,21 +276,223 @@ __global__ void gif_compose_kernel(const GifCompose c) {
     *reinterpret_cast<uchar4*>(c.canvas + at) = px;
 }
 
+
+// ------------------------------------------------------------------ encoder kernels
+// ref giflib.cpp:934-1098 (giflib_encoder_render_frame): every BGRA pixel of the composited frame
+// becomes a palette index.  The reference memoises "best palette entry" per 15-bit crushed colour
+// in raster order, and the FIRST pixel that lands in a bucket decides its entry (from the bucket's
+// midpoint, or from the pixel itself when it is near black / white).  To stay byte-identical the
+// device reproduces that order dependence: pass 1 finds each absent bucket's first pixel
+// (atomicMin over raster indices), pass 2 resolves those buckets, pass 3 maps all pixels.
+
+struct GifEncFrame {
+    const uint8_t* frame;   // BGRA
+    size_t step;
+    int width, height;      // frame size (= image descriptor size)
+    int canvas_w;           // gif->SWidth: row pitch of prev
+    const uint8_t* prev;    // previous frame, canvas_w x canvas_h BGRA
+    int16_t* lookup;        // [32768] palette index per crushed colour, -1 = absent
+    uint32_t* first;        // [32768] raster index of the first pixel of a bucket resolved this frame
+    int* first_dist;        // [32768] distance that first pixel saw (measured from the compare colour)
+    uint8_t* pixels;        // out: width*height indices
+    int ncolors, transparent /* -1 none */, prev_valid;
+    uint8_t palette[256 * 3];  // RGB
+};
+
+__device__ __forceinline__ int rgb_distance(int r0, int g0, int b0, int r1, int g1, int b1) {
+    return abs(r0 - r1) + abs(g0 - g1) + abs(b0 - b1);
+}
+
+__global__ void gif_enc_first_kernel(GifEncFrame f) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= f.width) return;
+    const uint8_t* s = f.frame + (size_t)y * f.step + (size_t)x * 4;
+    if (s[3] < 128 && f.transparent != -1) return;  // becomes the transparent index, never consults the table
+    const uint32_t crushed = ((uint32_t)(s[2] >> 3) << 10) | ((uint32_t)(s[1] >> 3) << 5) | (s[0] >> 3);
+    if (f.lookup[crushed] < 0) atomicMin(&f.first[crushed], (uint32_t)(y * f.width + x));
+}
+
+__global__ void gif_enc_bucket_kernel(GifEncFrame f) {
+    const int bucket = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bucket >= 32768) return;
+    const uint32_t idx = f.first[bucket];
+    if (idx == 0xFFFFFFFFu) return;
+    const uint8_t* s = f.frame + (size_t)(idx / f.width) * f.step + (size_t)(idx % f.width) * 4;
+    const int B = s[0], G = s[1], R = s[2];
+    const bool extreme = (R > 240 && G > 240 && B > 240) || (R < 15 && G < 15 && B < 15);
+    const int Rc = extreme ? R : (R & 0xf8) | 4, Gc = extreme ? G : (G & 0xf8) | 4, Bc = extreme ? B : (B & 0xf8) | 4;
+    int least = 0x7fffffff, best = 0;
+    for (int i = 0; i < f.ncolors; i++) {
+        if (i == f.transparent) continue;
+        const int d = rgb_distance(Rc, Gc, Bc, f.palette[i * 3], f.palette[i * 3 + 1], f.palette[i * 3 + 2]);
+        if (d < least) {
+            least = d;
+            best = i;
+        }
+    }
+    f.lookup[bucket] = (int16_t)best;
+    f.first_dist[bucket] = least;
+}
+
+__global__ void gif_enc_map_kernel(GifEncFrame f) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= f.width) return;
+    const uint8_t* s = f.frame + (size_t)y * f.step + (size_t)x * 4;
+    const int B = s[0], G = s[1], R = s[2], A = s[3];
+    const uint32_t idx = (uint32_t)(y * f.width + x);
+    int best;
+    if (A < 128 && f.transparent != -1) {
+        best = f.transparent;
+    } else {
+        const uint32_t crushed = ((uint32_t)(R >> 3) << 10) | ((uint32_t)(G >> 3) << 5) | (B >> 3);
+        best = f.lookup[crushed];
+        int least;
+        if (f.first[crushed] == idx) least = f.first_dist[crushed];
+        else least = rgb_distance(R, G, B, f.palette[best * 3], f.palette[best * 3 + 1], f.palette[best * 3 + 2]);
+        if (f.prev_valid && f.transparent != -1) {
+            const uint8_t* l = f.prev + 4 * ((size_t)y * f.canvas_w + x);
+            if (rgb_distance(R, G, B, l[2], l[1], l[0]) < least) best = f.transparent;
+        }
+    }
+    f.pixels[idx] = (uint8_t)best;
+}
+
+// giflib's EGifCompressLine / EGifCompressOutput / EGifBufferedOutput (egif_lib.c), one frame.
+// LZW is one serial chain; lane 0 walks it with the string table as an open-addressing hash in
+// shared memory.  Output = the code stream cut into 255-byte sub-blocks + the block terminator.
+__global__ void __launch_bounds__(32) gif_lzw_encode_kernel(const uint8_t* pixels, int width, int height, int interlace,
+                                                            int bpp, uint8_t* out, uint32_t out_cap, uint32_t* out_len) {
+    __shared__ uint32_t h_key[8192];
+    __shared__ uint16_t h_val[8192];
+    for (int i = threadIdx.x; i < 8192; i += 32) h_key[i] = 0xFFFFFFFFu;
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const int clear = 1 << bpp, eof = clear + 1;
+    const uint32_t mask = (1u << bpp) - 1;
+    int running_code = eof + 1, running_bits = bpp + 1, max_code1 = 1 << running_bits;
+    uint32_t shift_dword = 0;
+    int shift_state = 0;
+    uint32_t pos = 0, blk_start = 0;
+    int blk_n = 0;
+    bool overflow = false;
+    auto put_byte = [&](uint32_t b) {
+        if (blk_n == 0) {  // open a sub-block: reserve its count byte
+            if (pos >= out_cap) { overflow = true; return; }
+            blk_start = pos++;
+        }
+        if (pos >= out_cap) { overflow = true; return; }
+        out[pos++] = (uint8_t)b;
+        if (++blk_n == 255) {
+            out[blk_start] = 255;
+            blk_n = 0;
+        }
+    };
+    auto put_code = [&](int code) {
+        shift_dword |= (uint32_t)code << shift_state;
+        shift_state += running_bits;
+        while (shift_state >= 8) {
+            put_byte(shift_dword & 0xff);
+            shift_dword >>= 8;
+            shift_state -= 8;
+        }
+        if (running_code >= max_code1 && code <= 4095) max_code1 = 1 << ++running_bits;
+    };
+    put_code(clear);
+    int crnt = -1;
+    const int npass = interlace ? 4 : 1;
+    for (int ps = 0; ps < npass; ps++) {
+        const int y0 = interlace ? (ps == 0 ? 0 : ps == 1 ? 4 : ps == 2 ? 2 : 1) : 0;
+        const int dy = interlace ? (ps == 0 ? 8 : ps == 1 ? 8 : ps == 2 ? 4 : 2) : 1;
+        for (int y = y0; y < height; y += dy) {
+            const uint8_t* line = pixels + (size_t)y * width;
+            for (int x = 0; x < width; x++) {
+                const uint32_t px = line[x] & mask;
+                if (crnt < 0) {
+                    crnt = (int)px;
+                    continue;
+                }
+                const uint32_t key = ((uint32_t)crnt << 8) + px;
+                uint32_t h = (key * 2654435761u) >> 19;
+                int found = -1;
+                while (h_key[h] != 0xFFFFFFFFu) {
+                    if (h_key[h] == key) {
+                        found = h_val[h];
+                        break;
+                    }
+                    h = (h + 1) & 8191;
+                }
+                if (found >= 0) {
+                    crnt = found;
+                } else {
+                    put_code(crnt);
+                    crnt = (int)px;
+                    if (running_code >= 4095) {
+                        put_code(clear);
+                        running_code = eof + 1;
+                        running_bits = bpp + 1;
+                        max_code1 = 1 << running_bits;
+                        for (int i = 0; i < 8192; i++) h_key[i] = 0xFFFFFFFFu;
+                    } else {
+                        h_key[h] = key;  // h stopped on the empty slot of this key's probe sequence
+                        h_val[h] = (uint16_t)running_code++;
+                    }
+                }
+            }
+        }
+    }
+    put_code(crnt);
+    put_code(eof);
+    while (shift_state > 0) {  // FLUSH_OUTPUT
+        put_byte(shift_dword & 0xff);
+        shift_dword >>= 8;
+        shift_state -= 8;
+    }
+    if (blk_n > 0) out[blk_start] = (uint8_t)blk_n;
+    if (pos < out_cap) out[pos++] = 0;  // block terminator
+    else overflow = true;
+    *out_len = overflow ? 0xFFFFFFFFu : pos;
+}
 }  // namespace lp
 
 using namespace lp;
 
-// The mat handle is defined in abi_opencv.cu; the decoder only needs these few accessors.
+// The mat handle is defined in abi_opencv.cu; the adapters only need these few accessors.
 namespace lp {
 const uint8_t* mat_host_bytes(const void* mat, size_t* len);
 int mat_bind_device_frame(void* mat, int cols, int rows, int type, uint8_t** dev, size_t* step);
 void mat_mark_device_written(void* mat);
+int mat_device_view(void* mat, int* cols, int* rows, int* type, const uint8_t** dev, size_t* step);
+
+// One entry of giflib's GifFileType::ExtensionBlocks: the first sub-block of an extension carries
+// its label, the following ones CONTINUE_EXT_FUNC_CODE (0).
+struct GifExt {
+    int function;
+    std::vector<uint8_t> bytes;
+};
+// EGifGCBToExtension into every graphic-control block of at least 4 bytes (ref giflib.cpp:272-291)
+static void set_frame_gcb(std::vector<GifExt>& ext, const GifGcb& g) {
+    for (GifExt& e : ext) {
+        if (e.function != 0xF9 || e.bytes.size() < 4) continue;
+        e.bytes[0] = (uint8_t)((g.transparent != -1 ? 1 : 0) | (g.user_input ? 2 : 0) | ((g.disposal & 7) << 2));
+        e.bytes[1] = (uint8_t)(g.delay & 0xFF);
+        e.bytes[2] = (uint8_t)((g.delay >> 8) & 0xFF);
+        e.bytes[3] = (uint8_t)g.transparent;
+    }
+}
+// giflib_get_frame_gcb (ref giflib.cpp:248-270): defaults, then every well-formed block in order
+static GifGcb get_frame_gcb(const std::vector<GifExt>& ext) {
+    GifGcb g;
+    for (const GifExt& e : ext)
+        if (e.function == 0xF9) gcb_from_block(e.bytes.data(), (int)e.bytes.size(), &g);
+    return g;
+}
 }  // namespace lp
 
 struct giflib_decoder_struct {
     GifReader rd;
     GifImage image;                    // gif->Image
     std::vector<GifGcb> pending_gcbs;  // graphic control blocks seen since the last frame
+    std::vector<GifExt> ext;           // gif->ExtensionBlocks: every sub-block since the last frame
     bool seek_clear_extensions = false;
     bool have_read_first_frame = false;
     int prev_disposal = 0, prev_delay = 0, prev_left = 0, prev_top = 0, prev_width = 0, prev_height = 0;
@@ -304,8 +508,39 @@ struct giflib_decoder_struct {
     size_t indices_cap = 0, lzw_cap = 0;
 };
 
+// ref giflib.cpp:26-58.  The GifFileType fields the reference reads back from `e->gif` live here.
 struct giflib_encoder_struct {
-    int unused;
+    uint8_t* dst = nullptr;
+    size_t dst_len = 0, dst_offset = 0;
+    bool open = false;
+    int sw = 0, sh = 0, bg = 0;
+    bool has_gct = false;
+    std::vector<uint8_t> gct;  // RGB triplets
+    bool have_written_first_frame = false;
+    int prev_frame_disposal = 0;
+    std::vector<uint8_t> prev_colors;  // colour map used by the previous frame (for the memo's reuse test)
+    bool have_prev_colors = false;
+    // device state
+    uint8_t* d_prev = nullptr;
+    int16_t* d_lookup = nullptr;
+    uint32_t* d_first = nullptr;
+    int* d_first_dist = nullptr;
+    uint8_t* d_pixels = nullptr;
+    uint8_t* d_out = nullptr;
+    uint32_t* d_out_len = nullptr;
+    size_t pixels_cap = 0, out_cap = 0;
+
+    bool put(const void* p, size_t n) {  // encode_func, ref giflib.cpp:762-771
+        if (dst_offset + n > dst_len) return false;
+        memcpy(dst + dst_offset, p, n);
+        dst_offset += n;
+        return true;
+    }
+    bool put8(uint8_t b) { return put(&b, 1); }
+    bool put16(int v) {
+        const uint8_t b[2] = {(uint8_t)(v & 0xff), (uint8_t)((v >> 8) & 0xff)};
+        return put(b, 2);
+    }
 };
 
 extern "C" {
@@ -360,6 +595,7 @@ static bool read_extension(giflib_decoder d) {
     if (!d->rd.sub_block(&data, &len)) return false;
     bool first = true;
     while (len != 0) {
+        d->ext.push_back(GifExt{first ? (int)label : 0, std::vector<uint8_t>(data, data + len)});
         if (first && label == 0xF9) {
             GifGcb g;
             if (gcb_from_block(data, len, &g)) d->pending_gcbs.push_back(g);
@@ -375,6 +611,7 @@ static bool read_extension(giflib_decoder d) {
 static giflib_decoder_frame_state seek_next_frame(giflib_decoder d) {
     if (d->seek_clear_extensions) {
         d->pending_gcbs.clear();
+        d->ext.clear();
         d->seek_clear_extensions = false;
     }
     for (;;) {
@@ -495,6 +732,13 @@ bool giflib_decoder_decode_frame(giflib_decoder d, opencv_mat mat) {  // ref gif
         return false;
     }
     mat_mark_device_written(mat);
+    // ref giflib.cpp:548-565: a partial frame without a transparent index gets one forced into its
+    // graphic control block (the last palette entry), for the encoder's benefit
+    if ((im.height < chh || im.width < cw || im.left != 0 || im.top != 0) && gcb.transparent == -1) {
+        GifGcb forced = gcb;
+        forced.transparent = ncolors - 1;
+        set_frame_gcb(d->ext, forced);
+    }
     d->prev_disposal = gcb.disposal;
     d->prev_delay = gcb.delay;
     d->prev_left = im.left;
@@ -574,15 +818,181 @@ struct GifAnimationInfo giflib_decoder_get_animation_info(const giflib_decoder d
     return info;
 }
 
-// GIF encoding is a "next" row: not on the device yet, fail loudly.
-giflib_encoder giflib_encoder_create(void*, size_t) {
-    fprintf(stderr, "[lilliput_b200] GIF encoding is not implemented on the device path yet\n");
-    return nullptr;
+// ------------------------------------------------------------------ encoder (ref giflib.cpp:726-1306)
+
+// ref giflib.cpp:1100-1124 (EGifPutExtensionLeader / Block / Trailer per stored sub-block)
+static bool write_extensions(giflib_encoder e, const std::vector<GifExt>& ext) {
+    for (size_t i = 0; i < ext.size(); i++) {
+        const GifExt& b = ext[i];
+        if (b.function != 0) {
+            if (!e->put8(0x21) || !e->put8((uint8_t)b.function)) return false;
+        }
+        if (!e->put8((uint8_t)b.bytes.size()) || !e->put(b.bytes.data(), b.bytes.size())) return false;
+        if (i + 1 == ext.size() || ext[i + 1].function != 0) {
+            if (!e->put8(0)) return false;
+        }
+    }
+    return true;
 }
-bool giflib_encoder_init(giflib_encoder, const giflib_decoder, int, int) { return false; }
-bool giflib_encoder_encode_frame(giflib_encoder, const giflib_decoder, const opencv_mat) { return false; }
-bool giflib_encoder_flush(giflib_encoder, const giflib_decoder) { return false; }
-void giflib_encoder_release(giflib_encoder e) { delete e; }
-int giflib_encoder_get_output_length(giflib_encoder) { return 0; }
+
+giflib_encoder giflib_encoder_create(void* buf, size_t buf_len) {  // ref giflib.cpp:773-800
+    auto* e = new giflib_encoder_struct;
+    e->dst = static_cast<uint8_t*>(buf);
+    e->dst_len = buf_len;
+    e->open = true;
+    return e;
+}
+
+// ref giflib.cpp:803-860 + EGifPutScreenDesc: "GIF89a", logical screen descriptor, global colour table
+bool giflib_encoder_init(giflib_encoder e, const giflib_decoder d, int width, int height) {
+    if (!e || !d || !e->open) return false;
+    e->sw = width;
+    e->sh = height;
+    const GifReader& r = d->rd;
+    e->has_gct = r.gct != nullptr;
+    e->bg = (e->has_gct && r.bg_index >= 0 && r.bg_index < r.gct_colors) ? r.bg_index : 0;
+    if (e->has_gct) e->gct.assign(r.gct, r.gct + (size_t)r.gct_colors * 3);
+    // packed byte: colour-table flag | (SColorResolution - 1) << 4 | sort flag | BitsPerPixel - 1, which for a
+    // file with a global table is the source's own byte; without one giflib writes 0x07 in the low bits
+    const uint8_t packed = e->has_gct ? r.packed : (uint8_t)((r.packed & 0x70) | 0x07);
+    if (!e->put("GIF89a", 6) || !e->put16(width) || !e->put16(height) || !e->put8(packed) || !e->put8((uint8_t)e->bg) ||
+        !e->put8(r.aspect))
+        return false;
+    if (e->has_gct && !e->put(e->gct.data(), e->gct.size())) return false;
+    return true;
+}
+
+bool giflib_encoder_encode_frame(giflib_encoder e, const giflib_decoder d, const opencv_mat opaque_frame) {
+    if (!e || !d || !e->open || !opaque_frame) return false;
+    // ---- giflib_encoder_setup_frame (ref giflib.cpp:862-920)
+    const GifImage& im_in = d->image;
+    const bool has_local = im_in.colors != nullptr;
+    std::vector<GifExt> ext = d->ext;  // this frame's extension blocks: delay, transparent index, comments ...
+    GifGcb gcb = get_frame_gcb(ext);
+    if (gcb.transparent != -1 && e->has_gct && !has_local && gcb.transparent == e->bg && d->bg_a == 255) {
+        gcb.transparent = -1;  // transparent colour == opaque background colour: drop the transparency
+        set_frame_gcb(ext, gcb);
+    }
+    // ---- giflib_encoder_render_frame (ref giflib.cpp:934-1098)
+    int cols = 0, rows = 0, type = 0;
+    const uint8_t* frame_dev = nullptr;
+    size_t frame_step = 0;
+    if (mat_device_view(opaque_frame, &cols, &rows, &type, &frame_dev, &frame_step)) return false;
+    if (type != CV_8UC4) {
+        fprintf(stderr, "[lilliput_b200] GIF encoder needs a BGRA frame\n");
+        return false;
+    }
+    if (cols > e->sw) {
+        fprintf(stderr, "encountered error, gif frame wider than gif global width\n");
+        return false;
+    }
+    if (rows > e->sh) {
+        fprintf(stderr, "encountered error, gif frame taller than gif global height\n");
+        return false;
+    }
+    const uint8_t* colors = has_local ? im_in.colors : (e->has_gct ? e->gct.data() : nullptr);
+    const int ncolors = has_local ? im_in.ncolors : (e->has_gct ? (int)e->gct.size() / 3 : 0);
+    if (!colors) {
+        fprintf(stderr, "encountered error, gif frame has no color map\n");
+        return false;
+    }
+    cudaStream_t st = thread_stream();
+    const size_t npix = (size_t)cols * rows;
+    const size_t canvas_bytes = (size_t)e->sw * e->sh * 4;
+    if (!e->d_prev) {
+        if (cudaMallocAsync(&e->d_prev, canvas_bytes, st) != cudaSuccess) return false;
+        if (cudaMallocAsync(&e->d_lookup, 32768 * sizeof(int16_t), st) != cudaSuccess) return false;
+        if (cudaMallocAsync(&e->d_first, 32768 * sizeof(uint32_t), st) != cudaSuccess) return false;
+        if (cudaMallocAsync(&e->d_first_dist, 32768 * sizeof(int), st) != cudaSuccess) return false;
+        if (cudaMallocAsync(&e->d_out_len, sizeof(uint32_t), st) != cudaSuccess) return false;
+        cudaMemsetAsync(e->d_prev, 0, canvas_bytes, st);
+    }
+    if (npix > e->pixels_cap) {
+        if (e->d_pixels) cudaFreeAsync(e->d_pixels, st);
+        if (e->d_out) cudaFreeAsync(e->d_out, st);
+        e->pixels_cap = npix;
+        e->out_cap = npix * 2 + npix / 100 + 4096;  // 12-bit codes: at most 1.5 B/pixel + sub-block bytes
+        if (cudaMallocAsync(&e->d_pixels, npix + 64, st) != cudaSuccess) return false;
+        if (cudaMallocAsync(&e->d_out, e->out_cap, st) != cudaSuccess) return false;
+    }
+    // reuse the memo when the palette is byte-equal to the previous frame's
+    bool clear_lookup = true;
+    if (e->have_written_first_frame && e->have_prev_colors && e->prev_colors.size() == (size_t)ncolors * 3)
+        clear_lookup = memcmp(e->prev_colors.data(), colors, (size_t)ncolors * 3) != 0;
+    if (clear_lookup) cudaMemsetAsync(e->d_lookup, 0xFF, 32768 * sizeof(int16_t), st);
+    cudaMemsetAsync(e->d_first, 0xFF, 32768 * sizeof(uint32_t), st);
+    GifEncFrame f;
+    f.frame = frame_dev;
+    f.step = frame_step;
+    f.width = cols;
+    f.height = rows;
+    f.canvas_w = e->sw;
+    f.prev = e->d_prev;
+    f.lookup = e->d_lookup;
+    f.first = e->d_first;
+    f.first_dist = e->d_first_dist;
+    f.pixels = e->d_pixels;
+    f.ncolors = ncolors;
+    f.transparent = gcb.transparent;
+    f.prev_valid = e->have_written_first_frame && (e->prev_frame_disposal == 0 || e->prev_frame_disposal == 1);
+    memset(f.palette, 0, sizeof(f.palette));
+    memcpy(f.palette, colors, (size_t)std::min(ncolors, 256) * 3);
+    dim3 grid(ceil_div(cols, 128), rows);
+    gif_enc_first_kernel<<<grid, 128, 0, st>>>(f);
+    gif_enc_bucket_kernel<<<32768 / 128, 128, 0, st>>>(f);
+    gif_enc_map_kernel<<<grid, 128, 0, st>>>(f);
+    g_launches += 3;
+    // prev_frame_bgra = this frame (ref giflib.cpp:1091: the whole canvas)
+    cudaMemcpy2DAsync(e->d_prev, (size_t)e->sw * 4, frame_dev, frame_step, (size_t)cols * 4, rows,
+                      cudaMemcpyDeviceToDevice, st);
+    e->prev_colors.assign(colors, colors + (size_t)ncolors * 3);
+    e->have_prev_colors = true;
+    e->prev_frame_disposal = gcb.disposal;
+    // ---- giflib_encoder_encode_frame (ref giflib.cpp:1126-1183): extensions, image descriptor, LZW
+    int bpp = 1;
+    while ((1 << bpp) < ncolors) bpp++;
+    const int code_bits = bpp < 2 ? 2 : bpp;
+    gif_lzw_encode_kernel<<<1, 32, 0, st>>>(e->d_pixels, cols, rows, im_in.interlace ? 1 : 0, code_bits, e->d_out,
+                                           (uint32_t)e->out_cap, e->d_out_len);
+    g_launches++;
+    uint32_t out_len = 0;
+    cudaMemcpyAsync(&out_len, e->d_out_len, sizeof(out_len), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+    if (out_len == 0xFFFFFFFFu) return false;
+    if (!write_extensions(e, ext)) return false;
+    const uint8_t flags = (uint8_t)((has_local ? 0x80 : 0) | (im_in.interlace ? 0x40 : 0) | (has_local ? bpp - 1 : 0));
+    if (!e->put8(0x2C) || !e->put16(0) || !e->put16(0) || !e->put16(cols) || !e->put16(rows) || !e->put8(flags)) return false;
+    if (has_local && !e->put(im_in.colors, (size_t)im_in.ncolors * 3)) return false;
+    if (!e->put8((uint8_t)code_bits)) return false;
+    if (e->dst_offset + out_len > e->dst_len) return false;
+    if (cudaMemcpy(e->dst + e->dst_offset, e->d_out, out_len, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    e->dst_offset += out_len;
+    e->have_written_first_frame = true;
+    return true;
+}
+
+// ref giflib.cpp:1185-1222: trailing extension blocks, then the GIF trailer
+bool giflib_encoder_flush(giflib_encoder e, const giflib_decoder d) {
+    if (!e || !d || !e->open) return false;
+    if (!write_extensions(e, d->ext)) return false;
+    if (!e->put8(0x3B)) return false;
+    e->open = false;
+    return true;
+}
+
+void giflib_encoder_release(giflib_encoder e) {
+    if (!e) return;
+    cudaStream_t st = thread_stream();
+    if (e->d_prev) cudaFreeAsync(e->d_prev, st);
+    if (e->d_lookup) cudaFreeAsync(e->d_lookup, st);
+    if (e->d_first) cudaFreeAsync(e->d_first, st);
+    if (e->d_first_dist) cudaFreeAsync(e->d_first_dist, st);
+    if (e->d_pixels) cudaFreeAsync(e->d_pixels, st);
+    if (e->d_out) cudaFreeAsync(e->d_out, st);
+    if (e->d_out_len) cudaFreeAsync(e->d_out_len, st);
+    delete e;
+}
+
+int giflib_encoder_get_output_length(giflib_encoder e) { return (int)e->dst_offset; }
 
 }  // extern "C"

@@ -10,8 +10,10 @@
  *   VP8L (lossless): prefix codes + meta prefix image, colour cache, LZ77, the four transforms;
  *   ALPH (alpha plane of a lossy frame): raw or VP8L-coded, with its prediction filters.
  *
- * Encode: the entry points exist so the Go package links; WebP *encoding* is not implemented
- * (SURVEY.md 8 row R8): webp_encoder_create returns NULL, which webp.go:214-217 maps to an error.
+ * Encode (ref webp.cpp:388-783): lossless (quality > 100) and lossy stills, alpha through an ALPH
+ * chunk, ICC, and animations as full-canvas ANMF frames, all encoded on the device by this
+ * library's own VP8L / VP8 encoders: lossless output is pixel-exact; lossy output is a valid stream at
+ * libwebp's quality->quantiser mapping, not libwebp's bytes.
  */
 #ifndef LP_WEBP_H
 #define LP_WEBP_H

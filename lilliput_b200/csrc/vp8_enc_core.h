@@ -1,0 +1,471 @@
+// vp8_enc_core.h -- a VP8 key-frame (WebP lossy) ENCODER: 16x16 / chroma intra mode choice by
+// prediction error, forward DCT / WHT, dead-zone quantisation, in-loop reconstruction, token
+// coding with the default coefficient probabilities, boolean entropy coder, frame + partition
+// headers (RFC 6386).  Valid streams that any VP8 decoder (libwebp included) reads; NOT libwebp's
+// encoder: no rate-distortion search, no 4x4 intra modes, no segmentation, no probability
+// adaptation -- so files are not byte-comparable with the reference's (ref webp.cpp:721-729 calls
+// WebPEncodeBGR / BGRA), and at equal `quality` this encoder spends more bits for the same PSNR.
+// What IS checked (tests): the reference's decoder and vp8_core.h decode the stream to the same
+// pixels, those equal the encoder's own reconstruction, and PSNR tracks libwebp's at equal quality.
+//
+// Shares the decoder's primitives (vp8_core.h): prediction, inverse transforms, tables.
+#pragma once
+#include "vp8_core.h"
+
+namespace vp8enc {
+
+using vp8::BPS;
+
+// ---- boolean entropy encoder (RFC 6386 s.7.3) ----------------------------------------------
+struct BoolEnc {
+    uint8_t* out;
+    size_t pos, cap;
+    uint32_t range, bottom;
+    int bit_count;
+    int overflow;
+};
+LP_VP8_INL void be_init(BoolEnc& e, uint8_t* out, size_t cap) {
+    e.out = out;
+    e.pos = 0;
+    e.cap = cap;
+    e.range = 255;
+    e.bottom = 0;
+    e.bit_count = 24;
+    e.overflow = 0;
+}
+LP_VP8_INL void be_carry(BoolEnc& e) {
+    size_t q = e.pos;
+    while (q > 0 && e.out[q - 1] == 255) e.out[--q] = 0;
+    if (q > 0) e.out[q - 1]++;
+}
+LP_VP8_INL void be_put(BoolEnc& e, int bit, int prob) {
+    const uint32_t split = 1 + (((e.range - 1) * (uint32_t)prob) >> 8);
+    if (bit) {
+        e.bottom += split;
+        e.range -= split;
+    } else {
+        e.range = split;
+    }
+    while (e.range < 128) {
+        e.range <<= 1;
+        if (e.bottom & 0x80000000u) be_carry(e);
+        e.bottom <<= 1;
+        if (!--e.bit_count) {
+            if (e.pos < e.cap) e.out[e.pos++] = (uint8_t)(e.bottom >> 24);
+            else e.overflow = 1;
+            e.bottom &= 0xffffffu;
+            e.bit_count = 8;
+        }
+    }
+}
+LP_VP8_INL void be_put_bits(BoolEnc& e, uint32_t v, int n) {
+    while (n-- > 0) be_put(e, (v >> n) & 1, 128);
+}
+LP_VP8_INL void be_put_signed(BoolEnc& e, int v, int n) {  // magnitude then sign, the decoder's bd_signed
+    be_put_bits(e, (uint32_t)(v < 0 ? -v : v), n);
+    be_put(e, v < 0, 128);
+}
+LP_VP8_FN void be_flush(BoolEnc& e) {
+    int c = e.bit_count;
+    uint32_t v = e.bottom;
+    if (v & (1u << (32 - c))) be_carry(e);
+    v <<= c & 7;
+    c >>= 3;
+    while (--c >= 0) v <<= 8;
+    for (int i = 0; i < 4; i++) {
+        if (e.pos < e.cap) e.out[e.pos++] = (uint8_t)(v >> 24);
+        else e.overflow = 1;
+        v <<= 8;
+    }
+}
+
+// ---- forward transforms (the inverses are vp8::inverse_dct_add / inverse_wht) ----------------
+LP_VP8_FN void fdct4x4(const uint8_t* src, int src_stride, const uint8_t* ref, int ref_stride, int16_t* out) {
+    int tmp[16];
+    for (int i = 0; i < 4; i++) {
+        const int d0 = src[i * src_stride + 0] - ref[i * ref_stride + 0];
+        const int d1 = src[i * src_stride + 1] - ref[i * ref_stride + 1];
+        const int d2 = src[i * src_stride + 2] - ref[i * ref_stride + 2];
+        const int d3 = src[i * src_stride + 3] - ref[i * ref_stride + 3];
+        const int a0 = d0 + d3, a1 = d1 + d2, a2 = d1 - d2, a3 = d0 - d3;
+        tmp[0 + i * 4] = (a0 + a1) * 8;
+        tmp[1 + i * 4] = (a2 * 2217 + a3 * 5352 + 1812) >> 9;
+        tmp[2 + i * 4] = (a0 - a1) * 8;
+        tmp[3 + i * 4] = (a3 * 2217 - a2 * 5352 + 937) >> 9;
+    }
+    for (int i = 0; i < 4; i++) {
+        const int a0 = tmp[0 + i] + tmp[12 + i], a1 = tmp[4 + i] + tmp[8 + i];
+        const int a2 = tmp[4 + i] - tmp[8 + i], a3 = tmp[0 + i] - tmp[12 + i];
+        out[0 + i] = (int16_t)((a0 + a1 + 7) >> 4);
+        out[4 + i] = (int16_t)(((a2 * 2217 + a3 * 5352 + 12000) >> 16) + (a3 != 0));
+        out[8 + i] = (int16_t)((a0 - a1 + 7) >> 4);
+        out[12 + i] = (int16_t)((a3 * 2217 - a2 * 5352 + 51000) >> 16);
+    }
+}
+// in: the 16 DC terms (element 0 of 16 coefficient blocks, stride 16); out: 16 Y2 coefficients
+LP_VP8_FN void fwht(const int16_t* in, int16_t* out) {
+    int tmp[16];
+    for (int i = 0; i < 4; i++, in += 64) {
+        const int a0 = in[0 * 16] + in[2 * 16], a1 = in[1 * 16] + in[3 * 16];
+        const int a2 = in[1 * 16] - in[3 * 16], a3 = in[0 * 16] - in[2 * 16];
+        tmp[0 + i * 4] = a0 + a1;
+        tmp[1 + i * 4] = a3 + a2;
+        tmp[2 + i * 4] = a3 - a2;
+        tmp[3 + i * 4] = a0 - a1;
+    }
+    for (int i = 0; i < 4; i++) {
+        const int a0 = tmp[0 + i] + tmp[8 + i], a1 = tmp[4 + i] + tmp[12 + i];
+        const int a2 = tmp[4 + i] - tmp[12 + i], a3 = tmp[0 + i] - tmp[8 + i];
+        out[0 + i] = (int16_t)((a0 + a1) >> 1);
+        out[4 + i] = (int16_t)((a3 + a2) >> 1);
+        out[8 + i] = (int16_t)((a3 - a2) >> 1);
+        out[12 + i] = (int16_t)((a0 - a1) >> 1);
+    }
+}
+
+// Dead-zone quantiser: level = (|c| + bias * step / 256) / step, clamped to the token range.
+// coeffs (raster) -> levels (raster, signed); also leaves the dequantised values in coeffs.
+LP_VP8_FN int quantize_block(int16_t* coeffs, int16_t* levels, const int* dq, int first, int bias_dc, int bias_ac) {
+    int last = -1;
+    const uint8_t zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+    for (int n = 0; n < 16; n++) {
+        const int j = zigzag[n];
+        if (n < first) {
+            levels[j] = 0;
+            continue;  // coeffs[j] keeps the value the caller planted (DC from Y2)
+        }
+        const int step = dq[n > 0];
+        const int c = coeffs[j], a = c < 0 ? -c : c;
+        int lv = (a + ((n > 0 ? bias_ac : bias_dc) * step >> 8)) / step;
+        if (lv > 2047) lv = 2047;
+        levels[j] = (int16_t)(c < 0 ? -lv : lv);
+        coeffs[j] = (int16_t)(levels[j] * step);
+        if (lv) last = n;
+    }
+    return last;  // scan position of the last non-zero level, -1 if none
+}
+
+// ---- token writer: the exact mirror of vp8::get_coeffs --------------------------------------
+LP_VP8_FN void put_large_value(BoolEnc& e, int v, const uint8_t* p) {
+    if (v <= 4) {
+        be_put(e, 0, p[3]);
+        if (v == 2) be_put(e, 0, p[4]);
+        else {
+            be_put(e, 1, p[4]);
+            be_put(e, v == 4, p[5]);
+        }
+    } else if (v <= 10) {
+        be_put(e, 1, p[3]);
+        be_put(e, 0, p[6]);
+        if (v <= 6) {
+            be_put(e, 0, p[7]);
+            be_put(e, v == 6, 159);
+        } else {
+            be_put(e, 1, p[7]);
+            be_put(e, v >= 9, 165);
+            be_put(e, (v - 7) & 1, 145);
+        }
+    } else {
+        be_put(e, 1, p[3]);
+        be_put(e, 1, p[6]);
+        const int cat = v < 19 ? 0 : v < 35 ? 1 : v < 67 ? 2 : 3;
+        be_put(e, cat >> 1, p[8]);
+        be_put(e, cat & 1, p[9 + (cat >> 1)]);
+        const int extra = v - (3 + (8 << cat));
+        const uint8_t c3[3] = {173, 148, 140}, c4[4] = {176, 155, 140, 135}, c5[5] = {180, 157, 141, 134, 130};
+        const uint8_t c6[11] = {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129};
+        const int nb = cat == 3 ? 11 : cat + 3;
+        const uint8_t* tab = cat == 0 ? c3 : cat == 1 ? c4 : cat == 2 ? c5 : c6;
+        for (int i = 0; i < nb; i++) be_put(e, (extra >> (nb - 1 - i)) & 1, tab[i]);
+    }
+}
+// levels in raster order; returns 1 when the block has a non-zero level at or after `first`.
+LP_VP8_FN int put_coeffs(BoolEnc& e, const uint8_t* proba, int type, int ctx, int first, const int16_t* levels) {
+    const uint8_t bands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
+    const uint8_t zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+    const uint8_t* tp = proba + type * (8 * 3 * 11);
+    int last = -1;
+    for (int n = first; n < 16; n++)
+        if (levels[zigzag[n]]) last = n;
+    int n = first;
+    const uint8_t* p = tp + (bands[n] * 3 + ctx) * 11;
+    if (last < 0) {
+        be_put(e, 0, p[0]);
+        return 0;
+    }
+    be_put(e, 1, p[0]);
+    while (n < 16) {
+        const int c = levels[zigzag[n]];
+        const int v = c < 0 ? -c : c;
+        if (!v) {
+            be_put(e, 0, p[1]);
+            p = tp + (bands[++n] * 3 + 0) * 11;
+            continue;
+        }
+        be_put(e, 1, p[1]);
+        int next_ctx;
+        if (v == 1) {
+            be_put(e, 0, p[2]);
+            next_ctx = 1;
+        } else {
+            be_put(e, 1, p[2]);
+            put_large_value(e, v, p);
+            next_ctx = 2;
+        }
+        be_put(e, c < 0, 128);
+        if (++n == 16) break;
+        p = tp + (bands[n] * 3 + next_ctx) * 11;
+        if (n > last) {
+            be_put(e, 0, p[0]);  // end of block
+            break;
+        }
+        be_put(e, 1, p[0]);
+    }
+    return 1;
+}
+
+// ---- colour conversion (BT.601 limited range, 16.16 fixed point like libwebp's importer) -----
+LP_VP8_INL int rgb_to_y(int r, int g, int b) { return (16839 * r + 33059 * g + 6420 * b + (16 << 16) + (1 << 15)) >> 16; }
+// r, g, b are SUMS over a 2x2 block
+LP_VP8_INL int rgb_to_u(int r, int g, int b) { return vp8::clip8((-9719 * r - 19081 * g + 28800 * b + (128 << 18) + (1 << 17)) >> 18); }
+LP_VP8_INL int rgb_to_v(int r, int g, int b) { return vp8::clip8((28800 * r - 24116 * g - 4684 * b + (128 << 18) + (1 << 17)) >> 18); }
+
+// ---- quality -> quantiser index (libwebp's mapping, so `quality` means the same thing) --------
+// q = 127 * (1 - cbrt(linear(quality / 100))), linear(c) = c < 0.75 ? c * 2/3 : 2c - 1.
+// Integer cube root by search keeps this usable without libm on the device.
+LP_VP8_HD int quality_to_q(int quality) {
+    if (quality < 0) quality = 0;
+    if (quality > 100) quality = 100;
+    // linear_c in 1/3000 units: c < 0.75 -> c*2/3 = quality*20/3000 ; else 2c-1 = (quality*60 - 3000)/3000
+    const long lin = quality < 75 ? (long)quality * 20 : (long)quality * 60 - 3000;  // / 3000
+    // v = cbrt(lin/3000); find the largest k in 0..127 with ((127 - k)/127)^3 >= lin/3000  <=>  q = k
+    // (q = floor(127 * (1 - v))  <=>  127 - q is the smallest integer m with m >= 127 v ... solve by scan)
+    int q = 0;
+    for (int k = 127; k >= 0; k--) {
+        // 127*(1 - v) >= k  <=>  v <= (127 - k)/127  <=>  lin/3000 <= ((127-k)/127)^3
+        const long m = 127 - k;
+        if (lin * 127 * 127 * 127 <= m * m * m * 3000) {
+            q = k;
+            break;
+        }
+    }
+    return q;
+}
+
+// Loop-filter level from the quantiser: stronger quantisation, stronger deblocking (0 = off).
+LP_VP8_FN int filter_level_for_q(int q) {
+    const int level = kVp8AcTable[q] * 3 / 10;
+    return level < 2 ? 0 : level > 63 ? 63 : level;
+}
+
+// ---- the encoder ----------------------------------------------------------------------------
+struct Params {
+    int width, height, mb_w, mb_h;
+    int q;             // quantiser index 0..127
+    int filter_level;  // 0..63
+};
+
+// Source planes: mb_w*16 x mb_h*16 luma, half-size chroma, padded by edge replication.
+// recon_*: same geometry, written here (the decoder's unfiltered reconstruction).
+// levels: mb_w*mb_h*25*16 int16 (blocks 0..15 Y, 16..19 U, 20..23 V, 24 Y2), modes: 2 bytes per MB.
+struct Buffers {
+    const uint8_t *sy, *su, *sv;
+    uint8_t *ry, *ru, *rv;
+    int16_t* levels;
+    uint8_t* modes;
+};
+
+LP_VP8_FN uint32_t sse_block(const uint8_t* a, int as, const uint8_t* b, int bs, int size) {
+    uint32_t s = 0;
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) {
+            const int d = a[y * as + x] - b[y * bs + x];
+            s += (uint32_t)(d * d);
+        }
+    return s;
+}
+
+// Pass 1: mode decision, transform, quantisation and reconstruction of every macroblock, raster order.
+LP_VP8_FN void analyse_and_reconstruct(const Params& P, const Buffers& B) {
+    const int ys = P.mb_w * 16, cs = P.mb_w * 8;
+    vp8::QuantMat qm;
+    qm.y1[0] = kVp8DcTable[P.q];
+    qm.y1[1] = kVp8AcTable[P.q];
+    qm.y2[0] = kVp8DcTable[P.q] * 2;
+    qm.y2[1] = (kVp8AcTable[P.q] * 101581) >> 16;
+    if (qm.y2[1] < 8) qm.y2[1] = 8;
+    qm.uv[0] = kVp8DcTable[P.q > 117 ? 117 : P.q];
+    qm.uv[1] = kVp8AcTable[P.q];
+    uint8_t yb[vp8::YB_SIZE], ub[vp8::CB_SIZE], vb[vp8::CB_SIZE];
+    int16_t coeffs[25 * 16];
+    for (int mb_y = 0; mb_y < P.mb_h; mb_y++)
+        for (int mb_x = 0; mb_x < P.mb_w; mb_x++) {
+            uint8_t* yd = yb + BPS + 8;
+            uint8_t* ud = ub + BPS + 8;
+            uint8_t* vd = vb + BPS + 8;
+            const uint8_t* sy = B.sy + (size_t)mb_y * 16 * ys + mb_x * 16;
+            const uint8_t* su = B.su + (size_t)mb_y * 8 * cs + mb_x * 8;
+            const uint8_t* sv = B.sv + (size_t)mb_y * 8 * cs + mb_x * 8;
+            uint8_t* py = B.ry + (size_t)mb_y * 16 * ys + mb_x * 16;
+            uint8_t* pu = B.ru + (size_t)mb_y * 8 * cs + mb_x * 8;
+            uint8_t* pv = B.rv + (size_t)mb_y * 8 * cs + mb_x * 8;
+            // prediction borders from the reconstruction, as the decoder will see them (s.12.2)
+            for (int j = 0; j < 16; j++) yd[j * BPS - 1] = mb_x > 0 ? py[j * ys - 1] : 129;
+            for (int j = 0; j < 8; j++) {
+                ud[j * BPS - 1] = mb_x > 0 ? pu[j * cs - 1] : 129;
+                vd[j * BPS - 1] = mb_x > 0 ? pv[j * cs - 1] : 129;
+            }
+            for (int i = -1; i < 16; i++)
+                yd[i - BPS] = mb_y > 0 ? ((i < 0 && mb_x == 0) ? 129 : py[i - ys]) : 127;
+            for (int i = -1; i < 8; i++) {
+                ud[i - BPS] = mb_y > 0 ? ((i < 0 && mb_x == 0) ? 129 : pu[i - cs]) : 127;
+                vd[i - BPS] = mb_y > 0 ? ((i < 0 && mb_x == 0) ? 129 : pv[i - cs]) : 127;
+            }
+            // luma 16x16 mode: least squared prediction error
+            int ymode = 0;
+            uint32_t best = 0xffffffffu;
+            for (int m = 0; m < 4; m++) {
+                vp8::pred_block(yd, BPS, 16, m, mb_y > 0, mb_x > 0);
+                const uint32_t s = sse_block(sy, ys, yd, BPS, 16);
+                if (s < best) {
+                    best = s;
+                    ymode = m;
+                }
+            }
+            vp8::pred_block(yd, BPS, 16, ymode, mb_y > 0, mb_x > 0);
+            int uvmode = 0;
+            best = 0xffffffffu;
+            for (int m = 0; m < 4; m++) {
+                vp8::pred_block(ud, BPS, 8, m, mb_y > 0, mb_x > 0);
+                vp8::pred_block(vd, BPS, 8, m, mb_y > 0, mb_x > 0);
+                const uint32_t s = sse_block(su, cs, ud, BPS, 8) + sse_block(sv, cs, vd, BPS, 8);
+                if (s < best) {
+                    best = s;
+                    uvmode = m;
+                }
+            }
+            vp8::pred_block(ud, BPS, 8, uvmode, mb_y > 0, mb_x > 0);
+            vp8::pred_block(vd, BPS, 8, uvmode, mb_y > 0, mb_x > 0);
+            // residual transforms + quantisation
+            int16_t* lv = B.levels + ((size_t)mb_y * P.mb_w + mb_x) * 25 * 16;
+            for (int n = 0; n < 16; n++)
+                fdct4x4(sy + (n >> 2) * 4 * ys + (n & 3) * 4, ys, yd + (n >> 2) * 4 * BPS + (n & 3) * 4, BPS, coeffs + n * 16);
+            fwht(coeffs, coeffs + 24 * 16);
+            quantize_block(coeffs + 24 * 16, lv + 24 * 16, qm.y2, 0, 96, 108);
+            vp8::inverse_wht(coeffs + 24 * 16, coeffs);  // plants the dequantised DCs
+            for (int n = 0; n < 16; n++) quantize_block(coeffs + n * 16, lv + n * 16, qm.y1, 1, 96, 110);
+            for (int n = 0; n < 4; n++) {
+                fdct4x4(su + (n >> 1) * 4 * cs + (n & 1) * 4, cs, ud + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS, coeffs + (16 + n) * 16);
+                fdct4x4(sv + (n >> 1) * 4 * cs + (n & 1) * 4, cs, vd + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS, coeffs + (20 + n) * 16);
+                quantize_block(coeffs + (16 + n) * 16, lv + (16 + n) * 16, qm.uv, 0, 110, 115);
+                quantize_block(coeffs + (20 + n) * 16, lv + (20 + n) * 16, qm.uv, 0, 110, 115);
+            }
+            // reconstruction, exactly as the decoder will do it
+            for (int n = 0; n < 16; n++) vp8::inverse_dct_add(coeffs + n * 16, yd + (n >> 2) * 4 * BPS + (n & 3) * 4, BPS);
+            for (int n = 0; n < 4; n++) {
+                vp8::inverse_dct_add(coeffs + (16 + n) * 16, ud + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
+                vp8::inverse_dct_add(coeffs + (20 + n) * 16, vd + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
+            }
+            for (int j = 0; j < 16; j++)
+                for (int i = 0; i < 16; i++) py[j * ys + i] = yd[j * BPS + i];
+            for (int j = 0; j < 8; j++)
+                for (int i = 0; i < 8; i++) {
+                    pu[j * cs + i] = ud[j * BPS + i];
+                    pv[j * cs + i] = vd[j * BPS + i];
+                }
+            B.modes[((size_t)mb_y * P.mb_w + mb_x) * 2 + 0] = (uint8_t)ymode;
+            B.modes[((size_t)mb_y * P.mb_w + mb_x) * 2 + 1] = (uint8_t)uvmode;
+        }
+}
+
+// Pass 2: the bitstream.  part0 / tokens are scratch areas; `out` receives the "VP8 " chunk payload.
+// top_nz: mb_w*9 bytes of scratch.  Returns the payload size, 0 when it does not fit.
+LP_VP8_FN size_t write_bitstream(const Params& P, const Buffers& B, uint8_t* part0, size_t part0_cap, uint8_t* tokens,
+                                 size_t tokens_cap, uint8_t* top_nz, uint8_t* out, size_t out_cap) {
+    BoolEnc h;
+    be_init(h, part0, part0_cap);
+    be_put_bits(h, 0, 1);  // colour space
+    be_put_bits(h, 0, 1);  // clamping type: clamping required
+    be_put_bits(h, 0, 1);  // no segmentation
+    be_put_bits(h, 0, 1);  // normal loop filter
+    be_put_bits(h, (uint32_t)P.filter_level, 6);
+    be_put_bits(h, 0, 3);  // sharpness
+    be_put_bits(h, 0, 1);  // no loop-filter deltas
+    be_put_bits(h, 0, 2);  // one token partition
+    be_put_bits(h, (uint32_t)P.q, 7);
+    for (int i = 0; i < 5; i++) be_put_bits(h, 0, 1);  // no quantiser deltas
+    be_put_bits(h, 0, 1);                               // refresh_entropy_probs
+    {
+        const uint8_t* upd = &kVp8CoeffUpdateProba[0][0][0][0];
+        for (int i = 0; i < 4 * 8 * 3 * 11; i++) be_put(h, 0, upd[i]);  // keep the default probabilities
+    }
+    be_put_bits(h, 0, 1);  // mb_no_coeff_skip = 0: no per-macroblock skip flag
+    for (int i = 0; i < P.mb_w * P.mb_h; i++) {
+        const int ymode = B.modes[i * 2], uvmode = B.modes[i * 2 + 1];
+        be_put(h, 1, 145);  // not 4x4
+        if (ymode == vp8::TM_PRED || ymode == vp8::H_PRED) {
+            be_put(h, 1, 156);
+            be_put(h, ymode == vp8::TM_PRED, 128);
+        } else {
+            be_put(h, 0, 156);
+            be_put(h, ymode == vp8::V_PRED, 163);
+        }
+        if (uvmode == vp8::DC_PRED) {
+            be_put(h, 0, 142);
+        } else {
+            be_put(h, 1, 142);
+            if (uvmode == vp8::V_PRED) {
+                be_put(h, 0, 114);
+            } else {
+                be_put(h, 1, 114);
+                be_put(h, uvmode == vp8::TM_PRED, 183);
+            }
+        }
+    }
+    be_flush(h);
+    BoolEnc t;
+    be_init(t, tokens, tokens_cap);
+    const uint8_t* proba = &kVp8CoeffProba0[0][0][0][0];
+    for (int i = 0; i < P.mb_w * 9; i++) top_nz[i] = 0;
+    for (int mb_y = 0; mb_y < P.mb_h; mb_y++) {
+        uint8_t left_nz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int mb_x = 0; mb_x < P.mb_w; mb_x++) {
+            const int16_t* lv = B.levels + ((size_t)mb_y * P.mb_w + mb_x) * 25 * 16;
+            uint8_t* tnz = top_nz + mb_x * 9;
+            for (int k = -1; k < 24; k++) {  // Y2, 16 Y, 4 U, 4 V: the decoder's order and contexts
+                int type, ti, li, first = 0;
+                const int16_t* blk;
+                if (k < 0) {
+                    type = 1; ti = 8; li = 8; blk = lv + 24 * 16;
+                } else if (k < 16) {
+                    type = 0; ti = k & 3; li = k >> 2; blk = lv + k * 16; first = 1;
+                } else {
+                    const int c = k - 16;
+                    type = 2; ti = 4 + (c >> 2) * 2 + (c & 1); li = 4 + (c >> 2) * 2 + ((c >> 1) & 1); blk = lv + k * 16;
+                }
+                const int nz = put_coeffs(t, proba, type, tnz[ti] + left_nz[li], first, blk);
+                tnz[ti] = left_nz[li] = (uint8_t)nz;
+            }
+        }
+    }
+    be_flush(t);
+    if (h.overflow || t.overflow) return 0;
+    const size_t total = 10 + h.pos + t.pos;
+    if (total > out_cap || h.pos >= (1u << 19)) return 0;
+    const uint32_t tag = 0u | (0u << 1) | (1u << 4) | ((uint32_t)h.pos << 5);  // key frame, profile 0, shown
+    out[0] = (uint8_t)tag;
+    out[1] = (uint8_t)(tag >> 8);
+    out[2] = (uint8_t)(tag >> 16);
+    out[3] = 0x9d;
+    out[4] = 0x01;
+    out[5] = 0x2a;
+    out[6] = (uint8_t)P.width;
+    out[7] = (uint8_t)((P.width >> 8) & 0x3f);
+    out[8] = (uint8_t)P.height;
+    out[9] = (uint8_t)((P.height >> 8) & 0x3f);
+    for (size_t i = 0; i < h.pos; i++) out[10 + i] = part0[i];
+    for (size_t i = 0; i < t.pos; i++) out[10 + h.pos + i] = tokens[i];
+    return total;
+}
+
+}  // namespace vp8enc

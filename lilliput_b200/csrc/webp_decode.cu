@@ -578,10 +578,6 @@ struct webp_decoder_struct {
     size_t in_cap = 0, work_cap = 0, arena_cap = 0, alpha_cap = 0, alph_in_cap = 0;
 };
 
-struct webp_encoder_struct {
-    int unused;
-};
-
 extern "C" {
 
 // ref webp.cpp:61-139
@@ -723,11 +719,5 @@ bool webp_decoder_decode(const webp_decoder d, opencv_mat mat) {
     mat_mark_device_written(mat);
     return true;
 }
-
-// ---- encoder: not implemented (see include/lp_webp.h) ---------------------------------------
-webp_encoder webp_encoder_create(void*, size_t, const void*, size_t, uint32_t, int) { return nullptr; }
-size_t webp_encoder_write(webp_encoder, const opencv_mat, const int*, size_t, int, int, int, int, int) { return 0; }
-void webp_encoder_release(webp_encoder) {}
-size_t webp_encoder_flush(webp_encoder) { return 0; }
 
 }  // extern "C"

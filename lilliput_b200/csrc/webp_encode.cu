@@ -1,0 +1,424 @@
+// webp_encode.cu -- lilliput's WebP encoder surface (include/lp_webp.h = ref webp.hpp:56-73) on
+// sm_100a.  Replaces webp_encoder_* (ref webp.cpp:388-783), i.e. libwebp's WebPEncodeBGR(A) /
+// WebPEncodeLosslessBGR(A) for the first frame, WebPAnimEncoder for animations, and libwebpmux's
+// assembly (VP8X / ICCP / ANIM / ANMF / ALPH chunks).
+//
+//   lossless (quality > 100, ref webp.cpp:466-470): vp8l_enc_core.h -- residuals and histograms per
+//     pixel in parallel, prefix codes on the host (a few hundred symbols), a prefix sum of the
+//     per-pixel bit lengths, then every pixel packed in parallel.  Exact by construction.
+//   lossy: vp8_enc_core.h -- parallel BGR -> YUV 4:2:0, then one thread per frame walks the
+//     macroblocks (mode choice, transforms, quantisation, reconstruction) and the two boolean-coded
+//     partitions.  A valid VP8 stream at libwebp's quality->quantiser mapping; NOT libwebp's
+//     rate-distortion-optimised choices, so the bytes differ from the reference's by design
+//     (DESIGN.md s.1 row R8 says what is and is not claimed).
+//   alpha of a lossy frame: an ALPH chunk holding a VP8L-coded plane (same lossless coder).
+//   animation: every frame a full-canvas ANMF (no blending, no disposal), durations = the delays
+//     handed to webp_encoder_write.  (The reference's WebPAnimEncoder also searches sub-rectangles
+//     and key-frame placement; that is a size optimisation, not a semantic one.)
+#include <cstring>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "lp_webp.h"
+
+#define LP_VP8_FN static __device__
+#define LP_VP8_INL static __device__ __forceinline__
+#define LP_VP8_HD static __host__ __device__
+#define LP_VP8_TABLE static __device__ const
+#include "vp8_enc_core.h"
+
+#define LP_L_HD static __host__ __device__ __forceinline__
+#include "vp8l_enc_core.h"
+
+namespace lp {
+
+int mat_device_view(void* mat, int* cols, int* rows, int* type, const uint8_t** dev, size_t* step);
+
+// ------------------------------------------------------------------ lossless kernels
+
+__global__ void vp8l_residual_kernel(const uint8_t* frame, size_t step, int channels, int width, int height,
+                                     uint32_t* resid, uint32_t* hist /* 4 x 256 */) {
+    __shared__ uint32_t sh[4 * 256];
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < width) {
+        const uint32_t r = vp8lenc::residual_at(frame, step, channels, x, y);
+        resid[(size_t)y * width + x] = r;
+        atomicAdd(&sh[(r >> 8) & 255], 1u);
+        atomicAdd(&sh[256 + ((r >> 16) & 255)], 1u);
+        atomicAdd(&sh[512 + (r & 255)], 1u);
+        atomicAdd(&sh[768 + (r >> 24)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+__global__ void vp8l_bitlen_kernel(const uint32_t* resid, size_t n, const vp8lenc::CodeTable* table, unsigned long long* len) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = resid[i];
+    len[i] = (unsigned long long)(table->len[0][(r >> 8) & 255] + table->len[1][(r >> 16) & 255] + table->len[2][r & 255] +
+                                  table->len[3][r >> 24]);
+}
+
+__global__ void vp8l_pack_kernel(const uint32_t* resid, size_t n, const vp8lenc::CodeTable* table,
+                                 const unsigned long long* off, unsigned long long base_bit, uint32_t* out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t bits;
+    int nb;
+    vp8lenc::pixel_bits(resid[i], *table, &bits, &nb);
+    if (!nb) return;
+    const unsigned long long at = base_bit + off[i];
+    const size_t w = (size_t)(at >> 5);
+    const int sh = (int)(at & 31);
+    const uint64_t lo = bits << sh;
+    const uint64_t hi = sh ? bits >> (64 - sh) : 0;
+    if ((uint32_t)lo) atomicOr(&out[w], (uint32_t)lo);
+    if ((uint32_t)(lo >> 32)) atomicOr(&out[w + 1], (uint32_t)(lo >> 32));
+    if ((uint32_t)hi) atomicOr(&out[w + 2], (uint32_t)hi);
+}
+
+__global__ void extract_alpha_kernel(const uint8_t* frame, size_t step, int width, int height, uint8_t* plane) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < width) plane[(size_t)y * width + x] = frame[(size_t)y * step + (size_t)x * 4 + 3];
+}
+
+// frame (channels 3/4) -> "VP8L" payload; plane (channels 1) -> "ALPH" payload.
+static int vp8l_encode_dev(const uint8_t* d_frame, size_t step, int width, int height, int channels,
+                           std::vector<uint8_t>* out, cudaStream_t st) {
+    const size_t npix = (size_t)width * height;
+    uint8_t* scratch = nullptr;
+    const size_t resid_b = round_up(npix * 4, (size_t)256), len_b = round_up(npix * 8, (size_t)256);
+    const size_t table_b = round_up(sizeof(vp8lenc::CodeTable), (size_t)256);
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)npix, st);
+    cub_bytes = round_up(cub_bytes + 256, (size_t)256);
+    LP_CUDA_OK(cudaMallocAsync(&scratch, 4096 + table_b + resid_b + 2 * len_b + cub_bytes, st));
+    uint32_t* d_hist = reinterpret_cast<uint32_t*>(scratch);
+    auto* d_table = reinterpret_cast<vp8lenc::CodeTable*>(scratch + 4096);
+    uint32_t* d_resid = reinterpret_cast<uint32_t*>(scratch + 4096 + table_b);
+    auto* d_len = reinterpret_cast<unsigned long long*>(scratch + 4096 + table_b + resid_b);
+    auto* d_off = d_len + len_b / 8;
+    void* d_cub = reinterpret_cast<uint8_t*>(d_off) + len_b;
+    int rc = LP_OK;
+    uint32_t* d_out = nullptr;
+    do {
+        cudaMemsetAsync(d_hist, 0, 4096, st);
+        dim3 grid(ceil_div(width, 256), height);
+        vp8l_residual_kernel<<<grid, 256, 0, st>>>(d_frame, step, channels, width, height, d_resid, d_hist);
+        g_launches++;
+        uint32_t hist[4 * 256];
+        if (cudaMemcpyAsync(hist, d_hist, sizeof(hist), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            rc = LP_ERR_CUDA;
+            break;
+        }
+        vp8lenc::BitWriter bw;
+        vp8lenc::CodeTable table;
+        if (channels == 1) bw.put(1, 8);  // ALPH header byte: VP8L-compressed, no filter, no pre-processing
+        vp8lenc::write_stream_head(bw, width, height, channels == 4, channels != 1, channels != 1, hist, &table);
+        const unsigned long long base_bit = bw.nbits;
+        cudaMemcpyAsync(d_table, &table, sizeof(table), cudaMemcpyHostToDevice, st);
+        const int blocks = (int)ceil_div(npix, (size_t)256);
+        vp8l_bitlen_kernel<<<blocks, 256, 0, st>>>(d_resid, npix, d_table, d_len);
+        cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_len, d_off, (int)npix, st);
+        g_launches += 2;
+        unsigned long long last_off = 0, last_len = 0;
+        cudaMemcpyAsync(&last_off, d_off + (npix - 1), 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&last_len, d_len + (npix - 1), 8, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) {
+            rc = LP_ERR_CUDA;
+            break;
+        }
+        const unsigned long long total_bits = base_bit + last_off + last_len;
+        const size_t total_bytes = (size_t)((total_bits + 7) / 8);
+        const size_t words = total_bytes / 4 + 4;
+        if (cudaMallocAsync(&d_out, words * 4, st) != cudaSuccess) {
+            rc = LP_ERR_CUDA;
+            break;
+        }
+        cudaMemsetAsync(d_out, 0, words * 4, st);
+        bw.flush();  // the head's last partial byte: its unused high bits are zero, pixels OR in above them
+        cudaMemcpyAsync(d_out, bw.bytes.data(), bw.bytes.size(), cudaMemcpyHostToDevice, st);
+        vp8l_pack_kernel<<<blocks, 256, 0, st>>>(d_resid, npix, d_table, d_off, base_bit, d_out);
+        g_launches++;
+        out->resize(total_bytes);
+        if (cudaMemcpyAsync(out->data(), d_out, total_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            rc = LP_ERR_CUDA;
+    } while (0);
+    if (d_out) cudaFreeAsync(d_out, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+// ------------------------------------------------------------------ lossy kernels
+
+// BGR(A) -> padded Y / U / V planes (edge replication up to the macroblock grid).
+__global__ void vp8_planes_kernel(const uint8_t* frame, size_t step, int channels, int width, int height, int ys, int yh,
+                                  uint8_t* sy, uint8_t* su, uint8_t* sv) {
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;  // one chroma sample = 2x2 luma
+    if (cx >= ys / 2) return;
+    int r = 0, g = 0, b = 0;
+    for (int dy = 0; dy < 2; dy++)
+        for (int dx = 0; dx < 2; dx++) {
+            const int x = min(2 * cx + dx, width - 1), y = min(2 * cy + dy, height - 1);
+            const uint8_t* p = frame + (size_t)y * step + (size_t)x * channels;
+            sy[(size_t)(2 * cy + dy) * ys + 2 * cx + dx] = (uint8_t)vp8enc::rgb_to_y(p[2], p[1], p[0]);
+            b += p[0];
+            g += p[1];
+            r += p[2];
+        }
+    su[(size_t)cy * (ys / 2) + cx] = (uint8_t)vp8enc::rgb_to_u(r, g, b);
+    sv[(size_t)cy * (ys / 2) + cx] = (uint8_t)vp8enc::rgb_to_v(r, g, b);
+}
+
+struct Vp8EncJob {
+    vp8enc::Params P;
+    vp8enc::Buffers B;
+    uint8_t *part0, *tokens, *top_nz, *out;
+    size_t part0_cap, tokens_cap, out_cap;
+    size_t* out_len;
+};
+
+__global__ void vp8_encode_kernel(Vp8EncJob j) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (j.P.filter_level < 0) j.P.filter_level = vp8enc::filter_level_for_q(j.P.q);
+    vp8enc::analyse_and_reconstruct(j.P, j.B);
+    *j.out_len = vp8enc::write_bitstream(j.P, j.B, j.part0, j.part0_cap, j.tokens, j.tokens_cap, j.top_nz, j.out, j.out_cap);
+}
+
+static int vp8_encode_dev(const uint8_t* d_frame, size_t step, int width, int height, int channels, int quality,
+                          std::vector<uint8_t>* out, cudaStream_t st) {
+    Vp8EncJob j;
+    j.P.width = width;
+    j.P.height = height;
+    j.P.mb_w = (width + 15) >> 4;
+    j.P.mb_h = (height + 15) >> 4;
+    j.P.q = vp8enc::quality_to_q(quality);
+    j.P.filter_level = -1;  // chosen on the device, where the quantiser tables live
+    const int ys = j.P.mb_w * 16, yh = j.P.mb_h * 16;
+    const size_t ypl = (size_t)ys * yh, nmb = (size_t)j.P.mb_w * j.P.mb_h;
+    const size_t planes_b = round_up(ypl * 3 / 2, (size_t)256);
+    const size_t levels_b = round_up(nmb * 25 * 16 * 2, (size_t)256), modes_b = round_up(nmb * 2, (size_t)256);
+    j.part0_cap = round_up(nmb * 2 + 4096, (size_t)256);
+    j.tokens_cap = round_up(nmb * 2048 + 4096, (size_t)256);
+    j.out_cap = 16 + j.part0_cap + j.tokens_cap;
+    const size_t topnz_b = round_up((size_t)j.P.mb_w * 9, (size_t)256);
+    uint8_t* scratch = nullptr;
+    LP_CUDA_OK(cudaMallocAsync(&scratch, 256 + 2 * planes_b + levels_b + modes_b + j.part0_cap + j.tokens_cap + topnz_b + j.out_cap, st));
+    uint8_t* p = scratch;
+    j.out_len = reinterpret_cast<size_t*>(p);
+    p += 256;
+    uint8_t* src = p;
+    p += planes_b;
+    uint8_t* rec = p;
+    p += planes_b;
+    j.B.sy = src;
+    j.B.su = src + ypl;
+    j.B.sv = src + ypl + ypl / 4;
+    j.B.ry = rec;
+    j.B.ru = rec + ypl;
+    j.B.rv = rec + ypl + ypl / 4;
+    j.B.levels = reinterpret_cast<int16_t*>(p);
+    p += levels_b;
+    j.B.modes = p;
+    p += modes_b;
+    j.part0 = p;
+    p += j.part0_cap;
+    j.tokens = p;
+    p += j.tokens_cap;
+    j.top_nz = p;
+    p += topnz_b;
+    j.out = p;
+    dim3 grid(ceil_div(ys / 2, 128), yh / 2);
+    vp8_planes_kernel<<<grid, 128, 0, st>>>(d_frame, step, channels, width, height, ys, yh, src, src + ypl, src + ypl + ypl / 4);
+    vp8_encode_kernel<<<1, 32, 0, st>>>(j);
+    g_launches += 2;
+    size_t n = 0;
+    int rc = LP_OK;
+    if (cudaMemcpyAsync(&n, j.out_len, sizeof(n), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+        rc = LP_ERR_CUDA;
+    if (!rc && n == 0) rc = LP_ERR_INVALID_IMAGE;
+    if (!rc) {
+        out->resize(n);
+        if (cudaMemcpy(out->data(), j.out, n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = LP_ERR_CUDA;
+    }
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+// ------------------------------------------------------------------ RIFF assembly (host)
+
+static void put_le32(std::vector<uint8_t>& v, uint32_t x) {
+    for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i)));
+}
+static void put_le24(std::vector<uint8_t>& v, uint32_t x) {
+    for (int i = 0; i < 3; i++) v.push_back((uint8_t)(x >> (8 * i)));
+}
+static void put_chunk(std::vector<uint8_t>& v, const char* tag, const uint8_t* p, size_t n) {
+    v.insert(v.end(), tag, tag + 4);
+    put_le32(v, (uint32_t)n);
+    v.insert(v.end(), p, p + n);
+    if (n & 1) v.push_back(0);
+}
+
+struct EncodedFrame {
+    std::vector<uint8_t> image;  // "VP8 " or "VP8L" payload
+    std::vector<uint8_t> alph;   // "ALPH" payload (lossy frames with alpha)
+    bool lossless = false, has_alpha = false;
+    int width = 0, height = 0, duration = 0;
+};
+
+static void put_image_chunks(std::vector<uint8_t>& v, const EncodedFrame& f) {
+    if (!f.alph.empty()) put_chunk(v, "ALPH", f.alph.data(), f.alph.size());
+    put_chunk(v, f.lossless ? "VP8L" : "VP8 ", f.image.data(), f.image.size());
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+struct webp_encoder_struct {
+    uint8_t* dst = nullptr;
+    size_t dst_len = 0;
+    std::vector<uint8_t> icc;
+    uint32_t bgcolor = 0, loop_count = 0;
+    int frame_count = 1;  // ref webp.cpp:401: counts from 1
+    int first_frame_delay = 0;
+    std::vector<EncodedFrame> frames;
+};
+
+extern "C" {
+
+// ref webp.cpp:388-421
+webp_encoder webp_encoder_create(void* buf, size_t buf_len, const void* icc, size_t icc_len, uint32_t bgcolor, int loop_count) {
+    auto* e = new webp_encoder_struct;
+    e->dst = static_cast<uint8_t*>(buf);
+    e->dst_len = buf_len;
+    if (icc_len) e->icc.assign(static_cast<const uint8_t*>(icc), static_cast<const uint8_t*>(icc) + icc_len);
+    e->bgcolor = bgcolor;
+    e->loop_count = (uint32_t)loop_count;
+    return e;
+}
+
+// ref webp.cpp:423-560 (finalisation), 562-760 (frames)
+size_t webp_encoder_write(webp_encoder e, const opencv_mat src, const int* opt, size_t opt_len, int delay, int, int, int,
+                          int) {
+    if (!e) return 0;
+    // options (ref webp.cpp:451-498): only quality / lossless change what this encoder does
+    float quality = 100.0f;
+    bool lossless = false;
+    for (size_t i = 0; opt && i + 1 < opt_len; i += 2) {
+        if (opt[i] == CV_IMWRITE_WEBP_QUALITY) {
+            const float q = opt[i + 1] < 1 ? 1.0f : (float)opt[i + 1];
+            quality = q > 100.0f ? 100.0f : q;
+            lossless = q > 100.0f;
+        }
+    }
+    if (!src) {  // finalise
+        if (e->frame_count == 1 || e->frames.empty()) return 0;
+        std::vector<uint8_t> body;
+        const bool anim = e->frames.size() > 1;
+        bool any_alpha = false;
+        for (const EncodedFrame& f : e->frames) any_alpha |= f.has_alpha;
+        const EncodedFrame& f0 = e->frames[0];
+        const bool need_vp8x = anim || !e->icc.empty() || !f0.alph.empty();
+        if (need_vp8x) {
+            std::vector<uint8_t> x;
+            x.push_back((uint8_t)((anim ? 0x02 : 0) | (any_alpha ? 0x10 : 0) | (!e->icc.empty() ? 0x20 : 0)));
+            x.insert(x.end(), 3, 0);
+            put_le24(x, (uint32_t)f0.width - 1);
+            put_le24(x, (uint32_t)f0.height - 1);
+            put_chunk(body, "VP8X", x.data(), x.size());
+            if (!e->icc.empty()) put_chunk(body, "ICCP", e->icc.data(), e->icc.size());
+        }
+        if (anim) {
+            std::vector<uint8_t> a;
+            put_le32(a, e->bgcolor);
+            a.push_back((uint8_t)(e->loop_count & 0xff));
+            a.push_back((uint8_t)((e->loop_count >> 8) & 0xff));
+            put_chunk(body, "ANIM", a.data(), a.size());
+            for (const EncodedFrame& f : e->frames) {
+                std::vector<uint8_t> m;
+                put_le24(m, 0);
+                put_le24(m, 0);
+                put_le24(m, (uint32_t)f.width - 1);
+                put_le24(m, (uint32_t)f.height - 1);
+                put_le24(m, (uint32_t)(f.duration < 0 ? 0 : f.duration > 0xffffff ? 0xffffff : f.duration));
+                m.push_back(0x02);  // do not blend, do not dispose: every frame is a full canvas
+                put_image_chunks(m, f);
+                put_chunk(body, "ANMF", m.data(), m.size());
+            }
+        } else {
+            put_image_chunks(body, f0);
+        }
+        std::vector<uint8_t> file;
+        file.insert(file.end(), {'R', 'I', 'F', 'F'});
+        put_le32(file, (uint32_t)(4 + body.size()));
+        file.insert(file.end(), {'W', 'E', 'B', 'P'});
+        file.insert(file.end(), body.begin(), body.end());
+        if (file.size() > e->dst_len) {
+            fprintf(stderr, "Error: Final encoded size (%zu) exceeds buffer size (%zu)\n", file.size(), e->dst_len);
+            return 0;
+        }
+        memcpy(e->dst, file.data(), file.size());
+        return file.size();
+    }
+    int cols = 0, rows = 0, type = 0;
+    const uint8_t* dev = nullptr;
+    size_t step = 0;
+    if (mat_device_view(src, &cols, &rows, &type, &dev, &step)) return 0;
+    if (type != CV_8UC3 && type != CV_8UC4) {
+        // (the reference converts 1-channel input to BGR first, ref webp.cpp:576-585; not on this path yet)
+        fprintf(stderr, "[lilliput_b200] WebP encoder needs a BGR or BGRA frame\n");
+        return 0;
+    }
+    if (cols > 16383 || rows > 16383) return 0;  // WebP's 14-bit dimensions
+    if (!e->frames.empty() && (cols != e->frames[0].width || rows != e->frames[0].height)) {
+        fprintf(stderr, "[lilliput_b200] WebP animation frames must share the canvas size\n");
+        return 0;
+    }
+    const int channels = type == CV_8UC4 ? 4 : 3;
+    cudaStream_t st = thread_stream();
+    EncodedFrame f;
+    f.width = cols;
+    f.height = rows;
+    f.lossless = lossless;
+    f.has_alpha = channels == 4;
+    f.duration = delay;
+    int rc;
+    if (lossless) {
+        rc = vp8l_encode_dev(dev, step, cols, rows, channels, &f.image, st);
+    } else {
+        rc = vp8_encode_dev(dev, step, cols, rows, channels, (int)quality, &f.image, st);
+        if (!rc && channels == 4) {
+            uint8_t* plane = nullptr;
+            if (cudaMallocAsync(&plane, (size_t)cols * rows + 256, st) != cudaSuccess) return 0;
+            dim3 grid(ceil_div(cols, 256), rows);
+            extract_alpha_kernel<<<grid, 256, 0, st>>>(dev, step, cols, rows, plane);
+            g_launches++;
+            rc = vp8l_encode_dev(plane, (size_t)cols, cols, rows, 1, &f.alph, st);
+            cudaFreeAsync(plane, st);
+        }
+    }
+    if (rc) return 0;
+    if (e->frames.empty()) e->first_frame_delay = delay;
+    const size_t size = f.image.size() + f.alph.size();
+    e->frames.push_back(std::move(f));
+    e->frame_count++;
+    return size;
+}
+
+void webp_encoder_release(webp_encoder e) { delete e; }
+
+size_t webp_encoder_flush(webp_encoder e) { return webp_encoder_write(e, nullptr, nullptr, 0, 0, 0, 0, 0, 0); }
+
+}  // extern "C"

@@ -480,9 +480,6 @@ static std::string lower(std::string s) {
     return s;
 }
 
-// ref lilliput.go:129-164.  GIF goes to the giflib adapter; WebP / AVIF / video are routed away
-// BEFORE the OpenCV adapter is tried and, until those adapters exist on the device, are reported
-
 // ------------------------------------------------------------------ WebP adapter
 
 class WebpDecoder : public Decoder {  // ref webp.go:13-18, 30-176
@@ -552,7 +549,59 @@ class WebpDecoder : public Decoder {  // ref webp.go:13-18, 30-176
     size_t len = 0;
 };
 
-// as LP_ERR_UNSUPPORTED rather than silently mis-decoded.
+class WebpEncoder : public Encoder {  // ref webp.go:20-26, 178-261
+  public:
+    static Error Create(Decoder* decodedBy, uint8_t* dst, size_t cap, std::unique_ptr<Encoder>* out) {
+        std::vector<uint8_t> icc = decodedBy ? decodedBy->ICC() : std::vector<uint8_t>();
+        // ICCHeaderIsSane (ref color_info.cpp:70-79): a profile whose declared size disagrees with its
+        // length is dropped and the output is written untagged (ref webp.go:190-197)
+        if (!icc.empty()) {
+            const size_t declared = icc.size() >= 128 ? (((size_t)icc[0] << 24) | ((size_t)icc[1] << 16) | ((size_t)icc[2] << 8) | icc[3]) : 0;
+            if (icc.size() < 128 || declared != icc.size()) icc.clear();
+        }
+        const uint32_t bg = decodedBy ? decodedBy->BackgroundColor() : 0xFFFFFFFFu;
+        const int loops = decodedBy ? decodedBy->LoopCount() : 0;
+        webp_encoder e = webp_encoder_create(dst, cap, icc.empty() ? nullptr : icc.data(), icc.size(), bg, loops);
+        if (!e) return LP_ERR_BUF_TOO_SMALL;
+        auto* self = new WebpEncoder;
+        self->encoder = e;
+        out->reset(self);
+        return LP_OK;
+    }
+    ~WebpEncoder() override { webp_encoder_release(encoder); }
+    Error Encode(Framebuffer* f, const std::map<int, int>& opt, bool* content, size_t* out_len) override {
+        *content = false;
+        if (hasFlushed) return LP_ERR_EOF;
+        if (!f) {
+            const size_t n = webp_encoder_flush(encoder);
+            if (n == 0) return LP_ERR_INVALID_IMAGE;
+            hasFlushed = true;
+            *out_len = n;
+            *content = true;
+            return LP_OK;
+        }
+        std::vector<int> flat;
+        for (const auto& kv : opt) {
+            flat.push_back(kv.first);
+            flat.push_back(kv.second);
+        }
+        const int delay = (int)(f->duration_ns / 1000000);
+        const size_t n = webp_encoder_write(encoder, f->mat, flat.empty() ? nullptr : flat.data(), flat.size(), delay,
+                                            (int)f->blend, (int)f->dispose, 0, 0);
+        if (n == 0) return LP_ERR_INVALID_IMAGE;
+        frameIndex++;
+        return LP_OK;  // (nil, nil): send the next frame
+    }
+
+  private:
+    webp_encoder encoder = nullptr;
+    int frameIndex = 0;
+    bool hasFlushed = false;
+};
+
+// ref lilliput.go:129-164.  GIF goes to the giflib adapter, WebP to the WebP adapter; AVIF / video are
+// routed away BEFORE the OpenCV adapter is tried and reported as LP_ERR_UNSUPPORTED (out of scope,
+// DESIGN.md s.8) rather than silently mis-decoded.
 Error NewDecoder(const uint8_t* buf, size_t len, std::unique_ptr<Decoder>* out) {
     if (len == 0) return LP_ERR_INVALID_IMAGE;
     if (len >= 6 && (!memcmp(buf, "GIF87a", 6) || !memcmp(buf, "GIF89a", 6)))
@@ -570,7 +619,8 @@ Error NewEncoder(const std::string& ext_, Decoder* decodedBy, uint8_t* dst, size
                  std::unique_ptr<Encoder>* out) {
     std::string ext = lower(ext_);
     if (ext == ".gif") return GifEncoder::Create(decodedBy, dst, cap, out);
-    if (ext == ".webp" || ext == ".avif" || ext == ".thumbhash") return LP_ERR_UNSUPPORTED;
+    if (ext == ".webp") return WebpEncoder::Create(decodedBy, dst, cap, out);  // ref lilliput.go:185-187
+    if (ext == ".avif" || ext == ".thumbhash") return LP_ERR_UNSUPPORTED;
     if (ext == ".mp4" || ext == ".webm") return LP_ERR_INVALID_IMAGE;
     return OpenCVEncoder::Create(ext_, dst, cap, out);
 }
@@ -893,7 +943,9 @@ extern "C" int lp_encode_host(const char* ext, const uint8_t* pixels, int w, int
     std::map<int, int> o;
     for (size_t i = 0; i + 1 < opt_len; i += 2) o[opt[i]] = opt[i + 1];
     bool content = false;
-    return enc->Encode(&a, o, &content, out_len);
+    e = enc->Encode(&a, o, &content, out_len);
+    if (e || content) return e;
+    return enc->Encode(nullptr, o, &content, out_len);  // multi-frame encoders answer at the flush (ops.go:285-292)
 }
 
 extern "C" int lp_orient_host(const uint8_t* src, int w, int h, int type, int orientation,

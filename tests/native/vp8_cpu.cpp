@@ -65,3 +65,81 @@ extern "C" int alph_cpu_decode(const uint8_t* d, size_t n, int w, int h, uint8_t
     vp8l::Arena a{mem.data(), mem.size(), 0};
     return vp8l::decode_alph(d, n, w, h, a, alpha);
 }
+
+// ---- VP8L encoder core, host build: whole stream written serially (the device packs pixels in parallel)
+#include "../../lilliput_b200/csrc/vp8l_enc_core.h"
+
+// channels 3/4: a "VP8L" chunk payload from a BGR(A) frame; channels 1: an ALPH chunk payload
+// (header byte + headerless VP8L stream) from a plane.  Returns the size, or -1 if it does not fit.
+extern "C" long vp8l_cpu_encode(const uint8_t* frame, size_t step, int w, int h, int channels, uint8_t* out, size_t cap) {
+    std::vector<uint32_t> hist(4 * 256, 0);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint32_t r = vp8lenc::residual_at(frame, step, channels, x, y);
+            hist[(r >> 8) & 255]++;
+            hist[256 + ((r >> 16) & 255)]++;
+            hist[512 + (r & 255)]++;
+            hist[768 + (r >> 24)]++;
+        }
+    vp8lenc::BitWriter bw;
+    vp8lenc::CodeTable t;
+    if (channels == 1) bw.put(1, 8);  // ALPH header: lossless compression, no filter, no pre-processing
+    vp8lenc::write_stream_head(bw, w, h, channels == 4, channels != 1, channels != 1, hist.data(), &t);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            uint64_t bits;
+            int n;
+            vp8lenc::pixel_bits(vp8lenc::residual_at(frame, step, channels, x, y), t, &bits, &n);
+            bw.put((uint32_t)bits, n > 32 ? 32 : n);
+            if (n > 32) bw.put((uint32_t)(bits >> 32), n - 32);
+        }
+    bw.flush();
+    if (bw.bytes.size() > cap) return -1;
+    memcpy(out, bw.bytes.data(), bw.bytes.size());
+    return (long)bw.bytes.size();
+}
+
+// ---- VP8 lossy encoder core, host build
+#include "../../lilliput_b200/csrc/vp8_enc_core.h"
+
+// BGR(A) frame -> "VP8 " chunk payload.  Returns the size (0 = failed).  `recon_bgr` (optional) gets
+// what a decoder WITHOUT loop filter would show, for debugging.
+extern "C" long vp8_cpu_encode(const uint8_t* frame, size_t step, int w, int h, int channels, int quality,
+                               int filter_level, uint8_t* out, size_t cap) {
+    vp8enc::Params P;
+    P.width = w;
+    P.height = h;
+    P.mb_w = (w + 15) >> 4;
+    P.mb_h = (h + 15) >> 4;
+    P.q = vp8enc::quality_to_q(quality);
+    P.filter_level = filter_level < 0 ? vp8enc::filter_level_for_q(P.q) : filter_level;
+    const int ys = P.mb_w * 16, cs = P.mb_w * 8, yh = P.mb_h * 16, ch = P.mb_h * 8;
+    std::vector<uint8_t> sy((size_t)ys * yh), su((size_t)cs * ch), sv((size_t)cs * ch);
+    std::vector<uint8_t> ry(sy.size()), ru(su.size()), rv(sv.size());
+    auto px = [&](int x, int y) { return frame + (size_t)(y < h ? y : h - 1) * step + (size_t)(x < w ? x : w - 1) * channels; };
+    for (int y = 0; y < yh; y++)
+        for (int x = 0; x < ys; x++) {
+            const uint8_t* p = px(x, y);
+            sy[(size_t)y * ys + x] = (uint8_t)vp8enc::rgb_to_y(p[2], p[1], p[0]);
+        }
+    for (int y = 0; y < ch; y++)
+        for (int x = 0; x < cs; x++) {
+            int r = 0, g = 0, b = 0;
+            for (int dy = 0; dy < 2; dy++)
+                for (int dx = 0; dx < 2; dx++) {
+                    const uint8_t* p = px(2 * x + dx, 2 * y + dy);
+                    b += p[0];
+                    g += p[1];
+                    r += p[2];
+                }
+            su[(size_t)y * cs + x] = (uint8_t)vp8enc::rgb_to_u(r, g, b);
+            sv[(size_t)y * cs + x] = (uint8_t)vp8enc::rgb_to_v(r, g, b);
+        }
+    std::vector<int16_t> levels((size_t)P.mb_w * P.mb_h * 25 * 16);
+    std::vector<uint8_t> modes((size_t)P.mb_w * P.mb_h * 2);
+    vp8enc::Buffers B{sy.data(), su.data(), sv.data(), ry.data(), ru.data(), rv.data(), levels.data(), modes.data()};
+    vp8enc::analyse_and_reconstruct(P, B);
+    const size_t scratch = (size_t)P.mb_w * P.mb_h * 1024 + 4096;
+    std::vector<uint8_t> part0(scratch), tokens(scratch), top_nz((size_t)P.mb_w * 9);
+    return (long)vp8enc::write_bitstream(P, B, part0.data(), part0.size(), tokens.data(), tokens.size(), top_nz.data(), out, cap);
+}

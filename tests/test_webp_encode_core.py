@@ -1,0 +1,78 @@
+"""CPU: the WebP ENCODER cores the device runs (vp8l_enc_core.h lossless, vp8_enc_core.h lossy),
+compiled for the host by tests/native/vp8_cpu.cpp.
+  lossless: the stream decodes (with the device's own decoder core, and with the reference's libwebp
+            where oracle/_ref is present) to exactly the input pixels;
+  lossy:    the stream is a valid VP8 key frame -- both decoders agree bit for bit on its pixels --
+            and its PSNR against the source is within 1 dB of (in practice above) what libwebp
+            reaches at the same `quality` on the committed golden streams' sources."""
+import numpy as np
+import pytest
+
+from lilliput_b200.synth import synth_image
+from tests.webp_util import (alph_cpu_decode, psnr, riff, vp8_cpu_decode, vp8_cpu_encode, vp8_cpu_lib, vp8l_cpu_decode,
+                             vp8l_cpu_encode)
+
+
+@pytest.fixture(scope="module")
+def cpu():
+    return vp8_cpu_lib()
+
+
+IMAGES = [(5, 200, 120, 3, 6.0), (6, 97, 61, 4, 40.0), (7, 1, 1, 3, 6.0), (8, 513, 3, 4, 6.0), (9, 2, 300, 3, 20.0)]
+
+
+@pytest.mark.parametrize("seed,w,h,ch,noise", IMAGES)
+def test_lossless_encoder_round_trips(cpu, seed, w, h, ch, noise):
+    img = synth_image(seed, w, h, ch, noise=noise)
+    payload = vp8l_cpu_encode(cpu, img)
+    assert np.array_equal(vp8l_cpu_decode(cpu, payload, w, h, ch), img)
+
+
+def test_lossless_encoder_flat_and_random_images(cpu):
+    flat = np.zeros((40, 40, 3), np.uint8)
+    flat[:] = (10, 200, 30)  # single-symbol prefix codes everywhere
+    rnd = np.random.default_rng(5).integers(0, 256, (50, 70, 4), dtype=np.uint8)
+    for img in (flat, rnd):
+        h, w, ch = img.shape
+        assert np.array_equal(vp8l_cpu_decode(cpu, vp8l_cpu_encode(cpu, img), w, h, ch), img)
+
+
+def test_alpha_plane_round_trips_through_alph(cpu):
+    a = np.clip(synth_image(3, 96, 64, 1, noise=20.0).reshape(64, 96).astype(int) * 2 - 128, 0, 255).astype(np.uint8)
+    payload = vp8l_cpu_encode(cpu, a)
+    assert payload[0] == 1  # ALPH header: VP8L-compressed, unfiltered
+    assert np.array_equal(alph_cpu_decode(cpu, payload, 96, 64), a)
+
+
+def test_lossless_and_alpha_streams_decode_with_the_reference(cpu, ref_lib):
+    img = synth_image(11, 120, 90, 4, noise=15.0)
+    _, frames, _, rc = ref_lib.webp_frames(riff([(b"VP8L", vp8l_cpu_encode(cpu, img))]))
+    assert rc == 0 and np.array_equal(frames[0], img)
+    # lossy colour + lossless alpha in a VP8X container
+    vp8x = bytes([0x10, 0, 0, 0]) + (119).to_bytes(3, "little") + (89).to_bytes(3, "little")
+    data = riff([(b"VP8X", vp8x), (b"ALPH", vp8l_cpu_encode(cpu, img[:, :, 3])), (b"VP8 ", vp8_cpu_encode(cpu, img, 80))])
+    _, frames, _, rc = ref_lib.webp_frames(data)
+    assert rc == 0 and np.array_equal(frames[0][:, :, 3], img[:, :, 3])
+
+
+@pytest.mark.parametrize("quality", [20, 50, 75, 90, 100])
+@pytest.mark.parametrize("seed,w,h,noise", [(21, 256, 256, 6.0), (22, 97, 61, 30.0), (23, 17, 33, 6.0), (24, 1, 1, 6.0)])
+def test_lossy_encoder_writes_valid_streams_of_sane_quality(cpu, quality, seed, w, h, noise):
+    img = synth_image(seed, w, h, 3, noise=noise)
+    payload = vp8_cpu_encode(cpu, img, quality)
+    got = vp8_cpu_decode(cpu, payload)
+    assert got.shape == img.shape
+    if w >= 64 and noise < 10:
+        assert psnr(got, img) > 27.0 + quality / 25.0  # smooth synthetic content: 28-31 dB across the range
+
+
+def test_lossy_stream_decodes_identically_with_the_reference_and_matches_libwebp_quality(cpu, ref_lib):
+    cv2 = pytest.importorskip("cv2")
+    for seed, w, h, noise in [(31, 320, 200, 6.0), (32, 97, 61, 30.0), (33, 33, 65, 12.0)]:
+        img = synth_image(seed, w, h, 3, noise=noise)
+        for quality in (30, 75, 90):
+            payload = vp8_cpu_encode(cpu, img, quality)
+            _, frames, _, rc = ref_lib.webp_frames(riff([(b"VP8 ", payload)]))
+            assert rc == 0 and np.array_equal(frames[0], vp8_cpu_decode(cpu, payload))
+            ok, lw = cv2.imencode(".webp", img, [cv2.IMWRITE_WEBP_QUALITY, quality])
+            assert psnr(frames[0], img) > psnr(cv2.imdecode(lw, cv2.IMREAD_COLOR), img) - 1.0

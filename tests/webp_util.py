@@ -31,9 +31,11 @@ def vp8_cpu_lib():
     srcs = [os.path.join(ROOT, "tests", "native", "vp8_cpu.cpp"),
             os.path.join(ROOT, "lilliput_b200", "csrc", "vp8_core.h"),
             os.path.join(ROOT, "lilliput_b200", "csrc", "vp8_tables.h"),
-            os.path.join(ROOT, "lilliput_b200", "csrc", "vp8l_core.h")]
+            os.path.join(ROOT, "lilliput_b200", "csrc", "vp8l_core.h"),
+            os.path.join(ROOT, "lilliput_b200", "csrc", "vp8_enc_core.h"),
+            os.path.join(ROOT, "lilliput_b200", "csrc", "vp8l_enc_core.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, srcs[0]])
     return ctypes.CDLL(so)
 
 
@@ -81,3 +83,38 @@ def alph_cpu_decode(lib, payload: bytes, w: int, h: int) -> np.ndarray:
                              out.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0, rc
     return out
+
+
+def vp8l_cpu_encode(lib, img: np.ndarray) -> bytes:
+    """vp8l_enc_core.h on the host: BGR(A) frame -> "VP8L" payload, or a plane -> "ALPH" payload."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    c = 1 if img.ndim == 2 else img.shape[2]
+    out = np.zeros(w * h * 8 + 65536, np.uint8)
+    lib.vp8l_cpu_encode.restype = ctypes.c_long
+    n = lib.vp8l_cpu_encode(img.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(w * c), w, h, c,
+                            out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.size))
+    assert n > 0, n
+    return out[:n].tobytes()
+
+
+def vp8_cpu_encode(lib, img: np.ndarray, quality: int, filter_level: int = -1) -> bytes:
+    """vp8_enc_core.h on the host: BGR(A) frame -> "VP8 " payload."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, c = img.shape
+    out = np.zeros(w * h * 4 + 65536, np.uint8)
+    lib.vp8_cpu_encode.restype = ctypes.c_long
+    n = lib.vp8_cpu_encode(img.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(w * c), w, h, c, quality, filter_level,
+                           out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.size))
+    assert n > 0, n
+    return out[:n].tobytes()
+
+
+def riff(chunks) -> bytes:
+    body = b"WEBP" + b"".join(t + struct.pack("<I", len(p)) + p + (b"\0" if len(p) & 1 else b"") for t, p in chunks)
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+def psnr(a, b) -> float:
+    m = ((a.astype(np.float64) - b.astype(np.float64)) ** 2).mean()
+    return 99.0 if m == 0 else float(10 * np.log10(255.0 * 255.0 / m))

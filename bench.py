@@ -216,6 +216,17 @@ def cpu_model():
 
 # ------------------------------------------------------------------------------ main
 
+def resize_traffic(images_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the resize kernel per launch, from the committed
+    `ncu --set full` capture (profiles/r01_resize_traffic.json: measured per image on a 1184-image launch,
+    1.014x the algorithmic bytes), scaled to this run's images per launch.  None if the file is missing."""
+    path = os.path.join(ROOT, "profiles", "r01_resize_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return int(json.load(f)["traffic_bytes_per_image"] * images_per_launch)
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -371,7 +382,7 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "resize_area_kernel<3,6>", "bound": "hbm", "achieved": round(achieved, 1),
                          "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": resize_traffic(per_launch_images),
                          "bytes_per_launch": int(per_launch_images * RESIZE_BYTES_PER_IMAGE),
                          "ms_per_launch": round(resize_ms_per_launch, 4)},
         }

@@ -71,70 +71,115 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total,
 
 // clean[] gets the entropy-coded bytes with every "FF 00" reduced to "FF"; the segment ends at the
 // first FF that is followed by anything else (a marker).  clean_len[img] = bytes written.
+// One CTA per image, 8 KB tiles: every thread takes one aligned 16-byte vector, learns its
+// neighbours' edge bytes by shuffle, a block scan places the kept bytes in a shared staging
+// tile, and the tile leaves as 4-byte words (stuffed bytes are ~0.4 % of the stream, so this is a
+// copy that occasionally closes a gap).  The marker search rides along: only the tile that holds
+// the marker pays for the second look.
 __global__ void __launch_bounds__(kHuffThreads)
     jpeg_unstuff_kernel(JpegDecodeItem* items, const uint8_t* scan, uint8_t* clean) {
     __shared__ uint32_t warp_sums[kHuffThreads / 32];
-    __shared__ uint32_t s_end, s_carry;
+    __shared__ uint32_t s_end;
+    __shared__ __align__(16) uint8_t stage[kHuffThreads * 16 + 16];
     JpegDecodeItem& it = items[blockIdx.x];
     const uint8_t* src = scan + it.scan_off;
     const uint32_t len = it.scan_len;
     uint8_t* dst = clean + it.clean_off;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        s_end = len;
-        s_carry = 0;
-    }
-    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31;
     if (it.status != 0) {
         if (tid == 0) it.clean_len = 0;
         return;
     }
-    // pass 1: first marker = FF followed by a byte that is not 00 (a trailing lone FF also ends it)
-    uint32_t my_end = len;
-    for (uint32_t i = tid; i < len; i += kHuffThreads) {
-        if (src[i] == 0xFF) {
-            const uint32_t nx = (i + 1 < len) ? src[i + 1] : 0xD9;
-            if (nx != 0x00) {
-                my_end = i;
-                break;  // positions only grow along this thread's stride
-            }
-        }
-    }
-    atomicMin(&s_end, my_end);
+    if (tid == 0) s_end = len;
     __syncthreads();
-    const uint32_t end = s_end;
-    // pass 2: compaction, 8 bytes per thread per round
-    constexpr uint32_t kPer = 8;
-    for (uint32_t base = 0; base < end; base += kHuffThreads * kPer) {
-        const uint32_t b0 = base + tid * kPer;
-        uint8_t v[kPer];
-        uint32_t keep = 0, cnt = 0;
-        uint8_t prev = (b0 > 0 && b0 <= end) ? src[b0 - 1] : 0;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+    const uint8_t* abase = src - mis;  // 16-byte aligned; the bytes before src belong to the same upload
+    uint32_t carry = 0;
+    uint32_t end = len;
+    constexpr uint32_t kTile = kHuffThreads * 16;
+    for (uint32_t t0 = 0; t0 < mis + end; t0 += kTile) {
+        const uint32_t aoff = t0 + (uint32_t)tid * 16;      // offset from abase
+        const int64_t i0 = (int64_t)aoff - (int64_t)mis;    // stream index of this thread's first byte
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (aoff < mis + len + 16) w = *reinterpret_cast<const uint4*>(abase + aoff);
+        // neighbours' edge bytes
+        uint32_t prev = __shfl_up_sync(0xffffffffu, w.w >> 24, 1);
+        uint32_t next = __shfl_down_sync(0xffffffffu, w.x & 0xffu, 1);
+        if (lane == 0) prev = i0 > 0 ? src[i0 - 1] : 0;
+        if (lane == 31) next = (i0 + 16 < (int64_t)len) ? src[i0 + 16] : 0xD9u;
+        // Per-byte classification, four bytes per instruction (SIMD-in-register compares):
+        //   stuffed zero = 00 preceded by FF (dropped); marker = FF followed by anything but 00.
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        uint32_t m00[4], mff[4];
 #pragma unroll
-        for (uint32_t k = 0; k < kPer; k++) {
-            const uint32_t i = b0 + k;
-            const uint8_t c = i < end ? src[i] : 0;
-            v[k] = c;
-            const bool drop = (i >= end) || (c == 0x00 && prev == 0xFF);
-            if (!drop) {
-                keep |= 1u << k;
-                cnt++;
-            }
-            prev = c;
+        for (int q = 0; q < 4; q++) {
+            m00[q] = __vcmpeq4(ws[q], 0u);
+            mff[q] = __vcmpeq4(ws[q], 0xFFFFFFFFu);
         }
+        const uint32_t prev_ff = prev == 0xFFu ? 0xFFu : 0u, next_00 = next == 0x00u ? 0xFF000000u : 0u;
+        uint32_t drop16 = 0, mark16 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t pff = (mff[q] << 8) | (q ? mff[q - 1] >> 24 : prev_ff);            // byte before is FF
+            const uint32_t n00 = (m00[q] >> 8) | (q < 3 ? m00[q + 1] << 24 : next_00);        // byte after is 00
+            const uint32_t d = m00[q] & pff, mk = mff[q] & ~n00;
+            drop16 |= (((d & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << (4 * q);           // byte masks -> 4 bits
+            mark16 |= (((mk & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << (4 * q);
+        }
+        // bytes of this vector that lie inside the stream [0, len)
+        const int64_t lo = -i0, hi = (int64_t)len - i0;  // valid k: lo <= k < hi
+        uint32_t valid16 = 0xFFFFu;
+        if (lo > 0) valid16 &= lo >= 16 ? 0u : (0xFFFFu << lo);
+        if (hi < 16) valid16 &= hi <= 0 ? 0u : (0xFFFFu >> (16 - hi));
+        // the first byte of the stream has no predecessor (whatever sits in memory before it)
+        if (lo >= 0 && lo < 16) drop16 &= ~(1u << (int)lo);
+        // the last byte of the stream counts as followed by a marker byte
+        if (hi >= 1 && hi <= 16) {
+            const int kl = (int)hi - 1;
+            if (((ws[kl >> 2] >> (8 * (kl & 3))) & 0xFFu) == 0xFFu) mark16 |= 1u << kl;
+        }
+        mark16 &= valid16;
+        const uint32_t my_marker = mark16 ? (uint32_t)(i0 + (__ffs(mark16) - 1)) : 0xFFFFFFFFu;
+        if (__syncthreads_or(my_marker != 0xFFFFFFFFu)) {
+            if (my_marker != 0xFFFFFFFFu) atomicMin(&s_end, my_marker);
+            __syncthreads();
+            end = s_end;
+        }
+        uint32_t keep = valid16 & ~drop16;
+        {
+            const int64_t he = (int64_t)end - i0;  // bytes at or after the marker are dropped
+            if (he < 16) keep &= he <= 0 ? 0u : (0xFFFFu >> (16 - he));
+        }
+        uint8_t bsrc[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) bsrc[k] = (uint8_t)(ws[k >> 2] >> (8 * (k & 3)));
+        const uint32_t cnt = __popc(keep);
         uint32_t total;
         const uint32_t ex = block_excl_scan<kHuffThreads>(cnt, &total, warp_sums);
-        uint32_t o = s_carry + ex;
+        {
+            uint32_t o = ex;
 #pragma unroll
-        for (uint32_t k = 0; k < kPer; k++)
-            if (keep & (1u << k)) dst[o++] = v[k];
+            for (int k = 0; k < 16; k++)
+                if (keep & (1u << k)) stage[o++] = bsrc[k];
+        }
         __syncthreads();
-        if (tid == 0) s_carry += total;
+        // staged tile -> dst[carry, carry + total): bytes up to 4-byte alignment, words, tail bytes
+        uint8_t* d = dst + carry;
+        const uint32_t head = min(total, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(d) & 3)) & 3));
+        const uint32_t nwords = (total - head) >> 2;
+        const uint32_t tail0 = head + (nwords << 2);
+        if ((uint32_t)tid < head) d[tid] = stage[tid];
+        for (uint32_t j = tid; j < nwords; j += kHuffThreads) {
+            const uint8_t* q = stage + head + 4 * j;
+            *reinterpret_cast<uint32_t*>(d + head + 4 * j) = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+        }
+        if (tail0 + tid < total) d[tail0 + tid] = stage[tail0 + tid];
+        carry += total;
         __syncthreads();
     }
-    if (tid == 0) it.clean_len = s_carry;
+    if (tid == 0) it.clean_len = carry;
     // zero padding so the 8-byte window loads past the end read defined data
-    for (uint32_t k = tid; k < 32; k += kHuffThreads) dst[s_carry + k] = 0;
+    for (uint32_t k = tid; k < 32; k += kHuffThreads) dst[carry + k] = 0;
 }
 
 // ------------------------------------------------------------------ 2. sync + write
@@ -157,6 +202,14 @@ struct HuffShared {
     uint8_t zz[64];
     uint8_t blk_dc[16], blk_ac[16];  // table id per block-in-MCU
     uint8_t blk_comp[16], blk_bx[16], blk_by[16];
+    // The usual layout -- the first n_first blocks of an MCU (component 0) share one DC/AC table pair
+    // and all the others share another -- lets the symbol loop pick its lookahead table with a
+    // compare + select instead of a table walk on every block boundary.
+    uint32_t two_tables, n_first;
+    uint32_t dcb_first, dcb_rest, acb_first, acb_rest;  // shared-memory byte addresses
+    // write pass: coefficient offset of block-in-MCU b of MCU (rx, ry) inside the region of interest =
+    // w_boff[b] + rx * w_hx[b] + ry * w_vrow[b]   (int16 elements from coef_off)
+    uint32_t w_boff[16], w_hx[16], w_vrow[16];
 };
 
 // MSB-first bit reader over the unstuffed string: 64-bit window, one 32-bit load per 32 bits used.
@@ -205,13 +258,12 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
     int16_t* dcp = nullptr;  // DC difference slot of the current block (all blocks, MCU order)
     int mx = 0, my = 0;
     uint64_t remaining = 0;
+    int roi_mx0 = 0, roi_my0 = 0, roi_mcx = 0, roi_mcy = 0, mcus_x = 0;
+    int16_t* coef_base = nullptr;
     auto set_dst = [&]() {   // nullptr when the block lies outside the region of interest
-        const int c = hs.blk_comp[blk];
-        const int rx = (mx - it->roi_mx0) * it->h[c] + hs.blk_bx[blk];
-        const int ry = (my - it->roi_my0) * it->v[c] + hs.blk_by[blk];
-        const bool inside = (unsigned)(mx - it->roi_mx0) < (unsigned)it->roi_mcx &&
-                            (unsigned)(my - it->roi_my0) < (unsigned)it->roi_mcy;
-        dstblk = inside ? coef + it->coef_off + ((size_t)it->block_off[c] + (size_t)ry * it->bw[c] + rx) * 64
+        const int rmx = mx - roi_mx0, rmy = my - roi_my0;
+        const bool inside = (unsigned)rmx < (unsigned)roi_mcx && (unsigned)rmy < (unsigned)roi_mcy;
+        dstblk = inside ? coef_base + hs.w_boff[blk] + (uint32_t)rmx * hs.w_hx[blk] + (size_t)rmy * hs.w_vrow[blk]
                         : nullptr;
     };
     if (WRITE) {
@@ -220,15 +272,32 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
             return;
         }
         remaining = total_slots - pos + z_start;  // slots from the start of the current block
+        roi_mx0 = it->roi_mx0;
+        roi_my0 = it->roi_my0;
+        roi_mcx = it->roi_mcx;
+        roi_mcy = it->roi_mcy;
+        mcus_x = it->mcus_x;
+        coef_base = coef + it->coef_off;
         const uint32_t mcu = (uint32_t)((pos >> 6) / (uint32_t)nb);
-        mx = (int)(mcu % (uint32_t)it->mcus_x);
-        my = (int)(mcu / (uint32_t)it->mcus_x);
+        mx = (int)(mcu % (uint32_t)mcus_x);
+        my = (int)(mcu / (uint32_t)mcus_x);
         set_dst();
         dcp = dcdiff + (pos >> 6);
     }
     // shared-memory byte addresses of the current block's lookahead tables
-    uint32_t dcb = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[blk]][0]);
-    uint32_t acb = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[blk]][0]);
+    const bool two = hs.two_tables != 0;  // uniform across the CTA
+    const uint32_t n_first = hs.n_first, dcbF = hs.dcb_first, dcbR = hs.dcb_rest, acbF = hs.acb_first, acbR = hs.acb_rest;
+    uint32_t dcb, acb;
+    auto set_tables = [&]() {
+        if (two) {
+            dcb = blk < n_first ? dcbF : dcbR;
+            acb = blk < n_first ? acbF : acbR;
+        } else {
+            dcb = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[blk]][0]);
+            acb = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[blk]][0]);
+        }
+    };
+    set_tables();
     // The symbol step uses selects instead of branches: lanes of a warp sit at unrelated places of
     // unrelated subsequences, so every branch here would be a divergent one.  Coefficient slots are
     // not counted per symbol: slots = 64 * blocks closed + z_end - z_start.
@@ -278,24 +347,29 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
         }
         bw.skip(used);
         bits_left -= used;
-        z = zt >= 64 ? 0u : zt;
-        if (z == 0) {  // block finished
+        const bool fin = zt >= 64;  // block finished
+        z = fin ? 0u : zt;
+        if (!WRITE) {
+            // lanes sit at unrelated places, so SOME lane closes a block in nearly every iteration: keep the
+            // bookkeeping to selects instead of a branch the whole warp would walk through
+            closed += fin ? 1u : 0u;
+            const uint32_t nxt = blk + 1 == (uint32_t)nb ? 0u : blk + 1;
+            blk = fin ? nxt : blk;
+            set_tables();
+        } else if (fin) {
             closed++;
             blk++;
             if (blk == (uint32_t)nb) {
                 blk = 0;
-                if (WRITE && ++mx == it->mcus_x) {
+                if (++mx == mcus_x) {
                     mx = 0;
                     my++;
                 }
             }
-            dcb = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[blk]][0]);
-            acb = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[blk]][0]);
-            if (WRITE) {
-                if ((uint64_t)closed * 64 >= remaining) break;  // every MCU produced: the rest is padding
-                dcp++;
-                set_dst();
-            }
+            set_tables();
+            if ((uint64_t)closed * 64 >= remaining) break;  // every MCU produced: the rest is padding
+            dcp++;
+            set_dst();
         }
     }
     p = limit - (uint32_t)bits_left;  // bits_left <= 0 here unless the stream ended early
@@ -332,7 +406,23 @@ __global__ void __launch_bounds__(kHuffThreads, 4)
                     hs.blk_comp[k] = (uint8_t)c;
                     hs.blk_bx[k] = (uint8_t)(j % it.h[c]);
                     hs.blk_by[k] = (uint8_t)(j / it.h[c]);
+                    hs.w_boff[k] = (it.block_off[c] + (uint32_t)(j / it.h[c]) * it.bw[c] + (uint32_t)(j % it.h[c])) * 64u;
+                    hs.w_hx[k] = (uint32_t)it.h[c] * 64u;
+                    hs.w_vrow[k] = (uint32_t)it.v[c] * it.bw[c] * 64u;
                 }
+            const int nfirst = it.h[0] * it.v[0];
+            bool two = true;
+            for (int b = 0; b < k; b++) {
+                const int ref = b < nfirst ? 0 : nfirst;
+                if (hs.blk_dc[b] != hs.blk_dc[ref] || hs.blk_ac[b] != hs.blk_ac[ref]) two = false;
+            }
+            const int rest = nfirst < k ? nfirst : 0;
+            hs.two_tables = two;
+            hs.n_first = (uint32_t)nfirst;
+            hs.dcb_first = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[0]][0]);
+            hs.acb_first = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[0]][0]);
+            hs.dcb_rest = (uint32_t)__cvta_generic_to_shared(&hs.dc_look[hs.blk_dc[rest]][0]);
+            hs.acb_rest = (uint32_t)__cvta_generic_to_shared(&hs.ac_look[hs.blk_ac[rest]][0]);
             s_status = 0;
             s_carry = 0;
         }

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -112,7 +113,7 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
     const int slots = jpeg_huff_parallel_slots();
     b->chunk = cfg->chunk > 0 ? cfg->chunk : (slots > 0 ? 2 * slots : 512);
     b->chunk = std::min(b->chunk, cfg->max_images);
-    b->max_chunks = ceil_div(cfg->max_images, b->chunk);
+    b->max_chunks = ceil_div(cfg->max_images, b->chunk) + 1;  // +1: the pipelined path opens with a half chunk
     // worst-case per-image layout: 4:4:4 needs the most blocks
     const size_t mcus = (size_t)ceil_div(b->W, 8) * ceil_div(b->H, 8);
     b->max_blocks_alloc = mcus * 3 + 4 * ((size_t)ceil_div(b->W, 8) + ceil_div(b->H, 8)) + 16;
@@ -260,7 +261,7 @@ static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t
         it.status = rc ? -1 : 0;
         if (rc) continue;
         if (it.restart_interval) b->parallel_huffman = false;  // RSTn streams take the serial kernel
-        const int slot = k % b->chunk;
+        const int slot = k - i0;  // position inside its chunk: the per-chunk scratch is indexed from the chunk's first image
         it.scan_off = b->file_dev_off[k] + h.scan_offset;
         it.coef_off = (uint64_t)slot * b->blocks * 64;
         it.plane_off = (uint64_t)slot * b->plane_bytes;
@@ -445,10 +446,22 @@ extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const s
     LP_CUDA_OK(cudaSetDevice(b->cfg.device));
     batch_begin(b, n);
     const long launches0 = g_launches;
-    const int nchunks = ceil_div(n, b->chunk);
+    // Chunk schedule: nothing can run before the first chunk's headers are parsed and its bytes have
+    // crossed PCIe, so the pipeline opens with HALF a chunk (one full wave of Huffman CTAs instead of
+    // two) and continues with full ones.
+    std::vector<std::pair<int, int>> sched;
+    {
+        int i0 = 0;
+        if (n > b->chunk && b->chunk >= 2) {
+            sched.push_back({0, b->chunk / 2});
+            i0 = b->chunk / 2;
+        }
+        for (; i0 < n; i0 += b->chunk) sched.push_back({i0, std::min(b->chunk, n - i0)});
+    }
+    const int nchunks = (int)sched.size();
     int finished = 0;
     for (int c = 0; c < nchunks; c++) {
-        const int i0 = c * b->chunk, cnt = std::min(b->chunk, n - i0);
+        const int i0 = sched[c].first, cnt = sched[c].second;
         int rc = batch_parse_chunk(b, in, in_len, i0, cnt);
         if (rc) return rc;
         rc = batch_upload_chunk(b, in, in_len, i0, cnt, b->st_h2d);
@@ -464,15 +477,13 @@ extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const s
         LP_CUDA_OK(cudaEventRecord(b->ev_d2h[c], b->st_d2h));
         // hand back chunks whose bytes have already landed
         while (finished < c && cudaEventQuery(b->ev_d2h[finished]) == cudaSuccess) {
-            const int f0 = finished * b->chunk;
-            batch_finish_chunk(b, f0, std::min(b->chunk, n - f0), out, out_len, status);
+            batch_finish_chunk(b, sched[finished].first, sched[finished].second, out, out_len, status);
             finished++;
         }
     }
     for (; finished < nchunks; finished++) {
         LP_CUDA_OK(cudaEventSynchronize(b->ev_d2h[finished]));
-        const int f0 = finished * b->chunk;
-        batch_finish_chunk(b, f0, std::min(b->chunk, n - f0), out, out_len, status);
+        batch_finish_chunk(b, sched[finished].first, sched[finished].second, out, out_len, status);
     }
     b->last_launches = (int)(g_launches - launches0);
     return LP_OK;

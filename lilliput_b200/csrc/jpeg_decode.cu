@@ -409,6 +409,12 @@ __global__ void jpeg_multiscan_kernel(JpegDecodeItem* item, const JpegScanDesc* 
 #define LP_FIX_2_562915447 20995
 #define LP_FIX_3_072711026 25172
 
+__device__ __forceinline__ int sat_s16(int v) {
+    int r;
+    asm("cvt.sat.s16.s32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
 template <int SHIFT, bool SAT16>
 __device__ __forceinline__ void idct8(int& v0, int& v1, int& v2, int& v3, int& v4, int& v5, int& v6,
                                       int& v7) {
@@ -445,26 +451,29 @@ __device__ __forceinline__ void idct8(int& v0, int& v1, int& v2, int& v3, int& v
     v5 = (tmp12 - t1 + R) >> SHIFT;
     v3 = (tmp13 + t0 + R) >> SHIFT;
     v4 = (tmp13 - t0 + R) >> SHIFT;
-    if (SAT16) {
-        v0 = min(max(v0, -32768), 32767); v1 = min(max(v1, -32768), 32767);
-        v2 = min(max(v2, -32768), 32767); v3 = min(max(v3, -32768), 32767);
-        v4 = min(max(v4, -32768), 32767); v5 = min(max(v5, -32768), 32767);
-        v6 = min(max(v6, -32768), 32767); v7 = min(max(v7, -32768), 32767);
+    if (SAT16) {  // int16 saturation between the passes (what the SIMD IDCT's packssdw does): one cvt.sat each
+        v0 = sat_s16(v0); v1 = sat_s16(v1); v2 = sat_s16(v2); v3 = sat_s16(v3);
+        v4 = sat_s16(v4); v5 = sat_s16(v5); v6 = sat_s16(v6); v7 = sat_s16(v7);
     }
 }
 
+// Four samples: clamp to [-128, 127], + 128, pack.  cvt.pack.sat.s8.s32 saturates and packs two values
+// per instruction; the level shift is an XOR of the sign bits.
 __device__ __forceinline__ uint32_t pack_px(int a, int b, int c, int d) {
-    a = min(max(a, -128), 127) + 128;
-    b = min(max(b, -128), 127) + 128;
-    c = min(max(c, -128), 127) + 128;
-    d = min(max(d, -128), 127) + 128;
-    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+    uint32_t hi, w;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(b), "r"(a), "r"(hi));
+    return w ^ 0x80808080u;
 }
 
 __global__ void __launch_bounds__(128)
     jpeg_idct_kernel(const JpegDecodeItem* items, const int16_t* coef, uint8_t* planes) {
     const JpegDecodeItem& it = items[blockIdx.y];
     if (it.status != 0) return;
+    // the image's quantisation tables, once per CTA (read back 8 entries per load below)
+    __shared__ __align__(16) uint16_t s_qt[3][64];
+    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) s_qt[i >> 6][i & 63] = it.qt[i >> 6][i & 63];
+    __syncthreads();
     const int blk = blockIdx.x * blockDim.x + threadIdx.x;
     int c = 0;
     if (it.ncomp == 3) c = blk >= (int)it.block_off[2] ? 2 : (blk >= (int)it.block_off[1] ? 1 : 0);
@@ -473,18 +482,20 @@ __global__ void __launch_bounds__(128)
     const int rel = blk - (int)it.block_off[c];
     const int X = rel % it.bw[c], Y = rel / it.bw[c];
     const uint4* src = reinterpret_cast<const uint4*>(coef + it.coef_off + (size_t)blk * 64);
-    const uint16_t* q = it.qt[c];
+    const uint4* q4 = reinterpret_cast<const uint4*>(s_qt[c]);
     int v[64];
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const uint4 u = __ldg(src + r);
+        const uint4 qq = q4[r];
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             // 16-bit wrapping multiply (pmullw), as libjpeg-turbo's SIMD dequantisation does
             const int lo = (int16_t)(w[k] & 0xffff), hi = (int16_t)(w[k] >> 16);
-            v[r * 8 + 2 * k] = (int16_t)(lo * (int)q[r * 8 + 2 * k]);
-            v[r * 8 + 2 * k + 1] = (int16_t)(hi * (int)q[r * 8 + 2 * k + 1]);
+            v[r * 8 + 2 * k] = (int16_t)(lo * (int)(qw[k] & 0xffff));
+            v[r * 8 + 2 * k + 1] = (int16_t)(hi * (int)(qw[k] >> 16));
         }
     }
 #pragma unroll
@@ -606,30 +617,40 @@ __global__ void __launch_bounds__(128)
             cs[c][5 + k] = 3 * (int)((n8.y >> (8 * k)) & 0xff) + (int)((f8.y >> (8 * k)) & 0xff);
         }
     }
+    // 3 * (3*near + far) per chroma column once, so a pixel's chroma is add + add + shift; the -128 of
+    // Cb / Cr is folded into the colour-conversion constants; clamps are one VIMNMX.RELU each; bytes are
+    // assembled with PRMT (3 per output word) instead of shift + or per byte.
+    int c3[2][10];
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int j = 1; j < 9; j++) c3[c][j] = 3 * cs[c][j];
     uint32_t ow[12];
 #pragma unroll
-    for (int k = 0; k < 12; k++) ow[k] = 0;
+    for (int q = 0; q < 4; q++) {  // 4 pixels -> 3 output words
+        uint32_t B[4], G[4], R[4];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int j = 1 + (k >> 1);  // index of this pixel's chroma column in cs[]
-        int cb, cr;
-        if (k & 1) {
-            cb = (3 * cs[0][j] + cs[0][j + 1] + 7) >> 4;
-            cr = (3 * cs[1][j] + cs[1][j + 1] + 7) >> 4;
-        } else {
-            cb = (3 * cs[0][j] + cs[0][j - 1] + 8) >> 4;
-            cr = (3 * cs[1][j] + cs[1][j - 1] + 8) >> 4;
+        for (int t = 0; t < 4; t++) {
+            const int k = 4 * q + t;
+            const int j = 1 + (k >> 1);
+            int cb, cr;
+            if (k & 1) {
+                cb = (c3[0][j] + cs[0][j + 1] + 7) >> 4;
+                cr = (c3[1][j] + cs[1][j + 1] + 7) >> 4;
+            } else {
+                cb = (c3[0][j] + cs[0][j - 1] + 8) >> 4;
+                cr = (c3[1][j] + cs[1][j - 1] + 8) >> 4;
+            }
+            const int Y = (int)__byte_perm(yw[q], 0, 0x4440 + t);  // byte t of the word, zero-extended
+            // (c * (x - 128) + 32768) >> 16 with the -128 folded into the addend
+            R[t] = (uint32_t)__vimin_s32_relu(Y + ((91881 * cr + (32768 - 91881 * 128)) >> 16), 255);
+            G[t] = (uint32_t)__vimin_s32_relu(Y + ((-22554 * cb - 46802 * cr + (32768 + (22554 + 46802) * 128)) >> 16), 255);
+            B[t] = (uint32_t)__vimin_s32_relu(Y + ((116130 * cb + (32768 - 116130 * 128)) >> 16), 255);
         }
-        cb -= 128;
-        cr -= 128;
-        const int Y = (int)((yw[k >> 2] >> (8 * (k & 3))) & 0xff);
-        const int r = min(max(Y + ((91881 * cr + 32768) >> 16), 0), 255);
-        const int g = min(max(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16), 0), 255);
-        const int b = min(max(Y + ((116130 * cb + 32768) >> 16), 0), 255);
-        const int o = k * 3;
-        ow[o >> 2] |= (uint32_t)b << (8 * (o & 3));
-        ow[(o + 1) >> 2] |= (uint32_t)g << (8 * ((o + 1) & 3));
-        ow[(o + 2) >> 2] |= (uint32_t)r << (8 * ((o + 2) & 3));
+        // bytes: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+        ow[3 * q + 0] = __byte_perm(__byte_perm(B[0], G[0], 0x0040), __byte_perm(R[0], B[1], 0x0040), 0x5410);
+        ow[3 * q + 1] = __byte_perm(__byte_perm(G[1], R[1], 0x0040), __byte_perm(B[2], G[2], 0x0040), 0x5410);
+        ow[3 * q + 2] = __byte_perm(__byte_perm(R[2], B[3], 0x0040), __byte_perm(G[3], R[3], 0x0040), 0x5410);
     }
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(x0 - it.win_x0) * 3);
     dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);

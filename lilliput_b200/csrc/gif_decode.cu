@@ -148,6 +148,13 @@ struct LzwBits {
     uint64_t acc;
     int cnt;
     __device__ __forceinline__ int get(int n) {
+        if (cnt < n && p + 4 <= end) {  // 32 bits per refill while a whole word is left
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+            acc |= (uint64_t)__funnelshift_r(q[0], q[1], 8 * (int)(a & 3)) << cnt;  // q[1]: inside the padded buffer
+            p += 4;
+            cnt += 32;
+        }
         while (cnt < n) {
             if (p >= end) return -1;
             acc |= (uint64_t)(*p++) << cnt;

@@ -35,12 +35,22 @@ struct LsbBits {
     const uint8_t* end;
     uint64_t acc;
     int cnt;
+    // 32 bits per refill: two aligned word loads + a funnel shift instead of a chain of byte loads
+    // (the refill sits on the critical path of every symbol of a serial decoder)
     __device__ __forceinline__ void fill() {
-        while (cnt <= 56) {
-            acc |= (uint64_t)(p < end ? *p : 0) << cnt;
-            p++;
-            cnt += 8;
+        if (cnt > 32) return;
+        uint32_t w;
+        if (p + 4 <= end) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+            w = __funnelshift_r(q[0], q[1], 8 * (int)(a & 3));  // q[1] may lie past `end`: inside the padded buffer
+        } else {
+            w = 0;
+            for (int k = 0; k < 4; k++) w |= (uint32_t)(p + k < end ? p[k] : 0) << (8 * k);
         }
+        acc |= (uint64_t)w << cnt;
+        p += 4;
+        cnt += 32;
     }
     __device__ __forceinline__ uint32_t get(int n) {
         if (cnt < n) fill();

@@ -61,15 +61,26 @@ LP_VP8_INL void bd_init(BoolDec& b, const uint8_t* p, size_t n) {
 }
 
 LP_VP8_INL void bd_fill(BoolDec& b) {
-    // keep at least one byte of lookahead; take up to 6 bytes per refill
+#ifdef __CUDA_ARCH__
+    // device: 4 bytes per refill from two aligned word loads (the refill is on every symbol's critical path)
+    if (b.p + 4 <= b.end) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(b.p);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t le = __funnelshift_r(q[0], q[1], 8 * (int)(a & 3));  // q[1]: inside the padded buffer
+        b.p += 4;
+        b.value = (b.value << 32) | __byte_perm(le, 0, 0x0123);
+        b.bits += 32;
+    } else {
+#else
+    // take up to 6 bytes per refill
     if (b.p + 6 <= b.end) {
         uint64_t w = 0;
-#pragma unroll
         for (int i = 0; i < 6; i++) w = (w << 8) | b.p[i];
         b.p += 6;
         b.value = (b.value << 48) | w;
         b.bits += 48;
     } else {
+#endif
         const uint32_t byte = b.p < b.end ? *b.p++ : 0u;  // zeros past the end, as libwebp feeds
         b.value = (b.value << 8) | byte;
         b.bits += 8;

@@ -55,13 +55,26 @@ LP_VP8_INL void bits_init(Bits& b, const uint8_t* p, size_t n) {
     b.eos = 0;
 }
 LP_VP8_INL void bits_fill(Bits& b) {
-    while (b.nbits <= 56) {
-        uint64_t byte = 0;
-        if (b.pos < b.n) byte = b.p[b.pos];
-        else if (b.pos >= b.n + 8) b.eos = 1;  // ran well past the end: the stream is truncated
-        b.pos++;
-        b.val |= byte << b.nbits;
-        b.nbits += 8;
+    // 32 bits per refill (the refill is on the critical path of every symbol)
+    while (b.nbits <= 32) {
+        uint64_t w = 0;
+        if (b.pos + 4 <= b.n) {
+#ifdef __CUDA_ARCH__
+            const uintptr_t a = reinterpret_cast<uintptr_t>(b.p + b.pos);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+            w = __funnelshift_r(q[0], q[1], 8 * (int)(a & 3));  // q[1] may lie past the stream: inside the padded buffer
+#else
+            w = (uint64_t)b.p[b.pos] | ((uint64_t)b.p[b.pos + 1] << 8) | ((uint64_t)b.p[b.pos + 2] << 16) |
+                ((uint64_t)b.p[b.pos + 3] << 24);
+#endif
+        } else {
+            for (int k = 0; k < 4; k++)
+                if (b.pos + k < b.n) w |= (uint64_t)b.p[b.pos + k] << (8 * k);
+            if (b.pos >= b.n + 8) b.eos = 1;  // ran well past the end: the stream is truncated
+        }
+        b.pos += 4;
+        b.val |= w << b.nbits;
+        b.nbits += 32;
     }
 }
 LP_VP8_INL uint32_t bits_read(Bits& b, int n) {  // n <= 32

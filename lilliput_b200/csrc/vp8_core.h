@@ -9,7 +9,7 @@
 // and on golden frames made by it (tests/golden).
 //
 // The same functions compile for the device (webp_decode.cu, LP_VP8_FN = __device__) and for the
-// CPU test harness (tests/native/vp8_cpu.cpp).  Layout of one frame's working set:
+// CPU test harness (oracle/oracle_webp.cpp).  Layout of one frame's working set:
 //   y / u / v planes      mb_w*16 x mb_h*16 (and half size), reconstructed then filtered in place
 //   top_modes[mb_w*4]     sub-block modes of the row above (mode context, RFC 6386 s.11.3)
 //   top_nz[mb_w*9]        non-zero flags of the row above: 4 Y, 2 U, 2 V, 1 Y2 (s.13.3)

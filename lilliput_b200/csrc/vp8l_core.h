@@ -8,7 +8,7 @@
 // (ref webp.cpp:336-351); libwebp is a vendored BINARY in the reference, nothing is taken from it.
 // Parity is pinned on the reference's decoder itself (oracle/_ref, tests/test_webp_core.py) and on
 // golden frames made by it.  The same functions compile for the device (webp_decode.cu) and for
-// the CPU test harness (tests/native/vp8_cpu.cpp).
+// the CPU test harness (oracle/oracle_webp.cpp).
 //
 // Lossless decoding is exact by definition: every output must be bit-identical.
 #pragma once

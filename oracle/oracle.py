@@ -155,3 +155,86 @@ def blend_over(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
     if rc != 0:
         raise RuntimeError("oracle_blend_over rc=%d" % rc)
     return out
+
+
+# --- GIF (oracle_gif.c): giflib record walk + LZW + the reference's compositor, and its encoder ----
+def _gif_sigs():
+    l = lib()
+    l.oracle_gif_open.restype = C.c_void_p
+    l.oracle_gif_open.argtypes = [C.c_void_p, C.c_size_t]
+    l.oracle_gif_close.argtypes = [C.c_void_p]
+    l.oracle_gif_width.argtypes = [C.c_void_p]
+    l.oracle_gif_height.argtypes = [C.c_void_p]
+    l.oracle_gif_next_frame.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    l.oracle_gif_skip_frame.argtypes = [C.c_void_p]
+    l.oracle_gif_enc_open.restype = C.c_void_p
+    l.oracle_gif_enc_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    l.oracle_gif_enc_close.argtypes = [C.c_void_p]
+    l.oracle_gif_enc_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    l.oracle_gif_enc_finish.restype = C.c_size_t
+    l.oracle_gif_enc_finish.argtypes = [C.c_void_p, C.c_void_p]
+    return l
+
+
+def gif_frames(data: bytes, max_frames: int = 1 << 16):
+    """Every composited full-canvas BGRA frame: (frames, delays in 1/100 s, giflib disposal modes, rc)."""
+    l = _gif_sigs()
+    src = np.frombuffer(data, dtype=np.uint8)
+    d = l.oracle_gif_open(src.ctypes.data, src.size)
+    if not d:
+        raise RuntimeError("oracle_gif_open failed")
+    try:
+        w, h = l.oracle_gif_width(d), l.oracle_gif_height(d)
+        canvas = np.zeros((h, w, 4), dtype=np.uint8)
+        frames, delays, disps, rc = [], [], [], 0
+        for _ in range(max_frames):
+            dl, dp = C.c_int(), C.c_int()
+            r = l.oracle_gif_next_frame(d, canvas.ctypes.data, C.byref(dl), C.byref(dp))
+            if r <= 0:
+                rc = r
+                break
+            frames.append(canvas.copy())
+            delays.append(dl.value)
+            disps.append(dp.value)
+        return frames, delays, disps, rc
+    finally:
+        l.oracle_gif_close(d)
+
+
+def gif_transcode(data: bytes, per_frame=None, max_frames: int = 0, cap: int = 8 << 20) -> bytes:
+    """GIF -> GIF as ImageOps.Transform drives it: decode + composite each frame, per_frame(BGRA) (fit /
+    resize; identity when None), encode with the reference's palette mapping and giflib's LZW."""
+    l = _gif_sigs()
+    src = np.frombuffer(data, dtype=np.uint8)
+    d = l.oracle_gif_open(src.ctypes.data, src.size)
+    if not d:
+        raise RuntimeError("oracle_gif_open failed")
+    dst = np.zeros(cap, dtype=np.uint8)
+    e = None
+    try:
+        w, h = l.oracle_gif_width(d), l.oracle_gif_height(d)
+        canvas = np.zeros((h, w, 4), dtype=np.uint8)
+        n = 0
+        while True:
+            if max_frames and n >= max_frames:
+                # ops.go:384-390: past the frame cap the remaining frames are skipped (decoded to the end)
+                while l.oracle_gif_skip_frame(d) > 0:  # gifDecoder.SkipFrame until EOF
+                    pass
+                break
+            r = l.oracle_gif_next_frame(d, canvas.ctypes.data, None, None)
+            if r < 0:
+                raise RuntimeError("oracle gif decode failed")
+            if r == 0:
+                break
+            f = np.ascontiguousarray(per_frame(canvas) if per_frame else canvas)
+            if e is None:
+                e = l.oracle_gif_enc_open(d, f.shape[1], f.shape[0], dst.ctypes.data, dst.size)
+            if not l.oracle_gif_enc_frame(e, d, f.ctypes.data, f.shape[1], f.shape[0]):
+                raise RuntimeError("oracle gif encode failed")
+            n += 1
+        size = l.oracle_gif_enc_finish(e, d) if e else 0
+        return dst[:size].tobytes()
+    finally:
+        if e:
+            l.oracle_gif_enc_close(e)
+        l.oracle_gif_close(d)

@@ -1,11 +1,20 @@
-// vp8_cpu.cpp -- TEST INFRASTRUCTURE.  Compiles lilliput_b200/csrc/vp8_core.h for the host so
-// the VP8 decoding logic the device kernels run can be checked bit-for-bit against the
-// reference's libwebp (through oracle/_ref) on a machine without a GPU.  Not part of the product.
+// oracle_webp.cpp -- TEST INFRASTRUCTURE (oracle/): the WebP codec logic as a CPU library.
+//
+// Unlike the C restatements next to it, this oracle is NOT an independent second implementation: it
+// compiles the very headers the device kernels are built from (lilliput_b200/csrc/vp8_core.h,
+// vp8l_core.h, vp8_enc_core.h, vp8l_enc_core.h) for the host, with serial drivers around them.  What
+// that buys: the exact decoding / encoding logic of the product can be checked bit-for-bit against
+// the reference's libwebp (oracle/_ref) on a machine without a GPU, and the GPU tests then only have
+// to show that the parallel schedule (warp-cooperative reconstruction, parallel bit packing ...)
+// reproduces this serial run.  Pinned: tests/test_webp_core.py + tests/golden/webp_golden.npz (made
+// by the reference), and in the build container a 1 496-configuration libwebp encoder sweep.
+// libwebp 1.5.0 is the algorithm's home (deps/build-deps-linux.sh:235; call sites ref webp.cpp:65-112,
+// 309-350); the bitstream formats are RFC 6386 (VP8) and the WebP lossless specification (VP8L).
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
-#include "../../lilliput_b200/csrc/vp8_core.h"
+#include "../lilliput_b200/csrc/vp8_core.h"
 
 extern "C" int vp8_cpu_info(const uint8_t* d, size_t n, int* w, int* h) {
     if (n < 10 || d[3] != 0x9d || d[4] != 0x01 || d[5] != 0x2a) return 1;
@@ -41,7 +50,7 @@ extern "C" int vp8_cpu_decode_bgr(const uint8_t* d, size_t n, uint8_t* out, int 
 }
 
 // ---- VP8L (lossless) and ALPH, same idea ---------------------------------------------------
-#include "../../lilliput_b200/csrc/vp8l_core.h"
+#include "../lilliput_b200/csrc/vp8l_core.h"
 
 // Decodes a "VP8L" chunk payload to BGRA (channels = 4) or BGR (3).
 extern "C" int vp8l_cpu_decode(const uint8_t* d, size_t n, int w, int h, uint8_t* out, int channels) {
@@ -67,7 +76,7 @@ extern "C" int alph_cpu_decode(const uint8_t* d, size_t n, int w, int h, uint8_t
 }
 
 // ---- VP8L encoder core, host build: whole stream written serially (the device packs pixels in parallel)
-#include "../../lilliput_b200/csrc/vp8l_enc_core.h"
+#include "../lilliput_b200/csrc/vp8l_enc_core.h"
 
 // channels 3/4: a "VP8L" chunk payload from a BGR(A) frame; channels 1: an ALPH chunk payload
 // (header byte + headerless VP8L stream) from a plane.  Returns the size, or -1 if it does not fit.
@@ -100,7 +109,7 @@ extern "C" long vp8l_cpu_encode(const uint8_t* frame, size_t step, int w, int h,
 }
 
 // ---- VP8 lossy encoder core, host build
-#include "../../lilliput_b200/csrc/vp8_enc_core.h"
+#include "../lilliput_b200/csrc/vp8_enc_core.h"
 
 // BGR(A) frame -> "VP8 " chunk payload.  Returns the size (0 = failed).  `recon_bgr` (optional) gets
 // what a decoder WITHOUT loop filter would show, for debugging.

@@ -1,5 +1,5 @@
 """CPU: the VP8 key-frame decoding logic the device kernels run (lilliput_b200/csrc/vp8_core.h),
-compiled for the host by tests/native/vp8_cpu.cpp, against frames decoded by the reference's own
+compiled for the host by oracle/oracle_webp.cpp, against frames decoded by the reference's own
 libwebp (tests/golden/webp_golden.npz, made by make_golden_webp.py through oracle/_ref).
 Bit-exact: VP8 decoding is integer arithmetic end to end, upsampler and colour matrix included."""
 import hashlib

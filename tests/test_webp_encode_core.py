@@ -1,5 +1,5 @@
 """CPU: the WebP ENCODER cores the device runs (vp8l_enc_core.h lossless, vp8_enc_core.h lossy),
-compiled for the host by tests/native/vp8_cpu.cpp.
+compiled for the host by oracle/oracle_webp.cpp.
   lossless: the stream decodes (with the device's own decoder core, and with the reference's libwebp
             where oracle/_ref is present) to exactly the input pixels;
   lossy:    the stream is a valid VP8 key frame -- both decoders agree bit for bit on its pixels --

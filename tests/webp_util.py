@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_BUILD = os.path.join(ROOT, "tests", "native", "_build")
+_BUILD = os.path.join(ROOT, "oracle", "_build")
 
 
 def webp_golden():
@@ -25,10 +25,10 @@ def chunks_of(webp: bytes):
 
 
 def vp8_cpu_lib():
-    """tests/native/vp8_cpu.cpp (the device's VP8 logic compiled for the host) as a ctypes handle."""
+    """oracle/oracle_webp.cpp (the device's WebP codec logic compiled for the host) as a ctypes handle."""
     os.makedirs(_BUILD, exist_ok=True)
     so = os.path.join(_BUILD, "libvp8cpu.so")
-    srcs = [os.path.join(ROOT, "tests", "native", "vp8_cpu.cpp"),
+    srcs = [os.path.join(ROOT, "oracle", "oracle_webp.cpp"),
             os.path.join(ROOT, "lilliput_b200", "csrc", "vp8_core.h"),
             os.path.join(ROOT, "lilliput_b200", "csrc", "vp8_tables.h"),
             os.path.join(ROOT, "lilliput_b200", "csrc", "vp8l_core.h"),

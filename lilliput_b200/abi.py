@@ -153,6 +153,8 @@ class Lib:
     def decode(self, data: bytes) -> np.ndarray:
         """openCVDecoder.DecodeTo (ref opencv.go:816): packed BGR/BGRA/Gray u8."""
         w0, h0, t0, _ = self.header(data)
+        if max(w0, h0) > 8192:  # the helper's framebuffer limit (lilliput_host.cpp kHelperMaxSide)
+            raise LilliputError(LP_ERR_BUF_TOO_SMALL)
         src = np.frombuffer(data, dtype=np.uint8)
         ch = ((t0 >> 3) & 63) + 1
         px = np.empty(h0 * w0 * ch, dtype=np.uint8)

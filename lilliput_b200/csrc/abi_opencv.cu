@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -395,7 +396,12 @@ opencv_mat opencv_mat_create(int width, int height, int type) {
     m->rows = height;
     m->type = type;
     m->step = (size_t)width * m->elem();
-    m->owned_host.resize(m->step * height);
+    try {
+        m->owned_host.resize(m->step * height);
+    } catch (const std::bad_alloc&) {  // no exception crosses the C ABI: an impossible size is a NULL mat
+        delete m;
+        return nullptr;
+    }
     m->host = m->owned_host.data();
     m->host_cap = m->owned_host.size();
     m->host_valid = true;
@@ -455,7 +461,11 @@ int lp_mat_sync_host(opencv_mat mat) {
     if (m->host_valid || !m->dev_valid) return LP_OK;
     const size_t row = (size_t)m->cols * m->elem();
     if (row * m->rows > m->host_cap) {  // e.g. after an axis-swapping orientation into a small buffer
-        m->owned_host.resize(row * m->rows);
+        try {
+            m->owned_host.resize(row * m->rows);
+        } catch (const std::bad_alloc&) {
+            return LP_ERR_BUF_TOO_SMALL;
+        }
         m->host = m->owned_host.data();
         m->host_cap = m->owned_host.size();
     }

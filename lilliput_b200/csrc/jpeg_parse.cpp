@@ -131,8 +131,11 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
             if (ns != h.ncomp) h.supported = false;  // one scan per component: serial multi-scan path
             if (h.progressive || ns != h.ncomp) {
                 bool ok = true;
-                for (int i = 0; i < h.ncomp; i++)
+                for (int i = 0; i < h.ncomp; i++) {
+                    // (a frame header this decoder does not take -- 12-bit, 4 components -- leaves the factors 0)
+                    if (h.comp[i].h < 1 || h.comp[i].v < 1) { ok = false; break; }
                     if (h.maxh % h.comp[i].h || h.maxv % h.comp[i].v || !h.qt_present[h.comp[i].tq]) ok = false;
+                }
                 h.multiscan = ok;
             }
             for (int i = 0; i < ns && h.supported; i++) {

@@ -3,6 +3,8 @@
 // all of it is behind the per-image C ABI (lp_opencv.h).
 #include "lilliput_host.hpp"
 
+#include <new>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -850,7 +852,12 @@ static ImageOptions fromC(const lp_image_options* o) {
     return r;
 }
 
-extern "C" int lp_transform(const uint8_t* in, size_t in_len, const lp_image_options* opt,
+// The stage helpers below size their own framebuffers from the file's header; a real caller's ImageOps has
+// a fixed maxSize and refuses larger images with ErrBufTooSmall (ref opencv.go:250-267).  Same rule here, so a
+// hostile header cannot make a helper allocate gigabytes.
+static const int kHelperMaxSide = 8192;
+
+static int lp_transform_impl(const uint8_t* in, size_t in_len, const lp_image_options* opt,
                             uint8_t* dst, size_t dst_cap, size_t* out_len, int max_size) {
     if (!in || !opt || !dst || !out_len) return LP_ERR_BAD_ARGUMENT;
     std::unique_ptr<Decoder> d;
@@ -867,7 +874,7 @@ extern "C" int lp_transform(const uint8_t* in, size_t in_len, const lp_image_opt
     return ops->Transform(d.get(), fromC(opt), dst, dst_cap, out_len);
 }
 
-extern "C" int lp_decode_host(const uint8_t* in, size_t in_len, uint8_t* pixels,
+static int lp_decode_host_impl(const uint8_t* in, size_t in_len, uint8_t* pixels,
                               size_t pixels_cap, int* width, int* height, int* type,
                               int* orientation) {
     std::unique_ptr<Decoder> d;
@@ -886,6 +893,7 @@ extern "C" int lp_decode_host(const uint8_t* in, size_t in_len, uint8_t* pixels,
     size_t need = (size_t)h.width * h.height * t.Channels();
     if (need > pixels_cap) return LP_ERR_BUF_TOO_SMALL;
     int side = std::max(h.width, h.height);
+    if (side > kHelperMaxSide) return LP_ERR_BUF_TOO_SMALL;  // like an ImageOps whose framebuffers are smaller than the image
     Framebuffer f(side, side);
     if ((e = d->DecodeTo(&f))) return e;
     if (lp_mat_sync_host(f.mat)) return LP_ERR_CUDA;
@@ -901,7 +909,7 @@ static Error wrapPixels(Framebuffer& f, const uint8_t* src, int w, int h, int ty
     return LP_OK;
 }
 
-extern "C" int lp_fit_host(const uint8_t* src, int sw, int sh, int type, uint8_t* dst, int dw,
+static int lp_fit_host_impl(const uint8_t* src, int sw, int sh, int type, uint8_t* dst, int dw,
                            int dh) {
     int side = std::max(std::max(sw, sh), std::max(dw, dh));
     Framebuffer a(side, side), b(side, side);
@@ -913,7 +921,7 @@ extern "C" int lp_fit_host(const uint8_t* src, int sw, int sh, int type, uint8_t
     return LP_OK;
 }
 
-extern "C" int lp_resize_host(const uint8_t* src, int sw, int sh, int type, int cx, int cy, int cw,
+static int lp_resize_host_impl(const uint8_t* src, int sw, int sh, int type, int cx, int cy, int cw,
                               int ch, uint8_t* dst, int dw, int dh, int interpolation) {
     int side = std::max(std::max(sw, sh), std::max(dw, dh));
     Framebuffer a(side, side), b(side, side);
@@ -931,7 +939,7 @@ extern "C" int lp_resize_host(const uint8_t* src, int sw, int sh, int type, int 
     return LP_OK;
 }
 
-extern "C" int lp_encode_host(const char* ext, const uint8_t* pixels, int w, int h, int type,
+static int lp_encode_host_impl(const char* ext, const uint8_t* pixels, int w, int h, int type,
                               const int* opt, size_t opt_len, uint8_t* dst, size_t dst_cap,
                               size_t* out_len) {
     int side = std::max(w, h);
@@ -948,7 +956,7 @@ extern "C" int lp_encode_host(const char* ext, const uint8_t* pixels, int w, int
     return enc->Encode(nullptr, o, &content, out_len);  // multi-frame encoders answer at the flush (ops.go:285-292)
 }
 
-extern "C" int lp_orient_host(const uint8_t* src, int w, int h, int type, int orientation,
+static int lp_orient_host_impl(const uint8_t* src, int w, int h, int type, int orientation,
                               uint8_t* dst, int* ow, int* oh) {
     int side = std::max(w, h);
     Framebuffer a(side, side);
@@ -962,7 +970,7 @@ extern "C" int lp_orient_host(const uint8_t* src, int w, int h, int type, int or
     return LP_OK;
 }
 
-extern "C" int lp_gif_get_info(const uint8_t* in, size_t in_len, lp_gif_info* info) {
+static int lp_gif_get_info_impl(const uint8_t* in, size_t in_len, lp_gif_info* info) {
     if (!in || !info) return LP_ERR_BAD_ARGUMENT;
     std::unique_ptr<Decoder> d;
     Error e = NewDecoder(in, in_len, &d);
@@ -979,7 +987,7 @@ extern "C" int lp_gif_get_info(const uint8_t* in, size_t in_len, lp_gif_info* in
     return LP_OK;
 }
 
-extern "C" int lp_gif_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
+static int lp_gif_decode_frames_host_impl(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
                                          int max_frames, int* n_frames, int* delays_ms, int* disposals) {
     if (!in || !frames || !n_frames) return LP_ERR_BAD_ARGUMENT;
     *n_frames = 0;
@@ -991,6 +999,7 @@ extern "C" int lp_gif_decode_frames_host(const uint8_t* in, size_t in_len, uint8
     if ((e = d->Header(&h))) return e;
     const size_t frame_bytes = (size_t)h.width * h.height * 4;
     // like ImageOps, ONE framebuffer receives every frame (the compositor builds on its content)
+    if (std::max(h.width, h.height) > kHelperMaxSide) return LP_ERR_BUF_TOO_SMALL;
     Framebuffer f(std::max(h.width, h.height), std::max(h.width, h.height));
     for (int i = 0; i < max_frames; i++) {
         e = d->DecodeTo(&f);
@@ -1011,7 +1020,7 @@ extern "C" int lp_gif_decode_frames_host(const uint8_t* in, size_t in_len, uint8
 // meta[8*i..] = width, height, channels, x_offset, y_offset, delay_ms, dispose, blend.
 // info[0..7] = canvas width, canvas height, pixel type, frame count, total duration, loop count,
 // background colour, ICC length.
-extern "C" int lp_webp_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
+static int lp_webp_decode_frames_host_impl(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
                                           int max_frames, int* n_frames, int* meta, unsigned int* info) {
     if (!in || !n_frames) return LP_ERR_BAD_ARGUMENT;
     *n_frames = 0;
@@ -1036,6 +1045,11 @@ extern "C" int lp_webp_decode_frames_host(const uint8_t* in, size_t in_len, uint
     }
     int rc = LP_OK;
     size_t used = 0;
+    if (std::max(cw, ch) > kHelperMaxSide) {
+        webp_decoder_release(d);
+        opencv_mat_release(src);
+        return frames ? LP_ERR_BUF_TOO_SMALL : LP_OK;  // header-only queries still answer
+    }
     opencv_mat m = opencv_mat_create(cw, ch, type);
     for (int i = 0; frames && i < max_frames; i++) {
         if (!webp_decoder_decode(d, m)) {
@@ -1075,3 +1089,34 @@ extern "C" int lp_webp_decode_frames_host(const uint8_t* in, size_t in_len, uint
     opencv_mat_release(src);
     return rc;
 }
+
+// ---- C ABI entry points.  No C++ exception may cross the boundary: an allocation the input makes
+//      impossible (a header that declares a 60000 x 60000 canvas ...) is reported like the Go side reports a
+//      framebuffer that is too small.
+#define LP_GUARDED(call)                      \
+    try {                                     \
+        return call;                          \
+    } catch (const std::bad_alloc&) {         \
+        return LP_ERR_BUF_TOO_SMALL;          \
+    } catch (...) {                           \
+        return LP_ERR_BAD_ARGUMENT;           \
+    }
+extern "C" int lp_transform(const uint8_t* in, size_t in_len, const lp_image_options* opt,
+                            uint8_t* dst, size_t dst_cap, size_t* out_len, int max_size) { LP_GUARDED(lp_transform_impl(in, in_len, opt, dst, dst_cap, out_len, max_size)) }
+extern "C" int lp_decode_host(const uint8_t* in, size_t in_len, uint8_t* pixels,
+                              size_t pixels_cap, int* width, int* height, int* type,
+                              int* orientation) { LP_GUARDED(lp_decode_host_impl(in, in_len, pixels, pixels_cap, width, height, type, orientation)) }
+extern "C" int lp_fit_host(const uint8_t* src, int sw, int sh, int type, uint8_t* dst, int dw,
+                           int dh) { LP_GUARDED(lp_fit_host_impl(src, sw, sh, type, dst, dw, dh)) }
+extern "C" int lp_resize_host(const uint8_t* src, int sw, int sh, int type, int cx, int cy, int cw,
+                              int ch, uint8_t* dst, int dw, int dh, int interpolation) { LP_GUARDED(lp_resize_host_impl(src, sw, sh, type, cx, cy, cw, ch, dst, dw, dh, interpolation)) }
+extern "C" int lp_encode_host(const char* ext, const uint8_t* pixels, int w, int h, int type,
+                              const int* opt, size_t opt_len, uint8_t* dst, size_t dst_cap,
+                              size_t* out_len) { LP_GUARDED(lp_encode_host_impl(ext, pixels, w, h, type, opt, opt_len, dst, dst_cap, out_len)) }
+extern "C" int lp_orient_host(const uint8_t* src, int w, int h, int type, int orientation,
+                              uint8_t* dst, int* ow, int* oh) { LP_GUARDED(lp_orient_host_impl(src, w, h, type, orientation, dst, ow, oh)) }
+extern "C" int lp_gif_get_info(const uint8_t* in, size_t in_len, lp_gif_info* info) { LP_GUARDED(lp_gif_get_info_impl(in, in_len, info)) }
+extern "C" int lp_gif_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
+                                         int max_frames, int* n_frames, int* delays_ms, int* disposals) { LP_GUARDED(lp_gif_decode_frames_host_impl(in, in_len, frames, frames_cap, max_frames, n_frames, delays_ms, disposals)) }
+extern "C" int lp_webp_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
+                                          int max_frames, int* n_frames, int* meta, unsigned int* info) { LP_GUARDED(lp_webp_decode_frames_host_impl(in, in_len, frames, frames_cap, max_frames, n_frames, meta, info)) }

@@ -121,3 +121,26 @@ def test_jpeg_header_and_cicp_helpers(golden):
     assert l.opencv_decoder_get_png_cicp(arr, n, *[C.byref(v) for v in vals]) == 1
     assert [v.value for v in vals] == [12, 13, 0, 1]
     assert l.opencv_png_insert_cicp(arr, n, n + 3, 1, 1, 1, 1) == n  # no room: unchanged
+
+
+def test_hostile_headers_are_refused_not_fatal():
+    """Found by tests/fuzz_probe.py: (1) a frame header this decoder does not take (12-bit) followed by a
+    scan header used to divide by a zero sampling factor; (2) a header declaring a gigantic image made the
+    stage helpers allocate by the header's word.  Both are host-side and must answer with an error code."""
+    from lilliput_b200 import abi
+    lib = abi.load_cuda()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "jpeg_multiscan_golden.npz"))
+    data = bytearray(g["jpg_" + str(g["names"][0])].tobytes())
+    i = data.find(b"\xff\xc2")
+    assert i > 0
+    data[i + 4] = 12  # sample precision
+    try:
+        lib.header(bytes(data))
+    except abi.LilliputError:
+        pass
+    from tests.png_writer import write_png
+    png = bytearray(write_png(np.zeros((2, 2, 3), np.int64), 2, 8))
+    png[16:24] = (60000).to_bytes(4, "big") + (60000).to_bytes(4, "big")  # IHDR width, height (CRC not checked here)
+    with pytest.raises(abi.LilliputError) as e:
+        lib.decode(bytes(png))
+    assert e.value.code == abi.LP_ERR_BUF_TOO_SMALL

@@ -20,7 +20,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CUDA_LIB = os.path.join(ROOT, "lilliput_b200", "liblilliput_b200.so")
+CUDA_LIB = os.environ.get("LP_CUDA_LIB") or os.path.join(ROOT, "lilliput_b200", "liblilliput_b200.so")
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
 
 # ImageOpsSizeMethod, ref ops.go:17-22

@@ -189,7 +189,7 @@ struct alignas(8) SubState {
     uint32_t phase;  // (block-in-MCU << 6) | zig-zag index expected at p
 };
 
-constexpr int kDcBits = 9, kAcBits = 11;
+constexpr int kDcBits = 9, kAcBits = 12;  // a longer code in ANY lane sends the whole warp through the slow walk
 
 // Per-CTA decode tables.  DC tables are indexed by the next 9 bits, AC tables by the next 11
 // (longer codes -- well under 0.1 % of symbols with the Annex-K tables -- take the canonical walk).
@@ -377,7 +377,11 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
     nslots = closed * 64 + z - z_start;
 }
 
-__global__ void __launch_bounds__(kHuffThreads, 4)
+// 3 CTAs/SM (40 registers) measured faster than 4 at 32 registers (spills in the write pass) or 2 at 62
+#ifndef LP_HUFF_MIN_CTAS
+#define LP_HUFF_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     jpeg_huff_sync_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* clean,
                           SubState* states_all, uint32_t* nslots_all, int16_t* coef, int16_t* dcdiff_all,
                           uint32_t sub_per_thread) {

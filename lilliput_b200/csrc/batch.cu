@@ -24,6 +24,13 @@ struct lp_batch {
     cudaStream_t st_h2d = nullptr;   // input copies (pipelined transform)
     cudaStream_t st_d2h = nullptr;   // output copies (pipelined transform)
     int chunk = 0, max_chunks = 0;
+    int first_chunk = 0;  // pipelined path: size of the opening chunk (one wave of Huffman CTAs)
+    int pipe_chunk = 0;   // pipelined path: size of the following chunks
+    // Huffman tables of the last file seen (fast path of table_set_for)
+    int last_table_idx = -1;
+    bool last_present[2][4];
+    uint8_t last_bits[2][4][17];
+    uint8_t last_vals[2][4][256];
     // geometry (fixed by cfg)
     int W = 0, H = 0, out_w = 0, out_h = 0;
     int crop_x = 0, crop_y = 0, crop_w = 0, crop_h = 0;
@@ -109,11 +116,17 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
         delete b;
         return nullptr;
     }
-    // default chunk: two full waves of the per-image Huffman CTAs (no mostly-empty tail wave)
     const int slots = jpeg_huff_parallel_slots();
-    b->chunk = cfg->chunk > 0 ? cfg->chunk : (slots > 0 ? 2 * slots : 512);
+    // default chunk: three full waves of the per-image Huffman CTAs (no mostly-empty tail wave; larger
+    // launches for the bandwidth-bound kernels); the pipelined path opens with a single wave
+    b->chunk = cfg->chunk > 0 ? cfg->chunk : (slots > 0 ? 3 * slots : 512);
+    b->first_chunk = slots > 0 ? std::min(slots, b->chunk) : b->chunk / 2;
+    // the pipelined host-buffer path prefers finer grains (what is exposed is the first upload and the last
+    // download): two waves per chunk measured best there, three for the device-resident path
+    b->pipe_chunk = (cfg->chunk > 0 || slots <= 0) ? b->chunk : std::min(b->chunk, 2 * slots);
     b->chunk = std::min(b->chunk, cfg->max_images);
-    b->max_chunks = ceil_div(cfg->max_images, b->chunk) + 1;  // +1: the pipelined path opens with a half chunk
+    b->pipe_chunk = std::max(1, std::min(b->pipe_chunk, b->chunk));
+    b->max_chunks = ceil_div(cfg->max_images, b->pipe_chunk) + 2;  // + the opening chunk of the pipelined path
     // worst-case per-image layout: 4:4:4 needs the most blocks
     const size_t mcus = (size_t)ceil_div(b->W, 8) * ceil_div(b->H, 8);
     b->max_blocks_alloc = mcus * 3 + 4 * ((size_t)ceil_div(b->W, 8) + ceil_div(b->H, 8)) + 16;
@@ -170,7 +183,23 @@ extern "C" void lp_batch_destroy(lp_batch* b) {
     batch_free(b);
 }
 
+static int table_set_lookup(lp_batch* b, const JpegHeader& h);
 static int table_set_for(lp_batch* b, const JpegHeader& h) {
+    // nearly every file of a batch carries the tables of the previous one: compare before building a key
+    if (b->last_table_idx >= 0 && !memcmp(h.huff_present, b->last_present, sizeof(h.huff_present)) &&
+        !memcmp(h.huff_bits, b->last_bits, sizeof(h.huff_bits)) && !memcmp(h.huff_vals, b->last_vals, sizeof(h.huff_vals)))
+        return b->last_table_idx;
+    const int found = table_set_lookup(b, h);
+    if (found >= 0) {
+        memcpy(b->last_present, h.huff_present, sizeof(h.huff_present));
+        memcpy(b->last_bits, h.huff_bits, sizeof(h.huff_bits));
+        memcpy(b->last_vals, h.huff_vals, sizeof(h.huff_vals));
+        b->last_table_idx = found;
+    }
+    return found;
+}
+
+static int table_set_lookup(lp_batch* b, const JpegHeader& h) {
     std::string key;
     for (int tc = 0; tc < 2; tc++)
         for (int th = 0; th < 4; th++) {
@@ -195,13 +224,15 @@ static void batch_begin(lp_batch* b, int n) {
     b->n = n;
     b->tables.clear();
     b->table_index.clear();
+    b->last_table_idx = -1;
     b->tables_uploaded = 0;
     b->dev_off = b->clean_off = b->state_off = 0;
     b->parallel_huffman = true;
 }
 
-// Host: parse the headers of images [i0, i0+cnt), lay out their device scratch.
-static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int i0, int cnt) {
+// Host: where the files of images [i0, i0+cnt) go in the device scan buffer (no header parsing, so the
+// bytes can start crossing PCIe before the headers are looked at).
+static int batch_layout_chunk(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int i0, int cnt) {
     // input files go to HBM as they are (contiguous runs of pointers = one transfer)
     int i = i0;
     while (i < i0 + cnt) {
@@ -214,6 +245,11 @@ static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t
         b->dev_off = round_up(b->dev_off + run, (size_t)16);
         i = j + 1;
     }
+    return LP_OK;
+}
+
+// Host: parse the headers of images [i0, i0+cnt), lay out their device scratch.
+static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int i0, int cnt) {
     for (int k = i0; k < i0 + cnt; k++) {
         JpegHeader h;
         int rc = jpeg_parse_header(in[k], in_len[k], &h);
@@ -275,8 +311,8 @@ static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t
     return LP_OK;
 }
 
-// H2D: the chunk's files, its items and any Huffman table sets not yet on the device.
-static int batch_upload_chunk(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int i0, int cnt,
+// H2D: the chunk's files.
+static int batch_upload_files(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int i0, int cnt,
                               cudaStream_t st) {
     int i = i0;
     while (i < i0 + cnt) {
@@ -286,6 +322,11 @@ static int batch_upload_chunk(lp_batch* b, const uint8_t* const* in, const size_
         LP_CUDA_OK(cudaMemcpyAsync(b->d_scan + b->file_dev_off[i], in[i], run, cudaMemcpyHostToDevice, st));
         i = j + 1;
     }
+    return LP_OK;
+}
+
+// H2D: the chunk's items and any Huffman table sets not yet on the device.
+static int batch_upload_items(lp_batch* b, int i0, int cnt, cudaStream_t st) {
     LP_CUDA_OK(cudaMemcpyAsync(b->d_items + i0, b->items.data() + i0, (size_t)cnt * sizeof(JpegDecodeItem),
                                cudaMemcpyHostToDevice, st));
     if (b->tables.size() > b->tables_uploaded) {
@@ -383,9 +424,11 @@ extern "C" int lp_batch_stage(lp_batch* b, const uint8_t* const* in, const size_
     batch_begin(b, n);
     for (int i0 = 0; i0 < n; i0 += b->chunk) {
         const int cnt = std::min(b->chunk, n - i0);
-        int rc = batch_parse_chunk(b, in, in_len, i0, cnt);
+        int rc = batch_layout_chunk(b, in, in_len, i0, cnt);
+        if (!rc) rc = batch_upload_files(b, in, in_len, i0, cnt, b->st);
+        if (!rc) rc = batch_parse_chunk(b, in, in_len, i0, cnt);
         if (rc) return rc;
-        rc = batch_upload_chunk(b, in, in_len, i0, cnt, b->st);
+        rc = batch_upload_items(b, i0, cnt, b->st);
         if (rc) return rc;
     }
     LP_CUDA_OK(cudaStreamSynchronize(b->st));
@@ -447,24 +490,26 @@ extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const s
     batch_begin(b, n);
     const long launches0 = g_launches;
     // Chunk schedule: nothing can run before the first chunk's headers are parsed and its bytes have
-    // crossed PCIe, so the pipeline opens with HALF a chunk (one full wave of Huffman CTAs instead of
-    // two) and continues with full ones.
+    // crossed PCIe, so the pipeline opens with a SMALL chunk (one full wave of Huffman CTAs instead of
+    // three) and continues with full ones.
     std::vector<std::pair<int, int>> sched;
     {
         int i0 = 0;
-        if (n > b->chunk && b->chunk >= 2) {
-            sched.push_back({0, b->chunk / 2});
-            i0 = b->chunk / 2;
+        if (n > b->pipe_chunk && b->first_chunk >= 1 && b->first_chunk < b->pipe_chunk) {
+            sched.push_back({0, b->first_chunk});
+            i0 = b->first_chunk;
         }
-        for (; i0 < n; i0 += b->chunk) sched.push_back({i0, std::min(b->chunk, n - i0)});
+        for (; i0 < n; i0 += b->pipe_chunk) sched.push_back({i0, std::min(b->pipe_chunk, n - i0)});
     }
     const int nchunks = (int)sched.size();
     int finished = 0;
     for (int c = 0; c < nchunks; c++) {
         const int i0 = sched[c].first, cnt = sched[c].second;
-        int rc = batch_parse_chunk(b, in, in_len, i0, cnt);
-        if (rc) return rc;
-        rc = batch_upload_chunk(b, in, in_len, i0, cnt, b->st_h2d);
+        // the bytes start crossing PCIe first; the headers are parsed while they travel
+        int rc = batch_layout_chunk(b, in, in_len, i0, cnt);
+        if (!rc) rc = batch_upload_files(b, in, in_len, i0, cnt, b->st_h2d);
+        if (!rc) rc = batch_parse_chunk(b, in, in_len, i0, cnt);
+        if (!rc) rc = batch_upload_items(b, i0, cnt, b->st_h2d);
         if (rc) return rc;
         LP_CUDA_OK(cudaEventRecord(b->ev_h2d[c], b->st_h2d));
         LP_CUDA_OK(cudaStreamWaitEvent(b->st, b->ev_h2d[c], 0));

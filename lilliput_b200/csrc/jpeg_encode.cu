@@ -248,20 +248,44 @@ __global__ void __launch_bounds__(128)
     jpeg_fdct_quant_kernel(const uint8_t* frames, size_t img_stride, size_t row_stride, EncGeom g,
                            const EncConst* ec, int16_t* coef, int n) {
     __shared__ uint16_t sq[2][64];
+    __shared__ float sqr[2][64];  // 1 / (8 * Q)
     if (threadIdx.x < 64) {
         sq[0][threadIdx.x] = ec->q[0][threadIdx.x];
         sq[1][threadIdx.x] = ec->q[1][threadIdx.x];
+        sqr[0][threadIdx.x] = 1.0f / (float)((int)ec->q[0][threadIdx.x] << 3);
+        sqr[1][threadIdx.x] = 1.0f / (float)((int)ec->q[1][threadIdx.x] << 3);
     }
     __syncthreads();
-    const int blocks_per_img = g.mcus_x * g.mcus_y * g.blocks_per_mcu;
+    const int nmcu = g.mcus_x * g.mcus_y;
+    const int blocks_per_img = nmcu * g.blocks_per_mcu;
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long)blocks_per_img * n) return;
-    const int img = (int)(gid / blocks_per_img);
-    const int b = (int)(gid % blocks_per_img);
-    const int mcu = b / g.blocks_per_mcu, k = b % g.blocks_per_mcu;
+    // Role-major thread order: all luma blocks of the launch, then all Cb, then all Cr, so that a warp
+    // runs ONE of the two very different gather paths below instead of both (the coefficient layout
+    // [image][mcu][block] is unchanged).
+    int img, mcu, k;
+    if (g.blocks_per_mcu == 1) {
+        img = (int)(gid / nmcu);
+        mcu = (int)(gid % nmcu);
+        k = 0;
+    } else {
+        const long ny = (long)n * nmcu * 4;
+        if (gid < ny) {
+            img = (int)(gid / (nmcu * 4));
+            const int r = (int)(gid % (nmcu * 4));
+            mcu = r >> 2;
+            k = r & 3;
+        } else {
+            const long c = gid - ny;
+            k = c >= (long)n * nmcu ? 5 : 4;
+            const long cc = c % ((long)n * nmcu);
+            img = (int)(cc / nmcu);
+            mcu = (int)(cc % nmcu);
+        }
+    }
     const int mx = mcu % g.mcus_x, my = mcu / g.mcus_x;
     const uint8_t* f = frames + (size_t)img * img_stride;
-    int16_t* out = coef + (size_t)gid * 64;
+    int16_t* out = coef + (((size_t)img * nmcu + mcu) * g.blocks_per_mcu + k) * 64;
     int d[64];
     int qsel = 0;
     if (g.blocks_per_mcu == 1 || k < 4) {
@@ -331,8 +355,13 @@ __global__ void __launch_bounds__(128)
         const int q8 = (int)sq[qsel][i] << 3;
         const int c = d[i];
         int a = c < 0 ? -c : c;
-        a = (a + (q8 >> 1)) / q8;
-        d[i] = c < 0 ? -a : a;
+        a += q8 >> 1;
+        // exact a / q8 without the ~20-instruction integer divide: float estimate (a < 2^24 is exact in
+        // fp32) and a +-1 correction from the remainder
+        int qt = (int)((float)a * sqr[qsel][i]);
+        const int rem = a - qt * q8;
+        qt += rem >= q8 ? 1 : (rem < 0 ? -1 : 0);
+        d[i] = c < 0 ? -qt : qt;
     }
     // natural -> zig-zag with compile-time indices (keeps d[] in registers)
     constexpr int kZZ[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,

@@ -467,7 +467,7 @@ __device__ __forceinline__ uint32_t pack_px(int a, int b, int c, int d) {
 }
 
 __global__ void __launch_bounds__(128)
-    jpeg_idct_kernel(const JpegDecodeItem* items, const int16_t* coef, uint8_t* planes) {
+    jpeg_idct_kernel(const JpegDecodeItem* items, const int16_t* coef, uint8_t* planes, int mcu_order) {
     const JpegDecodeItem& it = items[blockIdx.y];
     if (it.status != 0) return;
     // the image's quantisation tables, once per CTA (read back 8 entries per load below)
@@ -481,7 +481,20 @@ __global__ void __launch_bounds__(128)
     if (blk >= nblk) return;
     const int rel = blk - (int)it.block_off[c];
     const int X = rel % it.bw[c], Y = rel / it.bw[c];
-    const uint4* src = reinterpret_cast<const uint4*>(coef + it.coef_off + (size_t)blk * 64);
+    // The serial and multi-scan entropy decoders store blocks per component in raster order (index =
+    // blk); the parallel decoder stores them in scan order (jpeg_huff_parallel.cu): block (X % h, Y % v)
+    // of component c inside ROI MCU (X / h, Y / v).
+    size_t sblk = (size_t)blk;
+    if (mcu_order) {
+        const int h = it.h[c], vv = it.v[c];
+        int nb = 0, kfirst = 0;
+        for (int k = 0; k < it.ncomp; k++) {
+            if (k < c) kfirst += it.h[k] * it.v[k];
+            nb += it.h[k] * it.v[k];
+        }
+        sblk = ((size_t)(Y / vv) * it.roi_mcx + X / h) * nb + kfirst + (Y % vv) * h + X % h;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(coef + it.coef_off + sblk * 64);
     const uint4* q4 = reinterpret_cast<const uint4*>(s_qt[c]);
     int v[64];
 #pragma unroll
@@ -681,7 +694,8 @@ int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev
     if (ev_after_huff) LP_CUDA_OK(cudaEventRecord(ev_after_huff, st));
     {
         dim3 grid(ceil_div(b.max_blocks_per_image, 128), b.n);
-        jpeg_idct_kernel<<<grid, 128, 0, st>>>(b.items, b.coef, b.planes);
+        const int mcu_order = !b.scans && b.use_parallel_huffman;
+        jpeg_idct_kernel<<<grid, 128, 0, st>>>(b.items, b.coef, b.planes, mcu_order);
         g_launches++;
         LP_CUDA_OK(cudaGetLastError());
     }

@@ -207,9 +207,6 @@ struct HuffShared {
     // compare + select instead of a table walk on every block boundary.
     uint32_t two_tables, n_first;
     uint32_t dcb_first, dcb_rest, acb_first, acb_rest;  // shared-memory byte addresses
-    // write pass: coefficient offset of block-in-MCU b of MCU (rx, ry) inside the region of interest =
-    // w_boff[b] + rx * w_hx[b] + ry * w_vrow[b]   (int16 elements from coef_off)
-    uint32_t w_boff[16], w_hx[16], w_vrow[16];
 };
 
 // MSB-first bit reader over the unstuffed string: 64-bit window, one 32-bit load per 32 bits used.
@@ -242,8 +239,8 @@ struct BitWin {
 // Decode symbols that START in [p, limit).  Returns the exit state and the number of coefficient
 // slots consumed.  WRITE: store coefficients (DC slot receives the DC *difference*) starting at
 // absolute slot `pos`.
-template <bool WRITE>
-__device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
+template <bool WRITE, bool TWO>
+__device__ __forceinline__ void decode_span_t(const HuffShared& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
                                             uint32_t& phase, uint32_t& nslots, int nb,
                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it,
                                             int16_t* coef, int16_t* dcdiff, int* status) {
@@ -253,43 +250,42 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
     int32_t bits_left = (int32_t)(limit - p);  // symbols that START before `limit` belong to this span
     BitWin bw;
     bw.init(s, p);
-    // WRITE: running block position
-    int16_t* dstblk = nullptr;
-    int16_t* dcp = nullptr;  // DC difference slot of the current block (all blocks, MCU order)
+    // WRITE: running block position.  Coefficients of the region of interest are stored in MCU (scan)
+    // order -- block b of ROI MCU (rx, ry) at ((ry * roi_mcx + rx) * nb + b) * 64 -- so closing a block
+    // is "advance by 64"; only an MCU change (one close in nb) looks at the ROI again.
+    int16_t* dstblk = nullptr;  // current block's coefficients; meaningful only while `inside`
+    bool inside = false;        // the current MCU lies in the region of interest
+    int16_t* dcp = nullptr;     // DC difference slot of the current block (all blocks, MCU order)
     int mx = 0, my = 0;
-    uint64_t remaining = 0;
-    int roi_mx0 = 0, roi_my0 = 0, roi_mcx = 0, roi_mcy = 0, mcus_x = 0;
+    uint32_t blocks_left = 0;
+    bool bad = false;
     int16_t* coef_base = nullptr;
-    auto set_dst = [&]() {   // nullptr when the block lies outside the region of interest
-        const int rmx = mx - roi_mx0, rmy = my - roi_my0;
-        const bool inside = (unsigned)rmx < (unsigned)roi_mcx && (unsigned)rmy < (unsigned)roi_mcy;
-        dstblk = inside ? coef_base + hs.w_boff[blk] + (uint32_t)rmx * hs.w_hx[blk] + (size_t)rmy * hs.w_vrow[blk]
-                        : nullptr;
+    const uint32_t zzb = (uint32_t)__cvta_generic_to_shared(&hs.zz[0]);
+    auto set_mcu = [&]() {  // first block of MCU (mx, my)
+        const int rmx = mx - it->roi_mx0, rmy = my - it->roi_my0, rcx = it->roi_mcx;
+        inside = (unsigned)rmx < (unsigned)rcx && (unsigned)rmy < (unsigned)it->roi_mcy;
+        dstblk = coef_base + ((size_t)rmy * rcx + rmx) * ((size_t)nb * 64);
     };
     if (WRITE) {
         if (pos >= total_slots) {
             nslots = 0;
             return;
         }
-        remaining = total_slots - pos + z_start;  // slots from the start of the current block
-        roi_mx0 = it->roi_mx0;
-        roi_my0 = it->roi_my0;
-        roi_mcx = it->roi_mcx;
-        roi_mcy = it->roi_mcy;
-        mcus_x = it->mcus_x;
+        blocks_left = (uint32_t)((total_slots - pos + z_start) >> 6);  // counted from the start of the current block
         coef_base = coef + it->coef_off;
         const uint32_t mcu = (uint32_t)((pos >> 6) / (uint32_t)nb);
-        mx = (int)(mcu % (uint32_t)mcus_x);
-        my = (int)(mcu / (uint32_t)mcus_x);
-        set_dst();
+        const uint32_t mcus_x = (uint32_t)it->mcus_x;
+        mx = (int)(mcu % mcus_x);
+        my = (int)(mcu / mcus_x);
+        set_mcu();
+        dstblk += blk * 64;
         dcp = dcdiff + (pos >> 6);
     }
     // shared-memory byte addresses of the current block's lookahead tables
-    const bool two = hs.two_tables != 0;  // uniform across the CTA
     const uint32_t n_first = hs.n_first, dcbF = hs.dcb_first, dcbR = hs.dcb_rest, acbF = hs.acb_first, acbR = hs.acb_rest;
     uint32_t dcb, acb;
     auto set_tables = [&]() {
-        if (two) {
+        if (TWO) {
             dcb = blk < n_first ? dcbF : dcbR;
             acb = blk < n_first ? acbF : acbR;
         } else {
@@ -335,15 +331,17 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
         const uint32_t adv = ez ? (r == 15 ? 16u : 64u) : r + 1;
         const uint32_t zt = z + adv;
         const int used = len + (ez ? 0 : (int)sz);
-        if (WRITE && !ez) {
-            if (zt <= 64) {
-                const uint32_t raw = sz ? ((top << len) >> (32 - sz)) : 0u;
-                const int val = sz ? ((int)raw < (1 << (sz - 1)) ? (int)raw - (1 << sz) + 1 : (int)raw) : 0;
-                if (isdc) *dcp = (int16_t)val;                            // DC difference: every block
-                else if (dstblk) dstblk[hs.zz[zt - 1]] = (int16_t)val;   // AC: only inside the ROI
-            } else {
-                *status = -3;  // coefficient index past 63: corrupt data
-            }
+        if (WRITE) {
+            // value, destination and store without a branch: lanes sit in unrelated symbols
+            const uint32_t t2 = top << len;
+            const uint32_t raw = __funnelshift_l(t2, 0u, sz);  // next sz bits (0 when sz == 0)
+            const int val = (int)raw + ((int)t2 >= 0 ? (int)((0xFFFFFFFFu << sz) + 1u) : 0);  // T.81 F.2.2.1 EXTEND
+            uint32_t zi;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(zi) : "r"(zzb + ((zt - 1u) & 63u)));
+            int16_t* const where = isdc ? dcp : dstblk + zi;  // DC difference: every block; AC: inside the ROI
+            const bool inblk = zt <= 64;
+            bad |= !ez && !inblk;  // coefficient index past 63: corrupt data
+            if (!ez && inblk && (isdc || inside)) *where = (int16_t)val;
         }
         bw.skip(used);
         bits_left -= used;
@@ -359,22 +357,37 @@ __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t*
         } else if (fin) {
             closed++;
             blk++;
+            dstblk += 64;
             if (blk == (uint32_t)nb) {
                 blk = 0;
-                if (++mx == mcus_x) {
+                if (++mx == it->mcus_x) {
                     mx = 0;
                     my++;
                 }
+                set_mcu();
             }
             set_tables();
-            if ((uint64_t)closed * 64 >= remaining) break;  // every MCU produced: the rest is padding
+            if (--blocks_left == 0) break;  // every MCU produced: the rest is padding
             dcp++;
-            set_dst();
         }
     }
+    if (WRITE && bad) *status = -3;
     p = limit - (uint32_t)bits_left;  // bits_left <= 0 here unless the stream ended early
     phase = (blk << 6) | z;
     nslots = closed * 64 + z - z_start;
+}
+
+// Two copies of the symbol loop: the usual two-table-pair layout selects its lookahead tables with a
+// compare, anything else looks them up per block.  hs.two_tables is uniform across the CTA.
+template <bool WRITE>
+__device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
+                                            uint32_t& phase, uint32_t& nslots, int nb,
+                                            uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it,
+                                            int16_t* coef, int16_t* dcdiff, int* status) {
+    if (hs.two_tables)
+        decode_span_t<WRITE, true>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status);
+    else
+        decode_span_t<WRITE, false>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status);
 }
 
 // 3 CTAs/SM (40 registers) measured faster than 4 at 32 registers (spills in the write pass) or 2 at 62
@@ -410,9 +423,6 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
                     hs.blk_comp[k] = (uint8_t)c;
                     hs.blk_bx[k] = (uint8_t)(j % it.h[c]);
                     hs.blk_by[k] = (uint8_t)(j / it.h[c]);
-                    hs.w_boff[k] = (it.block_off[c] + (uint32_t)(j / it.h[c]) * it.bw[c] + (uint32_t)(j % it.h[c])) * 64u;
-                    hs.w_hx[k] = (uint32_t)it.h[c] * 64u;
-                    hs.w_vrow[k] = (uint32_t)it.v[c] * it.bw[c] * 64u;
                 }
             const int nfirst = it.h[0] * it.v[0];
             bool two = true;
@@ -571,11 +581,9 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
             if (j < nblk) {
                 const int mx = (int)(mcu % (uint32_t)it.mcus_x) - it.roi_mx0;
                 const int my = (int)(mcu / (uint32_t)it.mcus_x) - it.roi_my0;
-                if ((unsigned)mx < (unsigned)it.roi_mcx && (unsigned)my < (unsigned)it.roi_mcy) {
-                    const int rx = mx * it.h[c] + (int)(kk % it.h[c]), ry = my * it.v[c] + (int)(kk / it.h[c]);
-                    coef[it.coef_off + ((size_t)it.block_off[c] + (size_t)ry * it.bw[c] + rx) * 64] =
+                if ((unsigned)mx < (unsigned)it.roi_mcx && (unsigned)my < (unsigned)it.roi_mcy)
+                    coef[it.coef_off + (((size_t)my * it.roi_mcx + mx) * nb + koff + kk) * 64] =
                         (int16_t)(int)(s_carry + ex + (uint32_t)d);
-                }
             }
             __syncthreads();
             if (tid == 0) s_carry += total;

@@ -522,19 +522,18 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
         nxt_list = t;
         first_round = false;
     }
-    if (tid == 0) {
-        s_carry = 0;
-        it.pad_ = rounds;  // diagnostics: synchronisation rounds this image needed
-    }
-    __syncthreads();
+    if (tid == 0) it.pad_ = rounds;  // diagnostics: synchronisation rounds this image needed
     SubState* cur = st;
-    // ---- prefix sum of slot counts, then the writing decode
+    // ---- prefix sum of slot counts, then the writing decode.  Every thread learns each tile's total
+    //      from the scan, so the running offset lives in a register (no shared carry, no extra barriers).
+    uint64_t slots_before = 0;
     for (uint32_t base = 0; base < nsub; base += kHuffThreads) {
         const uint32_t i = base + tid;
         const uint32_t v = i < nsub ? ns[i] : 0;
         uint32_t total;
         const uint32_t ex = block_excl_scan<kHuffThreads>(v, &total, warp_sums);
-        const uint64_t pos = (uint64_t)s_carry + ex;
+        const uint64_t pos = slots_before + ex;
+        slots_before += total;
         if (i < nsub) {
             uint32_t p = i == 0 ? 0u : cur[i - 1].p;
             uint32_t phase = i == 0 ? 0u : cur[i - 1].phase;
@@ -549,47 +548,65 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
                 decode_span<true>(hs, s, p, limit, phase, n, nb, pos, total_slots, &it, coef, dcdiff, &status);
             if (status) s_status = status;
         }
-        __syncthreads();
-        if (tid == 0) s_carry += total;
-        __syncthreads();
     }
-    if (tid == 0) {
-        if ((uint64_t)s_carry < total_slots) s_status = -3;  // the stream ended before the last MCU
-        if (s_status) it.status = s_status;
-    }
+    if (tid == 0 && slots_before < total_slots) s_status = -3;  // the stream ended before the last MCU
     __syncthreads();
-    if (s_status) return;
+    if (s_status) {
+        if (tid == 0) it.status = s_status;
+        return;
+    }
     // ---- 3. DC differences -> DC values: per component, prefix sum over ALL blocks in MCU (scan)
-    //         order; only blocks inside the region of interest are stored
+    //         order; only blocks inside the region of interest are stored.  kDcRun consecutive blocks
+    //         per thread and tile: their loads are in flight together and one block scan serves them all.
+    constexpr int kDcRun = 8;
+    const uint32_t mcus_x = (uint32_t)it.mcus_x;
+    const int roi_mx0 = it.roi_mx0, roi_my0 = it.roi_my0, roi_mcx = it.roi_mcx, roi_mcy = it.roi_mcy;
     int koff = 0;
     for (int c = 0; c < it.ncomp; c++) {
-        const int bpc = it.h[c] * it.v[c];
-        const uint32_t nblk = (uint32_t)it.mcus_x * it.mcus_y * bpc;
-        if (tid == 0) s_carry = 0;
-        __syncthreads();
-        for (uint32_t base = 0; base < nblk; base += kHuffThreads) {
-            const uint32_t j = base + tid;
-            int d = 0;
-            uint32_t mcu = 0, kk = 0;
-            if (j < nblk) {
-                mcu = j / bpc;
-                kk = j % bpc;
-                d = dcdiff[(size_t)mcu * nb + koff + kk];
+        const uint32_t bpc = (uint32_t)(it.h[c] * it.v[c]);
+        const uint32_t nblk = mcus_x * (uint32_t)it.mcus_y * bpc;
+        const int16_t* dsrc = dcdiff + koff;
+        int16_t* cdst = coef + it.coef_off + (size_t)koff * 64;
+        uint32_t dc_before = 0;  // signed prefix sum through unsigned wrap-around arithmetic
+        for (uint32_t base = 0; base < nblk; base += kHuffThreads * kDcRun) {
+            const uint32_t j0 = base + (uint32_t)tid * kDcRun;
+            const uint32_t mcu0 = j0 / bpc, kk0 = j0 % bpc;
+            int d[kDcRun];
+            uint32_t sum = 0;
+            {
+                uint32_t mcu = mcu0, kk = kk0;
+#pragma unroll
+                for (int r = 0; r < kDcRun; r++) {
+                    d[r] = j0 + r < nblk ? dsrc[(size_t)mcu * nb + kk] : 0;
+                    sum += (uint32_t)d[r];
+                    if (++kk == bpc) {
+                        kk = 0;
+                        mcu++;
+                    }
+                }
             }
-            uint32_t total;  // signed prefix sum through unsigned wrap-around arithmetic
-            const uint32_t ex = block_excl_scan<kHuffThreads>((uint32_t)d, &total, warp_sums);
-            if (j < nblk) {
-                const int mx = (int)(mcu % (uint32_t)it.mcus_x) - it.roi_mx0;
-                const int my = (int)(mcu / (uint32_t)it.mcus_x) - it.roi_my0;
-                if ((unsigned)mx < (unsigned)it.roi_mcx && (unsigned)my < (unsigned)it.roi_mcy)
-                    coef[it.coef_off + (((size_t)my * it.roi_mcx + mx) * nb + koff + kk) * 64] =
-                        (int16_t)(int)(s_carry + ex + (uint32_t)d);
+            uint32_t total;
+            const uint32_t ex = block_excl_scan<kHuffThreads>(sum, &total, warp_sums);
+            uint32_t run = dc_before + ex;
+            dc_before += total;
+            uint32_t mcu = mcu0, kk = kk0;
+            int mx = (int)(mcu0 % mcus_x) - roi_mx0, my = (int)(mcu0 / mcus_x) - roi_my0;
+#pragma unroll
+            for (int r = 0; r < kDcRun; r++) {
+                run += (uint32_t)d[r];
+                if (j0 + r < nblk && (unsigned)mx < (unsigned)roi_mcx && (unsigned)my < (unsigned)roi_mcy)
+                    cdst[(((size_t)my * roi_mcx + mx) * nb + kk) * 64] = (int16_t)(int)run;
+                if (++kk == bpc) {
+                    kk = 0;
+                    mcu++;
+                    if (++mx == (int)mcus_x - roi_mx0) {
+                        mx = -roi_mx0;
+                        my++;
+                    }
+                }
             }
-            __syncthreads();
-            if (tid == 0) s_carry += total;
-            __syncthreads();
         }
-        koff += bpc;
+        koff += (int)bpc;
     }
 }
 

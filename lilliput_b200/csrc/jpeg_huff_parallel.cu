@@ -189,13 +189,14 @@ struct alignas(8) SubState {
     uint32_t phase;  // (block-in-MCU << 6) | zig-zag index expected at p
 };
 
-constexpr int kDcBits = 9, kAcBits = 12;  // a longer code in ANY lane sends the whole warp through the slow walk
+constexpr int kDcBits = 9, kAcBits = kHuffAcLookBits;  // a longer code in ANY lane sends the whole warp through the slow walk
 
 // Per-CTA decode tables.  DC tables are indexed by the next 9 bits, AC tables by the next 11
 // (longer codes -- well under 0.1 % of symbols with the Annex-K tables -- take the canonical walk).
 struct HuffShared {
     uint16_t dc_look[4][1 << kDcBits];  // (len << 8) | symbol, 0 = longer code
-    uint16_t ac_look[4][1 << kAcBits];
+    uint16_t ac_look[4][1 << kAcBits];  // bit 15 set: AC code longer than kAcBits -> ac_sub[entry & 0x7FFF]
+    uint16_t ac_sub[4 * kHuffLongPrefixes][16];  // next 4 bits -> (len << 8) | symbol, 0 = not a codeword
     int32_t maxcode[8][18];
     int32_t valoffset[8][17];
     uint8_t vals[8][256];
@@ -302,18 +303,24 @@ __device__ __forceinline__ void decode_span_t(const HuffShared& hs, const uint8_
         const uint32_t top = (uint32_t)(bw.acc >> 32);
         const bool isdc = z == 0;
         const uint32_t idx = isdc ? (top >> (32 - kDcBits)) : (top >> (32 - kAcBits));
-        uint32_t e;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"((isdc ? dcb : acb) + idx * 2u));
-        int len = (int)(e >> 8), sym = (int)(e & 0xFF);
-        if (__builtin_expect(e == 0, 0)) {  // longer than the lookahead: canonical walk (rare)
-            const int t = isdc ? hs.blk_dc[blk] : 4 + hs.blk_ac[blk];
-            len = (isdc ? kDcBits : kAcBits) + 1;
-            int code = (int)(top >> (32 - len));
-            while (len <= 16 && code > hs.maxcode[t][len]) {
-                len++;
-                code = (int)(top >> (32 - len));
+        int e;
+        asm volatile("ld.shared.s16 %0, [%1];" : "=r"(e) : "r"((isdc ? dcb : acb) + idx * 2u));
+        if (__builtin_expect(e <= 0, 0)) {  // longer than the lookahead (rare)
+            if (e < 0) {
+                // AC code of 13..16 bits: its prefix has a second-level table indexed by the next 4 bits
+                e = hs.ac_sub[e & 0x7FFF][(top >> (32 - kAcBits - 4)) & 15u];
+            } else {
+                // canonical walk: DC codes past the lookahead, AC prefixes without a second-level table
+                const int t = isdc ? hs.blk_dc[blk] : 4 + hs.blk_ac[blk];
+                int len = (isdc ? kDcBits : kAcBits) + 1;
+                int code = (int)(top >> (32 - len));
+                while (len <= 16 && code > hs.maxcode[t][len]) {
+                    len++;
+                    code = (int)(top >> (32 - len));
+                }
+                if (len <= 16) e = (len << 8) | hs.vals[t][(code + hs.valoffset[t][len]) & 0xFF];
             }
-            if (len > 16) {  // not a codeword: a wrong guess, or a corrupt stream
+            if (e == 0) {  // not a codeword: a wrong guess, or a corrupt stream
                 if (WRITE) {
                     *status = -3;
                     break;
@@ -322,8 +329,8 @@ __device__ __forceinline__ void decode_span_t(const HuffShared& hs, const uint8_
                 bits_left -= 1;
                 continue;
             }
-            sym = hs.vals[t][(code + hs.valoffset[t][len]) & 0xFF];
         }
+        const int len = e >> 8, sym = e & 0xFF;
         const uint32_t r = (uint32_t)sym >> 4, sz = (uint32_t)sym & 15;
         const bool ez = (sz == 0) && !isdc;  // EOB or ZRL (DC symbols have r == 0 and are values)
         // slots this symbol advances: value r+1, ZRL 16, EOB "to the end"; reaching or passing 64
@@ -460,6 +467,13 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
             }
             hs.ac_look[t][idx] = e;
         }
+        for (int i = tid; i < 4 * kHuffLongPrefixes * 16; i += kHuffThreads)
+            (&hs.ac_sub[0][0])[i] = (&g->long_sub[0][0][0])[i];
+    }
+    __syncthreads();
+    if (tid < 4 * kHuffLongPrefixes) {
+        const uint32_t pfx = (tables + it.table_set)->long_prefix[tid / kHuffLongPrefixes][tid % kHuffLongPrefixes];
+        if (pfx != 0xFFFFu) hs.ac_look[tid / kHuffLongPrefixes][pfx] = (uint16_t)(0x8000u | (uint32_t)tid);
     }
     __syncthreads();
     int nb = 0;

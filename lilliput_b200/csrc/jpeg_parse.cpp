@@ -258,6 +258,7 @@ int jpeg_parse_scans(const uint8_t* in, size_t len, const JpegHeader& h0, JpegSc
 // Canonical Huffman decode tables (T.81 Annex C / F.2.2.3) in the device layout.
 void jpeg_build_huff_set(const JpegHeader& h, JpegHuffSet* out) {
     memset(out, 0, sizeof(*out));
+    memset(out->long_prefix, 0xFF, sizeof(out->long_prefix));
     for (int tc = 0; tc < 2; tc++)
         for (int th = 0; th < 4; th++) {
             int t = tc * 4 + th;
@@ -275,6 +276,20 @@ void jpeg_build_huff_set(const JpegHeader& h, JpegHuffSet* out) {
                         unsigned first = code << (9 - len), cnt = 1u << (9 - len);
                         for (unsigned j = 0; j < cnt && first + j < 512; j++)
                             out->look[t][first + j] = (uint16_t)((len << 8) | h.huff_vals[tc][th][k]);
+                    }
+                    if (tc == 1 && len > kHuffAcLookBits) {
+                        const unsigned prefix = code >> (len - kHuffAcLookBits);
+                        int j = 0;
+                        while (j < kHuffLongPrefixes && out->long_prefix[th][j] != prefix &&
+                               out->long_prefix[th][j] != 0xFFFF)
+                            j++;
+                        if (j < kHuffLongPrefixes) {
+                            out->long_prefix[th][j] = (uint16_t)prefix;
+                            const unsigned rest = code & ((1u << (len - kHuffAcLookBits)) - 1);
+                            const unsigned first = rest << (16 - len), cnt = 1u << (16 - len);
+                            for (unsigned q = 0; q < cnt; q++)
+                                out->long_sub[th][j][first + q] = (uint16_t)((len << 8) | h.huff_vals[tc][th][k]);
+                        }
                     }
                     code++;
                 }

@@ -102,12 +102,20 @@ uint32_t jpeg_item_set_window(JpegDecodeItem* it, int x0, int y0, int x1, int y1
                               uint32_t* plane_bytes);
 
 // Huffman decode tables for one image (or many images sharing them), device format.
+constexpr int kHuffAcLookBits = 12;    // AC lookahead of the parallel decoder (jpeg_huff_parallel.cu)
+constexpr int kHuffLongPrefixes = 16;  // second-level tables per AC table for codes longer than that
 struct JpegHuffSet {
     // [class*4+id]: 9-bit lookahead: (len<<8)|symbol, 0 when the code is longer than 9 bits
     uint16_t look[8][512];
     int32_t maxcode[8][18];  // canonical decode for long codes; maxcode[17] = sentinel
     int32_t valoffset[8][17];
     uint8_t vals[8][256];
+    // AC codes longer than kHuffAcLookBits, two-level: long_prefix[id][j] = their first kHuffAcLookBits
+    // bits (0xFFFF = unused slot), long_sub[id][j][next 4 bits] = (len<<8)|symbol, 0 = not a codeword.
+    // Canonical codes put every long code behind a handful of all-ones prefixes (8 for the Annex K
+    // tables); prefixes that do not fit here are left to the bit-by-bit walk.
+    uint16_t long_prefix[4][kHuffLongPrefixes];
+    uint16_t long_sub[4][kHuffLongPrefixes][16];
 };
 void jpeg_build_huff_set(const JpegHeader& h, JpegHuffSet* out);
 // Walks every SOS of a multi-scan file, snapshotting the Huffman tables / restart interval in force.

@@ -210,31 +210,32 @@ struct HuffShared {
     uint32_t dcb_first, dcb_rest, acb_first, acb_rest;  // shared-memory byte addresses
 };
 
-// MSB-first bit reader over the unstuffed string: 64-bit window, one 32-bit load per 32 bits used.
+// MSB-first bit reader over the unstuffed string: the two 32-bit words the next symbol can touch
+// (a code is at most 16 bits, its value bits at most 15) plus a bit offset, so a peek is one funnel
+// shift and a skip one add; a third word is always in flight (its load is issued ~32 bits early).
 struct BitWin {
     const uint32_t* w;  // word after `nextw`
-    uint64_t acc;       // next bit at bit 63
-    uint32_t nextw;     // prefetched: its load is issued ~32 bits before it is needed
-    int avail;
+    uint32_t w0, w1;    // big-endian words; the next bit is bit (31 - bo) of w0
+    uint32_t nextw;     // prefetched, still little-endian
+    uint32_t bo;        // 0..31 after refill()
     __device__ __forceinline__ void init(const uint8_t* s, uint32_t p) {
         const uint32_t* base = reinterpret_cast<const uint32_t*>(s) + (p >> 5);
-        const uint64_t hi = __byte_perm(base[0], 0, 0x0123), lo = __byte_perm(base[1], 0, 0x0123);
-        acc = ((hi << 32) | lo) << (p & 31);
-        avail = 64 - (int)(p & 31);
+        w0 = __byte_perm(base[0], 0, 0x0123);
+        w1 = __byte_perm(base[1], 0, 0x0123);
         nextw = base[2];
         w = base + 3;
+        bo = p & 31;
     }
     __device__ __forceinline__ void refill() {
-        if (avail < 32) {
-            acc |= (uint64_t)__byte_perm(nextw, 0, 0x0123) << (32 - avail);
-            avail += 32;
+        if (bo >= 32) {
+            w0 = w1;
+            w1 = __byte_perm(nextw, 0, 0x0123);
             nextw = *w++;
+            bo -= 32;
         }
     }
-    __device__ __forceinline__ void skip(int n) {
-        acc <<= n;
-        avail -= n;
-    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(w1, w0, bo); }  // next 32 bits
+    __device__ __forceinline__ void skip(int n) { bo += n; }  // n <= 31 between refills
 };
 
 // Decode symbols that START in [p, limit).  Returns the exit state and the number of coefficient
@@ -300,7 +301,7 @@ __device__ __forceinline__ void decode_span_t(const HuffShared& hs, const uint8_
     // not counted per symbol: slots = 64 * blocks closed + z_end - z_start.
     while (bits_left > 0) {
         bw.refill();
-        const uint32_t top = (uint32_t)(bw.acc >> 32);
+        const uint32_t top = bw.peek();
         const bool isdc = z == 0;
         const uint32_t idx = isdc ? (top >> (32 - kDcBits)) : (top >> (32 - kAcBits));
         int e;

@@ -32,6 +32,7 @@ CV_8UC1, CV_8UC3, CV_8UC4 = 0, 16, 24
 INTER_LINEAR, INTER_CUBIC, INTER_AREA = 1, 2, 3
 
 LP_OK, LP_ERR_INVALID_IMAGE, LP_ERR_DECODING_FAILED, LP_ERR_BUF_TOO_SMALL = 0, -1, -2, -3
+LP_ERR_FRAMEBUF_NO_PIXELS, LP_ERR_SKIP_NOT_SUPPORTED, LP_ERR_ENCODE_TIMEOUT, LP_ERR_EOF = -4, -5, -6, -7
 
 LP_ERRORS = {
     0: "ok", -1: "ErrInvalidImage", -2: "ErrDecodingFailed", -3: "ErrBufTooSmall",

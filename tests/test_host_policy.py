@@ -1,0 +1,159 @@
+"""The host policy layer (lilliput_b200/host/lilliput_host.cpp = ImageOps.Transform and its helpers,
+ref ops.go:352-444) checked rule by rule.  The same C++ is linked twice: over the reference's own shims
+(oracle/_ref, runs on the CPU -- the variant that runs in the build container) and over the CUDA library
+(`-m gpu`).  Expectations are the reference's rules as written in ops.go, cited per test.
+"""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from lilliput_b200 import abi
+
+PIL_Image = pytest.importorskip("PIL.Image")
+
+
+@pytest.fixture(params=["reference_shims", pytest.param("cuda", marks=pytest.mark.gpu)])
+def lib(request):
+    if request.param == "cuda":
+        return request.getfixturevalue("cuda_lib")
+    return request.getfixturevalue("ref_lib")
+
+
+def _gif(n=5, w=48, h=36, duration_ms=70, loop=0):
+    rng = np.random.default_rng(5)
+    frames = []
+    for k in range(n):
+        a = np.full((h, w, 3), 30 + 40 * k, np.uint8)
+        a[4 + 3 * k:14 + 3 * k, 6 + 5 * k:20 + 5 * k] = rng.integers(0, 256, 3, dtype=np.uint8)
+        frames.append(PIL_Image.fromarray(a).quantize(32))
+    bio = io.BytesIO()
+    frames[0].save(bio, "GIF", save_all=True, append_images=frames[1:], duration=duration_ms, loop=loop, optimize=False)
+    return bio.getvalue()
+
+
+def _opts(**kw):
+    kw.setdefault("EncodeTimeout_ns", 600 * 10**9)
+    return abi.ImageOptions(**kw)
+
+
+def _dims(lib, data):
+    w, h, _, _ = lib.header(data)
+    return w, h
+
+
+# ---- calculateExpectedSize (ref ops.go:243-255), through Fit on a still image (ref ops.go:170-206)
+
+@pytest.mark.parametrize("req,exp", [
+    ((256, 256), (256, 256)),    # ordinary request
+    ((400, 400), (297, 297)),    # square request larger than min(src): min x min
+    ((1000, 900), (800, 297)),   # both larger, not square: source size
+    ((1000, 200), (1000, 200)),  # only one larger: the request stands (Fit then crops to the request's aspect)
+    ((300, 200), (300, 200)),
+])
+def test_expected_size_rules(lib, golden, req, exp):
+    data = golden["c1_input"].tobytes()  # 800 x 297
+    out = lib.transform(data, _opts(FileType=".jpeg", Width=req[0], Height=req[1], ResizeMethod=abi.ImageOpsFit,
+                                    EncodeOptions={abi.JpegQuality: 85}))
+    assert _dims(lib, out) == exp
+
+
+def test_noresize_still_skips_fit(lib, golden, oracle):
+    """ImageOpsNoResize on a non-animated source encodes the decoded frame as it is (ref ops.go:450-452)."""
+    data = golden["c1_input"].tobytes()
+    out = lib.transform(data, _opts(FileType=".png", ResizeMethod=abi.ImageOpsNoResize, Width=10, Height=10))
+    assert np.array_equal(oracle.png_decode(out), oracle.jpeg_decode(data)[0])
+
+
+def test_resize_stretches_to_the_request(lib, golden, oracle):
+    """ImageOpsResize ignores the aspect ratio and calculateExpectedSize (ref ops.go:208-236)."""
+    data = golden["c1_input"].tobytes()
+    out = lib.transform(data, _opts(FileType=".png", Width=1000, Height=50, ResizeMethod=abi.ImageOpsResize))
+    src = oracle.jpeg_decode(data)[0]
+    assert np.array_equal(oracle.png_decode(out), oracle.resize(src, 1000, 50))
+
+
+def test_orientation_is_applied_with_or_without_normalize(lib, golden, oracle):
+    """normalizeOrientation runs on every iteration (ref ops.go:392); the flag only tells inputCanvasSize that
+    the axes were swapped (ref ops.go:474-479) -- for a still Fit the pixels are the same either way."""
+    data = golden["c6_input"].tobytes()
+    src, orientation = oracle.jpeg_decode(data)
+    assert orientation not in (0, 1)
+    turned = oracle.orient(src, orientation)
+    for flag in (False, True):
+        out = lib.transform(data, _opts(FileType=".png", ResizeMethod=abi.ImageOpsNoResize, NormalizeOrientation=flag))
+        assert np.array_equal(oracle.png_decode(out), turned), flag
+
+
+# ---- animated sources: frame caps, single-frame output, timeouts (ref ops.go:384-390, 423-437)
+
+def test_animated_gif_to_gif_keeps_every_frame(lib):
+    out = lib.transform(_gif(5), _opts(FileType=".gif", Width=24, Height=18, ResizeMethod=abi.ImageOpsFit))
+    info = lib.gif_info(out)
+    assert (info["width"], info["height"], info["frame_count"]) == (24, 18, 5)
+
+
+def test_disable_animated_output_encodes_one_frame(lib):
+    """DisableAnimatedOutput: one frame, then the encoder is flushed (ref ops.go:423-425)."""
+    out = lib.transform(_gif(5), _opts(FileType=".gif", Width=24, Height=18, ResizeMethod=abi.ImageOpsFit,
+                                       DisableAnimatedOutput=True))
+    assert lib.gif_info(out)["frame_count"] == 1
+
+
+@pytest.mark.parametrize("cap", [1, 2, 4])
+def test_max_encode_frames_skips_the_rest(lib, cap):
+    """MaxEncodeFrames: after `cap` frames the decoder is skipped to EOF and the encoder flushed (ref ops.go:427-433)."""
+    out = lib.transform(_gif(5), _opts(FileType=".gif", Width=24, Height=18, ResizeMethod=abi.ImageOpsFit,
+                                       MaxEncodeFrames=cap))
+    assert lib.gif_info(out)["frame_count"] == cap
+
+
+def test_max_encode_duration_stops_before_the_frame_that_exceeds_it(lib):
+    """The running duration is checked BEFORE a frame is transformed (ref ops.go:384-390): 5 frames of 70 ms and a
+    200 ms cap keep the frames whose cumulative duration is <= 200 ms, i.e. two."""
+    out = lib.transform(_gif(5, duration_ms=70), _opts(FileType=".gif", Width=24, Height=18,
+                                                       ResizeMethod=abi.ImageOpsFit,
+                                                       MaxEncodeDuration_ns=200 * 10**6))
+    assert lib.gif_info(out)["frame_count"] == 2
+
+
+def test_frame_cap_on_a_decoder_that_cannot_skip(lib):
+    """WebP sources cannot SkipFrame: a frame cap that bites fails with ErrSkipNotSupported (ref ops.go:336-349,
+    webp.go SkipFrame)."""
+    webp = np.load(os.path.join(os.path.dirname(__file__), "golden", "webp_golden.npz"))["webp_anim_lossy"].tobytes()
+    with pytest.raises(abi.LilliputError) as e:
+        lib.transform(webp, _opts(FileType=".webp", Width=16, Height=16, ResizeMethod=abi.ImageOpsFit,
+                                  MaxEncodeFrames=1, EncodeOptions={abi.WebpQuality: 80}))
+    assert e.value.code == abi.LP_ERR_SKIP_NOT_SUPPORTED
+
+
+def test_zero_encode_timeout_fails_after_the_first_frame_of_an_animation(lib):
+    """encodeTimeoutTime = now + 0: a multi-frame encode returns ErrEncodeTimeout after its first frame
+    (ref ops.go:368,435-437); a still image never reaches that check (content is returned first)."""
+    with pytest.raises(abi.LilliputError) as e:
+        lib.transform(_gif(3), abi.ImageOptions(FileType=".gif", Width=24, Height=18, ResizeMethod=abi.ImageOpsFit))
+    assert e.value.code == abi.LP_ERR_ENCODE_TIMEOUT
+
+
+def test_zero_encode_timeout_is_harmless_for_a_still(lib, golden):
+    out = lib.transform(golden["c1_input"].tobytes(),
+                        abi.ImageOptions(FileType=".jpeg", Width=64, Height=64, ResizeMethod=abi.ImageOpsFit,
+                                         EncodeOptions={abi.JpegQuality: 85}))
+    assert _dims(lib, out) == (64, 64)
+
+
+# ---- errors (ref lilliput.go:19-27)
+
+def test_garbage_is_an_invalid_image(lib):
+    with pytest.raises(abi.LilliputError) as e:
+        lib.transform(b"\x00" * 64, _opts(FileType=".jpeg", Width=8, Height=8, ResizeMethod=abi.ImageOpsFit))
+    assert e.value.code == abi.LP_ERR_INVALID_IMAGE
+
+
+def test_small_destination_is_buf_too_small(lib, golden):
+    with pytest.raises(abi.LilliputError) as e:
+        lib.transform(golden["c1_input"].tobytes(),
+                      _opts(FileType=".jpeg", Width=256, Height=256, ResizeMethod=abi.ImageOpsFit,
+                            EncodeOptions={abi.JpegQuality: 85}), dst_cap=512)
+    assert e.value.code == abi.LP_ERR_BUF_TOO_SMALL

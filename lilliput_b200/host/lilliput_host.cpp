@@ -563,14 +563,19 @@ class WebpEncoder : public Encoder {  // ref webp.go:20-26, 178-261
         }
         const uint32_t bg = decodedBy ? decodedBy->BackgroundColor() : 0xFFFFFFFFu;
         const int loops = decodedBy ? decodedBy->LoopCount() : 0;
-        webp_encoder e = webp_encoder_create(dst, cap, icc.empty() ? nullptr : icc.data(), icc.size(), bg, loops);
-        if (!e) return LP_ERR_BUF_TOO_SMALL;
-        auto* self = new WebpEncoder;
-        self->encoder = e;
-        out->reset(self);
+        // the encoder borrows the profile until flush (ref webp.cpp:397-398 keeps the pointer, webp.go keeps the
+        // slice alive in the encoder struct): it lives in this object, not on Create's stack
+        std::unique_ptr<WebpEncoder> self(new WebpEncoder);
+        self->icc = std::move(icc);
+        self->encoder = webp_encoder_create(dst, cap, self->icc.empty() ? nullptr : self->icc.data(), self->icc.size(),
+                                            bg, loops);
+        if (!self->encoder) return LP_ERR_BUF_TOO_SMALL;
+        out->reset(self.release());
         return LP_OK;
     }
-    ~WebpEncoder() override { webp_encoder_release(encoder); }
+    ~WebpEncoder() override {
+        if (encoder) webp_encoder_release(encoder);
+    }
     Error Encode(Framebuffer* f, const std::map<int, int>& opt, bool* content, size_t* out_len) override {
         *content = false;
         if (hasFlushed) return LP_ERR_EOF;
@@ -597,6 +602,7 @@ class WebpEncoder : public Encoder {  // ref webp.go:20-26, 178-261
 
   private:
     webp_encoder encoder = nullptr;
+    std::vector<uint8_t> icc;  // borrowed by `encoder`
     int frameIndex = 0;
     bool hasFlushed = false;
 };
@@ -947,7 +953,8 @@ static int lp_encode_host_impl(const char* ext, const uint8_t* pixels, int w, in
     Error e = wrapPixels(a, pixels, w, h, type);
     if (e) return e;
     std::unique_ptr<Encoder> enc;
-    if ((e = NewEncoder(ext, nullptr, dst, dst_cap, &enc))) return e;
+    e = NewEncoder(ext, nullptr, dst, dst_cap, &enc);
+    if (e) return e;
     std::map<int, int> o;
     for (size_t i = 0; i + 1 < opt_len; i += 2) o[opt[i]] = opt[i + 1];
     bool content = false;

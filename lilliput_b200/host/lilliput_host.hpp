@@ -36,8 +36,10 @@ namespace lilliput {
 using Error = int;
 
 // ref opencv.go:20-60 (DisposeMethod / BlendMethod)
-enum DisposeMethod { NoDispose = 0, DisposeToBackgroundColor = 1 };
-enum BlendMethod { UseAlphaBlending = 0, NoBlend = 1 };
+// fixed underlying type: the Go types are plain ints and decoders store other codes in them (GIF's
+// "restore previous" is 2, ref giflib.go:218), which an unfixed two-value enum may not hold
+enum DisposeMethod : int { NoDispose = 0, DisposeToBackgroundColor = 1 };
+enum BlendMethod : int { UseAlphaBlending = 0, NoBlend = 1 };
 
 struct PixelType {
     int v = 0;

@@ -277,7 +277,9 @@ void jpeg_build_huff_set(const JpegHeader& h, JpegHuffSet* out) {
                         for (unsigned j = 0; j < cnt && first + j < 512; j++)
                             out->look[t][first + j] = (uint16_t)((len << 8) | h.huff_vals[tc][th][k]);
                     }
-                    if (tc == 1 && len > kHuffAcLookBits) {
+                    // (code >> len) != 0: an over-subscribed table from a hostile DHT -- not a codeword, and its
+                    // "prefix" would index outside the lookahead table on the device
+                    if (tc == 1 && len > kHuffAcLookBits && (code >> len) == 0) {
                         const unsigned prefix = code >> (len - kHuffAcLookBits);
                         int j = 0;
                         while (j < kHuffLongPrefixes && out->long_prefix[th][j] != prefix &&

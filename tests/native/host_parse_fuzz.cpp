@@ -79,6 +79,9 @@ static void exercise(std::vector<uint8_t>& d) {
             static lp::JpegHuffSet hs;
             lp::jpeg_build_huff_set(h, &hs);
             g_sink += hs.look[0][0] + hs.long_prefix[0][0];
+            for (int t = 0; t < 4; t++)  // the device indexes its lookahead table with these
+                for (int j = 0; j < lp::kHuffLongPrefixes; j++)
+                    if (hs.long_prefix[t][j] != 0xFFFF && hs.long_prefix[t][j] >= (1u << lp::kHuffAcLookBits)) abort();
             if (h.multiscan) {
                 static std::vector<lp::JpegScanDesc> scans(256);
                 static std::vector<lp::JpegHuffSet> sets(64);
@@ -89,6 +92,14 @@ static void exercise(std::vector<uint8_t>& d) {
                     for (int k = 0; k < nscans; k++) {  // every segment must lie inside the file
                         if ((size_t)scans[k].data_off + scans[k].data_len > d.size()) abort();
                         if (scans[k].table_set < 0 || scans[k].table_set >= nsets) abort();
+                        // everything the multi-scan kernel indexes with
+                        const lp::JpegScanDesc& sc = scans[k];
+                        if (sc.ns < 1 || sc.ns > 3 || sc.Ss < 0 || sc.Ss > sc.Se || sc.Se > 63 || sc.Al < 0 || sc.Al > 13 ||
+                            sc.Ah < 0 || sc.Ah > 15)
+                            abort();
+                        for (int q = 0; q < sc.ns; q++)
+                            if (sc.ci[q] < 0 || sc.ci[q] >= h.ncomp || sc.td[q] < 0 || sc.td[q] > 3 || sc.ta[q] < 0 || sc.ta[q] > 3)
+                                abort();
                     }
                 }
             } else if (h.scan_offset + h.scan_length > d.size()) {
@@ -104,7 +115,23 @@ static void exercise(std::vector<uint8_t>& d) {
                 g_sink += lp::jpeg_item_set_window(&it, 0, 0, h.width, h.height, false, &plane_bytes);
         }
         lp::PngHeader ph;
-        if (lp::png_parse(d.data(), d.size(), &ph) == 0) g_png++;
+        if (lp::png_parse(d.data(), d.size(), &ph) == 0) {
+            g_png++;
+            // what the PNG kernels take on trust
+            const bool depth_ok = ph.bit_depth == 1 || ph.bit_depth == 2 || ph.bit_depth == 4 || ph.bit_depth == 8 || ph.bit_depth == 16;
+            const bool type_ok = ph.color_type == 0 || ph.color_type == 2 || ph.color_type == 3 || ph.color_type == 4 || ph.color_type == 6;
+            if (ph.width < 1 || ph.height < 1 || !depth_ok || !type_ok || ph.npal < 0 || ph.npal > 256 || ph.ntrns < 0 ||
+                ph.ntrns > 256 || ph.src_channels < 1 || ph.src_channels > 4 || ph.out_channels < 1 || ph.out_channels > 4 ||
+                ph.bpp < 1 || ph.bpp > 8)
+                abort();
+            if (ph.row_bytes != ((size_t)ph.width * ph.src_channels * ph.bit_depth + 7) / 8) abort();
+            size_t total = 0;
+            for (const auto& sgm : ph.idat) {
+                if (sgm.offset > d.size() || sgm.length > d.size() - sgm.offset) abort();
+                total += sgm.length;
+            }
+            if (total != ph.idat_total) abort();
+        }
     }
     {
         std::vector<uint8_t> grown(d.size() + 64);

@@ -474,7 +474,8 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     __syncthreads();
     if (tid < 4 * kHuffLongPrefixes) {
         const uint32_t pfx = (tables + it.table_set)->long_prefix[tid / kHuffLongPrefixes][tid % kHuffLongPrefixes];
-        if (pfx != 0xFFFFu) hs.ac_look[tid / kHuffLongPrefixes][pfx] = (uint16_t)(0x8000u | (uint32_t)tid);
+        // (0xFFFF = unused slot; the builder never emits a prefix of more than kAcBits bits)
+        if (pfx < (1u << kAcBits)) hs.ac_look[tid / kHuffLongPrefixes][pfx] = (uint16_t)(0x8000u | (uint32_t)tid);
     }
     __syncthreads();
     int nb = 0;

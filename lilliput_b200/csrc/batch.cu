@@ -340,6 +340,14 @@ static int batch_upload_items(lp_batch* b, int i0, int cnt, cudaStream_t st) {
 
 // Every kernel of the path for images [i0, i0+cnt) on stream st; ev = 6 timing events or null.
 static int batch_launch_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st, cudaEvent_t* ev) {
+    if (!b->layout_known) {
+        // no image up to and including this chunk had a usable header (every item carries its parse error):
+        // there is no geometry to launch with and nothing to decode
+        if (ev)
+            for (int k = 0; k < 6; k++) LP_CUDA_OK(cudaEventRecord(ev[k], st));
+        LP_CUDA_OK(cudaMemsetAsync(b->d_out_len + i0, 0, (size_t)cnt * sizeof(uint32_t), st));
+        return LP_OK;
+    }
     if (ev) LP_CUDA_OK(cudaEventRecord(ev[0], st));
     JpegDecodeBatch d;
     d.items = b->d_items + i0;

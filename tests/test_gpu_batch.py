@@ -68,6 +68,25 @@ def test_batch_per_item_errors(cuda_lib, oracle):
         b.close()
 
 
+def test_batch_where_no_image_is_usable(cuda_lib, oracle):
+    """Every header is refused: there is no geometry to launch with (this used to divide by zero on the host --
+    found by tests/native/host_batch_fake_gpu.cpp).  The context must stay usable."""
+    w, h = 160, 120
+    wrong_size = oracle.jpeg_encode(synth_image(5, 96, 64, 3), 90)
+    files = [b"\xff\xd8\xff garbage", wrong_size, b"\x00", b"GIF89a not a jpeg"]
+    b = abi.Batch(cuda_lib, 0, 8, w, h, 32, 32, 85, max_in_bytes=1 << 20)
+    try:
+        outs, status = b.transform(files)
+        assert all(s != 0 for s in status) and all(o == b"" for o in outs)
+        good = _corpus(oracle, 2, w, h)
+        outs, status = b.transform(good)
+        assert status == [0, 0]
+        dec, _ = oracle.jpeg_decode(good[1])
+        assert outs[1] == oracle.jpeg_encode(oracle.fit(dec, 32, 32), 85)
+    finally:
+        b.close()
+
+
 def test_empty_batch(cuda_lib):
     b = abi.Batch(cuda_lib, 0, 4, 64, 64, 8, 8, 85, max_in_bytes=4096)
     try:

@@ -125,18 +125,27 @@ static int ensure_dev(Mat* m) {
 static int fresh_dev(Mat* m, int cols, int rows, int type) {
     int rc = ensure_device();
     if (rc) return rc;
+    if (cols < 0 || rows < 0) return LP_ERR_BAD_ARGUMENT;
+    Mat shape;
+    shape.type = type;
+    const size_t row = (size_t)cols * shape.elem();
+    if (!m->dev || m->is_view || m->dev->bytes < row * rows) {
+        auto fresh = dev_alloc(row * rows);
+        if (!fresh) return LP_ERR_CUDA;  // `m` keeps its old geometry and contents
+        m->dev = fresh;
+    }
     m->cols = cols;
     m->rows = rows;
     m->type = type;
-    const size_t row = (size_t)cols * m->elem();
     m->step = row;
-    if (!m->dev || m->is_view || m->dev->bytes < row * rows) {
-        m->dev = dev_alloc(row * rows);
-        if (!m->dev) return LP_ERR_CUDA;
-    }
     m->dev_off = 0;
     m->dev_step = row;
     m->is_view = false;
+    // From here on the device buffer is the one that matches the geometry (the caller is about to fill it; if that
+    // fails its contents are undefined, as a failed cv:: call leaves them).  The host memory may be smaller than
+    // the new geometry, so it must never be uploaded from again until lp_mat_sync_host has rewritten it.
+    m->dev_valid = true;
+    m->host_valid = false;
     return LP_OK;
 }
 
@@ -391,6 +400,7 @@ int opencv_type_convert_depth(int t, int depth) { return (depth & 7) | (t & ~7);
 
 // ---- mats (ref opencv.cpp:22-81, 196-241) ---------------------------------------------------
 opencv_mat opencv_mat_create(int width, int height, int type) {
+    if (width < 0 || height < 0) return nullptr;  // (the reference's cv::Mat would throw; nothing throws across this ABI)
     Mat* m = new Mat;
     m->cols = width;
     m->rows = height;
@@ -398,7 +408,7 @@ opencv_mat opencv_mat_create(int width, int height, int type) {
     m->step = (size_t)width * m->elem();
     try {
         m->owned_host.resize(m->step * height);
-    } catch (const std::bad_alloc&) {  // no exception crosses the C ABI: an impossible size is a NULL mat
+    } catch (const std::exception&) {  // no exception crosses the C ABI: an impossible size is a NULL mat
         delete m;
         return nullptr;
     }
@@ -410,6 +420,7 @@ opencv_mat opencv_mat_create(int width, int height, int type) {
 
 opencv_mat opencv_mat_create_from_data(int width, int height, int type, void* data,
                                        size_t data_len) {
+    if (width < 0 || height < 0) return nullptr;
     Mat tmp;
     tmp.type = type;
     size_t total = (size_t)width * height * tmp.elem();
@@ -440,6 +451,7 @@ opencv_mat opencv_mat_create_empty_from_data(int length, void* data) {
 
 bool opencv_mat_set_row_stride(opencv_mat mat, size_t stride) {
     Mat* m = static_cast<Mat*>(mat);
+    if (!m) return false;
     if (m->step == stride) return true;
     size_t width_stride = (size_t)m->cols * m->elem();
     if (stride < width_stride || m->step != width_stride) return false;
@@ -451,9 +463,9 @@ bool opencv_mat_set_row_stride(opencv_mat mat, size_t stride) {
 
 void opencv_mat_release(opencv_mat mat) { delete static_cast<Mat*>(mat); }
 
-int opencv_mat_get_width(const opencv_mat mat) { return static_cast<const Mat*>(mat)->cols; }
-int opencv_mat_get_height(const opencv_mat mat) { return static_cast<const Mat*>(mat)->rows; }
-void* opencv_mat_get_data(const opencv_mat mat) { return static_cast<const Mat*>(mat)->host; }
+int opencv_mat_get_width(const opencv_mat mat) { return mat ? static_cast<const Mat*>(mat)->cols : 0; }
+int opencv_mat_get_height(const opencv_mat mat) { return mat ? static_cast<const Mat*>(mat)->rows : 0; }
+void* opencv_mat_get_data(const opencv_mat mat) { return mat ? static_cast<const Mat*>(mat)->host : nullptr; }
 
 int lp_mat_sync_host(opencv_mat mat) {
     Mat* m = static_cast<Mat*>(mat);
@@ -488,6 +500,11 @@ void opencv_mat_resize(const opencv_mat src, opencv_mat dst, int width, int heig
                        int interpolation) {
     Mat* s = static_cast<Mat*>(src);
     Mat* d = static_cast<Mat*>(dst);
+    if (!s || !d || width < 1 || height < 1 || s->cols < 1 || s->rows < 1) return;  // (cv::resize asserts on these)
+    if (interpolation != CV_INTER_LINEAR && interpolation != CV_INTER_AREA) {
+        fprintf(stderr, "[lilliput_b200] opencv_mat_resize: interpolation %d is not supported\n", interpolation);
+        return;  // nothing touched: `dst` keeps its geometry and contents
+    }
     if (ensure_dev(s)) return;
     if (fresh_dev(d, width, height, s->type)) return;
     ResizeArgs a;
@@ -507,17 +524,27 @@ void opencv_mat_resize(const opencv_mat src, opencv_mat dst, int width, int heig
     a.n = 1;
     a.interpolation = interpolation;
     int rc = resize_launch(a, thread_stream());
+    // also on failure: `d` already has the new geometry and a device buffer of that size, while its host
+    // memory may be smaller -- the (undefined) device contents are the ones that count from here on
+    d->dev_valid = true;
+    d->host_valid = false;
     if (rc) {
         fprintf(stderr, "[lilliput_b200] opencv_mat_resize failed (%d)\n", rc);
         return;
     }
     sync_stream();
-    d->dev_valid = true;
-    d->host_valid = false;
 }
 
 opencv_mat opencv_mat_crop(const opencv_mat src, int x, int y, int width, int height) {
     Mat* s = static_cast<Mat*>(src);
+    if (!s) return nullptr;
+    // cv::Mat(m, Rect) throws on a rectangle that leaves the matrix (ref opencv.cpp:211-215 does not catch it); here
+    // such a view would make every later kernel read outside the allocation, so it is refused
+    if (x < 0 || y < 0 || width < 0 || height < 0 || (long long)x + width > s->cols || (long long)y + height > s->rows) {
+        fprintf(stderr, "[lilliput_b200] opencv_mat_crop: (%d,%d %dx%d) is not inside %dx%d\n", x, y, width, height,
+                s->cols, s->rows);
+        return nullptr;
+    }
     if (ensure_dev(s)) return nullptr;
     Mat* v = new Mat;
     v->cols = width;
@@ -538,7 +565,7 @@ opencv_mat opencv_mat_crop(const opencv_mat src, int x, int y, int width, int he
 void opencv_mat_orientation_transform(CVImageOrientation orientation, opencv_mat mat) {
     Mat* m = static_cast<Mat*>(mat);
     const int o = (int)orientation;
-    if (o <= 1 || o > 8) return;  // TL: nothing to do
+    if (!m || o <= 1 || o > 8) return;  // TL: nothing to do
     if (ensure_dev(m)) return;
     const bool swap = o >= 5;
     const int W = swap ? m->rows : m->cols, H = swap ? m->cols : m->rows;
@@ -590,7 +617,7 @@ void opencv_mat_set_color(opencv_mat mat, int red, int green, int blue, int alph
 int opencv_mat_clear_to_transparent(opencv_mat mat, int xOffset, int yOffset, int width, int height) {
     Mat* m = static_cast<Mat*>(mat);
     if (!m) return OPENCV_ERROR_NULL_MATRIX;
-    if (xOffset < 0 || yOffset < 0 || xOffset + width > m->cols || yOffset + height > m->rows)
+    if (xOffset < 0 || yOffset < 0 || (long long)xOffset + width > m->cols || (long long)yOffset + height > m->rows)
         return OPENCV_ERROR_OUT_OF_BOUNDS;
     if (width <= 0 || height <= 0) return OPENCV_ERROR_INVALID_DIMENSIONS;
     if (m->channels() != 3 && m->channels() != 4) return OPENCV_ERROR_INVALID_CHANNEL_COUNT;
@@ -609,7 +636,7 @@ static int copy_region_common(opencv_mat src, opencv_mat dst, int xOffset, int y
     Mat* d = static_cast<Mat*>(dst);
     if (!s || !d || s->rows == 0 || s->cols == 0 || d->rows == 0 || d->cols == 0)
         return OPENCV_ERROR_NULL_MATRIX;
-    if (xOffset < 0 || yOffset < 0 || xOffset + width > d->cols || yOffset + height > d->rows)
+    if (xOffset < 0 || yOffset < 0 || (long long)xOffset + width > d->cols || (long long)yOffset + height > d->rows)
         return OPENCV_ERROR_OUT_OF_BOUNDS;
     if (width <= 0 || height <= 0) return OPENCV_ERROR_INVALID_DIMENSIONS;
     const int sc = s->channels(), dc = d->channels();

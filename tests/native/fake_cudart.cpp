@@ -56,7 +56,18 @@ cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
-    *v = a == cudaDevAttrMultiProcessorCount ? 148 : 0;
+    switch (a) {  // (cub sizes its launch loops with these: a 0 would make them spin)
+        case cudaDevAttrMultiProcessorCount: *v = 148; break;
+        case cudaDevAttrMaxGridDimX: *v = 2147483647; break;
+        case cudaDevAttrMaxGridDimY: case cudaDevAttrMaxGridDimZ: *v = 65535; break;
+        case cudaDevAttrMaxThreadsPerBlock: *v = 1024; break;
+        case cudaDevAttrMaxSharedMemoryPerBlock: *v = 48 * 1024; break;
+        case cudaDevAttrMaxSharedMemoryPerBlockOptin: *v = 227 * 1024; break;
+        case cudaDevAttrWarpSize: *v = 32; break;
+        case cudaDevAttrComputeCapabilityMajor: *v = 10; break;
+        case cudaDevAttrComputeCapabilityMinor: *v = 0; break;
+        default: *v = 1; break;
+    }
     return cudaSuccess;
 }
 cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) { *n = 3; return cudaSuccess; }

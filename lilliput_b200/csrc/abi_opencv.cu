@@ -848,7 +848,7 @@ bool opencv_encoder_write(opencv_encoder e, const opencv_mat src, const int* opt
     bool ok = jpeg_encode_launch(b, st, nullptr) == LP_OK;
     uint32_t n = 0;
     if (ok) ok = cudaMemcpyAsync(&n, b.out_len, 4, cudaMemcpyDeviceToHost, st) == cudaSuccess && !sync_stream();
-    if (ok && n == 0) ok = false;
+    if (ok && (n == 0 || (size_t)n > cap)) ok = false;  // (n > cap cannot come from the kernel; never read past the buffer)
     if (ok) {
         Mat* d = enc->dst;
         if ((size_t)n > d->host_cap) {

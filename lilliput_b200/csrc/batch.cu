@@ -416,7 +416,8 @@ static void batch_finish_chunk(lp_batch* b, int i0, int cnt, uint8_t* const* out
     for (int i = i0; i < i0 + cnt; i++) {
         int st = b->parse_status[i];
         if (!st && b->h_items_back[i].status != 0) st = LP_ERR_DECODING_FAILED;
-        if (!st && b->h_out_len[i] == 0) st = LP_ERR_BUF_TOO_SMALL;
+        // (a length above the slot size cannot come from the encoder kernel; it must never reach the memcpy below)
+        if (!st && (b->h_out_len[i] == 0 || b->h_out_len[i] > cap)) st = LP_ERR_BUF_TOO_SMALL;
         if (status) status[i] = st;
         out_len[i] = 0;
         if (st) continue;

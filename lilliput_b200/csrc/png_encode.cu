@@ -306,7 +306,7 @@ int png_encode_frame(const uint8_t* frame, size_t row_stride, int W, int H, int 
     LP_CUDA_OK(cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, st));
     LP_CUDA_OK(cudaMemcpyAsync(adl.data(), d_adler, (size_t)nchunks * 8, cudaMemcpyDeviceToHost, st));
     LP_CUDA_OK(cudaStreamSynchronize(st));
-    if (total == 0) {
+    if (total == 0 || total > z_cap) {  // (total > z_cap cannot come from the pack kernel; never read past d_z)
         cudaFreeAsync(buf, st);
         return LP_ERR_CUDA;
     }

@@ -138,6 +138,10 @@ static int vp8l_encode_dev(const uint8_t* d_frame, size_t step, int width, int h
         }
         const unsigned long long total_bits = base_bit + last_off + last_len;
         const size_t total_bytes = (size_t)((total_bits + 7) / 8);
+        if (total_bits < base_bit || total_bytes > npix * 8 + (1u << 20)) {  // no code is longer than 15 bits: a nonsensical device answer
+            rc = LP_ERR_CUDA;
+            break;
+        }
         const size_t words = total_bytes / 4 + 4;
         if (cudaMallocAsync(&d_out, words * 4, st) != cudaSuccess) {
             rc = LP_ERR_CUDA;
@@ -246,7 +250,7 @@ static int vp8_encode_dev(const uint8_t* d_frame, size_t step, int width, int he
     if (cudaMemcpyAsync(&n, j.out_len, sizeof(n), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess)
         rc = LP_ERR_CUDA;
-    if (!rc && n == 0) rc = LP_ERR_INVALID_IMAGE;
+    if (!rc && (n == 0 || n > j.out_cap)) rc = LP_ERR_INVALID_IMAGE;  // (n > out_cap cannot come from the kernel)
     if (!rc) {
         out->resize(n);
         if (cudaMemcpy(out->data(), j.out, n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = LP_ERR_CUDA;

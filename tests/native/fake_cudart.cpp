@@ -40,8 +40,25 @@ cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 
-cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
+// LP_FAKE_CHAOS=1: small device -> host reads (status words, lengths, counters) come back as random bytes: the host
+// must not turn a nonsensical device answer into an out-of-bounds access of its own.
+static void copy(void* d, const void* s, size_t n, cudaMemcpyKind k) {
+    static const bool chaos = getenv("LP_FAKE_CHAOS") != nullptr;
+    if (!n) return;
+    if (chaos && k == cudaMemcpyDeviceToHost && n <= 64 && (rand() & 3) == 0) {
+        for (size_t i = 0; i < n; i++) ((uint8_t*)d)[i] = (uint8_t)rand();
+        return;
+    }
+    memmove(d, s, n);
+    if (chaos && k == cudaMemcpyDeviceToHost && n <= (64u << 10) && (rand() & 3) == 0)  // arrays of lengths / states
+        for (size_t i = 0; i + 4 <= n; i += 4)
+            if (rand() % 10 == 0) {
+                const uint32_t v = (uint32_t)rand() * 2654435761u;
+                memcpy((uint8_t*)d + i, &v, 4);
+            }
+}
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind k) { copy(d, s, n, k); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t) { copy(d, s, n, k); return cudaSuccess; }
 cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
     for (size_t y = 0; y < h; y++) memmove((char*)d + y * dp, (const char*)s + y * sp, w);
     return cudaSuccess;

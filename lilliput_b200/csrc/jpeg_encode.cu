@@ -163,25 +163,40 @@ static void build_enc_const(int W, int H, bool gray, int quality, EncConst* c) {
 static std::mutex g_enc_mu;
 static std::map<std::tuple<int, int, int, int, int>, EncConst*> g_enc_consts;  // (dev,W,H,gray,q)
 
-static int get_enc_const(int W, int H, bool gray, int quality, EncConst** dev, int* header_len) {
+// Cached per (device, size, gray, quality) up to a bound; past it (a service encoding to arbitrary sizes would
+// otherwise grow the cache by sizeof(EncConst) per new key for as long as it lives) the constants are built per call
+// and live in stream order around the two launches that read them (*transient: the caller frees them on `st`).
+static int get_enc_const(int W, int H, bool gray, int quality, cudaStream_t st, EncConst** dev, int* header_len,
+                         bool* transient) {
+    static const size_t cap = getenv("LP_JPEG_ENC_CONST_CAP") ? (size_t)atol(getenv("LP_JPEG_ENC_CONST_CAP")) : 4096;
+    *transient = false;
     int d = 0;
     LP_CUDA_OK(cudaGetDevice(&d));
     std::lock_guard<std::mutex> lk(g_enc_mu);
     auto key = std::make_tuple(d, W, H, (int)gray, quality);
     auto it = g_enc_consts.find(key);
     static std::map<std::tuple<int, int, int, int, int>, int> lens;
-    if (it == g_enc_consts.end()) {
-        EncConst h;
-        build_enc_const(W, H, gray, quality, &h);
-        EncConst* p = nullptr;
+    if (it != g_enc_consts.end()) {
+        *dev = it->second;
+        *header_len = lens[key];
+        return LP_OK;
+    }
+    EncConst h;
+    build_enc_const(W, H, gray, quality, &h);
+    EncConst* p = nullptr;
+    *header_len = h.header_len;
+    if (g_enc_consts.size() < cap) {
         LP_CUDA_OK(cudaMalloc(&p, sizeof(EncConst)));
         LP_CUDA_OK(cudaMemcpy(p, &h, sizeof(EncConst), cudaMemcpyHostToDevice));
         g_enc_consts[key] = p;
         lens[key] = h.header_len;
-        it = g_enc_consts.find(key);
+    } else {
+        LP_CUDA_OK(cudaMallocAsync(&p, sizeof(EncConst), st));
+        // (pageable source: cudaMemcpyAsync has read it by the time it returns)
+        LP_CUDA_OK(cudaMemcpyAsync(p, &h, sizeof(EncConst), cudaMemcpyHostToDevice, st));
+        *transient = true;
     }
-    *dev = it->second;
-    *header_len = lens[key];
+    *dev = p;
     return LP_OK;
 }
 
@@ -650,8 +665,17 @@ int jpeg_encode_launch(const JpegEncodeBatch& b, cudaStream_t st, cudaEvent_t ev
     EncGeom g = make_geom(b.width, b.height, b.channels);
     EncConst* ec = nullptr;
     int header_len = 0;
-    int rc = get_enc_const(b.width, b.height, b.channels == 1, b.quality, &ec, &header_len);
+    bool ec_transient = false;
+    int rc = get_enc_const(b.width, b.height, b.channels == 1, b.quality, st, &ec, &header_len, &ec_transient);
     if (rc) return rc;
+    struct Release {  // constants that are not in the cache go back in stream order, i.e. after the launches below
+        EncConst* p;
+        bool on;
+        cudaStream_t st;
+        ~Release() {
+            if (on) cudaFreeAsync(p, st);
+        }
+    } release{ec, ec_transient, st};
     const size_t nmcu = (size_t)g.mcus_x * g.mcus_y;
     const size_t coef_bytes = round_up(nmcu * g.blocks_per_mcu * 64 * sizeof(int16_t), (size_t)256);
     const size_t bits_bytes = round_up(nmcu * sizeof(uint32_t), (size_t)256);

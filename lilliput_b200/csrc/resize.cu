@@ -80,7 +80,7 @@ struct AreaTabDev {
 };
 
 static std::mutex g_tab_mu;
-static std::map<std::tuple<int, int, int, int>, AreaTabDev> g_tabs;  // (device, ssize, dsize, padt)
+static std::map<std::tuple<int, int, int>, AreaTabDev> g_tabs;  // (device, ssize, dsize)
 
 static int pad_taps(int maxt) {
     const int opts[] = {2, 3, 4, 6, 8, 12, 16};
@@ -89,25 +89,44 @@ static int pad_taps(int maxt) {
     return maxt;
 }
 
-// Device-resident tap table, cached per (device, ssize, dsize).
-static int get_area_tab(int ssize, int dsize, AreaTabDev* out) {
+// The cache is bounded: a service that resizes to arbitrary sizes would otherwise grow it (a few KB of HBM per
+// (source, destination) size pair) for as long as it lives.  Past the bound a table is built per call, allocated
+// and freed in stream order around the launch that uses it.
+static size_t tab_cache_cap() {
+    static const size_t cap = getenv("LP_RESIZE_TAB_CAP") ? (size_t)atol(getenv("LP_RESIZE_TAB_CAP")) : 4096;
+    return cap;
+}
+
+static void free_area_tab(const AreaTabDev& d, cudaStream_t st) {
+    cudaFreeAsync(d.first, st);
+    cudaFreeAsync(d.count, st);
+    cudaFreeAsync(d.perm, st);
+    cudaFreeAsync(d.w, st);
+}
+
+// Device-resident tap table for (ssize -> dsize), cached per device.  *transient = the table is not in the cache
+// (it is full): the caller hands it to free_area_tab on `st` after the launch that reads it.
+static int get_area_tab(int ssize, int dsize, cudaStream_t st, AreaTabDev* out, bool* transient) {
+    *transient = false;
     int dev = 0;
     LP_CUDA_OK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_tab_mu);
-    AreaTabHost h = make_area_tab(ssize, dsize);
-    int padt = pad_taps(h.maxt);
-    auto key = std::make_tuple(dev, ssize, dsize, padt);
-    auto it = g_tabs.find(key);
-    if (it != g_tabs.end()) {
-        *out = it->second;
-        return LP_OK;
+    const auto key = std::make_tuple(dev, ssize, dsize);
+    {
+        std::lock_guard<std::mutex> lk(g_tab_mu);
+        auto it = g_tabs.find(key);
+        if (it != g_tabs.end()) {
+            *out = it->second;
+            return LP_OK;
+        }
     }
+    // miss: the table is built outside the lock (pure host work)
+    AreaTabHost h = make_area_tab(ssize, dsize);
     AreaTabDev d;
     d.maxt = h.maxt;
-    d.padt = padt;
-    std::vector<float> w((size_t)dsize * padt, 0.f);
+    d.padt = pad_taps(h.maxt);
+    std::vector<float> w((size_t)dsize * d.padt, 0.f);
     for (int i = 0; i < dsize; i++)
-        memcpy(&w[(size_t)i * padt], &h.w[(size_t)i * h.maxt], sizeof(float) * h.maxt);
+        memcpy(&w[(size_t)i * d.padt], &h.w[(size_t)i * h.maxt], sizeof(float) * h.maxt);
     // Within each 256-pixel tile, order destination pixels by tap count so that whole warps share a
     // chain length and the shorter ones skip the zero-weight tail tap.
     std::vector<int> perm(dsize);
@@ -117,17 +136,41 @@ static int get_area_tab(int ssize, int dsize, AreaTabDev* out) {
         std::stable_sort(perm.begin() + x0, perm.begin() + x1,
                          [&](int a, int b) { return h.count[a] < h.count[b]; });
     }
-    LP_CUDA_OK(cudaMalloc(&d.first, sizeof(int) * dsize));
-    LP_CUDA_OK(cudaMalloc(&d.count, sizeof(int) * dsize));
-    LP_CUDA_OK(cudaMalloc(&d.perm, sizeof(int) * dsize));
-    LP_CUDA_OK(cudaMemcpy(d.perm, perm.data(), sizeof(int) * dsize, cudaMemcpyHostToDevice));
-    LP_CUDA_OK(cudaMalloc(&d.w, sizeof(float) * w.size()));
-    LP_CUDA_OK(cudaMemcpy(d.first, h.first.data(), sizeof(int) * dsize, cudaMemcpyHostToDevice));
-    LP_CUDA_OK(cudaMemcpy(d.count, h.count.data(), sizeof(int) * dsize, cudaMemcpyHostToDevice));
-    LP_CUDA_OK(cudaMemcpy(d.w, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
     d.h_first = h.first;
     d.h_count = h.count;
-    g_tabs[key] = d;
+    const size_t ib = sizeof(int) * (size_t)dsize, wb = sizeof(float) * w.size();
+    {
+        std::lock_guard<std::mutex> lk(g_tab_mu);
+        auto it = g_tabs.find(key);  // another thread may have built it meanwhile
+        if (it != g_tabs.end()) {
+            *out = it->second;
+            return LP_OK;
+        }
+        if (g_tabs.size() < tab_cache_cap()) {
+            LP_CUDA_OK(cudaMalloc(&d.first, ib));
+            LP_CUDA_OK(cudaMalloc(&d.count, ib));
+            LP_CUDA_OK(cudaMalloc(&d.perm, ib));
+            LP_CUDA_OK(cudaMalloc(&d.w, wb));
+            LP_CUDA_OK(cudaMemcpy(d.first, h.first.data(), ib, cudaMemcpyHostToDevice));
+            LP_CUDA_OK(cudaMemcpy(d.count, h.count.data(), ib, cudaMemcpyHostToDevice));
+            LP_CUDA_OK(cudaMemcpy(d.perm, perm.data(), ib, cudaMemcpyHostToDevice));
+            LP_CUDA_OK(cudaMemcpy(d.w, w.data(), wb, cudaMemcpyHostToDevice));
+            g_tabs[key] = d;
+            *out = d;
+            return LP_OK;
+        }
+    }
+    // cache full: stream-ordered, one launch long.  (The sources are pageable host memory: cudaMemcpyAsync has
+    // read them by the time it returns.)
+    LP_CUDA_OK(cudaMallocAsync(&d.first, ib, st));
+    LP_CUDA_OK(cudaMallocAsync(&d.count, ib, st));
+    LP_CUDA_OK(cudaMallocAsync(&d.perm, ib, st));
+    LP_CUDA_OK(cudaMallocAsync(&d.w, wb, st));
+    LP_CUDA_OK(cudaMemcpyAsync(d.first, h.first.data(), ib, cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaMemcpyAsync(d.count, h.count.data(), ib, cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaMemcpyAsync(d.perm, perm.data(), ib, cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaMemcpyAsync(d.w, w.data(), wb, cudaMemcpyHostToDevice, st));
+    *transient = true;
     *out = d;
     return LP_OK;
 }
@@ -607,10 +650,23 @@ int resize_launch(const ResizeArgs& a, cudaStream_t st) {
             return LP_OK;
         }
         AreaTabDev tx, ty;
-        int rc = get_area_tab(a.crop_w, a.dst_w, &tx);
+        bool tx_tmp = false, ty_tmp = false;
+        int rc = get_area_tab(a.crop_w, a.dst_w, st, &tx, &tx_tmp);
         if (rc) return rc;
-        rc = get_area_tab(a.crop_h, a.dst_h, &ty);
-        if (rc) return rc;
+        rc = get_area_tab(a.crop_h, a.dst_h, st, &ty, &ty_tmp);
+        if (rc) {
+            if (tx_tmp) free_area_tab(tx, st);
+            return rc;
+        }
+        struct Release {  // tables that are not in the cache go back in stream order, i.e. after the launch below
+            const AreaTabDev &x, &y;
+            bool fx, fy;
+            cudaStream_t st;
+            ~Release() {
+                if (fx) free_area_tab(x, st);
+                if (fy) free_area_tab(y, st);
+            }
+        } release{tx, ty, tx_tmp, ty_tmp, st};
         AreaParams p;
         p.src = a.src; p.src_img_stride = a.src_img_stride; p.src_row_stride = a.src_row_stride;
         p.dst = a.dst; p.dst_img_stride = a.dst_img_stride; p.dst_row_stride = a.dst_row_stride;

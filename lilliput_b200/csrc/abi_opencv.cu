@@ -475,7 +475,7 @@ int lp_mat_sync_host(opencv_mat mat) {
     if (row * m->rows > m->host_cap) {  // e.g. after an axis-swapping orientation into a small buffer
         try {
             m->owned_host.resize(row * m->rows);
-        } catch (const std::bad_alloc&) {
+        } catch (const std::exception&) {
             return LP_ERR_BUF_TOO_SMALL;
         }
         m->host = m->owned_host.data();

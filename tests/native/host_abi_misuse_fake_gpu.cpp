@@ -34,6 +34,17 @@ int main(int argc, char** argv) {
         std::vector<uint8_t> store;  // backing memory of a create_from_data mat
     };
     std::vector<Slot> pool(8);
+    std::vector<std::vector<uint8_t>> files;  // optional seed files (argv[3..]): sources for the decoder ops
+    for (int i = 3; i < argc; i++) {
+        FILE* f = fopen(argv[i], "rb");
+        if (!f) continue;
+        std::vector<uint8_t> v;
+        uint8_t buf[4096];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof buf, f)) > 0) v.insert(v.end(), buf, buf + n);
+        fclose(f);
+        if (v.size() >= 16) files.push_back(std::move(v));
+    }
     auto dim = [&]() -> int {
         switch (rng() % 10) {
             case 0: return 0;
@@ -49,7 +60,7 @@ int main(int argc, char** argv) {
         Slot& a = pool[rng() % pool.size()];
         Slot& b = pool[rng() % pool.size()];
         alarm(120);
-        const unsigned op = rng() % 16;
+        const unsigned op = rng() % (files.empty() ? 16 : 19);
         if (getenv("LP_TRACE")) fprintf(stderr, "op %u a=%d b=%d\n", op, (int)(&a - pool.data()), (int)(&b - pool.data()));
         switch (op) {
             case 0: {  // (re)create owning
@@ -121,6 +132,38 @@ int main(int argc, char** argv) {
             }
             case 14: sink += (unsigned)opencv_type_depth((int)(rng() % 64)) + (unsigned)opencv_type_channels((int)(rng() % 64)) +
                              (unsigned)opencv_type_convert_depth((int)(rng() % 64), (int)(rng() % 8)); break;
+            case 16: case 17: case 18: {  // decode a (possibly damaged) file into whatever mat slot `a` holds
+                if (!a.m) break;
+                std::vector<uint8_t> d = files[rng() % files.size()];
+                if (rng() % 3 == 0) d[rng() % d.size()] ^= (uint8_t)(1u << (rng() % 8));
+                if (rng() % 7 == 0) d.resize(16 + rng() % (d.size() - 15));
+                opencv_mat src = opencv_mat_create_from_data((int)d.size(), 1, 0, d.data(), d.size());
+                if (!src) break;
+                if (op == 16) {
+                    if (opencv_decoder dec = opencv_decoder_create(src)) {
+                        if (opencv_decoder_read_header(dec)) sink += opencv_decoder_read_data(dec, a.m);
+                        opencv_decoder_release(dec);
+                    }
+                } else if (op == 17) {
+                    if (webp_decoder w = webp_decoder_create(src)) {
+                        for (int k = 0; k < 4; k++) {
+                            sink += webp_decoder_decode(w, a.m);
+                            if (!webp_decoder_has_more_frames(w)) break;
+                            webp_decoder_advance_frame(w);
+                        }
+                        webp_decoder_release(w);
+                    }
+                } else if (giflib_decoder g = giflib_decoder_create(src)) {
+                    for (int k = 0; k < 4; k++) {
+                        if (giflib_decoder_decode_frame_header(g) != giflib_decoder_have_next_frame) break;
+                        if (rng() & 1) { if (!giflib_decoder_decode_frame(g, a.m)) break; }
+                        else if (giflib_decoder_skip_frame(g) != giflib_decoder_have_next_frame) break;
+                    }
+                    giflib_decoder_release(g);
+                }
+                opencv_mat_release(src);
+                break;
+            }
             default: if (a.m) { opencv_mat_release(a.m); a.m = nullptr; a.store.clear(); } break;
         }
         if (getenv("LP_TRACE") && a.m) fprintf(stderr, "   -> a: %d x %d\n", opencv_mat_get_width(a.m), opencv_mat_get_height(a.m));

@@ -19,5 +19,5 @@ g++ -O1 -g -std=c++17 $SAN -I$ROOT/include -I$ROOT/lilliput_b200/csrc -I${CUDA_H
 export ASAN_OPTIONS=detect_leaks=0:allocator_may_return_null=1:max_allocation_size_mb=16384
 ./transform_fake $ITERS $OUT/seeds/* 2>&1 | grep -v "iterations$" | grep -v "^\[lilliput" | tail -5
 g++ -O1 -g -std=c++17 $SAN -I$ROOT/include $ROOT/tests/native/host_abi_misuse_fake_gpu.cpp -o misuse_fake -L. -llp_fake -Wl,-rpath,$OUT/fake
-./misuse_fake $((ITERS * 100)) 2>&1 | grep -v "calls$" | grep -v "^\[lilliput" | grep -v "^Error: Final encoded" | tail -3
+./misuse_fake $((ITERS * 100)) 3 $OUT/seeds/* 2>&1 | grep -v "calls$" | grep -v "^\[lilliput" | grep -v "^Error: Final encoded" | tail -3
 ./batch_fake $((ITERS / 100 + 1)) $OUT/seeds/*jpeg_3* $OUT/seeds/*jpegvar* $OUT/seeds/*c1_input 2>&1 | grep -v "^\[lilliput" | tail -5

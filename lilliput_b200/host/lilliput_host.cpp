@@ -121,6 +121,7 @@ Error Framebuffer::Fit(int w, int h, Framebuffer* dst) {
     int left, top, wc, hc;
     fitCropRect(width, height, w, h, &left, &top, &wc, &hc);
     opencv_mat view = opencv_mat_crop(mat, left, top, wc, hc);
+    if (!view) return LP_ERR_BAD_ARGUMENT;  // (cannot happen for a rectangle fitCropRect made; the CUDA ABI refuses others)
     Error e = dst->resizeMat(w, h, pixelType);
     if (e) {
         opencv_mat_release(view);
@@ -936,6 +937,7 @@ static int lp_resize_host_impl(const uint8_t* src, int sw, int sh, int type, int
     if (cx < 0 || cy < 0 || cw < 1 || ch < 1 || cx + cw > sw || cy + ch > sh)
         return LP_ERR_BAD_ARGUMENT;
     opencv_mat view = opencv_mat_crop(a.mat, cx, cy, cw, ch);
+    if (!view) return LP_ERR_BAD_ARGUMENT;
     e = b.resizeMat(dw, dh, PixelType{type});
     if (!e) opencv_mat_resize(view, b.mat, dw, dh, interpolation);
     opencv_mat_release(view);

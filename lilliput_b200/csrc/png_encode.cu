@@ -293,7 +293,7 @@ int png_encode_frame(const uint8_t* frame, size_t row_stride, int W, int H, int 
     uint2* d_adler = reinterpret_cast<uint2*>(buf + off_adler);
     uint8_t* d_z = buf + off_z;
     uint32_t* d_total = d_len + nchunks;
-    png_filter_kernel<<<ceil_div(H * 32, 128), 128, 0, st>>>(frame, row_stride, W, H, C, adaptive ? 1 : 0, d_filt);
+    png_filter_kernel<<<(unsigned)ceil_div((long long)H * 32, 128LL), 128, 0, st>>>(frame, row_stride, W, H, C, adaptive ? 1 : 0, d_filt);
     g_launches++;
     png_deflate_kernel<<<ceil_div(nchunks, kDefWarps), kDefWarps * 32, 0, st>>>(d_filt, raw, nchunks, level == 0,
                                                                               d_comp, d_len, d_adler);

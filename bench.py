@@ -121,43 +121,128 @@ def make_corpus(lib, device, n, seed0):
 # ------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed regions.  A timed region is a few hundred ms, shorter
+    than nvidia-smi takes to start, so the sampler is started BEFORE the warm-up and every sample carries
+    a host time stamp; stop() keeps the samples that fall inside the windows opened with begin()/end().
+    Primary source: NVML polled every 5 ms from a thread; fallback: an `nvidia-smi -lms 50` child."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+            (0x4, "sw_power_cap"))
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
-        self.rows = []
+        self.uuid = uuid
+        self.nvml_rows = []       # (t, sm_mhz, reasons bit mask)
+        self.smi_rows = []        # (t, sm_mhz, max_mhz, [reason names])
+        self.windows = []
+        self.max_mhz = None
         self.proc = None
+        self.threads = []
+        self.halt = threading.Event()
+        self.source = None
+
+    # -- sources
+    def _nvml_open(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:                                        # CUDA_VISIBLE_DEVICES may renumber: go by UUID
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{self.uuid}")
+            except Exception:
+                h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        reasons(h)                                           # probe once: raises if unsupported
+        return pynvml, h, reasons
+
+    def _nvml_poll(self, pynvml, h, reasons):
+        while not self.halt.is_set():
+            try:
+                self.nvml_rows.append((time.perf_counter(), int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                       int(reasons(h))))
+            except Exception:
+                pass
+            self.halt.wait(0.005)
+
+    def _smi_read(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            if r and r[0].isdigit():
+                names = [n for k, (_, n) in enumerate(self.BITS) if len(r) > 2 + k and r[2 + k] == "Active"]
+                self.smi_rows.append((time.perf_counter(), int(r[0]),
+                                      int(r[1]) if len(r) > 1 and r[1].isdigit() else None, names))
 
     def start(self):
         try:
+            pynvml, h, reasons = self._nvml_open()
+            t = threading.Thread(target=self._nvml_poll, args=(pynvml, h, reasons), daemon=True)
+            t.start()
+            self.threads.append(t)
+        except Exception:
+            pass
+        try:
+            sel = f"--id={self.uuid and 'GPU-' + str(self.uuid) or self.index}"
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+                ["nvidia-smi", sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            t = threading.Thread(target=self._smi_read, daemon=True)
+            t.start()
+            self.threads.append(t)
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.perf_counter()
+
+    def _inside(self, t):
+        return any(a <= t <= (b if b is not None else t) for a, b in self.windows)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.halt.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        for t in self.threads:
+            t.join(timeout=2)
+        return self.summary(self.nvml_rows, self.smi_rows)
+
+    def summary(self, nvml_rows, smi_rows):
+        window = "timed regions"
+        rows = [r for r in nvml_rows if self._inside(r[0])]
+        if rows:
+            source, sm, mx = "nvml 5 ms", [r[1] for r in rows], self.max_mhz
+            mask = 0
+            for r in rows:
+                mask |= r[2]
+            reasons = [n for b, n in self.BITS if mask & b]
+        else:
+            rows = [r for r in smi_rows if self._inside(r[0])]
+            if not rows and smi_rows and self.windows:
+                # nothing landed inside (region shorter than the sampling period): the warm-up runs the same
+                # kernels back to back, so its samples are the next best thing -- and the JSON says so
+                t_end = max(b or a for a, b in self.windows)
+                rows = [r for r in smi_rows if r[0] <= t_end]
+                window = "warm-up + timed regions"
+            source, sm = "nvidia-smi -lms 50", [r[1] for r in rows]
+            mxs = [r[2] for r in rows if r[2]]
+            mx = max(mxs) if mxs else None
+            reasons = [n for _, n in self.BITS if any(n in r[3] for r in rows)]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": int(np.median(sm)), "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm),
+                "source": source, "window": window}
 
 
 # ------------------------------------------------------------------------------ CPU reference arm
@@ -304,11 +389,16 @@ def main():
     # ---------------- device-resident: inputs staged in HBM once, kernels only in the timed region
     st = b.stage([(base + o, l_) for o, l_ in zip(offs, lens)])
     assert all(s == 0 for s in st), "corpus rejected by the header parser"
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
+    sampler.start()                      # before the warm-up: nvidia-smi needs longer to start than a step takes
     for _ in range(args.warmup):
         b.run()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     stage_sum = {}
     dev_ms = 0.0
     t0 = time.perf_counter()
@@ -319,7 +409,7 @@ def main():
             stage_sum[k] = stage_sum.get(k, 0.0) + v
     barrier()
     wall_s = time.perf_counter() - t0
-    clocks = sampler.stop()
+    sampler.end()
     launches = b.last_launches() * args.steps
     outs, fst = b.fetch(n)
     assert all(s == 0 for s in fst), "device pipeline reported per-image failures"
@@ -330,12 +420,15 @@ def main():
         rc = b.transform_into(ptrs, ln, n, out_ptrs, out_lens, status)
         assert rc == 0
     barrier()
+    sampler.begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         rc = b.transform_into(ptrs, ln, n, out_ptrs, out_lens, status)
         assert rc == 0
     barrier()
     e2e_s = time.perf_counter() - t0
+    sampler.end()
+    clocks = sampler.stop()
     assert all(status[i] == 0 for i in range(n))
 
     dev_s, e2e_max, wall_max = max_over_ranks([dev_ms / 1000.0, e2e_s, wall_s], dist, device="cuda")

@@ -124,7 +124,7 @@ class ClockSampler:
     """SM clock + throttle reasons DURING the timed regions.  A timed region is a few hundred ms, shorter
     than nvidia-smi takes to start, so the sampler is started BEFORE the warm-up and every sample carries
     a host time stamp; stop() keeps the samples that fall inside the windows opened with begin()/end().
-    Primary source: NVML polled every 5 ms from a thread; fallback: an `nvidia-smi -lms 50` child."""
+    Primary source: NVML polled every 20 ms from a thread; fallback: an `nvidia-smi -lms 100` child."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -168,7 +168,7 @@ class ClockSampler:
                                        int(reasons(h))))
             except Exception:
                 pass
-            self.halt.wait(0.005)
+            self.halt.wait(0.02)
 
     def _smi_read(self):
         for line in self.proc.stdout:
@@ -189,7 +189,7 @@ class ClockSampler:
         try:
             sel = f"--id={self.uuid and 'GPU-' + str(self.uuid) or self.index}"
             self.proc = subprocess.Popen(
-                ["nvidia-smi", sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             t = threading.Thread(target=self._smi_read, daemon=True)
             t.start()
@@ -222,7 +222,7 @@ class ClockSampler:
         window = "timed regions"
         rows = [r for r in nvml_rows if self._inside(r[0])]
         if rows:
-            source, sm, mx = "nvml 5 ms", [r[1] for r in rows], self.max_mhz
+            source, sm, mx = "nvml 20 ms", [r[1] for r in rows], self.max_mhz
             mask = 0
             for r in rows:
                 mask |= r[2]
@@ -235,7 +235,7 @@ class ClockSampler:
                 t_end = max(b or a for a, b in self.windows)
                 rows = [r for r in smi_rows if r[0] <= t_end]
                 window = "warm-up + timed regions"
-            source, sm = "nvidia-smi -lms 50", [r[1] for r in rows]
+            source, sm = "nvidia-smi -lms 100", [r[1] for r in rows]
             mxs = [r[2] for r in rows if r[2]]
             mx = max(mxs) if mxs else None
             reasons = [n for _, n in self.BITS if any(n in r[3] for r in rows)]

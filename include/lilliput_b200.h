@@ -80,6 +80,18 @@ int lp_transform(const uint8_t* in, size_t in_len, const lp_image_options* opt, 
 /* Name of the backend behind the per-image ABI: "cuda-sm100a" or "reference". */
 const char* lp_backend_name(void);
 
+/* ---- host-only container sniffers (never touch the device) ------------------
+ * The Go side keeps its own copies (opencv.go:467-637); these expose the C++ mirror's so the
+ * reference's unit tests for them (opencv_test.go:9-220) can be replayed against this library. */
+/* detectAPNG (ref opencv.go:623-637): 1 if an acTL / fcTL / fdAT chunk is reachable, else 0. */
+int lp_detect_apng(const uint8_t* in, size_t in_len);
+/* detectContentLength (ref opencv.go:513-620): bytes up to and including PNG IEND / JPEG EOI,
+ * in_len for anything else or when no end marker is found. */
+int lp_detect_content_length(const uint8_t* in, size_t in_len);
+/* makePngChunkIter + next() (ref opencv.go:468-511): -1 if `in` lacks the PNG signature, else the
+ * number of chunks the iterator visits; the 4-byte types of the first min(count, cap) go to `types`. */
+int lp_png_chunk_types(const uint8_t* in, size_t in_len, uint8_t* types, int cap);
+
 /* ---- stage-level checks on HOST buffers (through the per-image ABI) -------- */
 /* Decode a JPEG/PNG to packed BGR/BGRA/Gray; returns LP status, fills dims. */
 int lp_decode_host(const uint8_t* in, size_t in_len, uint8_t* pixels, size_t pixels_cap,

@@ -225,6 +225,16 @@ int detectContentLength(const uint8_t* img, size_t len) {  // ref opencv.go:611-
     return std::min(detectContentLengthJPEG(img, len), detectContentLengthPNG(img, len));
 }
 
+bool pngChunkTypes(const uint8_t* img, size_t len, std::vector<std::array<uint8_t, 4>>* types) {
+    types->clear();
+    if (len < 8 || memcmp(img, kPngMagic, 8) != 0) return false;  // makePngChunkIter's error
+    walkPngChunks(img, len, [&](const uint8_t* type, size_t) {
+        types->push_back({type[0], type[1], type[2], type[3]});
+        return true;
+    });
+    return true;
+}
+
 // ------------------------------------------------------------ OpenCV adapter
 
 class OpenCVDecoder : public Decoder {  // ref opencv.go:131-137, 442-463
@@ -291,6 +301,16 @@ class OpenCVDecoder : public Decoder {  // ref opencv.go:131-137, 442-463
             n = opencv_decoder_get_png_icc((void*)buf, len, icc.data(), icc.size());
         icc.resize(n > 0 ? n : 0);
         return icc;
+    }
+    bool CICP(::lilliput::CICP* out) override {  // ref opencv.go:745-768
+        if (Description() != "PNG" || len == 0) return false;
+        uint8_t primaries = 0, transfer = 0, matrix = 0, fullRange = 0;
+        if (!opencv_decoder_get_png_cicp((void*)buf, len, &primaries, &transfer, &matrix, &fullRange)) return false;
+        out->Primaries = primaries;
+        out->Transfer = transfer;
+        out->Matrix = matrix;
+        out->FullRange = fullRange != 0;
+        return true;
     }
 
   private:
@@ -766,8 +786,10 @@ Error ImageOps::skipToEnd(Decoder* d) {  // ref ops.go:336-344
     }
 }
 
-// ref ops.go:352-444.  Differences from the Go are only the ones the scope
-// table excludes: no HDR tone-map / cICP policy.
+// ref ops.go:352-444 (+ the colour set-up of initializeTransform, ops.go:483-545).  Differences from the Go are
+// only the ones the scope table excludes: no HDR tone-map and no ICC synthesised from cICP (SURVEY 2 #6, 8f-3:
+// color_info.cpp stays the reference's).  What IS mirrored of the cICP policy: an SDR cICP chunk of a PNG source
+// is re-attached to a PNG output (ops.go:306-332); an HDR (PQ / HLG) tag is never re-emitted (ops.go:513-517).
 Error ImageOps::Transform(Decoder* d, const ImageOptions& opt, uint8_t* dst, size_t dst_cap,
                           size_t* out_len) {
     struct CompositeGuard {  // the deferred close at ops.go:353-358
@@ -779,6 +801,17 @@ Error ImageOps::Transform(Decoder* d, const ImageOptions& opt, uint8_t* dst, siz
     ImageHeader h;
     Error e = d->Header(&h);
     if (e) return e;
+    std::unique_ptr<::lilliput::CICP> outputCICP;  // ref ops.go:511-517
+    {
+        ::lilliput::CICP c;
+        if (d->CICP(&c) && !c.IsHDR()) outputCICP.reset(new ::lilliput::CICP(c));
+    }
+    auto applyOutputCICP = [&](size_t n) -> size_t {  // ref ops.go:310-332
+        if (!outputCICP || n == 0) return n;
+        if (n < sizeof kPngMagic || memcmp(dst, kPngMagic, sizeof kPngMagic) != 0) return n;
+        return opencv_png_insert_cicp(dst, n, dst_cap, outputCICP->Primaries, outputCICP->Transfer,
+                                      outputCICP->Matrix, outputCICP->FullRange ? 1 : 0);
+    };
     std::unique_ptr<Encoder> enc;
     if ((e = NewEncoder(opt.FileType, d, dst, dst_cap, &enc))) return e;
 
@@ -790,6 +823,7 @@ Error ImageOps::Transform(Decoder* d, const ImageOptions& opt, uint8_t* dst, siz
         bool content = false;
         Error ee = enc->Encode(nullptr, opt.EncodeOptions, &content, n);
         if (ee == LP_OK && !content) *n = 0;
+        if (ee == LP_OK) *n = applyOutputCICP(*n);  // ref ops.go:285-291
         return ee;
     };
 
@@ -821,7 +855,7 @@ Error ImageOps::Transform(Decoder* d, const ImageOptions& opt, uint8_t* dst, siz
             e = enc->Encode(active(), opt.EncodeOptions, &content, &n);
         if (e) return e;
         if (content) {
-            *out_len = n;
+            *out_len = applyOutputCICP(n);  // ref ops.go:274-281
             return LP_OK;
         }
         frameCount++;
@@ -1124,6 +1158,15 @@ extern "C" int lp_encode_host(const char* ext, const uint8_t* pixels, int w, int
                               size_t* out_len) { LP_GUARDED(lp_encode_host_impl(ext, pixels, w, h, type, opt, opt_len, dst, dst_cap, out_len)) }
 extern "C" int lp_orient_host(const uint8_t* src, int w, int h, int type, int orientation,
                               uint8_t* dst, int* ow, int* oh) { LP_GUARDED(lp_orient_host_impl(src, w, h, type, orientation, dst, ow, oh)) }
+extern "C" int lp_detect_apng(const uint8_t* in, size_t in_len) { return in && detectAPNG(in, in_len) ? 1 : 0; }
+extern "C" int lp_detect_content_length(const uint8_t* in, size_t in_len) { return in ? detectContentLength(in, in_len) : 0; }
+static int lp_png_chunk_types_impl(const uint8_t* in, size_t in_len, uint8_t* types, int cap) {
+    std::vector<std::array<uint8_t, 4>> t;
+    if (!in || !pngChunkTypes(in, in_len, &t)) return -1;
+    for (int i = 0; types && i < cap && i < (int)t.size(); i++) memcpy(types + 4 * i, t[i].data(), 4);
+    return (int)t.size();
+}
+extern "C" int lp_png_chunk_types(const uint8_t* in, size_t in_len, uint8_t* types, int cap) { LP_GUARDED(lp_png_chunk_types_impl(in, in_len, types, cap)) }
 extern "C" int lp_gif_get_info(const uint8_t* in, size_t in_len, lp_gif_info* info) { LP_GUARDED(lp_gif_get_info_impl(in, in_len, info)) }
 extern "C" int lp_gif_decode_frames_host(const uint8_t* in, size_t in_len, uint8_t* frames, size_t frames_cap,
                                          int max_frames, int* n_frames, int* delays_ms, int* disposals) { LP_GUARDED(lp_gif_decode_frames_host_impl(in, in_len, frames, frames_cap, max_frames, n_frames, delays_ms, disposals)) }

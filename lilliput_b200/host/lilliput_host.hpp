@@ -20,6 +20,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <array>
 #include <map>
 #include <memory>
 #include <string>
@@ -90,6 +91,12 @@ class Framebuffer {
     BlendMethod blend = UseAlphaBlending;
 };
 
+struct CICP {  // ref opencv.go:719-741 (ITU-T H.273 code points carried by a PNG cICP chunk)
+    uint8_t Primaries = 0, Transfer = 0, Matrix = 0;
+    bool FullRange = false;
+    bool IsHDR() const { return Transfer == 16 || Transfer == 18; }  // PQ / HLG, ref color_info.cpp:39-42
+};
+
 class Decoder {  // ref lilliput.go:42-88
   public:
     virtual ~Decoder() {}
@@ -102,6 +109,8 @@ class Decoder {  // ref lilliput.go:42-88
     virtual int LoopCount() { return 0; }
     virtual int64_t Duration_ns() { return 0; }
     virtual giflib_decoder GifHandle() { return nullptr; }  // Go: type assertion to *gifDecoder
+    // Go: type assertion to interface{ CICP() (CICP, bool) } (ops.go:511); only the PNG decoder has one
+    virtual bool CICP(::lilliput::CICP*) { return false; }
 };
 
 // SetGIFMaxFrameDimension (ref giflib.go:44-52; default 10000, giflib.go:39,305-307)
@@ -140,6 +149,8 @@ void fitCropRect(int srcW, int srcH, int dstW, int dstH, int* left, int* top, in
 // ref opencv.go:533-637
 int detectContentLength(const uint8_t* img, size_t len);
 bool detectAPNG(const uint8_t* img, size_t len);
+// ref opencv.go:468-511: chunk types in the order pngChunkIter visits them; false if not a PNG
+bool pngChunkTypes(const uint8_t* img, size_t len, std::vector<std::array<uint8_t, 4>>* types);
 
 class ImageOps {  // ref ops.go:67-150
   public:

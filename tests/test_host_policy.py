@@ -157,3 +157,84 @@ def test_small_destination_is_buf_too_small(lib, golden):
                       _opts(FileType=".jpeg", Width=256, Height=256, ResizeMethod=abi.ImageOpsFit,
                             EncodeOptions={abi.JpegQuality: 85}), dst_cap=512)
     assert e.value.code == abi.LP_ERR_BUF_TOO_SMALL
+
+
+# ---- cICP colour signalling of a PNG source (ref ops.go:306-332, 511-517; the reference's own tests:
+#      png_cicp_test.go:89-155).  SDR tags ride through to a PNG output; PQ / HLG tags are never re-emitted
+#      (the tone-mapping the reference applies to those pixels is out of scope -- DESIGN.md s.8).
+
+def _with_cicp(png, primaries, transfer):
+    """injectPNGCICP (ref png_cicp_test.go:15-35): a cICP chunk directly after IHDR."""
+    import struct
+    import zlib
+    body = bytes([primaries, transfer, 0, 1])
+    chunk = struct.pack(">I", 4) + b"cICP" + body + struct.pack(">I", zlib.crc32(b"cICP" + body))
+    at = 8 + 12 + struct.unpack(">I", png[8:12])[0]
+    return png[:at] + chunk + png[at:]
+
+
+def _png_chunks(png):
+    """pngChunkTypes (ref png_cicp_test.go:37-46) plus the chunk bodies."""
+    import struct
+    out, i = [], 8
+    while i + 8 <= len(png):
+        n = struct.unpack(">I", png[i:i + 4])[0]
+        out.append((png[i + 4:i + 8], png[i + 8:i + 8 + n]))
+        i += n + 12
+    return out
+
+
+def _png_source(golden):
+    return golden["png_rgb"].tobytes()
+
+
+def _transform_png(lib, data):
+    """transformPNG (ref png_cicp_test.go:57-84): Fit at the source's own size, PNG compression 7."""
+    w, h = _dims(lib, data)
+    return lib.transform(data, _opts(FileType=".png", Width=w, Height=h, ResizeMethod=abi.ImageOpsFit,
+                                     EncodeOptions={abi.PngCompression: 7}))
+
+
+def test_sdr_cicp_round_trips_to_png(lib, golden, oracle):
+    """TestPNGSDRCICPRoundTrips: Display-P3 primaries + sRGB transfer is signalling only -- the chunk survives,
+    right after IHDR, and the pixels are the untagged transform's."""
+    src = _png_source(golden)
+    plain = _transform_png(lib, src)
+    tagged = _transform_png(lib, _with_cicp(src, 12, 13))
+    chunks = _png_chunks(tagged)
+    assert chunks[0][0] == b"IHDR" and chunks[1] == (b"cICP", bytes([12, 13, 0, 1]))
+    assert len(tagged) == len(plain) + 16
+    assert tagged[:33] + tagged[49:] == plain                       # nothing else in the file moved
+    assert np.array_equal(oracle.png_decode(tagged), oracle.png_decode(plain))
+
+
+def test_png_without_cicp_gains_none(lib, golden):
+    """TestPNGWithoutCICPUnchanged."""
+    assert b"cICP" not in [t for t, _ in _png_chunks(_transform_png(lib, _png_source(golden)))]
+
+
+@pytest.mark.parametrize("transfer", [16, 18])
+def test_hdr_cicp_tag_is_not_re_emitted(lib, golden, transfer):
+    """The second half of TestPNGHDRCICPIsTonemapped: a PQ (16) or HLG (18) tag no longer describes the output
+    and is dropped (ref ops.go:513-517)."""
+    out = _transform_png(lib, _with_cicp(_png_source(golden), 9, transfer))
+    assert b"cICP" not in [t for t, _ in _png_chunks(out)]
+
+
+def test_sdr_cicp_is_png_output_only(lib, golden):
+    """applyOutputCICP is a no-op for anything that does not start with the PNG signature (ref ops.go:314-316)."""
+    src = _with_cicp(_png_source(golden), 12, 13)
+    w, h = _dims(lib, src)
+    o = _opts(FileType=".jpeg", Width=w, Height=h, ResizeMethod=abi.ImageOpsFit, EncodeOptions={abi.JpegQuality: 85})
+    assert lib.transform(src, o) == lib.transform(_png_source(golden), o)
+
+
+def test_sdr_cicp_needs_sixteen_spare_bytes(lib, golden):
+    """The insert is skipped when the caller's buffer has no room for the chunk (ref opencv.cpp:421-424):
+    the transform still succeeds, untagged."""
+    src = _png_source(golden)
+    plain = _transform_png(lib, src)
+    w, h = _dims(lib, src)
+    o = _opts(FileType=".png", Width=w, Height=h, ResizeMethod=abi.ImageOpsFit, EncodeOptions={abi.PngCompression: 7})
+    out = lib.transform(_with_cicp(src, 12, 13), o, dst_cap=len(plain) + 15)
+    assert out == plain

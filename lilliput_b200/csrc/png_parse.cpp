@@ -130,20 +130,30 @@ const uint16_t kDBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 12
 const uint8_t kDExt[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 }  // namespace
 
-// Inflates a zlib stream into `out` (at most cap bytes).  Returns bytes produced or -1.
+// Inflates a zlib stream into `out`.  Stops as soon as `cap` bytes exist and returns cap -- the caller asks for
+// exactly the bytes it needs, the way libpng's png_inflate_read does, and like zlib it then looks at nothing after
+// them (no end-of-stream, no Adler-32).  Returns fewer than cap when the stream ends first, -1 when it is malformed
+// or runs out of input.
 long host_zlib_inflate(const uint8_t* in, size_t n, uint8_t* out, size_t cap) {
-    if (n < 2 || (in[0] & 15) != 8 || (((unsigned)in[0] << 8) | in[1]) % 31 || (in[1] & 0x20)) return -1;
+    if (n < 2 || (in[0] & 15) != 8 || (in[0] >> 4) > 7 || (((unsigned)in[0] << 8) | in[1]) % 31 || (in[1] & 0x20)) return -1;
+    const unsigned window = 1u << ((in[0] >> 4) + 8);
+    if (cap == 0) return 0;
     Bits b{in + 2, n - 2};
     size_t o = 0;
     int last;
     do {
         last = (int)b.get(1);
         const int type = (int)b.get(2);
+        if (b.pos > b.n) return -1;
         if (type == 0) {
             b.get(b.cnt & 7);
             unsigned len = b.get(16), nlen = b.get(16);
-            if ((len ^ 0xFFFF) != nlen || o + len > cap) return -1;
-            for (unsigned i = 0; i < len; i++) out[o++] = (uint8_t)b.get(8);
+            if (b.pos > b.n || (len ^ 0xFFFF) != nlen) return -1;
+            for (unsigned i = 0; i < len; i++) {
+                out[o++] = (uint8_t)b.get(8);
+                if (b.pos > b.n) return -1;
+                if (o == cap) return (long)o;
+            }
         } else if (type == 1 || type == 2) {
             Canon hl, hd;
             uint8_t lens[320];
@@ -167,7 +177,7 @@ long host_zlib_inflate(const uint8_t* in, size_t n, uint8_t* out, size_t cap) {
                 int i = 0;
                 while (i < nl + nd) {
                     int s = hc.decode(b);
-                    if (s < 0) return -1;
+                    if (s < 0 || b.pos > b.n) return -1;
                     if (s < 16) { lens[i++] = (uint8_t)s; continue; }
                     int rep, v = 0;
                     if (s == 16) { if (!i) return -1; v = lens[i - 1]; rep = 3 + (int)b.get(2); }
@@ -176,23 +186,30 @@ long host_zlib_inflate(const uint8_t* in, size_t n, uint8_t* out, size_t cap) {
                     if (i + rep > nl + nd) return -1;
                     while (rep--) lens[i++] = (uint8_t)v;
                 }
+                if (b.pos > b.n || lens[256] == 0) return -1;  // zlib: "missing end-of-block"
                 if (!hl.build(lens, nl)) return -1;
                 hd.build(lens + nl, nd);
             }
             for (;;) {
                 int s = hl.decode(b);
-                if (s < 0) return -1;
-                if (s < 256) { if (o >= cap) return -1; out[o++] = (uint8_t)s; }
-                else if (s == 256) break;
-                else {
+                if (s < 0 || b.pos > b.n) return -1;
+                if (s < 256) {
+                    out[o++] = (uint8_t)s;
+                    if (o == cap) return (long)o;
+                } else if (s == 256) {
+                    break;
+                } else {
                     s -= 257;
                     if (s >= 29) return -1;
                     unsigned len = kLBase[s] + b.get(kLExt[s]);
                     int ds = hd.decode(b);
                     if (ds < 0 || ds >= 30) return -1;
                     unsigned dist = kDBase[ds] + b.get(kDExt[ds]);
-                    if (dist > o || o + len > cap) return -1;
-                    for (unsigned i = 0; i < len; i++, o++) out[o] = out[o - dist];
+                    if (b.pos > b.n || dist > o || dist > window) return -1;
+                    for (unsigned i = 0; i < len; i++, o++) {
+                        out[o] = out[o - dist];
+                        if (o + 1 == cap) return (long)cap;
+                    }
                 }
             }
         } else {
@@ -202,29 +219,126 @@ long host_zlib_inflate(const uint8_t* in, size_t n, uint8_t* out, size_t cap) {
     return (long)o;
 }
 
-// iCCP: keyword\0 method(0) zlib(profile).  Returns profile length copied into dest, or 0.
+// ---- iCCP, with the acceptance rules of the reference's libpng 1.6.47 (png_handle_iCCP, png_icc_check_length /
+//      _header / _tag_table): what that library refuses to store, opencv_decoder_get_png_icc reports as "no
+//      profile" (ref opencv.cpp:315-345), and so must this.
+
+static inline uint32_t fourcc(const char* s) { return be32(reinterpret_cast<const uint8_t*>(s)); }
+
+// CRC-32 of a chunk's type + body against the stored value (a CRC error in a critical chunk is a png_error).
+static bool png_chunk_crc_ok(const uint8_t* type, uint32_t n) {
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < 4 + (size_t)n; i++) {
+        c ^= type[i];
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1)));
+    }
+    return ~c == be32(type + 4 + n);
+}
+
+// One iCCP chunk body -> the validated profile, or false.
+static bool png_read_iccp_chunk(const uint8_t* d, uint32_t n, int color_type, std::vector<uint8_t>* out) {
+    const uint32_t read_length = n < 81 ? n : 81;  // keyword + separator + method: at most 81 bytes
+    if (n - read_length < 11) return false;        // "too short": libpng wants 11 bytes of zlib stream AFTER those 81
+    uint32_t k = 0;
+    while (k < 80 && k < read_length && d[k]) k++;
+    if (k < 1 || k > 79) return false;                          // "bad keyword"
+    if (!(k + 1 < read_length && d[k + 1] == 0)) return false;  // "bad compression method"
+    const uint8_t* z = d + k + 2;
+    const size_t zn = n - k - 2;
+    uint8_t head[132];
+    if (host_zlib_inflate(z, zn, head, sizeof head) != (long)sizeof head) return false;  // profile truncated
+    const uint32_t plen = be32(head);
+    if (plen < 132 || plen > 8000000u) return false;            // "too short" / over PNG_USER_CHUNK_MALLOC_MAX
+    if (head[8] > 3 && (plen & 3)) return false;                // "invalid length" (ICC v4+: multiple of 4)
+    const uint32_t tags = be32(head + 128);
+    if (tags > 357913930u || (uint64_t)plen < 132 + 12ull * tags) return false;  // "tag count too large"
+    if (be32(head + 64) >= 0xffff) return false;                // "invalid rendering intent"
+    if (be32(head + 36) != fourcc("acsp")) return false;        // "invalid signature"
+    const uint32_t space = be32(head + 16);
+    if (space == fourcc("RGB ")) {
+        if (!(color_type & 2)) return false;                    // RGB profile on a grayscale PNG
+    } else if (space == fourcc("GRAY")) {
+        if (color_type & 2) return false;                       // gray profile on a colour PNG
+    } else {
+        return false;                                           // "invalid ICC profile color space"
+    }
+    const uint32_t cls = be32(head + 12);
+    if (cls == fourcc("abst") || cls == fourcc("link")) return false;
+    const uint32_t pcs = be32(head + 20);
+    if (pcs != fourcc("XYZ ") && pcs != fourcc("Lab ")) return false;  // "unexpected ICC PCS encoding"
+    std::vector<uint8_t> prof(plen);
+    if (host_zlib_inflate(z, zn, prof.data(), plen) != (long)plen) return false;  // truncated; extra data is allowed
+    for (uint32_t t = 0; t < tags; t++) {
+        const uint8_t* tag = prof.data() + 132 + 12 * (size_t)t;
+        const uint32_t start = be32(tag + 4), length = be32(tag + 8);
+        if (start > plen || length > plen - start) return false;  // "ICC profile tag outside profile"
+    }
+    out->swap(prof);
+    return true;
+}
+
+// What png_read_info + png_get_iCCP leave in the caller's hands: the profile of the first iCCP chunk, if libpng
+// would have stored it, and only if the header part of the file (everything up to the first IDAT) reads cleanly.
+// Returns the profile length copied into dest, or 0.
 int png_extract_icc(const uint8_t* in, size_t len, uint8_t* dest, size_t dest_len) {
     if (len < 8 || memcmp(in, kPngSig, 8) != 0) return 0;
     size_t pos = 8;
-    while (pos + 12 <= len) {
+    int color_type = -1;
+    bool seen_plte = false;
+    std::vector<uint8_t> profile;
+    for (;;) {
+        if (pos + 8 > len) return 0;  // ran off the data before IDAT: libpng's read callback errors out
         const uint32_t n = be32(in + pos);
         const uint8_t* type = in + pos + 4;
         const uint8_t* d = in + pos + 8;
+        if (n > 0x7fffffffu) return 0;  // "PNG unsigned integer out of range"
+        for (int i = 0; i < 4; i++)
+            if (!((type[i] >= 'A' && type[i] <= 'Z') || (type[i] >= 'a' && type[i] <= 'z'))) return 0;  // "invalid chunk type"
+        if (type[2] & 0x20) return 0;  // reserved bit set: "bad header (invalid type)"
+        if (color_type < 0) {  // the first chunk has to be a well-formed IHDR (png_check_IHDR)
+            if (memcmp(type, "IHDR", 4) != 0 || n != 13 || pos + 12 + 13 > len) return 0;
+            if (!png_chunk_crc_ok(type, n)) return 0;
+            const uint32_t w = be32(d), h = be32(d + 4);
+            const int bd = d[8], ct = d[9];
+            if (w == 0 || h == 0 || w > 1000000u || h > 1000000u) return 0;  // libpng's default user limits
+            if (bd != 1 && bd != 2 && bd != 4 && bd != 8 && bd != 16) return 0;
+            if (ct == 1 || ct == 5 || ct > 6) return 0;
+            if ((ct == 3 && bd > 8) || ((ct == 2 || ct == 4 || ct == 6) && bd < 8)) return 0;
+            if (d[10] != 0 || d[11] != 0 || d[12] > 1) return 0;
+            color_type = ct;
+            pos += 25;
+            continue;
+        }
+        if (!memcmp(type, "IDAT", 4)) break;  // png_read_info stops at the first IDAT header
         if (pos + 12 + (size_t)n > len) return 0;
-        if (!memcmp(type, "IDAT", 4) || !memcmp(type, "IEND", 4)) return 0;  // iCCP precedes IDAT
-        if (!memcmp(type, "iCCP", 4)) {
-            size_t k = 0;
-            while (k < n && k < 80 && d[k]) k++;
-            if (k + 2 >= n || d[k + 1] != 0) return 0;
-            std::vector<uint8_t> buf(dest_len + 1);
-            long got = host_zlib_inflate(d + k + 2, n - k - 2, buf.data(), buf.size());
-            if (got <= 0 || (size_t)got > dest_len) return 0;
-            memcpy(dest, buf.data(), (size_t)got);
-            return (int)got;
+        if (!memcmp(type, "IEND", 4) || !memcmp(type, "IHDR", 4)) return 0;  // out of place: png_chunk_error
+        if (!memcmp(type, "PLTE", 4)) {  // png_handle_PLTE, as libpng 1.6.47 behaves
+            if (!(color_type & 2)) {
+                // "ignored in grayscale PNG": skipped whatever it holds, and it does not count as a palette
+            } else if (color_type == 3) {
+                // the palette of a palette image is critical: duplicate, bad length, empty or CRC error all end the read
+                if (seen_plte || n > 3 * 256 || n % 3 || n == 0 || !png_chunk_crc_ok(type, n)) return 0;
+                seen_plte = true;
+            } else if (seen_plte) {
+                // a suggested palette in an RGB(A) image is treated like an ancillary chunk: "duplicate" is skipped
+            } else if (n > 3 * 256 || n % 3) {
+                // "invalid": skipped, and a later PLTE is still the first
+            } else {
+                if (n == 0) return 0;  // png_set_PLTE: "Invalid palette" is a png_error for every colour type
+                seen_plte = true;      // a CRC error here is only a warning and the chunk still counts
+            }
+        } else if (!(type[0] & 0x20)) {
+            return 0;  // an unknown critical chunk ends the read with an error
+        } else if (!memcmp(type, "iCCP", 4)) {
+            // after PLTE the chunk is out of place; once a profile has been stored a further chunk is a duplicate:
+            // both are skipped.  A chunk that was refused does not stop a later one from being taken.
+            if (profile.empty() && !seen_plte) png_read_iccp_chunk(d, n, color_type, &profile);
         }
         pos += 12 + (size_t)n;
     }
-    return 0;
+    if (profile.empty() || profile.size() > dest_len) return 0;
+    memcpy(dest, profile.data(), profile.size());
+    return (int)profile.size();
 }
 
 }  // namespace lp

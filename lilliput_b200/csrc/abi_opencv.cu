@@ -921,24 +921,13 @@ int opencv_decoder_get_png_icc(void* src, size_t src_len, void* dest, size_t des
 
 int opencv_decoder_get_png_cicp(void* src, size_t src_len, uint8_t* primaries, uint8_t* transfer,
                                 uint8_t* matrix, uint8_t* full_range) {
-    const uint8_t* p = static_cast<const uint8_t*>(src);
-    static const uint8_t sig[8] = {0x89, 0x50, 0x4E, 0x47, 0x0D, 0x0A, 0x1A, 0x0A};
-    if (!p || src_len < 8 || memcmp(p, sig, 8)) return 0;
-    size_t off = 8;
-    while (off + 12 <= src_len) {
-        uint32_t n = be32(p + off);
-        const uint8_t* type = p + off + 4;
-        if (!memcmp(type, "IDAT", 4) || !memcmp(type, "IEND", 4)) break;  // png_read_info stops here
-        if (!memcmp(type, "cICP", 4) && n == 4 && off + 12 + n <= src_len) {
-            *primaries = p[off + 8];
-            *transfer = p[off + 9];
-            *matrix = p[off + 10];
-            *full_range = p[off + 11];
-            return 1;
-        }
-        off += 12 + (size_t)n;
-    }
-    return 0;
+    uint8_t v[4];
+    if (!src || !png_extract_cicp(static_cast<const uint8_t*>(src), src_len, v)) return 0;
+    *primaries = v[0];
+    *transfer = v[1];
+    *matrix = v[2];
+    *full_range = v[3];
+    return 1;
 }
 
 static uint32_t crc32_bytes(const uint8_t* p, size_t n) {

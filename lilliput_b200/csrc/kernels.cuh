@@ -183,6 +183,8 @@ struct PngHeader {
 };
 int png_parse(const uint8_t* data, size_t len, PngHeader* out);
 int png_extract_icc(const uint8_t* data, size_t len, uint8_t* dest, size_t dest_len);
+// cICP code points (primaries, transfer, matrix, full range) of the chunk libpng would report; 1 if found
+int png_extract_cicp(const uint8_t* data, size_t len, uint8_t* out4);
 
 // One PNG to decode (array in HBM).  zoff: the concatenated IDAT payload (one zlib stream);
 // raw: (row_bytes+1)*height bytes of filtered scanlines, defiltered in place; frame: packed output.

@@ -277,68 +277,94 @@ static bool png_read_iccp_chunk(const uint8_t* d, uint32_t n, int color_type, st
     return true;
 }
 
-// What png_read_info + png_get_iCCP leave in the caller's hands: the profile of the first iCCP chunk, if libpng
-// would have stored it, and only if the header part of the file (everything up to the first IDAT) reads cleanly.
-// Returns the profile length copied into dest, or 0.
-int png_extract_icc(const uint8_t* in, size_t len, uint8_t* dest, size_t dest_len) {
-    if (len < 8 || memcmp(in, kPngSig, 8) != 0) return 0;
+// The part of a PNG that png_read_info reads -- everything up to the first IDAT header -- walked with libpng
+// 1.6.47's rules for what ends the read with an error.  `visit(type, body, n, colour_type, after_plte)` is called
+// for every ancillary chunk.  Returns false when png_read_info would have failed (png_error -> longjmp), which
+// makes every getter built on it answer "nothing".
+template <class F>
+static bool png_walk_info(const uint8_t* in, size_t len, F&& visit) {
+    if (len < 8 || memcmp(in, kPngSig, 8) != 0) return false;
     size_t pos = 8;
     int color_type = -1;
     bool seen_plte = false;
-    std::vector<uint8_t> profile;
     for (;;) {
-        if (pos + 8 > len) return 0;  // ran off the data before IDAT: libpng's read callback errors out
+        if (pos + 8 > len) return false;  // ran off the data before IDAT: libpng's read callback errors out
         const uint32_t n = be32(in + pos);
         const uint8_t* type = in + pos + 4;
         const uint8_t* d = in + pos + 8;
-        if (n > 0x7fffffffu) return 0;  // "PNG unsigned integer out of range"
+        if (n > 0x7fffffffu) return false;  // "PNG unsigned integer out of range"
         for (int i = 0; i < 4; i++)
-            if (!((type[i] >= 'A' && type[i] <= 'Z') || (type[i] >= 'a' && type[i] <= 'z'))) return 0;  // "invalid chunk type"
-        if (type[2] & 0x20) return 0;  // reserved bit set: "bad header (invalid type)"
+            if (!((type[i] >= 'A' && type[i] <= 'Z') || (type[i] >= 'a' && type[i] <= 'z'))) return false;  // "invalid chunk type"
+        if (type[2] & 0x20) return false;  // reserved bit set: "bad header (invalid type)"
         if (color_type < 0) {  // the first chunk has to be a well-formed IHDR (png_check_IHDR)
-            if (memcmp(type, "IHDR", 4) != 0 || n != 13 || pos + 12 + 13 > len) return 0;
-            if (!png_chunk_crc_ok(type, n)) return 0;
+            if (memcmp(type, "IHDR", 4) != 0 || n != 13 || pos + 12 + 13 > len) return false;
+            if (!png_chunk_crc_ok(type, n)) return false;
             const uint32_t w = be32(d), h = be32(d + 4);
             const int bd = d[8], ct = d[9];
-            if (w == 0 || h == 0 || w > 1000000u || h > 1000000u) return 0;  // libpng's default user limits
-            if (bd != 1 && bd != 2 && bd != 4 && bd != 8 && bd != 16) return 0;
-            if (ct == 1 || ct == 5 || ct > 6) return 0;
-            if ((ct == 3 && bd > 8) || ((ct == 2 || ct == 4 || ct == 6) && bd < 8)) return 0;
-            if (d[10] != 0 || d[11] != 0 || d[12] > 1) return 0;
+            if (w == 0 || h == 0 || w > 1000000u || h > 1000000u) return false;  // libpng's default user limits
+            if (bd != 1 && bd != 2 && bd != 4 && bd != 8 && bd != 16) return false;
+            if (ct == 1 || ct == 5 || ct > 6) return false;
+            if ((ct == 3 && bd > 8) || ((ct == 2 || ct == 4 || ct == 6) && bd < 8)) return false;
+            if (d[10] != 0 || d[11] != 0 || d[12] > 1) return false;
             color_type = ct;
             pos += 25;
             continue;
         }
-        if (!memcmp(type, "IDAT", 4)) break;  // png_read_info stops at the first IDAT header
-        if (pos + 12 + (size_t)n > len) return 0;
-        if (!memcmp(type, "IEND", 4) || !memcmp(type, "IHDR", 4)) return 0;  // out of place: png_chunk_error
+        if (!memcmp(type, "IDAT", 4)) return true;  // png_read_info stops at the first IDAT header
+        if (pos + 12 + (size_t)n > len) return false;
+        if (!memcmp(type, "IEND", 4) || !memcmp(type, "IHDR", 4)) return false;  // out of place: png_chunk_error
         if (!memcmp(type, "PLTE", 4)) {  // png_handle_PLTE, as libpng 1.6.47 behaves
             if (!(color_type & 2)) {
                 // "ignored in grayscale PNG": skipped whatever it holds, and it does not count as a palette
             } else if (color_type == 3) {
                 // the palette of a palette image is critical: duplicate, bad length, empty or CRC error all end the read
-                if (seen_plte || n > 3 * 256 || n % 3 || n == 0 || !png_chunk_crc_ok(type, n)) return 0;
+                if (seen_plte || n > 3 * 256 || n % 3 || n == 0 || !png_chunk_crc_ok(type, n)) return false;
                 seen_plte = true;
             } else if (seen_plte) {
                 // a suggested palette in an RGB(A) image is treated like an ancillary chunk: "duplicate" is skipped
             } else if (n > 3 * 256 || n % 3) {
                 // "invalid": skipped, and a later PLTE is still the first
             } else {
-                if (n == 0) return 0;  // png_set_PLTE: "Invalid palette" is a png_error for every colour type
-                seen_plte = true;      // a CRC error here is only a warning and the chunk still counts
+                if (n == 0) return false;  // png_set_PLTE: "Invalid palette" is a png_error for every colour type
+                seen_plte = true;          // a CRC error here is only a warning and the chunk still counts
             }
         } else if (!(type[0] & 0x20)) {
-            return 0;  // an unknown critical chunk ends the read with an error
-        } else if (!memcmp(type, "iCCP", 4)) {
-            // after PLTE the chunk is out of place; once a profile has been stored a further chunk is a duplicate:
-            // both are skipped.  A chunk that was refused does not stop a later one from being taken.
-            if (profile.empty() && !seen_plte) png_read_iccp_chunk(d, n, color_type, &profile);
+            return false;  // an unknown critical chunk ends the read with an error
+        } else {
+            visit(type, d, n, color_type, seen_plte);
         }
         pos += 12 + (size_t)n;
     }
-    if (profile.empty() || profile.size() > dest_len) return 0;
+}
+
+// What png_read_info + png_get_iCCP leave in the caller's hands (ref opencv.cpp:315-345): the first profile libpng
+// would have stored.  Returns the profile length copied into dest, or 0.
+int png_extract_icc(const uint8_t* in, size_t len, uint8_t* dest, size_t dest_len) {
+    std::vector<uint8_t> profile;
+    const bool ok = png_walk_info(in, len, [&](const uint8_t* type, const uint8_t* d, uint32_t n, int color_type, bool after_plte) {
+        // after PLTE the chunk is out of place; once a profile has been stored a further chunk is a duplicate:
+        // both are skipped.  A chunk that was refused does not stop a later one from being taken.
+        if (!memcmp(type, "iCCP", 4) && profile.empty() && !after_plte) png_read_iccp_chunk(d, n, color_type, &profile);
+    });
+    if (!ok || profile.empty() || profile.size() > dest_len) return 0;
     memcpy(dest, profile.data(), profile.size());
     return (int)profile.size();
+}
+
+// png_read_info + png_get_cICP (ref opencv.cpp:347-395): the four code points of the first cICP chunk libpng
+// accepts.  A chunk that was read (4 bytes, CRC good) counts as THE cICP chunk even when png_set_cICP then refuses
+// it for a non-zero matrix; a later one is a duplicate.  Returns 1 and fills out[4], or 0.
+int png_extract_cicp(const uint8_t* in, size_t len, uint8_t* out) {
+    bool seen = false, found = false;
+    const bool ok = png_walk_info(in, len, [&](const uint8_t* type, const uint8_t* d, uint32_t n, int, bool after_plte) {
+        if (memcmp(type, "cICP", 4) != 0 || seen || after_plte) return;
+        if (n != 4 || !png_chunk_crc_ok(type, n)) return;
+        seen = true;
+        if (d[2] != 0) return;  // "Invalid cICP matrix coefficients": RGB data only
+        memcpy(out, d, 4);
+        found = true;
+    });
+    return ok && found ? 1 : 0;
 }
 
 }  // namespace lp

@@ -277,3 +277,90 @@ def test_png_icc_random_mutants_match_the_reference(both, golden, capfd, seed):
         accepted += isinstance(want, bytes)
     assert accepted > 150          # the campaign is not all refusals
     _quiet(capfd)
+
+
+# ------------------------------------------------------------------------------------------- cICP
+
+def _bind_cicp(lib):
+    l = lib.l
+    l.opencv_decoder_get_png_cicp.restype = C.c_int
+    l.opencv_decoder_get_png_cicp.argtypes = [C.c_char_p, C.c_size_t] + [C.POINTER(C.c_uint8)] * 4
+
+    def get(b):
+        v = [C.c_uint8(0xEE) for _ in range(4)]
+        found = l.opencv_decoder_get_png_cicp(b, len(b), *[C.byref(x) for x in v])
+        return tuple(x.value for x in v) if found else None
+    return get
+
+
+def _cicp(a, b, c, d, n=4, crc=None):
+    return _chunk(b"cICP", (bytes([a, b, c, d]) + bytes(4))[:n], crc=crc)
+
+
+def _cicp_cases():
+    good = _fill(_header(132))
+    ihdr = struct.pack(">IIBBBBB", 2, 2, 8, 2, 0, 0, 0)
+    return {
+        "plain": _png(),
+        "sdr_p3": _png(_cicp(12, 13, 0, 1)),
+        "pq_2020": _png(_cicp(9, 16, 0, 1)),
+        "hlg": _png(_cicp(9, 18, 0, 0)),
+        "matrix_nonzero_is_refused": _png(_cicp(1, 13, 5, 1)),
+        "range_2": _png(_cicp(1, 13, 0, 2)),
+        "three_bytes": _png(_cicp(1, 13, 0, 1, n=3)),
+        "five_bytes": _png(_cicp(1, 13, 0, 1, n=5)),
+        "all_zero": _png(_cicp(0, 0, 0, 0)),
+        "all_ff": _png(_cicp(255, 255, 0, 255)),
+        "two_first_wins": _png(_cicp(12, 13, 0, 1), _cicp(9, 16, 0, 1)),
+        "two_first_refused_matrix": _png(_cicp(1, 13, 5, 1), _cicp(9, 16, 0, 1)),
+        "two_first_crc_error": _png(_cicp(1, 13, 0, 1, crc=3), _cicp(9, 16, 0, 1)),
+        "two_first_wrong_length": _png(_cicp(1, 13, 0, 1, n=5), _cicp(9, 16, 0, 1)),
+        "after_plte_rgb": _png(_chunk(b"PLTE", bytes(9)), _cicp(12, 13, 0, 1)),
+        "after_plte_palette": _png(_chunk(b"PLTE", bytes(9)), _cicp(12, 13, 0, 1), ctype=3),
+        "before_plte_palette": _png(_cicp(12, 13, 0, 1), _chunk(b"PLTE", bytes(9)), ctype=3),
+        "after_ignored_plte_gray": _png(_chunk(b"PLTE", bytes(9)), _cicp(12, 13, 0, 1), ctype=0),
+        "after_idat": _png(after=(_cicp(12, 13, 0, 1),)),
+        "crc_error": _png(_cicp(12, 13, 0, 1, crc=3)),
+        "with_iccp_after": _png(_cicp(12, 13, 0, 1), _iccp(good)),
+        "with_iccp_before": _png(_iccp(good), _cicp(12, 13, 0, 1)),
+        "with_srgb": _png(_chunk(b"sRGB", b"\0"), _cicp(12, 13, 0, 1)),
+        "with_mdcv_clli": _png(_cicp(9, 16, 0, 1), _chunk(b"mDCV", bytes(24)), _chunk(b"cLLI", bytes(8))),
+        "gray_image": _png(_cicp(12, 13, 0, 1), ctype=0),
+        "ends_inside_cicp": _png(_cicp(12, 13, 0, 1))[:40],
+        "ends_before_idat": _png(_cicp(12, 13, 0, 1))[:49],
+        "ends_in_idat_body": _png(_cicp(12, 13, 0, 1))[:60],
+        "ihdr_crc_error": MAGIC + _chunk(b"IHDR", ihdr, crc=1) + _png(_cicp(12, 13, 0, 1))[33:],
+        "unknown_critical_after": _png(_cicp(12, 13, 0, 1), _chunk(b"ZZZZ", b"")),
+        "not_png": bytes(64),
+    }
+
+
+def test_png_cicp_matches_the_reference(ref_lib, capfd):
+    p, r = _bind_cicp(abi.load_cuda()), _bind_cicp(ref_lib)
+    cases = _cicp_cases()
+    for name, data in cases.items():
+        assert p(data) == r(data), name
+    assert p(cases["sdr_p3"]) == (12, 13, 0, 1) and p(cases["two_first_wins"]) == (12, 13, 0, 1)
+    assert p(cases["matrix_nonzero_is_refused"]) is None and p(cases["two_first_refused_matrix"]) is None
+    assert p(cases["two_first_crc_error"]) == (9, 16, 0, 1)
+    assert p(cases["after_plte_rgb"]) is None and p(cases["after_ignored_plte_gray"]) == (12, 13, 0, 1)
+    assert p(cases["ends_before_idat"]) is None and p(cases["ends_in_idat_body"]) == (12, 13, 0, 1)
+    rnd = random.Random(5)
+    seeds = list(cases.values())
+    accepted = 0
+    for it in range(6000):
+        b = bytearray(rnd.choice(seeds))
+        mode = rnd.randrange(3)
+        if mode == 0:
+            for _ in range(rnd.randrange(1, 4)):
+                b[rnd.randrange(8, min(len(b), 80))] = rnd.randrange(256)
+        elif mode == 1:
+            b = b[:rnd.randrange(8, len(b))]
+        else:
+            for _ in range(rnd.randrange(1, 5)):
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+        want = r(bytes(b))
+        assert p(bytes(b)) == want, (it, mode)
+        accepted += want is not None
+    assert accepted > 300
+    _quiet(capfd)

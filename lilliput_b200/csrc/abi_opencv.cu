@@ -746,7 +746,7 @@ int opencv_decoder_get_pixel_type(const opencv_decoder d) {
 }
 int opencv_decoder_get_orientation(const opencv_decoder d) {
     const Decoder* dd = static_cast<Decoder*>(d);
-    return dd->is_png ? 1 : dd->jpeg.orientation;
+    return dd->is_png ? dd->png.orientation : dd->jpeg.orientation;
 }
 
 bool opencv_decoder_read_data(opencv_decoder d, opencv_mat dst) {

@@ -255,7 +255,9 @@ static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t
         int rc = jpeg_parse_header(in[k], in_len[k], &h);
         if (!rc && !h.supported) rc = LP_ERR_UNSUPPORTED;
         if (!rc && (h.width != b->W || h.height != b->H)) rc = LP_ERR_BAD_ARGUMENT;
-        if (!rc && h.orientation != 1) rc = LP_ERR_UNSUPPORTED;  // batch path: TL only
+        // batch path: TL only.  EXIF values outside 2..8 (0, 9, 300 ... the reader passes them through,
+        // like the reference's) are no-ops for OrientationTransform, so they are TL as well
+        if (!rc && h.orientation >= 2 && h.orientation <= 8) rc = LP_ERR_UNSUPPORTED;
         if (!rc && h.ncomp != 3) rc = LP_ERR_UNSUPPORTED;
         int ts = rc ? 0 : table_set_for(b, h);
         if (!rc && ts < 0) rc = LP_ERR_UNSUPPORTED;

@@ -15,33 +15,91 @@ static const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 
                                     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
                                     58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-// EXIF IFD0 tag 0x0112 from an APP1 payload; 0 when absent/invalid.
-static int exif_orientation(const uint8_t* p, size_t n) {
-    if (n < 14 || memcmp(p, "Exif\0\0", 6) != 0) return 0;
-    const uint8_t* t = p + 6;
-    size_t tn = n - 6;
-    bool le;
-    if (t[0] == 'I' && t[1] == 'I') le = true;
-    else if (t[0] == 'M' && t[1] == 'M') le = false;
-    else return 0;
-    auto rd16 = [&](size_t o) -> unsigned { return le ? (t[o] | (t[o + 1] << 8)) : ((t[o] << 8) | t[o + 1]); };
-    auto rd32 = [&](size_t o) -> uint32_t {
-        return le ? ((uint32_t)t[o] | ((uint32_t)t[o + 1] << 8) | ((uint32_t)t[o + 2] << 16) | ((uint32_t)t[o + 3] << 24))
-                  : (((uint32_t)t[o] << 24) | ((uint32_t)t[o + 1] << 16) | ((uint32_t)t[o + 2] << 8) | t[o + 3]);
-    };
-    if (rd16(2) != 42) return 0;
-    size_t ifd = rd32(4);
-    if (ifd + 2 > tn) return 0;
-    unsigned cnt = rd16(ifd);
-    for (unsigned i = 0; i < cnt; i++) {
-        size_t e = ifd + 2 + (size_t)i * 12;
-        if (e + 12 > tn) return 0;
-        if (rd16(e) == 0x0112) {
-            unsigned v = rd16(e + 8);
-            return (v >= 1 && v <= 8) ? (int)v : 0;
+// EXIF orientation the way the reference's OpenCV 4.11 reads it (modules/imgcodecs/src/exif.cpp driven by
+// grfmt_jpeg.cpp; restated from behaviour and pinned by tests/test_host_exif.py against the live reference).
+// What that reader does and a tidy TIFF parser would not:
+//  * only the FIRST APP1 segment of the file is looked at, whatever its identifier; its first 6 bytes are skipped
+//    unread ("Exif\0\0" is never compared), so an XMP APP1 in front hides the EXIF one;
+//  * a byte-order mark that is neither "II" nor "MM" reads big-endian;
+//  * IFD0 entries are parsed in file order and the parse stops at the first entry whose data lies outside the
+//    segment (strings, rationals); entries already read stay valid, later ones are never seen;
+//  * the orientation value is the 16-bit word at entry + 8, whatever the entry's type and count say, and is
+//    reported as it is (0, 9, 300 ...); of two orientation entries the first counts.
+// Returns true and sets *value when an orientation entry was read.
+namespace {
+struct ExifBytes {
+    const uint8_t* d;
+    size_t n;
+    bool intel;
+    bool stop = false;  // OpenCV: ExifParsingError thrown
+    unsigned u16(size_t o) {
+        if (stop || o + 1 >= n || o + 1 < o) { stop = true; return 0; }
+        return intel ? (unsigned)(d[o] | (d[o + 1] << 8)) : (unsigned)((d[o] << 8) | d[o + 1]);
+    }
+    uint32_t u32(size_t o) {
+        if (stop || o + 3 >= n || o + 3 < o) { stop = true; return 0; }
+        return intel ? ((uint32_t)d[o] | ((uint32_t)d[o + 1] << 8) | ((uint32_t)d[o + 2] << 16) | ((uint32_t)d[o + 3] << 24))
+                     : (((uint32_t)d[o] << 24) | ((uint32_t)d[o + 1] << 16) | ((uint32_t)d[o + 2] << 8) | d[o + 3]);
+    }
+    void rationals(size_t entry, int count) {  // count (numerator, denominator) pairs at the offset the entry names
+        size_t o = u32(entry + 8);
+        for (int i = 0; i < count && !stop; i++, o += 8) { u32(o); u32(o + 4); }
+    }
+    void string(size_t entry) {
+        size_t len = u32(entry + 4);
+        size_t off = len > 4 ? (size_t)u32(entry + 8) : entry + 8;
+        if (stop) return;
+        if (off >= n || len > n - off) stop = true;
+    }
+};
+}  // namespace
+
+bool exif_orientation_opencv(const uint8_t* tiff, size_t n, int* value) {
+    if (n == 0) return false;
+    ExifBytes x{tiff, n, n >= 2 && tiff[0] == tiff[1] && tiff[0] == 'I'};
+    if (x.u16(2) != 0x002A || x.stop) return false;
+    size_t off = x.u32(4);
+    const unsigned entries = x.u16(off);
+    off += 2;
+    bool found = false;
+    for (unsigned i = 0; i < entries && !x.stop; i++, off += 12) {
+        const unsigned tag = x.u16(off);
+        if (x.stop) break;
+        unsigned v = 0;
+        switch (tag) {
+            case 0x010E: case 0x010F: case 0x0110: case 0x0131: case 0x0132: case 0x8298:  // description, make, model, software, date, copyright
+                x.string(off);
+                break;
+            case 0x0112:  // orientation
+                v = x.u16(off + 8);
+                if (!x.stop && !found) {
+                    *value = (int)v;
+                    found = true;
+                }
+                break;
+            case 0x011A: case 0x011B:  // x / y resolution
+                x.rationals(off, 1);
+                break;
+            case 0x0128: case 0x011C: case 0x0213:  // resolution unit, planar configuration, YCbCr positioning
+                x.u16(off + 8);
+                break;
+            case 0x013E:  // white point
+                x.rationals(off, 2);
+                break;
+            case 0x013F: case 0x0214:  // primary chromaticities, reference black / white
+                x.rationals(off, 6);
+                break;
+            case 0x0211:  // YCbCr coefficients
+                x.rationals(off, 3);
+                break;
+            case 0x8769:  // Exif IFD pointer
+                x.u32(off + 8);
+                break;
+            default:
+                break;
         }
     }
-    return 0;
+    return found;
 }
 
 int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
@@ -49,7 +107,7 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
     h = JpegHeader();
     if (len < 4 || in[0] != 0xFF || in[1] != 0xD8) return LP_ERR_INVALID_IMAGE;
     size_t pos = 2;
-    bool have_sof = false;
+    bool have_sof = false, seen_app1 = false;
     while (pos + 4 <= len) {
         if (in[pos] != 0xFF) { pos++; continue; }
         uint8_t m = in[pos + 1];
@@ -122,8 +180,11 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
         } else if (m == 0xDD) {
             if (n >= 2) h.restart_interval = (p[0] << 8) | p[1];
         } else if (m == 0xE1) {
-            int o = exif_orientation(p, n);
-            if (o) h.orientation = o;
+            if (!seen_app1 && n > 6) {
+                int o = 0;
+                if (exif_orientation_opencv(p + 6, n - 6, &o)) h.orientation = o;
+            }
+            seen_app1 = true;
         } else if (m == 0xDA) {
             if (!have_sof || n < 1) return LP_ERR_INVALID_IMAGE;
             int ns = p[0];

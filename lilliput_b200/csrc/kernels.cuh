@@ -180,7 +180,10 @@ struct PngHeader {
     uint16_t trns_rgb[3] = {0, 0, 0};
     std::vector<PngSegment> idat;
     size_t idat_total = 0;
+    int orientation = 1;  // from an eXIf chunk in front of the first IDAT (OpenCV reads it like a JPEG's EXIF block)
 };
+// EXIF orientation of a TIFF block, read the way the reference's OpenCV reads it (jpeg_parse.cpp)
+bool exif_orientation_opencv(const uint8_t* tiff, size_t n, int* value);
 int png_parse(const uint8_t* data, size_t len, PngHeader* out);
 int png_extract_icc(const uint8_t* data, size_t len, uint8_t* dest, size_t dest_len);
 // cICP code points (primaries, transfer, matrix, full range) of the chunk libpng would report; 1 if found

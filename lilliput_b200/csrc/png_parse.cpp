@@ -17,12 +17,14 @@ static inline uint32_t be32(const uint8_t* p) {
 }
 static const uint8_t kPngSig[8] = {0x89, 0x50, 0x4E, 0x47, 0x0D, 0x0A, 0x1A, 0x0A};
 
+static bool png_chunk_crc_ok(const uint8_t* type, uint32_t n);
+
 int png_parse(const uint8_t* in, size_t len, PngHeader* out) {
     PngHeader& h = *out;
     h = PngHeader();
     if (len < 8 + 25 || memcmp(in, kPngSig, 8) != 0) return LP_ERR_INVALID_IMAGE;
     size_t pos = 8;
-    bool have_ihdr = false;
+    bool have_ihdr = false, have_exif = false;
     while (pos + 12 <= len) {
         const uint32_t n = be32(in + pos);
         const uint8_t* type = in + pos + 4;
@@ -45,6 +47,16 @@ int png_parse(const uint8_t* in, size_t len, PngHeader* out) {
                 memcpy(h.trns, d, h.ntrns);
             } else if (h.color_type == 2 && n >= 6) {
                 for (int i = 0; i < 3; i++) h.trns_rgb[i] = (uint16_t)((d[2 * i] << 8) | d[2 * i + 1]);
+            }
+        } else if (!memcmp(type, "eXIf", 4)) {
+            // OpenCV's PNG reader hands libpng's eXIf block (png_get_eXIf_1 after png_read_info, so only a chunk in
+            // front of the first IDAT) to the same ExifReader as a JPEG's APP1.  libpng keeps the first chunk whose
+            // CRC is good and which starts with a proper byte-order mark ("II" / "MM").
+            if (!have_exif && h.idat.empty() && n >= 2 && d[0] == d[1] && (d[0] == 'I' || d[0] == 'M') &&
+                png_chunk_crc_ok(type, n)) {
+                have_exif = true;
+                int o = 0;
+                if (exif_orientation_opencv(d, n, &o)) h.orientation = o;
             }
         } else if (!memcmp(type, "IDAT", 4)) {
             h.idat.push_back({pos + 8, (size_t)n});

@@ -238,3 +238,22 @@ def test_sdr_cicp_needs_sixteen_spare_bytes(lib, golden):
     o = _opts(FileType=".png", Width=w, Height=h, ResizeMethod=abi.ImageOpsFit, EncodeOptions={abi.PngCompression: 7})
     out = lib.transform(_with_cicp(src, 12, 13), o, dst_cap=len(plain) + 15)
     assert out == plain
+
+
+# ---- a PNG can carry an EXIF orientation too (eXIf chunk, read by OpenCV's PNG decoder like a JPEG's APP1), and
+#      Transform applies it on every iteration (ref ops.go:392)
+
+def test_png_exif_orientation_is_applied(lib, golden, oracle):
+    import struct
+    import zlib
+    src = _png_source(golden)
+    tiff = b"II*\0" + struct.pack("<IH", 8, 1) + struct.pack("<HHI", 0x0112, 3, 1) + struct.pack("<HH", 6, 0) + bytes(4)
+    chunk = struct.pack(">I", len(tiff)) + b"eXIf" + tiff + struct.pack(">I", zlib.crc32(b"eXIf" + tiff))
+    at = 8 + 12 + struct.unpack(">I", src[8:12])[0]
+    turned = src[:at] + chunk + src[at:]
+    w, h, _, o = lib.header(turned)
+    assert (w, h, o) == (*_dims(lib, src), 6)
+    plain = oracle.png_decode(lib.transform(src, _opts(FileType=".png", ResizeMethod=abi.ImageOpsNoResize)))
+    out = oracle.png_decode(lib.transform(turned, _opts(FileType=".png", ResizeMethod=abi.ImageOpsNoResize)))
+    assert out.shape[:2] == (w, h)
+    assert np.array_equal(out, np.rot90(plain, k=-1))          # orientation 6 = 90 degrees clockwise

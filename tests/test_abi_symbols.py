@@ -104,8 +104,15 @@ def test_jpeg_header_and_cicp_helpers(golden):
     assert l.opencv_decoder_get_pixel_type(d) == 16
     l.opencv_decoder_release(d)
     # cICP insert + read back (ref opencv.cpp:413-464, png_cicp_test.go)
-    png = bytearray(b"\x89PNG\r\n\x1a\n" + b"\x00\x00\x00\x0dIHDR" + bytes(13) + bytes(4) +
-                    b"\x00\x00\x00\x00IEND\xaeB`\x82")
+    # a well-formed 1x1 gray PNG: the reader follows libpng (tests/test_host_icc.py) and reports nothing for a
+    # file whose header part png_read_info would refuse
+    import struct
+    import zlib
+
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body))
+    png = bytearray(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 1, 1, 8, 0, 0, 0, 0)) +
+                    chunk(b"IDAT", zlib.compress(b"\x00\x7f")) + chunk(b"IEND", b""))
     cap = len(png) + 32
     arr = (C.c_uint8 * cap)(*png)
     l.opencv_png_insert_cicp.restype = C.c_size_t

@@ -818,6 +818,9 @@ struct GifAnimationInfo giflib_decoder_get_animation_info(const giflib_decoder d
         }
     }
     if (!found_gcb) {
+        // the reference's stand-in here is a zero-initialised GraphicsControlBlock (giflib.cpp:1331), whose
+        // TransparentColor 0 is not NO_TRANSPARENT_COLOR: the colour comes out with alpha 0
+        first_gcb.transparent = 0;
         uint8_t R, G, B, A;
         background_color(r, first_gcb, &R, &G, &B, &A);
         info.bg_red = R; info.bg_green = G; info.bg_blue = B; info.bg_alpha = A;

@@ -24,29 +24,69 @@ int png_parse(const uint8_t* in, size_t len, PngHeader* out) {
     h = PngHeader();
     if (len < 8 + 25 || memcmp(in, kPngSig, 8) != 0) return LP_ERR_INVALID_IMAGE;
     size_t pos = 8;
-    bool have_ihdr = false, have_exif = false;
+    bool have_ihdr = false, have_exif = false, have_plte = false;
     while (pos + 12 <= len) {
         const uint32_t n = be32(in + pos);
         const uint8_t* type = in + pos + 4;
         const uint8_t* d = in + pos + 8;
         if (pos + 12 + (size_t)n > len) break;  // truncated chunk: keep what was seen
-        if (!memcmp(type, "IHDR", 4) && n >= 13) {
-            h.width = (int)be32(d);
-            h.height = (int)be32(d + 4);
-            h.bit_depth = d[8];
-            h.color_type = d[9];
+        // Header chunks are taken the way libpng 1.6.47 takes them for the reference (png_read_info under OpenCV's
+        // PngDecoder::readHeader; pinned by tests/test_host_png_header.py): what it refuses, readHeader refuses.
+        if (h.idat.empty()) {  // everything in front of the image data is read by png_read_info
+            for (int i = 0; i < 4; i++)
+                if (!((type[i] >= 'A' && type[i] <= 'Z') || (type[i] >= 'a' && type[i] <= 'z'))) return LP_ERR_INVALID_IMAGE;
+            if (type[2] & 0x20) return LP_ERR_INVALID_IMAGE;  // reserved bit: "bad header (invalid type)"
+            if (!(type[0] & 0x20) && memcmp(type, "IHDR", 4) && memcmp(type, "PLTE", 4) && memcmp(type, "IDAT", 4))
+                return LP_ERR_INVALID_IMAGE;  // IEND out of place, or a critical chunk nobody knows
+        }
+        if (!h.idat.empty() && memcmp(type, "IDAT", 4) && memcmp(type, "IEND", 4)) {
+            // behind the first IDAT only more image data and the end matter to this parser (the header is complete)
+        } else if (!memcmp(type, "IHDR", 4)) {
+            if (have_ihdr || pos != 8 || n != 13 || !png_chunk_crc_ok(type, n)) return LP_ERR_INVALID_IMAGE;
+            const uint32_t w = be32(d), hh = be32(d + 4);
+            const int bd = d[8], ct = d[9];
+            if (w == 0 || hh == 0 || w > 1000000u || hh > 1000000u) return LP_ERR_INVALID_IMAGE;  // png_check_IHDR, default user limits
+            if (bd != 1 && bd != 2 && bd != 4 && bd != 8 && bd != 16) return LP_ERR_INVALID_IMAGE;
+            if (ct == 1 || ct == 5 || ct > 6) return LP_ERR_INVALID_IMAGE;
+            if ((ct == 3 && bd > 8) || ((ct == 2 || ct == 4 || ct == 6) && bd < 8)) return LP_ERR_INVALID_IMAGE;
+            if (d[10] != 0 || d[11] != 0 || d[12] > 1) return LP_ERR_INVALID_IMAGE;
+            h.width = (int)w;
+            h.height = (int)hh;
+            h.bit_depth = bd;
+            h.color_type = ct;
             h.interlace = d[12];
             have_ihdr = true;
+        } else if (!have_ihdr) {
+            return LP_ERR_INVALID_IMAGE;  // "Missing IHDR before ..."
         } else if (!memcmp(type, "PLTE", 4)) {
-            h.npal = (int)std::min<uint32_t>(n / 3, 256);
-            memcpy(h.palette, d, (size_t)h.npal * 3);
+            if (!h.idat.empty() || !(h.color_type & 2)) {
+                // after the image data, or in a grayscale image: skipped
+            } else if (h.color_type == 3) {
+                if (have_plte || n > 3 * 256 || n % 3 || n == 0 || !png_chunk_crc_ok(type, n)) return LP_ERR_INVALID_IMAGE;
+                have_plte = true;
+                h.npal = (int)std::min<uint32_t>(n / 3, 1u << h.bit_depth);  // entries past 2^depth are dropped
+                memcpy(h.palette, d, (size_t)h.npal * 3);
+            } else if (!have_plte && !(n > 3 * 256 || n % 3)) {
+                if (n == 0) return LP_ERR_INVALID_IMAGE;  // "Invalid palette"
+                have_plte = true;  // a suggested palette: nothing is decoded with it, but tRNS may not follow... (see below)
+            }
         } else if (!memcmp(type, "tRNS", 4)) {
-            h.has_trns = true;
-            if (h.color_type == 3) {
-                h.ntrns = (int)std::min<uint32_t>(n, 256);
-                memcpy(h.trns, d, h.ntrns);
-            } else if (h.color_type == 2 && n >= 6) {
-                for (int i = 0; i < 3; i++) h.trns_rgb[i] = (uint16_t)((d[2 * i] << 8) | d[2 * i + 1]);
+            // kept only in front of the image data, once, with a good CRC and the length its colour type asks for
+            if (h.idat.empty() && !h.has_trns && png_chunk_crc_ok(type, n)) {
+                if (h.color_type == 3) {
+                    if (have_plte && n >= 1 && n <= (uint32_t)h.npal && n <= 256) {
+                        h.has_trns = true;
+                        h.ntrns = (int)n;
+                        memcpy(h.trns, d, h.ntrns);
+                    }
+                } else if (h.color_type == 2) {
+                    if (n == 6) {
+                        h.has_trns = true;
+                        for (int i = 0; i < 3; i++) h.trns_rgb[i] = (uint16_t)((d[2 * i] << 8) | d[2 * i + 1]);
+                    }
+                } else if (h.color_type == 0) {
+                    if (n == 2) h.has_trns = true;
+                }
             }
         } else if (!memcmp(type, "eXIf", 4)) {
             // OpenCV's PNG reader hands libpng's eXIf block (png_get_eXIf_1 after png_read_info, so only a chunk in
@@ -59,6 +99,7 @@ int png_parse(const uint8_t* in, size_t len, PngHeader* out) {
                 if (exif_orientation_opencv(d, n, &o)) h.orientation = o;
             }
         } else if (!memcmp(type, "IDAT", 4)) {
+            if (h.idat.empty() && h.color_type == 3 && !have_plte) return LP_ERR_INVALID_IMAGE;  // "Missing PLTE before IDAT"
             h.idat.push_back({pos + 8, (size_t)n});
             h.idat_total += n;
         } else if (!memcmp(type, "IEND", 4)) {

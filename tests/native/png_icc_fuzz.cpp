@@ -1,10 +1,10 @@
 // ASan + UBSan fuzz of the host-side iCCP / cICP extraction (lilliput_b200/csrc/png_parse.cpp: png_extract_icc, its
-// zlib inflater, png_extract_cicp) on mutated PNGs, exact-size heap buffers on both sides.  CPU only.  Seeds: any PNG files, e.g. the
+// zlib inflater, png_extract_cicp) and of the PNG header parser (png_parse, incl. the eXIf orientation reader) on mutated PNGs, exact-size heap buffers on both sides.  CPU only.  Seeds: any PNG files, e.g. the
 // cases of tests/test_host_icc.py written out one per file.  Build and run:
 //   nvcc -O1 -g -std=c++17 -x cu -Xcompiler -fsanitize=address,-fsanitize=undefined,-fno-sanitize-recover=undefined \
 //        -Iinclude -Ililliput_b200/csrc -c lilliput_b200/csrc/png_parse.cpp -o /tmp/png_parse_asan.o
-//   g++ -O1 -g -std=c++17 -fsanitize=address,undefined tests/native/png_icc_fuzz.cpp /tmp/png_parse_asan.o \
-//        -o /tmp/png_icc_fuzz -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+//   nvcc -O1 -g -std=c++17 -x cu -Xcompiler -fsanitize=address,-fsanitize=undefined -Iinclude -Ililliput_b200/csrc \
+//        tests/native/png_icc_fuzz.cpp /tmp/png_parse_asan.o /tmp/jpeg_parse_asan.o -o /tmp/png_icc_fuzz   (jpeg_parse.cpp built like png_parse.cpp: the EXIF reader lives there)
 //   /tmp/png_icc_fuzz 400000 seeds/*
 // Round 1: 400 000 mutants of 100 seed files (iCCP and cICP cases), 8 159 of them yielding a profile, no report.
 #include <cstdio>
@@ -13,10 +13,7 @@
 #include <cstring>
 #include <vector>
 #include <string>
-namespace lp {
-int png_extract_icc(const uint8_t* in, size_t len, uint8_t* dest, size_t dest_len);
-int png_extract_cicp(const uint8_t* in, size_t len, uint8_t* out4);
-}
+#include "kernels.cuh"  // lp::PngHeader, png_parse, png_extract_icc, png_extract_cicp
 static uint64_t s = 88172645463325252ull;
 static uint32_t rnd() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_t)(s >> 11); }
 int main(int argc, char** argv) {
@@ -44,6 +41,8 @@ int main(int argc, char** argv) {
         uint8_t* four = (uint8_t*)malloc(4);
         if (lp::png_extract_cicp(in, d.size(), four)) sink += four[0] + four[3];
         free(four);
+        lp::PngHeader ph;
+        if (lp::png_parse(in, d.size(), &ph) == 0) sink += (unsigned)ph.width + ph.orientation + ph.idat.size();
         hits += n > 0;
         free(in); free(out);
     }

@@ -147,7 +147,9 @@ def test_hostile_headers_are_refused_not_fatal():
         pass
     from tests.png_writer import write_png
     png = bytearray(write_png(np.zeros((2, 2, 3), np.int64), 2, 8))
-    png[16:24] = (60000).to_bytes(4, "big") + (60000).to_bytes(4, "big")  # IHDR width, height (CRC not checked here)
+    png[16:24] = (60000).to_bytes(4, "big") + (60000).to_bytes(4, "big")  # IHDR width, height ...
+    import zlib
+    png[29:33] = zlib.crc32(bytes(png[12:29])).to_bytes(4, "big")         # ... with its CRC put right (a bad one is ErrInvalidImage)
     with pytest.raises(abi.LilliputError) as e:
         lib.decode(bytes(png))
     assert e.value.code == abi.LP_ERR_BUF_TOO_SMALL

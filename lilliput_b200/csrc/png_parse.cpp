@@ -29,7 +29,13 @@ int png_parse(const uint8_t* in, size_t len, PngHeader* out) {
         const uint32_t n = be32(in + pos);
         const uint8_t* type = in + pos + 4;
         const uint8_t* d = in + pos + 8;
-        if (pos + 12 + (size_t)n > len) break;  // truncated chunk: keep what was seen
+        if (pos + 12 + (size_t)n > len) {
+            // OpenCV's PngDecoder::readHeader pulls in whole chunks up to and including the first IDAT: a file that
+            // ends before that chunk is complete is refused at the header.  Behind it: keep what was seen, the
+            // decode reports the short stream.
+            if (h.idat.empty()) return LP_ERR_INVALID_IMAGE;
+            break;
+        }
         // Header chunks are taken the way libpng 1.6.47 takes them for the reference (png_read_info under OpenCV's
         // PngDecoder::readHeader; pinned by tests/test_host_png_header.py): what it refuses, readHeader refuses.
         if (h.idat.empty()) {  // everything in front of the image data is read by png_read_info
@@ -108,6 +114,7 @@ int png_parse(const uint8_t* in, size_t len, PngHeader* out) {
         pos += 12 + (size_t)n;
     }
     if (!have_ihdr || h.width < 1 || h.height < 1) return LP_ERR_INVALID_IMAGE;
+    if (h.idat.empty()) return LP_ERR_INVALID_IMAGE;  // the data ended before a first IDAT chunk was complete
     switch (h.color_type) {
         case 0: h.src_channels = 1; break;
         case 2: h.src_channels = 3; break;

@@ -1,7 +1,7 @@
 """CPU: what opencv_decoder_read_header reports for a PNG (width, height, pixel type, orientation, or a refusal) --
 product (png_parse.cpp, host-only) against the live reference (libpng 1.6.47 under OpenCV's PngDecoder) on the
 golden files and on seeded, structured mutants: IHDR fields rewritten (CRC fixed), chunks renamed, tRNS / PLTE
-chunks of every length inserted in every position.  Full agreement is asserted, refusals included.  (Chunk LENGTH
+chunks of every length inserted in every position, files cut short anywhere.  Full agreement is asserted, refusals included.  (Chunk LENGTH
 fields are left alone: a damaged length makes the reference spend seconds per file.)"""
 import random
 import struct
@@ -50,8 +50,10 @@ def test_png_header_matches_the_reference(ref_lib, golden):
     for it in range(6000):
         name, s = rnd.choice(pool)
         b = bytearray(s)
-        mode = rnd.randrange(5)
-        if mode == 0:        # bit depth / colour type / compression / filter / interlace
+        mode = rnd.randrange(6)
+        if mode == 5:        # the file simply ends somewhere
+            b = b[:rnd.randrange(8, len(b))]
+        elif mode == 0:      # bit depth / colour type / compression / filter / interlace
             f = rnd.choice([24, 25, 26, 27, 28])
             b[f] = rnd.choice([0, 1, 2, 3, 4, 5, 6, 7, 8, 16, 32]) if f < 26 else rnd.choice([0, 1, 2])
             _fix_crc(b, 8)

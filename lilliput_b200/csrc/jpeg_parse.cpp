@@ -114,6 +114,9 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
         if (m == 0xFF) { pos++; continue; }
         if (m == 0xD9) break;
         if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { pos += 2; continue; }
+        if (m == 0x00) { pos += 2; continue; }  // FF 00 between segments is not a marker: libjpeg skips it as garbage
+        // marker codes libjpeg's read_markers has no case for ("Unsupported marker type"), and JPG
+        if ((m >= 0x02 && m <= 0xBF) || (m >= 0xF0 && m <= 0xFD) || m == 0xC8) return LP_ERR_INVALID_IMAGE;
         size_t seg = ((size_t)in[pos + 2] << 8) | in[pos + 3];
         if (seg < 2 || pos + 2 + seg > len) return LP_ERR_INVALID_IMAGE;
         const uint8_t* p = in + pos + 4;
@@ -144,13 +147,17 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
                 n -= 17 + total;
             }
         } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
-            if (n < 6) return LP_ERR_INVALID_IMAGE;
+            if (n < 6 || have_sof) return LP_ERR_INVALID_IMAGE;  // a second frame header: "duplicate SOF"
             h.progressive = (m == 0xC2);
             int prec = p[0];
             h.height = (p[1] << 8) | p[2];
             h.width = (p[3] << 8) | p[4];
             h.ncomp = p[5];
-            if (h.width < 1 || h.height < 1) return LP_ERR_INVALID_IMAGE;
+            // get_sof / initial_setup of the reference's libjpeg-turbo: empty image, segment length that does not fit
+            // the component count, more than 10 components, a dimension over 65500, a precision other than 8 or 12
+            if (h.width < 1 || h.height < 1 || h.ncomp < 1) return LP_ERR_INVALID_IMAGE;
+            if (n != (size_t)(6 + 3 * h.ncomp) || h.ncomp > 10) return LP_ERR_INVALID_IMAGE;
+            if (h.width > 65500 || h.height > 65500 || (prec != 8 && prec != 12)) return LP_ERR_INVALID_IMAGE;
             if (prec != 8 || (h.ncomp != 1 && h.ncomp != 3) || n < (size_t)(6 + 3 * h.ncomp)) {
                 have_sof = true;  // dimensions known, but not decodable here
                 h.ncomp = h.ncomp == 1 ? 1 : 3;
@@ -188,7 +195,16 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
         } else if (m == 0xDA) {
             if (!have_sof || n < 1) return LP_ERR_INVALID_IMAGE;
             int ns = p[0];
-            if (ns < 1 || ns > 3 || n < (size_t)(1 + 2 * ns + 3)) return LP_ERR_INVALID_IMAGE;
+            if (ns < 1 || ns > 3 || n != (size_t)(1 + 2 * ns + 3)) return LP_ERR_INVALID_IMAGE;  // get_sos: exact length
+            if (h.comp[0].h >= 1) {  // frame components known: every selector names one of them, none twice
+                for (int i = 0; i < ns; i++) {
+                    bool known = false;
+                    for (int j = 0; j < h.ncomp; j++) known = known || h.comp[j].id == p[1 + 2 * i];
+                    if (!known) return LP_ERR_INVALID_IMAGE;  // "Invalid component ID in SOS"
+                    for (int k = 0; k < i; k++)
+                        if (p[1 + 2 * k] == p[1 + 2 * i]) return LP_ERR_INVALID_IMAGE;
+                }
+            }
             if (ns != h.ncomp) h.supported = false;  // one scan per component: serial multi-scan path
             if (h.progressive || ns != h.ncomp) {
                 bool ok = true;

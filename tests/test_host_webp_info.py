@@ -47,3 +47,41 @@ def test_webp_container_fields_match_the_reference(ref_lib):
             one_sided += (p is None) != (r is None)
     assert both > 1000
     assert one_sided < 4000 * 0.03          # the acceptance sets stay close (1.2 % when this was written)
+
+
+def _icc(lib, b):
+    import ctypes as C
+    l = lib.l
+    l.opencv_mat_create_from_data.restype = C.c_void_p
+    l.opencv_mat_create_from_data.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    l.webp_decoder_create.restype = C.c_void_p
+    l.webp_decoder_create.argtypes = [C.c_void_p]
+    l.webp_decoder_get_icc.restype = C.c_size_t
+    l.webp_decoder_get_icc.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    l.webp_decoder_release.argtypes = [C.c_void_p]
+    l.opencv_mat_release.argtypes = [C.c_void_p]
+    a = np.frombuffer(b, dtype=np.uint8).copy()
+    m = l.opencv_mat_create_from_data(a.size, 1, 0, a.ctypes.data, a.size)
+    d = l.webp_decoder_create(m)
+    if not d:
+        l.opencv_mat_release(m)
+        return None
+    big, small = C.create_string_buffer(32768), C.create_string_buffer(16)
+    n, n_small = l.webp_decoder_get_icc(d, big, 32768), l.webp_decoder_get_icc(d, small, 16)
+    l.webp_decoder_release(d)
+    l.opencv_mat_release(m)
+    return big.raw[:n], n_small
+
+
+def test_webp_icc_bytes_match_the_reference(ref_lib):
+    """webp_decoder_get_icc (ref webp.cpp:136-160): the ICCP chunk's bytes, and what a 16-byte buffer gets."""
+    product = abi.load_cuda()
+    g = webp_golden()
+    with_icc = 0
+    for k in g.files:
+        a = g[k]
+        if k.startswith("webp_") and a.dtype == np.uint8 and a.ndim == 1 and a.size >= 16:
+            want = _icc(ref_lib, a.tobytes())
+            assert _icc(product, a.tobytes()) == want, k
+            with_icc += bool(want and len(want[0]))
+    assert with_icc >= 2

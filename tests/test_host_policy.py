@@ -257,3 +257,18 @@ def test_png_exif_orientation_is_applied(lib, golden, oracle):
     out = oracle.png_decode(lib.transform(turned, _opts(FileType=".png", ResizeMethod=abi.ImageOpsNoResize)))
     assert out.shape[:2] == (w, h)
     assert np.array_equal(out, np.rot90(plain, k=-1))          # orientation 6 = 90 degrees clockwise
+
+
+@pytest.mark.parametrize("value", [0, 9, 300, 65535])
+def test_out_of_range_exif_orientation_is_reported_and_does_nothing(lib, oracle, value):
+    """The reader passes the EXIF word through unvalidated (tests/test_host_exif.py); OrientationTransform then
+    has no case for it (ref opencv.cpp:217-221) and the frame is encoded as decoded."""
+    import struct
+    from lilliput_b200.synth import synth_image
+    base = oracle.jpeg_encode(synth_image(3, 40, 24, 3), 85)
+    tiff = b"II*\0" + struct.pack("<IH", 8, 1) + struct.pack("<HHI", 0x0112, 3, 1) + struct.pack("<HH", value, 0) + bytes(4)
+    seg = b"Exif\0\0" + tiff
+    tagged = base[:2] + b"\xff\xe1" + struct.pack(">H", len(seg) + 2) + seg + base[2:]
+    assert lib.header(tagged) == (40, 24, 16, value)
+    o = _opts(FileType=".png", ResizeMethod=abi.ImageOpsNoResize, NormalizeOrientation=True)
+    assert lib.transform(tagged, o) == lib.transform(base, o)

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "kernels.cuh"
+#include "jpeg_std_tables.h"
 #include "lilliput_b200.h"
 
 namespace lp {
@@ -107,7 +108,7 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
     h = JpegHeader();
     if (len < 4 || in[0] != 0xFF || in[1] != 0xD8) return LP_ERR_INVALID_IMAGE;
     size_t pos = 2;
-    bool have_sof = false, seen_app1 = false;
+    bool have_sof = false, seen_app1 = false, undecodable = false;
     while (pos + 4 <= len) {
         if (in[pos] != 0xFF) { pos++; continue; }
         uint8_t m = in[pos + 1];
@@ -170,8 +171,11 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
                 h.comp[i].h = p[7 + 3 * i] >> 4;
                 h.comp[i].v = p[7 + 3 * i] & 15;
                 h.comp[i].tq = p[8 + 3 * i];
-                if (h.comp[i].h < 1 || h.comp[i].h > 4 || h.comp[i].v < 1 || h.comp[i].v > 4 || h.comp[i].tq > 3)
-                    return LP_ERR_INVALID_IMAGE;
+                if (h.comp[i].h < 1 || h.comp[i].h > 4 || h.comp[i].v < 1 || h.comp[i].v > 4) return LP_ERR_INVALID_IMAGE;
+                if (h.comp[i].tq > 3) {  // libjpeg reads such a header and fails when the decode looks for the table
+                    h.comp[i].tq = 0;
+                    undecodable = true;
+                }
                 h.maxh = h.comp[i].h > h.maxh ? h.comp[i].h : h.maxh;
                 h.maxv = h.comp[i].v > h.maxv ? h.comp[i].v : h.maxv;
             }
@@ -215,6 +219,20 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
                 }
                 h.multiscan = ok;
             }
+            // libjpeg-turbo fills the table slots 0 and 1 that no DHT segment defined with the Annex K tables when the
+            // decode starts (jinit_huff_decoder -> std_huff_tables: Motion-JPEG frames are written without DHT), so a
+            // file that lost or never had them decodes in the reference; slots 2 and 3 stay undefined
+            for (int tc = 0; tc < 2; tc++)
+                for (int th = 0; th < 2; th++)
+                    if (!h.huff_present[tc][th]) {
+                        const uint8_t* bits = tc == 0 ? (th == 0 ? kDcLBits : kDcCBits) : (th == 0 ? kAcLBits : kAcCBits);
+                        const uint8_t* vals = tc == 0 ? kDcVals : (th == 0 ? kAcLVals : kAcCVals);
+                        int total = 0;
+                        for (int i = 0; i <= 16; i++) { h.huff_bits[tc][th][i] = bits[i]; total += i ? bits[i] : 0; }
+                        memset(h.huff_vals[tc][th], 0, 256);
+                        memcpy(h.huff_vals[tc][th], vals, total);
+                        h.huff_present[tc][th] = true;
+                    }
             for (int i = 0; i < ns && h.supported; i++) {
                 int ci = -1;
                 for (int j = 0; j < h.ncomp; j++)
@@ -223,9 +241,15 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
                 h.comp[ci].td = p[2 + 2 * i] >> 4;
                 h.comp[ci].ta = p[2 + 2 * i] & 15;
                 if (h.comp[ci].td > 3 || h.comp[ci].ta > 3 || !h.huff_present[0][h.comp[ci].td] ||
-                    !h.huff_present[1][h.comp[ci].ta] || !h.qt_present[h.comp[ci].tq])
-                    return LP_ERR_INVALID_IMAGE;
+                    !h.huff_present[1][h.comp[ci].ta] || !h.qt_present[h.comp[ci].tq]) {
+                    // a table the scan needs was never defined (or its segment was lost to damage): the reference's
+                    // header read succeeds and its decode fails ("... table 0x%02x was not defined"); same here
+                    h.comp[ci].td = h.comp[ci].ta = 0;
+                    undecodable = true;
+                    break;
+                }
             }
+            if (undecodable) h.supported = h.multiscan = false;  // read_data refuses on the host: ErrDecodingFailed
             h.scan_offset = pos + 2 + seg;
             // upper bound of the entropy-coded segment: up to the last EOI if there is one
             size_t end = len;

@@ -272,3 +272,38 @@ def test_out_of_range_exif_orientation_is_reported_and_does_nothing(lib, oracle,
     assert lib.header(tagged) == (40, 24, 16, value)
     o = _opts(FileType=".png", ResizeMethod=abi.ImageOpsNoResize, NormalizeOrientation=True)
     assert lib.transform(tagged, o) == lib.transform(base, o)
+
+
+@pytest.mark.parametrize("damage", ["lost_quantisation_table", "table_selector_out_of_range"])
+def test_jpeg_with_a_missing_table_reads_its_header_and_fails_to_decode(lib, oracle, damage):
+    """libjpeg checks tables when the decode starts, not when the header is read: Header() succeeds and DecodeTo
+    is what fails (ErrDecodingFailed, ref opencv.go:829-831) -- not ErrInvalidImage from the header."""
+    from lilliput_b200.synth import synth_image
+    b = bytearray(oracle.jpeg_encode(synth_image(3, 40, 24, 3), 85))
+    if damage == "lost_quantisation_table":
+        b[b.find(b"\xff\xdb")] = 0x3F                  # the marker's FF is gone: the segment is skipped as garbage
+    else:
+        b[b.find(b"\xff\xc0") + 12] = 151              # Tq of the first component
+    assert lib.header(bytes(b)) == (40, 24, 16, 1)
+    with pytest.raises(abi.LilliputError) as e:
+        lib.decode(bytes(b))
+    assert e.value.code == -2
+    with pytest.raises(abi.LilliputError) as e:
+        lib.transform(bytes(b), _opts(FileType=".jpeg", Width=16, Height=16, ResizeMethod=abi.ImageOpsFit))
+    assert e.value.code == -2
+
+
+@pytest.mark.parametrize("lost", ["first", "all"])
+def test_jpeg_without_huffman_tables_decodes_with_the_annex_k_tables(lib, oracle, lost):
+    """Motion-JPEG frames are written without DHT segments; libjpeg-turbo fills the undefined slots 0 and 1 with the
+    Annex K tables when the decode starts (jdhuff.c: jinit_huff_decoder -> std_huff_tables), so such a file -- or
+    one whose DHT was lost to damage -- decodes in the reference.  The source here was encoded with those tables."""
+    from lilliput_b200.synth import synth_image
+    base = oracle.jpeg_encode(synth_image(3, 40, 24, 3), 85)
+    b = bytearray(base)
+    at = b.find(b"\xff\xc4")
+    while at >= 0:
+        b[at] = 0x3F                                   # no longer a marker: skipped as garbage
+        at = b.find(b"\xff\xc4", at + 1) if lost == "all" else -1
+    assert lib.header(bytes(b)) == (40, 24, 16, 1)
+    assert np.array_equal(lib.decode(bytes(b)), oracle.jpeg_decode(base)[0])

@@ -133,7 +133,7 @@ class ClockSampler:
 
     def __init__(self, index, uuid=None):
         self.index = index
-        self.uuid = uuid
+        self.uuid = uuid[4:] if uuid and str(uuid).startswith("GPU-") else uuid   # bare UUID; "GPU-" is added where used
         self.nvml_rows = []       # (t, sm_mhz, reasons bit mask)
         self.smi_rows = []        # (t, sm_mhz, max_mhz, [reason names])
         self.windows = []

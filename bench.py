@@ -187,7 +187,9 @@ class ClockSampler:
         except Exception:
             pass
         try:
-            sel = f"--id={self.uuid and 'GPU-' + str(self.uuid) or self.index}"
+            # the plain index is what nvidia-smi counts by unless CUDA_VISIBLE_DEVICES renumbers the devices
+            by_uuid = self.uuid and os.environ.get("CUDA_VISIBLE_DEVICES")
+            sel = f"--id={'GPU-' + str(self.uuid) if by_uuid else self.index}"
             self.proc = subprocess.Popen(
                 ["nvidia-smi", sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)

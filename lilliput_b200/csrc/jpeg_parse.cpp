@@ -133,6 +133,7 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
                 p += need;
                 n -= need;
             }
+            if (n != 0) return LP_ERR_INVALID_IMAGE;  // get_dqt: "Bogus marker length"
         } else if (m == 0xC4) {
             while (n >= 17) {
                 int tc = p[0] >> 4, th = p[0] & 15;
@@ -147,6 +148,7 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
                 p += 17 + total;
                 n -= 17 + total;
             }
+            if (n != 0) return LP_ERR_INVALID_IMAGE;  // get_dht: "Bogus marker length"
         } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
             if (n < 6 || have_sof) return LP_ERR_INVALID_IMAGE;  // a second frame header: "duplicate SOF"
             h.progressive = (m == 0xC2);
@@ -189,7 +191,8 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
         } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
             return LP_ERR_UNSUPPORTED;  // lossless / differential / arithmetic
         } else if (m == 0xDD) {
-            if (n >= 2) h.restart_interval = (p[0] << 8) | p[1];
+            if (n != 2) return LP_ERR_INVALID_IMAGE;  // get_dri: the segment is exactly 4 bytes
+            h.restart_interval = (p[0] << 8) | p[1];
         } else if (m == 0xE1) {
             if (!seen_app1 && n > 6) {
                 int o = 0;

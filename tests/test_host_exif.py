@@ -141,8 +141,8 @@ def test_exif_mutants_agree_whenever_both_accept(libs, oracle, capfd, seed):
     """2 x 3 000 mutants of the files above (bytes flipped in the first 90 bytes or anywhere before the frame header,
     truncation).  Whenever both libraries take the header, width, height, pixel type and orientation are equal.
     Which damaged headers libjpeg refuses, and when (header or decode), is mirrored for the common cases (unknown
-    marker codes, frame / scan header lengths, precision, component selectors, tables that were never defined):
-    0.6 % of the mutants are taken by one side only; the share is bounded below so that it cannot grow unnoticed."""
+    marker codes, frame / scan / table segment lengths, precision, component selectors, tables that were never defined):
+    under 0.1 % of the mutants are taken by one side only; the share is bounded below so that it cannot grow unnoticed."""
     product, reference = libs
     seeds = list(_cases(oracle).values())
     rnd = random.Random(seed)
@@ -166,7 +166,7 @@ def test_exif_mutants_agree_whenever_both_accept(libs, oracle, capfd, seed):
         else:
             one_sided += (p[0] == "error") != (r[0] == "error")
     assert both > 1500
-    assert one_sided < 3000 * 0.015
+    assert one_sided < 3000 * 0.005
     capfd.readouterr()
 
 

@@ -1,7 +1,7 @@
 // ASan + UBSan fuzz of the JPEG header parser incl. the OpenCV-style EXIF reader (lilliput_b200/csrc/jpeg_parse.cpp:
 // jpeg_parse_header, exif_orientation_opencv) on mutated files, exact-size heap input.  CPU only.  Seeds: the files of
 // tests/test_host_exif.py written out one per file.  Build like png_icc_fuzz.cpp (nvcc -x cu, same sanitizer flags),
-// link with the sanitized jpeg_parse object.  Round 1: 600 000 mutants of 66 seeds, 358 373 headers accepted, no report.
+// link with the sanitized jpeg_parse object.  Round 1: 600 000 mutants of 66 seeds, 399 202 headers accepted, no report (re-run on the last parser of the round).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -1,0 +1,708 @@
+// inflate_core.h -- warp-parallel DEFLATE (RFC 1951) decoding of ONE zlib stream by ONE warp.
+//
+// Replaces the bit-serial inflate that libpng/zlib-ng run for the reference's PNG decode
+// (ref opencv.cpp:166-171 -> cv::PngDecoder::readData -> png_read_image -> inflate).  The result is the
+// inflated byte string, identical to zlib's; only the schedule differs.
+//
+// A DEFLATE block is one serial bit string, but its prefix code self-synchronises: a decoder started at
+// a wrong bit falls onto true symbol boundaries within a few symbols, and -- unlike JPEG -- the decoder
+// has no other state than the bit position.  So, per "window" of 32 x kSubBits bits of one block:
+//   pass A   lane i decodes the symbols that START in [P + i*S, P + (i+1)*S) from a guessed start
+//            (lane 0's start is exact), counting output bytes and matches;
+//   pass B   lane i re-decodes from lane i-1's exit position whenever that differs from the start it
+//            used, until nothing changes (exact by induction from lane 0; lanes behind an end-of-block
+//            or an invalid code are ignored);
+//   pass C   a prefix sum of the byte counts gives every lane its output position; literals are written
+//            to a shared-memory ring in parallel, matches are listed (in stream order, by a second
+//            prefix sum) and then copied one after another by the whole warp.
+// The ring is flushed to global memory in 16-byte vectors; matches that reach behind the ring read the
+// flushed bytes back.  Windows whose output would overrun half the ring are cut short (the write pass
+// takes a byte budget), so match-heavy streams degrade to "few symbols per window", never to an error.
+//
+// The same source compiles for the device (one warp = 32 threads, collectives = shuffles / ballots) and
+// for the host (LP_INF_HOST: lanes simulated by loops), so the CPU test-suite runs the exact control
+// flow of the kernel against zlib (tests/test_inflate_core.py); the GPU tests then only have to show
+// that the real warp reproduces the simulation.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#ifdef LP_INF_HOST
+#define LP_INF_FN static inline
+#define LP_INF_LANES(l) for (int l = 0; l < 32; l++)
+#else
+#define LP_INF_FN static __device__ __forceinline__
+#define LP_INF_LANES(l) for (int l = (int)(threadIdx.x & 31), _lp_once = 0; !_lp_once; _lp_once = 1)
+#endif
+
+namespace lpinf {
+
+constexpr uint32_t kSubBits = 512;             // bits per lane and window
+constexpr uint32_t kWinBits = 32 * kSubBits;
+constexpr uint32_t kInWords = kWinBits / 32 + 8;  // window + the bits a symbol / a refill may read past it
+constexpr uint32_t kRing = 16384, kRingMask = kRing - 1;
+constexpr uint32_t kCapT = kRing / 2;          // output bytes per window
+constexpr uint32_t kMaxMatches = kCapT / 3 + 8;  // a match is at least 3 bytes
+constexpr int kLitBits = 10, kDistBits = 8;
+
+// lane-private variable: one register on the device, 32 slots in the host simulation
+#ifdef LP_INF_HOST
+template <class T>
+struct LaneVar {
+    T v[32];
+    T& operator[](int l) { return v[l]; }
+    const T& operator[](int l) const { return v[l]; }
+};
+#else
+template <class T>
+struct LaneVar {
+    T v;
+    __device__ __forceinline__ T& operator[](int) { return v; }
+    __device__ __forceinline__ const T& operator[](int) const { return v; }
+};
+#endif
+
+// ---- warp collectives -------------------------------------------------------------------------------
+LP_INF_FN void wsync() {
+#ifndef LP_INF_HOST
+    __syncwarp();
+#endif
+}
+LP_INF_FN void shift_up(LaneVar<uint32_t>& out, const LaneVar<uint32_t>& in, uint32_t lane0) {
+#ifdef LP_INF_HOST
+    uint32_t prev = lane0;
+    for (int l = 0; l < 32; l++) {
+        const uint32_t cur = in[l];
+        out[l] = prev;
+        prev = cur;
+    }
+#else
+    const uint32_t t = __shfl_up_sync(0xffffffffu, in.v, 1);
+    out.v = (threadIdx.x & 31) ? t : lane0;
+#endif
+}
+LP_INF_FN uint32_t ballot(const LaneVar<uint32_t>& p) {
+#ifdef LP_INF_HOST
+    uint32_t m = 0;
+    for (int l = 0; l < 32; l++) m |= (p[l] ? 1u : 0u) << l;
+    return m;
+#else
+    return __ballot_sync(0xffffffffu, p.v != 0);
+#endif
+}
+LP_INF_FN uint32_t excl_scan(LaneVar<uint32_t>& out, const LaneVar<uint32_t>& in) {  // returns the total
+#ifdef LP_INF_HOST
+    uint32_t s = 0;
+    for (int l = 0; l < 32; l++) {
+        const uint32_t v = in[l];
+        out[l] = s;
+        s += v;
+    }
+    return s;
+#else
+    const int lane = threadIdx.x & 31;
+    uint32_t inc = in.v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    out.v = inc - in.v;
+    return __shfl_sync(0xffffffffu, inc, 31);
+#endif
+}
+LP_INF_FN uint32_t bcast(const LaneVar<uint32_t>& v, int src) {
+#ifdef LP_INF_HOST
+    return v[src];
+#else
+    return __shfl_sync(0xffffffffu, v.v, src);
+#endif
+}
+// lanes holding the same value as this lane (bit mask)
+LP_INF_FN void match_any(LaneVar<uint32_t>& out, const LaneVar<uint32_t>& in) {
+#ifdef LP_INF_HOST
+    for (int l = 0; l < 32; l++) {
+        uint32_t m = 0;
+        for (int k = 0; k < 32; k++) m |= (in[k] == in[l] ? 1u : 0u) << k;
+        out[l] = m;
+    }
+#else
+    out.v = __match_any_sync(0xffffffffu, in.v);
+#endif
+}
+LP_INF_FN uint32_t popc32(uint32_t x) {
+#ifdef LP_INF_HOST
+    return (uint32_t)__builtin_popcount(x);
+#else
+    return (uint32_t)__popc(x);
+#endif
+}
+LP_INF_FN uint32_t ffs32(uint32_t x) {  // 1-based, 0 for x == 0
+#ifdef LP_INF_HOST
+    return (uint32_t)__builtin_ffs((int)x);
+#else
+    return (uint32_t)__ffs((int)x);
+#endif
+}
+LP_INF_FN uint32_t brev32(uint32_t x) {
+#ifdef LP_INF_HOST
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+#else
+    return __brev(x);
+#endif
+}
+
+// ---- per-warp working set (shared memory on the device) -----------------------------------------------
+struct Match {
+    uint32_t q;   // absolute output position of the copy's first byte
+    uint32_t ld;  // (length << 16) | distance
+};
+
+// Lookup entries (32 bit):  bits 0..3 code length (0 = not a code of <= lookahead bits)
+//   literal/length table: bits 4..5 kind (0 literal, 1 end of block, 2 length, 3 invalid symbol 286/287),
+//                         bits 8..16 literal value or length base, bits 20..22 extra-bit count
+//   distance table:       bits 4..5 kind (0 distance, 3 invalid symbol 30/31), bits 8..22 base, bits 24..27 extra bits
+struct WarpShared {
+    alignas(16) uint8_t ring[kRing];
+    uint32_t inbuf[kInWords];
+    uint32_t lit[1 << kLitBits];
+    uint32_t dist[1 << kDistBits];
+    uint32_t cnt32[2][16];     // codes per length (lit, dist)
+    uint16_t first[2][17];     // canonical first code per length, for the long-code walk
+    uint16_t index[2][17];     // first sorted-symbol index per length
+    uint16_t lsym[288], dsym[32];
+    uint8_t lens[320];
+    uint16_t cl[128];          // code-length code lookahead (7 bits): (symbol << 4) | length
+};
+
+LP_INF_FN uint32_t lit_entry(uint32_t sym, uint32_t len) {
+    if (sym < 256) return len | (sym << 8);
+    if (sym == 256) return len | (1u << 4);
+    if (sym > 285) return len | (3u << 4);
+    const uint32_t ls = sym - 257;
+    uint32_t extra, base;
+    if (ls < 8) { extra = 0; base = 3 + ls; }
+    else if (ls == 28) { extra = 0; base = 258; }
+    else { extra = (ls - 4) >> 2; base = 3 + ((4 + (ls & 3)) << extra); }
+    return len | (2u << 4) | (base << 8) | (extra << 20);
+}
+LP_INF_FN uint32_t dist_entry(uint32_t sym, uint32_t len) {
+    if (sym > 29) return len | (3u << 4);
+    uint32_t extra, base;
+    if (sym < 4) { extra = 0; base = 1 + sym; }
+    else { extra = (sym - 2) >> 1; base = 1 + ((2 + (sym & 1)) << extra); }
+    return len | (base << 8) | (extra << 24);
+}
+
+// Canonical code (RFC 1951 3.2.2) of `n` code lengths -> lookahead table + long-code walk data.
+// t = 0: literal/length, t = 1: distance.  Returns 0, or 1 for an over-subscribed code (zlib: "invalid
+// code lengths set" / "invalid distances set"; incomplete codes are accepted like the earlier kernel did).
+LP_INF_FN int build_table(WarpShared& ws, int t, const uint8_t* lens, int n) {
+    uint32_t* look = t ? ws.dist : ws.lit;
+    uint16_t* sorted = t ? ws.dsym : ws.lsym;
+    const int look_bits = t ? kDistBits : kLitBits;
+    LP_INF_LANES(l) {
+        if (l < 16) ws.cnt32[t][l] = 0;
+    }
+    wsync();
+    // codes per length: lane l owns length l (n <= 288)
+    LP_INF_LANES(l) {
+        if (l >= 1 && l < 16) {
+            uint32_t c = 0;
+            for (int i = 0; i < n; i++) c += lens[i] == l;
+            ws.cnt32[t][l] = c;
+        }
+    }
+    wsync();
+    int over = 0;
+    LP_INF_LANES(l) {
+        if (l == 0) {
+            int left = 1;
+            uint32_t first = 0, index = 0;
+            for (int len = 1; len < 16; len++) {
+                left = (left << 1) - (int)ws.cnt32[t][len];
+                if (left < 0) over = 1;
+                ws.first[t][len] = (uint16_t)first;
+                ws.index[t][len] = (uint16_t)index;
+                index += ws.cnt32[t][len];
+                first = (first + ws.cnt32[t][len]) << 1;
+            }
+            ws.first[t][16] = (uint16_t)over;  // broadcast slot
+        }
+    }
+    wsync();
+    over = ws.first[t][16];
+    if (over) return 1;
+    // symbols sorted by (length, symbol): lane l places the symbols of length l+1 ... spread by length so
+    // that no two lanes write the same region (15 lengths, <= 288 symbols)
+    LP_INF_LANES(l) {
+        if (l >= 1 && l < 16) {
+            uint32_t at = ws.index[t][l];
+            for (int i = 0; i < n; i++)
+                if (lens[i] == l) sorted[at++] = (uint16_t)i;
+        }
+    }
+    wsync();
+    // lookahead entries, one canonical walk per entry (entries are spread over the lanes)
+    LP_INF_LANES(l) {
+        for (uint32_t j = (uint32_t)l; j < (1u << look_bits); j += 32) {
+            uint32_t code = 0, e = 0;
+            for (int len = 1; len <= look_bits; len++) {
+                code |= (j >> (len - 1)) & 1u;
+                const uint32_t c = ws.cnt32[t][len], f = ws.first[t][len];
+                if (code - f < c) {  // (unsigned: code >= f always holds on a valid walk)
+                    const uint32_t sym = sorted[ws.index[t][len] + (code - f)];
+                    e = t ? dist_entry(sym, (uint32_t)len) : lit_entry(sym, (uint32_t)len);
+                    break;
+                }
+                code <<= 1;
+            }
+            look[j] = e;
+        }
+    }
+    wsync();
+    return 0;
+}
+
+// LSB-first bit reader over the window buffer: `pos` counts bits from bit 0 of inbuf[0].
+struct Bits {
+    uint64_t acc;
+    uint32_t n;    // valid bits in acc
+    uint32_t wp;   // next word of inbuf
+    uint32_t pos;  // bit position of acc's bit 0
+};
+LP_INF_FN void bits_init(Bits& b, const uint32_t* inbuf, uint32_t pos) {
+    b.wp = pos >> 5;
+    b.acc = (uint64_t)inbuf[b.wp] >> (pos & 31);
+    b.n = 32 - (pos & 31);
+    b.wp++;
+    b.pos = pos;
+}
+LP_INF_FN void bits_fill(Bits& b, const uint32_t* inbuf) {  // afterwards n >= 32
+    if (b.n < 32) {
+        b.acc |= (uint64_t)inbuf[b.wp < kInWords ? b.wp : kInWords - 1] << b.n;
+        b.wp++;
+        b.n += 32;
+    }
+}
+LP_INF_FN void bits_drop(Bits& b, uint32_t k) {
+    b.acc >>= k;
+    b.n -= k;
+    b.pos += k;
+}
+LP_INF_FN uint32_t bits_get(Bits& b, const uint32_t* inbuf, uint32_t k) {  // k <= 16
+    bits_fill(b, inbuf);
+    const uint32_t v = (uint32_t)b.acc & ((1u << k) - 1u);
+    bits_drop(b, k);
+    return v;
+}
+
+// One code of table t at the reader; returns the lookup entry (length in bits 0..3 already consumed),
+// or 0 when the next bits are no code word.
+LP_INF_FN uint32_t decode_code(const WarpShared& ws, int t, Bits& b) {
+    bits_fill(b, ws.inbuf);
+    const int look_bits = t ? kDistBits : kLitBits;
+    uint32_t e = (t ? ws.dist : ws.lit)[(uint32_t)b.acc & ((1u << look_bits) - 1u)];
+    if (e & 15u) {
+        bits_drop(b, e & 15u);
+        return e;
+    }
+    // longer than the lookahead: canonical walk, bit by bit (rare)
+    uint32_t code = 0;
+    const uint32_t bitsv = (uint32_t)b.acc;
+    for (int len = 1; len < 16; len++) {
+        code |= (bitsv >> (len - 1)) & 1u;
+        const uint32_t c = ws.cnt32[t][len], f = ws.first[t][len];
+        if (code - f < c) {
+            const uint32_t sym = (t ? ws.dsym : ws.lsym)[ws.index[t][len] + (code - f)];
+            bits_drop(b, (uint32_t)len);
+            return t ? dist_entry(sym, (uint32_t)len) : lit_entry(sym, (uint32_t)len);
+        }
+        code <<= 1;
+    }
+    return 0;
+}
+
+struct Span {
+    uint32_t exit;  // bit position (window-relative) of the first symbol not consumed
+    uint32_t cnt;   // output bytes
+    uint32_t nm;    // matches
+    uint32_t flag;  // 0, 1 = stopped behind an end-of-block symbol, 2 = invalid data
+};
+enum { kFlagNone = 0, kFlagEob = 1, kFlagBad = 2 };
+
+// Decode the symbols that start in [start, end).  WRITE: literals go to the ring at absolute output
+// position q, matches are appended to mlist; stops in front of the first symbol that would take the
+// output past `budget` bytes (exit then points at that symbol, flag stays 0).
+template <bool WRITE>
+LP_INF_FN void decode_span(WarpShared& ws, uint32_t start, uint32_t end, uint32_t q, uint32_t budget,
+                           Match* mlist, Span& r) {
+    Bits b;
+    bits_init(b, ws.inbuf, start);
+    uint32_t cnt = 0, nm = 0, flag = kFlagNone;
+    while (b.pos < end) {
+        const uint32_t sym_pos = b.pos;
+        const uint32_t e = decode_code(ws, 0, b);
+        const uint32_t kind = (e >> 4) & 3u;
+        if (e == 0 || kind == 3) {
+            flag = kFlagBad;
+            break;
+        }
+        if (kind == 0) {
+            if (WRITE) {
+                if (cnt + 1 > budget) {
+                    b.pos = sym_pos;
+                    break;
+                }
+                ws.ring[(q + cnt) & kRingMask] = (uint8_t)(e >> 8);
+            }
+            cnt++;
+            continue;
+        }
+        if (kind == 1) {
+            flag = kFlagEob;
+            break;
+        }
+        // length + distance
+        const uint32_t lx = (e >> 20) & 7u;
+        uint32_t len = (e >> 8) & 0x1FFu;
+        if (lx) len += bits_get(b, ws.inbuf, lx);
+        const uint32_t d = decode_code(ws, 1, b);
+        if (d == 0 || ((d >> 4) & 3u) == 3) {
+            flag = kFlagBad;
+            break;
+        }
+        const uint32_t dx = (d >> 24) & 15u;
+        uint32_t dist = (d >> 8) & 0x7FFFu;
+        if (dx) dist += bits_get(b, ws.inbuf, dx);
+        if (WRITE) {
+            if (cnt + len > budget) {
+                b.pos = sym_pos;
+                break;
+            }
+            if (dist > q + cnt) {  // zlib: "invalid distance too far back"
+                flag = kFlagBad;
+                break;
+            }
+            mlist[nm].q = q + cnt;
+            mlist[nm].ld = (len << 16) | dist;
+        }
+        cnt += len;
+        nm++;
+    }
+    r.exit = b.pos;
+    r.cnt = cnt;
+    r.nm = nm;
+    r.flag = flag;
+}
+
+// ---- the stream ------------------------------------------------------------------------------------------
+
+struct Stream {
+    const uint8_t* z;   // zlib stream (global memory)
+    uint32_t z_len;
+    uint8_t* out;       // inflated bytes (global memory)
+    uint32_t cap;       // bytes expected
+    Match* mlist;       // kMaxMatches entries (global scratch of this warp)
+};
+
+// inbuf <- the window that starts at absolute bit P; returns the window-relative bit offset of P (0..31+).
+LP_INF_FN uint32_t load_window(WarpShared& ws, const Stream& s, uint64_t P) {
+    const uint64_t byte0 = P >> 3;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s.z) + (uintptr_t)byte0;
+    const uintptr_t a0 = a & ~(uintptr_t)3;
+    const uintptr_t zend = reinterpret_cast<uintptr_t>(s.z) + s.z_len;
+    LP_INF_LANES(l) {
+        for (uint32_t w = (uint32_t)l; w < kInWords; w += 32) {
+            const uintptr_t wa = a0 + 4u * (uintptr_t)w;
+            uint32_t v = 0;
+            if (wa + 4 <= zend && wa >= reinterpret_cast<uintptr_t>(s.z)) {
+                v = *reinterpret_cast<const uint32_t*>(wa);
+            } else {
+                for (int k = 0; k < 4; k++) {
+                    const uintptr_t ba = wa + (uintptr_t)k;
+                    if (ba >= reinterpret_cast<uintptr_t>(s.z) && ba < zend) v |= (uint32_t)(*reinterpret_cast<const uint8_t*>(ba)) << (8 * k);
+                }
+            }
+            ws.inbuf[w] = v;
+        }
+    }
+    wsync();
+    return (uint32_t)((a - a0) * 8 + (P & 7));
+}
+
+// ring -> out for [flushed, upto), both multiples of 16 when the vector path is usable
+LP_INF_FN void flush_ring(WarpShared& ws, const Stream& s, uint32_t flushed, uint32_t upto, bool vec) {
+    if (vec) {
+        LP_INF_LANES(l) {
+            for (uint32_t p = flushed + 16u * (uint32_t)l; p < upto; p += 16u * 32u) {
+#ifdef LP_INF_HOST
+                memcpy(s.out + p, ws.ring + (p & kRingMask), 16);
+#else
+                *reinterpret_cast<uint4*>(s.out + p) = *reinterpret_cast<const uint4*>(ws.ring + (p & kRingMask));
+#endif
+            }
+        }
+    } else {
+        LP_INF_LANES(l) {
+            for (uint32_t p = flushed + (uint32_t)l; p < upto; p += 32u) s.out[p] = ws.ring[p & kRingMask];
+        }
+    }
+    wsync();
+}
+
+// Whole stream.  Returns 0 or -3 (corrupt); *produced = bytes written to s.out.
+LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced) {
+    uint32_t o = 0, flushed = 0;
+    *produced = 0;
+    if (s.z_len < 2) return -3;
+    const bool vec = (reinterpret_cast<uintptr_t>(s.out) & 15) == 0;
+    {
+        uint32_t h0 = 0, h1 = 0;
+        h0 = s.z[0];
+        h1 = s.z[1];
+        if ((h0 & 15u) != 8 || (h1 & 0x20u)) return -3;  // not deflate / preset dictionary
+    }
+    uint64_t P = 16;  // absolute bit position in the stream
+    const uint64_t total_bits = (uint64_t)s.z_len * 8;
+    int last = 0;
+    while (!last) {
+        if (P + 3 > total_bits) return -3;
+        uint32_t rel = load_window(ws, s, P);
+        // ---- block header (lane 0 reads, the warp learns the result through shared memory)
+        uint32_t type = 0, hdr_err = 0, hdr_bits = 0;
+        {
+            LaneVar<uint32_t> a, bb, cc, dd;
+            LP_INF_LANES(l) {
+                a[l] = bb[l] = cc[l] = dd[l] = 0;
+                if (l == 0) {
+                    Bits b;
+                    bits_init(b, ws.inbuf, rel);
+                    const uint32_t lastv = bits_get(b, ws.inbuf, 1);
+                    const uint32_t ty = bits_get(b, ws.inbuf, 2);
+                    uint32_t err = 0;
+                    if (ty == 1) {
+                        int i = 0;
+                        for (; i < 144; i++) ws.lens[i] = 8;
+                        for (; i < 256; i++) ws.lens[i] = 9;
+                        for (; i < 280; i++) ws.lens[i] = 7;
+                        for (; i < 288; i++) ws.lens[i] = 8;
+                        for (i = 0; i < 32; i++) ws.lens[288 + i] = 5;
+                        cc[l] = 288 | (32u << 16);  // fixed code: 288 literal/length + 32 distance symbols (30, 31 invalid)
+                    } else if (ty == 2) {
+                        const uint32_t nl = bits_get(b, ws.inbuf, 5) + 257, nd = bits_get(b, ws.inbuf, 5) + 1;
+                        const uint32_t nc = bits_get(b, ws.inbuf, 4) + 4;
+                        if (nl > 286 || nd > 30) err = 1;
+                        uint8_t cl[19];
+                        for (int i = 0; i < 19; i++) cl[i] = 0;
+                        const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                        for (uint32_t i = 0; i < nc && !err; i++) cl[order[i]] = (uint8_t)bits_get(b, ws.inbuf, 3);
+                        // code-length code: 7-bit lookahead (codes are at most 7 bits)
+                        uint32_t count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        for (int i = 0; i < 19; i++) count[cl[i]]++;
+                        count[0] = 0;
+                        int left = 1;
+                        for (int len = 1; len < 8; len++) {
+                            left = (left << 1) - (int)count[len];
+                            if (left < 0) err = 1;
+                        }
+                        for (int i = 0; i < 128; i++) ws.cl[i] = 0;
+                        if (!err) {
+                            uint32_t code = 0;
+                            for (int len = 1; len < 8; len++) {
+                                for (int sym = 0; sym < 19; sym++) {
+                                    if (cl[sym] != len) continue;
+                                    const uint32_t rev = brev32(code) >> (32 - len);
+                                    for (uint32_t j = rev; j < 128; j += 1u << len) ws.cl[j] = (uint16_t)((sym << 4) | len);
+                                    code++;
+                                }
+                                code <<= 1;
+                            }
+                        }
+                        uint32_t i = 0;
+                        while (!err && i < nl + nd) {
+                            bits_fill(b, ws.inbuf);
+                            const uint32_t e = ws.cl[(uint32_t)b.acc & 127u];
+                            if (!e) { err = 1; break; }
+                            bits_drop(b, e & 15u);
+                            const uint32_t sy = e >> 4;
+                            if (sy < 16) { ws.lens[i++] = (uint8_t)sy; continue; }
+                            uint32_t rep, v = 0;
+                            if (sy == 16) {
+                                if (!i) { err = 1; break; }
+                                v = ws.lens[i - 1];
+                                rep = 3 + bits_get(b, ws.inbuf, 2);
+                            } else if (sy == 17) rep = 3 + bits_get(b, ws.inbuf, 3);
+                            else rep = 11 + bits_get(b, ws.inbuf, 7);
+                            if (i + rep > nl + nd) { err = 1; break; }
+                            while (rep--) ws.lens[i++] = (uint8_t)v;
+                        }
+                        if (!err && ws.lens[256] == 0) err = 1;  // zlib: "missing end-of-block"
+                        cc[l] = nl | (nd << 16);
+                        if (b.pos > kInWords * 32 - 64) err = 1;  // header ran out of the window (cannot happen: <= ~4600 bits)
+                    } else if (ty == 3) {
+                        err = 1;
+                    }
+                    a[l] = lastv | (ty << 1) | (err << 3);
+                    bb[l] = b.pos - rel;
+                }
+            }
+            const uint32_t av = bcast(a, 0);
+            last = (int)(av & 1u);
+            type = (av >> 1) & 3u;
+            hdr_err = av >> 3;
+            hdr_bits = bcast(bb, 0);
+            const uint32_t nn = bcast(cc, 0);
+            wsync();
+            if (hdr_err) return -3;
+            P += hdr_bits;
+            if (type != 0) {
+                const int nl = (int)(nn & 0xFFFF), nd = (int)(nn >> 16);
+                if (build_table(ws, 0, ws.lens, nl)) return -3;
+                if (build_table(ws, 1, ws.lens + nl, nd)) return -3;
+            }
+        }
+        if (type == 0) {
+            // ---- stored block: LEN / NLEN at the next byte boundary, then raw bytes
+            const uint64_t pb = (P + 7) >> 3;
+            if (pb + 4 > s.z_len) return -3;
+            const uint32_t len = (uint32_t)s.z[pb] | ((uint32_t)s.z[pb + 1] << 8);
+            const uint32_t nlen = (uint32_t)s.z[pb + 2] | ((uint32_t)s.z[pb + 3] << 8);
+            if ((len ^ 0xFFFFu) != nlen || pb + 4 + len > s.z_len || len > s.cap - o) return -3;
+            const uint8_t* src = s.z + pb + 4;
+            uint32_t done = 0;
+            while (done < len) {
+                const uint32_t n = len - done < kCapT ? len - done : kCapT;
+                LP_INF_LANES(l) {
+                    for (uint32_t i = (uint32_t)l; i < n; i += 32) ws.ring[(o + i) & kRingMask] = src[done + i];
+                }
+                wsync();
+                o += n;
+                done += n;
+                const uint32_t upto = vec ? (o & ~15u) : o;
+                flush_ring(ws, s, flushed, upto, vec);
+                flushed = upto;
+            }
+            P = (pb + 4 + len) * 8;
+            continue;
+        }
+        // ---- compressed block: windows of 32 subsequences until the end-of-block symbol
+        bool eob = false;
+        while (!eob) {
+            if (P >= total_bits) return -3;  // the block runs past the end of the stream
+            rel = load_window(ws, s, P);
+            LaneVar<uint32_t> start, exitp, cnt, nm, flag, want, changed, term;
+            Span sp;
+            // pass A: guessed starts
+            LP_INF_LANES(l) {
+                start[l] = rel + (uint32_t)l * kSubBits;
+                decode_span<false>(ws, start[l], rel + (uint32_t)(l + 1) * kSubBits, 0, 0, nullptr, sp);
+                exitp[l] = sp.exit; cnt[l] = sp.cnt; nm[l] = sp.nm; flag[l] = sp.flag;
+            }
+            // pass B: fixed point
+            for (int round = 0; round < 33; round++) {
+                shift_up(want, exitp, rel);
+                LP_INF_LANES(l) { term[l] = flag[l] != kFlagNone; }
+                const uint32_t tm = ballot(term);
+                LP_INF_LANES(l) {
+                    const bool dead = (tm & ((1u << l) - 1u)) != 0;
+                    changed[l] = (!dead && want[l] != start[l]) ? 1u : 0u;
+                }
+                if (!ballot(changed)) break;
+                LP_INF_LANES(l) {
+                    if (changed[l]) {
+                        start[l] = want[l];
+                        decode_span<false>(ws, start[l], rel + (uint32_t)(l + 1) * kSubBits, 0, 0, nullptr, sp);
+                        exitp[l] = sp.exit; cnt[l] = sp.cnt; nm[l] = sp.nm; flag[l] = sp.flag;
+                    }
+                }
+            }
+            LP_INF_LANES(l) { term[l] = flag[l] != kFlagNone; }
+            const uint32_t tm = ballot(term);
+            const int k = tm ? (int)ffs32(tm) - 1 : 32;  // first lane that ends the block (or fails)
+            // lanes behind k carry nothing
+            LP_INF_LANES(l) {
+                if (l > k) { cnt[l] = 0; nm[l] = 0; }
+            }
+            LaneVar<uint32_t> coff, moff;
+            const uint32_t T = excl_scan(coff, cnt);
+            excl_scan(moff, nm);
+            if (T > s.cap - o) {
+                // more data than the image has room for: libpng stops reading at the last row; an earlier kernel
+                // version and the tests treat it as corrupt
+                return -3;
+            }
+            // pass C: write.  Lanes whose bytes end within the window budget write everything; the first lane
+            // that would cross it writes what fits; lanes behind it (and behind k) write nothing.
+            LaneVar<uint32_t> wexit, wcnt, wnm, wflag, full;
+            LP_INF_LANES(l) { full[l] = (l <= k && coff[l] + cnt[l] <= kCapT) ? 1u : 0u; }
+            const uint32_t fm = ballot(full);
+            const int nfull = (int)ffs32(~fm) - 1 < 0 ? 32 : (int)ffs32(~fm) - 1;  // leading full lanes
+            LP_INF_LANES(l) {
+                wexit[l] = exitp[l]; wcnt[l] = 0; wnm[l] = 0; wflag[l] = kFlagNone;
+                const bool active = l <= nfull && l <= k && l < 32;
+                if (active) {
+                    const uint32_t budget = l < nfull ? 0xFFFFFFFFu : (kCapT > coff[l] ? kCapT - coff[l] : 0u);
+                    decode_span<true>(ws, start[l], rel + (uint32_t)(l + 1) * kSubBits, o + coff[l], budget,
+                                      s.mlist + moff[l], sp);
+                    wexit[l] = sp.exit; wcnt[l] = sp.cnt; wnm[l] = sp.nm; wflag[l] = sp.flag;
+                }
+            }
+            wsync();
+            {
+                LP_INF_LANES(l) { term[l] = wflag[l] == kFlagBad; }
+                if (ballot(term)) return -3;
+            }
+            if (k < 32 && bcast(flag, k) == kFlagBad && nfull > k) return -3;  // an invalid code in the true stream
+            // what was actually written: lanes [0, last_w], the last one perhaps partially
+            const int last_w = nfull < 32 ? (nfull <= k ? nfull : k) : 31;
+            const int last_lane = last_w > 31 ? 31 : last_w;
+            const uint32_t new_rel = bcast(wexit, last_lane);
+            const uint32_t wT = bcast(coff, last_lane) + bcast(wcnt, last_lane);
+            const uint32_t wM = bcast(moff, last_lane) + bcast(wnm, last_lane);
+            eob = (last_lane == k) && bcast(wflag, last_lane) == kFlagEob;
+            // matches, in stream order: the whole warp copies one match at a time
+            const uint32_t ring_lo = o + wT > kRing ? o + wT - kRing : 0;  // oldest position the ring still holds
+            for (uint32_t base = 0; base < wM; base += 32) {
+                LaneVar<uint32_t> mq, mld;
+                LP_INF_LANES(l) {
+                    const uint32_t j = base + (uint32_t)l;
+                    mq[l] = j < wM ? s.mlist[j].q : 0;
+                    mld[l] = j < wM ? s.mlist[j].ld : 0;
+                }
+                const uint32_t nj = wM - base < 32 ? wM - base : 32;
+                for (uint32_t j = 0; j < nj; j++) {
+                    const uint32_t q = bcast(mq, (int)j), ld = bcast(mld, (int)j);
+                    const uint32_t len = ld >> 16, dist = ld & 0xFFFFu;
+                    const uint32_t src0 = q - dist;
+                    LP_INF_LANES(l) {
+                        for (uint32_t i = (uint32_t)l; i < len; i += 32) {
+                            const uint32_t sp_ = src0 + (dist >= len ? i : i % dist);
+                            const uint8_t v = sp_ >= ring_lo ? ws.ring[sp_ & kRingMask] : s.out[sp_];
+                            ws.ring[(q + i) & kRingMask] = v;
+                        }
+                    }
+                    wsync();
+                }
+            }
+            o += wT;
+            P += new_rel - rel;
+            const uint32_t upto = vec ? (o & ~15u) : o;
+            flush_ring(ws, s, flushed, upto, vec);
+            flushed = upto;
+        }
+    }
+    // tail bytes the vector flush left behind
+    LP_INF_LANES(l) {
+        for (uint32_t p = flushed + (uint32_t)l; p < o; p += 32u) s.out[p] = ws.ring[p & kRingMask];
+    }
+    wsync();
+    *produced = o;
+    return 0;
+}
+
+}  // namespace lpinf

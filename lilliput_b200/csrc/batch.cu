@@ -75,10 +75,12 @@ struct lp_batch {
     std::vector<cudaEvent_t> ev_h2d;  // per chunk
     std::vector<cudaEvent_t> ev_d2h;  // per chunk
     static constexpr int kMaxTables = 64;
+    bool owns_mem = true;  // false: device / pinned buffers were carved from a caller's arenas (xbatch.cu)
 };
 
 static void batch_free(lp_batch* b) {
     if (!b) return;
+    if (b->owns_mem) {
     cudaFree(b->d_scan); cudaFree(b->d_items); cudaFree(b->d_tables); cudaFree(b->d_coef);
     cudaFree(b->d_planes); cudaFree(b->d_frames); cudaFree(b->d_resized); cudaFree(b->d_enc_scratch);
     cudaFree(b->d_out); cudaFree(b->d_out_len);
@@ -86,6 +88,7 @@ static void batch_free(lp_batch* b) {
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_out_len) cudaFreeHost(b->h_out_len);
     if (b->h_items_back) cudaFreeHost(b->h_items_back);
+    }
     for (auto e : b->ev) cudaEventDestroy(e);
     for (auto e : b->ev_h2d) cudaEventDestroy(e);
     for (auto e : b->ev_d2h) cudaEventDestroy(e);
@@ -95,12 +98,23 @@ static void batch_free(lp_batch* b) {
     delete b;
 }
 
-extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
+namespace lp {
+lp_batch* batch_create_in(const lp_batch_config* cfg, uint8_t* dev_arena, size_t dev_bytes, uint8_t* host_arena,
+                          size_t host_bytes);
+}
+extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) { return lp::batch_create_in(cfg, nullptr, 0, nullptr, 0); }
+
+// dev_arena / host_arena non-null: every device / pinned buffer is carved from them (nothing is allocated or
+// freed by the context); returns nullptr when they are too small.
+lp_batch* lp::batch_create_in(const lp_batch_config* cfg, uint8_t* dev_arena, size_t dev_bytes, uint8_t* host_arena,
+                              size_t host_bytes) {
     if (!cfg || cfg->max_images < 1 || cfg->src_width < 1 || cfg->src_height < 1) return nullptr;
     if (ensure_device()) return nullptr;
     LP_CUDA_OK_NULL(cudaSetDevice(cfg->device));
     lp_batch* b = new lp_batch;
     b->cfg = *cfg;
+    b->owns_mem = dev_arena == nullptr;
+    size_t dev_used = 0, host_used = 0;
     b->W = cfg->src_width;
     b->H = cfg->src_height;
     if (cfg->resize_method == LP_OPS_FIT) {
@@ -136,8 +150,22 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
     const size_t N = cfg->max_images;
     auto fail = [&]() -> lp_batch* { batch_free(b); return nullptr; };
 #define BALLOC(ptr, bytes)                                                                      \
-    if (cudaMalloc(&(ptr), (bytes)) != cudaSuccess) {                                           \
+    if (dev_arena) {                                                                            \
+        const size_t need_ = round_up((size_t)(bytes), (size_t)256);                            \
+        if (dev_used + need_ > dev_bytes) return fail();                                        \
+        (ptr) = reinterpret_cast<decltype(ptr)>(dev_arena + dev_used);                          \
+        dev_used += need_;                                                                      \
+    } else if (cudaMalloc(&(ptr), (bytes)) != cudaSuccess) {                                    \
         fprintf(stderr, "[lilliput_b200] lp_batch_create: cudaMalloc(%zu) failed\n", (size_t)(bytes)); \
+        return fail();                                                                          \
+    }
+#define HALLOC(ptr, bytes)                                                                      \
+    if (host_arena) {                                                                           \
+        const size_t need_ = round_up((size_t)(bytes), (size_t)256);                            \
+        if (host_used + need_ > host_bytes) return fail();                                      \
+        (ptr) = reinterpret_cast<decltype(ptr)>(host_arena + host_used);                        \
+        host_used += need_;                                                                     \
+    } else if (cudaMallocHost(&(ptr), (bytes)) != cudaSuccess) {                                \
         return fail();                                                                          \
     }
     if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess) return fail();
@@ -158,9 +186,10 @@ extern "C" lp_batch* lp_batch_create(const lp_batch_config* cfg) {
     BALLOC(b->d_out, N * cfg->out_cap);
     BALLOC(b->d_out_len, N * sizeof(uint32_t));
 #undef BALLOC
-    if (cudaMallocHost(&b->h_out, N * cfg->out_cap) != cudaSuccess) return fail();
-    if (cudaMallocHost(&b->h_out_len, N * sizeof(uint32_t)) != cudaSuccess) return fail();
-    if (cudaMallocHost(&b->h_items_back, N * sizeof(JpegDecodeItem)) != cudaSuccess) return fail();
+    HALLOC(b->h_out, N * cfg->out_cap);
+    HALLOC(b->h_out_len, N * sizeof(uint32_t));
+    HALLOC(b->h_items_back, N * sizeof(JpegDecodeItem));
+#undef HALLOC
     b->ev.resize((size_t)b->max_chunks * 6);
     b->ev_h2d.resize(b->max_chunks);
     b->ev_d2h.resize(b->max_chunks);

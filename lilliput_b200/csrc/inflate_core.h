@@ -37,10 +37,10 @@
 
 namespace lpinf {
 
-constexpr uint32_t kSubBits = 512;             // bits per lane and window
+constexpr uint32_t kSubBits = 256;             // bits per lane and window
 constexpr uint32_t kWinBits = 32 * kSubBits;
 constexpr uint32_t kInWords = kWinBits / 32 + 8;  // window + the bits a symbol / a refill may read past it
-constexpr uint32_t kRing = 16384, kRingMask = kRing - 1;
+constexpr uint32_t kRing = 8192, kRingMask = kRing - 1;
 constexpr uint32_t kCapT = kRing / 2;          // output bytes per window
 constexpr uint32_t kMaxMatches = kCapT / 3 + 8;  // a match is at least 3 bytes
 constexpr int kLitBits = 10, kDistBits = 8;
@@ -311,18 +311,18 @@ LP_INF_FN uint32_t decode_code(const WarpShared& ws, int t, Bits& b) {
         bits_drop(b, e & 15u);
         return e;
     }
-    // longer than the lookahead: canonical walk, bit by bit (rare)
-    uint32_t code = 0;
+    // longer than the lookahead: the canonical walk continues behind it (a code of <= look_bits bits would
+    // have been found above), at most 15 - look_bits steps
     const uint32_t bitsv = (uint32_t)b.acc;
-    for (int len = 1; len < 16; len++) {
-        code |= (bitsv >> (len - 1)) & 1u;
+    uint32_t code = brev32(bitsv << (32 - look_bits));  // the first look_bits bits, most significant first
+    for (int len = look_bits + 1; len < 16; len++) {
+        code = (code << 1) | ((bitsv >> (len - 1)) & 1u);
         const uint32_t c = ws.cnt32[t][len], f = ws.first[t][len];
         if (code - f < c) {
             const uint32_t sym = (t ? ws.dsym : ws.lsym)[ws.index[t][len] + (code - f)];
             bits_drop(b, (uint32_t)len);
             return t ? dist_entry(sym, (uint32_t)len) : lit_entry(sym, (uint32_t)len);
         }
-        code <<= 1;
     }
     return 0;
 }
@@ -402,6 +402,25 @@ LP_INF_FN void decode_span(WarpShared& ws, uint32_t start, uint32_t end, uint32_
 
 // ---- the stream ------------------------------------------------------------------------------------------
 
+// Optional counters (LP_INF_STATS): the host simulation counts windows / rounds / re-decodes, the device
+// build (png_decode.cu with -DLP_INF_STATS) adds clock64() per phase.  [0] blocks [1] windows [2] rounds
+// [3] lane re-decodes in pass B [4] partial windows [5] matches; device clocks: [8] header+tables
+// [9] load_window [10] pass A [11] pass B [12] pass C [13] match copy [14] flush
+#ifdef LP_INF_STATS
+#ifdef LP_INF_HOST
+static unsigned long long g_stats[16];
+#define LP_INF_COUNT(i, v) (g_stats[i] += (v))
+#define LP_INF_CLOCK(i) do { } while (0)
+#else
+__device__ unsigned long long g_stats[16];
+#define LP_INF_COUNT(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
+#define LP_INF_CLOCK(i) do { const long long _now = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_stats[i], (unsigned long long)(_now - _t0)); _t0 = _now; } while (0)
+#endif
+#else
+#define LP_INF_COUNT(i, v) do { } while (0)
+#define LP_INF_CLOCK(i) do { } while (0)
+#endif
+
 struct Stream {
     const uint8_t* z;   // zlib stream (global memory)
     uint32_t z_len;
@@ -470,9 +489,14 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
     uint64_t P = 16;  // absolute bit position in the stream
     const uint64_t total_bits = (uint64_t)s.z_len * 8;
     int last = 0;
+#if defined(LP_INF_STATS) && !defined(LP_INF_HOST)
+    long long _t0 = clock64();
+#endif
     while (!last) {
         if (P + 3 > total_bits) return -3;
+        LP_INF_COUNT(0, 1);
         uint32_t rel = load_window(ws, s, P);
+        LP_INF_CLOCK(9);
         // ---- block header (lane 0 reads, the warp learns the result through shared memory)
         uint32_t type = 0, hdr_err = 0, hdr_bits = 0;
         {
@@ -566,6 +590,7 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                 if (build_table(ws, 1, ws.lens + nl, nd)) return -3;
             }
         }
+        LP_INF_CLOCK(8);
         if (type == 0) {
             // ---- stored block: LEN / NLEN at the next byte boundary, then raw bytes
             const uint64_t pb = (P + 7) >> 3;
@@ -594,7 +619,9 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
         bool eob = false;
         while (!eob) {
             if (P >= total_bits) return -3;  // the block runs past the end of the stream
+            LP_INF_COUNT(1, 1);
             rel = load_window(ws, s, P);
+            LP_INF_CLOCK(9);
             LaneVar<uint32_t> start, exitp, cnt, nm, flag, want, changed, term;
             Span sp;
             // pass A: guessed starts
@@ -603,6 +630,7 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                 decode_span<false>(ws, start[l], rel + (uint32_t)(l + 1) * kSubBits, 0, 0, nullptr, sp);
                 exitp[l] = sp.exit; cnt[l] = sp.cnt; nm[l] = sp.nm; flag[l] = sp.flag;
             }
+            LP_INF_CLOCK(10);
             // pass B: fixed point
             for (int round = 0; round < 33; round++) {
                 shift_up(want, exitp, rel);
@@ -613,6 +641,8 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                     changed[l] = (!dead && want[l] != start[l]) ? 1u : 0u;
                 }
                 if (!ballot(changed)) break;
+                LP_INF_COUNT(2, 1);
+                LP_INF_COUNT(3, popc32(ballot(changed)));
                 LP_INF_LANES(l) {
                     if (changed[l]) {
                         start[l] = want[l];
@@ -621,6 +651,7 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                     }
                 }
             }
+            LP_INF_CLOCK(11);
             LP_INF_LANES(l) { term[l] = flag[l] != kFlagNone; }
             const uint32_t tm = ballot(term);
             const int k = tm ? (int)ffs32(tm) - 1 : 32;  // first lane that ends the block (or fails)
@@ -665,35 +696,59 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
             const uint32_t wT = bcast(coff, last_lane) + bcast(wcnt, last_lane);
             const uint32_t wM = bcast(moff, last_lane) + bcast(wnm, last_lane);
             eob = (last_lane == k) && bcast(wflag, last_lane) == kFlagEob;
-            // matches, in stream order: the whole warp copies one match at a time
+            LP_INF_CLOCK(12);
+            LP_INF_COUNT(4, nfull < 32 && nfull <= k ? 1 : 0);
+            LP_INF_COUNT(5, wM);
+            // matches: every lane copies its own (they lie in its own output segment, in order).  A copy may
+            // start once its source bytes are final: below the high-water mark H (everything in front of the
+            // first lane that is still blocked), or inside the lane's own finished prefix.  The lowest
+            // unfinished lane is never blocked, so every round finishes at least one more lane; PNG data
+            // mostly refers a pixel or a scanline back, i.e. to the lane itself or in front of the window.
             const uint32_t ring_lo = o + wT > kRing ? o + wT - kRing : 0;  // oldest position the ring still holds
-            for (uint32_t base = 0; base < wM; base += 32) {
-                LaneVar<uint32_t> mq, mld;
+            if (wM) {
+                LaneVar<uint32_t> mi, mend, own_start, blocked_q, notdone;
                 LP_INF_LANES(l) {
-                    const uint32_t j = base + (uint32_t)l;
-                    mq[l] = j < wM ? s.mlist[j].q : 0;
-                    mld[l] = j < wM ? s.mlist[j].ld : 0;
+                    const bool wrote = l <= last_lane;
+                    mi[l] = moff[l];
+                    mend[l] = wrote ? moff[l] + wnm[l] : moff[l];
+                    own_start[l] = o + coff[l];
+                    blocked_q[l] = 0;
                 }
-                const uint32_t nj = wM - base < 32 ? wM - base : 32;
-                for (uint32_t j = 0; j < nj; j++) {
-                    const uint32_t q = bcast(mq, (int)j), ld = bcast(mld, (int)j);
-                    const uint32_t len = ld >> 16, dist = ld & 0xFFFFu;
-                    const uint32_t src0 = q - dist;
+                uint32_t H = o;
+                for (int round = 0; round < 34; round++) {
                     LP_INF_LANES(l) {
-                        for (uint32_t i = (uint32_t)l; i < len; i += 32) {
-                            const uint32_t sp_ = src0 + (dist >= len ? i : i % dist);
-                            const uint8_t v = sp_ >= ring_lo ? ws.ring[sp_ & kRingMask] : s.out[sp_];
-                            ws.ring[(q + i) & kRingMask] = v;
+                        while (mi[l] < mend[l]) {
+                            const Match m = s.mlist[mi[l]];
+                            const uint32_t len = m.ld >> 16, dist = m.ld & 0xFFFFu;
+                            const uint32_t src0 = m.q - dist, L = dist < len ? dist : len;
+                            const bool ok = src0 + L <= H || src0 >= own_start[l] || own_start[l] <= H;
+                            if (!ok) {
+                                blocked_q[l] = m.q;
+                                break;
+                            }
+                            for (uint32_t i = 0; i < len; i++) {
+                                const uint32_t sp_ = src0 + (dist >= len ? i : i % dist);
+                                const uint8_t v = sp_ >= ring_lo ? ws.ring[sp_ & kRingMask] : s.out[sp_];
+                                ws.ring[(m.q + i) & kRingMask] = v;
+                            }
+                            mi[l]++;
                         }
+                        notdone[l] = mi[l] < mend[l] ? 1u : 0u;
                     }
                     wsync();
+                    const uint32_t nd = ballot(notdone);
+                    if (!nd) break;
+                    LP_INF_COUNT(6, 1);
+                    H = bcast(blocked_q, (int)ffs32(nd) - 1);
                 }
             }
+            LP_INF_CLOCK(13);
             o += wT;
             P += new_rel - rel;
             const uint32_t upto = vec ? (o & ~15u) : o;
             flush_ring(ws, s, flushed, upto, vec);
             flushed = upto;
+            LP_INF_CLOCK(14);
         }
     }
     // tail bytes the vector flush left behind

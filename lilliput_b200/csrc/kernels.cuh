@@ -244,6 +244,20 @@ struct JpegEncodeBatch {
 size_t jpeg_encode_scratch_bytes(int width, int height, int channels, int n, size_t out_cap);
 int jpeg_encode_launch(const JpegEncodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_transform);
 
+// ---- webp_encode.cu -------------------------------------------------------------------------
+struct WebpEncodedFrame {
+    std::vector<uint8_t> image;  // "VP8 " or "VP8L" payload
+    std::vector<uint8_t> alph;   // "ALPH" payload (lossy frames with transparency)
+    bool lossless = false, has_alpha = false;
+    int width = 0, height = 0, duration = 0;
+};
+// n packed device frames of one geometry (frame i at d_frames + i*img_stride) -> lossy VP8 payloads (+ ALPH for
+// frames with transparency), ref webp.cpp:711-729 / 650-700 per frame.
+int webp_encode_lossy_batch(const uint8_t* d_frames, size_t img_stride, size_t row_step, int width, int height,
+                            int channels, int n, int quality, std::vector<WebpEncodedFrame>* out, cudaStream_t st);
+void webp_assemble(const WebpEncodedFrame* frames, int n, const uint8_t* icc, size_t icc_len, uint32_t bgcolor,
+                   uint32_t loop_count, std::vector<uint8_t>* file);
+
 // ---- pixel_ops.cu --------------------------------------------------------------------------
 int orient_launch(const uint8_t* src, int w, int h, int channels, int orientation, uint8_t* dst,
                   cudaStream_t st);

@@ -193,6 +193,18 @@ __global__ void png_convert_kernel(const PngDecodeItem* items, const uint8_t* ra
     }
 }
 
+#ifdef LP_INF_STATS
+// profiling build only (make EXTRA=-DLP_INF_STATS): the counters / per-phase clocks of inflate_core.h
+extern "C" void lp_png_inflate_stats(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, lpinf::g_stats, 16 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(lpinf::g_stats, z, sizeof(z));
+    }
+}
+#endif
+
 void png_item_set_passes(PngDecodeItem* it) {
     static const int X0[7] = {0, 4, 0, 2, 0, 1, 0}, Y0[7] = {0, 0, 4, 0, 2, 0, 1};
     static const int DX[7] = {8, 8, 4, 4, 2, 2, 1}, DY[7] = {8, 8, 8, 4, 4, 2, 2};

@@ -259,6 +259,301 @@ static int vp8_encode_dev(const uint8_t* d_frame, size_t step, int width, int he
     return rc;
 }
 
+// ------------------------------------------------------------------ batched lossy encode
+// N frames of one geometry per launch (the batch ABI, xbatch.cu): the per-frame work is the same code as
+// above, one frame per warp (lane 0 walks the macroblocks and the boolean coder -- a serial dependency
+// chain per frame, so the parallelism is across frames), alpha planes through one CTA per frame.
+
+__global__ void vp8_planes_batch_kernel(const uint8_t* frames, size_t img_stride, size_t step, int channels, int width,
+                                        int height, int ys, int yh, uint8_t* planes, size_t planes_stride) {
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;
+    if (cx >= ys / 2) return;
+    const uint8_t* frame = frames + (size_t)blockIdx.z * img_stride;
+    uint8_t* sy = planes + (size_t)blockIdx.z * planes_stride;
+    const size_t ypl = (size_t)ys * yh;
+    uint8_t* su = sy + ypl;
+    uint8_t* sv = su + ypl / 4;
+    int r = 0, g = 0, b = 0;
+    for (int dy = 0; dy < 2; dy++)
+        for (int dx = 0; dx < 2; dx++) {
+            const int x = min(2 * cx + dx, width - 1), y = min(2 * cy + dy, height - 1);
+            const uint8_t* p = frame + (size_t)y * step + (size_t)x * channels;
+            sy[(size_t)(2 * cy + dy) * ys + 2 * cx + dx] = (uint8_t)vp8enc::rgb_to_y(p[2], p[1], p[0]);
+            b += p[0];
+            g += p[1];
+            r += p[2];
+        }
+    su[(size_t)cy * (ys / 2) + cx] = (uint8_t)vp8enc::rgb_to_u(r, g, b);
+    sv[(size_t)cy * (ys / 2) + cx] = (uint8_t)vp8enc::rgb_to_v(r, g, b);
+}
+
+struct Vp8EncBatch {
+    vp8enc::Params P;       // shared geometry / quantiser
+    uint8_t* scratch;       // per-frame regions, `stride` apart
+    size_t stride;
+    size_t off_src, off_rec, off_levels, off_modes, off_part0, off_tokens, off_topnz;
+    size_t part0_cap, tokens_cap;
+    uint8_t* out;           // n * out_cap
+    size_t out_cap;
+    uint32_t* out_len;      // n (0 = did not fit)
+    int n;
+};
+
+constexpr int kVp8EncWarps = 4;
+__global__ void __launch_bounds__(kVp8EncWarps * 32) vp8_encode_batch_kernel(Vp8EncBatch b) {
+    const int f = blockIdx.x * kVp8EncWarps + (threadIdx.x >> 5);
+    if (f >= b.n || (threadIdx.x & 31) != 0) return;
+    vp8enc::Params P = b.P;
+    if (P.filter_level < 0) P.filter_level = vp8enc::filter_level_for_q(P.q);
+    uint8_t* base = b.scratch + (size_t)f * b.stride;
+    const size_t ypl = (size_t)P.mb_w * 16 * P.mb_h * 16;
+    vp8enc::Buffers B;
+    B.sy = base + b.off_src;
+    B.su = B.sy + ypl;
+    B.sv = B.su + ypl / 4;
+    B.ry = base + b.off_rec;
+    B.ru = B.ry + ypl;
+    B.rv = B.ru + ypl / 4;
+    B.levels = reinterpret_cast<int16_t*>(base + b.off_levels);
+    B.modes = base + b.off_modes;
+    vp8enc::analyse_and_reconstruct(P, B);
+    const size_t n = vp8enc::write_bitstream(P, B, base + b.off_part0, b.part0_cap, base + b.off_tokens, b.tokens_cap,
+                                             base + b.off_topnz, b.out + (size_t)f * b.out_cap, b.out_cap);
+    b.out_len[f] = (uint32_t)n;
+}
+
+// alpha plane of every frame + "does the frame have any non-opaque pixel" (libwebp drops the ALPH chunk of an
+// opaque picture: WebPEncode -> WebPPictureHasTransparency)
+__global__ void extract_alpha_batch_kernel(const uint8_t* frames, size_t img_stride, size_t step, int width, int height,
+                                           uint8_t* planes, uint32_t* transparent) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    uint8_t a = 255;
+    if (x < width) {
+        a = frames[(size_t)blockIdx.z * img_stride + (size_t)y * step + (size_t)x * 4 + 3];
+        planes[((size_t)blockIdx.z * height + y) * width + x] = a;
+    }
+    if (__syncthreads_or(a != 255) && threadIdx.x == 0) atomicOr(&transparent[blockIdx.z], 1u);
+}
+
+__global__ void vp8l_hist_plane_batch_kernel(const uint8_t* planes, int width, int height, uint32_t* hist /* n x 4 x 256 */) {
+    __shared__ uint32_t sh[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const uint8_t* plane = planes + (size_t)blockIdx.z * width * height;
+    if (x < width) {
+        const uint32_t r = vp8lenc::residual_at(plane, (size_t)width, 1, x, y);
+        atomicAdd(&sh[(r >> 8) & 255], 1u);
+    }
+    __syncthreads();
+    // a lone plane travels in green; red / blue residuals are 0 and alpha's is 0 except at (0,0) -- the
+    // host adds those three constant histograms itself
+    uint32_t* h = hist + (size_t)blockIdx.z * 1024;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&h[i], sh[i]);
+}
+
+// One CTA per frame: bit length of every pixel, running prefix sum, bits OR-ed into the (zeroed) output
+// behind the head the host wrote.  total_bits[f] = head bits + pixel bits.
+constexpr int kPackThreads = 512;
+__global__ void __launch_bounds__(kPackThreads)
+    vp8l_pack_plane_batch_kernel(const uint8_t* planes, int width, int height, const vp8lenc::CodeTable* tables,
+                                 const uint32_t* head_bits, const uint32_t* transparent, uint32_t* out, size_t out_words,
+                                 uint32_t* total_bits) {
+    __shared__ uint32_t warp_sums[kPackThreads / 32];
+    const int f = blockIdx.x;
+    if (!transparent[f]) return;
+    const vp8lenc::CodeTable& t = tables[f];
+    const uint8_t* plane = planes + (size_t)f * width * height;
+    uint32_t* o = out + (size_t)f * out_words;
+    const uint32_t npix = (uint32_t)width * height;
+    uint32_t base = head_bits[f];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t p0 = 0; p0 < npix; p0 += kPackThreads) {
+        const uint32_t p = p0 + threadIdx.x;
+        uint64_t bits = 0;
+        int nb = 0;
+        if (p < npix) {
+            const uint32_t r = vp8lenc::residual_at(plane, (size_t)width, 1, (int)(p % width), (int)(p / width));
+            vp8lenc::pixel_bits(r, t, &bits, &nb);
+        }
+        // block exclusive scan of nb
+        uint32_t inc = (uint32_t)nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t s = lane < kPackThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += v;
+            }
+            if (lane < kPackThreads / 32) warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const uint32_t at = base + (wid ? warp_sums[wid - 1] : 0) + inc - (uint32_t)nb;
+        base += warp_sums[kPackThreads / 32 - 1];
+        if (nb) {
+            const size_t w = at >> 5;
+            const int sh = (int)(at & 31);
+            const uint64_t lo = bits << sh;
+            const uint64_t hi = sh ? bits >> (64 - sh) : 0;
+            if ((uint32_t)lo) atomicOr(&o[w], (uint32_t)lo);
+            if ((uint32_t)(lo >> 32)) atomicOr(&o[w + 1], (uint32_t)(lo >> 32));
+            if ((uint32_t)hi) atomicOr(&o[w + 2], (uint32_t)hi);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total_bits[f] = base;
+}
+
+int webp_encode_lossy_batch(const uint8_t* d_frames, size_t img_stride, size_t row_step, int width, int height,
+                            int channels, int n, int quality, std::vector<WebpEncodedFrame>* out, cudaStream_t st) {
+    out->assign((size_t)n, WebpEncodedFrame());
+    if (n <= 0) return LP_OK;
+    if (width > 16383 || height > 16383 || (channels != 3 && channels != 4)) return LP_ERR_INVALID_IMAGE;
+    Vp8EncBatch b;
+    b.P.width = width;
+    b.P.height = height;
+    b.P.mb_w = (width + 15) >> 4;
+    b.P.mb_h = (height + 15) >> 4;
+    b.P.q = vp8enc::quality_to_q(quality);
+    b.P.filter_level = -1;
+    b.n = n;
+    const int ys = b.P.mb_w * 16, yh = b.P.mb_h * 16;
+    const size_t ypl = (size_t)ys * yh, nmb = (size_t)b.P.mb_w * b.P.mb_h;
+    const size_t planes_b = round_up(ypl * 3 / 2, (size_t)256);
+    const size_t levels_b = round_up(nmb * 25 * 16 * 2, (size_t)256), modes_b = round_up(nmb * 2, (size_t)256);
+    b.part0_cap = round_up(nmb * 2 + 4096, (size_t)256);
+    b.tokens_cap = round_up(nmb * 2048 + 4096, (size_t)256);
+    const size_t topnz_b = round_up((size_t)b.P.mb_w * 9, (size_t)256);
+    b.off_src = 0;
+    b.off_rec = planes_b;
+    b.off_levels = 2 * planes_b;
+    b.off_modes = b.off_levels + levels_b;
+    b.off_part0 = b.off_modes + modes_b;
+    b.off_tokens = b.off_part0 + b.part0_cap;
+    b.off_topnz = b.off_tokens + b.tokens_cap;
+    b.stride = b.off_topnz + topnz_b;
+    // the stream is the two partitions back to back: a slot that holds what they can hold never overflows;
+    // real frames use a few per cent of it, so the slots are compacted on the device before they cross PCIe
+    b.out_cap = round_up((size_t)16 + b.part0_cap + b.tokens_cap, (size_t)256);
+    const bool alpha = channels == 4;
+    const size_t npix = (size_t)width * height;
+    const size_t alph_words = (npix * 2 + 4096 + 3) / 4;  // one <=15-bit green code per pixel + the head
+    uint8_t* scratch = nullptr;
+    const size_t lens_b = round_up((size_t)n * 4, (size_t)256);
+    const size_t aplane_b = alpha ? round_up((size_t)n * npix, (size_t)256) : 0;
+    const size_t hist_b = alpha ? round_up((size_t)n * 1024 * 4, (size_t)256) : 0;
+    const size_t tables_b = alpha ? round_up((size_t)n * sizeof(vp8lenc::CodeTable), (size_t)256) : 0;
+    const size_t aout_b = alpha ? round_up((size_t)n * alph_words * 4, (size_t)256) : 0;
+    const size_t total = (size_t)n * b.stride + (size_t)n * b.out_cap + 4 * lens_b + aplane_b + hist_b + tables_b + aout_b;
+    if (cudaMallocAsync(&scratch, total, st) != cudaSuccess) {
+        fprintf(stderr, "[lilliput_b200] webp_encode_lossy_batch: cudaMallocAsync(%zu) failed\n", total);
+        cudaGetLastError();
+        return LP_ERR_CUDA;
+    }
+    uint8_t* p = scratch;
+    b.scratch = p; p += (size_t)n * b.stride;
+    b.out = p; p += (size_t)n * b.out_cap;
+    b.out_len = reinterpret_cast<uint32_t*>(p); p += lens_b;
+    uint32_t* d_transp = reinterpret_cast<uint32_t*>(p); p += lens_b;
+    uint32_t* d_head_bits = reinterpret_cast<uint32_t*>(p); p += lens_b;
+    uint32_t* d_total_bits = reinterpret_cast<uint32_t*>(p); p += lens_b;
+    uint8_t* d_aplanes = p; p += aplane_b;
+    uint32_t* d_hist = reinterpret_cast<uint32_t*>(p); p += hist_b;
+    auto* d_tables = reinterpret_cast<vp8lenc::CodeTable*>(p); p += tables_b;
+    uint32_t* d_aout = reinterpret_cast<uint32_t*>(p);
+    int rc = LP_OK;
+    std::vector<uint32_t> lens((size_t)n), transp((size_t)n, 0), total_bits((size_t)n, 0);
+    do {
+        {
+            dim3 grid(ceil_div(ys / 2, 128), yh / 2, n);
+            vp8_planes_batch_kernel<<<grid, 128, 0, st>>>(d_frames, img_stride, row_step, channels, width, height, ys, yh,
+                                                          b.scratch + b.off_src, b.stride);
+            vp8_encode_batch_kernel<<<ceil_div(n, kVp8EncWarps), kVp8EncWarps * 32, 0, st>>>(b);
+            g_launches += 2;
+        }
+        std::vector<uint32_t> hist;
+        if (alpha) {
+            cudaMemsetAsync(d_transp, 0, (size_t)n * 4, st);
+            cudaMemsetAsync(d_hist, 0, (size_t)n * 1024 * 4, st);
+            dim3 grid(ceil_div(width, 256), height, n);
+            extract_alpha_batch_kernel<<<grid, 256, 0, st>>>(d_frames, img_stride, row_step, width, height, d_aplanes, d_transp);
+            vp8l_hist_plane_batch_kernel<<<grid, 256, 0, st>>>(d_aplanes, width, height, d_hist);
+            g_launches += 2;
+            hist.resize((size_t)n * 1024);
+            cudaMemcpyAsync(transp.data(), d_transp, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(hist.data(), d_hist, (size_t)n * 1024 * 4, cudaMemcpyDeviceToHost, st);
+        }
+        cudaMemcpyAsync(lens.data(), b.out_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = LP_ERR_CUDA; break; }
+        // alpha planes of the frames that have transparency: prefix codes on the host, packing on the device
+        std::vector<vp8lenc::BitWriter> heads;
+        bool any_alpha = false;
+        if (alpha) {
+            heads.resize((size_t)n);
+            std::vector<vp8lenc::CodeTable> tables((size_t)n);
+            std::vector<uint32_t> head_bits((size_t)n, 0);
+            for (int i = 0; i < n; i++) {
+                if (!transp[i]) continue;
+                any_alpha = true;
+                uint32_t* h = hist.data() + (size_t)i * 1024;
+                h[256 + 0] = (uint32_t)npix;    // red residuals: all 0
+                h[512 + 0] = (uint32_t)npix;    // blue
+                h[768 + 0] = (uint32_t)npix;    // alpha: 0xff - 0xff = 0 everywhere (the first pixel predicts 0xff000000)
+                vp8lenc::BitWriter& bw = heads[i];
+                bw.put(1, 8);  // ALPH header byte: VP8L-compressed, no filter, no pre-processing
+                vp8lenc::write_stream_head(bw, width, height, false, false, false, h, &tables[i]);
+                head_bits[i] = (uint32_t)bw.nbits;
+                bw.flush();
+                if (bw.bytes.size() + 8 > alph_words * 4) { rc = LP_ERR_CUDA; break; }
+            }
+            if (rc) break;
+            if (any_alpha) {
+                cudaMemsetAsync(d_aout, 0, (size_t)n * alph_words * 4, st);
+                cudaMemcpyAsync(d_tables, tables.data(), (size_t)n * sizeof(vp8lenc::CodeTable), cudaMemcpyHostToDevice, st);
+                cudaMemcpyAsync(d_head_bits, head_bits.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st);
+                for (int i = 0; i < n; i++)
+                    if (transp[i])
+                        cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d_aout) + (size_t)i * alph_words * 4, heads[i].bytes.data(),
+                                        heads[i].bytes.size(), cudaMemcpyHostToDevice, st);
+                vp8l_pack_plane_batch_kernel<<<n, kPackThreads, 0, st>>>(d_aplanes, width, height, d_tables, d_head_bits, d_transp,
+                                                                         d_aout, alph_words, d_total_bits);
+                g_launches++;
+                cudaMemcpyAsync(total_bits.data(), d_total_bits, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+                if (cudaStreamSynchronize(st) != cudaSuccess) { rc = LP_ERR_CUDA; break; }  // (tables / heads stay alive until here)
+            }
+        }
+        // results home: one copy per frame of the bytes actually used
+        for (int i = 0; i < n && !rc; i++) {
+            WebpEncodedFrame& f = (*out)[i];
+            f.width = width;
+            f.height = height;
+            f.lossless = false;
+            f.has_alpha = alpha && transp[i];
+            if (lens[i] == 0 || lens[i] > b.out_cap) { f.image.clear(); continue; }  // caller reports the item
+            f.image.resize(lens[i]);
+            if (cudaMemcpyAsync(f.image.data(), b.out + (size_t)i * b.out_cap, lens[i], cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = LP_ERR_CUDA;
+            if (f.has_alpha) {
+                const size_t bytes = ((size_t)total_bits[i] + 7) / 8;
+                if (bytes == 0 || bytes > alph_words * 4) { f.image.clear(); continue; }
+                f.alph.resize(bytes);
+                if (cudaMemcpyAsync(f.alph.data(), reinterpret_cast<uint8_t*>(d_aout) + (size_t)i * alph_words * 4, bytes,
+                                    cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = LP_ERR_CUDA;
+            }
+        }
+        if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = LP_ERR_CUDA;
+    } while (0);
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
 // ------------------------------------------------------------------ RIFF assembly (host)
 
 static void put_le32(std::vector<uint8_t>& v, uint32_t x) {
@@ -274,16 +569,60 @@ static void put_chunk(std::vector<uint8_t>& v, const char* tag, const uint8_t* p
     if (n & 1) v.push_back(0);
 }
 
-struct EncodedFrame {
-    std::vector<uint8_t> image;  // "VP8 " or "VP8L" payload
-    std::vector<uint8_t> alph;   // "ALPH" payload (lossy frames with alpha)
-    bool lossless = false, has_alpha = false;
-    int width = 0, height = 0, duration = 0;
-};
+using EncodedFrame = WebpEncodedFrame;
 
 static void put_image_chunks(std::vector<uint8_t>& v, const EncodedFrame& f) {
     if (!f.alph.empty()) put_chunk(v, "ALPH", f.alph.data(), f.alph.size());
     put_chunk(v, f.lossless ? "VP8L" : "VP8 ", f.image.data(), f.image.size());
+}
+
+
+// RIFF file of one still (n == 1) or an animation: VP8X / ICCP / ANIM / ANMF / ALPH / VP8(L) as libwebpmux
+// lays them out (ref webp.cpp:511-560 WebPMuxAssemble).
+void webp_assemble(const WebpEncodedFrame* frames, int n, const uint8_t* icc, size_t icc_len, uint32_t bgcolor,
+                   uint32_t loop_count, std::vector<uint8_t>* file_out) {
+    std::vector<uint8_t> body;
+    const bool anim = n > 1;
+    bool any_alpha = false;
+    for (int i = 0; i < n; i++) any_alpha |= frames[i].has_alpha;
+    const WebpEncodedFrame& f0 = frames[0];
+    const bool need_vp8x = anim || icc_len != 0 || !f0.alph.empty();
+    if (need_vp8x) {
+        std::vector<uint8_t> x;
+        x.push_back((uint8_t)((anim ? 0x02 : 0) | (any_alpha ? 0x10 : 0) | (icc_len ? 0x20 : 0)));
+        x.insert(x.end(), 3, 0);
+        put_le24(x, (uint32_t)f0.width - 1);
+        put_le24(x, (uint32_t)f0.height - 1);
+        put_chunk(body, "VP8X", x.data(), x.size());
+        if (icc_len) put_chunk(body, "ICCP", icc, icc_len);
+    }
+    if (anim) {
+        std::vector<uint8_t> a;
+        put_le32(a, bgcolor);
+        a.push_back((uint8_t)(loop_count & 0xff));
+        a.push_back((uint8_t)((loop_count >> 8) & 0xff));
+        put_chunk(body, "ANIM", a.data(), a.size());
+        for (int i = 0; i < n; i++) {
+            const WebpEncodedFrame& f = frames[i];
+            std::vector<uint8_t> m;
+            put_le24(m, 0);
+            put_le24(m, 0);
+            put_le24(m, (uint32_t)f.width - 1);
+            put_le24(m, (uint32_t)f.height - 1);
+            put_le24(m, (uint32_t)(f.duration < 0 ? 0 : f.duration > 0xffffff ? 0xffffff : f.duration));
+            m.push_back(0x02);  // do not blend, do not dispose: every frame is a full canvas
+            put_image_chunks(m, f);
+            put_chunk(body, "ANMF", m.data(), m.size());
+        }
+    } else {
+        put_image_chunks(body, f0);
+    }
+    std::vector<uint8_t>& file = *file_out;
+    file.clear();
+    file.insert(file.end(), {'R', 'I', 'F', 'F'});
+    put_le32(file, (uint32_t)(4 + body.size()));
+    file.insert(file.end(), {'W', 'E', 'B', 'P'});
+    file.insert(file.end(), body.begin(), body.end());
 }
 
 }  // namespace lp
@@ -329,46 +668,8 @@ size_t webp_encoder_write(webp_encoder e, const opencv_mat src, const int* opt, 
     }
     if (!src) {  // finalise
         if (e->frame_count == 1 || e->frames.empty()) return 0;
-        std::vector<uint8_t> body;
-        const bool anim = e->frames.size() > 1;
-        bool any_alpha = false;
-        for (const EncodedFrame& f : e->frames) any_alpha |= f.has_alpha;
-        const EncodedFrame& f0 = e->frames[0];
-        const bool need_vp8x = anim || !e->icc.empty() || !f0.alph.empty();
-        if (need_vp8x) {
-            std::vector<uint8_t> x;
-            x.push_back((uint8_t)((anim ? 0x02 : 0) | (any_alpha ? 0x10 : 0) | (!e->icc.empty() ? 0x20 : 0)));
-            x.insert(x.end(), 3, 0);
-            put_le24(x, (uint32_t)f0.width - 1);
-            put_le24(x, (uint32_t)f0.height - 1);
-            put_chunk(body, "VP8X", x.data(), x.size());
-            if (!e->icc.empty()) put_chunk(body, "ICCP", e->icc.data(), e->icc.size());
-        }
-        if (anim) {
-            std::vector<uint8_t> a;
-            put_le32(a, e->bgcolor);
-            a.push_back((uint8_t)(e->loop_count & 0xff));
-            a.push_back((uint8_t)((e->loop_count >> 8) & 0xff));
-            put_chunk(body, "ANIM", a.data(), a.size());
-            for (const EncodedFrame& f : e->frames) {
-                std::vector<uint8_t> m;
-                put_le24(m, 0);
-                put_le24(m, 0);
-                put_le24(m, (uint32_t)f.width - 1);
-                put_le24(m, (uint32_t)f.height - 1);
-                put_le24(m, (uint32_t)(f.duration < 0 ? 0 : f.duration > 0xffffff ? 0xffffff : f.duration));
-                m.push_back(0x02);  // do not blend, do not dispose: every frame is a full canvas
-                put_image_chunks(m, f);
-                put_chunk(body, "ANMF", m.data(), m.size());
-            }
-        } else {
-            put_image_chunks(body, f0);
-        }
         std::vector<uint8_t> file;
-        file.insert(file.end(), {'R', 'I', 'F', 'F'});
-        put_le32(file, (uint32_t)(4 + body.size()));
-        file.insert(file.end(), {'W', 'E', 'B', 'P'});
-        file.insert(file.end(), body.begin(), body.end());
+        webp_assemble(e->frames.data(), (int)e->frames.size(), e->icc.data(), e->icc.size(), e->bgcolor, e->loop_count, &file);
         if (file.size() > e->dst_len) {
             fprintf(stderr, "Error: Final encoded size (%zu) exceeds buffer size (%zu)\n", file.size(), e->dst_len);
             return 0;
@@ -404,12 +705,18 @@ size_t webp_encoder_write(webp_encoder e, const opencv_mat src, const int* opt, 
     } else {
         rc = vp8_encode_dev(dev, step, cols, rows, channels, (int)quality, &f.image, st);
         if (!rc && channels == 4) {
+            // libwebp writes no ALPH chunk for an opaque picture (WebPEncode: WebPPictureHasTransparency)
             uint8_t* plane = nullptr;
-            if (cudaMallocAsync(&plane, (size_t)cols * rows + 256, st) != cudaSuccess) return 0;
-            dim3 grid(ceil_div(cols, 256), rows);
-            extract_alpha_kernel<<<grid, 256, 0, st>>>(dev, step, cols, rows, plane);
+            if (cudaMallocAsync(&plane, (size_t)cols * rows + 512, st) != cudaSuccess) return 0;
+            uint32_t* d_flag = reinterpret_cast<uint32_t*>(plane + round_up((size_t)cols * rows, (size_t)256));
+            cudaMemsetAsync(d_flag, 0, 4, st);
+            dim3 grid(ceil_div(cols, 256), rows, 1);
+            extract_alpha_batch_kernel<<<grid, 256, 0, st>>>(dev, 0, step, cols, rows, plane, d_flag);
             g_launches++;
-            rc = vp8l_encode_dev(plane, (size_t)cols, cols, rows, 1, &f.alph, st);
+            uint32_t flag = 0;
+            if (cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) rc = LP_ERR_CUDA;
+            f.has_alpha = flag != 0;
+            if (!rc && flag) rc = vp8l_encode_dev(plane, (size_t)cols, cols, rows, 1, &f.alph, st);
             cudaFreeAsync(plane, st);
         }
     }

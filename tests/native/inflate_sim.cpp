@@ -14,3 +14,9 @@ extern "C" int lp_inflate_sim(const uint8_t* z, uint32_t z_len, uint8_t* out, ui
     lpinf::Stream s{z, z_len, out, cap, ml.data()};
     return lpinf::inflate_stream(ws, s, produced);
 }
+
+#ifdef LP_INF_STATS
+extern "C" void lp_inflate_sim_stats(unsigned long long* out16, int reset) {
+    for (int i = 0; i < 16; i++) { out16[i] = lpinf::g_stats[i]; if (reset) lpinf::g_stats[i] = 0; }
+}
+#endif

@@ -189,6 +189,31 @@ void lp_batch_sync_rounds(const lp_batch* b, double* mean, int* max);
 const uint8_t* lp_batch_decoded_dev(const lp_batch* b, size_t* image_stride);
 const uint8_t* lp_batch_resized_dev(const lp_batch* b, size_t* image_stride);
 
+/* ---- heterogeneous batch: any supported formats and sizes, one set of options ----------------
+ * (BASELINE configs 3, 4, 5: PNG -> WebP, animated GIF -> animated WebP, mixed JPEG / PNG / WebP -> JPEG.)
+ * Per-item semantics, status and bytes are those of lp_transform(in[i], ..., opt, out[i], out_cap, ...).
+ * Items are grouped by decoder and source geometry and every stage of a group is one grid launch
+ * (csrc/xbatch.cu); whatever the grid path does not cover runs through lp_transform inside the call. */
+typedef struct lp_xbatch lp_xbatch;
+typedef struct lp_xbatch_config {
+    int device;          /* CUDA ordinal */
+    size_t arena_bytes;  /* device working memory; 0 = 60 % of what is free at creation */
+    int host_threads;    /* header parsing / per-image fallback workers; 0 = auto */
+    int max_size;        /* ImageOps maxSize for every item (lp_transform's max_size); 0 = 8192 */
+} lp_xbatch_config;
+typedef struct lp_xbatch_stats {
+    int grid_items, fallback_items, groups, launches;
+    double ms_parse, ms_grid, ms_fallback, ms_total; /* host wall clock of the phases */
+    double ms_decode, ms_resize, ms_encode;          /* CUDA-event time of the grid stages, summed over chunks */
+    size_t h2d_bytes, d2h_bytes;
+} lp_xbatch_stats;
+lp_xbatch* lp_xbatch_create(const lp_xbatch_config* cfg);
+void lp_xbatch_destroy(lp_xbatch* x);
+int lp_xbatch_transform(lp_xbatch* x, const uint8_t* const* in, const size_t* in_len, int n,
+                        const lp_image_options* opt, uint8_t* const* out, size_t out_cap, size_t* out_len,
+                        int* status);
+void lp_xbatch_get_stats(const lp_xbatch* x, lp_xbatch_stats* out);
+
 /* ---- single stages on device pointers, on `stream` (a cudaStream_t) -------- */
 
 /* Batched crop + INTER_AREA resize of `n` packed u8 images that share one

@@ -400,3 +400,62 @@ class Batch:
 
     def last_launches(self):
         return self.lib.l.lp_batch_last_launches(self.h)
+
+
+# ----------------------------------------------------------------------------------------------
+class _XBatchConfig(C.Structure):
+    _fields_ = [("device", C.c_int), ("arena_bytes", C.c_size_t), ("host_threads", C.c_int), ("max_size", C.c_int)]
+
+
+class _XBatchStats(C.Structure):
+    _fields_ = [("grid_items", C.c_int), ("fallback_items", C.c_int), ("groups", C.c_int), ("launches", C.c_int),
+                ("ms_parse", C.c_double), ("ms_grid", C.c_double), ("ms_fallback", C.c_double), ("ms_total", C.c_double),
+                ("ms_decode", C.c_double), ("ms_resize", C.c_double), ("ms_encode", C.c_double),
+                ("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t)]
+
+
+class XBatch:
+    """lp_xbatch_*: N independent images of any supported format / size, one set of options, grouped into grid
+    launches; per-item results are those of lp_transform (include/lilliput_b200.h)."""
+
+    def __init__(self, lib: Lib, device: int = 0, arena_bytes: int = 0, host_threads: int = 0, max_size: int = 8192):
+        self.lib = lib
+        l = lib.l
+        l.lp_xbatch_create.restype = C.c_void_p
+        l.lp_xbatch_create.argtypes = [C.POINTER(_XBatchConfig)]
+        l.lp_xbatch_destroy.argtypes = [C.c_void_p]
+        l.lp_xbatch_transform.restype = C.c_int
+        l.lp_xbatch_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_ImageOptions),
+                                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        l.lp_xbatch_get_stats.argtypes = [C.c_void_p, C.POINTER(_XBatchStats)]
+        cfg = _XBatchConfig(device, arena_bytes, host_threads, max_size)
+        self.h = l.lp_xbatch_create(C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("lp_xbatch_create failed (no CUDA device / out of memory)")
+
+    def close(self):
+        if self.h:
+            self.lib.l.lp_xbatch_destroy(self.h)
+            self.h = None
+
+    def transform_into(self, ptrs, lens, n, copt, out_ptrs, out_cap, out_lens, status):
+        """Raw call for bench.py: every array prebuilt."""
+        return self.lib.l.lp_xbatch_transform(self.h, ptrs, lens, n, C.byref(copt), out_ptrs, out_cap, out_lens, status)
+
+    def transform(self, bufs, opt: ImageOptions, out_cap: int = 1 << 20):
+        n = len(bufs)
+        ptrs, lens, keep = Batch._ptr_arrays(bufs)
+        out = np.empty((n, out_cap), dtype=np.uint8)
+        out_ptrs = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
+        out_lens = (C.c_size_t * n)()
+        status = (C.c_int * n)()
+        copt = opt._c()
+        rc = self.lib.l.lp_xbatch_transform(self.h, ptrs, lens, n, C.byref(copt), out_ptrs, out_cap, out_lens, status)
+        if rc:
+            raise LilliputError(rc)
+        return [out[i, : out_lens[i]].tobytes() for i in range(n)], list(status)
+
+    def stats(self) -> dict:
+        s = _XBatchStats()
+        self.lib.l.lp_xbatch_get_stats(self.h, C.byref(s))
+        return {k: getattr(s, k) for k, _ in _XBatchStats._fields_}

@@ -14,6 +14,7 @@
 // is always "the previous string plus one more pixel", i.e. a span of the output -- so emitting a
 // code is a warp-wide copy instead of a pointer chase.
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -167,10 +168,8 @@ struct LzwBits {
     }
 };
 
-__global__ void __launch_bounds__(32) gif_lzw_kernel(GifFrameDev f) {
-    __shared__ uint32_t t_off[4096];
-    __shared__ uint16_t t_len[4096];
-    const int lane = threadIdx.x;
+__device__ __forceinline__ int gif_lzw_decode_frame(const GifFrameDev& f, uint32_t* t_off, uint16_t* t_len) {
+    const int lane = threadIdx.x & 31;
     // giflib's DGifDecompressInput/Line state machine: `running` counts codes read since the last
     // clear (+ clear + 2); the code width grows when it passes maxcode1; a code creates entry
     // running - 2 from the previous string.
@@ -234,7 +233,14 @@ __global__ void __launch_bounds__(32) gif_lzw_kernel(GifFrameDev f) {
         __syncwarp();
         o += take;
     }
-    if (lane == 0) *f.status = status;
+    return status;
+}
+
+__global__ void __launch_bounds__(32) gif_lzw_kernel(GifFrameDev f) {
+    __shared__ uint32_t t_off[4096];
+    __shared__ uint16_t t_len[4096];
+    const int status = gif_lzw_decode_frame(f, t_off, t_len);
+    if (threadIdx.x == 0) *f.status = status;
 }
 
 struct GifCompose {
@@ -283,6 +289,300 @@ __global__ void gif_compose_kernel(const GifCompose c) {
     *reinterpret_cast<uchar4*>(c.canvas + at) = px;
 }
 
+
+// ------------------------------------------------------------------ batch decode (xbatch.cu)
+// Every frame of every animation of a task: sub-block removal and LZW run one warp per FRAME (frames are
+// independent code streams); the compositor runs one thread per canvas PIXEL and walks the frames of its
+// animation in order -- disposal, snapshot and drawing only ever look at the same pixel of the previous
+// state (ref giflib.cpp:349-568), so the frame sequence is a per-pixel recurrence.
+
+struct GifFrameJob {
+    uint64_t data_pos;   // first sub-block length byte, offset from the scratch base
+    uint64_t lzw_off;    // contiguous code stream (written by the deblock kernel)
+    uint64_t idx_off;    // npix palette indices
+    uint64_t colors_off; // colour table in force (inside the uploaded file)
+    uint32_t lzw_len, npix;
+    int32_t min_code;
+    int32_t fl, ft, fw, fh, interlace, transparent, ncolors;
+    int32_t prev_disposal, pl, pt, pw, ph;
+    int32_t status;
+    int32_t pad_;
+};
+struct GifAnimJob {
+    int32_t first_frame, nframes;
+    uchar4 bg;  // B, G, R, A of the first frame's background fill
+};
+
+constexpr int kGifDeblockWarps = 4;
+__global__ void __launch_bounds__(kGifDeblockWarps * 32) gif_deblock_kernel(GifFrameJob* jobs, uint8_t* base, int n) {
+    const int f = blockIdx.x * kGifDeblockWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= n) return;
+    const GifFrameJob j = jobs[f];
+    const uint8_t* src = base + j.data_pos;
+    uint8_t* dst = base + j.lzw_off;
+    uint32_t o = 0;
+    while (o < j.lzw_len) {
+        const uint32_t len = src[0];  // every lane reads the same byte (a broadcast load)
+        if (len == 0) break;
+        const uint32_t take = min(len, j.lzw_len - o);
+        for (uint32_t i = lane; i < take; i += 32) dst[o + i] = src[1 + i];
+        o += take;
+        src += 1 + len;
+    }
+    for (uint32_t i = lane; i < 16; i += 32) dst[o + i] = 0;  // the word reader may look one word past the end
+}
+
+__global__ void __launch_bounds__(32) gif_lzw_batch_kernel(GifFrameJob* jobs, uint8_t* base) {
+    __shared__ uint32_t t_off[4096];
+    __shared__ uint16_t t_len[4096];
+    GifFrameJob& j = jobs[blockIdx.x];
+    GifFrameDev f{base + j.lzw_off, j.lzw_len, j.min_code, j.npix, base + j.idx_off, nullptr};
+    const int status = gif_lzw_decode_frame(f, t_off, t_len);
+    if (threadIdx.x == 0) j.status = status;
+}
+
+__global__ void gif_compose_batch_kernel(const GifAnimJob* anims, const GifFrameJob* jobs, const uint8_t* base, int cw,
+                                         int chh, uint8_t* canvases, size_t canvas_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cw) return;
+    const GifAnimJob a = anims[blockIdx.z];
+    const size_t at = ((size_t)y * cw + x) * 4;
+    uchar4 px = make_uchar4(0, 0, 0, 0), snap = make_uchar4(0, 0, 0, 0);  // canvas and prev_frame_bgra start zeroed
+    for (int k = 0; k < a.nframes; k++) {
+        const GifFrameJob& c = jobs[a.first_frame + k];
+        if (k == 0) {
+            px = a.bg;
+        } else {
+            const bool in_prev = x >= c.pl && x < c.pl + c.pw && y >= c.pt && y < c.pt + c.ph;
+            if (in_prev && c.prev_disposal == 2) px = a.bg;
+            else if (in_prev && c.prev_disposal == 3) px = snap;
+            snap = px;  // snapshot after disposal, before drawing
+        }
+        const int fx = x - c.fl, fy = y - c.ft;
+        if (fx >= 0 && fx < c.fw && fy >= 0 && fy < c.fh) {
+            int row = fy;
+            if (c.interlace) {
+                const int h = c.fh;
+                const int n0 = (h + 7) / 8, n1 = (h + 3) / 8, n2 = (h + 1) / 4;
+                if ((fy & 7) == 0) row = fy / 8;
+                else if ((fy & 7) == 4) row = n0 + fy / 8;
+                else if ((fy & 3) == 2) row = n0 + n1 + fy / 4;
+                else row = n0 + n1 + n2 + fy / 2;
+            }
+            const int idx = base[c.idx_off + (size_t)row * c.fw + fx];
+            if (idx != c.transparent && idx < c.ncolors) {
+                const uint8_t* pal = base + c.colors_off + (size_t)idx * 3;
+                px = make_uchar4(pal[2], pal[1], pal[0], 255);
+            }
+        }
+        *reinterpret_cast<uchar4*>(canvases + (size_t)(a.first_frame + k) * canvas_stride + at) = px;
+    }
+}
+
+struct GifFramePlan {
+    size_t data_pos = 0, colors_pos = 0;
+    uint32_t lzw_len = 0;
+    int left = 0, top = 0, width = 0, height = 0, interlace = 0, ncolors = 0, min_code = 0;
+    int transparent = -1, disposal = 0, delay = 0;
+};
+struct GifAnimPlan {
+    int sw = 0, sh = 0, loop_count = 1;
+    uint32_t bgcolor = 0xFFFFFFFFu;   // gifDecoder.BackgroundColor()
+    uint8_t bg[4] = {255, 255, 255, 255};  // B, G, R, A of the first frame's fill (ref giflib.cpp:595-636)
+    std::vector<GifFramePlan> frames;
+    size_t lzw_total = 0, idx_total = 0, file_len = 0;
+};
+
+// The walk gifDecoder + ImageOps.Transform would make over a WELL-FORMED file (every record readable, every
+// frame with a colour table, terminator present); anything else returns nullptr and the file takes the
+// per-image path, which reproduces the reference's handling of damaged files.
+GifAnimPlan* gif_plan_parse(const uint8_t* data, size_t len, int max_frames) {
+    GifReader r;
+    r.p = data;
+    r.n = len;
+    if (!r.open() || r.sw <= 0 || r.sh <= 0) return nullptr;
+    std::unique_ptr<GifAnimPlan> p(new GifAnimPlan);
+    p->sw = r.sw;
+    p->sh = r.sh;
+    p->file_len = len;
+    bool found_loop = false, found_gcb = false, have_pending = false;
+    GifGcb pending, first_gcb;
+    for (;;) {
+        const int rec = r.record();
+        if (rec < 0) return nullptr;
+        if (rec == 2) break;
+        if (rec == 1) {
+            uint8_t label;
+            if (!r.get(&label)) return nullptr;
+            const uint8_t* d;
+            int n;
+            if (!r.sub_block(&d, &n)) return nullptr;
+            bool first = true;
+            while (n != 0) {
+                if (first && label == 0xF9) {
+                    GifGcb g;
+                    if (!gcb_from_block(d, n, &g)) return nullptr;  // malformed control block: per image
+                    pending = g;
+                    have_pending = true;
+                    if (!found_gcb) {
+                        found_gcb = true;
+                        first_gcb = g;
+                    }
+                } else if (first && !found_loop && label == 0xFF && n >= 11 && !memcmp(d, "NETSCAPE2.0", 11)) {
+                    const uint8_t* d2;
+                    int n2;
+                    const size_t save = r.pos;
+                    if (!r.sub_block(&d2, &n2)) return nullptr;
+                    if (n2 >= 3 && d2[0] == 1) {
+                        p->loop_count = d2[1] | (d2[2] << 8);
+                        found_loop = true;
+                    }
+                    r.pos = save;  // the generic walk below reads it again
+                }
+                first = false;
+                if (!r.sub_block(&d, &n)) return nullptr;
+            }
+            continue;
+        }
+        GifImage im;
+        if (!r.image_header(&im)) return nullptr;
+        if (im.width <= 0 || im.height <= 0 || im.width > 10000 || im.height > 10000) return nullptr;
+        GifFramePlan f;
+        f.left = im.left; f.top = im.top; f.width = im.width; f.height = im.height;
+        f.interlace = im.interlace ? 1 : 0;
+        f.min_code = im.min_code;
+        const uint8_t* colors = im.colors ? im.colors : r.gct;
+        f.ncolors = im.colors ? im.ncolors : r.gct_colors;
+        if (!colors) return nullptr;
+        f.colors_pos = (size_t)(colors - data);
+        f.data_pos = r.pos;
+        size_t total = 0;
+        for (;;) {
+            const uint8_t* d;
+            int n;
+            if (!r.sub_block(&d, &n)) return nullptr;
+            if (n == 0) break;
+            total += (size_t)n;
+        }
+        if (total > 0xFFFFFF00u) return nullptr;
+        f.lzw_len = (uint32_t)total;
+        const GifGcb g = have_pending ? pending : GifGcb();
+        f.transparent = g.transparent;
+        f.disposal = g.disposal;
+        f.delay = g.delay;
+        if (p->frames.empty()) {
+            uint8_t R, G, B, A;
+            background_color(r, g, &R, &G, &B, &A);
+            p->bg[0] = B; p->bg[1] = G; p->bg[2] = R; p->bg[3] = A;
+        }
+        have_pending = false;  // extensions are cleared after a frame (ref giflib.cpp:289-296)
+        pending = GifGcb();
+        p->lzw_total += round_up(total + 32, (size_t)16);
+        p->idx_total += round_up((size_t)im.width * im.height + 64, (size_t)16);
+        p->frames.push_back(f);
+        if ((int)p->frames.size() > max_frames) return nullptr;
+    }
+    if (p->frames.empty()) return nullptr;
+    {   // gifDecoder.BackgroundColor(): from the first graphic control block of the file (ref giflib.cpp:1349-1362)
+        if (!found_gcb) first_gcb.transparent = 0;  // the reference's zero-initialised stand-in
+        uint8_t R, G, B, A;
+        background_color(r, first_gcb, &R, &G, &B, &A);
+        p->bgcolor = ((uint32_t)A << 24) | ((uint32_t)R << 16) | ((uint32_t)G << 8) | B;
+    }
+    return p.release();
+}
+void gif_plan_free(GifAnimPlan* p) { delete p; }
+void gif_plan_info(const GifAnimPlan* p, int* width, int* height, int* nframes, uint32_t* bgcolor, int* loop_count) {
+    if (width) *width = p->sw;
+    if (height) *height = p->sh;
+    if (nframes) *nframes = (int)p->frames.size();
+    if (bgcolor) *bgcolor = p->bgcolor;
+    if (loop_count) *loop_count = p->loop_count;
+}
+int gif_plan_delay_ms(const GifAnimPlan* p, int frame) { return p->frames[(size_t)frame].delay * 10; }  // ref giflib.go:212
+size_t gif_plan_device_bytes(const GifAnimPlan* p) {
+    return round_up(p->file_len + 64, (size_t)256) + p->lzw_total + p->idx_total +
+           p->frames.size() * (sizeof(GifFrameJob) + 64) + 4096;
+}
+
+int gif_decode_batch(GifAnimPlan* const* plans, const uint8_t* const* files, const size_t* file_len, int n,
+                     uint8_t* d_scratch, size_t scratch_bytes, uint8_t* d_canvases, size_t canvas_stride,
+                     const int* first_frame, int* h_status, cudaStream_t st) {
+    if (n <= 0) return LP_OK;
+    const int nf = first_frame[n];
+    std::vector<GifFrameJob> jobs((size_t)nf);
+    std::vector<GifAnimJob> anims((size_t)n);
+    size_t off = 0;
+    std::vector<size_t> file_off((size_t)n);
+    for (int a = 0; a < n; a++) {
+        file_off[a] = off;
+        off += round_up(file_len[a] + 64, (size_t)256);
+    }
+    const int cw = plans[0]->sw, chh = plans[0]->sh;
+    for (int a = 0; a < n; a++) {
+        const GifAnimPlan& p = *plans[a];
+        if (p.sw != cw || p.sh != chh) return LP_ERR_BAD_ARGUMENT;
+        anims[a].first_frame = first_frame[a];
+        anims[a].nframes = (int)p.frames.size();
+        anims[a].bg = make_uchar4(p.bg[0], p.bg[1], p.bg[2], p.bg[3]);
+        int prev_disposal = 0, pl = 0, pt = 0, pw = 0, ph = 0;
+        for (size_t k = 0; k < p.frames.size(); k++) {
+            const GifFramePlan& f = p.frames[k];
+            GifFrameJob& j = jobs[(size_t)first_frame[a] + k];
+            memset(&j, 0, sizeof(j));
+            j.data_pos = file_off[a] + f.data_pos;
+            j.colors_off = file_off[a] + f.colors_pos;
+            j.lzw_off = off;
+            off += round_up((size_t)f.lzw_len + 32, (size_t)16);
+            j.lzw_len = f.lzw_len;
+            j.npix = (uint32_t)((size_t)f.width * f.height);
+            j.min_code = f.min_code;
+            j.fl = f.left; j.ft = f.top; j.fw = f.width; j.fh = f.height;
+            j.interlace = f.interlace;
+            j.transparent = f.transparent;
+            j.ncolors = f.ncolors;
+            j.prev_disposal = prev_disposal;
+            // previous rectangle clipped exactly as ref giflib.cpp:407-436 does
+            if (pl < 0) { pw += pl; pl = 0; }
+            if (pt < 0) { ph += pt; pt = 0; }
+            if (pl + pw > cw) pw = cw - pl;
+            if (pt + ph > chh) ph = chh - pt;
+            j.pl = pl; j.pt = pt; j.pw = pw < 0 ? 0 : pw; j.ph = ph < 0 ? 0 : ph;
+            prev_disposal = f.disposal;
+            pl = f.left; pt = f.top; pw = f.width; ph = f.height;
+        }
+    }
+    for (int k = 0; k < nf; k++) {
+        jobs[k].idx_off = off;
+        off += round_up((size_t)jobs[k].npix + 64, (size_t)16);
+    }
+    off = round_up(off, (size_t)256);
+    const size_t jobs_off = off;
+    off += round_up((size_t)nf * sizeof(GifFrameJob), (size_t)256);
+    const size_t anims_off = off;
+    off += round_up((size_t)n * sizeof(GifAnimJob), (size_t)256);
+    if (off > scratch_bytes) return LP_ERR_BUF_TOO_SMALL;
+    GifFrameJob* d_jobs = reinterpret_cast<GifFrameJob*>(d_scratch + jobs_off);
+    GifAnimJob* d_anims = reinterpret_cast<GifAnimJob*>(d_scratch + anims_off);
+    for (int a = 0; a < n; a++)
+        LP_CUDA_OK(cudaMemcpyAsync(d_scratch + file_off[a], files[a], file_len[a], cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nf * sizeof(GifFrameJob), cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaMemcpyAsync(d_anims, anims.data(), (size_t)n * sizeof(GifAnimJob), cudaMemcpyHostToDevice, st));
+    gif_deblock_kernel<<<ceil_div(nf, kGifDeblockWarps), kGifDeblockWarps * 32, 0, st>>>(d_jobs, d_scratch, nf);
+    gif_lzw_batch_kernel<<<nf, 32, 0, st>>>(d_jobs, d_scratch);
+    dim3 grid(ceil_div(cw, 128), chh, n);
+    gif_compose_batch_kernel<<<grid, 128, 0, st>>>(d_anims, d_jobs, d_scratch, cw, chh, d_canvases, canvas_stride);
+    g_launches += 3;
+    LP_CUDA_OK(cudaGetLastError());
+    LP_CUDA_OK(cudaMemcpyAsync(jobs.data(), d_jobs, (size_t)nf * sizeof(GifFrameJob), cudaMemcpyDeviceToHost, st));
+    LP_CUDA_OK(cudaStreamSynchronize(st));
+    for (int a = 0; a < n; a++) {
+        h_status[a] = 0;
+        for (int k = first_frame[a]; k < first_frame[a + 1]; k++)
+            if (jobs[k].status != 0) h_status[a] = LP_ERR_DECODING_FAILED;
+    }
+    return LP_OK;
+}
 
 // ------------------------------------------------------------------ encoder kernels
 // ref giflib.cpp:934-1098 (giflib_encoder_render_frame): every BGRA pixel of the composited frame

@@ -258,11 +258,39 @@ int webp_encode_lossy_batch(const uint8_t* d_frames, size_t img_stride, size_t r
 void webp_assemble(const WebpEncodedFrame* frames, int n, const uint8_t* icc, size_t icc_len, uint32_t bgcolor,
                    uint32_t loop_count, std::vector<uint8_t>* file);
 
+// ---- batch helpers of webp_decode.cu / gif_decode.cu (used by xbatch.cu) ------------------------
+struct WebpStillInfo {
+    int width = 0, height = 0;
+    size_t vp8_off = 0, vp8_len = 0;  // "VP8 " payload inside the file
+    bool simple_lossy = false;        // one VP8 key frame, no ALPH / ICCP / animation
+};
+bool webp_still_info(const uint8_t* data, size_t len, WebpStillInfo* out);
+int webp_vp8_decode_batch(const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len, int n, int width,
+                          int height, uint8_t* d_frames, size_t frame_stride, int* h_status, cudaStream_t st);
+struct GifAnimPlan;
+GifAnimPlan* gif_plan_parse(const uint8_t* data, size_t len, int max_frames);
+void gif_plan_free(GifAnimPlan* p);
+void gif_plan_info(const GifAnimPlan* p, int* width, int* height, int* nframes, uint32_t* bgcolor, int* loop_count);
+int gif_plan_delay_ms(const GifAnimPlan* p, int frame);
+size_t gif_plan_device_bytes(const GifAnimPlan* p);
+// decodes + composites every frame of `n` animations of one canvas size: animation a, frame f lands at
+// d_canvases + (first_frame[a] + f) * canvas_stride (BGRA); h_status per animation
+int gif_decode_batch(GifAnimPlan* const* plans, const uint8_t* const* files, const size_t* file_len, int n,
+                     uint8_t* d_scratch, size_t scratch_bytes, uint8_t* d_canvases, size_t canvas_stride,
+                     const int* first_frame, int* h_status, cudaStream_t st);
+
 // ---- pixel_ops.cu --------------------------------------------------------------------------
 int orient_launch(const uint8_t* src, int w, int h, int channels, int orientation, uint8_t* dst,
                   cudaStream_t st);
 int copy_region_launch(const uint8_t* src, size_t src_step, int src_ch, uint8_t* dst,
                        size_t dst_step, int dst_ch, int w, int h, cudaStream_t st);
+int compact_launch(const uint8_t* src, size_t stride, const uint32_t* len, uint32_t cap, int n, uint8_t* dst,
+                   unsigned long long* off /* n + 1 */, cudaStream_t st);
+struct SegCopy {
+    uint64_t src, dst;  // byte offsets from one base pointer
+    uint32_t len, pad_;
+};
+int seg_copy_launch(const SegCopy* d_segs, int n, uint8_t* base, cudaStream_t st);
 int blend_region_launch(const uint8_t* src, size_t src_step, int src_ch, uint8_t* dst,
                         size_t dst_step, int dst_ch, int w, int h, cudaStream_t st);
 

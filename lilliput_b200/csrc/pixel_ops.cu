@@ -127,3 +127,90 @@ int fill_launch(uint8_t* dst, size_t step, int C, int w, int h, int b, int g, in
 }
 
 }  // namespace lp
+
+// ------------------------------------------------------------------ slot compaction
+// n variable-length byte strings in fixed-size slots (string i = len[i] bytes at src + i*stride) -> one
+// contiguous buffer (each string at a 16-byte aligned offset), so a batch's encoded outputs cross PCIe as
+// one copy of the bytes actually used instead of n whole slots.  off[i] = start of string i, off[n] = total.
+namespace lp {
+
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const uint32_t* len, uint32_t cap, int n, unsigned long long* off) {
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        uint32_t l = i < n ? len[i] : 0;
+        if (l > cap) l = 0;  // a slot cannot hold more than its capacity: treat as failed (length 0)
+        unsigned long long v = ((unsigned long long)l + 15ull) & ~15ull, inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long s = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += t;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const unsigned long long ex = carry + (wid ? warp_sums[wid - 1] : 0) + inc - v;
+        if (i < n) off[i] = ex;
+        __syncthreads();
+        if (tid == 1023) carry = ex + v;
+        __syncthreads();
+    }
+    if (tid == 0) off[n] = carry;
+}
+
+__global__ void compact_copy_kernel(const uint8_t* src, size_t stride, const uint32_t* len, uint32_t cap,
+                                    const unsigned long long* off, uint8_t* dst) {
+    const int i = blockIdx.x;
+    uint32_t l = len[i];
+    if (l > cap) l = 0;
+    const uint8_t* s = src + (size_t)i * stride;
+    uint8_t* d = dst + off[i];
+    if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+        const uint32_t nv = (l + 15) / 16;  // slots are padded: reading the last vector whole stays inside the slot
+        for (uint32_t k = threadIdx.x; k < nv; k += blockDim.x)
+            reinterpret_cast<uint4*>(d)[k] = reinterpret_cast<const uint4*>(s)[k];
+    } else {
+        for (uint32_t k = threadIdx.x; k < l; k += blockDim.x) d[k] = s[k];
+    }
+}
+
+int compact_launch(const uint8_t* src, size_t stride, const uint32_t* len, uint32_t cap, int n, uint8_t* dst,
+                   unsigned long long* off, cudaStream_t st) {
+    if (n <= 0) return LP_OK;
+    compact_scan_kernel<<<1, 1024, 0, st>>>(len, cap, n, off);
+    compact_copy_kernel<<<n, 128, 0, st>>>(src, stride, len, cap, off, dst);
+    g_launches += 2;
+    LP_CUDA_OK(cudaGetLastError());
+    return LP_OK;
+}
+
+// `n` byte ranges copied inside one device buffer (PNG files whose IDAT payload is split over many chunks:
+// the zlib stream is gathered on the device instead of on the host)
+__global__ void seg_copy_kernel(const SegCopy* segs, uint8_t* base) {
+    const SegCopy sg = segs[blockIdx.x];
+    const uint8_t* s = base + sg.src;
+    uint8_t* d = base + sg.dst;
+    for (uint32_t k = threadIdx.x; k < sg.len; k += blockDim.x) d[k] = s[k];
+}
+int seg_copy_launch(const SegCopy* d_segs, int n, uint8_t* base, cudaStream_t st) {
+    if (n <= 0) return LP_OK;
+    seg_copy_kernel<<<n, 256, 0, st>>>(d_segs, base);
+    g_launches++;
+    LP_CUDA_OK(cudaGetLastError());
+    return LP_OK;
+}
+
+}  // namespace lp

@@ -548,6 +548,79 @@ static bool webp_parse(const uint8_t* b, size_t size, WebpContainer* c) {
     return true;
 }
 
+// ------------------------------------------------------------------ batch helpers (xbatch.cu)
+
+// What the batch path needs to know about a file: is it ONE lossy key frame without alpha, profile or
+// animation (then its VP8 payload can join a grid launch), and where that payload lies.
+bool webp_still_info(const uint8_t* data, size_t len, WebpStillInfo* out) {
+    WebpContainer c;
+    if (!webp_parse(data, len, &c)) return false;
+    if (c.frames.size() != 1) return true;
+    const WebpFrame& f = c.frames[0];
+    out->width = c.canvas_w;
+    out->height = c.canvas_h;
+    out->vp8_off = f.img_off;
+    out->vp8_len = f.img_len;
+    out->simple_lossy = !f.lossless && !f.has_alph && !c.has_icc && !(c.flags & kFlagAnim) && !(c.flags & kFlagAlpha) &&
+                        f.width == c.canvas_w && f.height == c.canvas_h && f.img_off + f.img_len <= len;
+    return true;
+}
+
+__global__ void vp8_output_batch_kernel(const uint8_t* work, size_t work_stride, int mb_w, int mb_h, int width, int height,
+                                        uint8_t* frames, size_t frame_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= width) return;
+    const uint8_t* base = work + (size_t)blockIdx.z * work_stride;
+    const size_t ypl = (size_t)mb_w * 16 * mb_h * 16;
+    const uint8_t* yp = base;
+    const uint8_t* up = base + ypl;
+    const uint8_t* vp = up + ypl / 4;
+    const int u = vp8::upsample_at(up, mb_w * 8, width, height, x, y);
+    const int v = vp8::upsample_at(vp, mb_w * 8, width, height, x, y);
+    uint8_t bgr[3];
+    vp8::yuv_to_bgr(yp[(size_t)y * (mb_w * 16) + x], u, v, bgr);
+    uint8_t* d = frames + (size_t)blockIdx.z * frame_stride + ((size_t)y * width + x) * 3;
+    d[0] = bgr[0];
+    d[1] = bgr[1];
+    d[2] = bgr[2];
+}
+
+// n VP8 key frames of one size: one warp per frame (vp8_decode_kernel), then every pixel of every frame
+// through the fancy upsampler + colour conversion in one launch.  Packed BGR frames, frame_stride apart.
+int webp_vp8_decode_batch(const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len, int n, int width,
+                          int height, uint8_t* d_frames, size_t frame_stride, int* h_status, cudaStream_t st) {
+    if (n <= 0) return LP_OK;
+    const int mb_w = (width + 15) >> 4, mb_h = (height + 15) >> 4;
+    const size_t wb = vp8::work_bytes(mb_w, mb_h);
+    uint8_t* scratch = nullptr;
+    const size_t items_b = round_up((size_t)n * sizeof(Vp8Item), (size_t)256), stat_b = round_up((size_t)n * 4, (size_t)256);
+    if (cudaMallocAsync(&scratch, items_b + stat_b + (size_t)n * wb, st) != cudaSuccess) {
+        cudaGetLastError();
+        return LP_ERR_CUDA;
+    }
+    Vp8Item* d_items = reinterpret_cast<Vp8Item*>(scratch);
+    int* d_status = reinterpret_cast<int*>(scratch + items_b);
+    uint8_t* d_work = scratch + items_b + stat_b;
+    std::vector<Vp8Item> items((size_t)n);
+    for (int i = 0; i < n; i++) items[i] = Vp8Item{d_in + in_off[i], in_len[i], d_work + (size_t)i * wb, d_status + i, mb_w, mb_h};
+    int rc = LP_OK;
+    cudaMemsetAsync(d_status, 0, (size_t)n * 4, st);
+    if (cudaMemcpyAsync(d_items, items.data(), (size_t)n * sizeof(Vp8Item), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = LP_ERR_CUDA;
+    if (!rc) {
+        vp8_decode_kernel<<<ceil_div(n, kVp8WarpsPerBlock), kVp8WarpsPerBlock * 32, 0, st>>>(d_items, n);
+        dim3 grid(ceil_div(width, 128), height, n);
+        vp8_output_batch_kernel<<<grid, 128, 0, st>>>(d_work, wb, mb_w, mb_h, width, height, d_frames, frame_stride);
+        g_launches += 2;
+        if (cudaGetLastError() != cudaSuccess) rc = LP_ERR_CUDA;
+    }
+    if (!rc && (cudaMemcpyAsync(h_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess))  // (also keeps `items` alive until the copy has been consumed)
+        rc = LP_ERR_CUDA;
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
 // The mat handle is defined in abi_opencv.cu.
 const uint8_t* mat_host_bytes(const void* mat, size_t* len);
 int mat_bind_device_frame(void* mat, int cols, int rows, int type, uint8_t** dev, size_t* step);

@@ -68,18 +68,28 @@ extern "C" double ref_bench_transform(const uint8_t* const* in, const size_t* in
 }
 
 // Exactly `total` Transforms spread over `threads` workers (round-robin over the n inputs);
-// returns elapsed seconds (<0 on error).  One bench.py "step" of the reference arm.
+// returns elapsed seconds (<0 on error).  One bench.py "step" of the reference arm.  The clock starts when
+// every worker exists and has run one untimed Transform (its thread-local ImageOps and framebuffers are
+// allocated and touched, as in a long-running service: SURVEY 8(d) "framebuffers reused like NewImageOps"),
+// so thread start-up and first-touch page faults are outside the timed region.
 extern "C" double ref_transform_many(const uint8_t* const* in, const size_t* in_len, int n,
                                      const lp_image_options* opt, int max_size, int threads,
                                      size_t out_cap, long total, int* first_error) {
     cv::setNumThreads(1);
     std::atomic<long> next{0};
     std::atomic<int> err{0};
-    auto t0 = std::chrono::steady_clock::now();
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; t++) {
-        pool.emplace_back([&]() {
+        pool.emplace_back([&, t]() {
             std::vector<uint8_t> out(out_cap);
+            {
+                size_t len = 0;
+                (void)lp_transform(in[t % n], in_len[t % n], opt, out.data(), out.size(), &len, max_size);
+            }
+            ready.fetch_add(1);
+            while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
             for (;;) {
                 long k = next.fetch_add(1);
                 if (k >= total || err.load()) break;
@@ -94,6 +104,9 @@ extern "C" double ref_transform_many(const uint8_t* const* in, const size_t* in_
             }
         });
     }
+    while (ready.load() < threads) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
     for (auto& th : pool) th.join();
     double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (first_error) *first_error = err.load();

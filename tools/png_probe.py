@@ -37,3 +37,9 @@ for (w, h, c) in cases:
         for _ in range(3): lib.decode(p)
         ms = (time.perf_counter() - t) / 3 * 1e3
         print(json.dumps({"png": f"{w}x{h}x{c}", "filter": ft, "bytes": len(p), "ok": ok, "ms_per_decode": round(ms, 2)}), flush=True)
+if os.environ.get("LP_CUDA_LIB", "").endswith("_stats.so"):
+    import ctypes as C
+    st = (C.c_ulonglong * 16)()
+    lib.l.lp_png_inflate_stats(st, 0)
+    names = ["blocks", "windows", "rounds", "redecodes", "partial", "matches", "match_rounds", "", "clk_header_tables", "clk_load_window", "clk_passA", "clk_passB", "clk_passC", "clk_matches", "clk_flush", ""]
+    print(json.dumps({n: int(v) for n, v in zip(names, st) if n}))

@@ -483,11 +483,14 @@ GifAnimPlan* gif_plan_parse(const uint8_t* data, size_t len, int max_frames) {
         if ((int)p->frames.size() > max_frames) return nullptr;
     }
     if (p->frames.empty()) return nullptr;
-    {   // gifDecoder.BackgroundColor(): from the first graphic control block of the file (ref giflib.cpp:1349-1362)
-        if (!found_gcb) first_gcb.transparent = 0;  // the reference's zero-initialised stand-in
+    // gifDecoder.BackgroundColor() (ref giflib.cpp:1308-1431): set when the walk meets the file's first graphic
+    // control block; a file that reaches its terminator without one keeps the initial white with alpha 0
+    if (found_gcb) {
         uint8_t R, G, B, A;
         background_color(r, first_gcb, &R, &G, &B, &A);
         p->bgcolor = ((uint32_t)A << 24) | ((uint32_t)R << 16) | ((uint32_t)G << 8) | B;
+    } else {
+        p->bgcolor = 0x00FFFFFFu;
     }
     return p.release();
 }

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -66,8 +67,11 @@ struct lp_batch {
     std::vector<size_t> file_dev_off;
     size_t dev_off = 0, clean_off = 0, state_off = 0;
     bool parallel_huffman = true;
-    uint8_t* h_out = nullptr;       // pinned
+    uint8_t* h_out = nullptr;       // pinned + device-mapped: the compaction kernel writes the encoded bytes straight into it
     uint32_t* h_out_len = nullptr;  // pinned
+    unsigned long long* h_off = nullptr;  // pinned + device-mapped: packed offsets, (cnt + 1) per chunk at [i0 + chunk ordinal]
+    struct ChunkLayout { uint32_t blocks = 0, plane_bytes = 0, total_blocks = 0; int ordinal = 0; };
+    std::map<int, ChunkLayout> chunk_layout;  // keyed by the chunk's first image
     JpegDecodeItem* h_items_back = nullptr;
     int n = 0;
     int last_launches = 0;
@@ -88,6 +92,7 @@ static void batch_free(lp_batch* b) {
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_out_len) cudaFreeHost(b->h_out_len);
     if (b->h_items_back) cudaFreeHost(b->h_items_back);
+    if (b->h_off) cudaFreeHost(b->h_off);
     }
     for (auto e : b->ev) cudaEventDestroy(e);
     for (auto e : b->ev_h2d) cudaEventDestroy(e);
@@ -189,6 +194,7 @@ lp_batch* lp::batch_create_in(const lp_batch_config* cfg, uint8_t* dev_arena, si
     HALLOC(b->h_out, N * cfg->out_cap);
     HALLOC(b->h_out_len, N * sizeof(uint32_t));
     HALLOC(b->h_items_back, N * sizeof(JpegDecodeItem));
+    HALLOC(b->h_off, (N + (size_t)b->max_chunks + 8) * sizeof(unsigned long long));
 #undef HALLOC
     b->ev.resize((size_t)b->max_chunks * 6);
     b->ev_h2d.resize(b->max_chunks);
@@ -257,6 +263,7 @@ static void batch_begin(lp_batch* b, int n) {
     b->tables_uploaded = 0;
     b->dev_off = b->clean_off = b->state_off = 0;
     b->parallel_huffman = true;
+    b->chunk_layout.clear();
 }
 
 // Host: where the files of images [i0, i0+cnt) go in the device scan buffer (no header parsing, so the
@@ -277,63 +284,100 @@ static int batch_layout_chunk(lp_batch* b, const uint8_t* const* in, const size_
     return LP_OK;
 }
 
-// Host: parse the headers of images [i0, i0+cnt), lay out their device scratch.
-static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int i0, int cnt) {
-    for (int k = i0; k < i0 + cnt; k++) {
-        JpegHeader h;
-        int rc = jpeg_parse_header(in[k], in_len[k], &h);
-        if (!rc && !h.supported) rc = LP_ERR_UNSUPPORTED;
-        if (!rc && (h.width != b->W || h.height != b->H)) rc = LP_ERR_BAD_ARGUMENT;
-        // batch path: TL only.  EXIF values outside 2..8 (0, 9, 300 ... the reader passes them through,
-        // like the reference's) are no-ops for OrientationTransform, so they are TL as well
-        if (!rc && h.orientation >= 2 && h.orientation <= 8) rc = LP_ERR_UNSUPPORTED;
-        if (!rc && h.ncomp != 3) rc = LP_ERR_UNSUPPORTED;
-        int ts = rc ? 0 : table_set_for(b, h);
-        if (!rc && ts < 0) rc = LP_ERR_UNSUPPORTED;
-        JpegDecodeItem& it = b->items[k];
-        memset(&it, 0, sizeof(it));
-        if (!rc) {
-            it.scan_len = (uint32_t)h.scan_length;
-            it.table_set = (uint32_t)ts;
-            it.width = h.width; it.height = h.height; it.ncomp = h.ncomp;
-            it.mcus_x = h.mcus_x; it.mcus_y = h.mcus_y; it.restart_interval = h.restart_interval;
-            uint32_t total_blocks = 0;
-            for (int c = 0; c < h.ncomp; c++) {
-                it.h[c] = h.comp[c].h; it.v[c] = h.comp[c].v;
-                it.dw[c] = (h.width * h.comp[c].h + h.maxh - 1) / h.maxh;
-                it.dh[c] = (h.height * h.comp[c].v + h.maxv - 1) / h.maxv;
-                total_blocks += (uint32_t)h.mcus_x * h.mcus_y * h.comp[c].h * h.comp[c].v;
-                memcpy(it.qt[c], h.qt[h.comp[c].tq], sizeof(it.qt[c]));
-                it.td[c] = h.comp[c].td; it.ta[c] = h.comp[c].ta;
+// Host: parse the headers of images [i0, i0+cnt), lay out their device scratch.  Pass 1 (a few threads) reads
+// the headers; pass 2 lays the chunk's scratch out for the densest sampling layout that occurs IN THIS CHUNK, so a
+// batch may mix 4:2:0 / 4:2:2 / 4:4:4 files in any order (the per-chunk scratch is sized for 4:4:4 anyway).
+static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int i0, int cnt, int ordinal) {
+    std::vector<JpegHeader> hdr((size_t)cnt);
+    std::vector<uint32_t> blocks_of((size_t)cnt, 0), planes_of((size_t)cnt, 0), total_of((size_t)cnt, 0);
+    auto pass1 = [&](int k0, int k1) {
+        for (int k = k0; k < k1; k++) {
+            JpegHeader& h = hdr[k - i0];
+            int rc = jpeg_parse_header(in[k], in_len[k], &h);
+            if (!rc && !h.supported) rc = LP_ERR_UNSUPPORTED;
+            if (!rc && (h.width != b->W || h.height != b->H)) rc = LP_ERR_BAD_ARGUMENT;
+            // batch path: TL only.  EXIF values outside 2..8 (0, 9, 300 ... the reader passes them through,
+            // like the reference's) are no-ops for OrientationTransform, so they are TL as well
+            if (!rc && h.orientation >= 2 && h.orientation <= 8) rc = LP_ERR_UNSUPPORTED;
+            if (!rc && h.ncomp != 3) rc = LP_ERR_UNSUPPORTED;
+            JpegDecodeItem& it = b->items[k];
+            memset(&it, 0, sizeof(it));
+            if (!rc) {
+                it.scan_len = (uint32_t)h.scan_length;
+                it.width = h.width; it.height = h.height; it.ncomp = h.ncomp;
+                it.mcus_x = h.mcus_x; it.mcus_y = h.mcus_y; it.restart_interval = h.restart_interval;
+                uint32_t total_blocks = 0;
+                for (int c = 0; c < h.ncomp; c++) {
+                    it.h[c] = h.comp[c].h; it.v[c] = h.comp[c].v;
+                    it.dw[c] = (h.width * h.comp[c].h + h.maxh - 1) / h.maxh;
+                    it.dh[c] = (h.height * h.comp[c].v + h.maxv - 1) / h.maxv;
+                    total_blocks += (uint32_t)h.mcus_x * h.mcus_y * h.comp[c].h * h.comp[c].v;
+                    memcpy(it.qt[c], h.qt[h.comp[c].tq], sizeof(it.qt[c]));
+                    it.td[c] = h.comp[c].td; it.ta[c] = h.comp[c].ta;
+                }
+                it.frame_channels = 3;
+                // decode only what Fit will read: the crop window (+ the chroma-upsampling margin)
+                uint32_t plane_bytes = 0;
+                const uint32_t blocks = jpeg_item_set_window(&it, b->crop_x, b->crop_y, b->crop_x + b->crop_w,
+                                                             b->crop_y + b->crop_h, true, &plane_bytes);
+                blocks_of[k - i0] = blocks;
+                planes_of[k - i0] = plane_bytes;
+                total_of[k - i0] = total_blocks;
+                if (blocks > b->max_blocks_alloc || total_blocks > b->max_blocks_alloc || plane_bytes > b->max_blocks_alloc * 64)
+                    rc = LP_ERR_UNSUPPORTED;  // beyond what the context was created for
             }
-            it.frame_channels = 3;
-            // decode only what Fit will read: the crop window (+ the chroma-upsampling margin)
-            uint32_t plane_bytes = 0;
-            const uint32_t blocks = jpeg_item_set_window(&it, b->crop_x, b->crop_y, b->crop_x + b->crop_w,
-                                                         b->crop_y + b->crop_h, true, &plane_bytes);
-            if (!b->layout_known) {  // the first image fixes the per-slot scratch strides
-                b->blocks = blocks;
-                b->plane_bytes = plane_bytes;
-                b->total_blocks = total_blocks;
-                b->win_w = it.win_w;
-                b->win_h = it.win_h;
-                b->win_x0 = it.win_x0;
-                b->frame_bytes = (size_t)it.win_stride * it.win_h;
-                b->layout_known = true;
-            }
-            if (blocks > b->blocks || total_blocks > b->total_blocks || total_blocks > b->max_blocks_alloc)
-                rc = LP_ERR_UNSUPPORTED;  // denser sampling than the slots were laid out for
+            b->parse_status[k] = rc;
+            it.status = rc ? -1 : 0;
         }
-        b->parse_status[k] = rc;
-        it.status = rc ? -1 : 0;
-        if (rc) continue;
+    };
+    const int nthreads = cnt >= 256 ? 4 : 1;
+    if (nthreads == 1) {
+        pass1(i0, i0 + cnt);
+    } else {
+        std::vector<std::thread> pool;
+        const int per = ceil_div(cnt, nthreads);
+        for (int t = 1; t < nthreads; t++)
+            pool.emplace_back(pass1, std::min(i0 + cnt, i0 + t * per), std::min(i0 + cnt, i0 + (t + 1) * per));
+        pass1(i0, std::min(i0 + cnt, i0 + per));
+        for (auto& th : pool) th.join();
+    }
+    lp_batch::ChunkLayout lay;
+    lay.ordinal = ordinal;
+    for (int k = i0; k < i0 + cnt; k++) {
+        if (b->parse_status[k]) continue;
+        const JpegDecodeItem& it = b->items[k];
+        lay.blocks = std::max(lay.blocks, blocks_of[k - i0]);
+        lay.plane_bytes = std::max(lay.plane_bytes, planes_of[k - i0]);
+        lay.total_blocks = std::max(lay.total_blocks, total_of[k - i0]);
+        if (!b->layout_known) {  // the decoded window depends on the geometry only, which the context fixes
+            b->win_w = it.win_w;
+            b->win_h = it.win_h;
+            b->win_x0 = it.win_x0;
+            b->frame_bytes = (size_t)it.win_stride * it.win_h;
+            b->layout_known = true;
+        }
+    }
+    lay.plane_bytes = round_up(lay.plane_bytes, 256u);
+    b->blocks = std::max(b->blocks, lay.blocks);
+    b->total_blocks = std::max(b->total_blocks, lay.total_blocks);
+    b->chunk_layout[i0] = lay;
+    for (int k = i0; k < i0 + cnt; k++) {
+        if (b->parse_status[k]) continue;
+        JpegDecodeItem& it = b->items[k];
+        const int ts = table_set_for(b, hdr[k - i0]);
+        if (ts < 0) {
+            b->parse_status[k] = LP_ERR_UNSUPPORTED;
+            it.status = -1;
+            continue;
+        }
+        it.table_set = (uint32_t)ts;
         if (it.restart_interval) b->parallel_huffman = false;  // RSTn streams take the serial kernel
         const int slot = k - i0;  // position inside its chunk: the per-chunk scratch is indexed from the chunk's first image
-        it.scan_off = b->file_dev_off[k] + h.scan_offset;
-        it.coef_off = (uint64_t)slot * b->blocks * 64;
-        it.plane_off = (uint64_t)slot * b->plane_bytes;
+        it.scan_off = b->file_dev_off[k] + hdr[k - i0].scan_offset;
+        it.coef_off = (uint64_t)slot * lay.blocks * 64;
+        it.plane_off = (uint64_t)slot * lay.plane_bytes;
         it.frame_off = (uint64_t)slot * b->frame_bytes;
-        it.dcdiff_off = (uint64_t)slot * b->total_blocks;
+        it.dcdiff_off = (uint64_t)slot * lay.total_blocks;
         it.clean_off = b->clean_off;
         it.state_off = b->state_off;
         b->clean_off += huff_clean_bytes(it.scan_len);
@@ -379,6 +423,7 @@ static int batch_launch_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st, cud
         LP_CUDA_OK(cudaMemsetAsync(b->d_out_len + i0, 0, (size_t)cnt * sizeof(uint32_t), st));
         return LP_OK;
     }
+    const lp_batch::ChunkLayout lay = b->chunk_layout.count(i0) ? b->chunk_layout[i0] : lp_batch::ChunkLayout();
     if (ev) LP_CUDA_OK(cudaEventRecord(ev[0], st));
     JpegDecodeBatch d;
     d.items = b->d_items + i0;
@@ -388,8 +433,8 @@ static int batch_launch_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st, cud
     d.planes = b->d_planes;
     d.frames = b->d_frames;
     d.n = cnt;
-    d.coef_elems_total = (size_t)cnt * b->blocks * 64;
-    d.max_blocks_per_image = (int)b->blocks;
+    d.coef_elems_total = (size_t)cnt * lay.blocks * 64;
+    d.max_blocks_per_image = (int)lay.blocks;
     d.max_width = b->win_w;
     d.max_height = b->win_h;
     d.dcdiff = b->d_dcdiff;
@@ -428,6 +473,11 @@ static int batch_launch_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st, cud
     e.scratch = b->d_enc_scratch;
     rc = jpeg_encode_launch(e, st, ev ? ev[4] : nullptr);
     if (rc) return rc;
+    // the encoded bytes leave packed: slots are out_cap (64 KB) apart but hold a few KB each, so a compaction
+    // kernel writes them back to back straight into the pinned, device-mapped host buffer (no D2H of the slots)
+    rc = compact_launch(e.out, b->cfg.out_cap, e.out_len, (uint32_t)b->cfg.out_cap, cnt, b->h_out + (size_t)i0 * b->cfg.out_cap,
+                        b->h_off + i0 + lay.ordinal, st);
+    if (rc) return rc;
     if (ev) LP_CUDA_OK(cudaEventRecord(ev[5], st));
     return LP_OK;
 }
@@ -437,13 +487,15 @@ static int batch_download_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st) {
     LP_CUDA_OK(cudaMemcpyAsync(b->h_out_len + i0, b->d_out_len + i0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
     LP_CUDA_OK(cudaMemcpyAsync(b->h_items_back + i0, b->d_items + i0, (size_t)cnt * sizeof(JpegDecodeItem),
                                cudaMemcpyDeviceToHost, st));
-    LP_CUDA_OK(cudaMemcpyAsync(b->h_out + (size_t)i0 * cap, b->d_out + (size_t)i0 * cap, (size_t)cnt * cap,
-                               cudaMemcpyDeviceToHost, st));
+    (void)cap;  // the encoded bytes are already in h_out: the compaction kernel wrote them there
     return LP_OK;
 }
 
 static void batch_finish_chunk(lp_batch* b, int i0, int cnt, uint8_t* const* out, size_t* out_len, int* status) {
     const size_t cap = b->cfg.out_cap;
+    const int ordinal = b->chunk_layout.count(i0) ? b->chunk_layout[i0].ordinal : 0;
+    const unsigned long long* off = b->h_off + i0 + ordinal;
+    const uint8_t* packed = b->h_out + (size_t)i0 * cap;
     for (int i = i0; i < i0 + cnt; i++) {
         int st = b->parse_status[i];
         if (!st && b->h_items_back[i].status != 0) st = LP_ERR_DECODING_FAILED;
@@ -452,7 +504,11 @@ static void batch_finish_chunk(lp_batch* b, int i0, int cnt, uint8_t* const* out
         if (status) status[i] = st;
         out_len[i] = 0;
         if (st) continue;
-        memcpy(out[i], b->h_out + (size_t)i * cap, b->h_out_len[i]);
+        if (off[i - i0] + b->h_out_len[i] > (unsigned long long)cnt * cap) {  // (cannot come from the scan kernel)
+            if (status) status[i] = LP_ERR_CUDA;
+            continue;
+        }
+        memcpy(out[i], packed + off[i - i0], b->h_out_len[i]);
         out_len[i] = b->h_out_len[i];
     }
 }
@@ -466,7 +522,7 @@ extern "C" int lp_batch_stage(lp_batch* b, const uint8_t* const* in, const size_
         const int cnt = std::min(b->chunk, n - i0);
         int rc = batch_layout_chunk(b, in, in_len, i0, cnt);
         if (!rc) rc = batch_upload_files(b, in, in_len, i0, cnt, b->st);
-        if (!rc) rc = batch_parse_chunk(b, in, in_len, i0, cnt);
+        if (!rc) rc = batch_parse_chunk(b, in, in_len, i0, cnt, i0 / b->chunk);
         if (rc) return rc;
         rc = batch_upload_items(b, i0, cnt, b->st);
         if (rc) return rc;
@@ -515,7 +571,8 @@ extern "C" int lp_batch_fetch(lp_batch* b, uint8_t* const* out, size_t* out_len,
     int rc = batch_download_chunk(b, 0, b->n, b->st);
     if (rc) return rc;
     LP_CUDA_OK(cudaStreamSynchronize(b->st));
-    batch_finish_chunk(b, 0, b->n, out, out_len, status);
+    for (int i0 = 0; i0 < b->n; i0 += b->chunk)  // the chunks lp_batch_stage / lp_batch_run used
+        batch_finish_chunk(b, i0, std::min(b->chunk, b->n - i0), out, out_len, status);
     return LP_OK;
 }
 
@@ -548,7 +605,7 @@ extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const s
         // the bytes start crossing PCIe first; the headers are parsed while they travel
         int rc = batch_layout_chunk(b, in, in_len, i0, cnt);
         if (!rc) rc = batch_upload_files(b, in, in_len, i0, cnt, b->st_h2d);
-        if (!rc) rc = batch_parse_chunk(b, in, in_len, i0, cnt);
+        if (!rc) rc = batch_parse_chunk(b, in, in_len, i0, cnt, c);
         if (!rc) rc = batch_upload_items(b, i0, cnt, b->st_h2d);
         if (rc) return rc;
         LP_CUDA_OK(cudaEventRecord(b->ev_h2d[c], b->st_h2d));

@@ -35,6 +35,7 @@ static cudaError_t alloc(void** p, size_t n) {
 cudaError_t cudaMalloc(void** p, size_t n) { return alloc(p, n); }
 cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return alloc(p, n); }
 cudaError_t cudaMallocHost(void** p, size_t n) { return alloc(p, n); }
+cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *free_b = (size_t)1 << 30; *total_b = (size_t)2 << 30; return cudaSuccess; }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return alloc(p, n); }
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }

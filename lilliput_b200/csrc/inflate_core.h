@@ -37,13 +37,21 @@
 
 namespace lpinf {
 
-constexpr uint32_t kSubBits = 256;             // bits per lane and window
+#ifndef LP_INF_SUB
+#define LP_INF_SUB 512
+#endif
+#ifndef LP_INF_WARM
+#define LP_INF_WARM 64
+#endif
+constexpr uint32_t kSubBits = LP_INF_SUB;      // bits per lane and window
 constexpr uint32_t kWinBits = 32 * kSubBits;
 constexpr uint32_t kInWords = kWinBits / 32 + 8;  // window + the bits a symbol / a refill may read past it
 constexpr uint32_t kRing = 8192, kRingMask = kRing - 1;
 constexpr uint32_t kCapT = kRing / 2;          // output bytes per window
 constexpr uint32_t kMaxMatches = kCapT / 3 + 8;  // a match is at least 3 bytes
 constexpr int kLitBits = 10, kDistBits = 8;
+constexpr uint32_t kCkBits = 64;                       // a checkpoint every kCkBits bits of a subsequence
+constexpr int kCk = (int)(kSubBits / kCkBits);         // slots 1 .. kCk-1 are used (slot 0 would be the entry itself)
 
 // lane-private variable: one register on the device, 32 slots in the host simulation
 #ifdef LP_INF_HOST
@@ -177,6 +185,10 @@ struct WarpShared {
     uint16_t lsym[288], dsym[32];
     uint8_t lens[320];
     uint16_t cl[128];          // code-length code lookahead (7 bits): (symbol << 4) | length
+    // per lane and checkpoint j: the first symbol start at or behind (nominal start + j * kCkBits) of the lane's
+    // latest decode, with the matches / bytes decoded in front of it
+    uint32_t ck_pos_nm[32][kCk];  // (position << 16) | matches; position 0xFFFF = none
+    uint32_t ck_cnt[32][kCk];
 };
 
 LP_INF_FN uint32_t lit_entry(uint32_t sym, uint32_t len) {
@@ -301,26 +313,27 @@ LP_INF_FN uint32_t bits_get(Bits& b, const uint32_t* inbuf, uint32_t k) {  // k 
     return v;
 }
 
-// One code of table t at the reader; returns the lookup entry (length in bits 0..3 already consumed),
-// or 0 when the next bits are no code word.
-LP_INF_FN uint32_t decode_code(const WarpShared& ws, int t, Bits& b) {
-    bits_fill(b, ws.inbuf);
+// 64 stream bits from bit position `pos` of the window buffer as two 32-bit halves: three word loads and two
+// funnel shifts, no state carried between symbols (every field of a symbol is then a shift + mask of lo / hi).
+LP_INF_FN uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // bits [sh, sh + 32) of hi:lo, sh < 32
+#ifdef LP_INF_HOST
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#else
+    return __funnelshift_r(lo, hi, sh);
+#endif
+}
+
+// A code longer than the lookahead of table t in `bits` (>= 15 valid bits): the canonical walk continues behind
+// the lookahead (a code of <= look_bits bits would have been in the table), at most 15 - look_bits steps.
+// Returns the entry (code length in bits 0..3) or 0 when the bits are no code word.
+LP_INF_FN uint32_t long_code(const WarpShared& ws, int t, uint32_t bits) {
     const int look_bits = t ? kDistBits : kLitBits;
-    uint32_t e = (t ? ws.dist : ws.lit)[(uint32_t)b.acc & ((1u << look_bits) - 1u)];
-    if (e & 15u) {
-        bits_drop(b, e & 15u);
-        return e;
-    }
-    // longer than the lookahead: the canonical walk continues behind it (a code of <= look_bits bits would
-    // have been found above), at most 15 - look_bits steps
-    const uint32_t bitsv = (uint32_t)b.acc;
-    uint32_t code = brev32(bitsv << (32 - look_bits));  // the first look_bits bits, most significant first
+    uint32_t code = brev32(bits << (32 - look_bits));  // the first look_bits bits, most significant first
     for (int len = look_bits + 1; len < 16; len++) {
-        code = (code << 1) | ((bitsv >> (len - 1)) & 1u);
+        code = (code << 1) | ((bits >> (len - 1)) & 1u);
         const uint32_t c = ws.cnt32[t][len], f = ws.first[t][len];
         if (code - f < c) {
             const uint32_t sym = (t ? ws.dsym : ws.lsym)[ws.index[t][len] + (code - f)];
-            bits_drop(b, (uint32_t)len);
             return t ? dist_entry(sym, (uint32_t)len) : lit_entry(sym, (uint32_t)len);
         }
     }
@@ -338,52 +351,87 @@ enum { kFlagNone = 0, kFlagEob = 1, kFlagBad = 2 };
 // Decode the symbols that start in [start, end).  WRITE: literals go to the ring at absolute output
 // position q, matches are appended to mlist; stops in front of the first symbol that would take the
 // output past `budget` bytes (exit then points at that symbol, flag stays 0).
-template <bool WRITE>
-LP_INF_FN void decode_span(WarpShared& ws, uint32_t start, uint32_t end, uint32_t q, uint32_t budget,
-                           Match* mlist, Span& r) {
-    Bits b;
-    bits_init(b, ws.inbuf, start);
-    uint32_t cnt = 0, nm = 0, flag = kFlagNone;
-    while (b.pos < end) {
-        const uint32_t sym_pos = b.pos;
-        const uint32_t e = decode_code(ws, 0, b);
+// REC (count passes): at every checkpoint boundary the lane crosses, the first symbol start behind it and the
+// counts in front of it are recorded.  CMP (re-decodes of pass B): if the previous decode of this lane recorded the
+// SAME position at a checkpoint, the two decodes have merged -- everything behind is identical -- so the decode
+// stops there and the totals follow by arithmetic (r.exit / r.flag are then left untouched by the caller).
+// Returns true when it merged.  ck slots are addressed relative to `nominal` (the subsequence start).
+template <bool WRITE, bool REC, bool CMP>
+LP_INF_FN bool decode_span(WarpShared& ws, uint32_t start, uint32_t end, uint32_t q, uint32_t budget,
+                           Match* mlist, Span& r, uint32_t nominal, int lane, uint32_t old_cnt, uint32_t old_nm) {
+    uint32_t pos = start, cnt = 0, nm = 0, flag = kFlagNone;
+    uint32_t next_ck = nominal + kCkBits;
+    int j = 0;
+    while (pos < end) {
+        if (REC && pos >= next_ck) {
+            while (pos >= next_ck) {
+                j++;
+                next_ck += kCkBits;
+            }
+            if (j < kCk) {
+                const uint32_t rel16 = (pos - nominal) & 0xFFFFu;
+                if (CMP) {
+                    const uint32_t o_pn = ws.ck_pos_nm[lane][j], o_c = ws.ck_cnt[lane][j];
+                    if ((o_pn >> 16) == rel16) {
+                        // merged: totals = this decode up to here + the old decode from here on
+                        const uint32_t dc = cnt - o_c, dn = nm - (o_pn & 0xFFFFu);
+                        for (int jj = j; jj < kCk; jj++) {
+                            const uint32_t pn = ws.ck_pos_nm[lane][jj];
+                            if ((pn >> 16) == 0xFFFFu) continue;
+                            ws.ck_pos_nm[lane][jj] = (pn & 0xFFFF0000u) | ((pn + dn) & 0xFFFFu);
+                            ws.ck_cnt[lane][jj] += dc;
+                        }
+                        r.cnt = old_cnt + dc;
+                        r.nm = old_nm + dn;
+                        r.exit = (uint32_t)j;  // (statistics only: the caller keeps its old exit)
+                        return true;
+                    }
+                }
+                ws.ck_pos_nm[lane][j] = (rel16 << 16) | (nm & 0xFFFFu);
+                ws.ck_cnt[lane][j] = cnt;
+            }
+        }
+        const uint32_t wi = pos >> 5, sh = pos & 31u;
+        const uint32_t w0 = ws.inbuf[wi], w1 = ws.inbuf[wi + 1], w2 = ws.inbuf[wi + 2];
+        const uint32_t lo = funnel_r(w0, w1, sh), hi = funnel_r(w1, w2, sh);
+        uint32_t e = ws.lit[lo & ((1u << kLitBits) - 1u)];
+        if (!(e & 15u)) e = long_code(ws, 0, lo);
         const uint32_t kind = (e >> 4) & 3u;
+        uint32_t used = e & 15u;
         if (e == 0 || kind == 3) {
             flag = kFlagBad;
             break;
         }
         if (kind == 0) {
             if (WRITE) {
-                if (cnt + 1 > budget) {
-                    b.pos = sym_pos;
-                    break;
-                }
+                if (cnt + 1 > budget) break;
                 ws.ring[(q + cnt) & kRingMask] = (uint8_t)(e >> 8);
             }
             cnt++;
+            pos += used;
             continue;
         }
         if (kind == 1) {
             flag = kFlagEob;
+            pos += used;
             break;
         }
-        // length + distance
+        // length (+ extra bits), then distance code (+ extra bits): at most 15 + 5 + 15 + 13 = 48 bits of lo / hi
         const uint32_t lx = (e >> 20) & 7u;
-        uint32_t len = (e >> 8) & 0x1FFu;
-        if (lx) len += bits_get(b, ws.inbuf, lx);
-        const uint32_t d = decode_code(ws, 1, b);
+        const uint32_t len = ((e >> 8) & 0x1FFu) + (funnel_r(lo, hi, used) & ((1u << lx) - 1u));
+        used += lx;  // <= 20
+        const uint32_t rest = funnel_r(lo, hi, used);  // 32 bits behind the length: the distance code and its extra bits
+        uint32_t d = ws.dist[rest & ((1u << kDistBits) - 1u)];
+        if (!(d & 15u)) d = long_code(ws, 1, rest);
         if (d == 0 || ((d >> 4) & 3u) == 3) {
             flag = kFlagBad;
             break;
         }
-        const uint32_t dx = (d >> 24) & 15u;
-        uint32_t dist = (d >> 8) & 0x7FFFu;
-        if (dx) dist += bits_get(b, ws.inbuf, dx);
+        const uint32_t dl = d & 15u, dx = (d >> 24) & 15u;
+        const uint32_t dist = ((d >> 8) & 0x7FFFu) + ((rest >> dl) & ((1u << dx) - 1u));
+        used += dl + dx;
         if (WRITE) {
-            if (cnt + len > budget) {
-                b.pos = sym_pos;
-                break;
-            }
+            if (cnt + len > budget) break;
             if (dist > q + cnt) {  // zlib: "invalid distance too far back"
                 flag = kFlagBad;
                 break;
@@ -393,11 +441,15 @@ LP_INF_FN void decode_span(WarpShared& ws, uint32_t start, uint32_t end, uint32_
         }
         cnt += len;
         nm++;
+        pos += used;
     }
-    r.exit = b.pos;
+    if (REC)
+        for (int jj = j + 1; jj < kCk; jj++) ws.ck_pos_nm[lane][jj] = 0xFFFF0000u;  // not reached by this decode
+    r.exit = pos;
     r.cnt = cnt;
     r.nm = nm;
     r.flag = flag;
+    return false;
 }
 
 // ---- the stream ------------------------------------------------------------------------------------------
@@ -624,15 +676,17 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
             LP_INF_CLOCK(9);
             LaneVar<uint32_t> start, exitp, cnt, nm, flag, want, changed, term;
             Span sp;
-            // pass A: guessed starts
+            // pass A: every lane from the start of its subsequence (exact for lane 0 only), recording checkpoints
             LP_INF_LANES(l) {
-                start[l] = rel + (uint32_t)l * kSubBits;
-                decode_span<false>(ws, start[l], rel + (uint32_t)(l + 1) * kSubBits, 0, 0, nullptr, sp);
+                const uint32_t nominal = rel + (uint32_t)l * kSubBits;
+                start[l] = nominal;
+                decode_span<false, true, false>(ws, nominal, nominal + kSubBits, 0, 0, nullptr, sp, nominal, l, 0, 0);
                 exitp[l] = sp.exit; cnt[l] = sp.cnt; nm[l] = sp.nm; flag[l] = sp.flag;
             }
             LP_INF_CLOCK(10);
-            // pass B: fixed point
-            for (int round = 0; round < 33; round++) {
+            // pass B: fixed point.  A lane whose left neighbour's exit differs from the entry it used decodes again
+            // from there -- but only until it meets a checkpoint of its previous decode (usually the first or second)
+            for (int round = 0; round < 34; round++) {
                 shift_up(want, exitp, rel);
                 LP_INF_LANES(l) { term[l] = flag[l] != kFlagNone; }
                 const uint32_t tm = ballot(term);
@@ -642,14 +696,34 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                 }
                 if (!ballot(changed)) break;
                 LP_INF_COUNT(2, 1);
-                LP_INF_COUNT(3, popc32(ballot(changed)));
+#if defined(LP_INF_STATS) && defined(LP_INF_HOST)
+                uint32_t round_len = 0;
+#endif
                 LP_INF_LANES(l) {
                     if (changed[l]) {
+                        const uint32_t nominal = rel + (uint32_t)l * kSubBits;
                         start[l] = want[l];
-                        decode_span<false>(ws, start[l], rel + (uint32_t)(l + 1) * kSubBits, 0, 0, nullptr, sp);
-                        exitp[l] = sp.exit; cnt[l] = sp.cnt; nm[l] = sp.nm; flag[l] = sp.flag;
+                        if (want[l] >= nominal + kSubBits) {  // the neighbour's last symbol covers this whole subsequence
+                            exitp[l] = want[l]; cnt[l] = 0; nm[l] = 0; flag[l] = kFlagNone;
+                            for (int jj = 1; jj < kCk; jj++) ws.ck_pos_nm[l][jj] = 0xFFFF0000u;
+                        } else {
+                            sp.cnt = sp.nm = 0;
+                            const bool merged = decode_span<false, true, true>(ws, want[l], nominal + kSubBits, 0, 0, nullptr, sp,
+                                                                               nominal, l, cnt[l], nm[l]);
+                            cnt[l] = sp.cnt; nm[l] = sp.nm;
+#if defined(LP_INF_STATS) && defined(LP_INF_HOST)
+                            { const uint32_t len_ = merged ? sp.exit : (uint32_t)kCk; if (len_ > round_len) round_len = len_; }
+#endif
+                            if (!merged) {
+                                LP_INF_COUNT(3, 1);
+                                exitp[l] = sp.exit; flag[l] = sp.flag;
+                            }
+                        }
                     }
                 }
+#if defined(LP_INF_STATS) && defined(LP_INF_HOST)
+                g_stats[7] += round_len;
+#endif
             }
             LP_INF_CLOCK(11);
             LP_INF_LANES(l) { term[l] = flag[l] != kFlagNone; }
@@ -678,8 +752,8 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                 const bool active = l <= nfull && l <= k && l < 32;
                 if (active) {
                     const uint32_t budget = l < nfull ? 0xFFFFFFFFu : (kCapT > coff[l] ? kCapT - coff[l] : 0u);
-                    decode_span<true>(ws, start[l], rel + (uint32_t)(l + 1) * kSubBits, o + coff[l], budget,
-                                      s.mlist + moff[l], sp);
+                    decode_span<true, false, false>(ws, start[l], rel + (uint32_t)(l + 1) * kSubBits, o + coff[l], budget,
+                                                    s.mlist + moff[l], sp, 0, l, 0, 0);
                     wexit[l] = sp.exit; wcnt[l] = sp.cnt; wnm[l] = sp.nm; wflag[l] = sp.flag;
                 }
             }

@@ -145,7 +145,7 @@ lp_batch* lp::batch_create_in(const lp_batch_config* cfg, uint8_t* dev_arena, si
     b->pipe_chunk = (cfg->chunk > 0 || slots <= 0) ? b->chunk : std::min(b->chunk, 2 * slots);
     b->chunk = std::min(b->chunk, cfg->max_images);
     b->pipe_chunk = std::max(1, std::min(b->pipe_chunk, b->chunk));
-    b->max_chunks = ceil_div(cfg->max_images, b->pipe_chunk) + 2;  // + the opening chunk of the pipelined path
+    b->max_chunks = ceil_div(cfg->max_images, b->pipe_chunk) + 3;  // + the opening chunk of the pipelined path
     // worst-case per-image layout: 4:4:4 needs the most blocks
     const size_t mcus = (size_t)ceil_div(b->W, 8) * ceil_div(b->H, 8);
     b->max_blocks_alloc = mcus * 3 + 4 * ((size_t)ceil_div(b->W, 8) + ceil_div(b->H, 8)) + 16;
@@ -593,8 +593,15 @@ extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const s
     {
         int i0 = 0;
         if (n > b->pipe_chunk && b->first_chunk >= 1 && b->first_chunk < b->pipe_chunk) {
-            sched.push_back({0, b->first_chunk});
-            i0 = b->first_chunk;
+            // ramp: a third of a wave (one Huffman CTA per SM), then a wave, then full chunks -- what is exposed at
+            // the start is the upload + header parse of the FIRST chunk only
+            const int third = b->first_chunk / 3;
+            if (third >= 32 && n > third + b->first_chunk) {
+                sched.push_back({0, third});
+                i0 = third;
+            }
+            sched.push_back({i0, b->first_chunk});
+            i0 += b->first_chunk;
         }
         for (; i0 < n; i0 += b->pipe_chunk) sched.push_back({i0, std::min(b->pipe_chunk, n - i0)});
     }

@@ -800,10 +800,22 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                                 blocked_q[l] = m.q;
                                 break;
                             }
-                            for (uint32_t i = 0; i < len; i++) {
-                                const uint32_t sp_ = src0 + (dist >= len ? i : i % dist);
-                                const uint8_t v = sp_ >= ring_lo ? ws.ring[sp_ & kRingMask] : s.out[sp_];
-                                ws.ring[(m.q + i) & kRingMask] = v;
+                            if (dist >= len && src0 >= ring_lo) {
+                                // the usual case: source and destination do not overlap and both live in the ring
+                                uint32_t sp_ = src0 & kRingMask, dp_ = m.q & kRingMask;
+                                if (sp_ + len <= kRing && dp_ + len <= kRing) {
+                                    for (uint32_t i = 0; i < len; i++) ws.ring[dp_ + i] = ws.ring[sp_ + i];
+                                } else {
+                                    for (uint32_t i = 0; i < len; i++) ws.ring[(dp_ + i) & kRingMask] = ws.ring[(sp_ + i) & kRingMask];
+                                }
+                            } else {
+                                uint32_t k = 0;  // i mod dist, kept incrementally
+                                for (uint32_t i = 0; i < len; i++) {
+                                    const uint32_t sp_ = src0 + k;
+                                    const uint8_t v = sp_ >= ring_lo ? ws.ring[sp_ & kRingMask] : s.out[sp_];
+                                    ws.ring[(m.q + i) & kRingMask] = v;
+                                    if (++k == dist) k = 0;
+                                }
                             }
                             mi[l]++;
                         }

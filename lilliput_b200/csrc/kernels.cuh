@@ -265,8 +265,8 @@ struct WebpStillInfo {
     bool simple_lossy = false;        // one VP8 key frame, no ALPH / ICCP / animation
 };
 bool webp_still_info(const uint8_t* data, size_t len, WebpStillInfo* out);
-int webp_vp8_decode_batch(const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len, int n, int width,
-                          int height, uint8_t* d_frames, size_t frame_stride, int* h_status, cudaStream_t st);
+int webp_vp8_decode_batch(const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len, int n, const int* width,
+                          const int* height, uint8_t* d_frames, const uint64_t* frame_off, int* h_status, cudaStream_t st);
 struct GifAnimPlan;
 GifAnimPlan* gif_plan_parse(const uint8_t* data, size_t len, int max_frames);
 void gif_plan_free(GifAnimPlan* p);

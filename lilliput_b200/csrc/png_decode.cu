@@ -116,13 +116,162 @@ __device__ void defilter_image(uint8_t* raw, uint32_t row_bytes, int height) {
     }
 }
 
+// ---- fused path: 8-bit truecolour (colour type 2 without tRNS, or 6), not interlaced -------------------------
+// Defilter + RGB(A) -> BGR(A) in one pass: the filtered scanlines are only READ (so they stay in L1; the in-place
+// version above invalidates the very line it reads next with each store) and the packed frame is only written.
+// Lane r owns scanline y0 + r; per iteration it takes FOUR pixels, one chunk behind lane r-1, whose four output
+// pixels of the previous iteration are exactly the pixels above it (shuffled as one word per pixel).  The raw
+// bytes of the next chunk are fetched (aligned words + funnel shift) before the current one is worked on.
+
+__device__ __forceinline__ bool png_fused_ok(const PngDecodeItem& it) {
+    return it.bit_depth == 8 && !it.interlace && ((it.color_type == 2 && it.out_channels == 3) || it.color_type == 6);
+}
+
+// NW 32-bit words starting at (possibly unaligned) p
+template <int NW>
+__device__ __forceinline__ void load_words_unaligned(const uint8_t* p, uint32_t* out) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int k = 0; k <= NW; k++) w[k] = q[k];
+#pragma unroll
+    for (int k = 0; k < NW; k++) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
+}
+
+__device__ __forceinline__ uint32_t png_unfilter_px(uint32_t x, uint32_t a, uint32_t b, uint32_t c, int ft, int nbytes) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k < nbytes) {
+            const int xv = (x >> (8 * k)) & 255, av = (a >> (8 * k)) & 255, bv = (b >> (8 * k)) & 255, cv = (c >> (8 * k)) & 255;
+            int pred;
+            if (ft == 1) pred = av;
+            else if (ft == 2) pred = bv;
+            else if (ft == 3) pred = (av + bv) >> 1;
+            else if (ft == 4) pred = paeth(av, bv, cv);
+            else pred = 0;
+            r |= (uint32_t)((xv + pred) & 255) << (8 * k);
+        }
+    }
+    return r;
+}
+
+template <int BPP>  // 3 or 4
+__device__ void defilter_to_frame(const uint8_t* raw, uint32_t row_bytes, int width, int height, uint8_t* frame,
+                                  uint32_t frame_stride) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t pitch = row_bytes + 1;
+    const int nchunks = (width + 3) >> 2;
+    constexpr int NW = BPP;  // words per 4-pixel chunk of raw bytes (4 * BPP bytes)
+    for (int y0 = 0; y0 < height; y0 += 32) {
+        const int y = y0 + lane;
+        const bool live = y < height;
+        const uint8_t* row = raw + (size_t)(live ? y : 0) * pitch;
+        const int ft = live ? row[0] : 0;
+        const uint8_t* rp = row + 1;
+        uint8_t* fp = frame + (size_t)(live ? y : 0) * frame_stride;
+        const uint8_t* above = y0 > 0 ? frame + (size_t)(y0 - 1) * frame_stride : nullptr;  // lane 0's "up": already BGR(A)
+        const bool fp_aligned = (reinterpret_cast<uintptr_t>(fp) & 3) == 0;
+        uint32_t nxt[NW], cur_raw[NW];
+        uint32_t out[4] = {0, 0, 0, 0};       // this lane's pixels of the previous iteration (raw channel order, one word each)
+        uint32_t left = 0, upleft = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) nxt[k] = 0;
+        if (live && nchunks > 0) load_words_unaligned<NW>(rp, nxt);
+        for (int t = 0; t < nchunks + 31; t++) {
+            // pixels above: lane r-1's outputs of the previous iteration (its chunk t-1-(r-1) = this lane's chunk)
+            uint32_t up[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) up[p] = __shfl_up_sync(0xffffffffu, out[p], 1);
+            const int c = t - lane;
+            const bool act = live && c >= 0 && c < nchunks;
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < NW; k++) cur_raw[k] = nxt[k];
+                if (c + 1 < nchunks) load_words_unaligned<NW>(rp + (size_t)(c + 1) * 4 * BPP, nxt);
+                if (lane == 0) {
+                    if (above) {
+                        // read the frame row back and undo the channel swap
+                        uint32_t f[NW];
+                        load_words_unaligned<NW>(above + (size_t)c * 4 * BPP, f);
+                        if (BPP == 4) {
+#pragma unroll
+                            for (int p = 0; p < 4; p++) up[p] = __byte_perm(f[p], 0, 0x3012);
+                        } else {
+                            const uint32_t q0 = f[0] & 0xFFFFFFu, q1 = (f[0] >> 24) | ((f[1] & 0xFFFFu) << 8),
+                                           q2 = (f[1] >> 16) | ((f[2] & 0xFFu) << 16), q3 = f[2] >> 8;
+                            up[0] = __byte_perm(q0, 0, 0x4012); up[1] = __byte_perm(q1, 0, 0x4012);
+                            up[2] = __byte_perm(q2, 0, 0x4012); up[3] = __byte_perm(q3, 0, 0x4012);
+                        }
+                    } else {
+                        up[0] = up[1] = up[2] = up[3] = 0;
+                    }
+                }
+                // the four pixels' filtered bytes, one word per pixel
+                uint32_t x[4];
+                if (BPP == 4) {
+#pragma unroll
+                    for (int p = 0; p < 4; p++) x[p] = cur_raw[p];
+                } else {
+                    x[0] = cur_raw[0] & 0xFFFFFFu;
+                    x[1] = (cur_raw[0] >> 24) | ((cur_raw[1] & 0xFFFFu) << 8);
+                    x[2] = (cur_raw[1] >> 16) | ((cur_raw[2] & 0xFFu) << 16);
+                    x[3] = cur_raw[2] >> 8;
+                }
+                uint32_t sw[4];
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const uint32_t v = png_unfilter_px(x[p], left, up[p], upleft, ft, BPP);
+                    left = v;
+                    upleft = up[p];
+                    out[p] = v;
+                    sw[p] = BPP == 4 ? __byte_perm(v, 0, 0x3012) : __byte_perm(v, 0, 0x4012);  // R,G,B(,A) -> B,G,R(,A)
+                }
+                const int npx = min(4, width - 4 * c);
+                uint8_t* d = fp + (size_t)c * 4 * BPP;
+                if (npx == 4 && fp_aligned) {
+                    if (BPP == 4) {
+                        if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) *reinterpret_cast<uint4*>(d) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
+                        else {
+#pragma unroll
+                            for (int p = 0; p < 4; p++) reinterpret_cast<uint32_t*>(d)[p] = sw[p];
+                        }
+                    } else {
+                        reinterpret_cast<uint32_t*>(d)[0] = sw[0] | (sw[1] << 24);
+                        reinterpret_cast<uint32_t*>(d)[1] = (sw[1] >> 8) | (sw[2] << 16);
+                        reinterpret_cast<uint32_t*>(d)[2] = (sw[2] >> 16) | (sw[3] << 8);
+                    }
+                } else {
+                    for (int p = 0; p < npx; p++)
+#pragma unroll
+                        for (int k = 0; k < BPP; k++) d[p * BPP + k] = (uint8_t)(sw[p] >> (8 * k));
+                }
+            } else if (c < 0) {
+                left = upleft = 0;
+                out[0] = out[1] = out[2] = out[3] = 0;
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+    }
+}
+
 __global__ void __launch_bounds__(kPngWarps * 32)
-    png_defilter_kernel(PngDecodeItem* items, uint8_t* rawall, int n) {
+    png_defilter_kernel(PngDecodeItem* items, uint8_t* rawall, uint8_t* frames, int n) {
     const int warp = threadIdx.x >> 5;
     const int img = blockIdx.x * kPngWarps + warp;
     if (img >= n) return;
     PngDecodeItem& it = items[img];
     if (it.status != 0) return;
+    if (frames && png_fused_ok(it)) {  // the common case: straight to the packed frame, no convert pass
+        const uint8_t* raw = rawall + it.raw_off;
+        uint8_t* frame = frames + it.frame_off;
+        if (it.bpp == 4) defilter_to_frame<4>(raw, it.row_bytes, it.width, it.height, frame, it.frame_stride);
+        else defilter_to_frame<3>(raw, it.row_bytes, it.width, it.height, frame, it.frame_stride);
+        return;
+    }
     for (int ps = 0; ps < it.npass; ps++) {  // Adam7: every reduced image is filtered on its own
         if (it.pass_w[ps] == 0 || it.pass_h[ps] == 0) continue;
         uint8_t* raw = rawall + it.raw_off + it.pass_off[ps];
@@ -144,7 +293,7 @@ __global__ void __launch_bounds__(kPngWarps * 32)
 
 __global__ void png_convert_kernel(const PngDecodeItem* items, const uint8_t* rawall, uint8_t* frames) {
     const PngDecodeItem& it = items[blockIdx.z];
-    if (it.status != 0) return;
+    if (it.status != 0 || png_fused_ok(it)) return;  // (fused: the defilter pass wrote the frame itself)
     const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
     if (ox >= it.width || oy >= it.height) return;
     int x = ox, y = oy, ps = 0;
@@ -240,7 +389,7 @@ int png_decode_launch(const PngDecodeBatch& b, cudaStream_t st) {
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     cudaFreeAsync(mlists, st);
-    png_defilter_kernel<<<ctas, kPngWarps * 32, 0, st>>>(b.items, b.raw, b.n);
+    png_defilter_kernel<<<ctas, kPngWarps * 32, 0, st>>>(b.items, b.raw, b.frames, b.n);
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     dim3 grid(ceil_div(b.max_width, 128), b.max_height, b.n);

@@ -586,16 +586,17 @@ __global__ void vp8_output_batch_kernel(const uint8_t* work, size_t work_stride,
     d[2] = bgr[2];
 }
 
-// n VP8 key frames of one size: one warp per frame (vp8_decode_kernel), then every pixel of every frame
-// through the fancy upsampler + colour conversion in one launch.  Packed BGR frames, frame_stride apart.
-int webp_vp8_decode_batch(const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len, int n, int width,
-                          int height, uint8_t* d_frames, size_t frame_stride, int* h_status, cudaStream_t st) {
+// n VP8 key frames (any sizes, equal sizes adjacent): one warp per frame (vp8_decode_kernel) in ONE launch,
+// then every pixel of every frame through the fancy upsampler + colour conversion, one launch per run of
+// equal geometry.  Packed BGR frames at d_frames + frame_off[i].
+int webp_vp8_decode_batch(const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len, int n, const int* width,
+                          const int* height, uint8_t* d_frames, const uint64_t* frame_off, int* h_status, cudaStream_t st) {
     if (n <= 0) return LP_OK;
-    const int mb_w = (width + 15) >> 4, mb_h = (height + 15) >> 4;
-    const size_t wb = vp8::work_bytes(mb_w, mb_h);
+    std::vector<size_t> work_off((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) work_off[i + 1] = work_off[i] + vp8::work_bytes((width[i] + 15) >> 4, (height[i] + 15) >> 4);
     uint8_t* scratch = nullptr;
     const size_t items_b = round_up((size_t)n * sizeof(Vp8Item), (size_t)256), stat_b = round_up((size_t)n * 4, (size_t)256);
-    if (cudaMallocAsync(&scratch, items_b + stat_b + (size_t)n * wb, st) != cudaSuccess) {
+    if (cudaMallocAsync(&scratch, items_b + stat_b + work_off[n], st) != cudaSuccess) {
         cudaGetLastError();
         return LP_ERR_CUDA;
     }
@@ -603,15 +604,28 @@ int webp_vp8_decode_batch(const uint8_t* d_in, const uint64_t* in_off, const uin
     int* d_status = reinterpret_cast<int*>(scratch + items_b);
     uint8_t* d_work = scratch + items_b + stat_b;
     std::vector<Vp8Item> items((size_t)n);
-    for (int i = 0; i < n; i++) items[i] = Vp8Item{d_in + in_off[i], in_len[i], d_work + (size_t)i * wb, d_status + i, mb_w, mb_h};
+    for (int i = 0; i < n; i++)
+        items[i] = Vp8Item{d_in + in_off[i], in_len[i], d_work + work_off[i], d_status + i, (width[i] + 15) >> 4, (height[i] + 15) >> 4};
     int rc = LP_OK;
     cudaMemsetAsync(d_status, 0, (size_t)n * 4, st);
     if (cudaMemcpyAsync(d_items, items.data(), (size_t)n * sizeof(Vp8Item), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = LP_ERR_CUDA;
     if (!rc) {
         vp8_decode_kernel<<<ceil_div(n, kVp8WarpsPerBlock), kVp8WarpsPerBlock * 32, 0, st>>>(d_items, n);
-        dim3 grid(ceil_div(width, 128), height, n);
-        vp8_output_batch_kernel<<<grid, 128, 0, st>>>(d_work, wb, mb_w, mb_h, width, height, d_frames, frame_stride);
-        g_launches += 2;
+        g_launches++;
+        for (int i0 = 0; i0 < n;) {
+            // frames of one geometry lie back to back, round_up(w * h * 3, 256) apart (the caller's layout)
+            const size_t fstride = round_up((size_t)width[i0] * height[i0] * 3, (size_t)256);
+            int i1 = i0 + 1;
+            while (i1 < n && width[i1] == width[i0] && height[i1] == height[i0] &&
+                   frame_off[i1] == frame_off[i0] + (uint64_t)(i1 - i0) * fstride)
+                i1++;
+            const int mb_w = (width[i0] + 15) >> 4, mb_h = (height[i0] + 15) >> 4;
+            dim3 grid(ceil_div(width[i0], 128), height[i0], i1 - i0);
+            vp8_output_batch_kernel<<<grid, 128, 0, st>>>(d_work + work_off[i0], vp8::work_bytes(mb_w, mb_h), mb_w, mb_h, width[i0],
+                                                          height[i0], d_frames + frame_off[i0], fstride);
+            g_launches++;
+            i0 = i1;
+        }
         if (cudaGetLastError() != cudaSuccess) rc = LP_ERR_CUDA;
     }
     if (!rc && (cudaMemcpyAsync(h_status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||

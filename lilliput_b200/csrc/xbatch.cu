@@ -332,20 +332,88 @@ static void lane_time(Lane& L, int from, int to, double* acc) {
     if (cudaEventElapsedTime(&ms, L.ev[from], L.ev[to]) == cudaSuccess) *acc += ms;
 }
 
-// ------------------------------------------------------------------ PNG groups
+// ------------------------------------------------------------------ PNG / WebP tasks
+// A task holds items of ONE decoder kind but any geometry, ordered so that equal geometries are adjacent: the
+// entropy stage (inflate / boolean decoder -- the long pole, latency-bound per stream) is one launch over the whole
+// task; the geometry-bound stages (resize, encode) are one launch per run of equal geometry.
+
+struct Run {
+    int k0, k1;  // positions inside the task
+};
+static std::vector<Run> runs_of(const lp_xbatch* X, const std::vector<int>& idx) {
+    std::vector<Run> r;
+    for (int k = 0; k < (int)idx.size();) {
+        const XItem& a = X->items[idx[k]];
+        int e = k + 1;
+        while (e < (int)idx.size()) {
+            const XItem& c = X->items[idx[e]];
+            if (c.w != a.w || c.h != a.h || c.ch != a.ch) break;
+            e++;
+        }
+        r.push_back(Run{k, e});
+        k = e;
+    }
+    return r;
+}
+
+// resize of every run + sinks.  frame_off / frame_stride describe the decoded frames; ok[k] = decode succeeded.
+static void resize_and_encode(lp_xbatch* X, Lane& L, Bump& bump, const std::vector<int>& idx, const std::vector<Run>& runs,
+                              const uint8_t* d_frames, const std::vector<uint64_t>& frame_off, const std::vector<char>& ok,
+                              std::vector<int>* failed) {
+    struct Out { uint8_t* d; size_t stride; };
+    std::vector<Out> outs(runs.size());
+    bool good = true;
+    cudaEventRecord(L.ev[1], L.st);
+    for (size_t r = 0; r < runs.size() && good; r++) {
+        const XItem& g = X->items[idx[runs[r].k0]];
+        const int n = runs[r].k1 - runs[r].k0;
+        const size_t fs = round_up((size_t)g.w * g.h * g.ch, (size_t)256);
+        outs[r].stride = round_up((size_t)g.ow * g.oh * g.ch, (size_t)256);
+        outs[r].d = bump.take<uint8_t>((size_t)n * outs[r].stride + 256);
+        if (!outs[r].d) { good = false; break; }
+        ResizeArgs a{d_frames + frame_off[runs[r].k0], fs, (size_t)g.w * g.ch, g.ch, g.cx, g.cy, g.cw, g.chh, outs[r].d,
+                     outs[r].stride, (size_t)g.ow * g.ch, g.ow, g.oh, n, 3};
+        good = resize_launch(a, L.st) == LP_OK;
+    }
+    cudaEventRecord(L.ev[2], L.st);
+    if (good) good = cudaStreamSynchronize(L.st) == cudaSuccess;
+    if (!good) {
+        cudaGetLastError();
+        failed->insert(failed->end(), idx.begin(), idx.end());
+        return;
+    }
+    lane_time(L, 0, 1, &L.ms_decode);
+    lane_time(L, 1, 2, &L.ms_resize);
+    cudaEventRecord(L.ev[2], L.st);
+    for (size_t r = 0; r < runs.size(); r++) {
+        const XItem& g = X->items[idx[runs[r].k0]];
+        std::vector<int> sub;
+        bool all = true;
+        for (int k = runs[r].k0; k < runs[r].k1; k++) {
+            all = all && ok[k];
+            sub.push_back(idx[k]);
+        }
+        if (!all) {  // rare: a corrupt stream in the run -- the run's items take the per-image path, which reports the precise error
+            failed->insert(failed->end(), sub.begin(), sub.end());
+            continue;
+        }
+        sink_encode(X, L, bump, sub, outs[r].d, outs[r].stride, g.ow, g.oh, g.ch, failed);
+    }
+    cudaEventRecord(L.ev[3], L.st);
+    cudaEventSynchronize(L.ev[3]);
+    lane_time(L, 2, 3, &L.ms_encode);
+}
 
 static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
     const int n = (int)idx.size();
     std::vector<int> failed;
-    const XItem& g = X->items[idx[0]];
-    const int w = g.w, h = g.h, ch = g.ch;
+    const std::vector<Run> runs = runs_of(X, idx);
     Bump bump{L.dev, L.dev_bytes};
-    const size_t frame_stride = round_up((size_t)w * h * ch, (size_t)256);
-    const size_t out_stride = round_up((size_t)g.ow * g.oh * ch, (size_t)256);
     std::vector<PngDecodeItem> items((size_t)n);
     std::vector<SegCopy> segs;
-    std::vector<uint64_t> file_off((size_t)n);
-    size_t in_bytes = 0, raw_bytes = 0;
+    std::vector<uint64_t> file_off((size_t)n), frame_off((size_t)n);
+    size_t in_bytes = 0, raw_bytes = 0, frame_bytes = 0;
+    int max_w = 0, max_h = 0;
     for (int k = 0; k < n; k++) {
         const PngHeader& ph = *X->items[idx[k]].png;
         const size_t span = ph.idat.back().offset + ph.idat.back().length - ph.idat.front().offset;
@@ -354,7 +422,8 @@ static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
     }
     size_t zg = in_bytes;  // gathered streams follow the uploaded file spans
     for (int k = 0; k < n; k++) {
-        const PngHeader& ph = *X->items[idx[k]].png;
+        const XItem& xi = X->items[idx[k]];
+        const PngHeader& ph = *xi.png;
         PngDecodeItem& it = items[k];
         memset(&it, 0, sizeof(it));
         it.z_len = (uint32_t)ph.idat_total;
@@ -366,7 +435,7 @@ static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
         it.out_channels = ph.out_channels;
         it.bpp = ph.bpp;
         it.row_bytes = (uint32_t)ph.row_bytes;
-        it.frame_stride = (uint32_t)((size_t)w * ch);
+        it.frame_stride = (uint32_t)((size_t)xi.w * xi.ch);
         it.interlace = ph.interlace ? 1 : 0;
         png_item_set_passes(&it);
         it.npal = ph.npal;
@@ -380,23 +449,26 @@ static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
         } else {
             it.z_off = zg;
             size_t o = zg;
-            for (const PngSegment& s : ph.idat) {
-                segs.push_back(SegCopy{file_off[k] + (s.offset - ph.idat.front().offset), o, (uint32_t)s.length, 0});
-                o += s.length;
+            for (const PngSegment& sg : ph.idat) {
+                segs.push_back(SegCopy{file_off[k] + (sg.offset - ph.idat.front().offset), o, (uint32_t)sg.length, 0});
+                o += sg.length;
             }
             zg += round_up(ph.idat_total + 16, (size_t)16);
         }
         it.raw_off = raw_bytes;
         raw_bytes += round_up((size_t)it.raw_total + 64, (size_t)256);
-        it.frame_off = (uint64_t)k * frame_stride;
+        frame_off[k] = frame_bytes;
+        it.frame_off = frame_bytes;
+        frame_bytes += round_up((size_t)xi.w * xi.h * xi.ch, (size_t)256);
+        max_w = std::max(max_w, xi.w);
+        max_h = std::max(max_h, xi.h);
     }
     uint8_t* d_in = bump.take<uint8_t>(zg + 4096);
     PngDecodeItem* d_items = bump.take<PngDecodeItem>((size_t)n * sizeof(PngDecodeItem));
     SegCopy* d_segs = bump.take<SegCopy>(segs.size() * sizeof(SegCopy) + 16);
     uint8_t* d_raw = bump.take<uint8_t>(raw_bytes + 256);
-    uint8_t* d_frames = bump.take<uint8_t>((size_t)n * frame_stride + 256);
-    uint8_t* d_resized = bump.take<uint8_t>((size_t)n * out_stride + 256);
-    if (!d_in || !d_items || !d_segs || !d_raw || !d_frames || !d_resized) {
+    uint8_t* d_frames = bump.take<uint8_t>(frame_bytes + 256);
+    if (!d_in || !d_items || !d_segs || !d_raw || !d_frames) {
         for (int i : idx) push_fallback(X, i);
         return;
     }
@@ -420,17 +492,10 @@ static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
         b.raw = d_raw;
         b.frames = d_frames;
         b.n = n;
-        b.max_width = w;
-        b.max_height = h;
+        b.max_width = max_w;
+        b.max_height = max_h;
         ok = png_decode_launch(b, L.st) == LP_OK;
     }
-    cudaEventRecord(L.ev[1], L.st);
-    if (ok) {
-        ResizeArgs r{d_frames, frame_stride, (size_t)w * ch, ch, g.cx, g.cy, g.cw, g.chh, d_resized, out_stride,
-                     (size_t)g.ow * ch, g.ow, g.oh, n, 3};
-        ok = resize_launch(r, L.st) == LP_OK;
-    }
-    cudaEventRecord(L.ev[2], L.st);
     if (ok) ok = cudaMemcpyAsync(items.data(), d_items, (size_t)n * sizeof(PngDecodeItem), cudaMemcpyDeviceToHost, L.st) == cudaSuccess;
     if (ok) ok = cudaStreamSynchronize(L.st) == cudaSuccess;
     if (!ok) {
@@ -438,82 +503,49 @@ static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
         for (int i : idx) push_fallback(X, i);
         return;
     }
-    lane_time(L, 0, 1, &L.ms_decode);
-    lane_time(L, 1, 2, &L.ms_resize);
-    // items whose stream is corrupt: Transform reports the precise error
-    std::vector<int> good;
-    std::vector<int> good_pos;
-    for (int k = 0; k < n; k++) {
-        if (items[k].status != 0) failed.push_back(idx[k]);
-        else { good.push_back(idx[k]); good_pos.push_back(k); }
-    }
-    if ((int)good.size() == n) {
-        cudaEventRecord(L.ev[2], L.st);
-        sink_encode(X, L, bump, good, d_resized, out_stride, g.ow, g.oh, ch, &failed);
-        cudaEventRecord(L.ev[3], L.st);
-        cudaEventSynchronize(L.ev[3]);
-        lane_time(L, 2, 3, &L.ms_encode);
-    } else {
-        failed.insert(failed.end(), good.begin(), good.end());  // rare: keep the grid path simple, redo the chunk's rest per image
-    }
+    std::vector<char> good((size_t)n);
+    for (int k = 0; k < n; k++) good[k] = items[k].status == 0;
+    resize_and_encode(X, L, bump, idx, runs, d_frames, frame_off, good, &failed);
     for (int i : failed) push_fallback(X, i);
 }
 
-// ------------------------------------------------------------------ WebP (VP8 key frame) groups
-
 static void run_webp(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
     const int n = (int)idx.size();
-    const XItem& g = X->items[idx[0]];
-    const int w = g.w, h = g.h, ch = 3;
+    const std::vector<Run> runs = runs_of(X, idx);
     Bump bump{L.dev, L.dev_bytes};
-    const size_t frame_stride = round_up((size_t)w * h * ch, (size_t)256);
-    const size_t out_stride = round_up((size_t)g.ow * g.oh * ch, (size_t)256);
-    std::vector<uint64_t> off((size_t)n);
+    std::vector<uint64_t> off((size_t)n), frame_off((size_t)n);
     std::vector<uint32_t> len((size_t)n);
-    size_t in_bytes = 0;
+    std::vector<int> ws((size_t)n), hs((size_t)n);
+    size_t in_bytes = 0, frame_bytes = 0;
     for (int k = 0; k < n; k++) {
+        const XItem& xi = X->items[idx[k]];
         off[k] = in_bytes;
-        len[k] = (uint32_t)X->items[idx[k]].webp.vp8_len;
+        len[k] = (uint32_t)xi.webp.vp8_len;
         in_bytes += round_up((size_t)len[k] + 64, (size_t)16);
+        frame_off[k] = frame_bytes;
+        frame_bytes += round_up((size_t)xi.w * xi.h * 3, (size_t)256);
+        ws[k] = xi.w;
+        hs[k] = xi.h;
     }
     uint8_t* d_in = bump.take<uint8_t>(in_bytes + 4096);
-    uint8_t* d_frames = bump.take<uint8_t>((size_t)n * frame_stride + 256);
-    uint8_t* d_resized = bump.take<uint8_t>((size_t)n * out_stride + 256);
+    uint8_t* d_frames = bump.take<uint8_t>(frame_bytes + 256);
     std::vector<int> st((size_t)n, 0), failed;
-    bool ok = d_in && d_frames && d_resized;
+    bool ok = d_in && d_frames;
     for (int k = 0; k < n && ok; k++) {
         ok = cudaMemcpyAsync(d_in + off[k], X->in[idx[k]] + X->items[idx[k]].webp.vp8_off, len[k], cudaMemcpyHostToDevice,
                              L.st) == cudaSuccess;
         L.h2d += len[k];
     }
     cudaEventRecord(L.ev[0], L.st);
-    if (ok) ok = webp_vp8_decode_batch(d_in, off.data(), len.data(), n, w, h, d_frames, frame_stride, st.data(), L.st) == LP_OK;
-    cudaEventRecord(L.ev[1], L.st);
-    if (ok) {
-        ResizeArgs r{d_frames, frame_stride, (size_t)w * ch, ch, g.cx, g.cy, g.cw, g.chh, d_resized, out_stride,
-                     (size_t)g.ow * ch, g.ow, g.oh, n, 3};
-        ok = resize_launch(r, L.st) == LP_OK;
-    }
-    cudaEventRecord(L.ev[2], L.st);
-    if (ok) ok = cudaStreamSynchronize(L.st) == cudaSuccess;
+    if (ok) ok = webp_vp8_decode_batch(d_in, off.data(), len.data(), n, ws.data(), hs.data(), d_frames, frame_off.data(), st.data(), L.st) == LP_OK;
     if (!ok) {
         cudaGetLastError();
         for (int i : idx) push_fallback(X, i);
         return;
     }
-    lane_time(L, 0, 1, &L.ms_decode);
-    lane_time(L, 1, 2, &L.ms_resize);
-    bool all = true;
-    for (int k = 0; k < n; k++) all = all && st[k] == 0;
-    if (all) {
-        cudaEventRecord(L.ev[2], L.st);
-        sink_encode(X, L, bump, idx, d_resized, out_stride, g.ow, g.oh, ch, &failed);
-        cudaEventRecord(L.ev[3], L.st);
-        cudaEventSynchronize(L.ev[3]);
-        lane_time(L, 2, 3, &L.ms_encode);
-    } else {
-        failed = idx;
-    }
+    std::vector<char> good((size_t)n);
+    for (int k = 0; k < n; k++) good[k] = st[k] == 0;
+    resize_and_encode(X, L, bump, idx, runs, d_frames, frame_off, good, &failed);
     for (int i : failed) push_fallback(X, i);
 }
 
@@ -819,40 +851,68 @@ extern "C" int lp_xbatch_transform(lp_xbatch* X, const uint8_t* const* in, const
         else groups[std::make_tuple((int)it.kind, it.w, it.h, it.ch, it.jpeg_sampling)].push_back(i);
     }
     std::vector<Task> tasks;
+    std::vector<double> cost;  // rough device time: the longest tasks start first
     const size_t lane_cap = X->lanes[0].dev_bytes;
+    // PNG and WebP: all geometries of a kind in as few tasks as the arena allows (the map keeps equal
+    // geometries adjacent); at least two, so both lanes work.  GIF: by canvas size.  JPEG: by geometry.
+    std::map<int, std::vector<int>> merged;
     for (auto& kv : groups) {
         const Kind kind = (Kind)std::get<0>(kv.first);
-        const std::vector<int>& g = kv.second;
-        if (kind == K_JPEG) {
-            // host staging bounds a JPEG task: out slots + item mirrors come from the lane's pinned arena
-            const XItem& it0 = X->items[g[0]];
-            const size_t slot = round_up(std::min(out_cap, std::max((size_t)65536, (size_t)it0.ow * it0.oh * 3)), (size_t)256) +
-                                sizeof(JpegDecodeItem) + 64;
-            const size_t per = std::max<size_t>(1, X->lanes[0].host_bytes / slot);
-            // two tasks at least, so both lanes work
-            const size_t want = std::min(per, std::max<size_t>(1, (g.size() + 1) / 2));
-            for (size_t a = 0; a < g.size(); a += want)
-                tasks.push_back(Task{kind, std::vector<int>(g.begin() + a, g.begin() + std::min(g.size(), a + want))});
-            continue;
-        }
+        if (kind == K_PNG || kind == K_WEBP) merged[(int)kind].insert(merged[(int)kind].end(), kv.second.begin(), kv.second.end());
+    }
+    auto split_by_memory = [&](Kind kind, const std::vector<int>& g) {
+        size_t total = 0;
+        for (int i : g) total += item_device_bytes(X, X->items[i], i);
+        const size_t half = total / 2 + 1;
         Task cur{kind, {}};
         size_t used = 64u << 20;
-        const size_t half = (g.size() + 1) / 2;
         for (int i : g) {
             const size_t need = item_device_bytes(X, X->items[i], i);
             if (need + (64u << 20) > lane_cap) {
                 X->fallback.push_back(i);
                 continue;
             }
-            if (!cur.idx.empty() && (used + need > lane_cap || cur.idx.size() >= std::max<size_t>(half, 1))) {
+            if (!cur.idx.empty() && (used + need > lane_cap || used > half + (64u << 20))) {
                 tasks.push_back(cur);
+                cost.push_back((double)used);
                 cur.idx.clear();
                 used = 64u << 20;
             }
             cur.idx.push_back(i);
             used += need;
         }
-        if (!cur.idx.empty()) tasks.push_back(cur);
+        if (!cur.idx.empty()) {
+            tasks.push_back(cur);
+            cost.push_back((double)used);
+        }
+    };
+    for (auto& kv : merged) split_by_memory((Kind)kv.first, kv.second);
+    for (auto& kv : groups) {
+        const Kind kind = (Kind)std::get<0>(kv.first);
+        const std::vector<int>& g = kv.second;
+        if (kind == K_PNG || kind == K_WEBP) continue;
+        if (kind == K_JPEG) {
+            // host staging bounds a JPEG task: out slots + item mirrors come from the lane's pinned arena
+            const XItem& it0 = X->items[g[0]];
+            const size_t slot = round_up(std::min(out_cap, std::max((size_t)65536, (size_t)it0.ow * it0.oh * 3)), (size_t)256) +
+                                sizeof(JpegDecodeItem) + 64;
+            const size_t per = std::max<size_t>(1, X->lanes[0].host_bytes / slot);
+            const size_t want = std::min(per, std::max<size_t>(1, (g.size() + 1) / 2));  // two tasks at least: both lanes work
+            for (size_t a = 0; a < g.size(); a += want) {
+                tasks.push_back(Task{kind, std::vector<int>(g.begin() + a, g.begin() + std::min(g.size(), a + want))});
+                cost.push_back((double)tasks.back().idx.size() * it0.w * it0.h * 0.05);
+            }
+            continue;
+        }
+        split_by_memory(kind, g);
+    }
+    {   // longest first
+        std::vector<int> order(tasks.size());
+        for (size_t t = 0; t < order.size(); t++) order[t] = (int)t;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+        std::vector<Task> sorted;
+        for (int t : order) sorted.push_back(std::move(tasks[t]));
+        tasks.swap(sorted);
     }
     X->stats.groups = (int)groups.size();
     // two lanes drain the task list

@@ -186,6 +186,23 @@ static int decode_jpeg_into(const Decoder* d, Mat* m) {
         int rc = jpeg_parse_scans(d->data, d->len, h, scans.data(), (int)scans.size(), &nscans, sets.data(),
                                   (int)sets.size(), &nsets);
         if (rc) return rc;
+        // every scan of a multi-scan file is walked by ONE device thread (jpeg_multiscan_kernel): bound the work a
+        // hostile file (up to 256 scans over a large frame) can queue on the caller's stream.  Real progressive
+        // files have ~10 scans; an 8192 x 8192 4:4:4 frame with 20 scans still passes.
+        size_t visits = 0;
+        for (int k = 0; k < nscans; k++) {
+            size_t per = 0;
+            for (int c = 0; c < scans[k].ns; c++) {
+                const int ci = scans[k].ci[c];
+                per += (size_t)h.mcus_x * h.mcus_y * h.comp[ci].h * h.comp[ci].v;
+            }
+            visits += per;
+        }
+        if (visits > ((size_t)1 << 26)) {
+            fprintf(stderr, "[lilliput_b200] multi-scan JPEG: %zu block visits over %d scans exceed the serial decoder's budget\n",
+                    visits, nscans);
+            return LP_ERR_UNSUPPORTED;
+        }
     }
     cudaStream_t st = thread_stream();
     JpegDecodeItem it;

@@ -115,7 +115,8 @@ lp_batch* lp::batch_create_in(const lp_batch_config* cfg, uint8_t* dev_arena, si
                               size_t host_bytes) {
     if (!cfg || cfg->max_images < 1 || cfg->src_width < 1 || cfg->src_height < 1) return nullptr;
     if (ensure_device()) return nullptr;
-    LP_CUDA_OK_NULL(cudaSetDevice(cfg->device));
+    DeviceGuard dev_guard(cfg->device);
+    if (!dev_guard.ok) return nullptr;
     lp_batch* b = new lp_batch;
     b->cfg = *cfg;
     b->owns_mem = dev_arena == nullptr;
@@ -213,7 +214,7 @@ lp_batch* lp::batch_create_in(const lp_batch_config* cfg, uint8_t* dev_arena, si
 
 extern "C" void lp_batch_destroy(lp_batch* b) {
     if (!b) return;
-    cudaSetDevice(b->cfg.device);
+    DeviceGuard dev_guard(b->cfg.device);
     cudaDeviceSynchronize();
     batch_free(b);
 }
@@ -516,7 +517,8 @@ static void batch_finish_chunk(lp_batch* b, int i0, int cnt, uint8_t* const* out
 extern "C" int lp_batch_stage(lp_batch* b, const uint8_t* const* in, const size_t* in_len, int n,
                               int* status) {
     if (!b || (n > 0 && (!in || !in_len)) || n < 0 || n > b->cfg.max_images) return LP_ERR_BAD_ARGUMENT;
-    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+    DeviceGuard dev_guard(b->cfg.device);
+    if (!dev_guard.ok) return LP_ERR_CUDA;
     batch_begin(b, n);
     for (int i0 = 0; i0 < n; i0 += b->chunk) {
         const int cnt = std::min(b->chunk, n - i0);
@@ -535,7 +537,8 @@ extern "C" int lp_batch_stage(lp_batch* b, const uint8_t* const* in, const size_
 
 extern "C" int lp_batch_run(lp_batch* b, float* stage_ms) {
     if (!b) return LP_ERR_BAD_ARGUMENT;
-    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+    DeviceGuard dev_guard(b->cfg.device);
+    if (!dev_guard.ok) return LP_ERR_CUDA;
     const long launches0 = g_launches;
     const int nchunks = ceil_div(b->n, b->chunk);
     for (int c = 0; c < nchunks; c++) {
@@ -566,7 +569,8 @@ extern "C" int lp_batch_run(lp_batch* b, float* stage_ms) {
 
 extern "C" int lp_batch_fetch(lp_batch* b, uint8_t* const* out, size_t* out_len, int* status) {
     if (!b || (b->n > 0 && (!out || !out_len))) return LP_ERR_BAD_ARGUMENT;
-    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+    DeviceGuard dev_guard(b->cfg.device);
+    if (!dev_guard.ok) return LP_ERR_CUDA;
     if (b->n == 0) return LP_OK;
     int rc = batch_download_chunk(b, 0, b->n, b->st);
     if (rc) return rc;
@@ -583,7 +587,8 @@ extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const s
                                   uint8_t* const* out, size_t* out_len, int* status) {
     if (!b || n < 0 || n > b->cfg.max_images || (n > 0 && (!in || !in_len || !out || !out_len)))
         return LP_ERR_BAD_ARGUMENT;
-    LP_CUDA_OK(cudaSetDevice(b->cfg.device));
+    DeviceGuard dev_guard(b->cfg.device);
+    if (!dev_guard.ok) return LP_ERR_CUDA;
     batch_begin(b, n);
     const long launches0 = g_launches;
     // Chunk schedule: nothing can run before the first chunk's headers are parsed and its bytes have

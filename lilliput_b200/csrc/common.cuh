@@ -41,6 +41,21 @@ cudaStream_t thread_stream();
 // (bench.py reports it as gpu_launches).
 extern thread_local long g_launches;
 
+// Makes `device` current for the scope and restores the caller's device afterwards (the batch entry points take a
+// device ordinal; the per-image ABI on the same host thread must keep seeing the device it was using).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = prev == device || cudaSetDevice(device) == cudaSuccess;
+        if (prev == device) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 template <class T>
 static inline T ceil_div(T a, T b) {
     return (a + b - 1) / b;

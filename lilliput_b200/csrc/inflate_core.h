@@ -800,19 +800,41 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                                 blocked_q[l] = m.q;
                                 break;
                             }
-                            if (dist >= len && src0 >= ring_lo) {
-                                // the usual case: source and destination do not overlap and both live in the ring
-                                uint32_t sp_ = src0 & kRingMask, dp_ = m.q & kRingMask;
-                                if (sp_ + len <= kRing && dp_ + len <= kRing) {
-                                    for (uint32_t i = 0; i < len; i++) ws.ring[dp_ + i] = ws.ring[sp_ + i];
+                            const uint32_t sp_ = src0 & kRingMask, dp_ = m.q & kRingMask;
+                            if (src0 >= ring_lo && sp_ + len <= kRing && dp_ + len <= kRing) {
+                                // both ends in the ring without wrap-around (the usual case): four bytes per step, loads
+                                // first, so they are in flight together instead of one dependent load-store pair per byte
+                                if (dist >= 4 || dist >= len) {
+                                    // (dist >= 4: a step of four never reads a byte it has not yet written)
+                                    uint32_t i = 0;
+                                    for (; i + 4 <= len; i += 4) {
+                                        const uint8_t b0 = ws.ring[sp_ + i], b1 = ws.ring[sp_ + i + 1], b2 = ws.ring[sp_ + i + 2],
+                                                      b3 = ws.ring[sp_ + i + 3];
+                                        ws.ring[dp_ + i] = b0; ws.ring[dp_ + i + 1] = b1; ws.ring[dp_ + i + 2] = b2; ws.ring[dp_ + i + 3] = b3;
+                                    }
+                                    if (i < len) {
+                                        const uint32_t r = len - i;  // 1..3
+                                        const uint8_t b0 = ws.ring[sp_ + i], b1 = r > 1 ? ws.ring[sp_ + i + 1] : 0,
+                                                      b2 = r > 2 ? ws.ring[sp_ + i + 2] : 0;
+                                        ws.ring[dp_ + i] = b0;
+                                        if (r > 1) ws.ring[dp_ + i + 1] = b1;
+                                        if (r > 2) ws.ring[dp_ + i + 2] = b2;
+                                    }
                                 } else {
-                                    for (uint32_t i = 0; i < len; i++) ws.ring[(dp_ + i) & kRingMask] = ws.ring[(sp_ + i) & kRingMask];
+                                    // run with a period of 1..3 bytes: the pattern is read once, then only stored
+                                    const uint8_t p0 = ws.ring[sp_], p1 = dist > 1 ? ws.ring[sp_ + 1] : p0,
+                                                  p2 = dist > 2 ? ws.ring[sp_ + 2] : (dist > 1 ? p0 : p0);
+                                    uint32_t k = 0;
+                                    for (uint32_t i = 0; i < len; i++) {
+                                        ws.ring[dp_ + i] = k == 0 ? p0 : k == 1 ? p1 : p2;
+                                        if (++k == dist) k = 0;
+                                    }
                                 }
                             } else {
                                 uint32_t k = 0;  // i mod dist, kept incrementally
                                 for (uint32_t i = 0; i < len; i++) {
-                                    const uint32_t sp_ = src0 + k;
-                                    const uint8_t v = sp_ >= ring_lo ? ws.ring[sp_ & kRingMask] : s.out[sp_];
+                                    const uint32_t sq = src0 + k;
+                                    const uint8_t v = sq >= ring_lo ? ws.ring[sq & kRingMask] : s.out[sq];
                                     ws.ring[(m.q + i) & kRingMask] = v;
                                     if (++k == dist) k = 0;
                                 }

@@ -252,6 +252,29 @@ int jpeg_parse_header(const uint8_t* in, size_t len, JpegHeader* out) {
                     break;
                 }
             }
+            // libjpeg's jpeg_make_d_derived_tbl (jdhuff.c) refuses a table whose code lengths over-subscribe the code
+            // space or whose DC symbols exceed 15 (JERR_BAD_HUFF_TABLE) when the scan starts: the header reads, the
+            // decode fails.  Same here, on every decode path (the parallel kernel would otherwise read a DC symbol's
+            // high nibble as a run).
+            for (int i = 0; i < ns && !undecodable && h.supported; i++) {
+                for (int tc = 0; tc < 2 && !undecodable; tc++) {
+                    const int th = tc ? h.comp[i].ta : h.comp[i].td;
+                    const uint8_t* bits = h.huff_bits[tc][th];
+                    unsigned code = 0;
+                    int total = 0, last = 0;
+                    for (int len = 1; len <= 16; len++)
+                        if (bits[len]) last = len;
+                    for (int len = 1; len <= last; len++) {
+                        code += bits[len];
+                        if (code >= (1u << len)) undecodable = true;  // "no code is allowed to be all ones" (jdhuff.c)
+                        code <<= 1;
+                        total += bits[len];
+                    }
+                    if (tc == 0)
+                        for (int k = 0; k < total && k < 256; k++)
+                            if (h.huff_vals[0][th][k] > 15) undecodable = true;
+                }
+            }
             if (undecodable) h.supported = h.multiscan = false;  // read_data refuses on the host: ErrDecodingFailed
             h.scan_offset = pos + 2 + seg;
             // upper bound of the entropy-coded segment: up to the last EOI if there is one

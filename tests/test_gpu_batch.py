@@ -116,3 +116,28 @@ def test_batch_roi_geometries(cuda_lib, oracle, geom):
             assert o == oracle.jpeg_encode(oracle.fit(dec, ew, eh), 85)
     finally:
         b.close()
+
+
+def test_batch_mixed_sampling_layouts_in_any_order(cuda_lib, oracle):
+    """4:2:0, 4:2:2 and 4:4:4 files of one size in one batch, densest layout last and first: the per-chunk scratch
+    layout follows the chunk's densest file, not the first file the context ever saw."""
+    cv2 = pytest.importorskip("cv2")
+    w, h = 320, 240
+    opt = abi.ImageOptions(FileType=".jpeg", Width=64, Height=64, ResizeMethod=abi.ImageOpsFit,
+                           EncodeOptions={abi.JpegQuality: 85})
+    files = []
+    for k, sf in enumerate([cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+                            cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420]):
+        ok, b = cv2.imencode(".jpg", synth_image(900 + k, w, h, 3), [cv2.IMWRITE_JPEG_QUALITY, 90,
+                                                                       cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf])
+        assert ok
+        files.append(bytes(b))
+    b = abi.Batch(cuda_lib, 0, 8, w, h, 64, 64, 85, max_in_bytes=1 << 22, chunk=3)
+    try:
+        for order in (files, files[::-1], [files[2], files[0], files[2], files[1]]):
+            outs, status = b.transform(order)
+            assert status == [0] * len(order)
+            for f, o in zip(order, outs):
+                assert o == cuda_lib.transform(f, opt)
+    finally:
+        b.close()

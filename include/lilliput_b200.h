@@ -180,6 +180,8 @@ int lp_batch_run(lp_batch* b, float* stage_ms);
 int lp_batch_fetch(lp_batch* b, uint8_t* const* out, size_t* out_len, int* status);
 /* Number of kernel launches issued by the last lp_batch_run / lp_batch_transform. */
 int lp_batch_last_launches(const lp_batch* b);
+/* Device-to-host bytes per image besides the encoded file (length, packed offset, item mirror). */
+size_t lp_batch_d2h_overhead_per_image(void);
 /* Images per pipelined chunk actually used by this context. */
 int lp_batch_chunk(const lp_batch* b);
 /* Diagnostics (valid after lp_batch_fetch / lp_batch_transform): rounds the parallel Huffman
@@ -213,6 +215,18 @@ int lp_xbatch_transform(lp_xbatch* x, const uint8_t* const* in, const size_t* in
                         const lp_image_options* opt, uint8_t* const* out, size_t out_cap, size_t* out_len,
                         int* status);
 void lp_xbatch_get_stats(const lp_xbatch* x, lp_xbatch_stats* out);
+
+/* ---- the same call over several GPUs of one node (shard by image index, no collective) ----
+ * One lp_xbatch per device behind one call: the batch is cut into contiguous blocks balanced by compressed bytes,
+ * every block runs on its own GPU from its own host thread, results land in the caller's arrays by index. */
+typedef struct lp_multi lp_multi;
+lp_multi* lp_multi_create(const int* devices, int n_devices, const lp_xbatch_config* config_template);
+void lp_multi_destroy(lp_multi* m);
+int lp_multi_device_count(const lp_multi* m);
+int lp_multi_transform(lp_multi* m, const uint8_t* const* in, const size_t* in_len, int n,
+                       const lp_image_options* opt, uint8_t* const* out, size_t out_cap, size_t* out_len,
+                       int* status);
+void lp_multi_get_stats(const lp_multi* m, int device_index, lp_xbatch_stats* out);
 
 /* ---- single stages on device pointers, on `stream` (a cudaStream_t) -------- */
 

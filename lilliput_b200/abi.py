@@ -459,3 +459,51 @@ class XBatch:
         s = _XBatchStats()
         self.lib.l.lp_xbatch_get_stats(self.h, C.byref(s))
         return {k: getattr(s, k) for k, _ in _XBatchStats._fields_}
+
+
+class MultiBatch:
+    """lp_multi_*: one lp_xbatch per GPU behind one call, sharded by image index (contiguous blocks balanced by
+    compressed bytes), no collective."""
+
+    def __init__(self, lib: Lib, devices, arena_bytes: int = 0, host_threads: int = 0, max_size: int = 8192):
+        self.lib = lib
+        l = lib.l
+        l.lp_multi_create.restype = C.c_void_p
+        l.lp_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(_XBatchConfig)]
+        l.lp_multi_destroy.argtypes = [C.c_void_p]
+        l.lp_multi_transform.restype = C.c_int
+        l.lp_multi_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_ImageOptions),
+                                         C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        l.lp_multi_get_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(_XBatchStats)]
+        devs = (C.c_int * len(devices))(*devices)
+        cfg = _XBatchConfig(0, arena_bytes, host_threads, max_size)
+        self.n_devices = len(devices)
+        self.h = l.lp_multi_create(devs, len(devices), C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("lp_multi_create failed")
+
+    def close(self):
+        if self.h:
+            self.lib.l.lp_multi_destroy(self.h)
+            self.h = None
+
+    def transform_into(self, ptrs, lens, n, copt, out_ptrs, out_cap, out_lens, status):
+        return self.lib.l.lp_multi_transform(self.h, ptrs, lens, n, C.byref(copt), out_ptrs, out_cap, out_lens, status)
+
+    def transform(self, bufs, opt: ImageOptions, out_cap: int = 1 << 20):
+        n = len(bufs)
+        ptrs, lens, keep = Batch._ptr_arrays(bufs)
+        out = np.empty((n, out_cap), dtype=np.uint8)
+        out_ptrs = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
+        out_lens = (C.c_size_t * n)()
+        status = (C.c_int * n)()
+        copt = opt._c()
+        rc = self.lib.l.lp_multi_transform(self.h, ptrs, lens, n, C.byref(copt), out_ptrs, out_cap, out_lens, status)
+        if rc:
+            raise LilliputError(rc)
+        return [out[i, : out_lens[i]].tobytes() for i in range(n)], list(status)
+
+    def stats(self, device_index: int) -> dict:
+        s = _XBatchStats()
+        self.lib.l.lp_multi_get_stats(self.h, device_index, C.byref(s))
+        return {k: getattr(s, k) for k, _ in _XBatchStats._fields_}

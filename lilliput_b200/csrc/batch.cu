@@ -644,6 +644,8 @@ extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const s
 }
 
 extern "C" int lp_batch_last_launches(const lp_batch* b) { return b ? b->last_launches : 0; }
+// bytes per image that come back besides the encoded file: length, packed offset, the item mirror (status, diagnostics)
+extern "C" size_t lp_batch_d2h_overhead_per_image(void) { return 4 + 8 + sizeof(JpegDecodeItem); }
 extern "C" int lp_batch_chunk(const lp_batch* b) { return b ? b->chunk : 0; }
 // Diagnostics after lp_batch_fetch / lp_batch_transform: Huffman synchronisation rounds per image.
 extern "C" void lp_batch_sync_rounds(const lp_batch* b, double* mean, int* max) {

@@ -189,6 +189,10 @@ struct WarpShared {
     // latest decode, with the matches / bytes decoded in front of it
     uint32_t ck_pos_nm[32][kCk];  // (position << 16) | matches; position 0xFFFF = none
     uint32_t ck_cnt[32][kCk];
+    // the matches of the window being written, in stream order, compact: (position in the window << 20) |
+    // (min(length - 3, 127) << 13) | distance; length field 127 = look the full record up in Stream::mlist
+    // (lengths >= 130 and distances >= 8192).  Reading them back from global memory cost ~300 cycles per match.
+    uint32_t mrec[kMaxMatches];
 };
 
 LP_INF_FN uint32_t lit_entry(uint32_t sym, uint32_t len) {
@@ -358,7 +362,8 @@ enum { kFlagNone = 0, kFlagEob = 1, kFlagBad = 2 };
 // Returns true when it merged.  ck slots are addressed relative to `nominal` (the subsequence start).
 template <bool WRITE, bool REC, bool CMP>
 LP_INF_FN bool decode_span(WarpShared& ws, uint32_t start, uint32_t end, uint32_t q, uint32_t budget,
-                           Match* mlist, Span& r, uint32_t nominal, int lane, uint32_t old_cnt, uint32_t old_nm) {
+                           Match* mlist, Span& r, uint32_t nominal, int lane, uint32_t old_cnt, uint32_t old_nm,
+                           uint32_t* mrec = nullptr, uint32_t obase = 0) {
     uint32_t pos = start, cnt = 0, nm = 0, flag = kFlagNone;
     uint32_t next_ck = nominal + kCkBits;
     int j = 0;
@@ -438,6 +443,10 @@ LP_INF_FN bool decode_span(WarpShared& ws, uint32_t start, uint32_t end, uint32_
             }
             mlist[nm].q = q + cnt;
             mlist[nm].ld = (len << 16) | dist;
+            {
+                const bool esc = len - 3 >= 127u || dist >= 8192u;
+                mrec[nm] = ((q + cnt - obase) << 20) | ((esc ? 127u : len - 3) << 13) | (esc ? 0u : dist);
+            }
         }
         cnt += len;
         nm++;
@@ -753,7 +762,7 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                 if (active) {
                     const uint32_t budget = l < nfull ? 0xFFFFFFFFu : (kCapT > coff[l] ? kCapT - coff[l] : 0u);
                     decode_span<true, false, false>(ws, start[l], rel + (uint32_t)(l + 1) * kSubBits, o + coff[l], budget,
-                                                    s.mlist + moff[l], sp, 0, l, 0, 0);
+                                                    s.mlist + moff[l], sp, 0, l, 0, 0, ws.mrec + moff[l], o);
                     wexit[l] = sp.exit; wcnt[l] = sp.cnt; wnm[l] = sp.nm; wflag[l] = sp.flag;
                 }
             }
@@ -792,7 +801,14 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                 for (int round = 0; round < 34; round++) {
                     LP_INF_LANES(l) {
                         while (mi[l] < mend[l]) {
-                            const Match m = s.mlist[mi[l]];
+                            const uint32_t rec = ws.mrec[mi[l]];
+                            Match m;
+                            if (((rec >> 13) & 127u) == 127u) {
+                                m = s.mlist[mi[l]];
+                            } else {
+                                m.q = o + (rec >> 20);
+                                m.ld = ((((rec >> 13) & 127u) + 3u) << 16) | (rec & 8191u);
+                            }
                             const uint32_t len = m.ld >> 16, dist = m.ld & 0xFFFFu;
                             const uint32_t src0 = m.q - dist, L = dist < len ? dist : len;
                             const bool ok = src0 + L <= H || src0 >= own_start[l] || own_start[l] <= H;

@@ -20,7 +20,7 @@
 
 namespace lp {
 
-constexpr int kPngWarps = 4;  // warps (= images) per CTA
+constexpr int kPngWarps = 3;  // warps (= images) per CTA: 3 x ~24 KB of shared memory, 3 CTAs per SM
 
 // One warp per image; the decoder itself is inflate_core.h (speculative per-lane subsequence decoding,
 // shared-memory output ring, 16-byte flushes).  Dynamic shared memory: one WarpShared per warp.

@@ -986,3 +986,81 @@ extern "C" int lp_xbatch_transform(lp_xbatch* X, const uint8_t* const* in, const
     cudaSetDevice(prev);
     return LP_OK;
 }
+
+// ------------------------------------------------------------------ library-level multi-GPU dispatch
+// images are independent units with zero exchange -- the batch is cut into one contiguous block per
+// GPU, balanced by compressed bytes, and each block runs through that GPU's own lp_xbatch (own arena, pinned
+// staging, streams) on its own host thread; results land in the caller's arrays by index.  No collective, no
+// peer traffic.  (bench.py's torchrun harness is the process-per-GPU form of the same sharding.)
+
+struct lp_multi {
+    std::vector<lp_xbatch*> ctx;
+    std::vector<int> devices;
+    std::vector<int> first;  // block boundaries of the last call (ctx.size() + 1)
+};
+
+extern "C" lp_multi* lp_multi_create(const int* devices, int n_devices, const lp_xbatch_config* tmpl) {
+    if (n_devices < 1 || !devices) return nullptr;
+    lp_multi* m = new lp_multi;
+    for (int g = 0; g < n_devices; g++) {
+        lp_xbatch_config c;
+        memset(&c, 0, sizeof(c));
+        if (tmpl) c = *tmpl;
+        c.device = devices[g];
+        lp_xbatch* x = lp_xbatch_create(&c);
+        if (!x) {
+            for (lp_xbatch* y : m->ctx) lp_xbatch_destroy(y);
+            delete m;
+            return nullptr;
+        }
+        m->ctx.push_back(x);
+        m->devices.push_back(devices[g]);
+    }
+    return m;
+}
+
+extern "C" void lp_multi_destroy(lp_multi* m) {
+    if (!m) return;
+    for (lp_xbatch* x : m->ctx) lp_xbatch_destroy(x);
+    delete m;
+}
+
+extern "C" int lp_multi_device_count(const lp_multi* m) { return m ? (int)m->ctx.size() : 0; }
+
+extern "C" int lp_multi_transform(lp_multi* m, const uint8_t* const* in, const size_t* in_len, int n,
+                                  const lp_image_options* opt, uint8_t* const* out, size_t out_cap, size_t* out_len,
+                                  int* status) {
+    if (!m || n < 0 || !opt || (n > 0 && (!in || !in_len || !out || !out_len || !status))) return LP_ERR_BAD_ARGUMENT;
+    const int G = (int)m->ctx.size();
+    // contiguous blocks with (nearly) equal compressed bytes
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += in_len[i] + 4096;  // (+ a per-image constant: tiny files still cost a launch slot)
+    m->first.assign((size_t)G + 1, n);
+    m->first[0] = 0;
+    {
+        size_t acc = 0;
+        int g = 1;
+        for (int i = 0; i < n && g < G; i++) {
+            acc += in_len[i] + 4096;
+            if (acc * G >= total * (size_t)g) m->first[g++] = i + 1;
+        }
+    }
+    std::vector<int> rc((size_t)G, LP_OK);
+    std::vector<std::thread> pool;
+    for (int g = 0; g < G; g++) {
+        const int i0 = m->first[g], cnt = m->first[g + 1] - m->first[g];
+        if (cnt <= 0) continue;
+        pool.emplace_back([=, &rc]() {
+            rc[g] = lp_xbatch_transform(m->ctx[g], in + i0, in_len + i0, cnt, opt, out + i0, out_cap, out_len + i0, status + i0);
+        });
+    }
+    for (auto& t : pool) t.join();
+    for (int g = 0; g < G; g++)
+        if (rc[g]) return rc[g];
+    return LP_OK;
+}
+
+// per-device statistics of the last call
+extern "C" void lp_multi_get_stats(const lp_multi* m, int device_index, lp_xbatch_stats* out) {
+    if (m && out && device_index >= 0 && device_index < (int)m->ctx.size()) lp_xbatch_get_stats(m->ctx[device_index], out);
+}

@@ -178,3 +178,24 @@ def test_xbatch_empty_and_small_buffers(cuda_lib, xb, oracle):
     assert outs == [] and status == []
     files = [oracle.jpeg_encode(synth_image(800 + k, 256, 256, 3), 90) for k in range(3)]
     check_against_per_image(cuda_lib, xb, files, opt, cap=700)       # too small for the output: same error per item
+
+
+def test_multi_gpu_dispatcher_matches_per_image(cuda_lib, oracle):
+    """lp_multi_*: the library-level sharding by image index.  Runs on however many GPUs the box has (1 is enough to
+    exercise the dispatcher; the same device twice exercises two contexts side by side)."""
+    import torch
+    ndev = max(1, torch.cuda.device_count())
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    m = abi.MultiBatch(cuda_lib, devices, arena_bytes=6 << 30)
+    try:
+        files = [oracle.jpeg_encode(synth_image(950 + k, 320, 200, 3), 90) for k in range(9)]
+        files += [rgb_png(synth_image(960 + k, 160 + 16 * k, 120, 4)) for k in range(4)]
+        opt = abi.ImageOptions(FileType=".jpeg", Width=64, Height=64, ResizeMethod=abi.ImageOpsFit,
+                               EncodeOptions={abi.JpegQuality: 85}, EncodeTimeout_ns=T)
+        outs, status = m.transform(files, opt)
+        assert status == [0] * len(files)
+        for f, o in zip(files, outs):
+            assert o == cuda_lib.transform(f, opt)
+        assert sum(m.stats(g)["grid_items"] + m.stats(g)["fallback_items"] for g in range(len(devices))) == len(files)
+    finally:
+        m.close()

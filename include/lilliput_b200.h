@@ -109,6 +109,10 @@ int lp_encode_host(const char* ext, const uint8_t* pixels, int width, int height
 int lp_orient_host(const uint8_t* src, int width, int height, int type, int orientation,
                    uint8_t* dst, int* out_w, int* out_h);
 
+/* Framebuffer.TonemapToSDR (ref opencv.go:791-810, color_info.cpp:112-270): PQ (16) / HLG (18) pixels of a packed
+ * 8-bit BGR / BGRA frame -> SDR BT.709, in place.  primaries = cICP colour primaries code point. */
+int lp_tonemap_host(uint8_t* pixels, int width, int height, int type, int transfer, int primaries);
+
 /* GIF: animation metadata as gifDecoder reports it (ref giflib.go:76-151). */
 typedef struct lp_gif_info {
     int width, height, frame_count, loop_count, duration_ms;

@@ -145,6 +145,10 @@ size_t opencv_png_insert_cicp(void* png, size_t png_len, size_t png_cap, uint8_t
  * PSNR benchmark), each of which would call this first.  Returns 0 on success.
  */
 int lp_mat_sync_host(opencv_mat mat);
+/* Additive: Framebuffer.TonemapToSDR (ref opencv.go:791-810): PQ / HLG pixels of an 8-bit BGR(A) mat -> SDR BT.709
+ * in place (ref color_info.cpp:112-270).  The Go side calls tonemap_rgb_8u_inplace on its own buffer; with the
+ * pixels in HBM the call goes through the mat instead.  transfer / primaries are the cICP code points. */
+int lp_mat_tonemap_to_sdr(opencv_mat mat, int transfer, int primaries);
 /* Additive: tell the library the host bytes were modified by the caller. */
 void lp_mat_mark_host_dirty(opencv_mat mat);
 

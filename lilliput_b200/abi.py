@@ -269,6 +269,16 @@ class Lib:
             metas.append(dict(x=x, y=y, delay=delay, dispose=dispose, blend=blend))
         return inf, frames, metas, rc
 
+    def tonemap(self, img: np.ndarray, transfer: int, primaries: int) -> np.ndarray:
+        """Framebuffer.TonemapToSDR (ref opencv.go:791-810) on a packed BGR / BGRA frame."""
+        out = np.ascontiguousarray(img).copy()
+        self.l.lp_tonemap_host.restype = C.c_int
+        self.l.lp_tonemap_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        rc = self.l.lp_tonemap_host(out.ctypes.data, out.shape[1], out.shape[0], self._type_of(out), transfer, primaries)
+        if rc:
+            raise LilliputError(rc)
+        return out
+
     def orient(self, img: np.ndarray, orientation: int) -> np.ndarray:
         """Framebuffer.OrientationTransform (ref opencv.go:271)."""
         img = np.ascontiguousarray(img, dtype=np.uint8)

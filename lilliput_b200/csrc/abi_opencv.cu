@@ -506,6 +506,21 @@ int lp_mat_sync_host(opencv_mat mat) {
     return rc;
 }
 
+// Additive: Framebuffer.TonemapToSDR (ref opencv.go:791-810 -> color_info.cpp:239-270 tonemap_rgb_8u_inplace) on the
+// device mirror of the mat.  In the reference this is a call on the Go buffer; here the pixels live in HBM.
+int lp_mat_tonemap_to_sdr(opencv_mat mat, int transfer, int primaries) {
+    Mat* m = static_cast<Mat*>(mat);
+    if (!m || m->rows <= 0 || m->cols <= 0) return LP_OK;
+    if ((m->type & 7) != 0 || (m->channels() != 3 && m->channels() != 4)) return LP_OK;  // the reference returns silently
+    int rc = ensure_dev(m);
+    if (rc) return rc;
+    rc = tonemap_to_sdr_launch(m->dptr(), m->dev_step, m->channels(), m->cols, m->rows, transfer, primaries, thread_stream());
+    if (rc) return rc;
+    m->dev_valid = true;
+    m->host_valid = false;
+    return sync_stream();
+}
+
 void lp_mat_mark_host_dirty(opencv_mat mat) {
     Mat* m = static_cast<Mat*>(mat);
     if (!m) return;

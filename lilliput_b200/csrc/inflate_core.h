@@ -327,6 +327,9 @@ LP_INF_FN uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // bits [s
 #endif
 }
 
+// oldest output position the ring still holds once a window that starts at o and produces wT bytes is written
+LP_INF_FN uint32_t ring_lo_d0(uint32_t o, uint32_t wT) { return o + wT > kRing ? o + wT - kRing : 0; }
+
 // A code longer than the lookahead of table t in `bits` (>= 15 valid bits): the canonical walk continues behind
 // the lookahead (a code of <= look_bits bits would have been in the table), at most 15 - look_bits steps.
 // Returns the entry (code length in bits 0..3) or 0 when the bits are no code word.
@@ -788,6 +791,43 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
             // unfinished lane is never blocked, so every round finishes at least one more lane; PNG data
             // mostly refers a pixel or a scanline back, i.e. to the lane itself or in front of the window.
             const uint32_t ring_lo = o + wT > kRing ? o + wT - kRing : 0;  // oldest position the ring still holds
+            // phase D0: matches whose source lies entirely in front of the window (three quarters of them in filtered
+            // PNG data: the pixel above is a scanline back) depend on nothing in the window -- they are spread evenly
+            // over the lanes, whatever subsequence they came from.  Sources behind the ring are read from the flushed
+            // output, eight byte-loads in flight at a time.
+            if (wM) {
+                LP_INF_LANES(l) {
+                    for (uint32_t j = (uint32_t)l; j < wM; j += 32) {
+                        const uint32_t rec = ws.mrec[j];
+                        Match m;
+                        if (((rec >> 13) & 127u) == 127u) {
+                            m = s.mlist[j];
+                        } else {
+                            m.q = o + (rec >> 20);
+                            m.ld = ((((rec >> 13) & 127u) + 3u) << 16) | (rec & 8191u);
+                        }
+                        const uint32_t len = m.ld >> 16, dist = m.ld & 0xFFFFu;
+                        if (!(dist >= len && (m.q - o) + len <= dist)) continue;  // depends on window bytes: phase D1
+                        const uint32_t src0 = m.q - dist;
+                        for (uint32_t i0 = 0; i0 < len; i0 += 8) {
+                            uint8_t b[8];
+#ifndef LP_INF_HOST
+#pragma unroll
+#endif
+                            for (uint32_t k = 0; k < 8; k++) {
+                                const uint32_t sq = src0 + i0 + k;
+                                b[k] = i0 + k < len ? (sq >= ring_lo_d0(o, wT) ? ws.ring[sq & kRingMask] : s.out[sq]) : (uint8_t)0;
+                            }
+#ifndef LP_INF_HOST
+#pragma unroll
+#endif
+                            for (uint32_t k = 0; k < 8; k++)
+                                if (i0 + k < len) ws.ring[(m.q + i0 + k) & kRingMask] = b[k];
+                        }
+                    }
+                }
+                wsync();
+            }
             if (wM) {
                 LaneVar<uint32_t> mi, mend, own_start, blocked_q, notdone;
                 LP_INF_LANES(l) {
@@ -799,7 +839,13 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                 }
                 uint32_t H = o;
                 for (int round = 0; round < 34; round++) {
+#if defined(LP_INF_STATS) && defined(LP_INF_HOST)
+                    uint32_t round_max = 0;
+#endif
                     LP_INF_LANES(l) {
+#if defined(LP_INF_STATS) && defined(LP_INF_HOST)
+                        uint32_t done_here = 0;
+#endif
                         while (mi[l] < mend[l]) {
                             const uint32_t rec = ws.mrec[mi[l]];
                             Match m;
@@ -810,12 +856,24 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                                 m.ld = ((((rec >> 13) & 127u) + 3u) << 16) | (rec & 8191u);
                             }
                             const uint32_t len = m.ld >> 16, dist = m.ld & 0xFFFFu;
+                            if (dist >= len && (m.q - o) + len <= dist) {  // done in phase D0
+                                mi[l]++;
+                                continue;
+                            }
                             const uint32_t src0 = m.q - dist, L = dist < len ? dist : len;
                             const bool ok = src0 + L <= H || src0 >= own_start[l] || own_start[l] <= H;
                             if (!ok) {
                                 blocked_q[l] = m.q;
+#if defined(LP_INF_STATS) && defined(LP_INF_HOST)
+                                g_stats[9]++;
+#endif
                                 break;
                             }
+#if defined(LP_INF_STATS) && defined(LP_INF_HOST)
+                            done_here++;
+                            if (src0 < ring_lo) { g_stats[8]++; g_stats[10] += len; }
+                            if (src0 + L <= o) g_stats[11]++;
+#endif
                             const uint32_t sp_ = src0 & kRingMask, dp_ = m.q & kRingMask;
                             if (src0 >= ring_lo && sp_ + len <= kRing && dp_ + len <= kRing) {
                                 // both ends in the ring without wrap-around (the usual case): four bytes per step, loads
@@ -857,9 +915,15 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                             }
                             mi[l]++;
                         }
+#if defined(LP_INF_STATS) && defined(LP_INF_HOST)
+                        if (done_here > round_max) round_max = done_here;
+#endif
                         notdone[l] = mi[l] < mend[l] ? 1u : 0u;
                     }
                     wsync();
+#if defined(LP_INF_STATS) && defined(LP_INF_HOST)
+                    g_stats[12] += round_max;
+#endif
                     const uint32_t nd = ballot(notdone);
                     if (!nd) break;
                     LP_INF_COUNT(6, 1);

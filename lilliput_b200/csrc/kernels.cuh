@@ -284,6 +284,9 @@ int orient_launch(const uint8_t* src, int w, int h, int channels, int orientatio
                   cudaStream_t st);
 int copy_region_launch(const uint8_t* src, size_t src_step, int src_ch, uint8_t* dst,
                        size_t dst_step, int dst_ch, int w, int h, cudaStream_t st);
+// ---- tonemap.cu ----------------------------------------------------------------------------
+int tonemap_to_sdr_launch(uint8_t* d_px, size_t step, int channels, int w, int h, int transfer, int primaries, cudaStream_t st);
+
 int compact_launch(const uint8_t* src, size_t stride, const uint32_t* len, uint32_t cap, int n, uint8_t* dst,
                    unsigned long long* off /* n + 1 */, cudaStream_t st);
 struct SegCopy {

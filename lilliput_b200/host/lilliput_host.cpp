@@ -64,6 +64,11 @@ Error Framebuffer::resizeMat(int w, int h, PixelType t) {
 
 // ref opencv.go:271-279: dims are re-read from the mat afterwards (SURVEY
 // Appendix C quirk 7 depends on this refresh).
+void Framebuffer::TonemapToSDR(int transfer, int primaries) {  // ref opencv.go:791-810
+    if (!mat || Width() <= 0 || Height() <= 0) return;
+    lp_mat_tonemap_to_sdr(mat, transfer, primaries);
+}
+
 void Framebuffer::OrientationTransform(int orientation) {
     if (!mat) return;
     opencv_mat_orientation_transform((CVImageOrientation)orientation, mat);
@@ -787,8 +792,8 @@ Error ImageOps::skipToEnd(Decoder* d) {  // ref ops.go:336-344
 }
 
 // ref ops.go:352-444 (+ the colour set-up of initializeTransform, ops.go:483-545).  Differences from the Go are
-// only the ones the scope table excludes: no HDR tone-map and no ICC synthesised from cICP (SURVEY 2 #6, 8f-3:
-// color_info.cpp stays the reference's).  What IS mirrored of the cICP policy: an SDR cICP chunk of a PNG source
+// only the ones the scope table excludes: no ICC synthesised from cICP (color_info.cpp's lcms profiles
+// stay the reference's).  HDR (PQ / HLG) sources ARE tone-mapped after every decode, as ops.go:154-165 does.  What IS mirrored of the cICP policy: an SDR cICP chunk of a PNG source
 // is re-attached to a PNG output (ops.go:306-332); an HDR (PQ / HLG) tag is never re-emitted (ops.go:513-517).
 Error ImageOps::Transform(Decoder* d, const ImageOptions& opt, uint8_t* dst, size_t dst_cap,
                           size_t* out_len) {
@@ -801,10 +806,12 @@ Error ImageOps::Transform(Decoder* d, const ImageOptions& opt, uint8_t* dst, siz
     ImageHeader h;
     Error e = d->Header(&h);
     if (e) return e;
-    std::unique_ptr<::lilliput::CICP> outputCICP;  // ref ops.go:511-517
+    std::unique_ptr<::lilliput::CICP> outputCICP, tonemapCICP;  // ref ops.go:511-517
     {
+        // HDR sources are tone-mapped unconditionally, right after every decode (ops.go:154-165); an SDR cICP is
+        // signalling only and travels to a PNG output untouched
         ::lilliput::CICP c;
-        if (d->CICP(&c) && !c.IsHDR()) outputCICP.reset(new ::lilliput::CICP(c));
+        if (d->CICP(&c)) (c.IsHDR() ? tonemapCICP : outputCICP).reset(new ::lilliput::CICP(c));
     }
     auto applyOutputCICP = [&](size_t n) -> size_t {  // ref ops.go:310-332
         if (!outputCICP || n == 0) return n;
@@ -834,6 +841,7 @@ Error ImageOps::Transform(Decoder* d, const ImageOptions& opt, uint8_t* dst, siz
             if (e != LP_ERR_EOF) return e;
             emptyFrame = true;
         }
+        if (!emptyFrame && tonemapCICP) active()->TonemapToSDR(tonemapCICP->Transfer, tonemapCICP->Primaries);
         duration += active()->duration_ns;
         if (opt.MaxEncodeDuration_ns != 0 && duration > opt.MaxEncodeDuration_ns) {
             e = skipToEnd(d);
@@ -1013,6 +1021,18 @@ static int lp_orient_host_impl(const uint8_t* src, int w, int h, int type, int o
     return LP_OK;
 }
 
+static int lp_tonemap_host_impl(uint8_t* pixels, int w, int h, int type, int transfer, int primaries) {
+    if (!pixels || w <= 0 || h <= 0) return LP_ERR_BAD_ARGUMENT;
+    int side = std::max(w, h);
+    Framebuffer a(side, side);
+    Error e = wrapPixels(a, pixels, w, h, type);
+    if (e) return e;
+    a.TonemapToSDR(transfer, primaries);
+    if (lp_mat_sync_host(a.mat)) return LP_ERR_CUDA;
+    memcpy(pixels, opencv_mat_get_data(a.mat), (size_t)w * h * opencv_type_channels(type));
+    return LP_OK;
+}
+
 static int lp_gif_get_info_impl(const uint8_t* in, size_t in_len, lp_gif_info* info) {
     if (!in || !info) return LP_ERR_BAD_ARGUMENT;
     std::unique_ptr<Decoder> d;
@@ -1156,6 +1176,9 @@ extern "C" int lp_resize_host(const uint8_t* src, int sw, int sh, int type, int 
 extern "C" int lp_encode_host(const char* ext, const uint8_t* pixels, int w, int h, int type,
                               const int* opt, size_t opt_len, uint8_t* dst, size_t dst_cap,
                               size_t* out_len) { LP_GUARDED(lp_encode_host_impl(ext, pixels, w, h, type, opt, opt_len, dst, dst_cap, out_len)) }
+extern "C" int lp_tonemap_host(uint8_t* pixels, int w, int h, int type, int transfer, int primaries) {
+    LP_GUARDED(lp_tonemap_host_impl(pixels, w, h, type, transfer, primaries))
+}
 extern "C" int lp_orient_host(const uint8_t* src, int w, int h, int type, int orientation,
                               uint8_t* dst, int* ow, int* oh) { LP_GUARDED(lp_orient_host_impl(src, w, h, type, orientation, dst, ow, oh)) }
 extern "C" int lp_detect_apng(const uint8_t* in, size_t in_len) { return in && detectAPNG(in, in_len) ? 1 : 0; }

@@ -72,6 +72,7 @@ class Framebuffer {
     Error Create4Channel(int w, int h);                        // ref opencv.go:240-246
     Error resizeMat(int w, int h, PixelType t);                // ref opencv.go:250-267
     void OrientationTransform(int orientation);                // ref opencv.go:271-279
+    void TonemapToSDR(int transfer, int primaries);            // ref opencv.go:791-810
     Error ResizeTo(int w, int h, Framebuffer* dst);            // ref opencv.go:294-309
     Error ClearToTransparent(int x, int y, int w, int h);      // ref opencv.go:312-319
     Error Fit(int w, int h, Framebuffer* dst);                 // ref opencv.go:326-374

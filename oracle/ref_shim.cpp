@@ -22,6 +22,14 @@
 extern "C" int lp_mat_sync_host(opencv_mat) { return 0; }
 extern "C" void lp_mat_mark_host_dirty(opencv_mat) {}
 extern "C" const char* lp_backend_name(void) { return "reference"; }
+// Framebuffer.TonemapToSDR over the reference's own tone-mapper (color_info.cpp, compiled from /root/reference)
+extern "C" void tonemap_rgb_8u_inplace(uint8_t* pixels, int width, int height, int channels, uint8_t transfer, uint8_t primaries);
+extern "C" int lp_mat_tonemap_to_sdr(opencv_mat mat, int transfer, int primaries) {
+    cv::Mat* m = static_cast<cv::Mat*>(mat);
+    if (!m || m->empty() || m->depth() != CV_8U || !m->isContinuous()) return 0;
+    tonemap_rgb_8u_inplace(m->data, m->cols, m->rows, m->channels(), (uint8_t)transfer, (uint8_t)primaries);
+    return 0;
+}
 
 // CPU baseline: `threads` workers, each with its own ImageOps (thread_local in
 // lp_transform) and cv::setNumThreads(1), run Transform over the

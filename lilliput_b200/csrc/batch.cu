@@ -70,7 +70,13 @@ struct lp_batch {
     uint8_t* h_out = nullptr;       // pinned + device-mapped: the compaction kernel writes the encoded bytes straight into it
     uint32_t* h_out_len = nullptr;  // pinned
     unsigned long long* h_off = nullptr;  // pinned + device-mapped: packed offsets, (cnt + 1) per chunk at [i0 + chunk ordinal]
-    struct ChunkLayout { uint32_t blocks = 0, plane_bytes = 0, total_blocks = 0; int ordinal = 0; };
+    struct ChunkLayout {
+        uint32_t blocks = 0, plane_bytes = 0, total_blocks = 0;
+        int ordinal = 0;
+        std::vector<uint2> rst_work;  // (image in chunk, restart interval) of the chunk's DRI images
+        uint2* d_rst_work = nullptr;  // stream-ordered allocation, freed after the chunk's launches
+    };
+    size_t state_cap = 0;  // entries of d_states / d_nslots
     std::map<int, ChunkLayout> chunk_layout;  // keyed by the chunk's first image
     JpegDecodeItem* h_items_back = nullptr;
     int n = 0;
@@ -84,6 +90,8 @@ struct lp_batch {
 
 static void batch_free(lp_batch* b) {
     if (!b) return;
+    for (auto& kv : b->chunk_layout)
+        if (kv.second.d_rst_work) cudaFree(kv.second.d_rst_work);
     if (b->owns_mem) {
     cudaFree(b->d_scan); cudaFree(b->d_items); cudaFree(b->d_tables); cudaFree(b->d_coef);
     cudaFree(b->d_planes); cudaFree(b->d_frames); cudaFree(b->d_resized); cudaFree(b->d_enc_scratch);
@@ -186,8 +194,9 @@ lp_batch* lp::batch_create_in(const lp_batch_config* cfg, uint8_t* dev_arena, si
     BALLOC(b->d_resized, N * b->resized_bytes + 256);
     BALLOC(b->d_enc_scratch, jpeg_encode_scratch_bytes(b->out_w, b->out_h, 3, b->chunk, cfg->out_cap));
     BALLOC(b->d_clean, cfg->max_in_bytes + 64 * N + 4096);
-    BALLOC(b->d_states, (cfg->max_in_bytes / 128 + 2 * N + 16) * 2 * 8);
-    BALLOC(b->d_nslots, (cfg->max_in_bytes / 128 + 2 * N + 16) * 2 * 4);
+    b->state_cap = (cfg->max_in_bytes / 128 + 2 * N + 16) * 2;
+    BALLOC(b->d_states, b->state_cap * 8);
+    BALLOC(b->d_nslots, b->state_cap * 4);
     BALLOC(b->d_dcdiff, (size_t)b->chunk * max_blocks * sizeof(int16_t));
     BALLOC(b->d_out, N * cfg->out_cap);
     BALLOC(b->d_out_len, N * sizeof(uint32_t));
@@ -264,6 +273,8 @@ static void batch_begin(lp_batch* b, int n) {
     b->tables_uploaded = 0;
     b->dev_off = b->clean_off = b->state_off = 0;
     b->parallel_huffman = true;
+    for (auto& kv : b->chunk_layout)
+        if (kv.second.d_rst_work) cudaFreeAsync(kv.second.d_rst_work, b->st);
     b->chunk_layout.clear();
 }
 
@@ -372,8 +383,22 @@ static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t
             continue;
         }
         it.table_set = (uint32_t)ts;
-        if (it.restart_interval) b->parallel_huffman = false;  // RSTn streams take the serial kernel
         const int slot = k - i0;  // position inside its chunk: the per-chunk scratch is indexed from the chunk's first image
+        size_t state_need = 2 * huff_nsub(it.scan_len);
+        if (it.restart_interval) {
+            // RSTn streams: one thread per restart interval (jpeg_rst_*): the marker offsets live where the
+            // self-synchronising decoder keeps its slot counts, clean_len carries the number of intervals
+            const uint32_t mcus = (uint32_t)it.mcus_x * it.mcus_y;
+            const uint32_t nint = (mcus + (uint32_t)it.restart_interval - 1) / (uint32_t)it.restart_interval;
+            it.clean_len = nint;
+            state_need = std::max(state_need, (size_t)nint + 2);
+            if (b->state_off + state_need > b->state_cap) {  // (a restart interval of a few MCUs over a huge batch)
+                b->parse_status[k] = LP_ERR_UNSUPPORTED;
+                it.status = -1;
+                continue;
+            }
+            for (uint32_t q = 0; q < nint; q++) b->chunk_layout[i0].rst_work.push_back(make_uint2((unsigned)slot, q));
+        }
         it.scan_off = b->file_dev_off[k] + hdr[k - i0].scan_offset;
         it.coef_off = (uint64_t)slot * lay.blocks * 64;
         it.plane_off = (uint64_t)slot * lay.plane_bytes;
@@ -382,7 +407,7 @@ static int batch_parse_chunk(lp_batch* b, const uint8_t* const* in, const size_t
         it.clean_off = b->clean_off;
         it.state_off = b->state_off;
         b->clean_off += huff_clean_bytes(it.scan_len);
-        b->state_off += 2 * huff_nsub(it.scan_len);
+        b->state_off += state_need;
     }
     return LP_OK;
 }
@@ -424,9 +449,16 @@ static int batch_launch_chunk(lp_batch* b, int i0, int cnt, cudaStream_t st, cud
         LP_CUDA_OK(cudaMemsetAsync(b->d_out_len + i0, 0, (size_t)cnt * sizeof(uint32_t), st));
         return LP_OK;
     }
-    const lp_batch::ChunkLayout lay = b->chunk_layout.count(i0) ? b->chunk_layout[i0] : lp_batch::ChunkLayout();
+    lp_batch::ChunkLayout none;
+    lp_batch::ChunkLayout& lay = b->chunk_layout.count(i0) ? b->chunk_layout[i0] : none;
     if (ev) LP_CUDA_OK(cudaEventRecord(ev[0], st));
     JpegDecodeBatch d;
+    if (!lay.rst_work.empty()) {
+        if (!lay.d_rst_work) LP_CUDA_OK(cudaMallocAsync(&lay.d_rst_work, lay.rst_work.size() * sizeof(uint2), st));
+        LP_CUDA_OK(cudaMemcpyAsync(lay.d_rst_work, lay.rst_work.data(), lay.rst_work.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+        d.rst_work = lay.d_rst_work;
+        d.n_rst_work = (int)lay.rst_work.size();
+    }
     d.items = b->d_items + i0;
     d.tables = b->d_tables;
     d.scan = b->d_scan;
@@ -652,7 +684,7 @@ extern "C" void lp_batch_sync_rounds(const lp_batch* b, double* mean, int* max) 
     double sum = 0;
     int mx = 0, cnt = 0;
     for (int i = 0; i < b->n; i++) {
-        if (b->parse_status[i]) continue;
+        if (b->parse_status[i] || b->items[i].restart_interval) continue;
         const int r = (int)b->h_items_back[i].pad_;
         sum += r;
         mx = std::max(mx, r);

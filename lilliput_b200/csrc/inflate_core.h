@@ -38,7 +38,7 @@
 namespace lpinf {
 
 #ifndef LP_INF_SUB
-#define LP_INF_SUB 512
+#define LP_INF_SUB 320
 #endif
 #ifndef LP_INF_WARM
 #define LP_INF_WARM 64
@@ -46,7 +46,10 @@ namespace lpinf {
 constexpr uint32_t kSubBits = LP_INF_SUB;      // bits per lane and window
 constexpr uint32_t kWinBits = 32 * kSubBits;
 constexpr uint32_t kInWords = kWinBits / 32 + 8;  // window + the bits a symbol / a refill may read past it
-constexpr uint32_t kRing = 8192, kRingMask = kRing - 1;
+#ifndef LP_INF_RING
+#define LP_INF_RING 4096
+#endif
+constexpr uint32_t kRing = LP_INF_RING, kRingMask = kRing - 1;
 constexpr uint32_t kCapT = kRing / 2;          // output bytes per window
 constexpr uint32_t kMaxMatches = kCapT / 3 + 8;  // a match is at least 3 bytes
 constexpr int kLitBits = 10, kDistBits = 8;

@@ -208,6 +208,138 @@ __global__ void jpeg_huff_decode_kernel(JpegDecodeItem* items, const JpegHuffSet
     it.status = status;
 }
 
+// ------------------------------------------------------------------ restart-interval-parallel decode
+// A scan with restart markers (DRI) is a sequence of independently decodable intervals: every RSTn marker is
+// byte aligned, the DC predictors restart at 0 behind it (T.81 E.1.4, F.2.2.x; libjpeg-turbo jdhuff.c
+// process_restart).  So: one pass finds the markers of every image (jpeg_rst_scan_kernel), then ONE THREAD PER
+// INTERVAL decodes its MCUs (jpeg_rst_decode_kernel) -- with DRI = one MCU row a 1080p batch of 4096 images is
+// 278 528 independent streams.  Coefficients go to the same scan-order layout the self-synchronising decoder of
+// non-DRI streams writes ([roi MCU][block in MCU], DC values final), so both kinds share one IDCT launch.
+
+// positions (byte offsets behind the marker) of the RSTn markers of one image, in order; rst_off[0] = 0
+__global__ void __launch_bounds__(256) jpeg_rst_scan_kernel(JpegDecodeItem* items, const uint8_t* scan, uint32_t* rst_all) {
+    __shared__ uint32_t warp_sums[8];
+    __shared__ uint32_t s_carry;
+    JpegDecodeItem& it = items[blockIdx.x];
+    if (it.status != 0 || it.restart_interval == 0) return;
+    const uint8_t* s = scan + it.scan_off;
+    const uint32_t len = it.scan_len;
+    uint32_t* out = rst_all + it.state_off;  // (state_off doubles as the interval table offset of DRI images)
+    const uint32_t cap = it.clean_len;       // intervals expected (set by the host); out has cap + 1 slots
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        s_carry = 1;
+        out[0] = 0;
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < len; base += 256 * 16) {
+        // 16 consecutive bytes per thread; marker = FF followed by D0..D7
+        const uint32_t b0 = base + (uint32_t)tid * 16;
+        uint32_t found = 0;
+        for (uint32_t k = 0; k < 16; k++) {
+            const uint32_t i = b0 + k;
+            if (i + 1 < len && s[i] == 0xFF && (s[i + 1] & 0xF8) == 0xD0) found |= 1u << k;
+        }
+        const uint32_t cnt = __popc(found);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        uint32_t before = s_carry;
+        for (int w = 0; w < wid; w++) before += warp_sums[w];
+        uint32_t at = before + inc - cnt;
+        for (uint32_t k = 0; k < 16; k++)
+            if (found & (1u << k)) {
+                if (at <= cap) out[at] = b0 + k + 2;
+                at++;
+            }
+        __syncthreads();
+        if (tid == 255) s_carry = before + inc;
+        __syncthreads();
+    }
+    if (tid == 0) it.pad_ = s_carry;  // intervals found (markers + 1)
+}
+
+__global__ void __launch_bounds__(128)
+    jpeg_rst_decode_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* scan, const uint32_t* rst_all,
+                           const uint2* work /* (image, interval) */, int nwork, int16_t* coef) {
+    __shared__ uint8_t zz[64];
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) zz[k] = c_zigzag[k];
+    __syncthreads();
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwork) return;
+    JpegDecodeItem& it = items[work[w].x];
+    if (it.status != 0) return;
+    const uint32_t k = work[w].y, nint = it.clean_len;
+    if (it.pad_ != nint) {  // fewer or more markers than intervals: damaged stream (the per-image path resynchronises as libjpeg does)
+        if (k == 0) it.status = -3;
+        return;
+    }
+    const uint32_t* off = rst_all + it.state_off;
+    const JpegHuffSet* hs = tables + it.table_set;
+    const uint8_t* base = scan + it.scan_off;
+    const uint32_t begin = off[k], end = k + 1 < nint ? off[k + 1] - 2 : it.scan_len;
+    if (k > 0 && (base[begin - 1] & 7u) != ((k - 1) & 7u)) {  // RSTn must count modulo 8
+        it.status = -3;
+        return;
+    }
+    BitReader b{base + begin, base + end, 0, 0, false};
+    int nb = 0;
+    for (int c = 0; c < it.ncomp; c++) nb += it.h[c] * it.v[c];
+    const uint32_t total_mcus = (uint32_t)it.mcus_x * it.mcus_y;
+    uint32_t mcu = k * (uint32_t)it.restart_interval;
+    const uint32_t mcu_end = min(total_mcus, mcu + (uint32_t)it.restart_interval);
+    int pred[3] = {0, 0, 0};
+    int status = 0;
+    int16_t* coef_base = coef + it.coef_off;
+    for (; mcu < mcu_end && !status; mcu++) {
+        const int mx = (int)(mcu % (uint32_t)it.mcus_x), my = (int)(mcu / (uint32_t)it.mcus_x);
+        const int rx = mx - it.roi_mx0, ry = my - it.roi_my0;
+        const bool inside = (unsigned)rx < (unsigned)it.roi_mcx && (unsigned)ry < (unsigned)it.roi_mcy;
+        int16_t* blk = coef_base + ((size_t)ry * it.roi_mcx + rx) * ((size_t)nb * 64);
+        for (int c = 0; c < it.ncomp && !status; c++) {
+            const int td = it.td[c], ta = 4 + it.ta[c];
+            for (int j = 0; j < it.h[c] * it.v[c]; j++, blk += 64) {
+                int s = huff_symbol(b, hs, td);
+                if (s < 0 || s > 15) { status = -3; break; }
+                if (s) pred[c] += receive_extend(b, s);
+                if (inside) blk[0] = (int16_t)pred[c];
+                for (int q = 1; q < 64;) {
+                    const int rs = huff_symbol(b, hs, ta);
+                    if (rs < 0) { status = -3; break; }
+                    const int r = rs >> 4, sz = rs & 15;
+                    if (sz == 0) {
+                        if (r != 15) break;
+                        q += 16;
+                        continue;
+                    }
+                    q += r;
+                    if (q > 63) { status = -3; break; }
+                    const int val = receive_extend(b, sz);
+                    if (inside) blk[zz[q]] = (int16_t)val;
+                    q++;
+                }
+                if (status) break;
+            }
+        }
+    }
+    if (status) it.status = status;
+}
+
+int jpeg_rst_launch(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* scan, uint32_t* rst_all, const uint2* d_work,
+                    int nwork, int n_images, int16_t* coef, cudaStream_t st) {
+    if (nwork <= 0) return LP_OK;
+    jpeg_rst_scan_kernel<<<n_images, 256, 0, st>>>(items, scan, rst_all);
+    jpeg_rst_decode_kernel<<<ceil_div(nwork, 128), 128, 0, st>>>(items, tables, scan, rst_all, d_work, nwork, coef);
+    g_launches += 2;
+    LP_CUDA_OK(cudaGetLastError());
+    return LP_OK;
+}
+
 // ------------------------------------------------------------------ multi-scan files (serial)
 // Progressive JPEG (T.81 Annex G; libjpeg-turbo's jdphuff.c is what the reference runs) and
 // sequential files with one scan per component.  Every scan refines the same coefficient array,
@@ -682,7 +814,9 @@ int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev
         LP_CUDA_OK(cudaGetLastError());
     } else if (b.use_parallel_huffman) {
         JpegHuffParallelArgs a{b.items, b.tables, b.scan, b.clean, b.states, b.nslots, b.coef, b.dcdiff, b.n};
-        int rc = jpeg_huff_parallel_launch(a, st);
+        int rc = jpeg_huff_parallel_launch(a, st);  // skips the images that carry restart markers
+        if (rc) return rc;
+        rc = jpeg_rst_launch(b.items, b.tables, b.scan, b.nslots, b.rst_work, b.n_rst_work, b.n, b.coef, st);
         if (rc) return rc;
     } else {
         const int threads = 32;

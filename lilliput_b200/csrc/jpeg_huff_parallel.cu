@@ -31,7 +31,10 @@ constexpr uint32_t kMinSubBits = 1024;  // shortest subsequence (bits); scratch 
 // sizing them so that one pass is exactly kSubPerThread full rounds of the CTA cuts that to ~2
 // (measured: 10.9 rounds at 1024 bits, 1.9 at one subsequence per thread).
 constexpr uint32_t kSubPerThread = 1;
-constexpr int kHuffThreads = 512;
+#ifndef LP_HUFF_THREADS
+#define LP_HUFF_THREADS 512
+#endif
+constexpr int kHuffThreads = LP_HUFF_THREADS;
 
 __constant__ uint8_t c_zigzag_p[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
                                        12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(kHuffThreads)
     const uint32_t len = it.scan_len;
     uint8_t* dst = clean + it.clean_off;
     const int tid = threadIdx.x, lane = tid & 31;
+    if (it.restart_interval != 0) return;  // restart-interval-parallel path (jpeg_decode.cu): clean_len holds its interval count
     if (it.status != 0) {
         if (tid == 0) it.clean_len = 0;
         return;
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     __shared__ int s_status;
     JpegDecodeItem& it = items[blockIdx.x];
     const int tid = threadIdx.x;
-    if (it.status != 0) return;
+    if (it.status != 0 || it.restart_interval != 0) return;  // (DRI images: one thread per restart interval instead)
     // ---- build the per-CTA tables
     {
         const JpegHuffSet* g = tables + it.table_set;

@@ -143,6 +143,11 @@ struct JpegDecodeBatch {
     // multi-scan files (n == 1): every scan decoded in order by one thread; `scan` holds the whole file
     const JpegScanDesc* scans = nullptr;
     int nscans = 0;
+    // images with restart markers inside a parallel-Huffman launch: (image, interval) work list (device), one
+    // thread per restart interval; their marker offsets live in `nslots` at the image's state_off, the number of
+    // intervals the host expects in clean_len
+    const uint2* rst_work = nullptr;
+    int n_rst_work = 0;
 };
 // Scratch sizing for the parallel Huffman path, per image with `scan_len` entropy-coded bytes.
 inline size_t huff_clean_bytes(size_t scan_len) { return ((scan_len + 48 + 15) / 16) * 16; }

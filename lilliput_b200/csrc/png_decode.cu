@@ -20,7 +20,7 @@
 
 namespace lp {
 
-constexpr int kPngWarps = 2;  // warps (= images) per CTA: 2 x ~25 KB of shared memory, 4 CTAs = 8 images per SM
+constexpr int kPngWarps = 2;  // warps (= images) per CTA: 2 x ~17 KB of shared memory, 6 CTAs = 12 images per SM
 
 // One warp per image; the decoder itself is inflate_core.h (speculative per-lane subsequence decoding,
 // shared-memory output ring, 16-byte flushes).  Dynamic shared memory: one WarpShared per warp.

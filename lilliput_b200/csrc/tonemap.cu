@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) tonemap_kernel(uint8_t* px, size_t step, 
 #pragma unroll
         for (int i = 0; i < 3; i++) lin[i] = tm_eotf(s.transfer, p[i]);
     }
-    if (PASS == 1) {
+    if constexpr (PASS == 1) {
         float mn = in ? fminf(fminf(lin[0], lin[1]), lin[2]) : FLT_MAX, mx = in ? fmaxf(fmaxf(lin[0], lin[1]), lin[2]) : -FLT_MAX;
         mn = warp_min(mn);
         mx = warp_max(mx);
@@ -114,11 +114,11 @@ __global__ void __launch_bounds__(256) tonemap_kernel(uint8_t* px, size_t step, 
             atomic_max_float(&red->mx, mx);
         }
         return;
-    }
+    } else {
     float im[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) im[i] = lin[i] * s.a1 + s.b1;
-    if (PASS == 2) {
+    if constexpr (PASS == 2) {
         const float gray = im[0] * 0.299f + im[1] * 0.587f + im[2] * 0.114f;
         const float lg = logf(fmaxf(gray, 1e-4f));
         const float lmn = warp_min(in ? lg : FLT_MAX), lmx = warp_max(in ? lg : -FLT_MAX);
@@ -134,10 +134,10 @@ __global__ void __launch_bounds__(256) tonemap_kernel(uint8_t* px, size_t step, 
             atomicAdd(&red->sch[2], s2);
         }
         return;
-    }
+    } else {
     float out[3] = {0, 0, 0};
     if (in) tm_reinhard(s, im, out);
-    if (PASS == 3) {
+    if constexpr (PASS == 3) {
         float mn = in ? fminf(fminf(out[0], out[1]), out[2]) : FLT_MAX, mx = in ? fmaxf(fmaxf(out[0], out[1]), out[2]) : -FLT_MAX;
         mn = warp_min(mn);
         mx = warp_max(mx);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) tonemap_kernel(uint8_t* px, size_t step, 
             atomic_max_float(&red->mx, mx);
         }
         return;
-    }
+    } else {
     if (!in) return;
     float t[3];
 #pragma unroll
@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(256) tonemap_kernel(uint8_t* px, size_t step, 
         p[i] = (uint8_t)min(max(v, 0), 255);
     }
     // alpha, when present, is untouched (ref color_info.cpp:262-267)
+    }
+    }
+    }
 }
 
 static void normalise_coeffs(float mn, float mx, float* a, float* b) {  // cv::TonemapImpl::process: (src - min) / (max - min)

@@ -166,7 +166,7 @@ static void parse_item(lp_xbatch* X, int i) {
         if (X->sink != S_JPEG) return;  // JPEG -> WebP carries the ICC profile and is not a measured path: per image
         JpegHeader h;
         if (jpeg_parse_header(d, n, &h) != LP_OK || !h.supported || h.multiscan) return;
-        if (h.ncomp != 3 || h.restart_interval != 0) return;
+        if (h.ncomp != 3) return;
         if (h.orientation >= 2 && h.orientation <= 8) return;
         if (h.width > max_side || h.height > max_side) return;
         it.w = h.width;

@@ -572,6 +572,11 @@ int gif_decode_batch(GifAnimPlan* const* plans, const uint8_t* const* files, con
     LP_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nf * sizeof(GifFrameJob), cudaMemcpyHostToDevice, st));
     LP_CUDA_OK(cudaMemcpyAsync(d_anims, anims.data(), (size_t)n * sizeof(GifAnimJob), cudaMemcpyHostToDevice, st));
     gif_deblock_kernel<<<ceil_div(nf, kGifDeblockWarps), kGifDeblockWarps * 32, 0, st>>>(d_jobs, d_scratch, nf);
+    static bool carveout_set = false;
+    if (!carveout_set) {  // 24 KB of dictionary per frame: let as many frames as possible share an SM
+        cudaFuncSetAttribute(gif_lzw_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
     gif_lzw_batch_kernel<<<nf, 32, 0, st>>>(d_jobs, d_scratch);
     dim3 grid(ceil_div(cw, 128), chh, n);
     gif_compose_batch_kernel<<<grid, 128, 0, st>>>(d_anims, d_jobs, d_scratch, cw, chh, d_canvases, canvas_stride);

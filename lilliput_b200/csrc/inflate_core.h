@@ -371,6 +371,7 @@ LP_INF_FN bool decode_span(WarpShared& ws, uint32_t start, uint32_t end, uint32_
                            Match* mlist, Span& r, uint32_t nominal, int lane, uint32_t old_cnt, uint32_t old_nm,
                            uint32_t* mrec = nullptr, uint32_t obase = 0) {
     uint32_t pos = start, cnt = 0, nm = 0, flag = kFlagNone;
+    uint32_t cw = 0xFFFFFFF0u, w0 = 0, w1 = 0, w2 = 0;  // window words in registers (cw = index of w0)
     uint32_t next_ck = nominal + kCkBits;
     int j = 0;
     while (pos < end) {
@@ -402,8 +403,22 @@ LP_INF_FN bool decode_span(WarpShared& ws, uint32_t start, uint32_t end, uint32_
                 ws.ck_cnt[lane][j] = cnt;
             }
         }
+        // the three window words the symbol can touch stay in registers; a symbol is 1..48 bits, so they slide by at
+        // most two words (shared-memory requests, not instructions, are what limits this kernel when many streams
+        // share an SM: ~0.5 loads per symbol here instead of 3)
         const uint32_t wi = pos >> 5, sh = pos & 31u;
-        const uint32_t w0 = ws.inbuf[wi], w1 = ws.inbuf[wi + 1], w2 = ws.inbuf[wi + 2];
+        if (wi != cw) {
+            if (wi == cw + 1) {
+                w0 = w1;
+                w1 = w2;
+                w2 = ws.inbuf[wi + 2];
+            } else {
+                w0 = ws.inbuf[wi];
+                w1 = ws.inbuf[wi + 1];
+                w2 = ws.inbuf[wi + 2];
+            }
+            cw = wi;
+        }
         const uint32_t lo = funnel_r(w0, w1, sh), hi = funnel_r(w1, w2, sh);
         uint32_t e = ws.lit[lo & ((1u << kLitBits) - 1u)];
         if (!(e & 15u)) e = long_code(ws, 0, lo);

@@ -381,6 +381,11 @@ int png_decode_launch(const PngDecodeBatch& b, cudaStream_t st) {
     const size_t smem = sizeof(lpinf::WarpShared) * kPngWarps;
     if (!attr_set) {
         LP_CUDA_OK(cudaFuncSetAttribute(png_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // all of the SM's L1 / shared memory as shared memory: the kernel lives in it (12 streams x 16 KB per SM)
+        LP_CUDA_OK(cudaFuncSetAttribute(png_inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, png_inflate_kernel, kPngWarps * 32, smem);
+        if (getenv("LP_DEBUG")) fprintf(stderr, "[lilliput_b200] png_inflate_kernel: %zu B shared memory per CTA, %d CTAs per SM\n", smem, per_sm);
         attr_set = true;
     }
     lpinf::Match* mlists = nullptr;  // per-image match list of the window being written

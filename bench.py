@@ -50,12 +50,61 @@ def parse_args():
                     help="BASELINE.json config: 2 = headline (1080p JPEG -> 256x256 JPEG), 3 = 4K RGBA PNG -> 512x512 "
                          "WebP, 4 = 128-frame 720p GIF -> 256x256 animated WebP, 5 = mixed JPEG/PNG/WebP -> 256x256 JPEG")
     ap.add_argument("--distinct", type=int, default=0, help="configs 3-5: distinct files generated (replicated to the batch)")
+    ap.add_argument("--variant", default="default", choices=["default", "cv2", "optimized", "dri"],
+                    help="config 2 corpus: default = this library's encoder (byte-identical to the reference's); cv2 = "
+                         "OpenCV / libjpeg-turbo written files; optimized = per-image optimised Huffman tables (a DHT "
+                         "per file); dri = restart interval of one MCU row.  Secondary, labelled lines.")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------ corpus
 
-def make_corpus(lib, device, n, seed0):
+def make_corpus_cv2(lib, device, n, seed0, variant):
+    """Same pixel content as make_corpus, files written by OpenCV's libjpeg-turbo build (cv2.imencode) in a thread
+    pool: q90, 4:2:0, standard tables ("cv2"), IMWRITE_JPEG_OPTIMIZE ("optimized") or a restart interval of one MCU
+    row = 120 MCUs ("dri")."""
+    import cv2
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from lilliput_b200.corpus import synth_frames_gpu
+    flags = [cv2.IMWRITE_JPEG_QUALITY, Q_IN]
+    if variant == "optimized":
+        flags += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+    if variant == "dri":
+        flags += [cv2.IMWRITE_JPEG_RST_INTERVAL, SRC_W // 16]
+    dev = torch.device("cuda", device)
+    blobs = []
+
+    def enc(im):
+        ok, b = cv2.imencode(".jpg", im, flags)
+        assert ok
+        return np.asarray(b).reshape(-1)
+    with ThreadPoolExecutor(max_workers=max(2, usable_cpus())) as ex:
+        for g0 in range(0, n, 64):
+            cnt = min(64, n - g0)
+            frames = synth_frames_gpu(dev, cnt, SRC_W, SRC_H, 3, seed0 + g0)
+            blobs += list(ex.map(enc, [frames[i] for i in range(cnt)]))
+    lens = [int(b.size) for b in blobs]
+    total = int(sum(lens))
+    lib.l.lp_host_alloc_pinned.restype = C.c_void_p
+    lib.l.lp_host_alloc_pinned.argtypes = [C.c_size_t]
+    base = lib.l.lp_host_alloc_pinned(total + 64)
+    arena = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(total + 64,))
+    offs, o = [], 0
+    for b in blobs:
+        arena[o:o + b.size] = b
+        offs.append(o)
+        o += b.size
+    return base, arena, offs, lens
+
+
+def make_corpus(lib, device, n, seed0, variant="default"):
+    if variant != "default":
+        return make_corpus_cv2(lib, device, n, seed0, variant)
+    return _make_corpus_default(lib, device, n, seed0)
+
+
+def _make_corpus_default(lib, device, n, seed0):
     """n distinct synthetic 1080p baseline JPEGs (q90, 4:2:0, no restart markers), made on the GPU:
     pixel content from torch (seeded per image), encoded by the library's own encoder, whose
     output is byte-identical to the reference encoder (tests/test_gpu_parity.py).  Returns a pinned
@@ -575,7 +624,7 @@ def main():
         # (a few seconds on a 16-CPU box, under a second on a 96-CPU one), workers warmed before each clock
         sample_n = args.batch
         from lilliput_b200.shard import corpus_seed
-        base, arena, offs, lens = make_corpus(lib, local_rank, sample_n, corpus_seed(1000, 0, sample_n))
+        base, arena, offs, lens = make_corpus(lib, local_rank, sample_n, corpus_seed(1000, 0, sample_n), args.variant)
         per_step = sample_n
         for _ in range(args.warmup):
             cpu_reference_run(base, offs, lens, per_step, threads)
@@ -604,7 +653,7 @@ def main():
     n = args.batch
     t_setup = time.time()
     from lilliput_b200.shard import corpus_seed, max_over_ranks
-    base, arena, offs, lens = make_corpus(lib, local_rank, n, corpus_seed(1000, rank, n))
+    base, arena, offs, lens = make_corpus(lib, local_rank, n, corpus_seed(1000, rank, n), args.variant)
     in_bytes = int(sum(lens))
     out_cap = 65536
     b = abi.Batch(lib, local_rank, n, SRC_W, SRC_H, DST, DST, Q_OUT, max_in_bytes=in_bytes + (1 << 20),
@@ -698,7 +747,12 @@ def main():
             "ms_per_step": round(1000 * dev_s / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "config2: batch 4096 synthetic 1920x1080 baseline JPEG q90 (4:2:0, no DRI) -> "
-                                   "Fit 256x256 JPEG q85, per GPU",
+                                   "Fit 256x256 JPEG q85, per GPU" + ("" if args.variant == "default" else
+                                                                      f" [SECONDARY corpus variant: {args.variant}]"),
+                       "corpus": {"default": "torch content, this library's encoder (byte-identical to the reference's), standard tables",
+                                  "cv2": "torch content, files written by cv2 (libjpeg-turbo), standard tables",
+                                  "optimized": "torch content, cv2 with per-image optimised Huffman tables (one DHT set per file)",
+                                  "dri": "torch content, cv2 with a restart interval of one MCU row (120 MCUs)"}[args.variant],
                        "images_per_gpu_per_step": n, "sharding": "by image index, no collective",
                        "l2": "inputs (%.2f GB compressed, 25 GB decoded per step) exceed the 126 MB L2; no flush needed"
                              % (in_bytes / 1e9),

@@ -203,7 +203,7 @@ const uint8_t* lp_batch_resized_dev(const lp_batch* b, size_t* image_stride);
 typedef struct lp_xbatch lp_xbatch;
 typedef struct lp_xbatch_config {
     int device;          /* CUDA ordinal */
-    size_t arena_bytes;  /* device working memory; 0 = 60 % of what is free at creation */
+    size_t arena_bytes;  /* device working memory; 0 = 72 % of what is free at creation */
     int host_threads;    /* header parsing / per-image fallback workers; 0 = auto */
     int max_size;        /* ImageOps maxSize for every item (lp_transform's max_size); 0 = 8192 */
 } lp_xbatch_config;

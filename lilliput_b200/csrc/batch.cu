@@ -10,6 +10,7 @@
 #include <map>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -61,7 +62,7 @@ struct lp_batch {
     // host
     std::vector<JpegDecodeItem> items;
     std::vector<JpegHuffSet> tables;
-    std::map<std::string, int> table_index;
+    std::unordered_map<std::string, int> table_index;  // every distinct Huffman table set of the batch (hashed)
     size_t tables_uploaded = 0;
     std::vector<int> parse_status;
     std::vector<size_t> file_dev_off;
@@ -84,7 +85,7 @@ struct lp_batch {
     std::vector<cudaEvent_t> ev;      // 6 per chunk (stage timing)
     std::vector<cudaEvent_t> ev_h2d;  // per chunk
     std::vector<cudaEvent_t> ev_d2h;  // per chunk
-    static constexpr int kMaxTables = 64;
+    int max_tables = 0;  // = max_images: a batch of per-image optimised tables has one set per file
     bool owns_mem = true;  // false: device / pinned buffers were carved from a caller's arenas (xbatch.cu)
 };
 
@@ -187,7 +188,8 @@ lp_batch* lp::batch_create_in(const lp_batch_config* cfg, uint8_t* dev_arena, si
     if (cudaStreamCreateWithFlags(&b->st_d2h, cudaStreamNonBlocking) != cudaSuccess) return fail();
     BALLOC(b->d_scan, cfg->max_in_bytes + 16 * N + 4096);
     BALLOC(b->d_items, N * sizeof(JpegDecodeItem));
-    BALLOC(b->d_tables, lp_batch::kMaxTables * sizeof(JpegHuffSet));
+    b->max_tables = (int)N;
+    BALLOC(b->d_tables, (size_t)b->max_tables * sizeof(JpegHuffSet));
     BALLOC(b->d_coef, (size_t)b->chunk * max_blocks * 64 * sizeof(int16_t));
     BALLOC(b->d_planes, (size_t)b->chunk * max_blocks * 64);
     BALLOC(b->d_frames, (size_t)b->chunk * b->frame_bytes + 256);
@@ -256,7 +258,7 @@ static int table_set_lookup(lp_batch* b, const JpegHeader& h) {
         }
     auto it = b->table_index.find(key);
     if (it != b->table_index.end()) return it->second;
-    if ((int)b->tables.size() >= lp_batch::kMaxTables) return -1;
+    if ((int)b->tables.size() >= b->max_tables) return -1;
     JpegHuffSet hs;
     jpeg_build_huff_set(h, &hs);
     b->tables.push_back(hs);

@@ -227,6 +227,9 @@ struct PngDecodeBatch {
 };
 // inflate -> defilter -> convert to packed Gray / BGR / BGRA u8.
 int png_decode_launch(const PngDecodeBatch& b, cudaStream_t st);
+// the two halves, for callers that keep every stream's scanlines but only a window of frames (xbatch.cu)
+int png_inflate_launch(const PngDecodeBatch& b, cudaStream_t st);
+int png_unfilter_launch(const PngDecodeBatch& b, int first, int count, cudaStream_t st);
 
 // ---- png_encode.cu ---------------------------------------------------------------------------
 // One packed device frame -> a complete PNG file in host memory (filter + deflate on the device).

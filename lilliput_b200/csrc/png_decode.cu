@@ -374,14 +374,15 @@ void png_item_set_passes(PngDecodeItem* it) {
     it->raw_total = off;
 }
 
-int png_decode_launch(const PngDecodeBatch& b, cudaStream_t st) {
+// inflate only: every stream of the batch in one launch (the long pole -- it wants as many streams in flight as fit)
+int png_inflate_launch(const PngDecodeBatch& b, cudaStream_t st) {
     if (b.n <= 0) return LP_OK;
     const int ctas = ceil_div(b.n, kPngWarps);
     static bool attr_set = false;
     const size_t smem = sizeof(lpinf::WarpShared) * kPngWarps;
     if (!attr_set) {
         LP_CUDA_OK(cudaFuncSetAttribute(png_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // all of the SM's L1 / shared memory as shared memory: the kernel lives in it (12 streams x 16 KB per SM)
+        // all of the SM's L1 / shared memory as shared memory: the kernel lives in it
         LP_CUDA_OK(cudaFuncSetAttribute(png_inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, png_inflate_kernel, kPngWarps * 32, smem);
@@ -394,14 +395,28 @@ int png_decode_launch(const PngDecodeBatch& b, cudaStream_t st) {
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     cudaFreeAsync(mlists, st);
-    png_defilter_kernel<<<ctas, kPngWarps * 32, 0, st>>>(b.items, b.raw, b.frames, b.n);
+    return LP_OK;
+}
+
+// defilter (+ convert) of items [first, first + count): their frame_off point into b.frames, which may be a buffer
+// that is reused from one sub-range to the next (the inflated scanlines of all items stay in b.raw)
+int png_unfilter_launch(const PngDecodeBatch& b, int first, int count, cudaStream_t st) {
+    if (count <= 0) return LP_OK;
+    const int ctas = ceil_div(count, kPngWarps);
+    png_defilter_kernel<<<ctas, kPngWarps * 32, 0, st>>>(b.items + first, b.raw, b.frames, count);
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
-    dim3 grid(ceil_div(b.max_width, 128), b.max_height, b.n);
-    png_convert_kernel<<<grid, 128, 0, st>>>(b.items, b.raw, b.frames);
+    dim3 grid(ceil_div(b.max_width, 128), b.max_height, count);
+    png_convert_kernel<<<grid, 128, 0, st>>>(b.items + first, b.raw, b.frames);
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
     return LP_OK;
+}
+
+int png_decode_launch(const PngDecodeBatch& b, cudaStream_t st) {
+    int rc = png_inflate_launch(b, st);
+    if (rc) return rc;
+    return png_unfilter_launch(b, 0, b.n, st);
 }
 
 }  // namespace lp

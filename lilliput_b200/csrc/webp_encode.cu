@@ -183,6 +183,192 @@ __global__ void vp8_planes_kernel(const uint8_t* frame, size_t step, int channel
     sv[(size_t)cy * (ys / 2) + cx] = (uint8_t)vp8enc::rgb_to_v(r, g, b);
 }
 
+// ---- macroblock analysis, one WARP per frame --------------------------------------------------
+// vp8enc::analyse_and_reconstruct (vp8_enc_core.h) walks the macroblocks on one lane; that chain (4 + 4 mode trials
+// over 384 pixels, 24 forward and 24 inverse 4x4 transforms per macroblock) was the longest stage of the animated
+// WebP path.  The macroblocks stay in raster order (each needs its left and top neighbours' reconstruction) but the
+// work INSIDE one is spread over the warp: prediction errors 8 luma / 4 chroma pixels per lane + a shuffle
+// reduction, one 4x4 block per lane for transform, quantisation and reconstruction.  Same arithmetic, same
+// decisions (ties keep the lower mode number), so the stream is byte-identical to the serial walk's.
+
+struct Vp8WarpBuf {
+    uint8_t yb[vp8::YB_SIZE], ub[vp8::CB_SIZE], vb[vp8::CB_SIZE];
+    int16_t coeffs[25 * 16];
+};
+
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// prediction of pixel (x, y) of a size x size block whose borders are in place around dst (mode as vp8::pred_block)
+__device__ __forceinline__ int vp8_pred_px(const uint8_t* dst, int bps, int size, int mode, int dc, int x, int y) {
+    if (mode == vp8::DC_PRED) return dc;
+    if (mode == vp8::TM_PRED) return vp8::clip8(dst[x - bps] + dst[y * bps - 1] - dst[-1 - bps]);
+    if (mode == vp8::V_PRED) return dst[x - bps];
+    return dst[y * bps - 1];
+}
+__device__ __forceinline__ int vp8_dc_value(const uint8_t* dst, int bps, int size, bool have_top, bool have_left, int lane) {
+    // every lane takes (at most) one border sample pair; vp8::pred_block's three edge cases
+    const int sh = size == 16 ? 4 : 3;
+    int s = 0;
+    if (lane < size) s = (have_top ? dst[lane - bps] : 0) + (have_left ? dst[lane * bps - 1] : 0);
+    s = warp_sum_i(s);
+    if (have_top && have_left) return (s + size) >> (sh + 1);
+    if (have_top || have_left) return (s + (size >> 1)) >> sh;
+    return 0x80;
+}
+
+__device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers& B, Vp8WarpBuf& wb) {
+    using namespace vp8enc;
+    const int lane = threadIdx.x & 31;
+    const int ys = P.mb_w * 16, cs = P.mb_w * 8;
+    vp8::QuantMat qm;
+    qm.y1[0] = kVp8DcTable[P.q];
+    qm.y1[1] = kVp8AcTable[P.q];
+    qm.y2[0] = kVp8DcTable[P.q] * 2;
+    qm.y2[1] = (kVp8AcTable[P.q] * 101581) >> 16;
+    if (qm.y2[1] < 8) qm.y2[1] = 8;
+    qm.uv[0] = kVp8DcTable[P.q > 117 ? 117 : P.q];
+    qm.uv[1] = kVp8AcTable[P.q];
+    uint8_t* yd = wb.yb + BPS + 8;
+    uint8_t* ud = wb.ub + BPS + 8;
+    uint8_t* vd = wb.vb + BPS + 8;
+    int16_t* coeffs = wb.coeffs;
+    for (int mb_y = 0; mb_y < P.mb_h; mb_y++)
+        for (int mb_x = 0; mb_x < P.mb_w; mb_x++) {
+            const uint8_t* sy = B.sy + (size_t)mb_y * 16 * ys + mb_x * 16;
+            const uint8_t* su = B.su + (size_t)mb_y * 8 * cs + mb_x * 8;
+            const uint8_t* sv = B.sv + (size_t)mb_y * 8 * cs + mb_x * 8;
+            uint8_t* py = B.ry + (size_t)mb_y * 16 * ys + mb_x * 16;
+            uint8_t* pu = B.ru + (size_t)mb_y * 8 * cs + mb_x * 8;
+            uint8_t* pv = B.rv + (size_t)mb_y * 8 * cs + mb_x * 8;
+            const bool have_top = mb_y > 0, have_left = mb_x > 0;
+            // prediction borders from the reconstruction, as the decoder will see them (s.12.2)
+            if (lane < 16) yd[lane * BPS - 1] = have_left ? py[lane * ys - 1] : 129;
+            if (lane < 8) {
+                ud[lane * BPS - 1] = have_left ? pu[lane * cs - 1] : 129;
+                vd[lane * BPS - 1] = have_left ? pv[lane * cs - 1] : 129;
+            }
+            if (lane < 17) {
+                const int i = lane - 1;
+                yd[i - BPS] = have_top ? ((i < 0 && mb_x == 0) ? 129 : py[i - ys]) : 127;
+            }
+            if (lane < 9) {
+                const int i = lane - 1;
+                ud[i - BPS] = have_top ? ((i < 0 && mb_x == 0) ? 129 : pu[i - cs]) : 127;
+                vd[i - BPS] = have_top ? ((i < 0 && mb_x == 0) ? 129 : pv[i - cs]) : 127;
+            }
+            __syncwarp();
+            // luma 16x16 mode: least squared prediction error; lane = (row, half row)
+            const int ydc = vp8_dc_value(yd, BPS, 16, have_top, have_left, lane);
+            int ymode = 0;
+            {
+                const int r = lane >> 1, c0 = (lane & 1) * 8;
+                uint32_t best = 0xffffffffu;
+                for (int m = 0; m < 4; m++) {
+                    int e = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int d = (int)sy[r * ys + c0 + k] - vp8_pred_px(yd, BPS, 16, m, ydc, c0 + k, r);
+                        e += d * d;
+                    }
+                    const uint32_t tot = (uint32_t)warp_sum_i(e);
+                    if (tot < best) {
+                        best = tot;
+                        ymode = m;
+                    }
+                }
+            }
+            // chroma mode: both planes together; lane = (plane, row, half row)
+            const int udc = vp8_dc_value(ud, BPS, 8, have_top, have_left, lane);
+            const int vdc = vp8_dc_value(vd, BPS, 8, have_top, have_left, lane);
+            int uvmode = 0;
+            {
+                const int pl = lane >> 4, r = (lane >> 1) & 7, c0 = (lane & 1) * 4;
+                const uint8_t* src = pl ? sv : su;
+                const uint8_t* dd = pl ? vd : ud;
+                const int dc = pl ? vdc : udc;
+                uint32_t best = 0xffffffffu;
+                for (int m = 0; m < 4; m++) {
+                    int e = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int d = (int)src[r * cs + c0 + k] - vp8_pred_px(dd, BPS, 8, m, dc, c0 + k, r);
+                        e += d * d;
+                    }
+                    const uint32_t tot = (uint32_t)warp_sum_i(e);
+                    if (tot < best) {
+                        best = tot;
+                        uvmode = m;
+                    }
+                }
+            }
+            // the chosen predictions into the work buffers (the borders they read are outside the written area)
+            {
+                const int r = lane >> 1, c0 = (lane & 1) * 8;
+                uint8_t pv8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) pv8[k] = (uint8_t)vp8_pred_px(yd, BPS, 16, ymode, ydc, c0 + k, r);
+                const int pl = lane >> 4, cr = (lane >> 1) & 7, cc0 = (lane & 1) * 4;
+                uint8_t* dd = pl ? vd : ud;
+                uint8_t pc4[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) pc4[k] = (uint8_t)vp8_pred_px(dd, BPS, 8, uvmode, pl ? vdc : udc, cc0 + k, cr);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 8; k++) yd[r * BPS + c0 + k] = pv8[k];
+#pragma unroll
+                for (int k = 0; k < 4; k++) dd[cr * BPS + cc0 + k] = pc4[k];
+            }
+            __syncwarp();
+            // residual transforms: one 4x4 block per lane (0..15 Y, 16..19 U, 20..23 V)
+            int16_t* lv = B.levels + ((size_t)mb_y * P.mb_w + mb_x) * 25 * 16;
+            if (lane < 16) {
+                fdct4x4(sy + (lane >> 2) * 4 * ys + (lane & 3) * 4, ys, yd + (lane >> 2) * 4 * BPS + (lane & 3) * 4, BPS, coeffs + lane * 16);
+            } else if (lane < 24) {
+                const int n = (lane - 16) & 3;
+                const bool isv = lane >= 20;
+                fdct4x4((isv ? sv : su) + (n >> 1) * 4 * cs + (n & 1) * 4, cs, (isv ? vd : ud) + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS,
+                        coeffs + lane * 16);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                fwht(coeffs, coeffs + 24 * 16);
+                quantize_block(coeffs + 24 * 16, lv + 24 * 16, qm.y2, 0, 96, 108);
+                vp8::inverse_wht(coeffs + 24 * 16, coeffs);  // plants the dequantised DCs
+            }
+            __syncwarp();
+            if (lane < 16) {
+                quantize_block(coeffs + lane * 16, lv + lane * 16, qm.y1, 1, 96, 110);
+                vp8::inverse_dct_add(coeffs + lane * 16, yd + (lane >> 2) * 4 * BPS + (lane & 3) * 4, BPS);
+            } else if (lane < 24) {
+                const int n = (lane - 16) & 3;
+                quantize_block(coeffs + lane * 16, lv + lane * 16, qm.uv, 0, 110, 115);
+                vp8::inverse_dct_add(coeffs + lane * 16, (lane >= 20 ? vd : ud) + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
+            }
+            __syncwarp();
+            // reconstruction out to the planes: 8 luma pixels and 4 chroma pixels per lane
+            {
+                const int r = lane >> 1, c0 = (lane & 1) * 8;
+#pragma unroll
+                for (int k = 0; k < 8; k++) py[r * ys + c0 + k] = yd[r * BPS + c0 + k];
+                const int pl = lane >> 4, cr = (lane >> 1) & 7, cc0 = (lane & 1) * 4;
+                uint8_t* pc = pl ? pv : pu;
+                const uint8_t* dd = pl ? vd : ud;
+#pragma unroll
+                for (int k = 0; k < 4; k++) pc[cr * cs + cc0 + k] = dd[cr * BPS + cc0 + k];
+            }
+            if (lane == 0) {
+                B.modes[((size_t)mb_y * P.mb_w + mb_x) * 2 + 0] = (uint8_t)ymode;
+                B.modes[((size_t)mb_y * P.mb_w + mb_x) * 2 + 1] = (uint8_t)uvmode;
+            }
+            __syncwarp();
+            __threadfence_block();  // the next macroblock's borders read what other lanes just wrote to global memory
+        }
+}
+
 struct Vp8EncJob {
     vp8enc::Params P;
     vp8enc::Buffers B;
@@ -191,10 +377,11 @@ struct Vp8EncJob {
     size_t* out_len;
 };
 
-__global__ void vp8_encode_kernel(Vp8EncJob j) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(32) vp8_encode_kernel(Vp8EncJob j) {
+    __shared__ Vp8WarpBuf wb;
     if (j.P.filter_level < 0) j.P.filter_level = vp8enc::filter_level_for_q(j.P.q);
-    vp8enc::analyse_and_reconstruct(j.P, j.B);
+    vp8_analyse_warp(j.P, j.B, wb);
+    if (threadIdx.x != 0) return;
     *j.out_len = vp8enc::write_bitstream(j.P, j.B, j.part0, j.part0_cap, j.tokens, j.tokens_cap, j.top_nz, j.out, j.out_cap);
 }
 
@@ -301,8 +488,9 @@ struct Vp8EncBatch {
 
 constexpr int kVp8EncWarps = 4;
 __global__ void __launch_bounds__(kVp8EncWarps * 32) vp8_encode_batch_kernel(Vp8EncBatch b) {
+    __shared__ Vp8WarpBuf wbs[kVp8EncWarps];
     const int f = blockIdx.x * kVp8EncWarps + (threadIdx.x >> 5);
-    if (f >= b.n || (threadIdx.x & 31) != 0) return;
+    if (f >= b.n) return;
     vp8enc::Params P = b.P;
     if (P.filter_level < 0) P.filter_level = vp8enc::filter_level_for_q(P.q);
     uint8_t* base = b.scratch + (size_t)f * b.stride;
@@ -316,7 +504,8 @@ __global__ void __launch_bounds__(kVp8EncWarps * 32) vp8_encode_batch_kernel(Vp8
     B.rv = B.ru + ypl / 4;
     B.levels = reinterpret_cast<int16_t*>(base + b.off_levels);
     B.modes = base + b.off_modes;
-    vp8enc::analyse_and_reconstruct(P, B);
+    vp8_analyse_warp(P, B, wbs[threadIdx.x >> 5]);
+    if ((threadIdx.x & 31) != 0) return;
     const size_t n = vp8enc::write_bitstream(P, B, base + b.off_part0, b.part0_cap, base + b.off_tokens, b.tokens_cap,
                                              base + b.off_topnz, b.out + (size_t)f * b.out_cap, b.out_cap);
     b.out_len[f] = (uint32_t)n;

@@ -404,15 +404,62 @@ static void resize_and_encode(lp_xbatch* X, Lane& L, Bump& bump, const std::vect
     lane_time(L, 2, 3, &L.ms_encode);
 }
 
+// resize of items [k0, k1) of a task (their frames at d_frames + frame_off[k]) into the task's output area
+static bool resize_range(lp_xbatch* X, Lane& L, const std::vector<int>& idx, int k0, int k1, const uint8_t* d_frames,
+                         const std::vector<uint64_t>& frame_off, uint8_t* d_out, const std::vector<uint64_t>& out_off) {
+    for (int k = k0; k < k1;) {
+        const XItem& g = X->items[idx[k]];
+        int e = k + 1;
+        while (e < k1) {
+            const XItem& c = X->items[idx[e]];
+            if (c.w != g.w || c.h != g.h || c.ch != g.ch) break;
+            e++;
+        }
+        const size_t fs = round_up((size_t)g.w * g.h * g.ch, (size_t)256), os = round_up((size_t)g.ow * g.oh * g.ch, (size_t)256);
+        ResizeArgs a{d_frames + frame_off[k], fs, (size_t)g.w * g.ch, g.ch, g.cx, g.cy, g.cw, g.chh, d_out + out_off[k], os,
+                     (size_t)g.ow * g.ch, g.ow, g.oh, e - k, 3};
+        if (resize_launch(a, L.st) != LP_OK) return false;
+        k = e;
+    }
+    return true;
+}
+
+// sinks over the runs of equal geometry of a whole task (resized frames at d_out + out_off[k])
+static void encode_runs(lp_xbatch* X, Lane& L, Bump& bump, const std::vector<int>& idx, const uint8_t* d_out,
+                        const std::vector<uint64_t>& out_off, const std::vector<char>& ok, std::vector<int>* failed) {
+    cudaEventRecord(L.ev[2], L.st);
+    for (const Run& r : runs_of(X, idx)) {
+        const XItem& g = X->items[idx[r.k0]];
+        std::vector<int> sub;
+        bool all = true;
+        for (int k = r.k0; k < r.k1; k++) {
+            all = all && ok[k];
+            sub.push_back(idx[k]);
+        }
+        if (!all) {  // rare: a corrupt stream in the run -- its items take the per-image path, which reports the precise error
+            failed->insert(failed->end(), sub.begin(), sub.end());
+            continue;
+        }
+        sink_encode(X, L, bump, sub, d_out + out_off[r.k0], round_up((size_t)g.ow * g.oh * g.ch, (size_t)256), g.ow, g.oh, g.ch, failed);
+    }
+    cudaEventRecord(L.ev[3], L.st);
+    cudaEventSynchronize(L.ev[3]);
+    lane_time(L, 2, 3, &L.ms_encode);
+}
+
+// PNG task.  Inflate wants every stream in flight at once and needs only the compressed stream and the scanlines
+// (~1.5 x the pixel bytes); the packed frames are needed only between defilter and resize.  So: ONE inflate launch over
+// the whole task, then defilter -> resize over windows of frames that reuse one buffer, then the sinks over the task.
 static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
     const int n = (int)idx.size();
     std::vector<int> failed;
-    const std::vector<Run> runs = runs_of(X, idx);
     Bump bump{L.dev, L.dev_bytes};
     std::vector<PngDecodeItem> items((size_t)n);
     std::vector<SegCopy> segs;
-    std::vector<uint64_t> file_off((size_t)n), frame_off((size_t)n);
-    size_t in_bytes = 0, raw_bytes = 0, frame_bytes = 0;
+    std::vector<uint64_t> file_off((size_t)n), frame_off((size_t)n), out_off((size_t)n);
+    std::vector<int> win_first;  // first item of every frame window
+    size_t in_bytes = 0, raw_bytes = 0, out_bytes = 0, win_bytes = 0, win_max = 0;
+    const size_t kWindow = std::min<size_t>((size_t)12 << 30, L.dev_bytes / 5);  // frames buffer
     int max_w = 0, max_h = 0;
     for (int k = 0; k < n; k++) {
         const PngHeader& ph = *X->items[idx[k]].png;
@@ -457,18 +504,28 @@ static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
         }
         it.raw_off = raw_bytes;
         raw_bytes += round_up((size_t)it.raw_total + 64, (size_t)256);
-        frame_off[k] = frame_bytes;
-        it.frame_off = frame_bytes;
-        frame_bytes += round_up((size_t)xi.w * xi.h * xi.ch, (size_t)256);
+        const size_t fb = round_up((size_t)xi.w * xi.h * xi.ch, (size_t)256);
+        if (k == 0 || win_bytes + fb > kWindow) {  // open a new frame window
+            win_first.push_back(k);
+            win_bytes = 0;
+        }
+        frame_off[k] = win_bytes;
+        it.frame_off = win_bytes;
+        win_bytes += fb;
+        win_max = std::max(win_max, win_bytes);
+        out_off[k] = out_bytes;
+        out_bytes += round_up((size_t)xi.ow * xi.oh * xi.ch, (size_t)256);
         max_w = std::max(max_w, xi.w);
         max_h = std::max(max_h, xi.h);
     }
+    win_first.push_back(n);
     uint8_t* d_in = bump.take<uint8_t>(zg + 4096);
     PngDecodeItem* d_items = bump.take<PngDecodeItem>((size_t)n * sizeof(PngDecodeItem));
     SegCopy* d_segs = bump.take<SegCopy>(segs.size() * sizeof(SegCopy) + 16);
     uint8_t* d_raw = bump.take<uint8_t>(raw_bytes + 256);
-    uint8_t* d_frames = bump.take<uint8_t>(frame_bytes + 256);
-    if (!d_in || !d_items || !d_segs || !d_raw || !d_frames) {
+    uint8_t* d_frames = bump.take<uint8_t>(win_max + 256);
+    uint8_t* d_out = bump.take<uint8_t>(out_bytes + 256);
+    if (!d_in || !d_items || !d_segs || !d_raw || !d_frames || !d_out) {
         for (int i : idx) push_fallback(X, i);
         return;
     }
@@ -485,17 +542,21 @@ static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
         ok = cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(SegCopy), cudaMemcpyHostToDevice, L.st) == cudaSuccess;
     cudaEventRecord(L.ev[0], L.st);
     if (ok && !segs.empty()) ok = seg_copy_launch(d_segs, (int)segs.size(), d_in, L.st) == LP_OK;
-    if (ok) {
-        PngDecodeBatch b;
-        b.items = d_items;
-        b.z = d_in;
-        b.raw = d_raw;
-        b.frames = d_frames;
-        b.n = n;
-        b.max_width = max_w;
-        b.max_height = max_h;
-        ok = png_decode_launch(b, L.st) == LP_OK;
+    PngDecodeBatch b;
+    b.items = d_items;
+    b.z = d_in;
+    b.raw = d_raw;
+    b.frames = d_frames;
+    b.n = n;
+    b.max_width = max_w;
+    b.max_height = max_h;
+    if (ok) ok = png_inflate_launch(b, L.st) == LP_OK;
+    for (size_t wdx = 0; wdx + 1 < win_first.size() && ok; wdx++) {
+        const int k0 = win_first[wdx], k1 = win_first[wdx + 1];
+        ok = png_unfilter_launch(b, k0, k1 - k0, L.st) == LP_OK;
+        if (ok) ok = resize_range(X, L, idx, k0, k1, d_frames, frame_off, d_out, out_off);
     }
+    cudaEventRecord(L.ev[1], L.st);
     if (ok) ok = cudaMemcpyAsync(items.data(), d_items, (size_t)n * sizeof(PngDecodeItem), cudaMemcpyDeviceToHost, L.st) == cudaSuccess;
     if (ok) ok = cudaStreamSynchronize(L.st) == cudaSuccess;
     if (!ok) {
@@ -503,9 +564,10 @@ static void run_png(lp_xbatch* X, Lane& L, const std::vector<int>& idx) {
         for (int i : idx) push_fallback(X, i);
         return;
     }
+    lane_time(L, 0, 1, &L.ms_decode);  // (the resize launches sit between the defilter launches here: counted as decode)
     std::vector<char> good((size_t)n);
     for (int k = 0; k < n; k++) good[k] = items[k].status == 0;
-    resize_and_encode(X, L, bump, idx, runs, d_frames, frame_off, good, &failed);
+    encode_runs(X, L, bump, idx, d_out, out_off, good, &failed);
     for (int i : failed) push_fallback(X, i);
 }
 
@@ -716,7 +778,7 @@ extern "C" lp_xbatch* lp_xbatch_create(const lp_xbatch_config* cfg) {
     X->threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::min(16u, std::max(2u, hc));
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    size_t arena = cfg->arena_bytes ? cfg->arena_bytes : (size_t)(free_b * 0.6);
+    size_t arena = cfg->arena_bytes ? cfg->arena_bytes : (size_t)(free_b * 0.72);
     arena = arena / 2 / 4096 * 4096 * 2;
     X->host_bytes = (size_t)2 << 30;
     bool ok = cudaMalloc(&X->arena, arena) == cudaSuccess && cudaMallocHost(&X->host_arena, X->host_bytes) == cudaSuccess;
@@ -788,8 +850,10 @@ static size_t item_device_bytes(const lp_xbatch* X, const XItem& it, int i) {
     const size_t outb = (size_t)it.ow * it.oh * 4 * 3 + (256u << 10);
     switch (it.kind) {
         case K_PNG: {
-            const size_t raw = ((size_t)it.w * 8 + 2) * it.h;  // >= raw_total for 8-bit RGBA, Adam7 included
-            return 2 * X->in_len[i] + raw + (size_t)it.w * it.h * it.ch + outb + 8192;
+            // compressed span (+ its gathered copy) + inflated scanlines + resized output; the packed frames live in a
+            // window buffer shared by the task (a fifth of the lane's arena, reserved by split_by_memory)
+            const size_t raw = ((size_t)it.w * (it.ch == 4 ? 4 : 3) + 2) * it.h * (it.png && it.png->interlace ? 2 : 1);
+            return 2 * X->in_len[i] + raw + outb + 8192;
         }
         case K_WEBP:
             return X->in_len[i] + (size_t)it.w * it.h * 3 + outb + 4096;
@@ -865,18 +929,24 @@ extern "C" int lp_xbatch_transform(lp_xbatch* X, const uint8_t* const* in, const
         for (int i : g) total += item_device_bytes(X, X->items[i], i);
         const size_t half = total / 2 + 1;
         Task cur{kind, {}};
-        size_t used = 64u << 20;
+        const size_t reserve = kind == K_PNG ? lane_cap / 5 + (64u << 20) : (64u << 20);  // PNG: the frame window
+        size_t used = reserve;
         for (int i : g) {
-            const size_t need = item_device_bytes(X, X->items[i], i);
-            if (need + (64u << 20) > lane_cap) {
+            const size_t need = item_device_bytes(X, X->items[i], i) +
+                                (kind == K_PNG ? 0 : 0);
+            if (kind == K_PNG && round_up((size_t)X->items[i].w * X->items[i].h * X->items[i].ch, (size_t)256) > std::min<size_t>((size_t)12 << 30, lane_cap / 5)) {
+                X->fallback.push_back(i);  // one frame larger than the window
+                continue;
+            }
+            if (need + reserve > lane_cap) {
                 X->fallback.push_back(i);
                 continue;
             }
-            if (!cur.idx.empty() && (used + need > lane_cap || used > half + (64u << 20))) {
+            if (!cur.idx.empty() && (used + need > lane_cap || used > half + reserve)) {
                 tasks.push_back(cur);
                 cost.push_back((double)used);
                 cur.idx.clear();
-                used = 64u << 20;
+                used = reserve;
             }
             cur.idx.push_back(i);
             used += need;

@@ -141,3 +141,39 @@ def test_batch_mixed_sampling_layouts_in_any_order(cuda_lib, oracle):
                 assert o == cuda_lib.transform(f, opt)
     finally:
         b.close()
+
+
+def test_batch_restart_interval_streams_decode_in_parallel(cuda_lib, oracle):
+    """DRI streams (one thread per restart interval) next to plain ones (self-synchronising decoder) in ONE batch:
+    the kernel is chosen per image, outputs == lp_transform (which the serial per-image kernel decodes)."""
+    cv2 = pytest.importorskip("cv2")
+    w, h = 480, 272
+    opt = abi.ImageOptions(FileType=".jpeg", Width=96, Height=96, ResizeMethod=abi.ImageOpsFit,
+                           EncodeOptions={abi.JpegQuality: 85})
+    files = []
+    for k, rst in enumerate([0, 30, 1, 0, 7, 30, 1000]):   # 30 = one MCU row at 4:2:0; 1 = every MCU; 1000 > all MCUs
+        ok, b = cv2.imencode(".jpg", synth_image(920 + k, w, h, 3), [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, rst])
+        assert ok
+        files.append(bytes(b))
+    ok, b444 = cv2.imencode(".jpg", synth_image(929, w, h, 3), [cv2.IMWRITE_JPEG_QUALITY, 88, cv2.IMWRITE_JPEG_RST_INTERVAL, 5,
+                                                                cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+    files.append(bytes(b444))
+    damaged = bytearray(files[1])
+    pos = damaged.find(b"\xff\xd3")
+    if pos > 0:
+        damaged[pos + 1] = 0xD5                                # a restart marker out of sequence
+        files.append(bytes(damaged))
+    b = abi.Batch(cuda_lib, 0, 16, w, h, 96, 96, 85, max_in_bytes=1 << 22, chunk=4)
+    try:
+        outs, status = b.transform(files)
+        for i, (f, o) in enumerate(zip(files, outs)):
+            try:
+                want, code = cuda_lib.transform(f, opt), 0
+            except abi.LilliputError as e:
+                want, code = b"", e.code
+            if i < 8:
+                assert status[i] == 0 and code == 0 and o == want, i
+            else:
+                assert (status[i] != 0) or o == want              # damaged: refused by the batch, or decoded like per image
+    finally:
+        b.close()

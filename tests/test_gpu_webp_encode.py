@@ -89,3 +89,16 @@ def test_webp_encoder_reports_a_full_destination(cuda_lib):
     img = synth_image(51, 200, 200, 3)
     with pytest.raises(abi.LilliputError):
         cuda_lib.encode(".webp", img, {abi.WebpQuality: 90}, dst_cap=500)
+
+
+def test_device_lossy_stream_is_byte_identical_to_the_serial_core(cuda_lib):
+    """The device analyses a macroblock with the whole warp (webp_encode.cu: vp8_analyse_warp); the host build of the
+    same core (oracle/_build/libvp8cpu.so, vp8enc::analyse_and_reconstruct) walks it on one thread.  Same
+    arithmetic, same decisions: the VP8 payloads must be the same bytes."""
+    from tests.webp_util import chunks_of, vp8_cpu_encode, vp8_cpu_lib
+    cpu = vp8_cpu_lib()
+    for seed, w, h, q, noise in [(71, 256, 256, 85, 6.0), (72, 97, 61, 40, 25.0), (73, 16, 16, 90, 3.0), (74, 333, 35, 75, 12.0)]:
+        img = synth_image(seed, w, h, 3, noise=noise)
+        data = cuda_lib.encode(".webp", img, {abi.WebpQuality: q})
+        payload = dict(chunks_of(data))[b"VP8 "]
+        assert bytes(payload) == bytes(vp8_cpu_encode(cpu, img, q)), (seed, w, h, q)

@@ -199,3 +199,22 @@ def test_multi_gpu_dispatcher_matches_per_image(cuda_lib, oracle):
         assert sum(m.stats(g)["grid_items"] + m.stats(g)["fallback_items"] for g in range(len(devices))) == len(files)
     finally:
         m.close()
+
+
+def test_many_distinct_huffman_table_sets(cuda_lib, xb):
+    """Per-image OPTIMISED Huffman tables (every file its own DHT): more distinct table sets than the 64 the batch
+    context used to hold, three sizes, one call -- all taken by the grid path, bytes == lp_transform."""
+    cv2 = pytest.importorskip("cv2")
+    files = []
+    for k in range(75):
+        w, h = [(320, 240), (400, 300), (512, 288)][k % 3]
+        ok, b = cv2.imencode(".jpg", synth_image(1200 + k, w, h, 3, noise=4.0 + (k % 7)), [cv2.IMWRITE_JPEG_QUALITY, 70 + (k % 25),
+                                                                                           cv2.IMWRITE_JPEG_OPTIMIZE, 1])
+        assert ok
+        files.append(bytes(b))
+    opt = abi.ImageOptions(FileType=".jpeg", Width=100, Height=100, ResizeMethod=abi.ImageOpsFit,
+                           EncodeOptions={abi.JpegQuality: 80}, EncodeTimeout_ns=T)
+    outs, status = check_against_per_image(cuda_lib, xb, files, opt)
+    assert status == [0] * len(files)
+    st = xb.stats()
+    assert st["grid_items"] == len(files) and st["fallback_items"] == 0

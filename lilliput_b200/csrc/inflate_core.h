@@ -196,6 +196,7 @@ struct WarpShared {
     // (min(length - 3, 127) << 13) | distance; length field 127 = look the full record up in Stream::mlist
     // (lengths >= 130 and distances >= 8192).  Reading them back from global memory cost ~300 cycles per match.
     uint32_t mrec[kMaxMatches];
+    uint16_t near[kMaxMatches];  // indices (into mrec) of the matches that depend on window bytes, in stream order
 };
 
 LP_INF_FN uint32_t lit_entry(uint32_t sym, uint32_t len) {
@@ -813,40 +814,83 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
             // PNG data: the pixel above is a scanline back) depend on nothing in the window -- they are spread evenly
             // over the lanes, whatever subsequence they came from.  Sources behind the ring are read from the flushed
             // output, eight byte-loads in flight at a time.
+            uint32_t n_near = 0;
             if (wM) {
-                LP_INF_LANES(l) {
-                    for (uint32_t j = (uint32_t)l; j < wM; j += 32) {
-                        const uint32_t rec = ws.mrec[j];
-                        Match m;
-                        if (((rec >> 13) & 127u) == 127u) {
-                            m = s.mlist[j];
-                        } else {
-                            m.q = o + (rec >> 20);
-                            m.ld = ((((rec >> 13) & 127u) + 3u) << 16) | (rec & 8191u);
-                        }
-                        const uint32_t len = m.ld >> 16, dist = m.ld & 0xFFFFu;
-                        if (!(dist >= len && (m.q - o) + len <= dist)) continue;  // depends on window bytes: phase D1
-                        const uint32_t src0 = m.q - dist;
-                        for (uint32_t i0 = 0; i0 < len; i0 += 8) {
-                            uint8_t b[8];
-#ifndef LP_INF_HOST
-#pragma unroll
-#endif
-                            for (uint32_t k = 0; k < 8; k++) {
-                                const uint32_t sq = src0 + i0 + k;
-                                b[k] = i0 + k < len ? (sq >= ring_lo_d0(o, wT) ? ws.ring[sq & kRingMask] : s.out[sq]) : (uint8_t)0;
+                for (uint32_t base = 0; base < wM; base += 32) {
+                    LaneVar<uint32_t> isnear;
+                    LP_INF_LANES(l) {
+                        const uint32_t j = base + (uint32_t)l;
+                        isnear[l] = 0;
+                        if (j < wM) {
+                            const uint32_t rec = ws.mrec[j];
+                            Match m;
+                            if (((rec >> 13) & 127u) == 127u) {
+                                m = s.mlist[j];
+                            } else {
+                                m.q = o + (rec >> 20);
+                                m.ld = ((((rec >> 13) & 127u) + 3u) << 16) | (rec & 8191u);
                             }
+                            const uint32_t len = m.ld >> 16, dist = m.ld & 0xFFFFu;
+                            if (!(dist >= len && (m.q - o) + len <= dist)) {
+                                isnear[l] = 1;  // depends on window bytes: phase D1
+                            } else {
+                                const uint32_t src0 = m.q - dist;
+                                for (uint32_t i0 = 0; i0 < len; i0 += 8) {
+                                    uint8_t b[8];
 #ifndef LP_INF_HOST
 #pragma unroll
 #endif
-                            for (uint32_t k = 0; k < 8; k++)
-                                if (i0 + k < len) ws.ring[(m.q + i0 + k) & kRingMask] = b[k];
+                                    for (uint32_t k = 0; k < 8; k++) {
+                                        const uint32_t sq = src0 + i0 + k;
+                                        b[k] = i0 + k < len ? (sq >= ring_lo ? ws.ring[sq & kRingMask] : s.out[sq]) : (uint8_t)0;
+                                    }
+#ifndef LP_INF_HOST
+#pragma unroll
+#endif
+                                    for (uint32_t k = 0; k < 8; k++)
+                                        if (i0 + k < len) ws.ring[(m.q + i0 + k) & kRingMask] = b[k];
+                                }
+                            }
+                        }
+                    }
+                    const uint32_t nm_ = ballot(isnear);
+                    LP_INF_LANES(l) {
+                        if (isnear[l]) ws.near[n_near + popc32(nm_ & ((1u << l) - 1u))] = (uint16_t)(base + (uint32_t)l);
+                    }
+                    n_near += popc32(nm_);
+                }
+                wsync();
+            }
+#ifndef LP_INF_D1_ROUNDS
+            // phase D1, serial form (measured 7 % faster in a 1024-stream batch than the per-lane rounds kept below under
+            // LP_INF_D1_ROUNDS: the chains leave 2-3 lanes active either way, and this form has nothing to check): the matches that depend on window bytes, in stream order, by one lane -- every
+            // source is final when its match is reached, so there is nothing to check
+            if (n_near) {
+                LP_INF_LANES(l) {
+                    if (l == 0) {
+                        for (uint32_t k = 0; k < n_near; k++) {
+                            const uint32_t j = ws.near[k], rec = ws.mrec[j];
+                            Match m;
+                            if (((rec >> 13) & 127u) == 127u) {
+                                m = s.mlist[j];
+                            } else {
+                                m.q = o + (rec >> 20);
+                                m.ld = ((((rec >> 13) & 127u) + 3u) << 16) | (rec & 8191u);
+                            }
+                            const uint32_t len = m.ld >> 16, dist = m.ld & 0xFFFFu, src0 = m.q - dist;
+                            uint32_t kk = 0;
+                            for (uint32_t i = 0; i < len; i++) {
+                                const uint32_t sq = src0 + kk;
+                                ws.ring[(m.q + i) & kRingMask] = sq >= ring_lo ? ws.ring[sq & kRingMask] : s.out[sq];
+                                if (++kk == dist) kk = 0;
+                            }
                         }
                     }
                 }
                 wsync();
             }
-            if (wM) {
+#else
+            if (n_near) {
                 LaneVar<uint32_t> mi, mend, own_start, blocked_q, notdone;
                 LP_INF_LANES(l) {
                     const bool wrote = l <= last_lane;
@@ -948,6 +992,7 @@ LP_INF_FN int inflate_stream(WarpShared& ws, const Stream& s, uint32_t* produced
                     H = bcast(blocked_q, (int)ffs32(nd) - 1);
                 }
             }
+#endif
             LP_INF_CLOCK(13);
             o += wT;
             P += new_rel - rel;

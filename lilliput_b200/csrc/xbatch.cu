@@ -254,6 +254,8 @@ static void sink_encode(lp_xbatch* X, Lane& L, Bump& bump, const std::vector<int
             failed->insert(failed->end(), idx.begin(), idx.end());
             return;
         }
+        const bool dbg = getenv("LP_DEBUG") != nullptr;
+        const auto tq0 = std::chrono::steady_clock::now();
         JpegEncodeBatch e;
         e.frames = d_frames;
         e.frame_img_stride = stride;
@@ -287,6 +289,10 @@ static void sink_encode(lp_xbatch* X, Lane& L, Bump& bump, const std::vector<int
             return;
         }
         L.d2h += total + (size_t)n * 12;
+        const auto tq1 = std::chrono::steady_clock::now();
+        if (dbg)
+            fprintf(stderr, "[lilliput_b200] jpeg sink: n=%d %dx%dx%d slot=%zu total=%zu: launches + D2H %.2f ms\n", n, ow, oh, ch, slot,
+                    total, std::chrono::duration<double, std::milli>(tq1 - tq0).count());
         for (int k = 0; k < n; k++) {
             const int i = idx[k];
             if (len[k] == 0 || len[k] > slot || len[k] > X->out_cap) {  // did not fit the slot: let Transform decide

@@ -210,8 +210,9 @@ typedef struct lp_xbatch_config {
 typedef struct lp_xbatch_stats {
     int grid_items, fallback_items, groups, launches;
     double ms_parse, ms_grid, ms_fallback, ms_total; /* host wall clock of the phases */
-    double ms_decode, ms_resize, ms_encode;          /* CUDA-event time of the grid stages, summed over chunks */
+    double ms_decode, ms_resize, ms_encode;          /* CUDA-event time of the grid stages, summed over chunks AND lanes */
     size_t h2d_bytes, d2h_bytes;
+    double ms_busy_max_lane; /* the two lanes run concurrently: the larger of their per-lane stage-time sums */
 } lp_xbatch_stats;
 lp_xbatch* lp_xbatch_create(const lp_xbatch_config* cfg);
 void lp_xbatch_destroy(lp_xbatch* x);
@@ -231,6 +232,8 @@ int lp_multi_transform(lp_multi* m, const uint8_t* const* in, const size_t* in_l
                        const lp_image_options* opt, uint8_t* const* out, size_t out_cap, size_t* out_len,
                        int* status);
 void lp_multi_get_stats(const lp_multi* m, int device_index, lp_xbatch_stats* out);
+/* Host-only: the block boundaries lp_multi_transform uses (first[0..parts], contiguous, balanced by bytes). */
+void lp_shard_blocks(const size_t* in_len, int n, int parts, int* first);
 
 /* ---- single stages on device pointers, on `stream` (a cudaStream_t) -------- */
 

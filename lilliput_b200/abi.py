@@ -421,7 +421,7 @@ class _XBatchStats(C.Structure):
     _fields_ = [("grid_items", C.c_int), ("fallback_items", C.c_int), ("groups", C.c_int), ("launches", C.c_int),
                 ("ms_parse", C.c_double), ("ms_grid", C.c_double), ("ms_fallback", C.c_double), ("ms_total", C.c_double),
                 ("ms_decode", C.c_double), ("ms_resize", C.c_double), ("ms_encode", C.c_double),
-                ("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t)]
+                ("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t), ("ms_busy_max_lane", C.c_double)]
 
 
 class XBatch:

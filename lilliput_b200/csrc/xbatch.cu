@@ -1057,6 +1057,7 @@ extern "C" int lp_xbatch_transform(lp_xbatch* X, const uint8_t* const* in, const
         X->stats.h2d_bytes += L.h2d;
         X->stats.d2h_bytes += L.d2h;
         X->stats.launches += (int)L.launches;
+        X->stats.ms_busy_max_lane = std::max(X->stats.ms_busy_max_lane, L.ms_decode + L.ms_resize + L.ms_encode);
     }
     X->stats.launches += (int)(lane_launches.load() + fb_launches.load());
     cudaSetDevice(prev);
@@ -1103,24 +1104,30 @@ extern "C" void lp_multi_destroy(lp_multi* m) {
 
 extern "C" int lp_multi_device_count(const lp_multi* m) { return m ? (int)m->ctx.size() : 0; }
 
+// Host-only: cut n items into `parts` contiguous blocks with (nearly) equal compressed bytes ("contiguous
+// blocks balanced by compressed bytes"); first[p] .. first[p + 1] is block p, first has parts + 1 entries.
+extern "C" void lp_shard_blocks(const size_t* in_len, int n, int parts, int* first) {
+    if (parts < 1 || !first) return;
+    for (int p = 0; p <= parts; p++) first[p] = n < 0 ? 0 : n;
+    first[0] = 0;
+    if (n <= 0 || !in_len) return;
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += in_len[i] + 4096;  // (+ a per-image constant: tiny files still cost a launch slot)
+    size_t acc = 0;
+    int g = 1;
+    for (int i = 0; i < n && g < parts; i++) {
+        acc += in_len[i] + 4096;
+        while (g < parts && acc * (size_t)parts >= total * (size_t)g) first[g++] = i + 1;
+    }
+}
+
 extern "C" int lp_multi_transform(lp_multi* m, const uint8_t* const* in, const size_t* in_len, int n,
                                   const lp_image_options* opt, uint8_t* const* out, size_t out_cap, size_t* out_len,
                                   int* status) {
     if (!m || n < 0 || !opt || (n > 0 && (!in || !in_len || !out || !out_len || !status))) return LP_ERR_BAD_ARGUMENT;
     const int G = (int)m->ctx.size();
-    // contiguous blocks with (nearly) equal compressed bytes
-    size_t total = 0;
-    for (int i = 0; i < n; i++) total += in_len[i] + 4096;  // (+ a per-image constant: tiny files still cost a launch slot)
     m->first.assign((size_t)G + 1, n);
-    m->first[0] = 0;
-    {
-        size_t acc = 0;
-        int g = 1;
-        for (int i = 0; i < n && g < G; i++) {
-            acc += in_len[i] + 4096;
-            if (acc * G >= total * (size_t)g) m->first[g++] = i + 1;
-        }
-    }
+    lp_shard_blocks(in_len, n, G, m->first.data());
     std::vector<int> rc((size_t)G, LP_OK);
     std::vector<std::thread> pool;
     for (int g = 0; g < G; g++) {

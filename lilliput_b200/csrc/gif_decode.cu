@@ -143,103 +143,159 @@ struct GifFrameDev {
     int* status;          // 0 ok, -1 short / corrupt stream
 };
 
-struct LzwBits {
-    const uint8_t* p;
-    const uint8_t* end;
-    uint64_t acc;
-    int cnt;
-    __device__ __forceinline__ int get(int n) {
-        if (cnt < n && p + 4 <= end) {  // 32 bits per refill while a whole word is left
-            const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-            acc |= (uint64_t)__funnelshift_r(q[0], q[1], 8 * (int)(a & 3)) << cnt;  // q[1]: inside the padded buffer
-            p += 4;
-            cnt += 32;
-        }
-        while (cnt < n) {
-            if (p >= end) return -1;
-            acc |= (uint64_t)(*p++) << cnt;
-            cnt += 8;
-        }
-        const int v = (int)(acc & ((1u << n) - 1));
-        acc >>= n;
-        cnt -= n;
-        return v;
-    }
+// LZW dictionary of one frame in shared memory: per entry the classic prefix link, its last pixel and the string
+// length in one word, plus the FIRST pixel of the string (what the next entry needs, so that creating an entry never
+// walks a chain).
+struct GifLzwShared {
+    uint32_t link[4096];  // prefix code | last pixel << 12 | string length << 20
+    uint8_t first[4096];
 };
 
-__device__ __forceinline__ int gif_lzw_decode_frame(const GifFrameDev& f, uint32_t* t_off, uint16_t* t_len) {
+// One frame's code stream, decoded by one warp, 32 codes per round.  giflib's DGifDecompressInput / DGifDecompressLine
+// state machine (ref giflib.cpp:181-184 -> DGifGetLine): `running` counts the codes read since the last clear
+// (+ clear + 2), the code width grows when it passes maxcode1 = 1 << bits, every code after the first one of a
+// segment adds entry `top` = previous string + first pixel of this one.  None of that depends on the VALUES of the
+// codes (clear codes aside), so a round is
+//   1. widths in closed form -> prefix sum -> every lane reads its own code; the round ends in front of the first
+//      clear / EOF / out-of-data code, which the next round handles alone;
+//   2. validity and the entry each code creates, again in closed form; the round is cut at the first invalid code;
+//   3. (length, first pixel) per code: from the table, or -- a code that names an entry created inside this round --
+//      from the lane in front of the creator, by pointer jumping;
+//   4. prefix sum of the lengths = where each string goes; the round is cut where the frame is full;
+//   5. the new entries are written, then every lane walks its own chain backwards, storing pixels.
+// The serial chain walk (one shared-memory load per pixel) is the cost that is left, and 32 of them run at once.
+// (The first version kept entries as spans of the OUTPUT and copied them warp-wide from global memory: ~650 cycles
+// per code, most of it the L1 miss after the store in front.)
+__device__ __forceinline__ int gif_lzw_decode_frame(const GifFrameDev& f, GifLzwShared& sh) {
+    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    // giflib's DGifDecompressInput/Line state machine: `running` counts codes read since the last
-    // clear (+ clear + 2); the code width grows when it passes maxcode1; a code creates entry
-    // running - 2 from the previous string.
     const int clear = 1 << f.min_code, eof = clear + 1;
-    int bits = f.min_code + 1, maxcode1 = 1 << bits, running = clear + 2, top = clear + 2;
-    LzwBits b{f.lzw, f.lzw + f.lzw_len, 0, 0};
-    uint32_t o = 0;
-    uint32_t prev_off = 0;
-    int prev_len = 0;  // 0 = no previous string since the last clear
+    int bits = f.min_code + 1, running = clear + 2, top = clear + 2;  // maxcode1 == 1 << bits throughout
+    const uint64_t total_bits = 8ull * f.lzw_len;
+    uint64_t bp = 0;    // bit position of the next code
+    uint32_t o = 0;     // pixels written
+    int prev_code = 0, prev_len = 0, prev_first = 0;  // previous string of this segment; prev_len 0 = none
     int status = 0;
     while (o < f.npix) {
-        // lane 0 reads the next code and resolves it to a span of the output (or a literal)
-        uint32_t src = 0;
-        int len = 0, lit = -1, cmd = 0;  // cmd: 0 emit, 1 clear, 3 error
-        if (lane == 0) {
-            const int code = b.get(bits);
-            if (code >= 0 && running < 4097 && ++running > maxcode1 && bits < 12) {
-                maxcode1 <<= 1;
-                bits++;
+        // closed-form widths need running <= maxcode1 (true from the first clear state on for min_code >= 1; a
+        // min_code of 0 starts with running 3 > 2 and gets there within two codes: those go one per round)
+        const bool regular = running <= (1 << bits) || bits >= 12;
+        const int r_j = min(running + lane, 4097);  // `running` when this lane's code is read
+        const int w_j = regular ? min(12, max(bits, 32 - __clz(r_j - 1))) : bits;
+        int incl = w_j;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint64_t at = bp + (uint64_t)(incl - w_j);
+        int code = -1;
+        if (at + (uint64_t)w_j <= total_bits && (regular || lane == 0)) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(f.lzw + (at >> 3));
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);  // q[1]: inside the padded buffer
+            code = (int)((__funnelshift_r(q[0], q[1], 8 * (int)(a & 3) + (int)(at & 7))) & ((1u << w_j) - 1));
+        }
+        const bool special = code < 0 || code == clear || code == eof || (!regular && lane > 0);
+        int n = __ffs(__ballot_sync(FULL, special)) - 1;
+        if (n < 0) n = 32;
+        if (n == 0) {
+            const int c0 = __shfl_sync(FULL, code, 0);
+            if (c0 < 0 || c0 == eof) {  // data ran out / EOF code before the last pixel: an error for giflib
+                status = -1;
+                break;
             }
-            if (code < 0) cmd = 3;                 // data ran out before the frame was complete
-            else if (code == eof) cmd = 3;         // giflib: EOF code before the last pixel is an error
-            else if (code == clear) cmd = 1;
-            else {
-                const int create = running - 2;    // entry this code will add (if there is a previous string)
-                if (code < clear) { lit = code; len = 1; }
-                else if (code > eof && code < top) { src = t_off[code]; len = t_len[code]; }
-                else if (prev_len && code == create && code == top) { src = prev_off; len = prev_len + 1; }  // KwKwK
-                else cmd = 3;
-                if (!cmd) {
-                    if (prev_len && create < 4096 && create == top) {
-                        t_off[create] = prev_off;
-                        t_len[create] = (uint16_t)min(prev_len + 1, 65535);
-                        top++;
-                    }
-                    prev_off = o;
-                    prev_len = len;
-                }
-            }
-            if (cmd == 1) {
-                bits = f.min_code + 1;
-                maxcode1 = 1 << bits;
-                running = clear + 2;
-                top = clear + 2;
-                prev_len = 0;
+            bp += bits;  // a clear code
+            bits = f.min_code + 1;
+            running = clear + 2;
+            top = clear + 2;
+            prev_len = 0;
+            continue;
+        }
+        // entry created by the code of lane j: none by the first code of a segment, none once the table is full
+        const int made_before = prev_len ? lane : max(lane - 1, 0);
+        const int top_j = min(4096, top + made_before);
+        const bool creates = (lane > 0 || prev_len) && top_j < 4096 && min(running + lane + 1, 4097) - 2 == top_j;
+        const bool in_table = code < clear || (code > eof && code < top);
+        const bool in_round = !in_table && code > eof && (code < top_j || (code == top_j && creates));
+        const bool invalid = lane < n && !in_table && !in_round;
+        const int iv = __ffs(__ballot_sync(FULL, invalid)) - 1;
+        const bool corrupt = iv >= 0;
+        if (corrupt) n = iv;
+        // (length, first pixel)
+        int len = 0, first = 0;
+        bool done = lane >= n;
+        if (!done && in_table) {
+            if (code < clear) { len = 1; first = code; }
+            else { len = (int)(sh.link[code] >> 20); first = sh.first[code]; }
+            done = true;
+        }
+        const int dep = code - top + (prev_len ? 0 : 1) - 1;  // lane whose string this code's entry extends; -1 = prev
+        while (!__all_sync(FULL, done)) {
+            const int src = max(dep, 0) & 31;
+            const int d_len = __shfl_sync(FULL, len, src), d_first = __shfl_sync(FULL, first, src);
+            const bool d_done = __shfl_sync(FULL, done, src);
+            if (!done) {
+                if (dep < 0) { len = prev_len + 1; first = prev_first; done = true; }
+                else if (d_done) { len = d_len + 1; first = d_first; done = true; }
             }
         }
-        cmd = __shfl_sync(0xffffffffu, cmd, 0);
-        if (cmd == 1) continue;
-        if (cmd >= 2) { status = -1; break; }
-        len = __shfl_sync(0xffffffffu, len, 0);
-        src = __shfl_sync(0xffffffffu, src, 0);
-        lit = __shfl_sync(0xffffffffu, lit, 0);
-        const uint32_t take = min((uint32_t)len, f.npix - o);
-        if (lit >= 0) {
-            if (lane == 0) f.indices[o] = (uint8_t)lit;
-        } else {
-            // bytes src.. were written before o, except the KwKwK tail byte which equals byte src
-            for (uint32_t i = lane; i < take; i += 32) f.indices[o + i] = f.indices[src + i < o ? src + i : src];
+        int lsum = lane < n ? len : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL, lsum, d);
+            if (lane >= d) lsum += t;
+        }
+        const uint32_t room = f.npix - o;
+        const int full_at = __ffs(__ballot_sync(FULL, lane < n && (uint32_t)lsum >= room)) - 1;
+        bool complete = false;
+        if (full_at >= 0) { n = full_at + 1; complete = true; }  // the codes behind are never read
+        if (n == 0) { status = -1; break; }                        // (only when the first code of the round is invalid)
+        // new entries: previous string + first pixel of this one
+        const int p_code = __shfl_up_sync(FULL, code, 1), p_len = __shfl_up_sync(FULL, len, 1),
+                  p_first = __shfl_up_sync(FULL, first, 1);
+        if (lane < n && creates) {
+            const int pc = lane ? p_code : prev_code, pl = lane ? p_len : prev_len, pf = lane ? p_first : prev_first;
+            sh.link[top_j] = (uint32_t)pc | (uint32_t)first << 12 | (uint32_t)(pl + 1) << 20;
+            sh.first[top_j] = (uint8_t)pf;
         }
         __syncwarp();
-        o += take;
+        if (lane < n) {
+            uint32_t p = o + (uint32_t)(lsum - 1);  // last pixel of this string
+            int c = code;
+            while (c > eof) {
+                const uint32_t l = sh.link[c];
+                if (p < f.npix) f.indices[p] = (uint8_t)(l >> 12);
+                p--;
+                c = (int)(l & 0xFFFu);
+            }
+            if (p < f.npix) f.indices[p] = (uint8_t)c;
+        }
+        __syncwarp();
+        // state behind the last code of the round
+        const int last = n - 1;
+        prev_code = __shfl_sync(FULL, code, last);
+        const int n_len = __shfl_sync(FULL, len, last);
+        prev_first = __shfl_sync(FULL, first, last);
+        const int total = __shfl_sync(FULL, lsum, last);
+        bp += (uint64_t)__shfl_sync(FULL, incl, last);
+        top = min(4096, top + (prev_len ? n : max(n - 1, 0)));
+        prev_len = n_len;
+        if (regular) {
+            running = min(running + n, 4097);
+            bits = min(12, max(bits, 32 - __clz(running - 1)));
+        } else if (running < 4097 && ++running > (1 << bits) && bits < 12) {
+            bits++;
+        }
+        o += min((uint32_t)total, room);
+        if (complete) break;
+        if (corrupt) { status = -1; break; }
     }
     return status;
 }
 
 __global__ void __launch_bounds__(32) gif_lzw_kernel(GifFrameDev f) {
-    __shared__ uint32_t t_off[4096];
-    __shared__ uint16_t t_len[4096];
-    const int status = gif_lzw_decode_frame(f, t_off, t_len);
+    __shared__ GifLzwShared sh;
+    const int status = gif_lzw_decode_frame(f, sh);
     if (threadIdx.x == 0) *f.status = status;
 }
 
@@ -333,11 +389,10 @@ __global__ void __launch_bounds__(kGifDeblockWarps * 32) gif_deblock_kernel(GifF
 }
 
 __global__ void __launch_bounds__(32) gif_lzw_batch_kernel(GifFrameJob* jobs, uint8_t* base) {
-    __shared__ uint32_t t_off[4096];
-    __shared__ uint16_t t_len[4096];
+    __shared__ GifLzwShared sh;
     GifFrameJob& j = jobs[blockIdx.x];
     GifFrameDev f{base + j.lzw_off, j.lzw_len, j.min_code, j.npix, base + j.idx_off, nullptr};
-    const int status = gif_lzw_decode_frame(f, t_off, t_len);
+    const int status = gif_lzw_decode_frame(f, sh);
     if (threadIdx.x == 0) j.status = status;
 }
 

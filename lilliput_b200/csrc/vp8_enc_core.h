@@ -179,14 +179,40 @@ LP_VP8_FN void put_large_value(BoolEnc& e, int v, const uint8_t* p) {
         for (int i = 0; i < nb; i++) be_put(e, (extra >> (nb - 1 - i)) & 1, tab[i]);
     }
 }
+// which of the 16 levels of a block (raster order in memory) are non-zero, as a mask in ZIG-ZAG order
+// (0 1 4 8 5 2 3 6 9 12 13 10 7 11 14 15): one 32-byte block load, the rest stays in registers
+LP_VP8_INL uint32_t nonzero_mask(const int16_t* levels) {
+    uint32_t w[8];
+#ifdef __CUDA_ARCH__
+    const uint4 a = reinterpret_cast<const uint4*>(levels)[0], b = reinterpret_cast<const uint4*>(levels)[1];  // blocks are 32-byte aligned
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) w[i] = (uint32_t)(uint16_t)levels[2 * i] | (uint32_t)(uint16_t)levels[2 * i + 1] << 16;
+#endif
+#define LP_NZ(r) ((w[(r) >> 1] >> (16 * ((r) & 1)) & 0xFFFFu) ? 1u : 0u)
+    return LP_NZ(0) | LP_NZ(1) << 1 | LP_NZ(4) << 2 | LP_NZ(8) << 3 | LP_NZ(5) << 4 | LP_NZ(2) << 5 | LP_NZ(3) << 6 |
+           LP_NZ(6) << 7 | LP_NZ(9) << 8 | LP_NZ(12) << 9 | LP_NZ(13) << 10 | LP_NZ(10) << 11 | LP_NZ(7) << 12 |
+           LP_NZ(11) << 13 | LP_NZ(14) << 14 | LP_NZ(15) << 15;
+#undef LP_NZ
+}
+// index (zig-zag order) of the last non-zero level at or after `first`, -1 when there is none
+LP_VP8_INL int last_nonzero(const int16_t* levels, int first) {
+    const uint32_t mm = nonzero_mask(levels) >> first << first;
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)mm);
+#else
+    int last = -1;
+    for (int n = 0; n < 16; n++)
+        if (mm >> n & 1u) last = n;
+    return last;
+#endif
+}
 // levels in raster order; returns 1 when the block has a non-zero level at or after `first`.
 LP_VP8_FN int put_coeffs(BoolEnc& e, const uint8_t* proba, int type, int ctx, int first, const int16_t* levels) {
     const uint8_t bands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
     const uint8_t zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
     const uint8_t* tp = proba + type * (8 * 3 * 11);
-    int last = -1;
-    for (int n = first; n < 16; n++)
-        if (levels[zigzag[n]]) last = n;
+    const int last = last_nonzero(levels, first);
     int n = first;
     const uint8_t* p = tp + (bands[n] * 3 + ctx) * 11;
     if (last < 0) {
@@ -378,10 +404,32 @@ LP_VP8_FN void analyse_and_reconstruct(const Params& P, const Buffers& B) {
         }
 }
 
-// Pass 2: the bitstream.  part0 / tokens are scratch areas; `out` receives the "VP8 " chunk payload.
-// top_nz: mb_w*9 bytes of scratch.  Returns the payload size, 0 when it does not fit.
-LP_VP8_FN size_t write_bitstream(const Params& P, const Buffers& B, uint8_t* part0, size_t part0_cap, uint8_t* tokens,
-                                 size_t tokens_cap, uint8_t* top_nz, uint8_t* out, size_t out_cap) {
+// Pass 2: the bitstream.  VP8 lets the coefficient tokens of a frame travel in up to 8 PARTITIONS, macroblock row r in
+// partition r mod n (RFC 6386 s.9.5), each with its own boolean coder -- the unit of parallelism of this pass: the
+// device gives every partition, and the first partition (modes), a lane of its own.  The contexts a coder needs from
+// the row above (which blocks had non-zero levels) are read from that row's levels, not carried from its coder, so
+// the partitions really are independent.  The serial write_bitstream below runs the same pieces one after the other
+// and is what the CPU tests and the oracle use: both produce the same bytes.
+
+// 8 partitions when the frame has 8 macroblock rows, else the largest power of two that leaves none empty
+LP_VP8_HD int log2_partitions(const Params& P) {
+    int l = 0;
+    while (l < 3 && (2 << l) <= P.mb_h) l++;
+    return l;
+}
+LP_VP8_HD int partition_rows(const Params& P, int part, int nparts) { return (P.mb_h - part + nparts - 1) / nparts; }
+// scratch region of a partition inside the token area (nmb * 2048 + 4096 bytes): 2 KiB per macroblock + slack
+LP_VP8_HD size_t partition_scratch_off(const Params& P, int part, int nparts) {
+    size_t rows_before = 0;
+    for (int q = 0; q < part; q++) rows_before += (size_t)partition_rows(P, q, nparts);
+    return rows_before * (size_t)P.mb_w * 2048 + (size_t)part * 64;
+}
+LP_VP8_HD size_t partition_scratch_cap(const Params& P, int part, int nparts) {
+    return (size_t)partition_rows(P, part, nparts) * (size_t)P.mb_w * 2048 + 64;
+}
+
+// first partition: frame header + per-macroblock modes.  Returns its size, 0 when it does not fit.
+LP_VP8_FN size_t write_part0(const Params& P, const Buffers& B, uint8_t* part0, size_t part0_cap) {
     BoolEnc h;
     be_init(h, part0, part0_cap);
     be_put_bits(h, 0, 1);  // colour space
@@ -391,7 +439,7 @@ LP_VP8_FN size_t write_bitstream(const Params& P, const Buffers& B, uint8_t* par
     be_put_bits(h, (uint32_t)P.filter_level, 6);
     be_put_bits(h, 0, 3);  // sharpness
     be_put_bits(h, 0, 1);  // no loop-filter deltas
-    be_put_bits(h, 0, 2);  // one token partition
+    be_put_bits(h, (uint32_t)log2_partitions(P), 2);
     be_put_bits(h, (uint32_t)P.q, 7);
     for (int i = 0; i < 5; i++) be_put_bits(h, 0, 1);  // no quantiser deltas
     be_put_bits(h, 0, 1);                               // refresh_entropy_probs
@@ -423,15 +471,31 @@ LP_VP8_FN size_t write_bitstream(const Params& P, const Buffers& B, uint8_t* par
         }
     }
     be_flush(h);
+    return h.overflow ? 0 : h.pos;
+}
+
+// 1 when a block has a non-zero level at or after `first` (what put_coeffs returns for it)
+LP_VP8_INL int block_nz(const int16_t* levels, int first) { return (nonzero_mask(levels) >> first) != 0; }
+
+// token partition `part` of `nparts`: rows part, part + nparts, ...  Returns its size, 0 when it does not fit.
+LP_VP8_FN size_t write_partition(const Params& P, const Buffers& B, int part, int nparts, uint8_t* buf, size_t cap) {
     BoolEnc t;
-    be_init(t, tokens, tokens_cap);
+    be_init(t, buf, cap);
     const uint8_t* proba = &kVp8CoeffProba0[0][0][0][0];
-    for (int i = 0; i < P.mb_w * 9; i++) top_nz[i] = 0;
-    for (int mb_y = 0; mb_y < P.mb_h; mb_y++) {
+    for (int mb_y = part; mb_y < P.mb_h; mb_y += nparts) {
         uint8_t left_nz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int mb_x = 0; mb_x < P.mb_w; mb_x++) {
             const int16_t* lv = B.levels + ((size_t)mb_y * P.mb_w + mb_x) * 25 * 16;
-            uint8_t* tnz = top_nz + mb_x * 9;
+            uint8_t tnz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (mb_y > 0) {  // bottom blocks of the macroblock above
+                const int16_t* up = lv - (size_t)P.mb_w * 25 * 16;
+                for (int i = 0; i < 4; i++) tnz[i] = (uint8_t)block_nz(up + (12 + i) * 16, 1);
+                tnz[4] = (uint8_t)block_nz(up + 18 * 16, 0);
+                tnz[5] = (uint8_t)block_nz(up + 19 * 16, 0);
+                tnz[6] = (uint8_t)block_nz(up + 22 * 16, 0);
+                tnz[7] = (uint8_t)block_nz(up + 23 * 16, 0);
+                tnz[8] = (uint8_t)block_nz(up + 24 * 16, 0);
+            }
             for (int k = -1; k < 24; k++) {  // Y2, 16 Y, 4 U, 4 V: the decoder's order and contexts
                 int type, ti, li, first = 0;
                 const int16_t* blk;
@@ -449,10 +513,22 @@ LP_VP8_FN size_t write_bitstream(const Params& P, const Buffers& B, uint8_t* par
         }
     }
     be_flush(t);
-    if (h.overflow || t.overflow) return 0;
-    const size_t total = 10 + h.pos + t.pos;
-    if (total > out_cap || h.pos >= (1u << 19)) return 0;
-    const uint32_t tag = 0u | (0u << 1) | (1u << 4) | ((uint32_t)h.pos << 5);  // key frame, profile 0, shown
+    return t.overflow ? 0 : t.pos;
+}
+
+// frame tag + start code + dimensions + (behind the first partition) the partition size table.  `sizes[nparts]`.
+// Returns the payload size, 0 when it does not fit; the caller copies part0 to out + 10 and the partitions to
+// out + 10 + part0_len + 3 * (nparts - 1) + (sizes in front of it).
+LP_VP8_FN size_t write_frame_header(const Params& P, size_t part0_len, const size_t* sizes, int nparts, uint8_t* out,
+                                    size_t out_cap) {
+    size_t total = 10 + part0_len + (size_t)3 * (nparts - 1);
+    bool ok = part0_len != 0 && part0_len < (1u << 19);
+    for (int i = 0; i < nparts; i++) {
+        ok = ok && sizes[i] != 0 && sizes[i] < (1u << 24);
+        total += sizes[i];
+    }
+    if (!ok || total > out_cap) return 0;
+    const uint32_t tag = 0u | (0u << 1) | (1u << 4) | ((uint32_t)part0_len << 5);  // key frame, profile 0, shown
     out[0] = (uint8_t)tag;
     out[1] = (uint8_t)(tag >> 8);
     out[2] = (uint8_t)(tag >> 16);
@@ -463,8 +539,35 @@ LP_VP8_FN size_t write_bitstream(const Params& P, const Buffers& B, uint8_t* par
     out[7] = (uint8_t)((P.width >> 8) & 0x3f);
     out[8] = (uint8_t)P.height;
     out[9] = (uint8_t)((P.height >> 8) & 0x3f);
-    for (size_t i = 0; i < h.pos; i++) out[10 + i] = part0[i];
-    for (size_t i = 0; i < t.pos; i++) out[10 + h.pos + i] = tokens[i];
+    uint8_t* tab = out + 10 + part0_len;
+    for (int i = 0; i + 1 < nparts; i++) {  // the last partition takes what is left
+        tab[3 * i + 0] = (uint8_t)sizes[i];
+        tab[3 * i + 1] = (uint8_t)(sizes[i] >> 8);
+        tab[3 * i + 2] = (uint8_t)(sizes[i] >> 16);
+    }
+    return total;
+}
+
+// part0 / tokens are scratch areas; `out` receives the "VP8 " chunk payload.  Returns the payload size, 0 when it does
+// not fit.  (top_nz: unused, kept for the callers' layouts.)
+LP_VP8_FN size_t write_bitstream(const Params& P, const Buffers& B, uint8_t* part0, size_t part0_cap, uint8_t* tokens,
+                                 size_t tokens_cap, uint8_t* top_nz, uint8_t* out, size_t out_cap) {
+    (void)top_nz;
+    const int nparts = 1 << log2_partitions(P);
+    if (partition_scratch_off(P, nparts - 1, nparts) + partition_scratch_cap(P, nparts - 1, nparts) > tokens_cap) return 0;
+    const size_t part0_len = write_part0(P, B, part0, part0_cap);
+    size_t sizes[8];
+    for (int q = 0; q < nparts; q++)
+        sizes[q] = write_partition(P, B, q, nparts, tokens + partition_scratch_off(P, q, nparts), partition_scratch_cap(P, q, nparts));
+    const size_t total = write_frame_header(P, part0_len, sizes, nparts, out, out_cap);
+    if (!total) return 0;
+    for (size_t i = 0; i < part0_len; i++) out[10 + i] = part0[i];
+    size_t at = 10 + part0_len + (size_t)3 * (nparts - 1);
+    for (int q = 0; q < nparts; q++) {
+        const uint8_t* src = tokens + partition_scratch_off(P, q, nparts);
+        for (size_t i = 0; i < sizes[q]; i++) out[at + i] = src[i];
+        at += sizes[q];
+    }
     return total;
 }
 

@@ -369,6 +369,43 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
         }
 }
 
+// The bitstream pass on a warp: lane q codes token partition q, lane `nparts` the first partition, then all lanes
+// copy the pieces into place.  Same bytes as vp8enc::write_bitstream (the serial composition of the same pieces).
+__device__ size_t vp8_write_bitstream_warp(const vp8enc::Params& P, const vp8enc::Buffers& B, uint8_t* part0, size_t part0_cap,
+                                           uint8_t* tokens, size_t tokens_cap, uint8_t* out, size_t out_cap) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int nparts = 1 << vp8enc::log2_partitions(P);
+    if (vp8enc::partition_scratch_off(P, nparts - 1, nparts) + vp8enc::partition_scratch_cap(P, nparts - 1, nparts) > tokens_cap)
+        return 0;
+    unsigned long long mine = 0;
+    if (lane < nparts)
+        mine = vp8enc::write_partition(P, B, lane, nparts, tokens + vp8enc::partition_scratch_off(P, lane, nparts),
+                                       vp8enc::partition_scratch_cap(P, lane, nparts));
+    else if (lane == nparts)
+        mine = vp8enc::write_part0(P, B, part0, part0_cap);
+    __syncwarp();
+    const size_t part0_len = (size_t)__shfl_sync(FULL, mine, nparts);
+    size_t sizes[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) sizes[q] = (size_t)__shfl_sync(FULL, mine, q);
+    size_t total = 0;
+    if (lane == 0) total = vp8enc::write_frame_header(P, part0_len, sizes, nparts, out, out_cap);
+    total = (size_t)__shfl_sync(FULL, (unsigned long long)total, 0);
+    if (!total) return 0;
+    for (size_t i = lane; i < part0_len; i += 32) out[10 + i] = part0[i];
+    size_t at = 10 + part0_len + (size_t)3 * (nparts - 1);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (q < nparts) {
+            const uint8_t* src = tokens + vp8enc::partition_scratch_off(P, q, nparts);
+            for (size_t i = lane; i < sizes[q]; i += 32) out[at + i] = src[i];
+            at += sizes[q];
+        }
+    }
+    return total;
+}
+
 struct Vp8EncJob {
     vp8enc::Params P;
     vp8enc::Buffers B;
@@ -381,8 +418,8 @@ __global__ void __launch_bounds__(32) vp8_encode_kernel(Vp8EncJob j) {
     __shared__ Vp8WarpBuf wb;
     if (j.P.filter_level < 0) j.P.filter_level = vp8enc::filter_level_for_q(j.P.q);
     vp8_analyse_warp(j.P, j.B, wb);
-    if (threadIdx.x != 0) return;
-    *j.out_len = vp8enc::write_bitstream(j.P, j.B, j.part0, j.part0_cap, j.tokens, j.tokens_cap, j.top_nz, j.out, j.out_cap);
+    const size_t n = vp8_write_bitstream_warp(j.P, j.B, j.part0, j.part0_cap, j.tokens, j.tokens_cap, j.out, j.out_cap);
+    if (threadIdx.x == 0) *j.out_len = n;
 }
 
 static int vp8_encode_dev(const uint8_t* d_frame, size_t step, int width, int height, int channels, int quality,
@@ -505,10 +542,9 @@ __global__ void __launch_bounds__(kVp8EncWarps * 32) vp8_encode_batch_kernel(Vp8
     B.levels = reinterpret_cast<int16_t*>(base + b.off_levels);
     B.modes = base + b.off_modes;
     vp8_analyse_warp(P, B, wbs[threadIdx.x >> 5]);
-    if ((threadIdx.x & 31) != 0) return;
-    const size_t n = vp8enc::write_bitstream(P, B, base + b.off_part0, b.part0_cap, base + b.off_tokens, b.tokens_cap,
-                                             base + b.off_topnz, b.out + (size_t)f * b.out_cap, b.out_cap);
-    b.out_len[f] = (uint32_t)n;
+    const size_t n = vp8_write_bitstream_warp(P, B, base + b.off_part0, b.part0_cap, base + b.off_tokens, b.tokens_cap,
+                                              b.out + (size_t)f * b.out_cap, b.out_cap);
+    if ((threadIdx.x & 31) == 0) b.out_len[f] = (uint32_t)n;
 }
 
 // alpha plane of every frame + "does the frame have any non-opaque pixel" (libwebp drops the ALPH chunk of an
@@ -719,7 +755,41 @@ int webp_encode_lossy_batch(const uint8_t* d_frames, size_t img_stride, size_t r
                 if (cudaStreamSynchronize(st) != cudaSuccess) { rc = LP_ERR_CUDA; break; }  // (tables / heads stay alive until here)
             }
         }
-        // results home: one copy per frame of the bytes actually used
+        // results home: the bytes actually used, packed on the device and fetched with ONE copy per kind (a copy per
+        // frame -- 16 K of them for a task of 128-frame animations -- cost more than the encoder)
+        std::vector<unsigned long long> off((size_t)n + 1, 0), aoff((size_t)n + 1, 0);
+        std::vector<uint32_t> alen((size_t)n, 0);
+        for (int i = 0; i < n; i++) {
+            const uint32_t l = lens[i] > b.out_cap ? 0u : lens[i];
+            off[(size_t)i + 1] = off[i] + (((unsigned long long)l + 15ull) & ~15ull);
+            if (alpha && transp[i]) {
+                const size_t bytes = ((size_t)total_bits[i] + 7) / 8;
+                alen[i] = bytes > alph_words * 4 ? 0u : (uint32_t)bytes;
+            }
+            aoff[(size_t)i + 1] = aoff[i] + (((unsigned long long)alen[i] + 15ull) & ~15ull);
+        }
+        const size_t img_total = (size_t)off[n], alph_total = (size_t)aoff[n];
+        uint8_t* d_pack = nullptr;
+        const size_t offs_b = round_up(((size_t)n + 1) * 8, (size_t)256);
+        if (cudaMallocAsync(&d_pack, offs_b + img_total + alph_total + 256, st) != cudaSuccess) {
+            cudaGetLastError();
+            rc = LP_ERR_CUDA;
+            break;
+        }
+        std::vector<uint8_t> home(img_total + alph_total);
+        auto* d_off = reinterpret_cast<unsigned long long*>(d_pack);
+        rc = compact_launch(b.out, b.out_cap, b.out_len, (uint32_t)b.out_cap, n, d_pack + offs_b, d_off, st);
+        if (!rc && img_total) cudaMemcpyAsync(home.data(), d_pack + offs_b, img_total, cudaMemcpyDeviceToHost, st);
+        if (!rc && alph_total) {
+            // (the packed alpha streams reuse d_head_bits for their byte lengths and the offset table: stream order
+            // puts both behind the kernels that read them)
+            cudaMemcpyAsync(d_head_bits, alen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st);
+            rc = compact_launch(reinterpret_cast<const uint8_t*>(d_aout), alph_words * 4, d_head_bits, (uint32_t)(alph_words * 4), n,
+                                d_pack + offs_b + img_total, d_off, st);
+            if (!rc) cudaMemcpyAsync(home.data() + img_total, d_pack + offs_b + img_total, alph_total, cudaMemcpyDeviceToHost, st);
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = LP_ERR_CUDA;
+        cudaFreeAsync(d_pack, st);
         for (int i = 0; i < n && !rc; i++) {
             WebpEncodedFrame& f = (*out)[i];
             f.width = width;
@@ -727,17 +797,12 @@ int webp_encode_lossy_batch(const uint8_t* d_frames, size_t img_stride, size_t r
             f.lossless = false;
             f.has_alpha = alpha && transp[i];
             if (lens[i] == 0 || lens[i] > b.out_cap) { f.image.clear(); continue; }  // caller reports the item
-            f.image.resize(lens[i]);
-            if (cudaMemcpyAsync(f.image.data(), b.out + (size_t)i * b.out_cap, lens[i], cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = LP_ERR_CUDA;
+            f.image.assign(home.data() + off[i], home.data() + off[i] + lens[i]);
             if (f.has_alpha) {
-                const size_t bytes = ((size_t)total_bits[i] + 7) / 8;
-                if (bytes == 0 || bytes > alph_words * 4) { f.image.clear(); continue; }
-                f.alph.resize(bytes);
-                if (cudaMemcpyAsync(f.alph.data(), reinterpret_cast<uint8_t*>(d_aout) + (size_t)i * alph_words * 4, bytes,
-                                    cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = LP_ERR_CUDA;
+                if (alen[i] == 0) { f.image.clear(); continue; }
+                f.alph.assign(home.data() + img_total + aoff[i], home.data() + img_total + aoff[i] + alen[i]);
             }
         }
-        if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = LP_ERR_CUDA;
     } while (0);
     cudaFreeAsync(scratch, st);
     return rc;

@@ -149,7 +149,6 @@ struct GifFrameDev {
 struct GifLzwShared {
     uint32_t link[4096];  // prefix code | last pixel << 12 | string length << 20
     uint8_t first[4096];
-    __align__(4) uint8_t stage[512 + 4];
 };
 
 // One frame's code stream, decoded by one warp, 32 codes per round.  giflib's DGifDecompressInput / DGifDecompressLine
@@ -169,7 +168,6 @@ struct GifLzwShared {
 // per code, most of it the L1 miss after the store in front.)
 __device__ __forceinline__ int gif_lzw_decode_frame(const GifFrameDev& f, GifLzwShared& sh) {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr uint32_t kStage = 512;
     const int lane = threadIdx.x & 31;
     const int clear = 1 << f.min_code, eof = clear + 1;
     int bits = f.min_code + 1, running = clear + 2, top = clear + 2;  // maxcode1 == 1 << bits throughout
@@ -261,50 +259,18 @@ __device__ __forceinline__ int gif_lzw_decode_frame(const GifFrameDev& f, GifLzw
             sh.first[top_j] = (uint8_t)pf;
         }
         __syncwarp();
-        // Strings go to a shared-memory stage first and leave as whole words: 32 lanes storing single bytes at 32
-        // unrelated global addresses cost one LSU pass EACH, and that -- not the chain walk -- bounded the first version
-        // of this loop.  Stage byte k holds pixel o + k - (o & 3), so stage words and global words line up.  A string
-        // that ends behind the stage is written straight to global memory, and so is everything behind it.
-        const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(f.indices) + o) & 3u);
-        const bool direct = lane < n && skew + (uint32_t)lsum > kStage;
+        // (Staging the strings in shared memory and storing whole words was measured: 15 % SLOWER.  The loop is bound by
+        // the latency of the dependent shared-memory load with ~2.5 warps per scheduler, not by the byte stores.)
         if (lane < n) {
+            uint32_t p = o + (uint32_t)(lsum - 1);  // last pixel of this string
             int c = code;
-            if (!direct) {
-                uint32_t p = skew + (uint32_t)(lsum - 1);  // last pixel of this string
-                while (c > eof) {
-                    const uint32_t l = sh.link[c];
-                    sh.stage[p] = (uint8_t)(l >> 12);
-                    p--;
-                    c = (int)(l & 0xFFFu);
-                }
-                sh.stage[p] = (uint8_t)c;
-            } else {
-                uint32_t p = o + (uint32_t)(lsum - 1);
-                while (c > eof) {
-                    const uint32_t l = sh.link[c];
-                    if (p < f.npix) f.indices[p] = (uint8_t)(l >> 12);
-                    p--;
-                    c = (int)(l & 0xFFFu);
-                }
-                if (p < f.npix) f.indices[p] = (uint8_t)c;
+            while (c > eof) {
+                const uint32_t l = sh.link[c];
+                if (p < f.npix) f.indices[p] = (uint8_t)(l >> 12);
+                p--;
+                c = (int)(l & 0xFFFu);
             }
-        }
-        __syncwarp();
-        {
-            const int fd = __ffs(__ballot_sync(FULL, direct)) - 1;
-            const int staged_codes = fd >= 0 ? fd : n;  // codes [0, staged_codes) sit in the stage
-            uint32_t nbytes = staged_codes ? (uint32_t)__shfl_sync(FULL, lsum, staged_codes - 1) : 0u;
-            nbytes = min(nbytes, room);
-            const uint32_t lo = skew, hi = skew + nbytes;  // stage bytes [lo, hi) -> pixels [o, o + nbytes)
-            uint8_t* gbase = f.indices + o - skew;         // 4-byte aligned (may point in front of the buffer; never dereferenced there)
-            for (uint32_t w = lane; w * 4 < hi; w += 32) {
-                const uint32_t b0 = w * 4;
-                if (b0 >= lo && b0 + 4 <= hi) {
-                    *reinterpret_cast<uint32_t*>(gbase + b0) = *reinterpret_cast<const uint32_t*>(sh.stage + b0);
-                } else {
-                    for (uint32_t b = max(b0, lo); b < min(b0 + 4, hi); b++) gbase[b] = sh.stage[b];
-                }
-            }
+            if (p < f.npix) f.indices[p] = (uint8_t)c;
         }
         __syncwarp();
         // state behind the last code of the round

@@ -46,15 +46,29 @@ LP_VP8_INL void be_put(BoolEnc& e, int bit, int prob) {
     } else {
         e.range = split;
     }
-    while (e.range < 128) {
-        e.range <<= 1;
-        if (e.bottom & 0x80000000u) be_carry(e);
-        e.bottom <<= 1;
-        if (!--e.bit_count) {
-            if (e.pos < e.cap) e.out[e.pos++] = (uint8_t)(e.bottom >> 24);
-            else e.overflow = 1;
-            e.bottom &= 0xffffffu;
-            e.bit_count = 8;
+    if (e.range < 128) {
+        // renormalise: `s` doublings.  All of them at once unless one of them would emit a byte or meet the carry
+        // flag on its way out of bit 31 (then the bit-by-bit form of RFC 6386 s.7.3 below, same result).
+#ifdef __CUDA_ARCH__
+        int s = __clz((int)e.range) - 24;
+#else
+        int s = __builtin_clz(e.range) - 24;
+#endif
+        e.range <<= s;
+        if (e.bit_count > s && (e.bottom >> (32 - s)) == 0) {
+            e.bottom <<= s;
+            e.bit_count -= s;
+            return;
+        }
+        while (s-- > 0) {
+            if (e.bottom & 0x80000000u) be_carry(e);
+            e.bottom <<= 1;
+            if (!--e.bit_count) {
+                if (e.pos < e.cap) e.out[e.pos++] = (uint8_t)(e.bottom >> 24);
+                else e.overflow = 1;
+                e.bottom &= 0xffffffu;
+                e.bit_count = 8;
+            }
         }
     }
 }

@@ -533,7 +533,7 @@ void opencv_mat_resize(const opencv_mat src, opencv_mat dst, int width, int heig
     Mat* s = static_cast<Mat*>(src);
     Mat* d = static_cast<Mat*>(dst);
     if (!s || !d || width < 1 || height < 1 || s->cols < 1 || s->rows < 1) return;  // (cv::resize asserts on these)
-    if (interpolation != CV_INTER_LINEAR && interpolation != CV_INTER_AREA) {
+    if (interpolation != CV_INTER_LINEAR && interpolation != CV_INTER_AREA && interpolation != CV_INTER_CUBIC) {
         fprintf(stderr, "[lilliput_b200] opencv_mat_resize: interpolation %d is not supported\n", interpolation);
         return;  // nothing touched: `dst` keeps its geometry and contents
     }

@@ -19,7 +19,7 @@ struct ResizeArgs {
     size_t dst_img_stride, dst_row_stride;
     int dst_w, dst_h;
     int n;
-    int interpolation;  // 1 = INTER_LINEAR, 3 = INTER_AREA
+    int interpolation;  // 1 = INTER_LINEAR, 2 = INTER_CUBIC, 3 = INTER_AREA
 };
 int resize_launch(const ResizeArgs& a, cudaStream_t st);
 

@@ -554,6 +554,158 @@ static void linear_tab(int ssize, int dsize, bool area_mode, bool clamp_ofs, std
     }
 }
 
+
+// ------------------------------------------------------------------ bicubic (INTER_CUBIC)
+//
+// cv::resize(INTER_CUBIC) as the reference's build answers it (ref opencv.cpp:20 exports the constant,
+// opencv.cpp:196-208 passes it through): the vendored IPP takes every u8 source of at least 4 x 4 and
+// returns the a = -0.75 kernel evaluated exactly (matched here in fp64: rows first, then columns,
+// replicated borders, round-half-even; equal to the binary to within 1 LSB on ~1e-5 of the samples, see
+// tests); smaller sources fall through to OpenCV's fixed-point code (11-bit coefficients, the first
+// width/16*16 samples of a row through the AVX2 fp32 form of the vertical pass), restated bit for bit.
+
+struct CubicParams {
+    const uint8_t* src;
+    size_t src_img_stride, src_row_stride;
+    uint8_t* dst;
+    size_t dst_img_stride, dst_row_stride;
+    int crop_x, crop_y, sw, sh, dw, dh, C;
+    const int* xofs;
+    const int* yofs;
+    const double* xa;  // [dw][4]   (exact form)
+    const double* yb;  // [dh][4]
+    const short* xs;   // [dw][4]   (fixed-point form)
+    const short* ys;   // [dh][4]
+    int fixed, nvec;
+};
+
+__global__ void resize_cubic_kernel(const CubicParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.dw * p.C) return;
+    const int dy = blockIdx.y, img = blockIdx.z;
+    const int dx = i / p.C, c = i % p.C;
+    const int sx = p.xofs[dx], sy = p.yofs[dy];
+    const uint8_t* base = p.src + (size_t)img * p.src_img_stride + (size_t)p.crop_x * p.C + c;
+    int col[4];
+    const uint8_t* R[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        col[k] = min(max(sx - 1 + k, 0), p.sw - 1) * p.C;
+        R[k] = base + (size_t)(p.crop_y + min(max(sy - 1 + k, 0), p.sh - 1)) * p.src_row_stride;
+    }
+    uint8_t out;
+    if (!p.fixed) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            double h = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) h = fma((double)R[k][col[j]], p.xa[4 * dx + j], h);
+            sum = fma(h, p.yb[4 * dy + k], sum);
+        }
+        const double r = rint(sum);
+        out = (uint8_t)(r < 0.0 ? 0.0 : r > 255.0 ? 255.0 : r);
+    } else {
+        int h[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            h[k] = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) h[k] += (int)R[k][col[j]] * (int)p.xs[4 * dx + j];
+        }
+        const short* b = p.ys + 4 * dy;
+        if (i < p.nvec) {
+            const float scale = 1.f / (2048.f * 2048.f);
+            float a = __fmul_rn((float)h[3], __fmul_rn((float)b[3], scale));
+            a = __fmaf_rn((float)h[2], __fmul_rn((float)b[2], scale), a);
+            a = __fmaf_rn((float)h[1], __fmul_rn((float)b[1], scale), a);
+            a = __fmaf_rn((float)h[0], __fmul_rn((float)b[0], scale), a);
+            out = sat_rne_u8(a);
+        } else {
+            const int v = (h[0] * b[0] + h[1] * b[1] + h[2] * b[2] + h[3] * b[3] + (1 << 21)) >> 22;
+            out = (uint8_t)min(max(v, 0), 255);
+        }
+    }
+    p.dst[(size_t)img * p.dst_img_stride + (size_t)dy * p.dst_row_stride + i] = out;
+}
+
+static void cubic_tab(int ssize, int dsize, std::vector<int>* ofs, std::vector<double>* cd, std::vector<short>* cs) {
+    const double scale = 1.0 / ((double)dsize / ssize);
+    ofs->resize(dsize);
+    cd->resize(4 * (size_t)dsize);
+    cs->resize(4 * (size_t)dsize);
+    for (int d = 0; d < dsize; d++) {
+        const double fd = (d + 0.5) * scale - 0.5;
+        {
+            const double A = -0.75, x = fd - std::floor(fd);
+            double* c = cd->data() + 4 * (size_t)d;
+            c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+            c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+            c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+            c[3] = 1.0 - c[0] - c[1] - c[2];
+        }
+        float f = (float)fd;
+        const int s = (int)std::floor(f);
+        f -= s;
+        (*ofs)[d] = s;  // floor of the fp32 position (OpenCV) == floor of the double one except on a rounding edge, where the weights carry it
+        {
+            // interpolateCubic in fp32 with the multiply-adds fused as the vendored build compiled them
+            const float A = -0.75f, x = f, t = x + 1.f, u = 1.f - x;
+            float c[4];
+            c[0] = fmaf(fmaf(fmaf(A, t, -5 * A), t, 8 * A), t, -4 * A);
+            c[1] = fmaf(fmaf(A + 2, x, -(A + 3)) * x, x, 1.f);
+            c[2] = fmaf(fmaf(A + 2, u, -(A + 3)) * u, u, 1.f);
+            c[3] = 1.f - c[0] - c[1] - c[2];
+            for (int k = 0; k < 4; k++)
+                (*cs)[4 * (size_t)d + k] = (short)std::min(std::max((int)lrintf(c[k] * 2048.f), -32768), 32767);
+        }
+    }
+}
+
+static int resize_cubic_launch(const ResizeArgs& a, cudaStream_t st) {
+    const int C = a.channels;
+    const bool fixed = a.crop_w < 4 || a.crop_h < 4;
+    std::vector<int> xo, yo;
+    std::vector<double> xd, yd;
+    std::vector<short> xs, ys;
+    cubic_tab(a.crop_w, a.dst_w, &xo, &xd, &xs);
+    cubic_tab(a.crop_h, a.dst_h, &yo, &yd, &ys);
+    if (!fixed) {  // the exact form takes its offsets from the double position
+        const double sxd = 1.0 / ((double)a.dst_w / a.crop_w), syd = 1.0 / ((double)a.dst_h / a.crop_h);
+        for (int d = 0; d < a.dst_w; d++) xo[d] = (int)std::floor((d + 0.5) * sxd - 0.5);
+        for (int d = 0; d < a.dst_h; d++) yo[d] = (int)std::floor((d + 0.5) * syd - 0.5);
+    }
+    const size_t nx = (size_t)a.dst_w, ny = (size_t)a.dst_h;
+    const size_t bytes = (nx + ny) * (sizeof(int) + 4 * sizeof(double) + 4 * sizeof(short));
+    uint8_t* dtab = nullptr;
+    LP_CUDA_OK(cudaMallocAsync(&dtab, bytes + 64, st));
+    std::vector<uint8_t> host(bytes);
+    size_t o = 0;
+    auto put = [&](const void* ptr, size_t n) {
+        memcpy(host.data() + o, ptr, n);
+        const size_t at = o;
+        o += n;
+        return at;
+    };
+    const size_t o_xa = put(xd.data(), 4 * nx * sizeof(double)), o_yb = put(yd.data(), 4 * ny * sizeof(double));
+    const size_t o_xo = put(xo.data(), nx * sizeof(int)), o_yo = put(yo.data(), ny * sizeof(int));
+    const size_t o_xs = put(xs.data(), 4 * nx * sizeof(short)), o_ys = put(ys.data(), 4 * ny * sizeof(short));
+    LP_CUDA_OK(cudaMemcpyAsync(dtab, host.data(), bytes, cudaMemcpyHostToDevice, st));
+    LP_CUDA_OK(cudaStreamSynchronize(st));  // `host` goes out of scope below
+    CubicParams p{a.src, a.src_img_stride, a.src_row_stride, a.dst, a.dst_img_stride, a.dst_row_stride,
+                  a.crop_x, a.crop_y, a.crop_w, a.crop_h, a.dst_w, a.dst_h, C,
+                  reinterpret_cast<const int*>(dtab + o_xo), reinterpret_cast<const int*>(dtab + o_yo),
+                  reinterpret_cast<const double*>(dtab + o_xa), reinterpret_cast<const double*>(dtab + o_yb),
+                  reinterpret_cast<const short*>(dtab + o_xs), reinterpret_cast<const short*>(dtab + o_ys),
+                  fixed ? 1 : 0, a.dst_w * C / 16 * 16};
+    dim3 grid(ceil_div(a.dst_w * C, 256), a.dst_h, a.n);
+    resize_cubic_kernel<<<grid, 256, 0, st>>>(p);
+    g_launches++;
+    LP_CUDA_OK(cudaGetLastError());
+    LP_CUDA_OK(cudaFreeAsync(dtab, st));
+    return LP_OK;
+}
+
 // ------------------------------------------------------------------ launcher
 
 static size_t area_smem_bytes(int slot_bytes) {
@@ -619,7 +771,7 @@ int resize_launch(const ResizeArgs& a, cudaStream_t st) {
     if (a.n <= 0) return LP_OK;
     if (a.crop_w < 1 || a.crop_h < 1 || a.dst_w < 1 || a.dst_h < 1) return LP_ERR_BAD_ARGUMENT;
     if (a.channels != 1 && a.channels != 3 && a.channels != 4) return LP_ERR_BAD_ARGUMENT;
-    if (a.interpolation != 1 && a.interpolation != 3) return LP_ERR_UNSUPPORTED;
+    if (a.interpolation != 1 && a.interpolation != 2 && a.interpolation != 3) return LP_ERR_UNSUPPORTED;
     const int C = a.channels;
     if (a.crop_w == a.dst_w && a.crop_h == a.dst_h) {  // cv::resize: same size is a copy
         LP_CUDA_OK(cudaMemcpy2DAsync(a.dst, a.dst_row_stride,
@@ -633,6 +785,7 @@ int resize_launch(const ResizeArgs& a, cudaStream_t st) {
                 a.src_row_stride, (size_t)a.dst_w * C, a.dst_h, cudaMemcpyDeviceToDevice, st));
         return LP_OK;
     }
+    if (a.interpolation == 2) return resize_cubic_launch(a, st);
     double scale_x = 1.0 / ((double)a.dst_w / a.crop_w), scale_y = 1.0 / ((double)a.dst_h / a.crop_h);
     int ix = (int)lrint(scale_x), iy = (int)lrint(scale_y);
     bool is_area_fast = std::fabs(scale_x - ix) < DBL_EPSILON && std::fabs(scale_y - iy) < DBL_EPSILON;

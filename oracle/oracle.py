@@ -13,7 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
-INTER_LINEAR, INTER_AREA = 1, 3
+INTER_LINEAR, INTER_CUBIC, INTER_AREA = 1, 2, 3
 
 
 def build(force: bool = False) -> None:

@@ -13,8 +13,14 @@
  *   - both scales integer         -> resizeAreaFast_Invoker<uchar,int>
  *   - both scales >= 1            -> ResizeArea_Invoker<uchar,float> (fp32 FMA, RNE)
  *   - otherwise / INTER_LINEAR    -> fixed-point bilinear (11-bit coefficients)
- * Pinned against oracle/_ref in tests/test_oracle_resize.py and against
- * tests/golden/resize_*.npz.
+ *   - INTER_CUBIC (exported by ref opencv.cpp:20, never passed by the Go side): sources under 4 px
+ *     on an axis -> OpenCV's fixed-point bicubic (HResizeCubic<uchar,int,short> + VResizeCubic, the
+ *     first width/16*16 samples of a row through the AVX2 float form); anything larger is taken by
+ *     the vendored IPP (ippiResizeCubic_8u, B=0 C=0.75), a binary whose result equals the exact
+ *     (double) evaluation of the a=-0.75 kernel to within 1 LSB on ~2e-5 of the samples
+ *     (tests/test_oracle_live_reference.py states the bound).
+ * Pinned against oracle/_ref in tests/test_oracle_live_reference.py and against
+ * tests/golden/golden.npz.
  */
 #include <float.h>
 #include <math.h>
@@ -192,13 +198,136 @@ static void resize_linear(const uint8_t* src, size_t sstep, int cn, int sw, int 
     free(xo); free(xa); free(yo); free(yb);
 }
 
+
+/* ---- INTER_CUBIC --------------------------------------------------------------------------- */
+
+static void cubic_coeffs_f(float x, float* c) {
+    /* interpolateCubic, A = -0.75, fp32 -- with the multiply-adds fused the way the vendored build
+     * (gcc, x86-64-v3, -ffp-contract=fast) compiled it; found by comparing against oracle/_ref */
+    const float A = -0.75f;
+    const float t = x + 1.f, u = 1.f - x;
+    c[0] = fmaf(fmaf(fmaf(A, t, -5 * A), t, 8 * A), t, -4 * A);
+    c[1] = fmaf(fmaf(A + 2, x, -(A + 3)) * x, x, 1.f);
+    c[2] = fmaf(fmaf(A + 2, u, -(A + 3)) * u, u, 1.f);
+    c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+static void cubic_coeffs_d(double x, double* c) {
+    const double A = -0.75;
+    c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    c[3] = 1.0 - c[0] - c[1] - c[2];
+}
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+/* OpenCV's own bicubic (resizeGeneric_ with HResizeCubic<uchar,int,short>, VResizeCubic<...,
+ * FixedPtCast<int,uchar,22>, VResizeCubicVec_32s8u>): the path cv::resize takes when IPP declines
+ * (a source under 4 px on an axis). */
+static void resize_cubic_fixed(const uint8_t* src, size_t sstep, int cn, int sw, int sh, uint8_t* dst,
+                               size_t dstep, int dw, int dh) {
+    double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+    int* xo = malloc(sizeof(int) * dw);
+    short* xa = malloc(sizeof(short) * 4 * dw);
+    for (int dx = 0; dx < dw; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5), c[4];
+        int sx = (int)floorf(fx);
+        fx -= sx;
+        cubic_coeffs_f(fx, c);
+        xo[dx] = sx;
+        for (int k = 0; k < 4; k++) xa[4 * dx + k] = (short)clampi((int)lrintf(c[k] * 2048.f), -32768, 32767);
+    }
+    int* H = malloc(sizeof(int) * (size_t)sh * dw * cn); /* horizontal pass of every source row */
+    for (int y = 0; y < sh; y++) {
+        const uint8_t* S = src + (size_t)y * sstep;
+        for (int dx = 0; dx < dw; dx++)
+            for (int c = 0; c < cn; c++) {
+                int v = 0;
+                for (int j = 0; j < 4; j++) v += S[clampi(xo[dx] - 1 + j, 0, sw - 1) * cn + c] * xa[4 * dx + j];
+                H[((size_t)y * dw + dx) * cn + c] = v;
+            }
+    }
+    const int W = dw * cn, nvec = W / 16 * 16;
+    const float scale = 1.f / (2048.f * 2048.f);
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5), c[4];
+        int sy = (int)floorf(fy);
+        fy -= sy;
+        cubic_coeffs_f(fy, c);
+        short b[4];
+        const int* R[4];
+        for (int k = 0; k < 4; k++) {
+            b[k] = (short)clampi((int)lrintf(c[k] * 2048.f), -32768, 32767);
+            R[k] = H + (size_t)clampi(sy - 1 + k, 0, sh - 1) * W;
+        }
+        uint8_t* D = dst + (size_t)dy * dstep;
+        for (int x = 0; x < W; x++) {
+            if (x < nvec) { /* v_muladd chain in fp32, v_round, saturating pack */
+                float a = (float)R[3][x] * (b[3] * scale);
+                a = fmaf((float)R[2][x], b[2] * scale, a);
+                a = fmaf((float)R[1][x], b[1] * scale, a);
+                a = fmaf((float)R[0][x], b[0] * scale, a);
+                D[x] = sat_u8_from_float(a);
+            } else {
+                int v = R[0][x] * b[0] + R[1][x] * b[1] + R[2][x] * b[2] + R[3][x] * b[3];
+                D[x] = sat_u8_from_int((v + (1 << 21)) >> 22);
+            }
+        }
+    }
+    free(xo); free(xa); free(H);
+}
+
+/* The a = -0.75 bicubic evaluated in double, rows first then columns, replicated borders, RNE:
+ * what the vendored IPP returns up to the bound stated in the header. */
+static void resize_cubic_exact(const uint8_t* src, size_t sstep, int cn, int sw, int sh, uint8_t* dst,
+                               size_t dstep, int dw, int dh) {
+    double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+    int* xo = malloc(sizeof(int) * dw);
+    double* xa = malloc(sizeof(double) * 4 * dw);
+    for (int dx = 0; dx < dw; dx++) {
+        double fx = (dx + 0.5) * scale_x - 0.5;
+        int sx = (int)floor(fx);
+        xo[dx] = sx;
+        cubic_coeffs_d(fx - sx, xa + 4 * dx);
+    }
+    for (int dy = 0; dy < dh; dy++) {
+        double fy = (dy + 0.5) * scale_y - 0.5, b[4];
+        int sy = (int)floor(fy);
+        cubic_coeffs_d(fy - sy, b);
+        const uint8_t* R[4];
+        for (int k = 0; k < 4; k++) R[k] = src + (size_t)clampi(sy - 1 + k, 0, sh - 1) * sstep;
+        uint8_t* D = dst + (size_t)dy * dstep;
+        for (int dx = 0; dx < dw; dx++)
+            for (int c = 0; c < cn; c++) {
+                double sum = 0.0;
+                for (int k = 0; k < 4; k++) {
+                    double h = 0.0;
+                    for (int j = 0; j < 4; j++)
+                        h = fma((double)R[k][clampi(xo[dx] - 1 + j, 0, sw - 1) * cn + c], xa[4 * dx + j], h);
+                    sum = fma(h, b[k], sum);
+                }
+                double r = rint(sum);
+                D[dx * cn + c] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+            }
+    }
+    free(xo); free(xa);
+}
+
 int oracle_resize(const uint8_t* src, size_t sstep, int cn, int cx, int cy, int sw, int sh,
                   uint8_t* dst, size_t dstep, int dw, int dh, int interpolation) {
-    if (interpolation != ORACLE_INTER_AREA && interpolation != ORACLE_INTER_LINEAR) return -1;
+    if (interpolation != ORACLE_INTER_AREA && interpolation != ORACLE_INTER_LINEAR && interpolation != ORACLE_INTER_CUBIC) return -1;
     if (sw < 1 || sh < 1 || dw < 1 || dh < 1) return -1;
     const uint8_t* s0 = src + (size_t)cy * sstep + (size_t)cx * cn;
     if (sw == dw && sh == dh) { /* cv::resize: same size is a plain copy */
         for (int y = 0; y < dh; y++) memcpy(dst + (size_t)y * dstep, s0 + (size_t)y * sstep, (size_t)dw * cn);
+        return 0;
+    }
+    if (interpolation == ORACLE_INTER_CUBIC) {
+        if (sw < 4 || sh < 4)
+            resize_cubic_fixed(s0, sstep, cn, sw, sh, dst, dstep, dw, dh);
+        else
+            resize_cubic_exact(s0, sstep, cn, sw, sh, dst, dstep, dw, dh);
         return 0;
     }
     double inv_x = (double)dw / sw, inv_y = (double)dh / sh;

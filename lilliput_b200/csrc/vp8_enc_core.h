@@ -264,6 +264,125 @@ LP_VP8_FN int put_coeffs(BoolEnc& e, const uint8_t* proba, int type, int ctx, in
     return 1;
 }
 
+// ---- probability adaptation (RFC 6386 s.13.4: the frame header may replace any of the 4 x 8 x 3 x 11 coefficient
+// probabilities) and the per-macroblock skip flag (s.9.11) ------------------------------------------------------------
+// 256 * -log2(p / 256): the cost, in 1/256 bit, of coding the likelier-with-probability-p/256 branch
+LP_VP8_TABLE uint16_t kVp8EntropyCost[256] = {
+    2048, 2048, 1792, 1642, 1536, 1454, 1386, 1329, 1280, 1236, 1198, 1162, 1130, 1101, 1073, 1048,
+    1024, 1002,  980,  961,  942,  924,  906,  890,  874,  859,  845,  831,  817,  804,  792,  780,
+     768,  757,  746,  735,  724,  714,  705,  695,  686,  676,  668,  659,  650,  642,  634,  626,
+     618,  611,  603,  596,  589,  582,  575,  568,  561,  555,  548,  542,  536,  530,  524,  518,
+     512,  506,  501,  495,  490,  484,  479,  474,  468,  463,  458,  453,  449,  444,  439,  434,
+     430,  425,  420,  416,  412,  407,  403,  399,  394,  390,  386,  382,  378,  374,  370,  366,
+     362,  358,  355,  351,  347,  343,  340,  336,  333,  329,  326,  322,  319,  315,  312,  309,
+     305,  302,  299,  296,  292,  289,  286,  283,  280,  277,  274,  271,  268,  265,  262,  259,
+     256,  253,  250,  247,  245,  242,  239,  236,  234,  231,  228,  226,  223,  220,  218,  215,
+     212,  210,  207,  205,  202,  200,  197,  195,  193,  190,  188,  185,  183,  181,  178,  176,
+     174,  171,  169,  167,  164,  162,  160,  158,  156,  153,  151,  149,  147,  145,  143,  140,
+     138,  136,  134,  132,  130,  128,  126,  124,  122,  120,  118,  116,  114,  112,  110,  108,
+     106,  104,  102,  101,   99,   97,   95,   93,   91,   89,   87,   86,   84,   82,   80,   78,
+      77,   75,   73,   71,   70,   68,   66,   64,   63,   61,   59,   58,   56,   54,   53,   51,
+      49,   48,   46,   44,   43,   41,   40,   38,   36,   35,   33,   32,   30,   28,   27,   25,
+      24,   22,   21,   19,   18,   16,   15,   13,   12,   10,    9,    7,    6,    4,    3,    1,
+};
+
+constexpr int kNumProbas = 4 * 8 * 3 * 11;
+// Per-frame side memory of the bitstream pass (`aux`, kAuxBytes, 4-byte aligned, zeroed by the encoder itself):
+//   uint32 stats[kNumProbas][2]  how often each adaptive branch of the token tree coded a 0 / a 1
+//   uint32 counts[2]             macroblocks, macroblocks without a non-zero level
+//   uint8  proba[kNumProbas]     the probabilities the frame is coded with
+//   uint8  update[kNumProbas]    1 = the header replaces the default by proba[i]
+//   uint8  skip_proba, use_skip
+constexpr size_t kAuxStatsOff = 0, kAuxCountsOff = (size_t)kNumProbas * 8, kAuxProbaOff = kAuxCountsOff + 8,
+                 kAuxUpdateOff = kAuxProbaOff + kNumProbas, kAuxSkipOff = kAuxUpdateOff + kNumProbas,
+                 kAuxBytes = (kAuxSkipOff + 2 + 255) / 256 * 256;
+
+LP_VP8_INL void stat_add(uint32_t* stats, int idx, int bit) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(stats + 2 * idx + bit, 1u);  // the lanes of a warp walk different partitions of the same frame
+#else
+    stats[2 * idx + bit]++;
+#endif
+}
+
+// put_coeffs with the coder replaced by counters: which adaptive branches the block takes.  (The fixed-probability
+// branches -- extra bits, signs -- cannot be adapted and are not counted.)
+LP_VP8_FN int record_coeffs(uint32_t* stats, int type, int ctx, int first, const int16_t* levels) {
+    const uint8_t bands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
+    const uint8_t zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+    const int tb = type * (8 * 3 * 11);
+    const int last = last_nonzero(levels, first);
+    int n = first;
+    int p = tb + (bands[n] * 3 + ctx) * 11;
+    if (last < 0) {
+        stat_add(stats, p + 0, 0);
+        return 0;
+    }
+    stat_add(stats, p + 0, 1);
+    while (n < 16) {
+        const int c = levels[zigzag[n]];
+        const int v = c < 0 ? -c : c;
+        if (!v) {
+            stat_add(stats, p + 1, 0);
+            p = tb + (bands[++n] * 3 + 0) * 11;
+            continue;
+        }
+        stat_add(stats, p + 1, 1);
+        int next_ctx;
+        if (v == 1) {
+            stat_add(stats, p + 2, 0);
+            next_ctx = 1;
+        } else {
+            stat_add(stats, p + 2, 1);
+            next_ctx = 2;
+            if (v <= 4) {  // the tree of put_large_value
+                stat_add(stats, p + 3, 0);
+                stat_add(stats, p + 4, v != 2);
+                if (v != 2) stat_add(stats, p + 5, v == 4);
+            } else if (v <= 10) {
+                stat_add(stats, p + 3, 1);
+                stat_add(stats, p + 6, 0);
+                stat_add(stats, p + 7, v > 6);
+            } else {
+                stat_add(stats, p + 3, 1);
+                stat_add(stats, p + 6, 1);
+                const int cat = v < 19 ? 0 : v < 35 ? 1 : v < 67 ? 2 : 3;
+                stat_add(stats, p + 8, cat >> 1);
+                stat_add(stats, p + 9 + (cat >> 1), cat & 1);
+            }
+        }
+        if (++n == 16) break;
+        p = tb + (bands[n] * 3 + next_ctx) * 11;
+        if (n > last) {
+            stat_add(stats, p + 0, 0);
+            break;
+        }
+        stat_add(stats, p + 0, 1);
+    }
+    return 1;
+}
+
+// all 25 blocks of a macroblock are zero: the decoder can be told to skip its tokens
+LP_VP8_INL int mb_is_skippable(const int16_t* lv) {
+    uint32_t any = 0;
+    for (int k = 0; k < 25; k++) any |= nonzero_mask(lv + k * 16);
+    return any == 0;
+}
+
+// One entry of the probability table from its counters: the frame's own frequency, adopted when the bits it saves over
+// the default pay for the 8 bits (+ flag) that announce it.  `c0` / `c1` = times the branch coded 0 / 1.
+LP_VP8_FN void decide_proba(uint32_t c0, uint32_t c1, int old_p, int update_p, uint8_t* proba, uint8_t* update) {
+    const uint32_t total = c0 + c1;
+    int new_p = total ? (int)(255u - (uint32_t)(((uint64_t)c1 * 255u) / total)) : 255;
+    if (new_p < 1) new_p = 1;
+    const uint64_t old_cost = (uint64_t)c0 * kVp8EntropyCost[old_p] + (uint64_t)c1 * kVp8EntropyCost[255 - old_p] + kVp8EntropyCost[update_p];
+    const uint64_t new_cost = (uint64_t)c0 * kVp8EntropyCost[new_p] + (uint64_t)c1 * kVp8EntropyCost[255 - new_p] +
+                              kVp8EntropyCost[255 - update_p] + 8 * 256;
+    const bool use_new = new_cost < old_cost;
+    *proba = (uint8_t)(use_new ? new_p : old_p);
+    *update = use_new ? 1 : 0;
+}
+
 // ---- colour conversion (BT.601 limited range, 16.16 fixed point like libwebp's importer) -----
 LP_VP8_INL int rgb_to_y(int r, int g, int b) { return (16839 * r + 33059 * g + 6420 * b + (16 << 16) + (1 << 15)) >> 16; }
 // r, g, b are SUMS over a 2x2 block
@@ -442,8 +561,13 @@ LP_VP8_HD size_t partition_scratch_cap(const Params& P, int part, int nparts) {
     return (size_t)partition_rows(P, part, nparts) * (size_t)P.mb_w * 2048 + 64;
 }
 
-// first partition: frame header + per-macroblock modes.  Returns its size, 0 when it does not fit.
-LP_VP8_FN size_t write_part0(const Params& P, const Buffers& B, uint8_t* part0, size_t part0_cap) {
+// aux accessors
+LP_VP8_INL uint32_t* aux_stats(uint8_t* aux) { return reinterpret_cast<uint32_t*>(aux + kAuxStatsOff); }
+LP_VP8_INL uint32_t* aux_counts(uint8_t* aux) { return reinterpret_cast<uint32_t*>(aux + kAuxCountsOff); }
+
+// first partition: frame header (with the probability updates and the skip probability decided from the statistics
+// in `aux`) + per-macroblock skip flag and modes.  Returns its size, 0 when it does not fit.
+LP_VP8_FN size_t write_part0(const Params& P, const Buffers& B, const uint8_t* aux, uint8_t* part0, size_t part0_cap) {
     BoolEnc h;
     be_init(h, part0, part0_cap);
     be_put_bits(h, 0, 1);  // colour space
@@ -459,11 +583,19 @@ LP_VP8_FN size_t write_part0(const Params& P, const Buffers& B, uint8_t* part0, 
     be_put_bits(h, 0, 1);                               // refresh_entropy_probs
     {
         const uint8_t* upd = &kVp8CoeffUpdateProba[0][0][0][0];
-        for (int i = 0; i < 4 * 8 * 3 * 11; i++) be_put(h, 0, upd[i]);  // keep the default probabilities
+        const uint8_t* proba = aux + kAuxProbaOff;
+        const uint8_t* update = aux + kAuxUpdateOff;
+        for (int i = 0; i < kNumProbas; i++) {
+            be_put(h, update[i], upd[i]);
+            if (update[i]) be_put_bits(h, proba[i], 8);
+        }
     }
-    be_put_bits(h, 0, 1);  // mb_no_coeff_skip = 0: no per-macroblock skip flag
+    const int use_skip = aux[kAuxSkipOff + 1], skip_p = aux[kAuxSkipOff];
+    be_put_bits(h, (uint32_t)use_skip, 1);  // mb_no_coeff_skip
+    if (use_skip) be_put_bits(h, (uint32_t)skip_p, 8);
     for (int i = 0; i < P.mb_w * P.mb_h; i++) {
         const int ymode = B.modes[i * 2], uvmode = B.modes[i * 2 + 1];
+        if (use_skip) be_put(h, mb_is_skippable(B.levels + (size_t)i * 25 * 16), skip_p);
         be_put(h, 1, 145);  // not 4x4
         if (ymode == vp8::TM_PRED || ymode == vp8::H_PRED) {
             be_put(h, 1, 156);
@@ -491,15 +623,32 @@ LP_VP8_FN size_t write_part0(const Params& P, const Buffers& B, uint8_t* part0, 
 // 1 when a block has a non-zero level at or after `first` (what put_coeffs returns for it)
 LP_VP8_INL int block_nz(const int16_t* levels, int first) { return (nonzero_mask(levels) >> first) != 0; }
 
-// token partition `part` of `nparts`: rows part, part + nparts, ...  Returns its size, 0 when it does not fit.
-LP_VP8_FN size_t write_partition(const Params& P, const Buffers& B, int part, int nparts, uint8_t* buf, size_t cap) {
+// The macroblocks of token partition `part` (rows part, part + nparts, ...) in the decoder's order and contexts.
+// CODE = false: count the adaptive branches into aux (the statistics the probabilities are decided from) and the
+// skippable macroblocks; CODE = true: write the partition with the probabilities in aux.  A macroblock without any
+// non-zero level has no tokens when the frame uses skip flags, and leaves "nothing non-zero" behind as context --
+// which is what its levels say anyway, so the contexts need no special case.
+template <bool CODE>
+LP_VP8_FN size_t walk_partition(const Params& P, const Buffers& B, int part, int nparts, uint8_t* aux, uint8_t* buf, size_t cap) {
     BoolEnc t;
-    be_init(t, buf, cap);
-    const uint8_t* proba = &kVp8CoeffProba0[0][0][0][0];
+    if (CODE) be_init(t, buf, cap);
+    const uint8_t* proba = aux + kAuxProbaOff;
+    uint32_t* stats = aux_stats(aux);
+    const int use_skip = CODE ? aux[kAuxSkipOff + 1] : 0;
+    uint32_t n_mb = 0, n_skip = 0;
     for (int mb_y = part; mb_y < P.mb_h; mb_y += nparts) {
         uint8_t left_nz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int mb_x = 0; mb_x < P.mb_w; mb_x++) {
             const int16_t* lv = B.levels + ((size_t)mb_y * P.mb_w + mb_x) * 25 * 16;
+            const int skippable = mb_is_skippable(lv);
+            n_mb++;
+            n_skip += (uint32_t)skippable;
+            if (skippable && (use_skip || !CODE)) {
+                // statistics pass: assume the frame WILL use skip flags when it has skippable macroblocks (decided
+                // in finish_statistics from the same counts), so their would-be tokens are not counted
+                for (int k = 0; k < 9; k++) left_nz[k] = 0;
+                continue;
+            }
             uint8_t tnz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (mb_y > 0) {  // bottom blocks of the macroblock above
                 const int16_t* up = lv - (size_t)P.mb_w * 25 * 16;
@@ -521,13 +670,43 @@ LP_VP8_FN size_t write_partition(const Params& P, const Buffers& B, int part, in
                     const int c = k - 16;
                     type = 2; ti = 4 + (c >> 2) * 2 + (c & 1); li = 4 + (c >> 2) * 2 + ((c >> 1) & 1); blk = lv + k * 16;
                 }
-                const int nz = put_coeffs(t, proba, type, tnz[ti] + left_nz[li], first, blk);
+                const int nz = CODE ? put_coeffs(t, proba, type, tnz[ti] + left_nz[li], first, blk)
+                                    : record_coeffs(stats, type, tnz[ti] + left_nz[li], first, blk);
                 tnz[ti] = left_nz[li] = (uint8_t)nz;
             }
         }
     }
+    if (!CODE) {
+#ifdef __CUDA_ARCH__
+        atomicAdd(aux_counts(aux) + 0, n_mb);
+        atomicAdd(aux_counts(aux) + 1, n_skip);
+#else
+        aux_counts(aux)[0] += n_mb;
+        aux_counts(aux)[1] += n_skip;
+#endif
+        return 0;
+    }
     be_flush(t);
     return t.overflow ? 0 : t.pos;
+}
+
+// entries [first, first + step, ...) of the probability table from the statistics; entry 0's caller also settles the
+// skip probability.  (The device spreads the 1056 entries over the 32 lanes of the frame's warp.)
+LP_VP8_FN void finish_statistics(uint8_t* aux, int first, int step) {
+    const uint32_t* stats = aux_stats(aux);
+    const uint8_t* def = &kVp8CoeffProba0[0][0][0][0];
+    const uint8_t* upd = &kVp8CoeffUpdateProba[0][0][0][0];
+    for (int i = first; i < kNumProbas; i += step)
+        decide_proba(stats[2 * i], stats[2 * i + 1], def[i], upd[i], aux + kAuxProbaOff + i, aux + kAuxUpdateOff + i);
+    if (first == 0) {
+        const uint32_t n_mb = aux_counts(aux)[0], n_skip = aux_counts(aux)[1];
+        // P(not skipped) in 1/256, as the decoder reads it; a flag per macroblock only pays when some are skipped
+        int sp = n_mb ? (int)(((uint64_t)(n_mb - n_skip) * 255u) / n_mb) : 255;
+        if (sp < 1) sp = 1;
+        if (sp > 255) sp = 255;
+        aux[kAuxSkipOff] = (uint8_t)sp;
+        aux[kAuxSkipOff + 1] = n_skip > 0 ? 1 : 0;
+    }
 }
 
 // frame tag + start code + dimensions + (behind the first partition) the partition size table.  `sizes[nparts]`.
@@ -562,17 +741,19 @@ LP_VP8_FN size_t write_frame_header(const Params& P, size_t part0_len, const siz
     return total;
 }
 
-// part0 / tokens are scratch areas; `out` receives the "VP8 " chunk payload.  Returns the payload size, 0 when it does
-// not fit.  (top_nz: unused, kept for the callers' layouts.)
+// part0 / tokens / aux (kAuxBytes, 4-byte aligned) are scratch areas; `out` receives the "VP8 " chunk payload.  Returns
+// the payload size, 0 when it does not fit.
 LP_VP8_FN size_t write_bitstream(const Params& P, const Buffers& B, uint8_t* part0, size_t part0_cap, uint8_t* tokens,
-                                 size_t tokens_cap, uint8_t* top_nz, uint8_t* out, size_t out_cap) {
-    (void)top_nz;
+                                 size_t tokens_cap, uint8_t* aux, uint8_t* out, size_t out_cap) {
     const int nparts = 1 << log2_partitions(P);
     if (partition_scratch_off(P, nparts - 1, nparts) + partition_scratch_cap(P, nparts - 1, nparts) > tokens_cap) return 0;
-    const size_t part0_len = write_part0(P, B, part0, part0_cap);
+    for (size_t i = 0; i < kAuxBytes; i++) aux[i] = 0;
+    for (int q = 0; q < nparts; q++) walk_partition<false>(P, B, q, nparts, aux, nullptr, 0);
+    finish_statistics(aux, 0, 1);
+    const size_t part0_len = write_part0(P, B, aux, part0, part0_cap);
     size_t sizes[8];
     for (int q = 0; q < nparts; q++)
-        sizes[q] = write_partition(P, B, q, nparts, tokens + partition_scratch_off(P, q, nparts), partition_scratch_cap(P, q, nparts));
+        sizes[q] = walk_partition<true>(P, B, q, nparts, aux, tokens + partition_scratch_off(P, q, nparts), partition_scratch_cap(P, q, nparts));
     const size_t total = write_frame_header(P, part0_len, sizes, nparts, out, out_cap);
     if (!total) return 0;
     for (size_t i = 0; i < part0_len; i++) out[10 + i] = part0[i];

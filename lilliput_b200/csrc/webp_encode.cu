@@ -369,21 +369,29 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
         }
 }
 
-// The bitstream pass on a warp: lane q codes token partition q, lane `nparts` the first partition, then all lanes
-// copy the pieces into place.  Same bytes as vp8enc::write_bitstream (the serial composition of the same pieces).
+// The bitstream pass on a warp: lanes 0..nparts-1 first count the token-tree branches of their partition (the statistics
+// the frame's probabilities are decided from), all 32 lanes settle the 1056 probabilities, then lane q codes token
+// partition q and lane `nparts` the first partition, and all lanes copy the pieces into place.  Same bytes as
+// vp8enc::write_bitstream (the serial composition of the same pieces).
 __device__ size_t vp8_write_bitstream_warp(const vp8enc::Params& P, const vp8enc::Buffers& B, uint8_t* part0, size_t part0_cap,
-                                           uint8_t* tokens, size_t tokens_cap, uint8_t* out, size_t out_cap) {
+                                           uint8_t* tokens, size_t tokens_cap, uint8_t* aux, uint8_t* out, size_t out_cap) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int nparts = 1 << vp8enc::log2_partitions(P);
     if (vp8enc::partition_scratch_off(P, nparts - 1, nparts) + vp8enc::partition_scratch_cap(P, nparts - 1, nparts) > tokens_cap)
         return 0;
+    for (size_t i = lane; i < vp8enc::kAuxBytes / 4; i += 32) reinterpret_cast<uint32_t*>(aux)[i] = 0;
+    __syncwarp();
+    if (lane < nparts) vp8enc::walk_partition<false>(P, B, lane, nparts, aux, nullptr, 0);
+    __syncwarp();
+    vp8enc::finish_statistics(aux, lane, 32);
+    __syncwarp();
     unsigned long long mine = 0;
     if (lane < nparts)
-        mine = vp8enc::write_partition(P, B, lane, nparts, tokens + vp8enc::partition_scratch_off(P, lane, nparts),
-                                       vp8enc::partition_scratch_cap(P, lane, nparts));
+        mine = vp8enc::walk_partition<true>(P, B, lane, nparts, aux, tokens + vp8enc::partition_scratch_off(P, lane, nparts),
+                                            vp8enc::partition_scratch_cap(P, lane, nparts));
     else if (lane == nparts)
-        mine = vp8enc::write_part0(P, B, part0, part0_cap);
+        mine = vp8enc::write_part0(P, B, aux, part0, part0_cap);
     __syncwarp();
     const size_t part0_len = (size_t)__shfl_sync(FULL, mine, nparts);
     size_t sizes[8];
@@ -409,7 +417,7 @@ __device__ size_t vp8_write_bitstream_warp(const vp8enc::Params& P, const vp8enc
 struct Vp8EncJob {
     vp8enc::Params P;
     vp8enc::Buffers B;
-    uint8_t *part0, *tokens, *top_nz, *out;
+    uint8_t *part0, *tokens, *aux, *out;
     size_t part0_cap, tokens_cap, out_cap;
     size_t* out_len;
 };
@@ -418,7 +426,7 @@ __global__ void __launch_bounds__(32) vp8_encode_kernel(Vp8EncJob j) {
     __shared__ Vp8WarpBuf wb;
     if (j.P.filter_level < 0) j.P.filter_level = vp8enc::filter_level_for_q(j.P.q);
     vp8_analyse_warp(j.P, j.B, wb);
-    const size_t n = vp8_write_bitstream_warp(j.P, j.B, j.part0, j.part0_cap, j.tokens, j.tokens_cap, j.out, j.out_cap);
+    const size_t n = vp8_write_bitstream_warp(j.P, j.B, j.part0, j.part0_cap, j.tokens, j.tokens_cap, j.aux, j.out, j.out_cap);
     if (threadIdx.x == 0) *j.out_len = n;
 }
 
@@ -438,9 +446,9 @@ static int vp8_encode_dev(const uint8_t* d_frame, size_t step, int width, int he
     j.part0_cap = round_up(nmb * 2 + 4096, (size_t)256);
     j.tokens_cap = round_up(nmb * 2048 + 4096, (size_t)256);
     j.out_cap = 16 + j.part0_cap + j.tokens_cap;
-    const size_t topnz_b = round_up((size_t)j.P.mb_w * 9, (size_t)256);
+    const size_t aux_b = vp8enc::kAuxBytes;  // statistics + probabilities of the bitstream pass (vp8_enc_core.h)
     uint8_t* scratch = nullptr;
-    LP_CUDA_OK(cudaMallocAsync(&scratch, 256 + 2 * planes_b + levels_b + modes_b + j.part0_cap + j.tokens_cap + topnz_b + j.out_cap, st));
+    LP_CUDA_OK(cudaMallocAsync(&scratch, 256 + 2 * planes_b + levels_b + modes_b + j.part0_cap + j.tokens_cap + aux_b + j.out_cap, st));
     uint8_t* p = scratch;
     j.out_len = reinterpret_cast<size_t*>(p);
     p += 256;
@@ -462,8 +470,8 @@ static int vp8_encode_dev(const uint8_t* d_frame, size_t step, int width, int he
     p += j.part0_cap;
     j.tokens = p;
     p += j.tokens_cap;
-    j.top_nz = p;
-    p += topnz_b;
+    j.aux = p;
+    p += aux_b;
     j.out = p;
     dim3 grid(ceil_div(ys / 2, 128), yh / 2);
     vp8_planes_kernel<<<grid, 128, 0, st>>>(d_frame, step, channels, width, height, ys, yh, src, src + ypl, src + ypl + ypl / 4);
@@ -515,7 +523,7 @@ struct Vp8EncBatch {
     vp8enc::Params P;       // shared geometry / quantiser
     uint8_t* scratch;       // per-frame regions, `stride` apart
     size_t stride;
-    size_t off_src, off_rec, off_levels, off_modes, off_part0, off_tokens, off_topnz;
+    size_t off_src, off_rec, off_levels, off_modes, off_part0, off_tokens, off_aux;
     size_t part0_cap, tokens_cap;
     uint8_t* out;           // n * out_cap
     size_t out_cap;
@@ -543,7 +551,7 @@ __global__ void __launch_bounds__(kVp8EncWarps * 32) vp8_encode_batch_kernel(Vp8
     B.modes = base + b.off_modes;
     vp8_analyse_warp(P, B, wbs[threadIdx.x >> 5]);
     const size_t n = vp8_write_bitstream_warp(P, B, base + b.off_part0, b.part0_cap, base + b.off_tokens, b.tokens_cap,
-                                              b.out + (size_t)f * b.out_cap, b.out_cap);
+                                              base + b.off_aux, b.out + (size_t)f * b.out_cap, b.out_cap);
     if ((threadIdx.x & 31) == 0) b.out_len[f] = (uint32_t)n;
 }
 
@@ -656,15 +664,15 @@ int webp_encode_lossy_batch(const uint8_t* d_frames, size_t img_stride, size_t r
     const size_t levels_b = round_up(nmb * 25 * 16 * 2, (size_t)256), modes_b = round_up(nmb * 2, (size_t)256);
     b.part0_cap = round_up(nmb * 2 + 4096, (size_t)256);
     b.tokens_cap = round_up(nmb * 2048 + 4096, (size_t)256);
-    const size_t topnz_b = round_up((size_t)b.P.mb_w * 9, (size_t)256);
+    const size_t aux_b = vp8enc::kAuxBytes;  // statistics + probabilities of the bitstream pass (vp8_enc_core.h)
     b.off_src = 0;
     b.off_rec = planes_b;
     b.off_levels = 2 * planes_b;
     b.off_modes = b.off_levels + levels_b;
     b.off_part0 = b.off_modes + modes_b;
     b.off_tokens = b.off_part0 + b.part0_cap;
-    b.off_topnz = b.off_tokens + b.tokens_cap;
-    b.stride = b.off_topnz + topnz_b;
+    b.off_aux = b.off_tokens + b.tokens_cap;
+    b.stride = b.off_aux + aux_b;
     // the stream is the two partitions back to back: a slot that holds what they can hold never overflows;
     // real frames use a few per cent of it, so the slots are compacted on the device before they cross PCIe
     b.out_cap = round_up((size_t)16 + b.part0_cap + b.tokens_cap, (size_t)256);

@@ -149,6 +149,6 @@ extern "C" long vp8_cpu_encode(const uint8_t* frame, size_t step, int w, int h, 
     vp8enc::Buffers B{sy.data(), su.data(), sv.data(), ry.data(), ru.data(), rv.data(), levels.data(), modes.data()};
     vp8enc::analyse_and_reconstruct(P, B);
     const size_t scratch = (size_t)P.mb_w * P.mb_h * 2048 + 4096;  // the layout vp8enc::partition_scratch_off assumes
-    std::vector<uint8_t> part0(scratch), tokens(scratch), top_nz((size_t)P.mb_w * 9);
-    return (long)vp8enc::write_bitstream(P, B, part0.data(), part0.size(), tokens.data(), tokens.size(), top_nz.data(), out, cap);
+    std::vector<uint8_t> part0(scratch), tokens(scratch), aux(vp8enc::kAuxBytes);
+    return (long)vp8enc::write_bitstream(P, B, part0.data(), part0.size(), tokens.data(), tokens.size(), aux.data(), out, cap);
 }

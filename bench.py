@@ -686,6 +686,11 @@ def main():
     for _ in range(args.warmup):
         b.run()
     barrier()
+    phase = (C.c_ulonglong * 8)()
+    has_phase = hasattr(lib.l, "lp_huff_phase_clocks")
+    if has_phase:
+        lib.l.lp_huff_phase_clocks.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+        lib.l.lp_huff_phase_clocks(phase, 1)   # clear the entropy kernel's per-phase cycle counters
     sampler.begin()
     stage_sum = {}
     dev_ms = 0.0
@@ -698,6 +703,11 @@ def main():
     barrier()
     wall_s = time.perf_counter() - t0
     sampler.end()
+    huff_phase = None
+    if has_phase and lib.l.lp_huff_phase_clocks(phase, 0) == 0 and phase[5]:
+        tot = float(sum(phase[k] for k in range(5))) or 1.0
+        huff_phase = {k: round(phase[i] / tot, 4) for i, k in enumerate(("tables", "guess", "sync", "write", "dc"))}
+        huff_phase["cycles_per_image"] = int(tot / phase[5])
     launches = b.last_launches() * args.steps
     outs, fst = b.fetch(n)
     assert all(s == 0 for s in fst), "device pipeline reported per-image failures"
@@ -762,6 +772,7 @@ def main():
                        "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage_sum.items()},
                        "chunk_images": chunk,
                        "huffman_sync_rounds": {"mean": round(mean_r.value, 2), "max": max_r.value},
+                       "huffman_phase_share": huff_phase,
                        "setup_s": round(setup_s, 1)},
             "e2e": {"value": round(e2e_v, 1), "unit": "images/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": out_bytes + n * d2h_over, "encoded_bytes_per_step": out_bytes,

@@ -695,6 +695,8 @@ extern "C" void lp_batch_sync_rounds(const lp_batch* b, double* mean, int* max) 
     if (mean) *mean = cnt ? sum / cnt : 0;
     if (max) *max = mx;
 }
+// Diagnostics: SM cycles per phase of the JPEG entropy kernels since the last reset (current device).
+extern "C" int lp_huff_phase_clocks(unsigned long long* out8, int reset) { return lp::jpeg_huff_phase_clocks(out8, reset); }
 extern "C" const uint8_t* lp_batch_decoded_dev(const lp_batch* b, size_t* image_stride) {
     if (image_stride) *image_stride = b->frame_bytes;
     return b->d_frames;

@@ -25,6 +25,19 @@
 
 namespace lp {
 
+// Diagnostics: SM cycles (clock64, thread 0 of every CTA) spent in the phases of the sync kernels, summed over the
+// CTAs since the last reset: [0] table set-up, [1] guess pass, [2] synchronisation rounds, [3] prefix sum + write
+// pass, [4] DC pass, [5] CTAs.  Four clock reads and five atomics per CTA.
+__device__ unsigned long long g_huff_phase[8];
+#define LP_PHASE_MARK(k)                                             \
+    do {                                                             \
+        if (threadIdx.x == 0) {                                      \
+            const long long now_ = clock64();                        \
+            atomicAdd(&g_huff_phase[k], (unsigned long long)(now_ - s_tphase)); \
+            s_tphase = now_;                                         \
+        }                                                            \
+    } while (0)
+
 constexpr uint32_t kMinSubBits = 1024;  // shortest subsequence (bits); scratch is sized for this
 // Subsequences per thread and pass.  Synchronising the position inside the MCU (not just the
 // codeword boundary) takes several hundred symbols, so short subsequences need ~10 re-decode rounds;
@@ -484,6 +497,8 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     const int tid = threadIdx.x;
     if (it.status != 0 || it.restart_interval != 0) return;  // (DRI images: one thread per restart interval instead)
     if (skip_two && two_table_layout(it)) return;               // version 2 of the kernel decodes these
+    __shared__ long long s_tphase;  // (shared, not a register pair every thread would carry through the loops)
+    if (tid == 0) s_tphase = clock64();
     // ---- build the per-CTA tables
     {
         const JpegHuffSet* g = tables + it.table_set;
@@ -563,6 +578,7 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     const uint64_t total_slots = (uint64_t)it.mcus_x * it.mcus_y * nb * 64;
     int16_t* dcdiff = dcdiff_all + it.dcdiff_off;
 
+    LP_PHASE_MARK(0);
     // ---- pass 0: every subsequence from a guessed state (exact only for subsequence 0)
     for (uint32_t i = tid; i < nsub; i += kHuffThreads) {
         uint32_t p = i * kSubBits, phase = 0, n = 0;
@@ -572,6 +588,7 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
         ns[i] = n;
     }
     __syncthreads();
+    LP_PHASE_MARK(1);
     // ---- synchronisation.  A subsequence is re-decoded from its left neighbour's exit state whenever
     //      that state changed; changes are collected in a work list so later (sparse) rounds keep all
     //      lanes busy.  States are updated in place: a reader that races with a writer sees either
@@ -610,6 +627,7 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
         first_round = false;
     }
     if (tid == 0) it.pad_ = rounds;  // diagnostics: synchronisation rounds this image needed
+    LP_PHASE_MARK(2);
     SubState* cur = st;
     // ---- prefix sum of slot counts, then the writing decode.  Every thread learns each tile's total
     //      from the scan, so the running offset lives in a register (no shared carry, no extra barriers).
@@ -642,7 +660,10 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
         if (tid == 0) it.status = s_status;
         return;
     }
+    LP_PHASE_MARK(3);
     dc_prefix_pass(it, coef, dcdiff, nb, warp_sums);
+    LP_PHASE_MARK(4);
+    if (tid == 0) atomicAdd(&g_huff_phase[5], 1ull);
 }
 
 
@@ -721,6 +742,30 @@ struct BitWin2 {
     __device__ __forceinline__ void skip(uint32_t n) { bo += n; }
 };
 
+// the first version's window: a 64-bit pointer walks the stream, one word in flight
+struct BitWinP {
+    const uint32_t* w;
+    uint32_t w0, w1, n0, bo;
+    __device__ __forceinline__ void init(const uint8_t* s, uint32_t p) {
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(s) + (p >> 5);
+        w0 = __byte_perm(base[0], 0, 0x0123);
+        w1 = __byte_perm(base[1], 0, 0x0123);
+        n0 = base[2];
+        w = base + 3;
+        bo = p & 31;
+    }
+    __device__ __forceinline__ void refill() {
+        if (bo >= 32) {
+            w0 = w1;
+            w1 = __byte_perm(n0, 0, 0x0123);
+            n0 = *w++;
+            bo -= 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(w1, w0, bo); }
+    __device__ __forceinline__ void skip(uint32_t n) { bo += n; }
+};
+
 // codes the lookahead tables do not hold: 13..16-bit AC codes behind a second-level table, everything else
 // through the canonical walk.  Returns an entry in the sym_entry format, 0 = not a codeword.
 __device__ __forceinline__ uint32_t slow_symbol2(const HuffShared2& hs, uint32_t top, bool isdc, uint32_t rest, uint32_t lo) {
@@ -737,14 +782,14 @@ __device__ __forceinline__ uint32_t slow_symbol2(const HuffShared2& hs, uint32_t
 }
 
 // Counting decode of the symbols that START in [p, limit): exit state and coefficient slots consumed.
-template <bool PAIR, int DEPTH>
+template <bool PAIR, class WIN>
 __device__ __forceinline__ void count_span2(const HuffShared2& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
                                             uint32_t& phase, uint32_t& nslots) {
     uint32_t blk = phase >> 6, z = phase & 63;
     const uint32_t z_start = z;
     uint32_t closed = 0;
     int32_t bits_left = (int32_t)(limit - p);
-    BitWin2<DEPTH> bw;
+    WIN bw;
     bw.init(s, p);
     const uint32_t n_first = hs.n_first, nb = hs.nb;
     const uint32_t dcF = (uint32_t)__cvta_generic_to_shared(&hs.dc2[0][0]), dcR = (uint32_t)__cvta_generic_to_shared(&hs.dc2[1][0]);
@@ -791,14 +836,14 @@ __device__ __forceinline__ void count_span2(const HuffShared2& hs, const uint8_t
 
 // Writing decode: coefficients (DC slot: the DC difference) of the symbols that start in [p, limit), the first one at
 // absolute coefficient slot `pos`.
-template <int DEPTH>
+template <class WIN>
 __device__ __forceinline__ void write_span2(const HuffShared2& hs, const uint8_t* s, uint32_t p, uint32_t limit, uint32_t phase,
                                             uint64_t pos, uint64_t total_slots, int16_t* coef_base, int16_t* dcdiff,
                                             int* status) {
     if (pos >= total_slots) return;
     uint32_t blk = phase >> 6, z = phase & 63;
     int32_t bits_left = (int32_t)(limit - p);
-    BitWin2<DEPTH> bw;
+    WIN bw;
     bw.init(s, p);
     const uint32_t n_first = hs.n_first, nb = hs.nb;
     uint32_t blocks_left = (uint32_t)((total_slots - pos + z) >> 6);  // counted from the start of the current block
@@ -874,7 +919,97 @@ __device__ __forceinline__ void write_span2(const HuffShared2& hs, const uint8_t
     if (bad) *status = -3;
 }
 
-template <bool PAIR, int DEPTH>
+// The first version's write loop (per-MCU ROI address from the item, block bookkeeping as it was) over version 2's
+// table entries: the measurement variant that separates "new tables" from "new bookkeeping".
+template <class WIN>
+__device__ __forceinline__ void write_span2L(const HuffShared2& hs, const uint8_t* s, uint32_t p, uint32_t limit, uint32_t phase,
+                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it, int16_t* coef,
+                                             int16_t* dcdiff, int* status) {
+    if (pos >= total_slots) return;
+    uint32_t blk = phase >> 6, z = phase & 63;
+    int32_t bits_left = (int32_t)(limit - p);
+    WIN bw;
+    bw.init(s, p);
+    const int nb = (int)hs.nb;
+    int16_t* dstblk = nullptr;
+    bool inside = false;
+    int16_t* dcp = nullptr;
+    int mx = 0, my = 0;
+    uint32_t blocks_left = (uint32_t)((total_slots - pos + z) >> 6);
+    bool bad = false;
+    int16_t* coef_base = coef + it->coef_off;
+    const uint32_t zzb = (uint32_t)__cvta_generic_to_shared(&hs.zz[0]);
+    auto set_mcu = [&]() {
+        const int rmx = mx - it->roi_mx0, rmy = my - it->roi_my0, rcx = it->roi_mcx;
+        inside = (unsigned)rmx < (unsigned)rcx && (unsigned)rmy < (unsigned)it->roi_mcy;
+        dstblk = coef_base + ((size_t)rmy * rcx + rmx) * ((size_t)nb * 64);
+    };
+    {
+        const uint32_t mcu = (uint32_t)((pos >> 6) / (uint32_t)nb);
+        const uint32_t mcus_x = (uint32_t)it->mcus_x;
+        mx = (int)(mcu % mcus_x);
+        my = (int)(mcu / mcus_x);
+        set_mcu();
+        dstblk += blk * 64;
+        dcp = dcdiff + (pos >> 6);
+    }
+    const uint32_t n_first = hs.n_first;
+    const uint32_t dcF = (uint32_t)__cvta_generic_to_shared(&hs.dc2[0][0]), dcR = (uint32_t)__cvta_generic_to_shared(&hs.dc2[1][0]);
+    const uint32_t acF = (uint32_t)__cvta_generic_to_shared(&hs.ac2[0][0]), acR = (uint32_t)__cvta_generic_to_shared(&hs.ac2[1][0]);
+    uint32_t dcb = blk < n_first ? dcF : dcR, acb = blk < n_first ? acF : acR;
+    while (bits_left > 0) {
+        bw.refill();
+        const uint32_t top = bw.peek();
+        const bool isdc = z == 0;
+        const uint32_t idx = isdc ? (top >> (32 - kDcBits)) : (top >> (32 - kAcBits));
+        uint32_t lo;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"((isdc ? dcb : acb) + idx * 4u));
+        if (__builtin_expect(lo == 0 || lo >= 0x8000u, 0)) {
+            lo = slow_symbol2(hs, top, isdc, blk < n_first ? 0u : 1u, lo);
+            if (lo == 0) {
+                *status = -3;
+                break;
+            }
+        }
+        const uint32_t len = lo & 31u, sz = (lo >> 5) & 15u;
+        const bool ez = sz == 0 && !isdc;
+        const uint32_t zt = z + (lo >> 9) + 1u;
+        {
+            const uint32_t t2 = top << len;
+            const uint32_t raw = __funnelshift_l(t2, 0u, sz);
+            const int val = (int)raw + ((int)t2 >= 0 ? (int)((0xFFFFFFFFu << sz) + 1u) : 0);
+            uint32_t zi;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(zi) : "r"(zzb + ((zt - 1u) & 63u)));
+            int16_t* const where = isdc ? dcp : dstblk + zi;
+            const bool inblk = zt <= 64;
+            bad |= !ez && !inblk;
+            if (!ez && inblk && (isdc || inside)) *where = (int16_t)val;
+        }
+        bw.skip(len + sz);
+        bits_left -= (int32_t)(len + sz);
+        const bool fin = zt >= 64;
+        z = fin ? 0u : zt;
+        if (fin) {
+            blk++;
+            dstblk += 64;
+            if (blk == (uint32_t)nb) {
+                blk = 0;
+                if (++mx == it->mcus_x) {
+                    mx = 0;
+                    my++;
+                }
+                set_mcu();
+            }
+            dcb = blk < n_first ? dcF : dcR;
+            acb = blk < n_first ? acF : acR;
+            if (--blocks_left == 0) break;
+            dcp++;
+        }
+    }
+    if (bad) *status = -3;
+}
+
+template <bool PAIR, class WIN, int WR>
 __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     jpeg_huff_sync2_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* clean,
                            SubState* states_all, uint32_t* nslots_all, int16_t* coef, int16_t* dcdiff_all,
@@ -887,6 +1022,8 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     const int tid = threadIdx.x;
     if (it.status != 0 || it.restart_interval != 0) return;
     if (!two_table_layout(it)) return;  // the first version of the kernel takes these
+    __shared__ long long s_tphase;
+    if (tid == 0) s_tphase = clock64();
     int nb = 0;
     for (int c = 0; c < it.ncomp; c++) nb += it.h[c] * it.v[c];
     // ---- per-CTA tables
@@ -976,15 +1113,17 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     const uint64_t total_slots = (uint64_t)it.mcus_x * it.mcus_y * nb * 64;
     int16_t* dcdiff = dcdiff_all + it.dcdiff_off;
 
+    LP_PHASE_MARK(0);
     // ---- pass 0: every subsequence from a guessed state (exact only for subsequence 0)
     for (uint32_t i = tid; i < nsub; i += kHuffThreads) {
         uint32_t p = i * kSubBits, phase = 0, n = 0;
         const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-        count_span2<PAIR, DEPTH>(hs, s, p, limit, phase, n);
+        count_span2<PAIR, WIN>(hs, s, p, limit, phase, n);
         st[i] = SubState{p, phase};
         ns[i] = n;
     }
     __syncthreads();
+    LP_PHASE_MARK(1);
     // ---- synchronisation rounds (see the first version for the argument)
     uint32_t* cur_list = list_a;
     uint32_t* nxt_list = list_b;
@@ -1001,7 +1140,7 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
             const SubState old = st[i];
             uint32_t p = (uint32_t)in64, phase = (uint32_t)(in64 >> 32), n = 0;
             const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-            if (p < limit) count_span2<PAIR, DEPTH>(hs, s, p, limit, phase, n);
+            if (p < limit) count_span2<PAIR, WIN>(hs, s, p, limit, phase, n);
             ns[i] = n;
             if (p != old.p || phase != old.phase) {
                 *reinterpret_cast<volatile uint64_t*>(&st[i]) = ((uint64_t)phase << 32) | p;
@@ -1017,6 +1156,7 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
         first_round = false;
     }
     if (tid == 0) it.pad_ = rounds;
+    LP_PHASE_MARK(2);
     // ---- prefix sum of slot counts, then the writing decode
     uint64_t slots_before = 0;
     int16_t* coef_base = coef + it.coef_off;
@@ -1033,7 +1173,10 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
             const uint32_t limit = min((i + 1) * kSubBits, total_bits);
             int status = 0;
             if (pos < total_slots && (uint32_t)(pos % ((uint64_t)nb * 64)) != ((phase >> 6) * 64 + (phase & 63))) status = -3;
-            if (!status && p < limit) write_span2<DEPTH>(hs, s, p, limit, phase, pos, total_slots, coef_base, dcdiff, &status);
+            if (!status && p < limit) {
+                if (WR == 0) write_span2<WIN>(hs, s, p, limit, phase, pos, total_slots, coef_base, dcdiff, &status);
+                else write_span2L<WIN>(hs, s, p, limit, phase, pos, total_slots, &it, coef, dcdiff, &status);
+            }
             if (status) s_status = status;
         }
     }
@@ -1043,10 +1186,24 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
         if (tid == 0) it.status = s_status;
         return;
     }
+    LP_PHASE_MARK(3);
     dc_prefix_pass(it, coef, dcdiff, nb, warp_sums);
+    LP_PHASE_MARK(4);
+    if (tid == 0) atomicAdd(&g_huff_phase[5], 1ull);
 }
 
 // ------------------------------------------------------------------ launcher
+
+// host: read (and optionally clear) the phase counters of the current device
+int jpeg_huff_phase_clocks(unsigned long long out[8], int reset) {
+    LP_CUDA_OK(cudaDeviceSynchronize());
+    LP_CUDA_OK(cudaMemcpyFromSymbol(out, g_huff_phase, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        LP_CUDA_OK(cudaMemcpyToSymbol(g_huff_phase, z, sizeof(z)));
+    }
+    return LP_OK;
+}
 
 int jpeg_huff_parallel_slots() {
     int dev = 0, sms = 0, per_sm = 0;
@@ -1068,12 +1225,17 @@ int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st) {
     const int v2 = hv >= 2;
     if (v2) {
         SubState* stp = reinterpret_cast<SubState*>(a.states);
+#define LP_H2(P_, W_, R_) jpeg_huff_sync2_kernel<P_, W_, R_><<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean, stp, a.nslots, a.coef, a.dcdiff, spt)
         switch (hv) {
-            case 3: jpeg_huff_sync2_kernel<true, 1><<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean, stp, a.nslots, a.coef, a.dcdiff, spt); break;
-            case 4: jpeg_huff_sync2_kernel<false, 2><<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean, stp, a.nslots, a.coef, a.dcdiff, spt); break;
-            case 5: jpeg_huff_sync2_kernel<false, 1><<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean, stp, a.nslots, a.coef, a.dcdiff, spt); break;
-            default: jpeg_huff_sync2_kernel<true, 2><<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean, stp, a.nslots, a.coef, a.dcdiff, spt); break;
+            case 3: LP_H2(true, BitWin2<1>, 0); break;   // the round's first measured form
+            case 4: LP_H2(false, BitWin2<2>, 0); break;
+            case 5: LP_H2(false, BitWin2<1>, 0); break;
+            case 6: LP_H2(true, BitWin2<1>, 1); break;
+            case 7: LP_H2(true, BitWinP, 0); break;
+            case 8: LP_H2(true, BitWin2<2>, 0); break;
+            default: LP_H2(true, BitWinP, 1); break;     // 2: two-symbol counting passes, the first version's write loop
         }
+#undef LP_H2
         g_launches++;
         LP_CUDA_OK(cudaGetLastError());
     }

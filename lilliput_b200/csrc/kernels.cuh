@@ -167,6 +167,8 @@ int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st);
 // Images the sync kernel can keep resident at once (SMs x CTAs per SM); chunk sizes that are a
 // multiple of this avoid a mostly-empty last wave.
 int jpeg_huff_parallel_slots();
+// Diagnostics: clock64 cycles per phase of the sync kernels summed over CTAs (see jpeg_huff_parallel.cu)
+int jpeg_huff_phase_clocks(unsigned long long out[8], int reset);
 // Launches: memset(coef) -> huffman decode -> idct -> upsample+colour.
 int jpeg_decode_launch(const JpegDecodeBatch& b, cudaStream_t st, cudaEvent_t ev_after_huff);
 

@@ -1,5 +1,6 @@
-// png_encode.cu -- PNG encode on sm_100a: scanline filtering + DEFLATE (fixed Huffman, hashed
-// LZ77, independent 32 KB chunks joined by sync-flush blocks) + container assembly.
+// png_encode.cu -- PNG encode on sm_100a: scanline filtering + DEFLATE (hash-chain LZ77 whose search effort follows
+// PngCompression, per-chunk dynamic Huffman codes, independent 32 KB chunks joined by sync-flush blocks:
+// deflate_enc_core.h) + container assembly.
 //
 // Replaces: opencv_encoder_write for ".png" (ref opencv.cpp:185-194 -> cv::ImageEncoder::write ->
 // OpenCV grfmt_png -> libpng 1.6.47 + zlib-ng 2.3.3).  PNG is lossless and the contract for this
@@ -12,9 +13,9 @@
 //
 // Kernels:
 //   png_filter_kernel    warp per scanline: the five candidate sums, pick, write [type][bytes].
-//   png_deflate_kernel   warp per 32 KB chunk: lane 0 runs a greedy hash-chain-free LZ77 (one
-//                        candidate per 4-byte hash, 4096-entry table in shared memory) and emits
-//                        fixed-Huffman codes; every chunk ends byte-aligned with an empty stored
+//   png_deflate_kernel   warp per 32 KB chunk: lane 0 runs defenc::write_chunk (LZ77 tokens into global scratch,
+//                        symbol statistics -> length-limited dynamic Huffman codes in shared memory, or fixed
+//                        codes / a stored block when smaller); every chunk ends byte-aligned with an empty stored
 //                        block, so chunks are independent and concatenate by memcpy.  All lanes
 //                        compute the chunk's Adler-32 partial sums.
 //   png_pack_kernel      CTA per image: prefix sum of chunk sizes, compaction into one zlib stream.
@@ -26,12 +27,15 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#define LP_DEF_FN static __device__
+#define LP_DEF_TABLE static __device__ const
+#include "deflate_enc_core.h"
+
 namespace lp {
 
-constexpr int kChunk = 32768;            // uncompressed bytes per DEFLATE chunk
-constexpr int kChunkOut = kChunk + 64;   // worst case: stored fallback
-constexpr int kHashBits = 12;
-constexpr int kDefWarps = 4;
+constexpr int kChunk = defenc::kChunk;        // uncompressed bytes per DEFLATE chunk
+constexpr int kChunkOut = defenc::kChunkOut;  // worst case: stored fallback
+constexpr int kDefWarps = 2;                  // (defenc::Work is ~15 KB of shared memory per chunk in flight)
 
 // ------------------------------------------------------------------ filtering
 
@@ -89,71 +93,21 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-// ------------------------------------------------------------------ DEFLATE, fixed Huffman
-
-struct BitOut {
-    uint8_t* p;
-    uint64_t acc;
-    int cnt;
-    __device__ __forceinline__ void put(uint32_t v, int n) {  // LSB first
-        acc |= (uint64_t)v << cnt;
-        cnt += n;
-        while (cnt >= 8) {
-            *p++ = (uint8_t)acc;
-            acc >>= 8;
-            cnt -= 8;
-        }
-    }
-    __device__ __forceinline__ void align() {
-        if (cnt) {
-            *p++ = (uint8_t)acc;
-            acc = 0;
-            cnt = 0;
-        }
-    }
-};
-
-// Fixed literal/length code of RFC 1951 3.2.6, bit-reversed for LSB-first packing.
-__device__ __forceinline__ void put_litlen(BitOut& b, int sym) {
-    uint32_t code;
-    int len;
-    if (sym < 144) { code = 0x30 + sym; len = 8; }
-    else if (sym < 256) { code = 0x190 + (sym - 144); len = 9; }
-    else if (sym < 280) { code = sym - 256; len = 7; }
-    else { code = 0xC0 + (sym - 280); len = 8; }
-    b.put(__brev(code) >> (32 - len), len);
-}
-
-__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-
-__device__ __forceinline__ void put_match(BitOut& b, int len, int dist) {
-    int ls = 28;
-    while (c_len_base[ls] > len) ls--;
-    put_litlen(b, 257 + ls);
-    if (c_len_extra[ls]) b.put((uint32_t)(len - c_len_base[ls]), c_len_extra[ls]);
-    int ds = 29;
-    while (c_dist_base[ds] > dist) ds--;
-    b.put(__brev((uint32_t)ds) >> 27, 5);
-    if (c_dist_extra[ds]) b.put((uint32_t)(dist - c_dist_base[ds]), c_dist_extra[ds]);
-}
+// ------------------------------------------------------------------ DEFLATE
 
 // chunk_len[i] = compressed bytes of chunk i (each chunk owns kChunkOut bytes of `comp`);
 // adler[i] = {sum of bytes, position-weighted sum} mod 65521 for the host-side combine.
+// scratch: per chunk kChunk uint16 of hash-chain links + defenc::kTokCap uint16 of tokens.
 __global__ void __launch_bounds__(kDefWarps * 32)
-    png_deflate_kernel(const uint8_t* filt, size_t total, int nchunks, int stored_only, uint8_t* comp,
-                       uint32_t* chunk_len, uint2* adler) {
-    __shared__ uint16_t hash_all[kDefWarps][1 << kHashBits];
+    png_deflate_kernel(const uint8_t* filt, size_t total, int nchunks, int level, uint8_t* comp, uint32_t* chunk_len,
+                       uint2* adler, uint16_t* scratch) {
+    __shared__ defenc::Work work[kDefWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x * kDefWarps + warp;
     if (chunk >= nchunks) return;
     const uint8_t* src = filt + (size_t)chunk * kChunk;
     const int n = (int)min((size_t)kChunk, total - (size_t)chunk * kChunk);
     uint8_t* dst = comp + (size_t)chunk * kChunkOut;
-    uint16_t* hash = hash_all[warp];
-    for (int i = lane; i < (1 << kHashBits); i += 32) hash[i] = 0xFFFF;
     // Adler-32 partials: A = sum b_i, B = sum (n - i) b_i
     uint64_t A = 0, B = 0;
     for (int i = lane; i < n; i += 32) {
@@ -168,55 +122,8 @@ __global__ void __launch_bounds__(kDefWarps * 32)
     __syncwarp();
     if (lane != 0) return;
     adler[chunk] = make_uint2((uint32_t)(A % 65521u), (uint32_t)(B % 65521u));
-    BitOut b{dst, 0, 0};
-    bool stored = stored_only != 0;
-    if (!stored) {
-        b.put(2, 3);  // BFINAL = 0, BTYPE = 01 (fixed Huffman)
-        int i = 0;
-        while (i < n) {
-            int best_len = 0, best_dist = 0;
-            if (i + 4 <= n) {
-                const uint32_t w = src[i] | (src[i + 1] << 8) | (src[i + 2] << 16) | ((uint32_t)src[i + 3] << 24);
-                const uint32_t h = (w * 2654435761u) >> (32 - kHashBits);
-                const int cand = hash[h];
-                hash[h] = (uint16_t)i;
-                if (cand != 0xFFFF && i - cand <= 32768 && cand < i) {
-                    int l = 0;
-                    const int maxl = min(258, n - i);
-                    while (l < maxl && src[cand + l] == src[i + l]) l++;
-                    if (l >= 4) {
-                        best_len = l;
-                        best_dist = i - cand;
-                    }
-                }
-            }
-            if (best_len) {
-                put_match(b, best_len, best_dist);
-                i += best_len;
-            } else {
-                put_litlen(b, src[i]);
-                i++;
-            }
-            if ((int)(b.p - dst) > n + 16) {  // expanding: give up, store the chunk instead
-                stored = true;
-                break;
-            }
-        }
-        if (!stored) {
-            put_litlen(b, 256);  // end of block
-            b.put(0, 3);         // empty stored block = sync flush: byte-aligns the chunk
-            b.align();
-            *b.p++ = 0x00; *b.p++ = 0x00; *b.p++ = 0xFF; *b.p++ = 0xFF;
-        }
-    }
-    if (stored) {
-        b = BitOut{dst, 0, 0};
-        *b.p++ = 0x00;  // BFINAL = 0, BTYPE = 00, padding
-        *b.p++ = (uint8_t)n; *b.p++ = (uint8_t)(n >> 8);
-        *b.p++ = (uint8_t)~n; *b.p++ = (uint8_t)((~n) >> 8);
-        for (int i = 0; i < n; i++) *b.p++ = src[i];
-    }
-    chunk_len[chunk] = (uint32_t)(b.p - dst);
+    uint16_t* prev = scratch + (size_t)chunk * (kChunk + defenc::kTokCap);
+    chunk_len[chunk] = (uint32_t)defenc::write_chunk(src, n, level, work[warp], prev, prev + kChunk, dst);
 }
 
 // Concatenate the chunks of one image: out = 78 01 | chunks... | 03 00 (final empty fixed block).
@@ -286,7 +193,9 @@ int png_encode_frame(const uint8_t* frame, size_t row_stride, int W, int H, int 
     const size_t off_len = off_comp + round_up(comp_bytes, (size_t)256);
     const size_t off_adler = off_len + round_up((size_t)nchunks * 4 + 4, (size_t)256);
     const size_t off_z = off_adler + round_up((size_t)nchunks * 8, (size_t)256);
-    LP_CUDA_OK(cudaMallocAsync(&buf, off_z + z_cap, st));
+    const size_t off_scratch = off_z + round_up(z_cap, (size_t)256);
+    const size_t scratch_bytes = level == 0 ? 0 : (size_t)nchunks * (kChunk + defenc::kTokCap) * sizeof(uint16_t);
+    LP_CUDA_OK(cudaMallocAsync(&buf, off_scratch + scratch_bytes, st));
     uint8_t* d_filt = buf;
     uint8_t* d_comp = buf + off_comp;
     uint32_t* d_len = reinterpret_cast<uint32_t*>(buf + off_len);
@@ -295,8 +204,9 @@ int png_encode_frame(const uint8_t* frame, size_t row_stride, int W, int H, int 
     uint32_t* d_total = d_len + nchunks;
     png_filter_kernel<<<(unsigned)ceil_div((long long)H * 32, 128LL), 128, 0, st>>>(frame, row_stride, W, H, C, adaptive ? 1 : 0, d_filt);
     g_launches++;
-    png_deflate_kernel<<<ceil_div(nchunks, kDefWarps), kDefWarps * 32, 0, st>>>(d_filt, raw, nchunks, level == 0,
-                                                                              d_comp, d_len, d_adler);
+    const int lvl = level < 0 ? 1 : level > 9 ? 9 : level;  // zlib's range; OpenCV's own default is 1
+    png_deflate_kernel<<<ceil_div(nchunks, kDefWarps), kDefWarps * 32, 0, st>>>(d_filt, raw, nchunks, lvl, d_comp, d_len, d_adler,
+                                                                              reinterpret_cast<uint16_t*>(buf + off_scratch));
     g_launches++;
     png_pack_kernel<<<1, 256, 0, st>>>(d_comp, d_len, nchunks, d_z, z_cap, d_total);
     g_launches++;

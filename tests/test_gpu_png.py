@@ -68,8 +68,9 @@ def test_png_errors(cuda_lib, golden):
 def test_png_encode_decodes_to_identical_pixels(cuda_lib, oracle, ref_lib, case):
     """PNG output contract = decoded-pixel equality + IHDR policy (colour type 0/2/6, 8-bit), not
     byte-identical files.  The file must decode with an independent decoder (oracle, PIL) to the
-    exact input pixels.  Size: this encoder uses fixed Huffman codes (dynamic trees are a listed
-    follow-up), which costs up to ~1.7x on noisy content against zlib's dynamic trees; bound it."""
+    exact input pixels.  Size: LZ77 whose search effort follows PngCompression + per-chunk dynamic Huffman codes
+    (deflate_enc_core.h): within 1.10 x of the reference's file at the same level (0.86-1.04 measured on the CPU build
+    of the same code, tests/test_deflate_enc_core.py)."""
     import io
     from PIL import Image
     w, h, ch, level = case
@@ -86,7 +87,7 @@ def test_png_encode_decodes_to_identical_pixels(cuda_lib, oracle, ref_lib, case)
     assert np.array_equal(cuda_lib.decode(data), img)   # and through the device decoder
     ref_size = len(ref_lib.encode(".png", img, opts))
     if level != 0 and w * h > 4096:
-        assert len(data) <= 1.8 * ref_size + 256, (len(data), ref_size)
+        assert len(data) <= 1.10 * ref_size + 256, (len(data), ref_size)
 
 
 def test_png_to_png_transform(cuda_lib, oracle, golden):
@@ -100,3 +101,37 @@ def test_png_to_png_transform(cuda_lib, oracle, golden):
     with pytest.raises(abi.LilliputError) as e:   # too-small destination -> ErrBufTooSmall
         cuda_lib.transform(data, opt, dst_cap=64)
     assert e.value.code == -3
+
+
+@pytest.mark.gpu
+def test_png_encoder_stream_is_the_serial_cores(cuda_lib, tmp_path):
+    """The device runs deflate_enc_core.h one lane per chunk; the CPU suite runs the same source against zlib.  Same
+    filtered scanlines in -> byte-identical zlib stream out, at every effort level."""
+    import ctypes as C
+    import os
+    import struct
+    import subprocess
+    import zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libdefenc.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so,
+                           os.path.join(root, "tests", "native", "deflate_enc_sim.cpp")])
+    l = C.CDLL(so)
+    l.defenc_compress.restype = C.c_long
+    l.defenc_compress.argtypes = [C.c_char_p, C.c_long, C.c_int, C.c_void_p, C.c_long]
+    for (w, h, ch, level, noise) in [(300, 200, 3, 1, 4.0), (256, 256, 4, 6, 0.0), (640, 360, 3, 9, 8.0), (97, 61, 1, 3, 2.0),
+                                     (50, 40, 3, 0, 4.0)]:
+        img = synth_image(900 + w, w, h, ch, noise=noise)
+        png = cuda_lib.encode(".png", img, {abi.PngCompression: level})
+        o, z = 8, b""
+        while o < len(png):
+            ln, = struct.unpack(">I", png[o:o + 4])
+            if png[o + 4:o + 8] == b"IDAT":
+                z += png[o + 8:o + 8 + ln]
+            o += 12 + ln
+        raw = zlib.decompress(z)
+        assert len(raw) == (w * ch + 1) * h
+        cap = len(raw) + 4096
+        out = (C.c_uint8 * cap)()
+        n = l.defenc_compress(raw, len(raw), level, out, cap)
+        assert n > 0 and bytes(out[:n]) == z, (w, h, ch, level)

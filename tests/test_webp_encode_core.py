@@ -76,3 +76,22 @@ def test_lossy_stream_decodes_identically_with_the_reference_and_matches_libwebp
             assert rc == 0 and np.array_equal(frames[0], vp8_cpu_decode(cpu, payload))
             ok, lw = cv2.imencode(".webp", img, [cv2.IMWRITE_WEBP_QUALITY, quality])
             assert psnr(frames[0], img) > psnr(cv2.imdecode(lw, cv2.IMREAD_COLOR), img) - 1.0
+
+
+@pytest.mark.parametrize("quality", [50, 75, 85, 95])
+def test_lossy_encoder_size_bound_against_libwebp(cpu, quality):
+    """SURVEY 7's acceptance rule for the lossy encoder: at libwebp's PSNR (within 0.25 dB), at most 1.10 x libwebp's
+    bytes -- on the content class of BASELINE config 3 (synthetic fields + edges + sensor-like noise).  The stream codes
+    its coefficients with per-frame probabilities and per-macroblock skip flags (RFC 6386 13.4 / 9.11); what it still
+    lacks against libwebp is the 4x4 intra modes, which cost 15-35 % on natural photographs (DESIGN.md has the numbers
+    measured on the reference's own sample photographs)."""
+    cv2 = pytest.importorskip("cv2")
+    for seed, w, h, noise in [(21, 512, 512, 6.0), (51, 512, 512, 3.0), (52, 256, 256, 6.0), (53, 512, 512, 12.0),
+                              (55, 384, 256, 25.0)]:
+        img = synth_image(seed, w, h, 3, noise=noise)
+        payload = vp8_cpu_encode(cpu, img, quality)
+        ok, lw = cv2.imencode(".webp", img, [cv2.IMWRITE_WEBP_QUALITY, quality])
+        assert ok
+        mine, theirs = psnr(vp8_cpu_decode(cpu, payload), img), psnr(cv2.imdecode(lw, cv2.IMREAD_COLOR), img)
+        assert mine >= theirs - 0.25, (seed, quality, mine, theirs)
+        assert len(payload) + 20 <= 1.10 * len(lw), (seed, quality, len(payload), len(lw))  # + RIFF / chunk headers

@@ -50,10 +50,12 @@ def parse_args():
                     help="BASELINE.json config: 2 = headline (1080p JPEG -> 256x256 JPEG), 3 = 4K RGBA PNG -> 512x512 "
                          "WebP, 4 = 128-frame 720p GIF -> 256x256 animated WebP, 5 = mixed JPEG/PNG/WebP -> 256x256 JPEG")
     ap.add_argument("--distinct", type=int, default=0, help="configs 3-5: distinct files generated (replicated to the batch)")
-    ap.add_argument("--variant", default="default", choices=["default", "cv2", "optimized", "dri"],
+    ap.add_argument("--variant", default="default", choices=["default", "cv2", "optimized", "dri", "pcg64"],
                     help="config 2 corpus: default = this library's encoder (byte-identical to the reference's); cv2 = "
                          "OpenCV / libjpeg-turbo written files; optimized = per-image optimised Huffman tables (a DHT "
-                         "per file); dri = restart interval of one MCU row.  Secondary, labelled lines.")
+                         "per file); dri = restart interval of one MCU row; pcg64 = SURVEY 8(d)'s generator to the letter "
+                         "(numpy PCG64(1000 + i) content made on the host CPUs, files written by libjpeg-turbo; ~0.7 s "
+                         "per image and core, so use it with a smaller --batch).  Secondary, labelled lines.")
     return ap.parse_args()
 
 
@@ -98,7 +100,26 @@ def make_corpus_cv2(lib, device, n, seed0, variant):
     return base, arena, offs, lens
 
 
+def make_corpus_pcg64(lib, n, first):
+    from lilliput_b200.corpus import corpus_config2_pcg64
+    blobs = corpus_config2_pcg64(n, first=first, w=SRC_W, h=SRC_H, seed0=1000, quality=Q_IN, workers=usable_cpus())
+    lens = [int(b.size) for b in blobs]
+    total = int(sum(lens))
+    lib.l.lp_host_alloc_pinned.restype = C.c_void_p
+    lib.l.lp_host_alloc_pinned.argtypes = [C.c_size_t]
+    base = lib.l.lp_host_alloc_pinned(total + 64)
+    arena = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(total + 64,))
+    offs, o = [], 0
+    for b in blobs:
+        arena[o:o + b.size] = b
+        offs.append(o)
+        o += b.size
+    return base, arena, offs, lens
+
+
 def make_corpus(lib, device, n, seed0, variant="default"):
+    if variant == "pcg64":
+        return make_corpus_pcg64(lib, n, seed0 - 1000)  # seed0 = 1000 + first image index of this rank's shard
     if variant != "default":
         return make_corpus_cv2(lib, device, n, seed0, variant)
     return _make_corpus_default(lib, device, n, seed0)
@@ -566,10 +587,15 @@ def main_x(args):
                                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
                                 "bytes_per_unit": cfg["resize_bytes"]}
         if world == 1 and not args.no_cpu_baseline and os.path.exists(abi.REF_LIB):
+            # bounded sample of at least --cpu-seconds of CPU work: calls of ~3 s each (the pool and its framebuffers are
+            # warmed before each clock starts) until the clocks add up
             probe_n = max(threads, 8)
             probe = x_reference_run(cfg, base, offs_d, lens_d, probe_n, threads)
-            total_n = int(max(probe_n, probe_n / probe * args.cpu_seconds))
-            el = x_reference_run(cfg, base, offs_d, lens_d, total_n, threads)
+            per_call = int(max(probe_n, probe_n / probe * 3.0))
+            total_n, el = 0, 0.0
+            while el < args.cpu_seconds:
+                el += x_reference_run(cfg, base, offs_d, lens_d, per_call, threads)
+                total_n += per_call
             line["cpu_baseline"] = {"value": round(total_n / el, 3), "unit": cfg["unit"], "cores": cores, "kind": "reference",
                                     "sample": f"{total_n} Transforms over the {len(files)} distinct inputs in {el:.1f} s, {threads} "
                                               f"threads on {cores} usable CPUs, workers warmed before the clock, "
@@ -763,7 +789,9 @@ def main():
                        "corpus": {"default": "torch content, this library's encoder (byte-identical to the reference's), standard tables",
                                   "cv2": "torch content, files written by cv2 (libjpeg-turbo), standard tables",
                                   "optimized": "torch content, cv2 with per-image optimised Huffman tables (one DHT set per file)",
-                                  "dri": "torch content, cv2 with a restart interval of one MCU row (120 MCUs)"}[args.variant],
+                                  "dri": "torch content, cv2 with a restart interval of one MCU row (120 MCUs)",
+                                  "pcg64": "SURVEY 8(d) generator: numpy PCG64(1000 + i) content on the host, files written by "
+                                           "libjpeg-turbo (cv2), standard tables"}[args.variant],
                        "images_per_gpu_per_step": n, "sharding": "by image index, no collective",
                        "l2": "inputs (%.2f GB compressed, 25 GB decoded per step) exceed the 126 MB L2; no flush needed"
                              % (in_bytes / 1e9),
@@ -790,9 +818,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline and os.path.exists(abi.REF_LIB):
             sample_n = n
             probe = cpu_reference_run(base, offs[:sample_n], lens[:sample_n], threads * 2, threads)
-            rate = threads * 2 / probe
-            total = int(max(threads * 2, rate * args.cpu_seconds))
-            el = cpu_reference_run(base, offs[:sample_n], lens[:sample_n], total, threads)
+            per_call = int(max(threads * 2, threads * 2 / probe * 3.0))
+            total, el = 0, 0.0
+            while el < args.cpu_seconds:   # at least --cpu-seconds of CPU work, ~3 s per call, workers warmed before each clock
+                el += cpu_reference_run(base, offs[:sample_n], lens[:sample_n], per_call, threads)
+                total += per_call
             line["cpu_baseline"] = {"value": round(total / el, 2), "unit": "images/s", "cores": cores,
                                     "kind": "reference",
                                     "sample": f"{total} Transforms over the first {sample_n} inputs of the same "

@@ -134,3 +134,52 @@ def corpus_config5(dev, variants=2, seed0=5000):
                    "webp": lambda im: encode_webp(im, 85)}[fmt]
             cells[(fmt, (w, h))] = _pool_map(enc, [frames[i] for i in range(variants)], threads=variants)
     return cells
+
+
+# ------------------------------------------------------------------ SURVEY 8(d) C2, to the letter (CPU generator)
+
+def pcg64_frame(i, w=1920, h=1080, seed0=1000):
+    """Image i of SURVEY.md 8(d)'s config-2 corpus: rng = numpy PCG64(seed0 + i); low-frequency field (six random 2-D
+    cosines per channel, amplitudes 40..90 in total), eight filled rectangles / ellipses, N(0, 6) noise, clipped to u8."""
+    rng = np.random.Generator(np.random.PCG64(seed0 + i))
+    yy = np.arange(h, dtype=np.float64)
+    xx = np.arange(w, dtype=np.float64)
+    img = np.full((h, w, 3), 128.0, dtype=np.float32)
+    for _ in range(6):
+        amp = (40 + 50 * rng.random(3)) / 6.0
+        f = (0.5 + 5.5 * rng.random((3, 2))) * (2 * np.pi / w)
+        ph = 2 * np.pi * rng.random(3)
+        for c in range(3):  # cos(fx x + fy y + ph) as two outer products: no transcendental per pixel
+            ax, ay = f[c, 0] * xx + ph[c], f[c, 1] * yy
+            img[:, :, c] += (amp[c] * (np.outer(np.cos(ay), np.cos(ax)) - np.outer(np.sin(ay), np.sin(ax)))).astype(np.float32)
+    for k in range(8):
+        cx, cy = int(rng.integers(0, w)), int(rng.integers(0, h))
+        rw, rh = int(rng.integers(48, 320)), int(rng.integers(27, 180))
+        col = (255 * rng.random(3)).astype(np.float32)
+        x0, x1, y0, y1 = max(cx - rw, 0), min(cx + rw, w), max(cy - rh, 0), min(cy + rh, h)
+        if k % 2:  # ellipse
+            sub_y = (np.arange(y0, y1, dtype=np.float32).reshape(-1, 1) - cy) / rh
+            sub_x = (np.arange(x0, x1, dtype=np.float32).reshape(1, -1) - cx) / rw
+            m = (sub_x * sub_x + sub_y * sub_y) < 1.0
+            img[y0:y1, x0:x1][m] = col
+        else:
+            img[y0:y1, x0:x1] = col
+    img += rng.standard_normal(img.shape, dtype=np.float32) * np.float32(6.0)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def _pcg64_jpeg(args):
+    import cv2
+    i, w, h, seed0, q = args
+    cv2.setNumThreads(1)
+    ok, b = cv2.imencode(".jpg", pcg64_frame(i, w, h, seed0), [cv2.IMWRITE_JPEG_QUALITY, q])  # 4:2:0, Annex K tables, no DRI
+    assert ok
+    return np.asarray(b).reshape(-1).copy()
+
+
+def corpus_config2_pcg64(n, first=0, w=1920, h=1080, seed0=1000, quality=90, workers=8):
+    """n files of the C2 corpus, images first .. first + n - 1, written by libjpeg-turbo (cv2) in `workers` processes."""
+    from concurrent.futures import ProcessPoolExecutor
+    jobs = [(first + k, w, h, seed0, quality) for k in range(n)]
+    with ProcessPoolExecutor(max_workers=max(1, workers)) as ex:
+        return list(ex.map(_pcg64_jpeg, jobs, chunksize=4))

@@ -262,7 +262,7 @@ template <bool WRITE, bool TWO>
 __device__ __forceinline__ void decode_span_t(const HuffShared& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
                                             uint32_t& phase, uint32_t& nslots, int nb,
                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it,
-                                            int16_t* coef, int16_t* dcdiff, int* status) {
+                                            int16_t* coef, int16_t* dcdiff, int* status, int nostore = 0) {
     uint32_t blk = phase >> 6, z = phase & 63;
     const uint32_t z_start = z;
     uint32_t closed = 0;                       // blocks completed in this span
@@ -366,7 +366,7 @@ __device__ __forceinline__ void decode_span_t(const HuffShared& hs, const uint8_
             int16_t* const where = isdc ? dcp : dstblk + zi;  // DC difference: every block; AC: inside the ROI
             const bool inblk = zt <= 64;
             bad |= !ez && !inblk;  // coefficient index past 63: corrupt data
-            if (!ez && inblk && (isdc || inside)) *where = (int16_t)val;
+            if (!ez && inblk && (isdc || (inside && !nostore))) *where = (int16_t)val;
         }
         bw.skip(used);
         bits_left -= used;
@@ -408,11 +408,11 @@ template <bool WRITE>
 __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
                                             uint32_t& phase, uint32_t& nslots, int nb,
                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it,
-                                            int16_t* coef, int16_t* dcdiff, int* status) {
+                                            int16_t* coef, int16_t* dcdiff, int* status, int nostore = 0) {
     if (hs.two_tables)
-        decode_span_t<WRITE, true>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status);
+        decode_span_t<WRITE, true>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status, nostore);
     else
-        decode_span_t<WRITE, false>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status);
+        decode_span_t<WRITE, false>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status, nostore);
 }
 
 // true when component 0's blocks share one DC / AC table pair and all other blocks another (uniform per image)
@@ -488,7 +488,7 @@ __device__ __forceinline__ void dc_prefix_pass(const JpegDecodeItem& it, int16_t
 __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     jpeg_huff_sync_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* clean,
                           SubState* states_all, uint32_t* nslots_all, int16_t* coef, int16_t* dcdiff_all,
-                          uint32_t sub_per_thread, int skip_two) {
+                          uint32_t sub_per_thread, int skip_two, int dbg_nostore) {
     __shared__ HuffShared hs;
     __shared__ uint32_t warp_sums[kHuffThreads / 32];
     __shared__ uint32_t s_carry;
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
                 (uint32_t)(pos % ((uint64_t)nb * 64)) != ((phase >> 6) * 64 + (phase & 63)))
                 status = -3;
             if (!status && p < limit)
-                decode_span<true>(hs, s, p, limit, phase, n, nb, pos, total_slots, &it, coef, dcdiff, &status);
+                decode_span<true>(hs, s, p, limit, phase, n, nb, pos, total_slots, &it, coef, dcdiff, &status, dbg_nostore);
             if (status) s_status = status;
         }
     }
@@ -1221,8 +1221,10 @@ int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st) {
     LP_CUDA_OK(cudaGetLastError());
     // LP_HUFF_V: 1 = every image on the first version of the kernel; 2 (default) = version 2 with two-symbol entries and
     // two stream words in flight; 3 / 4 / 5 = version 2 without one or both of those (measurement variants)
-    static const int hv = getenv("LP_HUFF_V") ? atoi(getenv("LP_HUFF_V")) : 2;
+    static const int hv = getenv("LP_HUFF_V") ? atoi(getenv("LP_HUFF_V")) : 1;
     const int v2 = hv >= 2;
+    // measurement only: LP_HUFF_NOSTORE=1 drops the AC coefficient stores of the first version's write pass (wrong pixels)
+    static const int nostore = getenv("LP_HUFF_NOSTORE") ? atoi(getenv("LP_HUFF_NOSTORE")) : 0;
     if (v2) {
         SubState* stp = reinterpret_cast<SubState*>(a.states);
 #define LP_H2(P_, W_, R_) jpeg_huff_sync2_kernel<P_, W_, R_><<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean, stp, a.nslots, a.coef, a.dcdiff, spt)
@@ -1242,7 +1244,7 @@ int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st) {
     {   // (with version 2 on, this one only decodes the images whose table layout version 2 does not take)
         jpeg_huff_sync_kernel<<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean,
                                                            reinterpret_cast<SubState*>(a.states), a.nslots, a.coef,
-                                                           a.dcdiff, spt, v2);
+                                                           a.dcdiff, spt, v2, nostore);
         g_launches++;
         LP_CUDA_OK(cudaGetLastError());
     }

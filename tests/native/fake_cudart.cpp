@@ -65,6 +65,9 @@ cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size
     return cudaSuccess;
 }
 cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+// device symbols (the entropy kernel's phase counters): no kernel ever runs here, so they read as zero
+cudaError_t cudaMemcpyFromSymbol(void* d, const void*, size_t n, size_t, cudaMemcpyKind) { memset(d, 0, n); return cudaSuccess; }
+cudaError_t cudaMemcpyToSymbol(const void*, const void*, size_t, size_t, cudaMemcpyKind) { return cudaSuccess; }
 cudaError_t cudaMemset2DAsync(void* d, size_t p, int v, size_t w, size_t h, cudaStream_t) {
     for (size_t y = 0; y < h; y++) memset((char*)d + y * p, v, w);
     return cudaSuccess;

@@ -218,3 +218,42 @@ def test_many_distinct_huffman_table_sets(cuda_lib, xb):
     assert status == [0] * len(files)
     st = xb.stats()
     assert st["grid_items"] == len(files) and st["fallback_items"] == 0
+
+
+def _with_exif_orientation(jpeg: bytes, orientation: int) -> bytes:
+    """APP1 / EXIF with one IFD entry (0x0112 orientation) right behind SOI."""
+    tiff = b"II*\x00\x08\x00\x00\x00" + b"\x01\x00" + b"\x12\x01\x03\x00\x01\x00\x00\x00" + bytes([orientation, 0, 0, 0]) + b"\x00\x00\x00\x00"
+    body = b"Exif\x00\x00" + tiff
+    return jpeg[:2] + b"\xff\xe1" + (len(body) + 2).to_bytes(2, "big") + body + jpeg[2:]
+
+
+def test_jpeg_share_of_config5_every_kind_in_one_call(cuda_lib, xb):
+    """The JPEG share of BASELINE config 5 as real corpora have it: five sizes, per-image optimised Huffman tables, 4:2:0 /
+    4:2:2 / 4:4:4 / gray, restart intervals, progressive files and EXIF-rotated ones in ONE call.  Every item comes back
+    LP_OK with the bytes lp_transform gives it, whichever path (grid or per-image hand-over) the batch chose for it."""
+    cv2 = pytest.importorskip("cv2")
+    sizes = [(854, 480), (1280, 720), (640, 360), (1024, 768), (500, 333)]
+    samp = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+    files = []
+    for k in range(60):
+        w, h = sizes[k % 5]
+        flags = [cv2.IMWRITE_JPEG_QUALITY, 60 + (k * 7) % 38, cv2.IMWRITE_JPEG_OPTIMIZE, 1,
+                 cv2.IMWRITE_JPEG_SAMPLING_FACTOR, samp[(k // 5) % 3]]
+        if k % 11 == 3:
+            flags += [cv2.IMWRITE_JPEG_RST_INTERVAL, 7]
+        if k % 13 == 5:
+            flags += [cv2.IMWRITE_JPEG_PROGRESSIVE, 1]
+        img = synth_image(1500 + k, w, h, 1 if k % 17 == 9 else 3, noise=3.0 + (k % 5))
+        ok, b = cv2.imencode(".jpg", img, flags)
+        assert ok
+        b = bytes(b)
+        if k % 7 == 2:
+            b = _with_exif_orientation(b, 2 + (k // 7) % 7)
+        files.append(b)
+    opt = abi.ImageOptions(FileType=".jpeg", Width=256, Height=256, ResizeMethod=abi.ImageOpsFit, NormalizeOrientation=True,
+                           EncodeOptions={abi.JpegQuality: 85}, EncodeTimeout_ns=T)
+    outs, status = check_against_per_image(cuda_lib, xb, files, opt)
+    assert status == [0] * len(files)
+    st = xb.stats()
+    assert st["grid_items"] + st["fallback_items"] == len(files)
+    assert st["grid_items"] >= 40  # the baseline colour files; progressive / rotated / gray ones may be handed over

@@ -262,7 +262,7 @@ template <bool WRITE, bool TWO>
 __device__ __forceinline__ void decode_span_t(const HuffShared& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
                                             uint32_t& phase, uint32_t& nslots, int nb,
                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it,
-                                            int16_t* coef, int16_t* dcdiff, int* status, int nostore = 0) {
+                                            int16_t* coef, int16_t* dcdiff, int* status) {
     uint32_t blk = phase >> 6, z = phase & 63;
     const uint32_t z_start = z;
     uint32_t closed = 0;                       // blocks completed in this span
@@ -366,7 +366,7 @@ __device__ __forceinline__ void decode_span_t(const HuffShared& hs, const uint8_
             int16_t* const where = isdc ? dcp : dstblk + zi;  // DC difference: every block; AC: inside the ROI
             const bool inblk = zt <= 64;
             bad |= !ez && !inblk;  // coefficient index past 63: corrupt data
-            if (!ez && inblk && (isdc || (inside && !nostore))) *where = (int16_t)val;
+            if (!ez && inblk && (isdc || inside)) *where = (int16_t)val;
         }
         bw.skip(used);
         bits_left -= used;
@@ -408,21 +408,14 @@ template <bool WRITE>
 __device__ __forceinline__ void decode_span(const HuffShared& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
                                             uint32_t& phase, uint32_t& nslots, int nb,
                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it,
-                                            int16_t* coef, int16_t* dcdiff, int* status, int nostore = 0) {
+                                            int16_t* coef, int16_t* dcdiff, int* status) {
     if (hs.two_tables)
-        decode_span_t<WRITE, true>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status, nostore);
+        decode_span_t<WRITE, true>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status);
     else
-        decode_span_t<WRITE, false>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status, nostore);
+        decode_span_t<WRITE, false>(hs, s, p, limit, phase, nslots, nb, pos, total_slots, it, coef, dcdiff, status);
 }
 
-// true when component 0's blocks share one DC / AC table pair and all other blocks another (uniform per image)
-__device__ __forceinline__ bool two_table_layout(const JpegDecodeItem& it) {
-    bool two = true;
-    for (int c = 2; c < it.ncomp; c++) two = two && it.td[c] == it.td[1] && it.ta[c] == it.ta[1];
-    return two;
-}
-
-// ---- 3. DC differences -> DC values (shared by both versions of the kernel)
+// ---- 3. DC differences -> DC values
 __device__ __forceinline__ void dc_prefix_pass(const JpegDecodeItem& it, int16_t* coef, const int16_t* dcdiff, int nb,
                                                uint32_t* warp_sums) {
     const int tid = threadIdx.x;
@@ -488,7 +481,7 @@ __device__ __forceinline__ void dc_prefix_pass(const JpegDecodeItem& it, int16_t
 __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     jpeg_huff_sync_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* clean,
                           SubState* states_all, uint32_t* nslots_all, int16_t* coef, int16_t* dcdiff_all,
-                          uint32_t sub_per_thread, int skip_two, int dbg_nostore) {
+                          uint32_t sub_per_thread) {
     __shared__ HuffShared hs;
     __shared__ uint32_t warp_sums[kHuffThreads / 32];
     __shared__ uint32_t s_carry;
@@ -496,7 +489,6 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     JpegDecodeItem& it = items[blockIdx.x];
     const int tid = threadIdx.x;
     if (it.status != 0 || it.restart_interval != 0) return;  // (DRI images: one thread per restart interval instead)
-    if (skip_two && two_table_layout(it)) return;               // version 2 of the kernel decodes these
     __shared__ long long s_tphase;  // (shared, not a register pair every thread would carry through the loops)
     if (tid == 0) s_tphase = clock64();
     // ---- build the per-CTA tables
@@ -650,7 +642,7 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
                 (uint32_t)(pos % ((uint64_t)nb * 64)) != ((phase >> 6) * 64 + (phase & 63)))
                 status = -3;
             if (!status && p < limit)
-                decode_span<true>(hs, s, p, limit, phase, n, nb, pos, total_slots, &it, coef, dcdiff, &status, dbg_nostore);
+                decode_span<true>(hs, s, p, limit, phase, n, nb, pos, total_slots, &it, coef, dcdiff, &status);
             if (status) s_status = status;
         }
     }
@@ -666,531 +658,6 @@ __global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
     if (tid == 0) atomicAdd(&g_huff_phase[5], 1ull);
 }
 
-
-// ================================================================== version 2 of the symbol loops
-//
-// For the usual layout (component 0's blocks share one DC / AC table pair, all other blocks another).
-// What the round-2 source-level profile of the first version said and what changed here:
-//   * 12.8 % of the stall samples sat on the byte swap that consumes the prefetched stream word: the
-//     load was issued only 32 bits ahead.  BitWin2 keeps two words in flight (64 bits ahead).
-//   * the lookahead entry was (len << 8) | symbol and every loop re-derived run / size / advance / EOB
-//     / ZRL from it (~8 integer instructions per symbol).  Entries now hold the derived fields:
-//     len | size << 5 | (advance - 1) << 9.
-//   * the two counting passes (guess + synchronisation, half of the kernel's instructions) decoded one
-//     symbol per table look-up.  A 12-bit window usually holds TWO complete AC codes, so the AC table
-//     entries are 32 bits wide: the low half describes the first symbol, the high half the first two
-//     together (bits used | slots advanced << 5), taken when the first symbol does not end the block and
-//     the second one still starts inside the subsequence.
-//   * the write pass recomputed the ROI address of every MCU with 64-bit multiplies; ROI blocks are
-//     consecutive in scan order, so it now carries a running pointer that advances by 64 per block while
-//     the current MCU is inside the region.
-
-struct HuffShared2 {
-    uint32_t ac2[2][1 << kAcBits];  // [first / rest]
-    uint32_t dc2[2][1 << kDcBits];  // low half only
-    uint16_t ac_sub[2 * kHuffLongPrefixes][16];
-    int32_t maxcode[4][18];  // 0/1: DC first / rest, 2/3: AC first / rest
-    int32_t valoffset[4][17];
-    uint8_t vals[4][256];
-    uint8_t zz[64];
-    uint32_t n_first, nb;
-    int32_t mcus_x, roi_mx0, roi_my0, roi_mcx, roi_mcy;
-};
-
-// (len << 8) | symbol  ->  len | size << 5 | (advance - 1) << 9.  advance = coefficient slots the symbol moves:
-// run + 1 for a value, 16 for ZRL, 64 ("to the end") for EOB; DC symbols are values with run 0.
-__host__ __device__ __forceinline__ uint32_t sym_entry(uint32_t e, bool dc) {
-    if (!e) return 0;
-    const uint32_t len = e >> 8, sym = e & 0xFF, r = sym >> 4, sz = sym & 15;
-    const uint32_t adv = (dc || sz) ? r + 1 : (r == 15 ? 16u : 64u);
-    return len | sz << 5 | (adv - 1) << 9;
-}
-
-// DEPTH = stream words in flight behind w0 / w1 (1: loaded 32 bits ahead of use, 2: 64 bits ahead).  The stream is
-// addressed as a CTA-uniform base plus a 32-bit word index, so a refill moves one index instead of a 64-bit pointer.
-template <int DEPTH>
-struct BitWin2 {
-    const uint32_t* base;  // uniform across the CTA
-    uint32_t wi;           // index of the next word to load
-    uint32_t w0, w1;       // big-endian words; the next bit is bit (31 - bo) of w0
-    uint32_t n0, n1;       // prefetched, still little-endian (n1 only when DEPTH == 2)
-    uint32_t bo;
-    __device__ __forceinline__ void init(const uint8_t* s, uint32_t p) {
-        base = reinterpret_cast<const uint32_t*>(s);
-        wi = p >> 5;
-        w0 = __byte_perm(base[wi], 0, 0x0123);
-        w1 = __byte_perm(base[wi + 1], 0, 0x0123);
-        n0 = base[wi + 2];
-        if (DEPTH == 2) n1 = base[wi + 3];
-        wi += 2 + DEPTH;
-        bo = p & 31;
-    }
-    __device__ __forceinline__ void refill() {
-        if (bo >= 32) {
-            w0 = w1;
-            w1 = __byte_perm(n0, 0, 0x0123);
-            if (DEPTH == 2) {
-                n0 = n1;
-                n1 = base[wi++];
-            } else {
-                n0 = base[wi++];
-            }
-            bo -= 32;
-        }
-    }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(w1, w0, bo); }
-    __device__ __forceinline__ void skip(uint32_t n) { bo += n; }
-};
-
-// the first version's window: a 64-bit pointer walks the stream, one word in flight
-struct BitWinP {
-    const uint32_t* w;
-    uint32_t w0, w1, n0, bo;
-    __device__ __forceinline__ void init(const uint8_t* s, uint32_t p) {
-        const uint32_t* base = reinterpret_cast<const uint32_t*>(s) + (p >> 5);
-        w0 = __byte_perm(base[0], 0, 0x0123);
-        w1 = __byte_perm(base[1], 0, 0x0123);
-        n0 = base[2];
-        w = base + 3;
-        bo = p & 31;
-    }
-    __device__ __forceinline__ void refill() {
-        if (bo >= 32) {
-            w0 = w1;
-            w1 = __byte_perm(n0, 0, 0x0123);
-            n0 = *w++;
-            bo -= 32;
-        }
-    }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(w1, w0, bo); }
-    __device__ __forceinline__ void skip(uint32_t n) { bo += n; }
-};
-
-// codes the lookahead tables do not hold: 13..16-bit AC codes behind a second-level table, everything else
-// through the canonical walk.  Returns an entry in the sym_entry format, 0 = not a codeword.
-__device__ __forceinline__ uint32_t slow_symbol2(const HuffShared2& hs, uint32_t top, bool isdc, uint32_t rest, uint32_t lo) {
-    if (lo & 0x8000u) return hs.ac_sub[lo & 0x7FFFu][(top >> (32 - kAcBits - 4)) & 15u];
-    const int t = (isdc ? 0 : 2) + (int)rest;
-    int len = (isdc ? kDcBits : kAcBits) + 1;
-    int code = (int)(top >> (32 - len));
-    while (len <= 16 && code > hs.maxcode[t][len]) {
-        len++;
-        code = (int)(top >> (32 - len));
-    }
-    if (len > 16) return 0;
-    return sym_entry((uint32_t)(len << 8) | hs.vals[t][(code + hs.valoffset[t][len]) & 0xFF], isdc);
-}
-
-// Counting decode of the symbols that START in [p, limit): exit state and coefficient slots consumed.
-template <bool PAIR, class WIN>
-__device__ __forceinline__ void count_span2(const HuffShared2& hs, const uint8_t* s, uint32_t& p, uint32_t limit,
-                                            uint32_t& phase, uint32_t& nslots) {
-    uint32_t blk = phase >> 6, z = phase & 63;
-    const uint32_t z_start = z;
-    uint32_t closed = 0;
-    int32_t bits_left = (int32_t)(limit - p);
-    WIN bw;
-    bw.init(s, p);
-    const uint32_t n_first = hs.n_first, nb = hs.nb;
-    const uint32_t dcF = (uint32_t)__cvta_generic_to_shared(&hs.dc2[0][0]), dcR = (uint32_t)__cvta_generic_to_shared(&hs.dc2[1][0]);
-    const uint32_t acF = (uint32_t)__cvta_generic_to_shared(&hs.ac2[0][0]), acR = (uint32_t)__cvta_generic_to_shared(&hs.ac2[1][0]);
-    uint32_t dcb = blk < n_first ? dcF : dcR, acb = blk < n_first ? acF : acR;
-    while (bits_left > 0) {
-        bw.refill();
-        const uint32_t top = bw.peek();
-        const bool isdc = z == 0;
-        const uint32_t idx = isdc ? (top >> (32 - kDcBits)) : (top >> (32 - kAcBits));
-        uint32_t e;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((isdc ? dcb : acb) + idx * 4u));
-        uint32_t lo = e & 0xFFFFu, hi = e >> 16;
-        if (__builtin_expect(lo == 0 || lo >= 0x8000u, 0)) {
-            hi = 0;
-            lo = slow_symbol2(hs, top, isdc, blk < n_first ? 0u : 1u, lo);
-            if (lo == 0) {  // not a codeword: a wrong guess, or a corrupt stream
-                bw.skip(1);
-                bits_left -= 1;
-                continue;
-            }
-        }
-        const uint32_t used1 = (lo & 31u) + ((lo >> 5) & 15u);
-        const uint32_t zt1 = z + (lo >> 9) + 1u;
-        // both symbols of the entry: the first must leave the block open (the next would be a DC code otherwise)
-        // and the second must still START in front of `limit`
-        const bool pair = PAIR && hi != 0 && zt1 < 64 && bits_left > (int32_t)used1;
-        const uint32_t used = pair ? (hi & 31u) : used1;
-        const uint32_t zt = pair ? z + (hi >> 5) : zt1;
-        bw.skip(used);
-        bits_left -= (int32_t)used;
-        const bool fin = zt >= 64;
-        z = fin ? 0u : zt;
-        closed += fin ? 1u : 0u;
-        const uint32_t nxt = blk + 1 == nb ? 0u : blk + 1;
-        blk = fin ? nxt : blk;
-        dcb = blk < n_first ? dcF : dcR;
-        acb = blk < n_first ? acF : acR;
-    }
-    p = limit - (uint32_t)bits_left;
-    phase = (blk << 6) | z;
-    nslots = closed * 64 + z - z_start;
-}
-
-// Writing decode: coefficients (DC slot: the DC difference) of the symbols that start in [p, limit), the first one at
-// absolute coefficient slot `pos`.
-template <class WIN>
-__device__ __forceinline__ void write_span2(const HuffShared2& hs, const uint8_t* s, uint32_t p, uint32_t limit, uint32_t phase,
-                                            uint64_t pos, uint64_t total_slots, int16_t* coef_base, int16_t* dcdiff,
-                                            int* status) {
-    if (pos >= total_slots) return;
-    uint32_t blk = phase >> 6, z = phase & 63;
-    int32_t bits_left = (int32_t)(limit - p);
-    WIN bw;
-    bw.init(s, p);
-    const uint32_t n_first = hs.n_first, nb = hs.nb;
-    uint32_t blocks_left = (uint32_t)((total_slots - pos + z) >> 6);  // counted from the start of the current block
-    int mx, my;
-    int16_t* dstblk;    // where the current block goes if its MCU is inside the ROI, else where the next inside block will
-    uint32_t step;      // 64 while the current MCU is inside the region of interest, else 0
-    {
-        const uint32_t mcu = (uint32_t)((pos >> 6) / nb);
-        mx = (int)(mcu % (uint32_t)hs.mcus_x);
-        my = (int)(mcu / (uint32_t)hs.mcus_x);
-        const int rmx = mx - hs.roi_mx0, rmy = my - hs.roi_my0, rcx = hs.roi_mcx, rcy = hs.roi_mcy;
-        const bool row_in = (unsigned)rmy < (unsigned)rcy;
-        const bool inside = row_in && (unsigned)rmx < (unsigned)rcx;
-        const int cy = min(max(rmy, 0), rcy), cx = row_in ? min(max(rmx, 0), rcx) : 0;  // ROI MCUs in front of this one
-        dstblk = coef_base + ((size_t)(cy * rcx + cx) * nb + (inside ? blk : 0u)) * 64;
-        step = inside ? 64u : 0u;
-    }
-    int16_t* dcp = dcdiff + (pos >> 6);
-    bool bad = false;
-    const uint32_t zzb = (uint32_t)__cvta_generic_to_shared(&hs.zz[0]);
-    const uint32_t dcF = (uint32_t)__cvta_generic_to_shared(&hs.dc2[0][0]), dcR = (uint32_t)__cvta_generic_to_shared(&hs.dc2[1][0]);
-    const uint32_t acF = (uint32_t)__cvta_generic_to_shared(&hs.ac2[0][0]), acR = (uint32_t)__cvta_generic_to_shared(&hs.ac2[1][0]);
-    uint32_t dcb = blk < n_first ? dcF : dcR, acb = blk < n_first ? acF : acR;
-    while (bits_left > 0) {
-        bw.refill();
-        const uint32_t top = bw.peek();
-        const bool isdc = z == 0;
-        const uint32_t idx = isdc ? (top >> (32 - kDcBits)) : (top >> (32 - kAcBits));
-        uint32_t lo;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"((isdc ? dcb : acb) + idx * 4u));
-        if (__builtin_expect(lo == 0 || lo >= 0x8000u, 0)) {
-            lo = slow_symbol2(hs, top, isdc, blk < n_first ? 0u : 1u, lo);
-            if (lo == 0) {
-                *status = -3;
-                break;
-            }
-        }
-        const uint32_t len = lo & 31u, sz = (lo >> 5) & 15u;
-        const bool ez = sz == 0 && !isdc;  // EOB or ZRL: nothing to store
-        const uint32_t zt = z + (lo >> 9) + 1u;
-        {
-            const uint32_t t2 = top << len;
-            const uint32_t raw = __funnelshift_l(t2, 0u, sz);  // next sz bits (0 when sz == 0)
-            const int val = (int)raw + ((int)t2 >= 0 ? (int)((0xFFFFFFFFu << sz) + 1u) : 0);  // T.81 F.2.2.1 EXTEND
-            uint32_t zi;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(zi) : "r"(zzb + ((zt - 1u) & 63u)));
-            int16_t* const where = isdc ? dcp : dstblk + zi;
-            const bool inblk = zt <= 64;
-            bad |= !ez && !inblk;  // coefficient index past 63: corrupt data
-            if (!ez && inblk && (isdc || step != 0)) *where = (int16_t)val;
-        }
-        bw.skip(len + sz);
-        bits_left -= (int32_t)(len + sz);
-        const bool fin = zt >= 64;
-        z = fin ? 0u : zt;
-        if (fin) {
-            blk++;
-            dstblk += step;
-            if (blk == nb) {
-                blk = 0;
-                if (++mx == hs.mcus_x) {
-                    mx = 0;
-                    my++;
-                }
-                step = ((unsigned)(mx - hs.roi_mx0) < (unsigned)hs.roi_mcx && (unsigned)(my - hs.roi_my0) < (unsigned)hs.roi_mcy) ? 64u : 0u;
-            }
-            dcb = blk < n_first ? dcF : dcR;
-            acb = blk < n_first ? acF : acR;
-            if (--blocks_left == 0) break;  // every MCU produced: the rest is padding
-            dcp++;
-        }
-    }
-    if (bad) *status = -3;
-}
-
-// The first version's write loop (per-MCU ROI address from the item, block bookkeeping as it was) over version 2's
-// table entries: the measurement variant that separates "new tables" from "new bookkeeping".
-template <class WIN>
-__device__ __forceinline__ void write_span2L(const HuffShared2& hs, const uint8_t* s, uint32_t p, uint32_t limit, uint32_t phase,
-                                             uint64_t pos, uint64_t total_slots, const JpegDecodeItem* it, int16_t* coef,
-                                             int16_t* dcdiff, int* status) {
-    if (pos >= total_slots) return;
-    uint32_t blk = phase >> 6, z = phase & 63;
-    int32_t bits_left = (int32_t)(limit - p);
-    WIN bw;
-    bw.init(s, p);
-    const int nb = (int)hs.nb;
-    int16_t* dstblk = nullptr;
-    bool inside = false;
-    int16_t* dcp = nullptr;
-    int mx = 0, my = 0;
-    uint32_t blocks_left = (uint32_t)((total_slots - pos + z) >> 6);
-    bool bad = false;
-    int16_t* coef_base = coef + it->coef_off;
-    const uint32_t zzb = (uint32_t)__cvta_generic_to_shared(&hs.zz[0]);
-    auto set_mcu = [&]() {
-        const int rmx = mx - it->roi_mx0, rmy = my - it->roi_my0, rcx = it->roi_mcx;
-        inside = (unsigned)rmx < (unsigned)rcx && (unsigned)rmy < (unsigned)it->roi_mcy;
-        dstblk = coef_base + ((size_t)rmy * rcx + rmx) * ((size_t)nb * 64);
-    };
-    {
-        const uint32_t mcu = (uint32_t)((pos >> 6) / (uint32_t)nb);
-        const uint32_t mcus_x = (uint32_t)it->mcus_x;
-        mx = (int)(mcu % mcus_x);
-        my = (int)(mcu / mcus_x);
-        set_mcu();
-        dstblk += blk * 64;
-        dcp = dcdiff + (pos >> 6);
-    }
-    const uint32_t n_first = hs.n_first;
-    const uint32_t dcF = (uint32_t)__cvta_generic_to_shared(&hs.dc2[0][0]), dcR = (uint32_t)__cvta_generic_to_shared(&hs.dc2[1][0]);
-    const uint32_t acF = (uint32_t)__cvta_generic_to_shared(&hs.ac2[0][0]), acR = (uint32_t)__cvta_generic_to_shared(&hs.ac2[1][0]);
-    uint32_t dcb = blk < n_first ? dcF : dcR, acb = blk < n_first ? acF : acR;
-    while (bits_left > 0) {
-        bw.refill();
-        const uint32_t top = bw.peek();
-        const bool isdc = z == 0;
-        const uint32_t idx = isdc ? (top >> (32 - kDcBits)) : (top >> (32 - kAcBits));
-        uint32_t lo;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"((isdc ? dcb : acb) + idx * 4u));
-        if (__builtin_expect(lo == 0 || lo >= 0x8000u, 0)) {
-            lo = slow_symbol2(hs, top, isdc, blk < n_first ? 0u : 1u, lo);
-            if (lo == 0) {
-                *status = -3;
-                break;
-            }
-        }
-        const uint32_t len = lo & 31u, sz = (lo >> 5) & 15u;
-        const bool ez = sz == 0 && !isdc;
-        const uint32_t zt = z + (lo >> 9) + 1u;
-        {
-            const uint32_t t2 = top << len;
-            const uint32_t raw = __funnelshift_l(t2, 0u, sz);
-            const int val = (int)raw + ((int)t2 >= 0 ? (int)((0xFFFFFFFFu << sz) + 1u) : 0);
-            uint32_t zi;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(zi) : "r"(zzb + ((zt - 1u) & 63u)));
-            int16_t* const where = isdc ? dcp : dstblk + zi;
-            const bool inblk = zt <= 64;
-            bad |= !ez && !inblk;
-            if (!ez && inblk && (isdc || inside)) *where = (int16_t)val;
-        }
-        bw.skip(len + sz);
-        bits_left -= (int32_t)(len + sz);
-        const bool fin = zt >= 64;
-        z = fin ? 0u : zt;
-        if (fin) {
-            blk++;
-            dstblk += 64;
-            if (blk == (uint32_t)nb) {
-                blk = 0;
-                if (++mx == it->mcus_x) {
-                    mx = 0;
-                    my++;
-                }
-                set_mcu();
-            }
-            dcb = blk < n_first ? dcF : dcR;
-            acb = blk < n_first ? acF : acR;
-            if (--blocks_left == 0) break;
-            dcp++;
-        }
-    }
-    if (bad) *status = -3;
-}
-
-template <bool PAIR, class WIN, int WR>
-__global__ void __launch_bounds__(kHuffThreads, LP_HUFF_MIN_CTAS)
-    jpeg_huff_sync2_kernel(JpegDecodeItem* items, const JpegHuffSet* tables, const uint8_t* clean,
-                           SubState* states_all, uint32_t* nslots_all, int16_t* coef, int16_t* dcdiff_all,
-                           uint32_t sub_per_thread) {
-    __shared__ HuffShared2 hs;
-    __shared__ uint32_t warp_sums[kHuffThreads / 32];
-    __shared__ uint32_t s_carry;
-    __shared__ int s_status;
-    JpegDecodeItem& it = items[blockIdx.x];
-    const int tid = threadIdx.x;
-    if (it.status != 0 || it.restart_interval != 0) return;
-    if (!two_table_layout(it)) return;  // the first version of the kernel takes these
-    __shared__ long long s_tphase;
-    if (tid == 0) s_tphase = clock64();
-    int nb = 0;
-    for (int c = 0; c < it.ncomp; c++) nb += it.h[c] * it.v[c];
-    // ---- per-CTA tables
-    const JpegHuffSet* g = tables + it.table_set;
-    const int rest_c = it.ncomp > 1 ? 1 : 0;
-    const int dc_id0 = it.td[0], dc_id1 = it.td[rest_c], ac_id0 = it.ta[0], ac_id1 = it.ta[rest_c];  // (selects below: no local array)
-    for (int i = tid; i < 4 * 18; i += kHuffThreads) {
-        const int t = i / 18, src = t == 0 ? dc_id0 : t == 1 ? dc_id1 : t == 2 ? 4 + ac_id0 : 4 + ac_id1;
-        hs.maxcode[t][i % 18] = g->maxcode[src][i % 18];
-    }
-    for (int i = tid; i < 4 * 17; i += kHuffThreads) {
-        const int t = i / 17, src = t == 0 ? dc_id0 : t == 1 ? dc_id1 : t == 2 ? 4 + ac_id0 : 4 + ac_id1;
-        hs.valoffset[t][i % 17] = g->valoffset[src][i % 17];
-    }
-    for (int i = tid; i < 4 * 256; i += kHuffThreads) {
-        const int t = i >> 8, src = t == 0 ? dc_id0 : t == 1 ? dc_id1 : t == 2 ? 4 + ac_id0 : 4 + ac_id1;
-        hs.vals[t][i & 255] = g->vals[src][i & 255];
-    }
-    for (int i = tid; i < 2 * (1 << kDcBits); i += kHuffThreads) {
-        const int t = i >> kDcBits, idx = i & ((1 << kDcBits) - 1);
-        hs.dc2[t][idx] = sym_entry(g->look[t ? dc_id1 : dc_id0][idx], true);
-    }
-    if (tid < 64) hs.zz[tid] = c_zigzag_p[tid];
-    if (tid == 0) {
-        hs.n_first = (uint32_t)(it.h[0] * it.v[0]);
-        hs.nb = (uint32_t)nb;
-        hs.mcus_x = it.mcus_x;
-        hs.roi_mx0 = it.roi_mx0;
-        hs.roi_my0 = it.roi_my0;
-        hs.roi_mcx = it.roi_mcx;
-        hs.roi_mcy = it.roi_mcy;
-        s_status = 0;
-        s_carry = 0;
-    }
-    __syncthreads();
-    // one-symbol entries: the 9-bit lookahead widened to kAcBits, then the codes of 10..kAcBits bits
-    for (int i = tid; i < 2 * (1 << kAcBits); i += kHuffThreads) {
-        const int t = i >> kAcBits, idx = i & ((1 << kAcBits) - 1);
-        uint32_t e = g->look[4 + (t ? ac_id1 : ac_id0)][idx >> (kAcBits - 9)];
-        if (!e) {
-            for (int len = 10; len <= kAcBits; len++) {
-                const int code = idx >> (kAcBits - len);
-                if (code <= hs.maxcode[2 + t][len]) {
-                    e = (uint32_t)(len << 8) | hs.vals[2 + t][(code + hs.valoffset[2 + t][len]) & 0xFF];
-                    break;
-                }
-            }
-        }
-        hs.ac2[t][idx] = sym_entry(e, false);
-    }
-    for (int i = tid; i < 2 * kHuffLongPrefixes * 16; i += kHuffThreads) {
-        const int t = i / (kHuffLongPrefixes * 16), r = i % (kHuffLongPrefixes * 16);
-        (&hs.ac_sub[0][0])[i] = (uint16_t)sym_entry(g->long_sub[t ? ac_id1 : ac_id0][r >> 4][r & 15], false);
-    }
-    __syncthreads();
-    if (tid < 2 * kHuffLongPrefixes) {
-        const int t = tid / kHuffLongPrefixes;
-        const uint32_t pfx = g->long_prefix[t ? ac_id1 : ac_id0][tid % kHuffLongPrefixes];  // 0xFFFF = unused slot
-        if (pfx < (1u << kAcBits)) hs.ac2[t][pfx] = 0x8000u | (uint32_t)tid;
-    }
-    __syncthreads();
-    // two-symbol halves: the second code must lie wholly inside the window bits the first one leaves
-    for (int i = tid; i < 2 * (1 << kAcBits); i += kHuffThreads) {
-        const int t = i >> kAcBits, idx = i & ((1 << kAcBits) - 1);
-        const uint32_t lo = hs.ac2[t][idx] & 0xFFFFu;
-        uint32_t hi = 0;
-        if (lo != 0 && lo < 0x8000u) {
-            const uint32_t used1 = (lo & 31u) + ((lo >> 5) & 15u), adv1 = (lo >> 9) + 1u;
-            if (used1 < (uint32_t)kAcBits && adv1 != 64u) {
-                const uint32_t lo2 = hs.ac2[t][(idx << used1) & ((1u << kAcBits) - 1)] & 0xFFFFu;
-                if (lo2 != 0 && lo2 < 0x8000u && (lo2 & 31u) <= (uint32_t)kAcBits - used1)
-                    hi = (used1 + (lo2 & 31u) + ((lo2 >> 5) & 15u)) | (adv1 + (lo2 >> 9) + 1u) << 5;
-            }
-        }
-        reinterpret_cast<uint16_t*>(&hs.ac2[t][idx])[1] = (uint16_t)hi;  // the high half only: low halves are being read
-    }
-    __syncthreads();
-    const uint8_t* s = clean + it.clean_off;
-    const uint32_t total_bits = it.clean_len * 8u;
-    uint32_t kSubBits = (total_bits + kHuffThreads * sub_per_thread - 1) / (kHuffThreads * sub_per_thread);
-    kSubBits = max(kMinSubBits, (kSubBits + 31u) & ~31u);
-    const uint32_t nsub = (total_bits + kSubBits - 1) / kSubBits;
-    SubState* st = states_all + it.state_off;
-    uint32_t* ns = nslots_all + it.state_off;
-    uint32_t* list_a = reinterpret_cast<uint32_t*>(st + nsub);
-    uint32_t* list_b = list_a + nsub;
-    const uint64_t total_slots = (uint64_t)it.mcus_x * it.mcus_y * nb * 64;
-    int16_t* dcdiff = dcdiff_all + it.dcdiff_off;
-
-    LP_PHASE_MARK(0);
-    // ---- pass 0: every subsequence from a guessed state (exact only for subsequence 0)
-    for (uint32_t i = tid; i < nsub; i += kHuffThreads) {
-        uint32_t p = i * kSubBits, phase = 0, n = 0;
-        const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-        count_span2<PAIR, WIN>(hs, s, p, limit, phase, n);
-        st[i] = SubState{p, phase};
-        ns[i] = n;
-    }
-    __syncthreads();
-    LP_PHASE_MARK(1);
-    // ---- synchronisation rounds (see the first version for the argument)
-    uint32_t* cur_list = list_a;
-    uint32_t* nxt_list = list_b;
-    uint32_t cur_count = nsub > 0 ? nsub - 1 : 0;
-    bool first_round = true;
-    uint32_t rounds = 0;
-    while (cur_count > 0) {
-        rounds++;
-        if (tid == 0) s_carry = 0;
-        __syncthreads();
-        for (uint32_t k = tid; k < cur_count; k += kHuffThreads) {
-            const uint32_t i = first_round ? k + 1 : cur_list[k];
-            const uint64_t in64 = *reinterpret_cast<volatile uint64_t*>(&st[i - 1]);
-            const SubState old = st[i];
-            uint32_t p = (uint32_t)in64, phase = (uint32_t)(in64 >> 32), n = 0;
-            const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-            if (p < limit) count_span2<PAIR, WIN>(hs, s, p, limit, phase, n);
-            ns[i] = n;
-            if (p != old.p || phase != old.phase) {
-                *reinterpret_cast<volatile uint64_t*>(&st[i]) = ((uint64_t)phase << 32) | p;
-                if (i + 1 < nsub) nxt_list[atomicAdd(&s_carry, 1u)] = i + 1;
-            }
-        }
-        __syncthreads();
-        cur_count = s_carry;
-        __syncthreads();
-        uint32_t* t = cur_list;
-        cur_list = nxt_list;
-        nxt_list = t;
-        first_round = false;
-    }
-    if (tid == 0) it.pad_ = rounds;
-    LP_PHASE_MARK(2);
-    // ---- prefix sum of slot counts, then the writing decode
-    uint64_t slots_before = 0;
-    int16_t* coef_base = coef + it.coef_off;
-    for (uint32_t base = 0; base < nsub; base += kHuffThreads) {
-        const uint32_t i = base + tid;
-        const uint32_t v = i < nsub ? ns[i] : 0;
-        uint32_t total;
-        const uint32_t ex = block_excl_scan<kHuffThreads>(v, &total, warp_sums);
-        const uint64_t pos = slots_before + ex;
-        slots_before += total;
-        if (i < nsub) {
-            const uint32_t p = i == 0 ? 0u : st[i - 1].p;
-            const uint32_t phase = i == 0 ? 0u : st[i - 1].phase;
-            const uint32_t limit = min((i + 1) * kSubBits, total_bits);
-            int status = 0;
-            if (pos < total_slots && (uint32_t)(pos % ((uint64_t)nb * 64)) != ((phase >> 6) * 64 + (phase & 63))) status = -3;
-            if (!status && p < limit) {
-                if (WR == 0) write_span2<WIN>(hs, s, p, limit, phase, pos, total_slots, coef_base, dcdiff, &status);
-                else write_span2L<WIN>(hs, s, p, limit, phase, pos, total_slots, &it, coef, dcdiff, &status);
-            }
-            if (status) s_status = status;
-        }
-    }
-    if (tid == 0 && slots_before < total_slots) s_status = -3;  // the stream ended before the last MCU
-    __syncthreads();
-    if (s_status) {
-        if (tid == 0) it.status = s_status;
-        return;
-    }
-    LP_PHASE_MARK(3);
-    dc_prefix_pass(it, coef, dcdiff, nb, warp_sums);
-    LP_PHASE_MARK(4);
-    if (tid == 0) atomicAdd(&g_huff_phase[5], 1ull);
-}
 
 // ------------------------------------------------------------------ launcher
 
@@ -1219,35 +686,11 @@ int jpeg_huff_parallel_launch(const JpegHuffParallelArgs& a, cudaStream_t st) {
     jpeg_unstuff_kernel<<<a.n, kHuffThreads, 0, st>>>(a.items, a.scan, a.clean);
     g_launches++;
     LP_CUDA_OK(cudaGetLastError());
-    // LP_HUFF_V: 1 = every image on the first version of the kernel; 2 (default) = version 2 with two-symbol entries and
-    // two stream words in flight; 3 / 4 / 5 = version 2 without one or both of those (measurement variants)
-    static const int hv = getenv("LP_HUFF_V") ? atoi(getenv("LP_HUFF_V")) : 1;
-    const int v2 = hv >= 2;
-    // measurement only: LP_HUFF_NOSTORE=1 drops the AC coefficient stores of the first version's write pass (wrong pixels)
-    static const int nostore = getenv("LP_HUFF_NOSTORE") ? atoi(getenv("LP_HUFF_NOSTORE")) : 0;
-    if (v2) {
-        SubState* stp = reinterpret_cast<SubState*>(a.states);
-#define LP_H2(P_, W_, R_) jpeg_huff_sync2_kernel<P_, W_, R_><<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean, stp, a.nslots, a.coef, a.dcdiff, spt)
-        switch (hv) {
-            case 3: LP_H2(true, BitWin2<1>, 0); break;   // the round's first measured form
-            case 4: LP_H2(false, BitWin2<2>, 0); break;
-            case 5: LP_H2(false, BitWin2<1>, 0); break;
-            case 6: LP_H2(true, BitWin2<1>, 1); break;
-            case 7: LP_H2(true, BitWinP, 0); break;
-            case 8: LP_H2(true, BitWin2<2>, 0); break;
-            default: LP_H2(true, BitWinP, 1); break;     // 2: two-symbol counting passes, the first version's write loop
-        }
-#undef LP_H2
-        g_launches++;
-        LP_CUDA_OK(cudaGetLastError());
-    }
-    {   // (with version 2 on, this one only decodes the images whose table layout version 2 does not take)
-        jpeg_huff_sync_kernel<<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean,
-                                                           reinterpret_cast<SubState*>(a.states), a.nslots, a.coef,
-                                                           a.dcdiff, spt, v2, nostore);
-        g_launches++;
-        LP_CUDA_OK(cudaGetLastError());
-    }
+    jpeg_huff_sync_kernel<<<a.n, kHuffThreads, 0, st>>>(a.items, a.tables, a.clean,
+                                                       reinterpret_cast<SubState*>(a.states), a.nslots, a.coef,
+                                                       a.dcdiff, spt);
+    g_launches++;
+    LP_CUDA_OK(cudaGetLastError());
     return LP_OK;
 }
 

@@ -383,6 +383,89 @@ LP_VP8_FN void decide_proba(uint32_t c0, uint32_t c1, int old_p, int update_p, u
     *update = use_new ? 1 : 0;
 }
 
+// ---- 4x4 intra modes (RFC 6386 s.8.3 / 12.3) ------------------------------------------------------------------------
+// Per macroblock 2 + 16 bytes of mode information: [0] = the 16x16 luma mode (0..3) or kI4 when the macroblock predicts
+// its sixteen 4x4 blocks one by one, [1] = the chroma mode, [2..17] = the sub-block modes in raster order.  A 16x16
+// macroblock fills them with its own mode, which is what its neighbours' sub-block modes are coded against (s.8.3).
+constexpr int kModeStride = 18;
+constexpr int kI4 = 4;
+constexpr int kTryI4 = 1;  // what the product encodes with (Params::try_i4 of the device launchers and of the host build)
+
+// cost, in 1/256 bit, of a bit coded with probability `p` of being 0
+LP_VP8_INL int bit_cost(int bit, int p) { return kVp8EntropyCost[bit ? 255 - p : p]; }
+
+// the sub-block mode tree of s.8.3 (kVp8YModesIntra4) walked for `mode`: PUT = code it, else return its cost
+template <bool PUT>
+LP_VP8_FN int i4_mode(BoolEnc* e, int mode, const uint8_t* prob) {
+    int cost = 0;
+#define LP_BM(bit_, k_)                              \
+    ((PUT ? (be_put(*e, (bit_), prob[k_]), 0) : (cost += bit_cost((bit_), prob[k_]))), (bit_))
+    if (LP_BM(mode != vp8::B_DC, 0)) {
+        if (LP_BM(mode != vp8::B_TM, 1)) {
+            if (LP_BM(mode != vp8::B_VE, 2)) {
+                if (!LP_BM(mode >= vp8::B_LD, 3)) {
+                    if (LP_BM(mode != vp8::B_HE, 4)) LP_BM(mode != vp8::B_RD, 5);
+                } else {
+                    if (LP_BM(mode != vp8::B_LD, 6)) {
+                        if (LP_BM(mode != vp8::B_VL, 7)) LP_BM(mode != vp8::B_HD, 8);
+                    }
+                }
+            }
+        }
+    }
+#undef LP_BM
+    return cost;
+}
+
+// put_coeffs with the coder replaced by a bit count (1/256 bit) under the default probabilities: the rate estimate
+// of the 16x16-versus-4x4 decision.  Returns the cost; *nz = what put_coeffs would return.
+LP_VP8_FN int cost_coeffs(int type, int ctx, int first, const int16_t* levels, int* nz) {
+    const uint8_t bands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
+    const uint8_t zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+    const uint8_t* tp = &kVp8CoeffProba0[0][0][0][0] + type * (8 * 3 * 11);
+    const int last = last_nonzero(levels, first);
+    int n = first, cost = 0;
+    const uint8_t* p = tp + (bands[n] * 3 + ctx) * 11;
+    *nz = last >= 0;
+    if (last < 0) return bit_cost(0, p[0]);
+    cost += bit_cost(1, p[0]);
+    while (n < 16) {
+        const int c = levels[zigzag[n]];
+        const int v = c < 0 ? -c : c;
+        if (!v) {
+            cost += bit_cost(0, p[1]);
+            p = tp + (bands[++n] * 3 + 0) * 11;
+            continue;
+        }
+        cost += bit_cost(1, p[1]) + 256;  // + the sign
+        int next_ctx;
+        if (v == 1) {
+            cost += bit_cost(0, p[2]);
+            next_ctx = 1;
+        } else {
+            cost += bit_cost(1, p[2]);
+            next_ctx = 2;
+            if (v <= 4) {
+                cost += bit_cost(0, p[3]) + bit_cost(v != 2, p[4]) + (v != 2 ? bit_cost(v == 4, p[5]) : 0);
+            } else if (v <= 10) {
+                cost += bit_cost(1, p[3]) + bit_cost(0, p[6]) + bit_cost(v > 6, p[7]) + (v > 6 ? 512 : 256);
+            } else {
+                const int cat = v < 19 ? 0 : v < 35 ? 1 : v < 67 ? 2 : 3;
+                cost += bit_cost(1, p[3]) + bit_cost(1, p[6]) + bit_cost(cat >> 1, p[8]) + bit_cost(cat & 1, p[9 + (cat >> 1)]) +
+                        256 * (cat == 3 ? 11 : cat + 3);  // extra bits: about one bit each
+            }
+        }
+        if (++n == 16) break;
+        p = tp + (bands[n] * 3 + next_ctx) * 11;
+        if (n > last) {
+            cost += bit_cost(0, p[0]);
+            break;
+        }
+        cost += bit_cost(1, p[0]);
+    }
+    return cost;
+}
+
 // ---- colour conversion (BT.601 limited range, 16.16 fixed point like libwebp's importer) -----
 LP_VP8_INL int rgb_to_y(int r, int g, int b) { return (16839 * r + 33059 * g + 6420 * b + (16 << 16) + (1 << 15)) >> 16; }
 // r, g, b are SUMS over a 2x2 block
@@ -422,11 +505,12 @@ struct Params {
     int width, height, mb_w, mb_h;
     int q;             // quantiser index 0..127
     int filter_level;  // 0..63
+    int try_i4;        // 1 = weigh sixteen 4x4 predictions against the 16x16 one per macroblock
 };
 
 // Source planes: mb_w*16 x mb_h*16 luma, half-size chroma, padded by edge replication.
 // recon_*: same geometry, written here (the decoder's unfiltered reconstruction).
-// levels: mb_w*mb_h*25*16 int16 (blocks 0..15 Y, 16..19 U, 20..23 V, 24 Y2), modes: 2 bytes per MB.
+// levels: mb_w*mb_h*25*16 int16 (blocks 0..15 Y, 16..19 U, 20..23 V, 24 Y2), modes: kModeStride bytes per MB.
 struct Buffers {
     const uint8_t *sy, *su, *sv;
     uint8_t *ry, *ru, *rv;
@@ -442,6 +526,49 @@ LP_VP8_FN uint32_t sse_block(const uint8_t* a, int as, const uint8_t* b, int bs,
             s += (uint32_t)(d * d);
         }
     return s;
+}
+
+// The sixteen 4x4 blocks of a macroblock predicted one by one (s.12.3): for every block the mode with the least
+// prediction error + mode cost, then transform, quantisation and reconstruction, because the next block predicts from
+// this one's reconstruction.  `yd` = the macroblock inside its bordered work buffer (borders and the above-right samples
+// set by the caller, as the decoder sets them); top_modes / left_modes = the neighbours' sub-block modes (updated to
+// this macroblock's on return).  Outputs: levels[16][16], modes[16], the reconstruction in yd.
+// Returns distortion (SSE) and adds the rate estimate (1/256 bit) to *rate.
+LP_VP8_FN uint32_t analyse_i4(const uint8_t* sy, int ys, uint8_t* yd, const int* y1q, int lambda4, uint8_t* top_modes,
+                              uint8_t* left_modes, int16_t* levels, uint8_t* modes, uint32_t* rate) {
+    uint32_t dist = 0, bits = 0;
+    uint8_t tnz[4] = {0, 0, 0, 0}, lnz[4] = {0, 0, 0, 0};  // contexts of the rate estimate only
+    int16_t coeffs[16];
+    for (int r = 1; r < 4; r++)  // the above-right samples of the macroblock serve every row of sub-blocks
+        for (int i = 16; i < 20; i++) yd[(4 * r - 1) * BPS + i] = yd[i - BPS];
+    for (int n = 0; n < 16; n++) {
+        const int bx = n & 3, by = n >> 2;
+        uint8_t* d = yd + by * 4 * BPS + bx * 4;
+        const uint8_t* src = sy + by * 4 * ys + bx * 4;
+        const uint8_t* prob = kVp8BModesProba[top_modes[bx]][left_modes[by]];
+        int best_mode = 0;
+        uint32_t best = 0xffffffffu;
+        for (int m = 0; m < 10; m++) {
+            vp8::pred_4x4(d, BPS, m);
+            const uint32_t score = sse_block(src, ys, d, BPS, 4) * 256u + (uint32_t)(i4_mode<false>(nullptr, m, prob) * lambda4);
+            if (score < best) {
+                best = score;
+                best_mode = m;
+            }
+        }
+        vp8::pred_4x4(d, BPS, best_mode);
+        fdct4x4(src, ys, d, BPS, coeffs);
+        quantize_block(coeffs, levels + n * 16, y1q, 0, 96, 110);
+        vp8::inverse_dct_add(coeffs, d, BPS);
+        dist += sse_block(src, ys, d, BPS, 4);
+        int nz;
+        bits += (uint32_t)i4_mode<false>(nullptr, best_mode, prob) + (uint32_t)cost_coeffs(3, tnz[bx] + lnz[by], 0, levels + n * 16, &nz);
+        tnz[bx] = lnz[by] = (uint8_t)nz;
+        modes[n] = (uint8_t)best_mode;
+        top_modes[bx] = left_modes[by] = (uint8_t)best_mode;
+    }
+    *rate += bits;
+    return dist;
 }
 
 // Pass 1: mode decision, transform, quantisation and reconstruction of every macroblock, raster order.
@@ -507,20 +634,92 @@ LP_VP8_FN void analyse_and_reconstruct(const Params& P, const Buffers& B) {
             vp8::pred_block(vd, BPS, 8, uvmode, mb_y > 0, mb_x > 0);
             // residual transforms + quantisation
             int16_t* lv = B.levels + ((size_t)mb_y * P.mb_w + mb_x) * 25 * 16;
+            uint8_t* md = B.modes + ((size_t)mb_y * P.mb_w + mb_x) * kModeStride;
             for (int n = 0; n < 16; n++)
                 fdct4x4(sy + (n >> 2) * 4 * ys + (n & 3) * 4, ys, yd + (n >> 2) * 4 * BPS + (n & 3) * 4, BPS, coeffs + n * 16);
             fwht(coeffs, coeffs + 24 * 16);
             quantize_block(coeffs + 24 * 16, lv + 24 * 16, qm.y2, 0, 96, 108);
             vp8::inverse_wht(coeffs + 24 * 16, coeffs);  // plants the dequantised DCs
             for (int n = 0; n < 16; n++) quantize_block(coeffs + n * 16, lv + n * 16, qm.y1, 1, 96, 110);
+            // ---- 16x16 or sixteen 4x4 predictions?  Both are carried to their reconstruction; the smaller
+            //      distortion + lambda * estimated bits wins (lambda = q^2 / 128 per bit, libwebp's mode lambda).
+            uint8_t top_modes[4], left_modes[4];
+            for (int i = 0; i < 4; i++) {
+                top_modes[i] = mb_y > 0 ? (md - (size_t)P.mb_w * kModeStride)[2 + 12 + i] : (uint8_t)vp8::B_DC;
+                left_modes[i] = mb_x > 0 ? (md - kModeStride)[2 + 4 * i + 3] : (uint8_t)vp8::B_DC;
+            }
+            bool use_i4 = false;
+            if (P.try_i4) {
+                // the 16x16 candidate's reconstruction, distortion and rate
+                uint8_t y16[16 * 16];
+                {
+                    int16_t rc[16];
+                    for (int n = 0; n < 16; n++) {
+                        uint8_t* d = yd + (n >> 2) * 4 * BPS + (n & 3) * 4;
+                        for (int k = 0; k < 16; k++) rc[k] = coeffs[n * 16 + k];
+                        uint8_t blk[4 * BPS];  // reconstruct into a scratch copy: yd keeps the prediction for the 4x4 trial's borders
+                        for (int j = 0; j < 4; j++)
+                            for (int i = 0; i < 4; i++) blk[j * BPS + i] = d[j * BPS + i];
+                        vp8::inverse_dct_add(rc, blk, BPS);
+                        for (int j = 0; j < 4; j++)
+                            for (int i = 0; i < 4; i++) y16[((n >> 2) * 4 + j) * 16 + (n & 3) * 4 + i] = blk[j * BPS + i];
+                    }
+                }
+                uint32_t d16 = sse_block(sy, ys, y16, 16, 16), r16 = 0;
+                {
+                    int nz;
+                    r16 += (uint32_t)cost_coeffs(1, 0, 0, lv + 24 * 16, &nz);
+                    uint8_t tnz[4] = {0, 0, 0, 0}, lnz[4] = {0, 0, 0, 0};
+                    for (int n = 0; n < 16; n++) {
+                        r16 += (uint32_t)cost_coeffs(0, tnz[n & 3] + lnz[n >> 2], 1, lv + n * 16, &nz);
+                        tnz[n & 3] = lnz[n >> 2] = (uint8_t)nz;
+                    }
+                    r16 += (uint32_t)bit_cost(1, 145) + 512;  // "not 4x4" + about two bits of 16x16 mode
+                }
+                // the 4x4 candidate in a copy of the work buffer (same borders)
+                uint8_t yb4[vp8::YB_SIZE];
+                for (int k = 0; k < vp8::YB_SIZE; k++) yb4[k] = yb[k];
+                uint8_t* yd4 = yb4 + BPS + 8;
+                // above-right samples: from the row above (the decoder's rule at the right edge and on the first row)
+                for (int i = 16; i < 20; i++)
+                    yd4[i - BPS] = mb_y > 0 ? (mb_x < P.mb_w - 1 ? py[i - ys] : py[15 - ys]) : 127;
+                int16_t lv4[16 * 16];
+                uint8_t m4[16], tm4[4], lm4[4];
+                for (int i = 0; i < 4; i++) {
+                    tm4[i] = top_modes[i];
+                    lm4[i] = left_modes[i];
+                }
+                const int q = qm.y1[1];
+                uint32_t r4 = (uint32_t)bit_cost(0, 145);
+                const uint32_t d4 = analyse_i4(sy, ys, yd4, qm.y1, (3 * q * q) >> 7, tm4, lm4, lv4, m4, &r4);
+                const uint64_t lam = (uint64_t)((q * q) >> 7);
+                const uint64_t s16 = (uint64_t)d16 * 256 + (uint64_t)r16 * lam, s4 = (uint64_t)d4 * 256 + (uint64_t)r4 * lam;
+                if (s4 < s16) {
+                    use_i4 = true;
+                    for (int k = 0; k < 16 * 16; k++) lv[k] = lv4[k];
+                    for (int k = 0; k < 16; k++) lv[24 * 16 + k] = 0;
+                    for (int j = 0; j < 16; j++)
+                        for (int i = 0; i < 16; i++) yd[j * BPS + i] = yd4[j * BPS + i];
+                    md[0] = (uint8_t)kI4;
+                    for (int k = 0; k < 16; k++) md[2 + k] = m4[k];
+                } else {
+                    for (int j = 0; j < 16; j++)
+                        for (int i = 0; i < 16; i++) yd[j * BPS + i] = y16[j * 16 + i];
+                }
+            }
+            if (!use_i4) {
+                md[0] = (uint8_t)ymode;
+                for (int k = 0; k < 16; k++) md[2 + k] = (uint8_t)ymode;  // what the neighbours' sub-block modes are coded against
+                if (!P.try_i4)
+                    for (int n = 0; n < 16; n++) vp8::inverse_dct_add(coeffs + n * 16, yd + (n >> 2) * 4 * BPS + (n & 3) * 4, BPS);
+            }
             for (int n = 0; n < 4; n++) {
                 fdct4x4(su + (n >> 1) * 4 * cs + (n & 1) * 4, cs, ud + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS, coeffs + (16 + n) * 16);
                 fdct4x4(sv + (n >> 1) * 4 * cs + (n & 1) * 4, cs, vd + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS, coeffs + (20 + n) * 16);
                 quantize_block(coeffs + (16 + n) * 16, lv + (16 + n) * 16, qm.uv, 0, 110, 115);
                 quantize_block(coeffs + (20 + n) * 16, lv + (20 + n) * 16, qm.uv, 0, 110, 115);
             }
-            // reconstruction, exactly as the decoder will do it
-            for (int n = 0; n < 16; n++) vp8::inverse_dct_add(coeffs + n * 16, yd + (n >> 2) * 4 * BPS + (n & 3) * 4, BPS);
+            // chroma reconstruction, exactly as the decoder will do it (luma: above)
             for (int n = 0; n < 4; n++) {
                 vp8::inverse_dct_add(coeffs + (16 + n) * 16, ud + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
                 vp8::inverse_dct_add(coeffs + (20 + n) * 16, vd + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
@@ -532,8 +731,7 @@ LP_VP8_FN void analyse_and_reconstruct(const Params& P, const Buffers& B) {
                     pu[j * cs + i] = ud[j * BPS + i];
                     pv[j * cs + i] = vd[j * BPS + i];
                 }
-            B.modes[((size_t)mb_y * P.mb_w + mb_x) * 2 + 0] = (uint8_t)ymode;
-            B.modes[((size_t)mb_y * P.mb_w + mb_x) * 2 + 1] = (uint8_t)uvmode;
+            md[1] = (uint8_t)uvmode;
         }
 }
 
@@ -594,15 +792,27 @@ LP_VP8_FN size_t write_part0(const Params& P, const Buffers& B, const uint8_t* a
     be_put_bits(h, (uint32_t)use_skip, 1);  // mb_no_coeff_skip
     if (use_skip) be_put_bits(h, (uint32_t)skip_p, 8);
     for (int i = 0; i < P.mb_w * P.mb_h; i++) {
-        const int ymode = B.modes[i * 2], uvmode = B.modes[i * 2 + 1];
+        const uint8_t* md = B.modes + (size_t)i * kModeStride;
+        const int ymode = md[0], uvmode = md[1];
+        const int mb_x = i % P.mb_w, mb_y = i / P.mb_w;
         if (use_skip) be_put(h, mb_is_skippable(B.levels + (size_t)i * 25 * 16), skip_p);
-        be_put(h, 1, 145);  // not 4x4
-        if (ymode == vp8::TM_PRED || ymode == vp8::H_PRED) {
-            be_put(h, 1, 156);
-            be_put(h, ymode == vp8::TM_PRED, 128);
+        if (ymode == kI4) {
+            be_put(h, 0, 145);  // sixteen 4x4 modes, each coded against the modes above and to the left (s.8.3)
+            for (int n = 0; n < 16; n++) {
+                const int bx = n & 3, by = n >> 2;
+                const int top = by > 0 ? md[2 + n - 4] : mb_y > 0 ? (md - (size_t)P.mb_w * kModeStride)[2 + 12 + bx] : (int)vp8::B_DC;
+                const int left = bx > 0 ? md[2 + n - 1] : mb_x > 0 ? (md - kModeStride)[2 + 4 * by + 3] : (int)vp8::B_DC;
+                i4_mode<true>(&h, md[2 + n], kVp8BModesProba[top][left]);
+            }
         } else {
-            be_put(h, 0, 156);
-            be_put(h, ymode == vp8::V_PRED, 163);
+            be_put(h, 1, 145);  // one 16x16 mode
+            if (ymode == vp8::TM_PRED || ymode == vp8::H_PRED) {
+                be_put(h, 1, 156);
+                be_put(h, ymode == vp8::TM_PRED, 128);
+            } else {
+                be_put(h, 0, 156);
+                be_put(h, ymode == vp8::V_PRED, 163);
+            }
         }
         if (uvmode == vp8::DC_PRED) {
             be_put(h, 0, 142);
@@ -646,26 +856,36 @@ LP_VP8_FN size_t walk_partition(const Params& P, const Buffers& B, int part, int
             if (skippable && (use_skip || !CODE)) {
                 // statistics pass: assume the frame WILL use skip flags when it has skippable macroblocks (decided
                 // in finish_statistics from the same counts), so their would-be tokens are not counted
-                for (int k = 0; k < 9; k++) left_nz[k] = 0;
+                for (int k = 0; k < 8; k++) left_nz[k] = 0;
+                if (B.modes[((size_t)mb_y * P.mb_w + mb_x) * kModeStride] != kI4) left_nz[8] = 0;
                 continue;
             }
+            const uint8_t* md = B.modes + ((size_t)mb_y * P.mb_w + mb_x) * kModeStride;
+            const bool i4 = md[0] == kI4;
             uint8_t tnz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (mb_y > 0) {  // bottom blocks of the macroblock above
                 const int16_t* up = lv - (size_t)P.mb_w * 25 * 16;
-                for (int i = 0; i < 4; i++) tnz[i] = (uint8_t)block_nz(up + (12 + i) * 16, 1);
+                const bool up_i4 = (md - (size_t)P.mb_w * kModeStride)[0] == kI4;
+                for (int i = 0; i < 4; i++) tnz[i] = (uint8_t)block_nz(up + (12 + i) * 16, up_i4 ? 0 : 1);
                 tnz[4] = (uint8_t)block_nz(up + 18 * 16, 0);
                 tnz[5] = (uint8_t)block_nz(up + 19 * 16, 0);
                 tnz[6] = (uint8_t)block_nz(up + 22 * 16, 0);
                 tnz[7] = (uint8_t)block_nz(up + 23 * 16, 0);
-                tnz[8] = (uint8_t)block_nz(up + 24 * 16, 0);
+                if (!i4) {
+                    // the Y2 context above is that of the nearest macroblock above that HAS a Y2 block: 4x4 macroblocks
+                    // neither read nor write it (s.13.3; the decoder carries it across them)
+                    int r = mb_y - 1;
+                    while (r >= 0 && B.modes[((size_t)r * P.mb_w + mb_x) * kModeStride] == kI4) r--;
+                    tnz[8] = r >= 0 ? (uint8_t)block_nz(B.levels + (((size_t)r * P.mb_w + mb_x) * 25 + 24) * 16, 0) : 0;
+                }
             }
-            for (int k = -1; k < 24; k++) {  // Y2, 16 Y, 4 U, 4 V: the decoder's order and contexts
+            for (int k = i4 ? 0 : -1; k < 24; k++) {  // [Y2], 16 Y, 4 U, 4 V: the decoder's order and contexts
                 int type, ti, li, first = 0;
                 const int16_t* blk;
                 if (k < 0) {
                     type = 1; ti = 8; li = 8; blk = lv + 24 * 16;
                 } else if (k < 16) {
-                    type = 0; ti = k & 3; li = k >> 2; blk = lv + k * 16; first = 1;
+                    type = i4 ? 3 : 0; ti = k & 3; li = k >> 2; blk = lv + k * 16; first = i4 ? 0 : 1;
                 } else {
                     const int c = k - 16;
                     type = 2; ti = 4 + (c >> 2) * 2 + (c & 1); li = 4 + (c >> 2) * 2 + ((c >> 1) & 1); blk = lv + k * 16;

@@ -194,6 +194,11 @@ __global__ void vp8_planes_kernel(const uint8_t* frame, size_t step, int channel
 struct Vp8WarpBuf {
     uint8_t yb[vp8::YB_SIZE], ub[vp8::CB_SIZE], vb[vp8::CB_SIZE];
     int16_t coeffs[25 * 16];
+    // the 4x4-prediction trial (vp8enc::analyse_i4 spread over the warp)
+    uint8_t yb4[vp8::YB_SIZE];   // the macroblock predicted block by block, same borders as yb
+    uint8_t tiles[10][5 * 16];   // one bordered 4x4 tile per candidate mode (stride 16, block at +20)
+    int16_t lv4[16 * 16];
+    int16_t c4[16];
 };
 
 __device__ __forceinline__ int warp_sum_i(int v) {
@@ -349,6 +354,107 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                 vp8::inverse_dct_add(coeffs + lane * 16, (lane >= 20 ? vd : ud) + (n >> 1) * 4 * BPS + (n & 1) * 4, BPS);
             }
             __syncwarp();
+            // ---- 16x16 or sixteen 4x4 predictions (vp8enc::analyse_and_reconstruct's decision, same arithmetic): the
+            //      candidate modes of a 4x4 block are tried by ten lanes at once, the winner's lane transforms,
+            //      quantises and reconstructs it (the next block predicts from that), the rate estimates of the sixteen
+            //      16x16-mode blocks run one per lane
+            uint8_t* md = B.modes + ((size_t)mb_y * P.mb_w + mb_x) * kModeStride;
+            bool use_i4 = false;
+            unsigned long long modes4 = 0;
+            if (P.try_i4) {
+                uint32_t tm = 0, lm = 0;  // the neighbours' sub-block modes, one nibble each
+                for (int i = 0; i < 4; i++) {
+                    tm |= (uint32_t)(have_top ? (md - (size_t)P.mb_w * kModeStride)[2 + 12 + i] : (uint8_t)vp8::B_DC) << (4 * i);
+                    lm |= (uint32_t)(have_left ? (md - kModeStride)[2 + 4 * i + 3] : (uint8_t)vp8::B_DC) << (4 * i);
+                }
+                uint32_t d16, r16;
+                {
+                    const int r = lane >> 1, c0 = (lane & 1) * 8;
+                    int e = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int d = (int)sy[r * ys + c0 + k] - (int)yd[r * BPS + c0 + k];
+                        e += d * d;
+                    }
+                    d16 = (uint32_t)warp_sum_i(e);
+                    const int mynz = lane < 16 ? block_nz(lv + lane * 16, 1) : 0;
+                    const uint32_t nzm = __ballot_sync(0xffffffffu, mynz != 0);
+                    int c = 0, nz;
+                    if (lane < 16) {
+                        const int ctx = ((lane & 3) ? (int)((nzm >> (lane - 1)) & 1u) : 0) + ((lane >> 2) ? (int)((nzm >> (lane - 4)) & 1u) : 0);
+                        c = cost_coeffs(0, ctx, 1, lv + lane * 16, &nz);
+                    } else if (lane == 16) {
+                        c = cost_coeffs(1, 0, 0, lv + 24 * 16, &nz);
+                    }
+                    r16 = (uint32_t)warp_sum_i(c) + (uint32_t)bit_cost(1, 145) + 512u;
+                }
+                // the trial buffer: yb's borders + the above-right samples (the decoder's rule, s.12.3)
+                uint8_t* yd4 = wb.yb4 + BPS + 8;
+                if (lane < 17) yd4[lane - 1 - BPS] = yd[lane - 1 - BPS];
+                if (lane < 16) yd4[lane * BPS - 1] = yd[lane * BPS - 1];
+                if (lane < 16) {
+                    const int i = 16 + (lane & 3), r = lane >> 2;
+                    const uint8_t v = have_top ? (mb_x < P.mb_w - 1 ? py[i - ys] : py[15 - ys]) : (uint8_t)127;
+                    yd4[(r ? 4 * r - 1 : -1) * BPS + i] = v;
+                }
+                __syncwarp();
+                const int q = qm.y1[1];
+                const int lambda4 = (3 * q * q) >> 7;
+                uint32_t d4 = 0, r4 = (uint32_t)bit_cost(0, 145), tnzb = 0, lnzb = 0;
+                for (int n = 0; n < 16; n++) {
+                    const int bx = n & 3, by = n >> 2;
+                    uint8_t* d = yd4 + by * 4 * BPS + bx * 4;
+                    const uint8_t* src = sy + by * 4 * ys + bx * 4;
+                    const uint8_t* prob = kVp8BModesProba[(tm >> (4 * bx)) & 15u][(lm >> (4 * by)) & 15u];
+                    uint8_t* tile = wb.tiles[lane < 10 ? lane : 0];
+                    uint32_t score = 0xffffffffu;
+                    if (lane < 10) {
+                        for (int k = 0; k < 9; k++) tile[3 + k] = d[k - 1 - BPS];
+                        for (int j = 0; j < 4; j++) tile[16 * (1 + j) + 3] = d[j * BPS - 1];
+                        vp8::pred_4x4(tile + 20, 16, lane);
+                        score = sse_block(src, ys, tile + 20, 16, 4) * 256u + (uint32_t)(i4_mode<false>(nullptr, lane, prob) * lambda4);
+                    }
+                    uint32_t mn = score;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    const int w = __ffs(__ballot_sync(0xffffffffu, score == mn)) - 1;  // ties: the lower mode number
+                    uint32_t my_d = 0, my_bits = 0;
+                    int my_nz = 0;
+                    if (lane == w) {
+                        fdct4x4(src, ys, tile + 20, 16, wb.c4);
+                        quantize_block(wb.c4, wb.lv4 + n * 16, qm.y1, 0, 96, 110);
+                        vp8::inverse_dct_add(wb.c4, tile + 20, 16);
+                        for (int j = 0; j < 4; j++)
+                            for (int i = 0; i < 4; i++) d[j * BPS + i] = tile[20 + j * 16 + i];
+                        my_d = sse_block(src, ys, tile + 20, 16, 4);
+                        my_bits = (uint32_t)i4_mode<false>(nullptr, w, prob) +
+                                  (uint32_t)cost_coeffs(3, (int)((tnzb >> bx) & 1u) + (int)((lnzb >> by) & 1u), 0, wb.lv4 + n * 16, &my_nz);
+                    }
+                    d4 += __shfl_sync(0xffffffffu, my_d, w);
+                    r4 += __shfl_sync(0xffffffffu, my_bits, w);
+                    const uint32_t nz = (uint32_t)__shfl_sync(0xffffffffu, my_nz, w);
+                    tnzb = (tnzb & ~(1u << bx)) | (nz << bx);
+                    lnzb = (lnzb & ~(1u << by)) | (nz << by);
+                    tm = (tm & ~(15u << (4 * bx))) | ((uint32_t)w << (4 * bx));
+                    lm = (lm & ~(15u << (4 * by))) | ((uint32_t)w << (4 * by));
+                    modes4 |= (unsigned long long)w << (4 * n);
+                    __syncwarp();
+                }
+                const unsigned long long lam = (unsigned long long)((q * q) >> 7);
+                const unsigned long long s16 = (unsigned long long)d16 * 256 + (unsigned long long)r16 * lam;
+                const unsigned long long s4 = (unsigned long long)d4 * 256 + (unsigned long long)r4 * lam;
+                use_i4 = s4 < s16;
+                if (use_i4) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) lv[lane * 8 + k] = wb.lv4[lane * 8 + k];
+                    if (lane < 16) lv[24 * 16 + lane] = 0;
+                    const int r = lane >> 1, c0 = (lane & 1) * 8;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) yd[r * BPS + c0 + k] = yd4[r * BPS + c0 + k];
+                }
+                __syncwarp();
+            }
+            if (lane < 16) md[2 + lane] = use_i4 ? (uint8_t)((modes4 >> (4 * lane)) & 15u) : (uint8_t)ymode;
             // reconstruction out to the planes: 8 luma pixels and 4 chroma pixels per lane
             {
                 const int r = lane >> 1, c0 = (lane & 1) * 8;
@@ -361,8 +467,8 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                 for (int k = 0; k < 4; k++) pc[cr * cs + cc0 + k] = dd[cr * BPS + cc0 + k];
             }
             if (lane == 0) {
-                B.modes[((size_t)mb_y * P.mb_w + mb_x) * 2 + 0] = (uint8_t)ymode;
-                B.modes[((size_t)mb_y * P.mb_w + mb_x) * 2 + 1] = (uint8_t)uvmode;
+                md[0] = use_i4 ? (uint8_t)kI4 : (uint8_t)ymode;
+                md[1] = (uint8_t)uvmode;
             }
             __syncwarp();
             __threadfence_block();  // the next macroblock's borders read what other lanes just wrote to global memory
@@ -439,10 +545,11 @@ static int vp8_encode_dev(const uint8_t* d_frame, size_t step, int width, int he
     j.P.mb_h = (height + 15) >> 4;
     j.P.q = vp8enc::quality_to_q(quality);
     j.P.filter_level = -1;  // chosen on the device, where the quantiser tables live
+    j.P.try_i4 = vp8enc::kTryI4;
     const int ys = j.P.mb_w * 16, yh = j.P.mb_h * 16;
     const size_t ypl = (size_t)ys * yh, nmb = (size_t)j.P.mb_w * j.P.mb_h;
     const size_t planes_b = round_up(ypl * 3 / 2, (size_t)256);
-    const size_t levels_b = round_up(nmb * 25 * 16 * 2, (size_t)256), modes_b = round_up(nmb * 2, (size_t)256);
+    const size_t levels_b = round_up(nmb * 25 * 16 * 2, (size_t)256), modes_b = round_up(nmb * vp8enc::kModeStride, (size_t)256);
     j.part0_cap = round_up(nmb * 2 + 4096, (size_t)256);
     j.tokens_cap = round_up(nmb * 2048 + 4096, (size_t)256);
     j.out_cap = 16 + j.part0_cap + j.tokens_cap;
@@ -657,11 +764,12 @@ int webp_encode_lossy_batch(const uint8_t* d_frames, size_t img_stride, size_t r
     b.P.mb_h = (height + 15) >> 4;
     b.P.q = vp8enc::quality_to_q(quality);
     b.P.filter_level = -1;
+    b.P.try_i4 = vp8enc::kTryI4;
     b.n = n;
     const int ys = b.P.mb_w * 16, yh = b.P.mb_h * 16;
     const size_t ypl = (size_t)ys * yh, nmb = (size_t)b.P.mb_w * b.P.mb_h;
     const size_t planes_b = round_up(ypl * 3 / 2, (size_t)256);
-    const size_t levels_b = round_up(nmb * 25 * 16 * 2, (size_t)256), modes_b = round_up(nmb * 2, (size_t)256);
+    const size_t levels_b = round_up(nmb * 25 * 16 * 2, (size_t)256), modes_b = round_up(nmb * vp8enc::kModeStride, (size_t)256);
     b.part0_cap = round_up(nmb * 2 + 4096, (size_t)256);
     b.tokens_cap = round_up(nmb * 2048 + 4096, (size_t)256);
     const size_t aux_b = vp8enc::kAuxBytes;  // statistics + probabilities of the bitstream pass (vp8_enc_core.h)

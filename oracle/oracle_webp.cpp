@@ -113,9 +113,10 @@ extern "C" long vp8l_cpu_encode(const uint8_t* frame, size_t step, int w, int h,
 
 // BGR(A) frame -> "VP8 " chunk payload.  Returns the size (0 = failed).  `recon_bgr` (optional) gets
 // what a decoder WITHOUT loop filter would show, for debugging.
-extern "C" long vp8_cpu_encode(const uint8_t* frame, size_t step, int w, int h, int channels, int quality,
-                               int filter_level, uint8_t* out, size_t cap) {
+static long vp8_cpu_encode_impl(const uint8_t* frame, size_t step, int w, int h, int channels, int quality,
+                                int filter_level, int try_i4, uint8_t* out, size_t cap) {
     vp8enc::Params P;
+    P.try_i4 = try_i4;
     P.width = w;
     P.height = h;
     P.mb_w = (w + 15) >> 4;
@@ -145,10 +146,20 @@ extern "C" long vp8_cpu_encode(const uint8_t* frame, size_t step, int w, int h, 
             sv[(size_t)y * cs + x] = (uint8_t)vp8enc::rgb_to_v(r, g, b);
         }
     std::vector<int16_t> levels((size_t)P.mb_w * P.mb_h * 25 * 16);
-    std::vector<uint8_t> modes((size_t)P.mb_w * P.mb_h * 2);
+    std::vector<uint8_t> modes((size_t)P.mb_w * P.mb_h * vp8enc::kModeStride);
     vp8enc::Buffers B{sy.data(), su.data(), sv.data(), ry.data(), ru.data(), rv.data(), levels.data(), modes.data()};
     vp8enc::analyse_and_reconstruct(P, B);
     const size_t scratch = (size_t)P.mb_w * P.mb_h * 2048 + 4096;  // the layout vp8enc::partition_scratch_off assumes
     std::vector<uint8_t> part0(scratch), tokens(scratch), aux(vp8enc::kAuxBytes);
     return (long)vp8enc::write_bitstream(P, B, part0.data(), part0.size(), tokens.data(), tokens.size(), aux.data(), out, cap);
+}
+// the encoder as the device runs it (vp8enc::kTryI4: whether macroblocks weigh 4x4 against 16x16 prediction)
+extern "C" long vp8_cpu_encode(const uint8_t* frame, size_t step, int w, int h, int channels, int quality,
+                               int filter_level, uint8_t* out, size_t cap) {
+    return vp8_cpu_encode_impl(frame, step, w, h, channels, quality, filter_level, vp8enc::kTryI4, out, cap);
+}
+// ... and with the choice forced on or off (measurements, tests of both paths)
+extern "C" long vp8_cpu_encode_i4(const uint8_t* frame, size_t step, int w, int h, int channels, int quality,
+                                  int filter_level, int try_i4, uint8_t* out, size_t cap) {
+    return vp8_cpu_encode_impl(frame, step, w, h, channels, quality, filter_level, try_i4, out, cap);
 }

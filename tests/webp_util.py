@@ -98,14 +98,19 @@ def vp8l_cpu_encode(lib, img: np.ndarray) -> bytes:
     return out[:n].tobytes()
 
 
-def vp8_cpu_encode(lib, img: np.ndarray, quality: int, filter_level: int = -1) -> bytes:
-    """vp8_enc_core.h on the host: BGR(A) frame -> "VP8 " payload."""
+def vp8_cpu_encode(lib, img: np.ndarray, quality: int, filter_level: int = -1, try_i4=None) -> bytes:
+    """vp8_enc_core.h on the host: BGR(A) frame -> "VP8 " payload.  try_i4: None = as the device encodes, 0 / 1 = forced."""
     img = np.ascontiguousarray(img, np.uint8)
     h, w, c = img.shape
     out = np.zeros(w * h * 4 + 65536, np.uint8)
-    lib.vp8_cpu_encode.restype = ctypes.c_long
-    n = lib.vp8_cpu_encode(img.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(w * c), w, h, c, quality, filter_level,
-                           out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.size))
+    if try_i4 is None:
+        lib.vp8_cpu_encode.restype = ctypes.c_long
+        n = lib.vp8_cpu_encode(img.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(w * c), w, h, c, quality, filter_level,
+                               out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.size))
+    else:
+        lib.vp8_cpu_encode_i4.restype = ctypes.c_long
+        n = lib.vp8_cpu_encode_i4(img.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(w * c), w, h, c, quality, filter_level,
+                                  int(try_i4), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.size))
     assert n > 0, n
     return out[:n].tobytes()
 

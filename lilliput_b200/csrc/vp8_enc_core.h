@@ -394,6 +394,49 @@ constexpr int kTryI4 = 1;  // what the product encodes with (Params::try_i4 of t
 // cost, in 1/256 bit, of a bit coded with probability `p` of being 0
 LP_VP8_INL int bit_cost(int bit, int p) { return kVp8EntropyCost[bit ? 255 - p : p]; }
 
+// The ten 4x4 predictors as data (tools/gen_vp8_pred4_table.py reads them out of vp8::pred_4x4's source): entry =
+// i0 | i1 << 4 | i2 << 8 | kind << 12 over the edge samples e[13] = {L, K, J, I, X, A, B, C, D, E, F, G, H} (left column
+// bottom-up, corner, the row above and its four above-right samples); kind 0 = (e[i0] + 2 e[i1] + e[i2] + 2) >> 2,
+// 1 = (e[i0] + e[i1] + 1) >> 1, 2 = e[i0], 3 = B_DC / B_TM (computed from the mode).  A lane can so evaluate any mode of
+// any pixel without the ten-way switch of pred_4x4.
+LP_VP8_TABLE uint16_t kVp8Pred4[10][16] = {
+    {0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000},  // B_DC
+    {0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000, 0x3000},  // B_TM
+    {0x0654, 0x0765, 0x0876, 0x0987, 0x0654, 0x0765, 0x0876, 0x0987, 0x0654, 0x0765, 0x0876, 0x0987, 0x0654, 0x0765, 0x0876, 0x0987},  // B_VE
+    {0x0234, 0x0234, 0x0234, 0x0234, 0x0123, 0x0123, 0x0123, 0x0123, 0x0012, 0x0012, 0x0012, 0x0012, 0x0001, 0x0001, 0x0001, 0x0001},  // B_HE
+    {0x0345, 0x0456, 0x0567, 0x0678, 0x0234, 0x0345, 0x0456, 0x0567, 0x0123, 0x0234, 0x0345, 0x0456, 0x0012, 0x0123, 0x0234, 0x0345},  // B_RD
+    {0x1054, 0x1065, 0x1076, 0x1087, 0x0543, 0x0654, 0x0765, 0x0876, 0x0432, 0x1054, 0x1065, 0x1076, 0x0321, 0x0543, 0x0654, 0x0765},  // B_VR
+    {0x0765, 0x0876, 0x0987, 0x0a98, 0x0876, 0x0987, 0x0a98, 0x0ba9, 0x0987, 0x0a98, 0x0ba9, 0x0cba, 0x0a98, 0x0ba9, 0x0cba, 0x0ccb},  // B_LD
+    {0x1065, 0x1076, 0x1087, 0x1098, 0x0765, 0x0876, 0x0987, 0x0a98, 0x1076, 0x1087, 0x1098, 0x0ba9, 0x0876, 0x0987, 0x0a98, 0x0cba},  // B_VL
+    {0x1043, 0x0543, 0x0654, 0x0765, 0x1032, 0x0432, 0x1043, 0x0543, 0x1021, 0x0321, 0x1032, 0x0432, 0x1010, 0x0210, 0x1021, 0x0321},  // B_HD
+    {0x1023, 0x0123, 0x1012, 0x0012, 0x1012, 0x0012, 0x1001, 0x0001, 0x1001, 0x0001, 0x2000, 0x2000, 0x2000, 0x2000, 0x2000, 0x2000},  // B_HU
+};
+
+// pixel p (= 4 * y + x) of mode `mode`; dc = (A + B + C + D + I + J + K + L + 4) >> 3
+LP_VP8_INL int pred4_px(int mode, int p, const uint8_t* e, int dc) {
+    const uint32_t t = kVp8Pred4[mode][p];
+    const int a = e[t & 15], b = e[(t >> 4) & 15], c = e[(t >> 8) & 15], kind = (int)(t >> 12);
+    if (kind == 0) return (a + 2 * b + c + 2) >> 2;
+    if (kind == 1) return (a + b + 1) >> 1;
+    if (kind == 2) return a;
+    if (mode == vp8::B_DC) return dc;
+    return vp8::clip8(e[5 + (p & 3)] + e[3 - (p >> 2)] - e[4]);  // B_TM: above + left - corner
+}
+
+// The path of every sub-block mode through the tree of s.8.3: nodes (= index of the probability) as nibbles, the
+// branch taken at each as a bit mask, length in bits 8..10.  i4_mode_cost == i4_mode<false> (checked in the tests),
+// without its data-dependent branches.
+LP_VP8_TABLE uint32_t kVp8BModePathNodes[10] = {0x0000000, 0x0000010, 0x0000210, 0x0043210, 0x0543210, 0x0543210, 0x0063210, 0x0763210, 0x8763210, 0x8763210};
+LP_VP8_TABLE uint16_t kVp8BModePathBits[10] = {0x100, 0x201, 0x303, 0x507, 0x617, 0x637, 0x50f, 0x61f, 0x73f, 0x77f};
+LP_VP8_INL int i4_mode_cost(int mode, const uint8_t* prob) {
+    const uint32_t nodes = kVp8BModePathNodes[mode], bits = kVp8BModePathBits[mode];
+    const int len = (int)(bits >> 8);
+    int cost = 0;
+    for (int k = 0; k < 7; k++)
+        if (k < len) cost += bit_cost((int)((bits >> k) & 1u), prob[(nodes >> (4 * k)) & 15u]);
+    return cost;
+}
+
 // the sub-block mode tree of s.8.3 (kVp8YModesIntra4) walked for `mode`: PUT = code it, else return its cost
 template <bool PUT>
 LP_VP8_FN int i4_mode(BoolEnc* e, int mode, const uint8_t* prob) {
@@ -418,50 +461,40 @@ LP_VP8_FN int i4_mode(BoolEnc* e, int mode, const uint8_t* prob) {
 }
 
 // put_coeffs with the coder replaced by a bit count (1/256 bit) under the default probabilities: the rate estimate
-// of the 16x16-versus-4x4 decision.  Returns the cost; *nz = what put_coeffs would return.
-LP_VP8_FN int cost_coeffs(int type, int ctx, int first, const int16_t* levels, int* nz) {
+// of the 16x16-versus-4x4 decision, written as a sum over scan positions so that the device can give every position a
+// lane.  cost_pos = what position n adds: `v` / `vprev` = the magnitudes at scan positions n and n - 1, `last` = the
+// last non-zero position (-1: none), ctx0 = the block's context.
+LP_VP8_INL int cost_pos(const uint8_t* tp, int ctx0, int first, int last, int v, int vprev, int n) {
     const uint8_t bands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
+    if (last < 0) return n == first ? bit_cost(0, tp[(bands[n] * 3 + ctx0) * 11]) : 0;  // "no coefficients"
+    if (n < first || n > last + 1 || n > 15) return 0;
+    const int ctx = n == first ? ctx0 : vprev == 0 ? 0 : vprev == 1 ? 1 : 2;
+    const uint8_t* p = tp + (bands[n] * 3 + ctx) * 11;
+    if (n == last + 1) return bit_cost(0, p[0]);  // end of block
+    int c = 0;
+    if (n == first || vprev != 0) c += bit_cost(1, p[0]);  // "not the end": coded unless the previous level was zero
+    if (!v) return c + bit_cost(0, p[1]);
+    c += bit_cost(1, p[1]) + 256;  // + the sign
+    if (v == 1) return c + bit_cost(0, p[2]);
+    c += bit_cost(1, p[2]);
+    if (v <= 4) return c + bit_cost(0, p[3]) + bit_cost(v != 2, p[4]) + (v != 2 ? bit_cost(v == 4, p[5]) : 0);
+    if (v <= 10) return c + bit_cost(1, p[3]) + bit_cost(0, p[6]) + bit_cost(v > 6, p[7]) + (v > 6 ? 512 : 256);
+    const int cat = v < 19 ? 0 : v < 35 ? 1 : v < 67 ? 2 : 3;
+    return c + bit_cost(1, p[3]) + bit_cost(1, p[6]) + bit_cost(cat >> 1, p[8]) + bit_cost(cat & 1, p[9 + (cat >> 1)]) +
+           256 * (cat == 3 ? 11 : cat + 3);  // extra bits: about one bit each
+}
+// Returns the cost of a block; *nz = what put_coeffs would return.
+LP_VP8_FN int cost_coeffs(int type, int ctx, int first, const int16_t* levels, int* nz) {
     const uint8_t zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
     const uint8_t* tp = &kVp8CoeffProba0[0][0][0][0] + type * (8 * 3 * 11);
     const int last = last_nonzero(levels, first);
-    int n = first, cost = 0;
-    const uint8_t* p = tp + (bands[n] * 3 + ctx) * 11;
     *nz = last >= 0;
-    if (last < 0) return bit_cost(0, p[0]);
-    cost += bit_cost(1, p[0]);
-    while (n < 16) {
+    int cost = 0, vprev = 0;
+    for (int n = first; n < 16; n++) {
         const int c = levels[zigzag[n]];
         const int v = c < 0 ? -c : c;
-        if (!v) {
-            cost += bit_cost(0, p[1]);
-            p = tp + (bands[++n] * 3 + 0) * 11;
-            continue;
-        }
-        cost += bit_cost(1, p[1]) + 256;  // + the sign
-        int next_ctx;
-        if (v == 1) {
-            cost += bit_cost(0, p[2]);
-            next_ctx = 1;
-        } else {
-            cost += bit_cost(1, p[2]);
-            next_ctx = 2;
-            if (v <= 4) {
-                cost += bit_cost(0, p[3]) + bit_cost(v != 2, p[4]) + (v != 2 ? bit_cost(v == 4, p[5]) : 0);
-            } else if (v <= 10) {
-                cost += bit_cost(1, p[3]) + bit_cost(0, p[6]) + bit_cost(v > 6, p[7]) + (v > 6 ? 512 : 256);
-            } else {
-                const int cat = v < 19 ? 0 : v < 35 ? 1 : v < 67 ? 2 : 3;
-                cost += bit_cost(1, p[3]) + bit_cost(1, p[6]) + bit_cost(cat >> 1, p[8]) + bit_cost(cat & 1, p[9 + (cat >> 1)]) +
-                        256 * (cat == 3 ? 11 : cat + 3);  // extra bits: about one bit each
-            }
-        }
-        if (++n == 16) break;
-        p = tp + (bands[n] * 3 + next_ctx) * 11;
-        if (n > last) {
-            cost += bit_cost(0, p[0]);
-            break;
-        }
-        cost += bit_cost(1, p[0]);
+        cost += cost_pos(tp, ctx, first, last, v, vprev, n);
+        vprev = v;
     }
     return cost;
 }
@@ -550,7 +583,7 @@ LP_VP8_FN uint32_t analyse_i4(const uint8_t* sy, int ys, uint8_t* yd, const int*
         uint32_t best = 0xffffffffu;
         for (int m = 0; m < 10; m++) {
             vp8::pred_4x4(d, BPS, m);
-            const uint32_t score = sse_block(src, ys, d, BPS, 4) * 256u + (uint32_t)(i4_mode<false>(nullptr, m, prob) * lambda4);
+            const uint32_t score = sse_block(src, ys, d, BPS, 4) * 256u + (uint32_t)(i4_mode_cost(m, prob) * lambda4);
             if (score < best) {
                 best = score;
                 best_mode = m;
@@ -562,7 +595,7 @@ LP_VP8_FN uint32_t analyse_i4(const uint8_t* sy, int ys, uint8_t* yd, const int*
         vp8::inverse_dct_add(coeffs, d, BPS);
         dist += sse_block(src, ys, d, BPS, 4);
         int nz;
-        bits += (uint32_t)i4_mode<false>(nullptr, best_mode, prob) + (uint32_t)cost_coeffs(3, tnz[bx] + lnz[by], 0, levels + n * 16, &nz);
+        bits += (uint32_t)i4_mode_cost(best_mode, prob) + (uint32_t)cost_coeffs(3, tnz[bx] + lnz[by], 0, levels + n * 16, &nz);
         tnz[bx] = lnz[by] = (uint8_t)nz;
         modes[n] = (uint8_t)best_mode;
         top_modes[bx] = left_modes[by] = (uint8_t)best_mode;
@@ -910,6 +943,11 @@ LP_VP8_FN size_t walk_partition(const Params& P, const Buffers& B, int part, int
     return t.overflow ? 0 : t.pos;
 }
 
+// The statistics are a SAMPLE: every second token partition, i.e. every second macroblock row (all rows when the frame
+// has a single partition).  The probabilities are estimates either way; counting half the rows halves the cost of the
+// statistics walk -- it is as long as the coding walk -- for well under 1 % of file size.
+LP_VP8_HD int stats_partition(int part, int nparts) { return nparts < 2 || (part & 1) == 0; }
+
 // entries [first, first + step, ...) of the probability table from the statistics; entry 0's caller also settles the
 // skip probability.  (The device spreads the 1056 entries over the 32 lanes of the frame's warp.)
 LP_VP8_FN void finish_statistics(uint8_t* aux, int first, int step) {
@@ -968,7 +1006,8 @@ LP_VP8_FN size_t write_bitstream(const Params& P, const Buffers& B, uint8_t* par
     const int nparts = 1 << log2_partitions(P);
     if (partition_scratch_off(P, nparts - 1, nparts) + partition_scratch_cap(P, nparts - 1, nparts) > tokens_cap) return 0;
     for (size_t i = 0; i < kAuxBytes; i++) aux[i] = 0;
-    for (int q = 0; q < nparts; q++) walk_partition<false>(P, B, q, nparts, aux, nullptr, 0);
+    for (int q = 0; q < nparts; q++)
+        if (stats_partition(q, nparts)) walk_partition<false>(P, B, q, nparts, aux, nullptr, 0);
     finish_statistics(aux, 0, 1);
     const size_t part0_len = write_part0(P, B, aux, part0, part0_cap);
     size_t sizes[8];

@@ -196,9 +196,8 @@ struct Vp8WarpBuf {
     int16_t coeffs[25 * 16];
     // the 4x4-prediction trial (vp8enc::analyse_i4 spread over the warp)
     uint8_t yb4[vp8::YB_SIZE];   // the macroblock predicted block by block, same borders as yb
-    uint8_t tiles[10][5 * 16];   // one bordered 4x4 tile per candidate mode (stride 16, block at +20)
+    uint8_t edge[16];            // the 13 edge samples of the 4x4 block being tried
     int16_t lv4[16 * 16];
-    int16_t c4[16];
 };
 
 __device__ __forceinline__ int warp_sum_i(int v) {
@@ -223,6 +222,40 @@ __device__ __forceinline__ int vp8_dc_value(const uint8_t* dst, int bps, int siz
     if (have_top && have_left) return (s + size) >> (sh + 1);
     if (have_top || have_left) return (s + (size >> 1)) >> sh;
     return 0x80;
+}
+
+// ---- one 4x4 block on 16 lanes (lane L = 4 * row + column; lanes 16..31 run along on zeros) ---------------------------
+// The same integer arithmetic as vp8enc::fdct4x4 / quantize_block / vp8::inverse_dct_add / vp8enc::cost_coeffs, with the
+// block's rows and columns exchanged by shuffles instead of a tmp[16] on one lane.
+__device__ __forceinline__ int fdct4x4_lanes(int diff, int L) {  // residual sample -> coefficient `L` (raster)
+    constexpr unsigned FULL = 0xffffffffu;
+    const int r0 = L & 12, c = L & 3, r = (L >> 2) & 3;
+    const int d0 = __shfl_sync(FULL, diff, r0), d1 = __shfl_sync(FULL, diff, r0 + 1), d2 = __shfl_sync(FULL, diff, r0 + 2),
+              d3 = __shfl_sync(FULL, diff, r0 + 3);
+    int a0 = d0 + d3, a1 = d1 + d2, a2 = d1 - d2, a3 = d0 - d3;
+    const int tmp = c == 0 ? (a0 + a1) * 8 : c == 1 ? (a2 * 2217 + a3 * 5352 + 1812) >> 9 : c == 2 ? (a0 - a1) * 8 : (a3 * 2217 - a2 * 5352 + 937) >> 9;
+    const int t0 = __shfl_sync(FULL, tmp, c), t1 = __shfl_sync(FULL, tmp, 4 + c), t2 = __shfl_sync(FULL, tmp, 8 + c),
+              t3 = __shfl_sync(FULL, tmp, 12 + c);
+    a0 = t0 + t3, a1 = t1 + t2, a2 = t1 - t2, a3 = t0 - t3;
+    const int out = r == 0 ? (a0 + a1 + 7) >> 4 : r == 1 ? ((a2 * 2217 + a3 * 5352 + 12000) >> 16) + (a3 != 0) : r == 2 ? (a0 - a1 + 7) >> 4
+                                                                                                                   : (a3 * 2217 - a2 * 5352 + 51000) >> 16;
+    return (int)(int16_t)out;
+}
+// dequantised coefficient `L` (raster) -> the residual the decoder adds at pixel L
+__device__ __forceinline__ int idct4x4_lanes(int coef, int L) {
+    constexpr unsigned FULL = 0xffffffffu;
+    {
+        const int i = (L >> 2) & 3, k = L & 3;  // vertical pass: this lane makes tmp[4 * i + k] from column i
+        const int i0 = __shfl_sync(FULL, coef, i), i4 = __shfl_sync(FULL, coef, 4 + i), i8 = __shfl_sync(FULL, coef, 8 + i),
+                  i12 = __shfl_sync(FULL, coef, 12 + i);
+        const int a = i0 + i8, b = i0 - i8, c = vp8::mul2(i4) - vp8::mul1(i12), d = vp8::mul1(i4) + vp8::mul2(i12);
+        coef = k == 0 ? a + d : k == 1 ? b + c : k == 2 ? b - c : a - d;
+    }
+    const int i = (L >> 2) & 3, k = L & 3;  // horizontal pass: pixel (row i, column k) from tmp[i], tmp[4 + i], ...
+    const int t0 = __shfl_sync(FULL, coef, i), t4 = __shfl_sync(FULL, coef, 4 + i), t8 = __shfl_sync(FULL, coef, 8 + i),
+              t12 = __shfl_sync(FULL, coef, 12 + i);
+    const int dc = t0 + 4, a = dc + t8, b = dc - t8, c = vp8::mul2(t4) - vp8::mul1(t12), d = vp8::mul1(t4) + vp8::mul2(t12);
+    return (k == 0 ? a + d : k == 1 ? b + c : k == 2 ? b - c : a - d) >> 3;
 }
 
 __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers& B, Vp8WarpBuf& wb) {
@@ -406,33 +439,73 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                     uint8_t* d = yd4 + by * 4 * BPS + bx * 4;
                     const uint8_t* src = sy + by * 4 * ys + bx * 4;
                     const uint8_t* prob = kVp8BModesProba[(tm >> (4 * bx)) & 15u][(lm >> (4 * by)) & 15u];
-                    uint8_t* tile = wb.tiles[lane < 10 ? lane : 0];
-                    uint32_t score = 0xffffffffu;
-                    if (lane < 10) {
-                        for (int k = 0; k < 9; k++) tile[3 + k] = d[k - 1 - BPS];
-                        for (int j = 0; j < 4; j++) tile[16 * (1 + j) + 3] = d[j * BPS - 1];
-                        vp8::pred_4x4(tile + 20, 16, lane);
-                        score = sse_block(src, ys, tile + 20, 16, 4) * 256u + (uint32_t)(i4_mode<false>(nullptr, lane, prob) * lambda4);
+                    // the block's 13 edge samples {L, K, J, I, X, A..H} where every lane can index them
+                    if (lane < 13)
+                        wb.edge[lane] = lane < 4 ? d[(3 - lane) * BPS - 1] : lane == 4 ? d[-BPS - 1] : d[-BPS + (lane - 5)];
+                    __syncwarp();
+                    const uint8_t* e = wb.edge;
+                    const int dc = (e[5] + e[6] + e[7] + e[8] + e[0] + e[1] + e[2] + e[3] + 4) >> 3;
+                    // all ten modes without a divergent switch (vp8enc::pred4_px): lane = (pixel, half); the lower half of the
+                    // warp tries modes 0..4 of its pixel, the upper half modes 5..9; squared errors summed over 16 lanes
+                    const int L = lane & 15, pr = L >> 2, pc = L & 3, half = lane >> 4;
+                    const int sp = (int)src[pr * ys + pc];
+                    uint32_t sse5[5];
+#pragma unroll
+                    for (int t = 0; t < 5; t++) {
+                        const int dd = sp - pred4_px(half * 5 + t, L, e, dc);
+                        int v = dd * dd;
+#pragma unroll
+                        for (int o = 8; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        sse5[t] = (uint32_t)v;
                     }
+                    // lane -> the mode it speaks for: m = 5 * half + (L % 5); score = distortion + lambda * mode bits
+                    const int t5 = L % 5, m = half * 5 + t5;
+                    const uint32_t my_sse = t5 == 0 ? sse5[0] : t5 == 1 ? sse5[1] : t5 == 2 ? sse5[2] : t5 == 3 ? sse5[3] : sse5[4];
+                    const uint32_t score = my_sse * 256u + (uint32_t)(i4_mode_cost(m, prob) * lambda4);
                     uint32_t mn = score;
 #pragma unroll
                     for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                    const int w = __ffs(__ballot_sync(0xffffffffu, score == mn)) - 1;  // ties: the lower mode number
-                    uint32_t my_d = 0, my_bits = 0;
-                    int my_nz = 0;
-                    if (lane == w) {
-                        fdct4x4(src, ys, tile + 20, 16, wb.c4);
-                        quantize_block(wb.c4, wb.lv4 + n * 16, qm.y1, 0, 96, 110);
-                        vp8::inverse_dct_add(wb.c4, tile + 20, 16);
-                        for (int j = 0; j < 4; j++)
-                            for (int i = 0; i < 4; i++) d[j * BPS + i] = tile[20 + j * 16 + i];
-                        my_d = sse_block(src, ys, tile + 20, 16, 4);
-                        my_bits = (uint32_t)i4_mode<false>(nullptr, w, prob) +
-                                  (uint32_t)cost_coeffs(3, (int)((tnzb >> bx) & 1u) + (int)((lnzb >> by) & 1u), 0, wb.lv4 + n * 16, &my_nz);
+                    uint32_t wm = score == mn ? (uint32_t)m : 15u;  // ties: the lower mode number, as the serial walk keeps it
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) wm = min(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+                    const int w = (int)wm;
+                    // the winner's prediction, transform, quantisation, reconstruction, distortion and rate of the block on
+                    // lanes 0..15 (lane = 4 * row + column; the upper half runs along)
+                    const bool act = lane < 16;
+                    const int pp = pred4_px(w, L, e, dc);
+                    const int coefq = fdct4x4_lanes(sp - pp, L);
+                    const int step = qm.y1[L > 0];
+                    int lvl;
+                    {
+                        const int a = coefq < 0 ? -coefq : coefq;
+                        int q_ = (a + (((L > 0 ? 110 : 96) * step) >> 8)) / step;
+                        if (q_ > 2047) q_ = 2047;
+                        lvl = coefq < 0 ? -q_ : q_;
                     }
-                    d4 += __shfl_sync(0xffffffffu, my_d, w);
-                    r4 += __shfl_sync(0xffffffffu, my_bits, w);
-                    const uint32_t nz = (uint32_t)__shfl_sync(0xffffffffu, my_nz, w);
+                    if (act) wb.lv4[n * 16 + L] = (int16_t)lvl;
+                    const int rec = vp8::clip8(pp + idct4x4_lanes((int)(int16_t)(lvl * step), L));
+                    if (act) d[pr * BPS + pc] = (uint8_t)rec;
+                    const uint32_t my_d_all = (uint32_t)warp_sum_i(act ? (sp - rec) * (sp - rec) : 0);
+                    // rate: scan position `lane` (vp8enc::cost_pos summed over the positions)
+                    uint32_t blk_bits;
+                    int blk_nz;
+                    {
+                        const int zz = lane < 16 ? (int)((0xFEB7ADC963258410ull >> (4 * lane)) & 15ull) : 0;  // zig-zag: scan -> raster
+                        const int mag = lvl < 0 ? -lvl : lvl;
+                        const int v = __shfl_sync(0xffffffffu, mag, zz);
+                        int vprev = __shfl_up_sync(0xffffffffu, v, 1);
+                        if (lane == 0) vprev = 0;
+                        const uint32_t nzm = __ballot_sync(0xffffffffu, act && v != 0);
+                        const int last = nzm ? 31 - __clz((int)nzm) : -1;
+                        const uint8_t* tp = &kVp8CoeffProba0[0][0][0][0] + 3 * (8 * 3 * 11);
+                        const int ctx0 = (int)((tnzb >> bx) & 1u) + (int)((lnzb >> by) & 1u);
+                        const int cp = act ? cost_pos(tp, ctx0, 0, last, v, vprev, lane) : 0;
+                        blk_bits = (uint32_t)warp_sum_i(cp) + (uint32_t)i4_mode_cost(w, prob);
+                        blk_nz = last >= 0;
+                    }
+                    d4 += my_d_all;
+                    r4 += blk_bits;
+                    const uint32_t nz = (uint32_t)blk_nz;
                     tnzb = (tnzb & ~(1u << bx)) | (nz << bx);
                     lnzb = (lnzb & ~(1u << by)) | (nz << by);
                     tm = (tm & ~(15u << (4 * bx))) | ((uint32_t)w << (4 * bx));
@@ -488,7 +561,7 @@ __device__ size_t vp8_write_bitstream_warp(const vp8enc::Params& P, const vp8enc
         return 0;
     for (size_t i = lane; i < vp8enc::kAuxBytes / 4; i += 32) reinterpret_cast<uint32_t*>(aux)[i] = 0;
     __syncwarp();
-    if (lane < nparts) vp8enc::walk_partition<false>(P, B, lane, nparts, aux, nullptr, 0);
+    if (lane < nparts && vp8enc::stats_partition(lane, nparts)) vp8enc::walk_partition<false>(P, B, lane, nparts, aux, nullptr, 0);
     __syncwarp();
     vp8enc::finish_statistics(aux, lane, 32);
     __syncwarp();
@@ -520,6 +593,13 @@ __device__ size_t vp8_write_bitstream_warp(const vp8enc::Params& P, const vp8enc
     return total;
 }
 
+// vp8enc::kTryI4 unless LP_WEBP_I4=0 / 1 says otherwise (measurements; the tests compare against the host build, which
+// follows kTryI4)
+static int vp8_try_i4() {
+    static const int v = getenv("LP_WEBP_I4") ? atoi(getenv("LP_WEBP_I4")) != 0 : vp8enc::kTryI4;
+    return v;
+}
+
 struct Vp8EncJob {
     vp8enc::Params P;
     vp8enc::Buffers B;
@@ -545,7 +625,7 @@ static int vp8_encode_dev(const uint8_t* d_frame, size_t step, int width, int he
     j.P.mb_h = (height + 15) >> 4;
     j.P.q = vp8enc::quality_to_q(quality);
     j.P.filter_level = -1;  // chosen on the device, where the quantiser tables live
-    j.P.try_i4 = vp8enc::kTryI4;
+    j.P.try_i4 = vp8_try_i4();
     const int ys = j.P.mb_w * 16, yh = j.P.mb_h * 16;
     const size_t ypl = (size_t)ys * yh, nmb = (size_t)j.P.mb_w * j.P.mb_h;
     const size_t planes_b = round_up(ypl * 3 / 2, (size_t)256);
@@ -764,7 +844,7 @@ int webp_encode_lossy_batch(const uint8_t* d_frames, size_t img_stride, size_t r
     b.P.mb_h = (height + 15) >> 4;
     b.P.q = vp8enc::quality_to_q(quality);
     b.P.filter_level = -1;
-    b.P.try_i4 = vp8enc::kTryI4;
+    b.P.try_i4 = vp8_try_i4();
     b.n = n;
     const int ys = b.P.mb_w * 16, yh = b.P.mb_h * 16;
     const size_t ypl = (size_t)ys * yh, nmb = (size_t)b.P.mb_w * b.P.mb_h;

@@ -163,3 +163,30 @@ extern "C" long vp8_cpu_encode_i4(const uint8_t* frame, size_t step, int w, int 
                                   int filter_level, int try_i4, uint8_t* out, size_t cap) {
     return vp8_cpu_encode_impl(frame, step, w, h, channels, quality, filter_level, try_i4, out, cap);
 }
+
+// Self-check of the data forms of the 4x4 predictors and of the sub-block mode costs (vp8_enc_core.h) against the code
+// forms (vp8::pred_4x4, vp8enc::i4_mode<false>) on `iters` random borders / probability rows.  Returns mismatches.
+extern "C" long vp8_cpu_check_pred4_tables(long iters, unsigned seed) {
+    long bad = 0;
+    uint32_t x = seed ? seed : 1u;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x; };
+    for (long it = 0; it < iters; it++) {
+        uint8_t buf[6 * 32];
+        for (auto& b : buf) b = (it % 3 == 0) ? (uint8_t)((rnd() & 1) * 255) : (uint8_t)rnd();
+        uint8_t* d = buf + 32 + 8;  // a 4x4 block with its borders at stride 32
+        uint8_t e[13];
+        for (int k = 0; k < 4; k++) e[k] = d[(3 - k) * 32 - 1];
+        e[4] = d[-32 - 1];
+        for (int k = 0; k < 8; k++) e[5 + k] = d[-32 + k];
+        const int dc = (e[5] + e[6] + e[7] + e[8] + e[0] + e[1] + e[2] + e[3] + 4) >> 3;
+        uint8_t prob[9];
+        for (auto& p : prob) p = (uint8_t)(1 + rnd() % 255);
+        for (int m = 0; m < 10; m++) {
+            vp8::pred_4x4(d, 32, m);
+            for (int p = 0; p < 16; p++)
+                if (vp8enc::pred4_px(m, p, e, dc) != d[(p >> 2) * 32 + (p & 3)]) bad++;
+            if (vp8enc::i4_mode_cost(m, prob) != vp8enc::i4_mode<false>(nullptr, m, prob)) bad++;
+        }
+    }
+    return bad;
+}

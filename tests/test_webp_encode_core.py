@@ -120,3 +120,11 @@ def test_4x4_prediction_pays_on_detail_and_both_forms_are_valid(cpu, ref_lib):
             quals.append(psnr(mine, img))
         assert sizes[1] < 0.92 * sizes[0], sizes  # measured 0.81 / 0.81 / 0.89
         assert quals[1] > quals[0] - 0.35, quals
+
+
+def test_data_forms_of_the_4x4_predictors_equal_the_code_forms(cpu):
+    """The device tries the ten sub-block modes through a table (kVp8Pred4, generated by tools/gen_vp8_pred4_table.py from
+    vp8::pred_4x4's source) and prices them through a path table: both must be the functions they replace."""
+    import ctypes
+    cpu.vp8_cpu_check_pred4_tables.restype = ctypes.c_long
+    assert cpu.vp8_cpu_check_pred4_tables(ctypes.c_long(30000), ctypes.c_uint(11)) == 0

@@ -1,0 +1,8 @@
+#!/bin/bash
+O=gpurun_out; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_webp_encode.py tests/test_gpu_xbatch.py -m gpu -x -q > $O/ab7_tests.log 2>&1; echo "tests rc=$?"; tail -3 $O/ab7_tests.log
+for c in 4 3; do
+  timeout 600 python bench.py --config $c --steps 2 --warmup 2 --no-cpu-baseline > $O/ab7_bench_c$c.json 2> $O/ab7_bench_c$c.err; echo "bench c$c rc=$?"
+  python -c "
+import json;d=json.load(open('$O/ab7_bench_c$c.json'));print('c$c',d['value'],d['e2e']['value'],d['config']['stage_ms_per_step'])"
+done

@@ -191,6 +191,10 @@ int lp_batch_chunk(const lp_batch* b);
 /* Diagnostics (valid after lp_batch_fetch / lp_batch_transform): rounds the parallel Huffman
  * synchronisation needed per image. */
 void lp_batch_sync_rounds(const lp_batch* b, double* mean, int* max);
+/* Diagnostics: SM cycles the JPEG entropy kernel spent per phase since the last reset on the current device, summed over
+ * its CTAs -- out8[0] table set-up, [1] guess pass, [2] synchronisation rounds, [3] prefix sum + write pass, [4] DC pass,
+ * [5] number of CTAs (= images).  reset != 0 clears the counters after reading.  Returns an lp_status. */
+int lp_huff_phase_clocks(unsigned long long* out8, int reset);
 /* Device pointer to the decoded frames / resized frames of the last run (tests). */
 const uint8_t* lp_batch_decoded_dev(const lp_batch* b, size_t* image_stride);
 const uint8_t* lp_batch_resized_dev(const lp_batch* b, size_t* image_stride);

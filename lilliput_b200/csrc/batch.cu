@@ -642,7 +642,16 @@ extern "C" int lp_batch_transform(lp_batch* b, const uint8_t* const* in, const s
             sched.push_back({i0, b->first_chunk});
             i0 += b->first_chunk;
         }
-        for (; i0 < n; i0 += b->pipe_chunk) sched.push_back({i0, std::min(b->pipe_chunk, n - i0)});
+        // ... and closes with one wave again: behind the last entropy launch nothing overlaps the IDCT -> colour ->
+        // resize -> encode -> D2H tail of the last chunk, so that chunk is kept small
+        const bool ramp_down = b->first_chunk >= 1 && b->first_chunk < b->pipe_chunk;
+        while (i0 < n) {
+            const int left = n - i0;
+            int cnt = std::min(b->pipe_chunk, left);
+            if (ramp_down && left > b->first_chunk && left <= b->pipe_chunk + b->first_chunk) cnt = left - b->first_chunk;
+            sched.push_back({i0, cnt});
+            i0 += cnt;
+        }
     }
     const int nchunks = (int)sched.size();
     int finished = 0;

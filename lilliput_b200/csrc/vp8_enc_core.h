@@ -221,6 +221,8 @@ LP_VP8_INL int last_nonzero(const int16_t* levels, int first) {
     return last;
 #endif
 }
+// 1 when a block has a non-zero level at or after `first` (what put_coeffs returns for it)
+LP_VP8_INL int block_nz(const int16_t* levels, int first) { return (nonzero_mask(levels) >> first) != 0; }
 // levels in raster order; returns 1 when the block has a non-zero level at or after `first`.
 LP_VP8_FN int put_coeffs(BoolEnc& e, const uint8_t* proba, int type, int ctx, int first, const int16_t* levels) {
     const uint8_t bands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
@@ -428,6 +430,21 @@ LP_VP8_INL int pred4_px(int mode, int p, const uint8_t* e, int dc) {
 // without its data-dependent branches.
 LP_VP8_TABLE uint32_t kVp8BModePathNodes[10] = {0x0000000, 0x0000010, 0x0000210, 0x0043210, 0x0543210, 0x0543210, 0x0063210, 0x0763210, 0x8763210, 0x8763210};
 LP_VP8_TABLE uint16_t kVp8BModePathBits[10] = {0x100, 0x201, 0x303, 0x507, 0x617, 0x637, 0x50f, 0x61f, 0x73f, 0x77f};
+// The cost (1/256 bit) of every sub-block mode in every context [above][left][mode]: i4_mode_cost over
+// kVp8BModesProba, tabulated (the two inputs are constants of the format; the tests compare the table with the walk).
+LP_VP8_TABLE uint16_t kVp8BModeCost[10][10][10] = {
+    {{38, 1154, 1728, 1874, 2103, 2019, 1628, 1777, 2225, 2135}, {193, 468, 1297, 1306, 1848, 1793, 1780, 1700, 1707, 1515}, {140, 914, 763, 1690, 1854, 1579, 1461, 1302, 1800, 1657}, {561, 641, 1388, 414, 1181, 1570, 1620, 1746, 859, 1002}, {299, 1065, 1263, 1105, 627, 1062, 1590, 1897, 860, 1135}, {277, 1113, 707, 1363, 1083, 663, 1603, 1536, 1539, 1283}, {212, 783, 1629, 1301, 1632, 2232, 720, 1563, 1716, 912}, {151, 1041, 1050, 1768, 1991, 2183, 1360, 736, 1741, 1389}, {518, 1048, 1418, 749, 747, 1296, 1501, 1626, 451, 1209}, {425, 829, 1369, 713, 1462, 1199, 1205, 1471, 1196, 530}},
+    {{239, 401, 1135, 1491, 1660, 1505, 1517, 1553, 1979, 2099}, {468, 240, 961, 1230, 1713, 1616, 1832, 1568, 1675, 1385}, {501, 452, 460, 1505, 1699, 1279, 1565, 976, 2123, 2126}, {676, 648, 1389, 324, 1595, 1674, 1457, 1933, 988, 868}, {458, 787, 1043, 909, 732, 962, 1165, 1524, 851, 1025}, {506, 815, 500, 1138, 1215, 712, 1514, 1079, 1262, 1265}, {333, 629, 1463, 1244, 1889, 3936, 794, 1553, 1907, 590}, {399, 646, 746, 1343, 1860, 1348, 1513, 607, 1863, 1009}, {626, 753, 1216, 603, 1064, 1408, 1299, 1410, 537, 965}, {501, 754, 1044, 662, 1225, 1614, 1305, 1431, 1385, 514}},
+    {{394, 552, 521, 1500, 1534, 975, 1606, 1136, 1661, 2182}, {659, 428, 372, 1412, 1861, 1217, 1679, 1132, 1979, 1551}, {695, 645, 241, 1962, 2082, 1191, 1533, 980, 1983, 2246}, {561, 839, 743, 863, 1124, 974, 1230, 846, 1085, 775}, {695, 880, 514, 955, 666, 890, 1056, 1187, 1525, 1121}, {746, 960, 381, 1285, 1177, 485, 1585, 1156, 1849, 1512}, {322, 777, 1059, 1783, 3319, 1274, 808, 1185, 1376, 645}, {490, 975, 482, 1774, 1519, 1782, 1115, 497, 1540, 1461}, {746, 1015, 1008, 702, 842, 1223, 1331, 781, 732, 711}, {524, 1084, 571, 1041, 1340, 880, 1045, 1142, 1198, 686}},
+    {{104, 867, 1447, 1008, 1939, 1842, 1520, 1924, 1674, 1577}, {536, 303, 1203, 677, 1386, 2174, 1812, 1901, 1258, 1161}, {305, 517, 877, 1106, 1424, 3471, 1423, 1059, 1314, 1235}, {686, 732, 2180, 250, 1507, 2066, 1875, 1552, 1048, 940}, {394, 817, 1032, 657, 955, 1555, 1284, 1288, 887, 1042}, {530, 620, 1000, 936, 1197, 628, 1093, 2767, 797, 1356}, {347, 615, 1605, 1185, 3388, 1343, 1004, 1337, 1007, 655}, {218, 741, 877, 1599, 3902, 3905, 1345, 750, 1350, 1613}, {676, 752, 1584, 550, 1253, 1597, 1865, 2384, 393, 1085}, {596, 687, 1168, 424, 1089, 1501, 1482, 1487, 1088, 813}},
+    {{228, 1069, 1062, 1376, 748, 978, 1513, 1519, 981, 1785}, {495, 513, 818, 940, 961, 888, 1615, 1353, 1042, 1359}, {518, 648, 591, 1039, 756, 986, 1194, 1452, 1303, 1458}, {686, 750, 1052, 668, 833, 1392, 1133, 1136, 644, 934}, {626, 1125, 1125, 996, 355, 1072, 1205, 1316, 871, 1215}, {634, 1077, 859, 1665, 644, 470, 1671, 1415, 822, 1166}, {555, 729, 1076, 1335, 3386, 1341, 818, 1334, 1073, 418}, {506, 878, 624, 1400, 883, 886, 1400, 802, 887, 1408}, {686, 1706, 1306, 977, 571, 983, 1288, 1722, 397, 1114}, {399, 870, 1451, 1068, 1069, 759, 965, 1485, 1220, 671}},
+    {{333, 763, 936, 1652, 1006, 520, 1653, 1408, 1469, 2227}, {512, 494, 749, 1158, 1212, 602, 1883, 1874, 1625, 1165}, {575, 644, 489, 1975, 1206, 596, 1578, 1094, 1392, 1992}, {792, 794, 947, 578, 1013, 947, 1615, 1201, 723, 761}, {695, 1024, 675, 1079, 574, 495, 1694, 1440, 1104, 3151}, {780, 1285, 570, 1999, 1259, 235, 3146, 1387, 1795, 1458}, {453, 898, 1311, 902, 1315, 3362, 458, 1309, 1316, 804}, {394, 938, 942, 1098, 1355, 1099, 945, 586, 1359, 1103}, {561, 1017, 1016, 1013, 652, 1173, 1016, 1161, 612, 1024}, {568, 796, 631, 1003, 1006, 856, 2567, 1268, 931, 757}},
+    {{265, 605, 1099, 1226, 1495, 1239, 946, 1025, 1735, 1460}, {366, 586, 905, 1056, 1406, 1244, 872, 1131, 1618, 1049}, {453, 564, 539, 1735, 1479, 1482, 1015, 882, 3193, 1148}, {555, 1097, 1576, 945, 1350, 890, 835, 1016, 1017, 486}, {705, 818, 1215, 967, 970, 633, 1219, 2463, 825, 569}, {676, 1264, 577, 868, 870, 768, 871, 1273, 1023, 944}, {296, 1147, 2048, 1798, 1649, 3696, 436, 1556, 2088, 712}, {343, 992, 1258, 1864, 1864, 1867, 618, 562, 1850, 1046}, {555, 1075, 1321, 819, 737, 1337, 1075, 1325, 1074, 485}, {289, 1170, 1308, 1175, 1642, 1645, 832, 2506, 1306, 502}},
+    {{340, 720, 766, 1874, 1764, 1269, 1253, 541, 1758, 2170}, {484, 654, 693, 1509, 1455, 1406, 1219, 499, 1917, 1262}, {490, 758, 445, 3242, 1823, 1274, 1664, 536, 1867, 2130}, {524, 1106, 1092, 847, 1362, 1106, 849, 896, 955, 596}, {714, 718, 843, 723, 728, 939, 938, 856, 3096, 1051}, {518, 1342, 499, 1339, 1078, 674, 1339, 711, 1604, 1348}, {453, 1178, 1390, 1917, 1514, 3561, 306, 941, 1916, 917}, {403, 1539, 980, 2173, 1770, 3817, 1075, 268, 3633, 1588}, {561, 1373, 1108, 609, 665, 2712, 972, 787, 977, 980}, {548, 1145, 1063, 809, 1408, 948, 1143, 616, 1264, 642}},
+    {{164, 985, 1244, 932, 1329, 1361, 1658, 1574, 954, 1609}, {596, 420, 927, 842, 1134, 1108, 1396, 2051, 853, 1033}, {403, 839, 729, 763, 932, 1663, 1247, 802, 1402, 1405}, {906, 880, 1078, 374, 1586, 1741, 1444, 2441, 471, 1030}, {642, 1097, 1022, 1025, 674, 1378, 1624, 2355, 407, 858}, {561, 1017, 821, 910, 703, 764, 1426, 912, 830, 1430}, {416, 1277, 1267, 868, 1281, 3328, 766, 1018, 1286, 513}, {407, 996, 599, 1006, 1265, 1268, 1262, 752, 1009, 1272}, {980, 1190, 1375, 788, 1034, 1297, 1700, 1707, 193, 1414}, {735, 887, 1297, 465, 896, 1159, 1560, 1294, 746, 749}},
+    {{110, 936, 1381, 1183, 1936, 1646, 1147, 1713, 1869, 1300}, {407, 413, 1030, 1018, 1910, 1398, 1313, 1645, 1503, 786}, {343, 641, 574, 1089, 1241, 1349, 1161, 1351, 1761, 1505}, {561, 769, 1207, 351, 1689, 1433, 1331, 1912, 1215, 795}, {474, 914, 1172, 766, 712, 2759, 1433, 1438, 714, 775}, {343, 893, 785, 1146, 1148, 789, 1298, 1554, 968, 1052}, {207, 1039, 1334, 1344, 1608, 3655, 809, 1460, 1614, 704}, {228, 931, 892, 1046, 3760, 1715, 993, 825, 1718, 1314}, {768, 727, 1059, 633, 989, 1073, 1319, 1333, 609, 820}, {305, 1176, 1375, 895, 1586, 1589, 984, 1980, 1325, 489}},
+};
+LP_VP8_INL int i4_mode_cost_ctx(int top, int left, int mode) { return kVp8BModeCost[top][left][mode]; }
 LP_VP8_INL int i4_mode_cost(int mode, const uint8_t* prob) {
     const uint32_t nodes = kVp8BModePathNodes[mode], bits = kVp8BModePathBits[mode];
     const int len = (int)(bits >> 8);
@@ -578,12 +595,11 @@ LP_VP8_FN uint32_t analyse_i4(const uint8_t* sy, int ys, uint8_t* yd, const int*
         const int bx = n & 3, by = n >> 2;
         uint8_t* d = yd + by * 4 * BPS + bx * 4;
         const uint8_t* src = sy + by * 4 * ys + bx * 4;
-        const uint8_t* prob = kVp8BModesProba[top_modes[bx]][left_modes[by]];
         int best_mode = 0;
         uint32_t best = 0xffffffffu;
         for (int m = 0; m < 10; m++) {
             vp8::pred_4x4(d, BPS, m);
-            const uint32_t score = sse_block(src, ys, d, BPS, 4) * 256u + (uint32_t)(i4_mode_cost(m, prob) * lambda4);
+            const uint32_t score = sse_block(src, ys, d, BPS, 4) * 256u + (uint32_t)(i4_mode_cost_ctx(top_modes[bx], left_modes[by], m) * lambda4);
             if (score < best) {
                 best = score;
                 best_mode = m;
@@ -595,7 +611,7 @@ LP_VP8_FN uint32_t analyse_i4(const uint8_t* sy, int ys, uint8_t* yd, const int*
         vp8::inverse_dct_add(coeffs, d, BPS);
         dist += sse_block(src, ys, d, BPS, 4);
         int nz;
-        bits += (uint32_t)i4_mode_cost(best_mode, prob) + (uint32_t)cost_coeffs(3, tnz[bx] + lnz[by], 0, levels + n * 16, &nz);
+        bits += (uint32_t)i4_mode_cost_ctx(top_modes[bx], left_modes[by], best_mode) + (uint32_t)cost_coeffs(3, tnz[bx] + lnz[by], 0, levels + n * 16, &nz);
         tnz[bx] = lnz[by] = (uint8_t)nz;
         modes[n] = (uint8_t)best_mode;
         top_modes[bx] = left_modes[by] = (uint8_t)best_mode;
@@ -682,7 +698,11 @@ LP_VP8_FN void analyse_and_reconstruct(const Params& P, const Buffers& B) {
                 left_modes[i] = mb_x > 0 ? (md - kModeStride)[2 + 4 * i + 3] : (uint8_t)vp8::B_DC;
             }
             bool use_i4 = false;
-            if (P.try_i4) {
+            // (a macroblock whose 16x16 residual quantises to DC terms only is flat: sixteen 4x4 predictions would spend
+            // mode bits on nothing, so the trial is skipped -- a third of the macroblocks of a photograph)
+            bool flat16 = true;
+            for (int n = 0; n < 16; n++) flat16 = flat16 && !block_nz(lv + n * 16, 1);
+            if (P.try_i4 && !flat16) {
                 // the 16x16 candidate's reconstruction, distortion and rate
                 uint8_t y16[16 * 16];
                 {
@@ -743,7 +763,7 @@ LP_VP8_FN void analyse_and_reconstruct(const Params& P, const Buffers& B) {
             if (!use_i4) {
                 md[0] = (uint8_t)ymode;
                 for (int k = 0; k < 16; k++) md[2 + k] = (uint8_t)ymode;  // what the neighbours' sub-block modes are coded against
-                if (!P.try_i4)
+                if (!P.try_i4 || flat16)
                     for (int n = 0; n < 16; n++) vp8::inverse_dct_add(coeffs + n * 16, yd + (n >> 2) * 4 * BPS + (n & 3) * 4, BPS);
             }
             for (int n = 0; n < 4; n++) {
@@ -863,8 +883,6 @@ LP_VP8_FN size_t write_part0(const Params& P, const Buffers& B, const uint8_t* a
     return h.overflow ? 0 : h.pos;
 }
 
-// 1 when a block has a non-zero level at or after `first` (what put_coeffs returns for it)
-LP_VP8_INL int block_nz(const int16_t* levels, int first) { return (nonzero_mask(levels) >> first) != 0; }
 
 // The macroblocks of token partition `part` (rows part, part + nparts, ...) in the decoder's order and contexts.
 // CODE = false: count the adaptive branches into aux (the statistics the probabilities are decided from) and the

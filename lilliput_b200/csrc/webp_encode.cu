@@ -394,7 +394,10 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
             uint8_t* md = B.modes + ((size_t)mb_y * P.mb_w + mb_x) * kModeStride;
             bool use_i4 = false;
             unsigned long long modes4 = 0;
-            if (P.try_i4) {
+            // (flat macroblocks -- no AC level survives the 16x16 candidate's quantisation -- skip the trial, as the
+            // serial walk does)
+            const uint32_t nzm = __ballot_sync(0xffffffffu, lane < 16 && block_nz(lv + lane * 16, 1) != 0);
+            if (P.try_i4 && nzm != 0) {
                 uint32_t tm = 0, lm = 0;  // the neighbours' sub-block modes, one nibble each
                 for (int i = 0; i < 4; i++) {
                     tm |= (uint32_t)(have_top ? (md - (size_t)P.mb_w * kModeStride)[2 + 12 + i] : (uint8_t)vp8::B_DC) << (4 * i);
@@ -410,8 +413,6 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                         e += d * d;
                     }
                     d16 = (uint32_t)warp_sum_i(e);
-                    const int mynz = lane < 16 ? block_nz(lv + lane * 16, 1) : 0;
-                    const uint32_t nzm = __ballot_sync(0xffffffffu, mynz != 0);
                     int c = 0, nz;
                     if (lane < 16) {
                         const int ctx = ((lane & 3) ? (int)((nzm >> (lane - 1)) & 1u) : 0) + ((lane >> 2) ? (int)((nzm >> (lane - 4)) & 1u) : 0);
@@ -438,7 +439,7 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                     const int bx = n & 3, by = n >> 2;
                     uint8_t* d = yd4 + by * 4 * BPS + bx * 4;
                     const uint8_t* src = sy + by * 4 * ys + bx * 4;
-                    const uint8_t* prob = kVp8BModesProba[(tm >> (4 * bx)) & 15u][(lm >> (4 * by)) & 15u];
+                    const int ctx_top = (int)((tm >> (4 * bx)) & 15u), ctx_left = (int)((lm >> (4 * by)) & 15u);
                     // the block's 13 edge samples {L, K, J, I, X, A..H} where every lane can index them
                     if (lane < 13)
                         wb.edge[lane] = lane < 4 ? d[(3 - lane) * BPS - 1] : lane == 4 ? d[-BPS - 1] : d[-BPS + (lane - 5)];
@@ -461,7 +462,7 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                     // lane -> the mode it speaks for: m = 5 * half + (L % 5); score = distortion + lambda * mode bits
                     const int t5 = L % 5, m = half * 5 + t5;
                     const uint32_t my_sse = t5 == 0 ? sse5[0] : t5 == 1 ? sse5[1] : t5 == 2 ? sse5[2] : t5 == 3 ? sse5[3] : sse5[4];
-                    const uint32_t score = my_sse * 256u + (uint32_t)(i4_mode_cost(m, prob) * lambda4);
+                    const uint32_t score = my_sse * 256u + (uint32_t)(i4_mode_cost_ctx(ctx_top, ctx_left, m) * lambda4);
                     uint32_t mn = score;
 #pragma unroll
                     for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -500,7 +501,7 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                         const uint8_t* tp = &kVp8CoeffProba0[0][0][0][0] + 3 * (8 * 3 * 11);
                         const int ctx0 = (int)((tnzb >> bx) & 1u) + (int)((lnzb >> by) & 1u);
                         const int cp = act ? cost_pos(tp, ctx0, 0, last, v, vprev, lane) : 0;
-                        blk_bits = (uint32_t)warp_sum_i(cp) + (uint32_t)i4_mode_cost(w, prob);
+                        blk_bits = (uint32_t)warp_sum_i(cp) + (uint32_t)i4_mode_cost_ctx(ctx_top, ctx_left, w);
                         blk_nz = last >= 0;
                     }
                     d4 += my_d_all;

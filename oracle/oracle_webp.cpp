@@ -187,6 +187,9 @@ extern "C" long vp8_cpu_check_pred4_tables(long iters, unsigned seed) {
                 if (vp8enc::pred4_px(m, p, e, dc) != d[(p >> 2) * 32 + (p & 3)]) bad++;
             if (vp8enc::i4_mode_cost(m, prob) != vp8enc::i4_mode<false>(nullptr, m, prob)) bad++;
         }
+        if (it < 100)  // the tabulated context costs against the walk over the format's probabilities
+            for (int m = 0; m < 10; m++)
+                if (vp8enc::i4_mode_cost_ctx((int)(it / 10), (int)(it % 10), m) != vp8enc::i4_mode<false>(nullptr, m, kVp8BModesProba[it / 10][it % 10])) bad++;
     }
     return bad;
 }

@@ -416,13 +416,13 @@ LP_VP8_TABLE uint16_t kVp8Pred4[10][16] = {
 
 // pixel p (= 4 * y + x) of mode `mode`; dc = (A + B + C + D + I + J + K + L + 4) >> 3
 LP_VP8_INL int pred4_px(int mode, int p, const uint8_t* e, int dc) {
+    // straight-line on purpose: the lanes of a warp ask for different kinds at once
     const uint32_t t = kVp8Pred4[mode][p];
     const int a = e[t & 15], b = e[(t >> 4) & 15], c = e[(t >> 8) & 15], kind = (int)(t >> 12);
-    if (kind == 0) return (a + 2 * b + c + 2) >> 2;
-    if (kind == 1) return (a + b + 1) >> 1;
-    if (kind == 2) return a;
-    if (mode == vp8::B_DC) return dc;
-    return vp8::clip8(e[5 + (p & 3)] + e[3 - (p >> 2)] - e[4]);  // B_TM: above + left - corner
+    const int tm = vp8::clip8(e[5 + (p & 3)] + e[3 - (p >> 2)] - e[4]);  // B_TM: above + left - corner
+    const int avg = kind == 0 ? (a + 2 * b + c + 2) >> 2 : (a + b + 1) >> 1;
+    const int special = mode == vp8::B_DC ? dc : tm;
+    return kind < 2 ? avg : kind == 2 ? a : special;
 }
 
 // The path of every sub-block mode through the tree of s.8.3: nodes (= index of the probability) as nibbles, the

@@ -413,12 +413,25 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                         e += d * d;
                     }
                     d16 = (uint32_t)warp_sum_i(e);
-                    int c = 0, nz;
-                    if (lane < 16) {
-                        const int ctx = ((lane & 3) ? (int)((nzm >> (lane - 1)) & 1u) : 0) + ((lane >> 2) ? (int)((nzm >> (lane - 4)) & 1u) : 0);
-                        c = cost_coeffs(0, ctx, 1, lv + lane * 16, &nz);
-                    } else if (lane == 16) {
-                        c = cost_coeffs(1, 0, 0, lv + 24 * 16, &nz);
+                    // rate of the 16x16 candidate: Y2 + sixteen luma blocks, two blocks per step, a scan position per lane
+                    // (vp8enc::cost_pos summed over positions = vp8enc::cost_coeffs)
+                    int c = 0;
+                    const int pos = lane & 15;
+                    const int zz = (int)((0xFEB7ADC963258410ull >> (4 * pos)) & 15ull);  // zig-zag: scan -> raster
+                    for (int it = 0; it < 9; it++) {
+                        const int blk = it < 8 ? 2 * it + (lane >> 4) : 24;       // the last step: Y2 on the lower half
+                        const bool on = it < 8 || lane < 16;
+                        const int first = it < 8 ? 1 : 0, type = it < 8 ? 0 : 1;
+                        const int lvv = on ? (int)lv[blk * 16 + zz] : 0;
+                        const int v = lvv < 0 ? -lvv : lvv;
+                        int vprev = __shfl_up_sync(0xffffffffu, v, 1);
+                        if (pos == 0) vprev = 0;
+                        const uint32_t nzb = __ballot_sync(0xffffffffu, on && v != 0 && pos >= first);
+                        const uint32_t mine = (nzb >> (lane & 16)) & 0xffffu;
+                        const int last = mine ? 31 - __clz((int)mine) : -1;
+                        const int ctx = it < 8 ? (((blk & 3) ? (int)((nzm >> (blk - 1)) & 1u) : 0) + ((blk >> 2) ? (int)((nzm >> (blk - 4)) & 1u) : 0)) : 0;
+                        const uint8_t* tp = &kVp8CoeffProba0[0][0][0][0] + type * (8 * 3 * 11);
+                        if (on && pos >= first) c += cost_pos(tp, ctx, first, last, v, vprev, pos);
                     }
                     r16 = (uint32_t)warp_sum_i(c) + (uint32_t)bit_cost(1, 145) + 512u;
                 }

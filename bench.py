@@ -487,7 +487,7 @@ def main_x(args):
     units = n  # images (configs 3, 5) or animations (config 4)
 
     if args.impl == "reference":
-        per_step = max(threads * 2, 32) if args.config != 4 else max(threads, 8)
+        per_step = max(threads * 6, 96) if args.config != 4 else max(threads * 2, 16)
         for _ in range(min(args.warmup, 1)):
             x_reference_run(cfg, base, offs_d, lens_d, threads, threads)
         t = 0.0
@@ -587,15 +587,13 @@ def main_x(args):
                                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
                                 "bytes_per_unit": cfg["resize_bytes"]}
         if world == 1 and not args.no_cpu_baseline and os.path.exists(abi.REF_LIB):
-            # bounded sample of at least --cpu-seconds of CPU work: calls of ~3 s each (the pool and its framebuffers are
-            # warmed before each clock starts) until the clocks add up
-            probe_n = max(threads, 8)
-            probe = x_reference_run(cfg, base, offs_d, lens_d, probe_n, threads)
-            per_call = int(max(probe_n, probe_n / probe * 3.0))
-            total_n, el = 0, 0.0
-            while el < args.cpu_seconds:
-                el += x_reference_run(cfg, base, offs_d, lens_d, per_call, threads)
-                total_n += per_call
+            # bounded sample: one call of at least --cpu-seconds of CPU work (the pool and its framebuffers are warmed
+            # before the clock starts)
+            total_n = max(4 * threads, 32)
+            el = x_reference_run(cfg, base, offs_d, lens_d, total_n, threads)
+            while el < args.cpu_seconds:   # grow the call until ONE call lasts --cpu-seconds (short calls under-report:
+                total_n = int(total_n * min(8.0, max(1.5, 1.25 * args.cpu_seconds / max(el, 1e-3))))  # few images per thread)
+                el = x_reference_run(cfg, base, offs_d, lens_d, total_n, threads)
             line["cpu_baseline"] = {"value": round(total_n / el, 3), "unit": cfg["unit"], "cores": cores, "kind": "reference",
                                     "sample": f"{total_n} Transforms over the {len(files)} distinct inputs in {el:.1f} s, {threads} "
                                               f"threads on {cores} usable CPUs, workers warmed before the clock, "
@@ -817,12 +815,11 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline and os.path.exists(abi.REF_LIB):
             sample_n = n
-            probe = cpu_reference_run(base, offs[:sample_n], lens[:sample_n], threads * 2, threads)
-            per_call = int(max(threads * 2, threads * 2 / probe * 3.0))
-            total, el = 0, 0.0
-            while el < args.cpu_seconds:   # at least --cpu-seconds of CPU work, ~3 s per call, workers warmed before each clock
-                el += cpu_reference_run(base, offs[:sample_n], lens[:sample_n], per_call, threads)
-                total += per_call
+            total = max(32 * threads, 1024)
+            el = cpu_reference_run(base, offs[:sample_n], lens[:sample_n], total, threads)
+            while el < args.cpu_seconds:   # one call of at least --cpu-seconds of CPU work, workers warmed before the clock
+                total = int(total * min(8.0, max(1.5, 1.25 * args.cpu_seconds / max(el, 1e-3))))
+                el = cpu_reference_run(base, offs[:sample_n], lens[:sample_n], total, threads)
             line["cpu_baseline"] = {"value": round(total / el, 2), "unit": "images/s", "cores": cores,
                                     "kind": "reference",
                                     "sample": f"{total} Transforms over the first {sample_n} inputs of the same "

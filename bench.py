@@ -609,9 +609,11 @@ def main_x(args):
 
 def resize_traffic(images_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum of the resize kernel per launch, from the committed
-    `ncu --set full` capture (profiles/r01_resize_traffic.json: measured per image on a 1184-image launch,
+    `ncu --set full` capture (profiles/r02_resize_traffic.json: measured per image on a 1332-image launch,
     1.014x the algorithmic bytes), scaled to this run's images per launch.  None if the file is missing."""
-    path = os.path.join(ROOT, "profiles", "r01_resize_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_resize_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01_resize_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:

@@ -224,11 +224,11 @@ LP_VP8_INL int last_nonzero(const int16_t* levels, int first) {
 // 1 when a block has a non-zero level at or after `first` (what put_coeffs returns for it)
 LP_VP8_INL int block_nz(const int16_t* levels, int first) { return (nonzero_mask(levels) >> first) != 0; }
 // levels in raster order; returns 1 when the block has a non-zero level at or after `first`.
-LP_VP8_FN int put_coeffs(BoolEnc& e, const uint8_t* proba, int type, int ctx, int first, const int16_t* levels) {
+LP_VP8_FN int put_coeffs(BoolEnc& e, const uint8_t* proba, int type, int ctx, int first, const int16_t* levels, int has_nz = 1) {
     const uint8_t bands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
     const uint8_t zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
     const uint8_t* tp = proba + type * (8 * 3 * 11);
-    const int last = last_nonzero(levels, first);
+    const int last = has_nz ? last_nonzero(levels, first) : -1;  // (has_nz == 0: the caller knows the block is empty)
     int n = first;
     const uint8_t* p = tp + (bands[n] * 3 + ctx) * 11;
     if (last < 0) {
@@ -309,11 +309,11 @@ LP_VP8_INL void stat_add(uint32_t* stats, int idx, int bit) {
 
 // put_coeffs with the coder replaced by counters: which adaptive branches the block takes.  (The fixed-probability
 // branches -- extra bits, signs -- cannot be adapted and are not counted.)
-LP_VP8_FN int record_coeffs(uint32_t* stats, int type, int ctx, int first, const int16_t* levels) {
+LP_VP8_FN int record_coeffs(uint32_t* stats, int type, int ctx, int first, const int16_t* levels, int has_nz = 1) {
     const uint8_t bands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
     const uint8_t zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
     const int tb = type * (8 * 3 * 11);
-    const int last = last_nonzero(levels, first);
+    const int last = has_nz ? last_nonzero(levels, first) : -1;
     int n = first;
     int p = tb + (bands[n] * 3 + ctx) * 11;
     if (last < 0) {
@@ -386,12 +386,18 @@ LP_VP8_FN void decide_proba(uint32_t c0, uint32_t c1, int old_p, int update_p, u
 }
 
 // ---- 4x4 intra modes (RFC 6386 s.8.3 / 12.3) ------------------------------------------------------------------------
-// Per macroblock 2 + 16 bytes of mode information: [0] = the 16x16 luma mode (0..3) or kI4 when the macroblock predicts
+// Per macroblock kModeStride bytes of mode information: [0] = the 16x16 luma mode (0..3) or kI4 when the macroblock predicts
 // its sixteen 4x4 blocks one by one, [1] = the chroma mode, [2..17] = the sub-block modes in raster order.  A 16x16
 // macroblock fills them with its own mode, which is what its neighbours' sub-block modes are coded against (s.8.3).
-constexpr int kModeStride = 18;
+constexpr int kModeStride = 24;  // + [20..23]: which of the 25 blocks have a non-zero level (bit k = block k), see mb_nz_mask
 constexpr int kI4 = 4;
 constexpr int kTryI4 = 1;  // what the product encodes with (Params::try_i4 of the device launchers and of the host build)
+
+// The macroblock's non-zero-block mask (written once by the analysis, read by the first partition and by both token
+// walks instead of scanning the 25 blocks' levels again: a block's flag is what the neighbours' contexts, the skip test
+// and the "no coefficients" shortcut of the token writer ask for).
+LP_VP8_INL uint32_t mb_nz_mask(const uint8_t* md) { return *reinterpret_cast<const uint32_t*>(md + 20); }
+LP_VP8_INL void mb_set_nz_mask(uint8_t* md, uint32_t m) { *reinterpret_cast<uint32_t*>(md + 20) = m; }
 
 // cost, in 1/256 bit, of a bit coded with probability `p` of being 0
 LP_VP8_INL int bit_cost(int bit, int p) { return kVp8EntropyCost[bit ? 255 - p : p]; }
@@ -785,6 +791,11 @@ LP_VP8_FN void analyse_and_reconstruct(const Params& P, const Buffers& B) {
                     pv[j * cs + i] = vd[j * BPS + i];
                 }
             md[1] = (uint8_t)uvmode;
+            {
+                uint32_t mask = 0;
+                for (int k = 0; k < 25; k++) mask |= (uint32_t)block_nz(lv + k * 16, 0) << k;
+                mb_set_nz_mask(md, mask);
+            }
         }
 }
 
@@ -848,7 +859,7 @@ LP_VP8_FN size_t write_part0(const Params& P, const Buffers& B, const uint8_t* a
         const uint8_t* md = B.modes + (size_t)i * kModeStride;
         const int ymode = md[0], uvmode = md[1];
         const int mb_x = i % P.mb_w, mb_y = i / P.mb_w;
-        if (use_skip) be_put(h, mb_is_skippable(B.levels + (size_t)i * 25 * 16), skip_p);
+        if (use_skip) be_put(h, mb_nz_mask(md) == 0, skip_p);
         if (ymode == kI4) {
             be_put(h, 0, 145);  // sixteen 4x4 modes, each coded against the modes above and to the left (s.8.3)
             for (int n = 0; n < 16; n++) {
@@ -901,33 +912,33 @@ LP_VP8_FN size_t walk_partition(const Params& P, const Buffers& B, int part, int
         uint8_t left_nz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int mb_x = 0; mb_x < P.mb_w; mb_x++) {
             const int16_t* lv = B.levels + ((size_t)mb_y * P.mb_w + mb_x) * 25 * 16;
-            const int skippable = mb_is_skippable(lv);
+            const uint8_t* md = B.modes + ((size_t)mb_y * P.mb_w + mb_x) * kModeStride;
+            const uint32_t nzmask = mb_nz_mask(md);
+            const bool i4 = md[0] == kI4;
+            const int skippable = nzmask == 0;
             n_mb++;
             n_skip += (uint32_t)skippable;
             if (skippable && (use_skip || !CODE)) {
                 // statistics pass: assume the frame WILL use skip flags when it has skippable macroblocks (decided
                 // in finish_statistics from the same counts), so their would-be tokens are not counted
                 for (int k = 0; k < 8; k++) left_nz[k] = 0;
-                if (B.modes[((size_t)mb_y * P.mb_w + mb_x) * kModeStride] != kI4) left_nz[8] = 0;
+                if (!i4) left_nz[8] = 0;
                 continue;
             }
-            const uint8_t* md = B.modes + ((size_t)mb_y * P.mb_w + mb_x) * kModeStride;
-            const bool i4 = md[0] == kI4;
             uint8_t tnz[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            if (mb_y > 0) {  // bottom blocks of the macroblock above
-                const int16_t* up = lv - (size_t)P.mb_w * 25 * 16;
-                const bool up_i4 = (md - (size_t)P.mb_w * kModeStride)[0] == kI4;
-                for (int i = 0; i < 4; i++) tnz[i] = (uint8_t)block_nz(up + (12 + i) * 16, up_i4 ? 0 : 1);
-                tnz[4] = (uint8_t)block_nz(up + 18 * 16, 0);
-                tnz[5] = (uint8_t)block_nz(up + 19 * 16, 0);
-                tnz[6] = (uint8_t)block_nz(up + 22 * 16, 0);
-                tnz[7] = (uint8_t)block_nz(up + 23 * 16, 0);
+            if (mb_y > 0) {  // bottom blocks of the macroblock above, from its mask
+                const uint32_t up = mb_nz_mask(md - (size_t)P.mb_w * kModeStride);
+                for (int i = 0; i < 4; i++) tnz[i] = (uint8_t)((up >> (12 + i)) & 1u);
+                tnz[4] = (uint8_t)((up >> 18) & 1u);
+                tnz[5] = (uint8_t)((up >> 19) & 1u);
+                tnz[6] = (uint8_t)((up >> 22) & 1u);
+                tnz[7] = (uint8_t)((up >> 23) & 1u);
                 if (!i4) {
                     // the Y2 context above is that of the nearest macroblock above that HAS a Y2 block: 4x4 macroblocks
                     // neither read nor write it (s.13.3; the decoder carries it across them)
                     int r = mb_y - 1;
                     while (r >= 0 && B.modes[((size_t)r * P.mb_w + mb_x) * kModeStride] == kI4) r--;
-                    tnz[8] = r >= 0 ? (uint8_t)block_nz(B.levels + (((size_t)r * P.mb_w + mb_x) * 25 + 24) * 16, 0) : 0;
+                    tnz[8] = r >= 0 ? (uint8_t)((mb_nz_mask(B.modes + ((size_t)r * P.mb_w + mb_x) * kModeStride) >> 24) & 1u) : 0;
                 }
             }
             for (int k = i4 ? 0 : -1; k < 24; k++) {  // [Y2], 16 Y, 4 U, 4 V: the decoder's order and contexts
@@ -941,8 +952,9 @@ LP_VP8_FN size_t walk_partition(const Params& P, const Buffers& B, int part, int
                     const int c = k - 16;
                     type = 2; ti = 4 + (c >> 2) * 2 + (c & 1); li = 4 + (c >> 2) * 2 + ((c >> 1) & 1); blk = lv + k * 16;
                 }
-                const int nz = CODE ? put_coeffs(t, proba, type, tnz[ti] + left_nz[li], first, blk)
-                                    : record_coeffs(stats, type, tnz[ti] + left_nz[li], first, blk);
+                const int has = (int)((nzmask >> (k < 0 ? 24 : k)) & 1u);
+                const int nz = CODE ? put_coeffs(t, proba, type, tnz[ti] + left_nz[li], first, blk, has)
+                                    : record_coeffs(stats, type, tnz[ti] + left_nz[li], first, blk, has);
                 tnz[ti] = left_nz[li] = (uint8_t)nz;
             }
         }

@@ -448,7 +448,12 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                 const int q = qm.y1[1];
                 const int lambda4 = (3 * q * q) >> 7;
                 uint32_t d4 = 0, r4 = (uint32_t)bit_cost(0, 145), tnzb = 0, lnzb = 0;
+                const unsigned long long lam = (unsigned long long)((q * q) >> 7);
+                const unsigned long long s16 = (unsigned long long)d16 * 256 + (unsigned long long)r16 * lam;
                 for (int n = 0; n < 16; n++) {
+                    // distortion and rate only grow: once the blocks tried so far cost what the 16x16 candidate costs in
+                    // total, the trial is lost -- the serial walk, which always finishes it, decides the same
+                    if ((unsigned long long)d4 * 256 + (unsigned long long)r4 * lam >= s16) break;
                     const int bx = n & 3, by = n >> 2;
                     uint8_t* d = yd4 + by * 4 * BPS + bx * 4;
                     const uint8_t* src = sy + by * 4 * ys + bx * 4;
@@ -527,8 +532,6 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                     modes4 |= (unsigned long long)w << (4 * n);
                     __syncwarp();
                 }
-                const unsigned long long lam = (unsigned long long)((q * q) >> 7);
-                const unsigned long long s16 = (unsigned long long)d16 * 256 + (unsigned long long)r16 * lam;
                 const unsigned long long s4 = (unsigned long long)d4 * 256 + (unsigned long long)r4 * lam;
                 use_i4 = s4 < s16;
                 if (use_i4) {
@@ -542,6 +545,11 @@ __device__ void vp8_analyse_warp(const vp8enc::Params& P, const vp8enc::Buffers&
                 __syncwarp();
             }
             if (lane < 16) md[2 + lane] = use_i4 ? (uint8_t)((modes4 >> (4 * lane)) & 15u) : (uint8_t)ymode;
+            {
+                // which of the 25 blocks kept a non-zero level: one block per lane, once, for the three bitstream walks
+                const uint32_t mask = __ballot_sync(0xffffffffu, lane < 25 && block_nz(lv + lane * 16, 0) != 0);
+                if (lane == 0) mb_set_nz_mask(md, mask);
+            }
             // reconstruction out to the planes: 8 luma pixels and 4 chroma pixels per lane
             {
                 const int r = lane >> 1, c0 = (lane & 1) * 8;

